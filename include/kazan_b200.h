@@ -1,0 +1,349 @@
+/* kazan_b200.h — C ABI of the B200-native execution back end for the Kazan Vulkan driver.
+ *
+ * This is the drop-in boundary for the data-parallel hot path: the entry points a
+ * `vulkan-driver` host (Rust `extern "C"` block) binds in place of the
+ * `unimplemented!()` bodies of its `vkCmd*` / `vkQueue*` functions.  Every function cites the
+ * reference interface it replaces (paths relative to the kazan-3d/kazan tree).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no CUDA or torch types in any signature
+ *    (a CUstream / cudaStream_t crosses the boundary as `void*`);
+ *  - structs whose name matches a Vulkan struct (KznBufferImageCopy <-> VkBufferImageCopy, ...)
+ *    are layout-identical to Vulkan-Headers 1.1.130 (the version the reference vendors,
+ *    external/Vulkan-Headers/include/vulkan/vulkan_core.h:47); tests/test_abi.py checks sizeof /
+ *    offsetof against the real header when it is available, so a host may pass its Vk structs as-is;
+ *  - enum values are the Vulkan values (VkFormat, VkCompareOp, VkBlendFactor, VkFilter, ...);
+ *  - return value: KznResult, numerically a VkResult (0 = VK_SUCCESS, 1 = VK_NOT_READY,
+ *    2 = VK_TIMEOUT, negative = error) so the host can return it unchanged.  Invalid usage that the
+ *    reference would `assert!`/panic on (vulkan-driver/src/api_impl.rs, e.g. :4992-5003) is reported
+ *    as KZN_ERROR_VALIDATION_FAILED; the ICD layer turns that into abort() like the reference;
+ *  - all kzn_cmd_* calls are asynchronous: they enqueue sm_100a kernels on the queue's CUDA stream
+ *    and return; completion is observed with a fence or kzn_queue_wait_idle;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    KZN_ERROR_INITIALIZATION_FAILED.
+ */
+#ifndef KAZAN_B200_H
+#define KAZAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KZN_API __attribute__((visibility("default")))
+#else
+#define KZN_API
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* results                                                                                      */
+
+typedef int32_t KznResult;
+#define KZN_SUCCESS 0
+#define KZN_NOT_READY 1                            /* VK_NOT_READY */
+#define KZN_TIMEOUT 2                              /* VK_TIMEOUT */
+#define KZN_ERROR_OUT_OF_HOST_MEMORY (-1)          /* VK_ERROR_OUT_OF_HOST_MEMORY */
+#define KZN_ERROR_OUT_OF_DEVICE_MEMORY (-2)        /* VK_ERROR_OUT_OF_DEVICE_MEMORY, api_impl.rs:3459-3471 */
+#define KZN_ERROR_INITIALIZATION_FAILED (-3)       /* VK_ERROR_INITIALIZATION_FAILED: no CUDA device */
+#define KZN_ERROR_DEVICE_LOST (-4)                 /* VK_ERROR_DEVICE_LOST: any CUresult/cudaError_t failure */
+#define KZN_ERROR_FEATURE_NOT_PRESENT (-8)         /* VK_ERROR_FEATURE_NOT_PRESENT */
+#define KZN_ERROR_FORMAT_NOT_SUPPORTED (-11)       /* VK_ERROR_FORMAT_NOT_SUPPORTED */
+#define KZN_ERROR_VALIDATION_FAILED (-1000011001)  /* VK_ERROR_VALIDATION_FAILED_EXT */
+
+/* library version, bumped on ABI changes */
+#define KZN_ABI_VERSION 1u
+KZN_API uint32_t kzn_abi_version(void);
+/* human-readable text for the last error on the calling thread ("" if none) */
+KZN_API const char* kzn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* constants of the reference driver (vulkan-driver/src/lib.rs:27-35)                           */
+
+#define KZN_MIN_MEMORY_MAP_ALIGNMENT 128u /* lib.rs:27 */
+#define KZN_BUFFER_ALIGNMENT 64u          /* lib.rs:33 */
+#define KZN_IMAGE_ALIGNMENT 64u           /* lib.rs:34 */
+#define KZN_SUBPIXEL_PRECISION_BITS 4u    /* api_impl.rs:1559 */
+#define KZN_WHOLE_SIZE (~0ull)            /* VK_WHOLE_SIZE */
+#define KZN_REMAINING_MIP_LEVELS (~0u)    /* VK_REMAINING_MIP_LEVELS */
+#define KZN_REMAINING_ARRAY_LAYERS (~0u)  /* VK_REMAINING_ARRAY_LAYERS */
+
+/* VkFormat values handled on the hot path (image.rs:58-88 implements only the first) */
+#define KZN_FORMAT_UNDEFINED 0u
+#define KZN_FORMAT_R8G8B8A8_UNORM 37u
+#define KZN_FORMAT_D32_SFLOAT 126u
+
+/* image.rs:17-22 `enum Tiling`.  TILED is the oracle-defined 16x16-texel tile layout
+ * (SURVEY.md Appendix E.10): the reference declares the variant but defines no address function. */
+#define KZN_TILING_LINEAR 0u
+#define KZN_TILING_TILED 1u
+#define KZN_TILE_DIM 16u /* texels per tile edge; one tile = 16*16*4 B = 1 KiB */
+
+#define KZN_IMAGE_ASPECT_COLOR_BIT 1u
+#define KZN_IMAGE_ASPECT_DEPTH_BIT 2u
+
+#define KZN_FILTER_NEAREST 0u
+#define KZN_FILTER_LINEAR 1u
+
+#define KZN_INDEX_TYPE_UINT16 0u
+#define KZN_INDEX_TYPE_UINT32 1u
+
+/* ------------------------------------------------------------------------------------------ */
+/* Vulkan-layout structs (vulkan_core.h line numbers of the reference's vendored header)        */
+
+typedef struct KznOffset3D { int32_t x, y, z; } KznOffset3D;                 /* VkOffset3D */
+typedef struct KznExtent3D { uint32_t width, height, depth; } KznExtent3D;   /* VkExtent3D */
+typedef struct KznOffset2D { int32_t x, y; } KznOffset2D;                    /* VkOffset2D */
+typedef struct KznExtent2D { uint32_t width, height; } KznExtent2D;          /* VkExtent2D */
+typedef struct KznRect2D { KznOffset2D offset; KznExtent2D extent; } KznRect2D; /* VkRect2D */
+
+typedef struct KznViewport { /* VkViewport */
+    float x, y, width, height, minDepth, maxDepth;
+} KznViewport;
+
+typedef union KznClearColorValue { /* VkClearColorValue, vulkan_core.h:2915-2919 */
+    float float32[4];
+    int32_t int32[4];
+    uint32_t uint32[4];
+} KznClearColorValue;
+
+typedef struct KznClearDepthStencilValue { /* VkClearDepthStencilValue */
+    float depth;
+    uint32_t stencil;
+} KznClearDepthStencilValue;
+
+typedef struct KznImageSubresourceRange { /* VkImageSubresourceRange */
+    uint32_t aspectMask, baseMipLevel, levelCount, baseArrayLayer, layerCount;
+} KznImageSubresourceRange;
+
+typedef struct KznImageSubresourceLayers { /* VkImageSubresourceLayers */
+    uint32_t aspectMask, mipLevel, baseArrayLayer, layerCount;
+} KznImageSubresourceLayers;
+
+typedef struct KznBufferCopy { /* VkBufferCopy */
+    uint64_t srcOffset, dstOffset, size;
+} KznBufferCopy;
+
+typedef struct KznBufferImageCopy { /* VkBufferImageCopy, vulkan_core.h:2906-2913 (56 bytes) */
+    uint64_t bufferOffset;
+    uint32_t bufferRowLength;
+    uint32_t bufferImageHeight;
+    KznImageSubresourceLayers imageSubresource;
+    KznOffset3D imageOffset;
+    KznExtent3D imageExtent;
+} KznBufferImageCopy;
+
+typedef struct KznImageCopy { /* VkImageCopy */
+    KznImageSubresourceLayers srcSubresource;
+    KznOffset3D srcOffset;
+    KznImageSubresourceLayers dstSubresource;
+    KznOffset3D dstOffset;
+    KznExtent3D extent;
+} KznImageCopy;
+
+typedef struct KznImageBlit { /* VkImageBlit, vulkan_core.h:2899-2904 */
+    KznImageSubresourceLayers srcSubresource;
+    KznOffset3D srcOffsets[2];
+    KznImageSubresourceLayers dstSubresource;
+    KznOffset3D dstOffsets[2];
+} KznImageBlit;
+
+typedef struct KznClearRect { /* VkClearRect */
+    KznRect2D rect;
+    uint32_t baseArrayLayer, layerCount;
+} KznClearRect;
+
+/* ------------------------------------------------------------------------------------------ */
+/* objects                                                                                      */
+
+typedef struct KznDevice KznDevice; /* one CUDA device + primary context  (api_impl.rs `Device`) */
+typedef struct KznQueue KznQueue;   /* one CUDA stream (lib.rs:30-32: 1 family x 1 queue)        */
+typedef struct KznMemory KznMemory; /* device_memory.rs:191-273 `DeviceMemory`                   */
+typedef struct KznFence KznFence;   /* handle.rs:327 `Fence {}` placeholder -> CUDA event        */
+
+/* Image as the hot path sees it: vulkan-driver/src/image.rs:30-39 `ImageProperties` plus the bound
+ * memory (`ImageMemory`, image.rs:92-95) resolved to a device address.
+ * Texel (x,y,z,layer) of a LINEAR image lives at
+ *     address + texel_size * (x + width * (y + height * (z + depth * layer)))        (image.rs:58-88)
+ * A TILED image stores each (z,layer) slice as ceil(w/16) x ceil(h/16) row-major tiles of 16x16
+ * row-major texels; slice pitch = texel_size*256*tiles_x*tiles_y. */
+typedef struct KznImageDesc {
+    uint64_t address; /* device address of texel 0; multiple of KZN_IMAGE_ALIGNMENT */
+    uint32_t format;  /* KZN_FORMAT_* */
+    uint32_t tiling;  /* KZN_TILING_* */
+    uint32_t width, height, depth;
+    uint32_t array_layers;
+    uint32_t mip_levels; /* must be 1, as in image.rs:65 */
+    uint32_t reserved;
+} KznImageDesc;
+
+/* size/alignment exactly as ImageProperties::computed_properties (image.rs:58-88) for LINEAR;
+ * whole-tile padded for TILED.  Returns KZN_ERROR_FORMAT_NOT_SUPPORTED where the reference hits
+ * `unimplemented!` (D32_SFLOAT is additionally accepted). */
+KZN_API KznResult kzn_image_memory_requirements(const KznImageDesc* image, uint64_t* size,
+                                                uint64_t* alignment);
+
+/* -- device ---------------------------------------------------------------------------------- */
+KZN_API KznResult kzn_device_count(int32_t* count);
+KZN_API KznResult kzn_device_create(int32_t ordinal, KznDevice** device);
+KZN_API void kzn_device_destroy(KznDevice* device);
+KZN_API KznResult kzn_device_wait_idle(KznDevice* device); /* vkDeviceWaitIdle api_impl.rs:3429 */
+KZN_API int32_t kzn_device_sm_count(const KznDevice* device);
+KZN_API int32_t kzn_device_ordinal(const KznDevice* device);
+
+/* -- memory: vkAllocateMemory api_impl.rs:3434-3474, vkMapMemory :3488-3500 ------------------- */
+#define KZN_MEMORY_TYPE_HOST_COHERENT 0u /* reference's only type (device_memory.rs:30-39): pinned, mapped */
+#define KZN_MEMORY_TYPE_DEVICE_LOCAL 1u  /* added after index 0: HBM only, not mappable */
+KZN_API KznResult kzn_memory_allocate(KznDevice* device, uint64_t size, uint32_t memory_type,
+                                      KznMemory** memory);
+KZN_API void kzn_memory_free(KznMemory* memory);
+KZN_API uint64_t kzn_memory_device_address(const KznMemory* memory);
+KZN_API uint64_t kzn_memory_size(const KznMemory* memory); /* rounded up to 128, device_memory.rs:166-181 */
+/* host pointer = base + offset (api_impl.rs:3488-3500); KZN_ERROR_VALIDATION_FAILED for DEVICE_LOCAL */
+KZN_API KznResult kzn_memory_map(KznMemory* memory, uint64_t offset, void** host_ptr);
+
+/* -- queue: vkGetDeviceQueue :3394, vkQueueSubmit :3414, vkQueueWaitIdle :3424 ---------------- */
+KZN_API KznResult kzn_queue_create(KznDevice* device, KznQueue** queue);
+/* run on a stream owned by the host (e.g. the framework's current stream); not destroyed with the queue */
+KZN_API KznResult kzn_queue_wrap_stream(KznDevice* device, void* cuda_stream, KznQueue** queue);
+KZN_API void kzn_queue_destroy(KznQueue* queue);
+KZN_API KznResult kzn_queue_wait_idle(KznQueue* queue);
+KZN_API void* kzn_queue_stream(const KznQueue* queue);
+/* number of kernels this library has launched on the queue since creation (bench `gpu_launches`) */
+KZN_API uint64_t kzn_queue_launch_count(const KznQueue* queue);
+
+/* plain transfers between host memory and device addresses on the queue (used by the ICD for
+ * HOST_COHERENT emulation and by the end-to-end benchmark); host memory should be pinned */
+KZN_API KznResult kzn_queue_upload(KznQueue* queue, uint64_t dst_address, const void* src, uint64_t size);
+KZN_API KznResult kzn_queue_download(KznQueue* queue, void* dst, uint64_t src_address, uint64_t size);
+KZN_API KznResult kzn_host_alloc_pinned(uint64_t size, void** ptr);
+KZN_API void kzn_host_free_pinned(void* ptr);
+
+/* -- fences: vkCreateFence..vkWaitForFences api_impl.rs:3653-3697 ----------------------------- */
+KZN_API KznResult kzn_fence_create(KznDevice* device, int32_t signaled, KznFence** fence);
+KZN_API void kzn_fence_destroy(KznFence* fence);
+KZN_API KznResult kzn_fence_reset(KznFence* fence);
+KZN_API KznResult kzn_queue_signal_fence(KznQueue* queue, KznFence* fence); /* tail of vkQueueSubmit */
+KZN_API KznResult kzn_fence_status(KznFence* fence);                         /* SUCCESS / NOT_READY */
+KZN_API KznResult kzn_fence_wait(KznFence* fence, uint64_t timeout_ns);      /* SUCCESS / TIMEOUT */
+
+/* ------------------------------------------------------------------------------------------ */
+/* transfer commands                                               */
+
+/* vkCmdClearColorImage  vulkan-driver/src/api_impl.rs:4780-4789 */
+KZN_API KznResult kzn_cmd_clear_color_image(KznQueue* queue, const KznImageDesc* image,
+                                            const KznClearColorValue* color, uint32_t range_count,
+                                            const KznImageSubresourceRange* ranges);
+/* vkCmdClearDepthStencilImage  api_impl.rs:4792-4801 (D32_SFLOAT: depth only) */
+KZN_API KznResult kzn_cmd_clear_depth_stencil_image(KznQueue* queue, const KznImageDesc* image,
+                                                    const KznClearDepthStencilValue* value,
+                                                    uint32_t range_count,
+                                                    const KznImageSubresourceRange* ranges);
+/* vkCmdClearAttachments  api_impl.rs:4804-4812, for one colour or depth attachment image */
+KZN_API KznResult kzn_cmd_clear_attachment(KznQueue* queue, const KznImageDesc* image,
+                                           const KznClearColorValue* color_or_depth,
+                                           uint32_t rect_count, const KznClearRect* rects);
+/* vkCmdCopyBufferToImage  api_impl.rs:4734-4743 */
+KZN_API KznResult kzn_cmd_copy_buffer_to_image(KznQueue* queue, uint64_t buffer_address,
+                                               uint64_t buffer_size, const KznImageDesc* image,
+                                               uint32_t region_count, const KznBufferImageCopy* regions);
+/* vkCmdCopyImageToBuffer  api_impl.rs:4746-4755 */
+KZN_API KznResult kzn_cmd_copy_image_to_buffer(KznQueue* queue, const KznImageDesc* image,
+                                               uint64_t buffer_address, uint64_t buffer_size,
+                                               uint32_t region_count, const KznBufferImageCopy* regions);
+/* vkCmdCopyBuffer  api_impl.rs:4696-4703 */
+KZN_API KznResult kzn_cmd_copy_buffer(KznQueue* queue, uint64_t src_address, uint64_t src_size,
+                                      uint64_t dst_address, uint64_t dst_size, uint32_t region_count,
+                                      const KznBufferCopy* regions);
+/* vkCmdFillBuffer  api_impl.rs:4769-4777 (size may be KZN_WHOLE_SIZE) */
+KZN_API KznResult kzn_cmd_fill_buffer(KznQueue* queue, uint64_t dst_address, uint64_t dst_size,
+                                      uint64_t offset, uint64_t size, uint32_t data);
+/* vkCmdUpdateBuffer  api_impl.rs:4758-4766 (host data is captured at call time, <= 65536 B) */
+KZN_API KznResult kzn_cmd_update_buffer(KznQueue* queue, uint64_t dst_address, uint64_t dst_size,
+                                        uint64_t offset, uint64_t size, const void* data);
+/* vkCmdCopyImage  api_impl.rs:4707-4717 */
+KZN_API KznResult kzn_cmd_copy_image(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst,
+                                     uint32_t region_count, const KznImageCopy* regions);
+/* vkCmdBlitImage  api_impl.rs:4720-4731 (R8G8B8A8_UNORM <-> R8G8B8A8_UNORM) */
+KZN_API KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst,
+                                     uint32_t region_count, const KznImageBlit* regions, uint32_t filter);
+/* layout swizzle between Tiling::Linear and Tiling::Tiled (image.rs:17-22,48-57): same extents and
+ * format, different `tiling`; what a layout transition / present of an OPTIMAL image performs */
+KZN_API KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst);
+
+/* ------------------------------------------------------------------------------------------ */
+/* draw path: vkCmdDraw api_impl.rs:4632, vkCmdDrawIndexed :4643,        */
+/* vkCreateGraphicsPipelines :4018 -> GraphicsPipeline::create pipeline.rs:167-183 (all stubs)  */
+
+/* Shader stages.  The reference cannot translate any shader with a body, so the
+ * programmable stages are selected from built-in programs defined by the oracle (oracle/raster.c);
+ * KZN_FS_IR runs a fragment entry point compiled by the PTX backend (kazan_b200_backend.h). */
+#define KZN_VS_PASSTHROUGH 0u      /* gl_Position = vec4(pos.xyz, pos.w or 1); colour passed through */
+#define KZN_FS_VERTEX_COLOR 0u     /* out = perspective-correct interpolated vertex rgba */
+#define KZN_FS_PROCEDURAL_ORBIT 1u /* the fill-rate shader of BASELINE.json configs[2] (fp32 fma orbit, K=32) */
+#define KZN_FS_ORBIT_ITERATIONS 32u
+
+typedef struct KznGraphicsPipelineState {
+    uint32_t vertex_program;   /* KZN_VS_* */
+    uint32_t fragment_program; /* KZN_FS_* */
+    uint32_t cull_mode;        /* VkCullModeFlags: 0 none, 1 front, 2 back, 3 both */
+    uint32_t front_face;       /* VkFrontFace: 0 counter-clockwise, 1 clockwise */
+    uint32_t depth_test_enable;
+    uint32_t depth_write_enable;
+    uint32_t depth_compare_op; /* VkCompareOp 0..7 */
+    uint32_t blend_enable;
+    uint32_t src_color_blend_factor; /* VkBlendFactor (0..9 supported: ZERO..ONE_MINUS_DST_ALPHA) */
+    uint32_t dst_color_blend_factor;
+    uint32_t color_blend_op; /* VkBlendOp 0..4 */
+    uint32_t src_alpha_blend_factor;
+    uint32_t dst_alpha_blend_factor;
+    uint32_t alpha_blend_op;
+    uint32_t color_write_mask; /* VkColorComponentFlags, R=1 G=2 B=4 A=8 */
+    uint32_t reserved;
+} KznGraphicsPipelineState;
+
+typedef struct KznVertexInput { /* one binding, VkVertexInputBindingDescription + 2 attributes */
+    uint64_t buffer_address;
+    uint64_t buffer_size;
+    uint32_t stride;
+    uint32_t position_offset;
+    uint32_t position_components; /* 3 (R32G32B32_SFLOAT, w=1) or 4 (R32G32B32A32_SFLOAT) */
+    uint32_t color_offset;        /* R32G32B32A32_SFLOAT; ~0u = no colour attribute (constant 1,1,1,1) */
+} KznVertexInput;
+
+typedef struct KznFramebuffer { /* vkCreateFramebuffer api_impl.rs:4383-4390 + render pass attachments */
+    KznImageDesc color; /* R8G8B8A8_UNORM, LINEAR or TILED; format 0 = no colour attachment */
+    KznImageDesc depth; /* D32_SFLOAT LINEAR; format 0 = no depth attachment */
+    uint32_t color_layer, depth_layer;
+    /* sort-first band splitting: only rows [band_y0, band_y1) are rendered;
+     * band_y1 == 0 means the whole framebuffer */
+    uint32_t band_y0, band_y1;
+} KznFramebuffer;
+
+typedef struct KznDrawStatistics { /* optional, device-written counters (8 x u64) */
+    uint64_t triangles_in, triangles_culled, triangles_binned, bin_entries, fragments_covered,
+        fragments_depth_passed, tiles_launched, bin_overflow_tiles;
+} KznDrawStatistics;
+
+KZN_API KznResult kzn_cmd_draw(KznQueue* queue, const KznGraphicsPipelineState* state,
+                               const KznFramebuffer* framebuffer, const KznViewport* viewport,
+                               const KznRect2D* scissor, const KznVertexInput* vertices,
+                               uint32_t vertex_count, uint32_t instance_count, uint32_t first_vertex,
+                               uint32_t first_instance);
+KZN_API KznResult kzn_cmd_draw_indexed(KznQueue* queue, const KznGraphicsPipelineState* state,
+                                       const KznFramebuffer* framebuffer, const KznViewport* viewport,
+                                       const KznRect2D* scissor, const KznVertexInput* vertices,
+                                       uint64_t index_buffer_address, uint64_t index_buffer_size,
+                                       uint32_t index_type, uint32_t index_count,
+                                       uint32_t instance_count, uint32_t first_index,
+                                       int32_t vertex_offset, uint32_t first_instance);
+/* where (device address of a KznDrawStatistics, zeroed by the caller) the next draws accumulate
+ * counters; 0 disables */
+KZN_API KznResult kzn_queue_set_draw_statistics(KznQueue* queue, uint64_t stats_address);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAZAN_B200_H */

@@ -1,0 +1,233 @@
+"""ctypes mirror of include/kazan_b200.h (struct layouts and prototypes).
+
+The structs are layout-identical to the Vulkan 1.1.130 structs they are named after
+(reference: external/Vulkan-Headers/include/vulkan/vulkan_core.h:2899-2919); tests/test_abi.py
+checks this file, the C header and the Vulkan header against each other.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "kazan_b200.h"
+
+# results -------------------------------------------------------------------------------------
+SUCCESS = 0
+NOT_READY = 1
+TIMEOUT = 2
+ERROR_OUT_OF_HOST_MEMORY = -1
+ERROR_OUT_OF_DEVICE_MEMORY = -2
+ERROR_INITIALIZATION_FAILED = -3
+ERROR_DEVICE_LOST = -4
+ERROR_FEATURE_NOT_PRESENT = -8
+ERROR_FORMAT_NOT_SUPPORTED = -11
+ERROR_VALIDATION_FAILED = -1000011001
+
+RESULT_NAMES = {
+    SUCCESS: "VK_SUCCESS",
+    NOT_READY: "VK_NOT_READY",
+    TIMEOUT: "VK_TIMEOUT",
+    ERROR_OUT_OF_HOST_MEMORY: "VK_ERROR_OUT_OF_HOST_MEMORY",
+    ERROR_OUT_OF_DEVICE_MEMORY: "VK_ERROR_OUT_OF_DEVICE_MEMORY",
+    ERROR_INITIALIZATION_FAILED: "VK_ERROR_INITIALIZATION_FAILED",
+    ERROR_DEVICE_LOST: "VK_ERROR_DEVICE_LOST",
+    ERROR_FEATURE_NOT_PRESENT: "VK_ERROR_FEATURE_NOT_PRESENT",
+    ERROR_FORMAT_NOT_SUPPORTED: "VK_ERROR_FORMAT_NOT_SUPPORTED",
+    ERROR_VALIDATION_FAILED: "VK_ERROR_VALIDATION_FAILED_EXT",
+}
+
+# constants -----------------------------------------------------------------------------------
+FORMAT_R8G8B8A8_UNORM = 37
+FORMAT_D32_SFLOAT = 126
+TILING_LINEAR = 0
+TILING_TILED = 1
+TILE_DIM = 16
+ASPECT_COLOR = 1
+ASPECT_DEPTH = 2
+FILTER_NEAREST = 0
+FILTER_LINEAR = 1
+INDEX_TYPE_UINT16 = 0
+INDEX_TYPE_UINT32 = 1
+WHOLE_SIZE = 2**64 - 1
+REMAINING = 2**32 - 1
+MEMORY_TYPE_HOST_COHERENT = 0
+MEMORY_TYPE_DEVICE_LOCAL = 1
+VS_PASSTHROUGH = 0
+FS_VERTEX_COLOR = 0
+FS_PROCEDURAL_ORBIT = 1
+# VkCompareOp
+COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_OR_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, \
+    COMPARE_GREATER_OR_EQUAL, COMPARE_ALWAYS = range(8)
+# VkBlendFactor (subset)
+BLEND_ZERO, BLEND_ONE, BLEND_SRC_COLOR, BLEND_ONE_MINUS_SRC_COLOR, BLEND_DST_COLOR, BLEND_ONE_MINUS_DST_COLOR, \
+    BLEND_SRC_ALPHA, BLEND_ONE_MINUS_SRC_ALPHA, BLEND_DST_ALPHA, BLEND_ONE_MINUS_DST_ALPHA = range(10)
+# VkBlendOp
+BLEND_OP_ADD, BLEND_OP_SUBTRACT, BLEND_OP_REVERSE_SUBTRACT, BLEND_OP_MIN, BLEND_OP_MAX = range(5)
+CULL_NONE, CULL_FRONT, CULL_BACK, CULL_BOTH = range(4)
+FRONT_FACE_CCW, FRONT_FACE_CW = 0, 1
+
+u32, i32, u64, f32 = C.c_uint32, C.c_int32, C.c_uint64, C.c_float
+
+
+class Offset3D(C.Structure):
+    _fields_ = [("x", i32), ("y", i32), ("z", i32)]
+
+
+class Extent3D(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("depth", u32)]
+
+
+class Offset2D(C.Structure):
+    _fields_ = [("x", i32), ("y", i32)]
+
+
+class Extent2D(C.Structure):
+    _fields_ = [("width", u32), ("height", u32)]
+
+
+class Rect2D(C.Structure):
+    _fields_ = [("offset", Offset2D), ("extent", Extent2D)]
+
+
+class Viewport(C.Structure):
+    _fields_ = [("x", f32), ("y", f32), ("width", f32), ("height", f32), ("minDepth", f32), ("maxDepth", f32)]
+
+
+class ClearColorValue(C.Union):
+    _fields_ = [("float32", f32 * 4), ("int32", i32 * 4), ("uint32", u32 * 4)]
+
+
+class ClearDepthStencilValue(C.Structure):
+    _fields_ = [("depth", f32), ("stencil", u32)]
+
+
+class ImageSubresourceRange(C.Structure):
+    _fields_ = [("aspectMask", u32), ("baseMipLevel", u32), ("levelCount", u32), ("baseArrayLayer", u32),
+                ("layerCount", u32)]
+
+
+class ImageSubresourceLayers(C.Structure):
+    _fields_ = [("aspectMask", u32), ("mipLevel", u32), ("baseArrayLayer", u32), ("layerCount", u32)]
+
+
+class BufferCopy(C.Structure):
+    _fields_ = [("srcOffset", u64), ("dstOffset", u64), ("size", u64)]
+
+
+class BufferImageCopy(C.Structure):
+    _fields_ = [("bufferOffset", u64), ("bufferRowLength", u32), ("bufferImageHeight", u32),
+                ("imageSubresource", ImageSubresourceLayers), ("imageOffset", Offset3D), ("imageExtent", Extent3D)]
+
+
+class ImageCopy(C.Structure):
+    _fields_ = [("srcSubresource", ImageSubresourceLayers), ("srcOffset", Offset3D),
+                ("dstSubresource", ImageSubresourceLayers), ("dstOffset", Offset3D), ("extent", Extent3D)]
+
+
+class ImageBlit(C.Structure):
+    _fields_ = [("srcSubresource", ImageSubresourceLayers), ("srcOffsets", Offset3D * 2),
+                ("dstSubresource", ImageSubresourceLayers), ("dstOffsets", Offset3D * 2)]
+
+
+class ClearRect(C.Structure):
+    _fields_ = [("rect", Rect2D), ("baseArrayLayer", u32), ("layerCount", u32)]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("address", u64), ("format", u32), ("tiling", u32), ("width", u32), ("height", u32), ("depth", u32),
+                ("array_layers", u32), ("mip_levels", u32), ("reserved", u32)]
+
+
+class GraphicsPipelineState(C.Structure):
+    _fields_ = [(n, u32) for n in (
+        "vertex_program", "fragment_program", "cull_mode", "front_face", "depth_test_enable", "depth_write_enable",
+        "depth_compare_op", "blend_enable", "src_color_blend_factor", "dst_color_blend_factor", "color_blend_op",
+        "src_alpha_blend_factor", "dst_alpha_blend_factor", "alpha_blend_op", "color_write_mask", "reserved")]
+
+
+class VertexInput(C.Structure):
+    _fields_ = [("buffer_address", u64), ("buffer_size", u64), ("stride", u32), ("position_offset", u32),
+                ("position_components", u32), ("color_offset", u32)]
+
+
+class Framebuffer(C.Structure):
+    _fields_ = [("color", ImageDesc), ("depth", ImageDesc), ("color_layer", u32), ("depth_layer", u32),
+                ("band_y0", u32), ("band_y1", u32)]
+
+
+class DrawStatistics(C.Structure):
+    _fields_ = [(n, u64) for n in (
+        "triangles_in", "triangles_culled", "triangles_binned", "bin_entries", "fragments_covered",
+        "fragments_depth_passed", "tiles_launched", "bin_overflow_tiles")]
+
+
+P = C.POINTER
+vp = C.c_void_p
+
+# name -> (restype, argtypes).  Opaque handles cross as void*.
+PROTOTYPES = {
+    "kzn_abi_version": (u32, []),
+    "kzn_last_error": (C.c_char_p, []),
+    "kzn_image_memory_requirements": (i32, [P(ImageDesc), P(u64), P(u64)]),
+    "kzn_device_count": (i32, [P(i32)]),
+    "kzn_device_create": (i32, [i32, P(vp)]),
+    "kzn_device_destroy": (None, [vp]),
+    "kzn_device_wait_idle": (i32, [vp]),
+    "kzn_device_sm_count": (i32, [vp]),
+    "kzn_device_ordinal": (i32, [vp]),
+    "kzn_memory_allocate": (i32, [vp, u64, u32, P(vp)]),
+    "kzn_memory_free": (None, [vp]),
+    "kzn_memory_device_address": (u64, [vp]),
+    "kzn_memory_size": (u64, [vp]),
+    "kzn_memory_map": (i32, [vp, u64, P(vp)]),
+    "kzn_queue_create": (i32, [vp, P(vp)]),
+    "kzn_queue_wrap_stream": (i32, [vp, vp, P(vp)]),
+    "kzn_queue_destroy": (None, [vp]),
+    "kzn_queue_wait_idle": (i32, [vp]),
+    "kzn_queue_stream": (vp, [vp]),
+    "kzn_queue_launch_count": (u64, [vp]),
+    "kzn_queue_upload": (i32, [vp, u64, vp, u64]),
+    "kzn_queue_download": (i32, [vp, vp, u64, u64]),
+    "kzn_host_alloc_pinned": (i32, [u64, P(vp)]),
+    "kzn_host_free_pinned": (None, [vp]),
+    "kzn_fence_create": (i32, [vp, i32, P(vp)]),
+    "kzn_fence_destroy": (None, [vp]),
+    "kzn_fence_reset": (i32, [vp]),
+    "kzn_queue_signal_fence": (i32, [vp, vp]),
+    "kzn_fence_status": (i32, [vp]),
+    "kzn_fence_wait": (i32, [vp, u64]),
+    "kzn_cmd_clear_color_image": (i32, [vp, P(ImageDesc), P(ClearColorValue), u32, P(ImageSubresourceRange)]),
+    "kzn_cmd_clear_depth_stencil_image": (i32, [vp, P(ImageDesc), P(ClearDepthStencilValue), u32,
+                                                P(ImageSubresourceRange)]),
+    "kzn_cmd_clear_attachment": (i32, [vp, P(ImageDesc), P(ClearColorValue), u32, P(ClearRect)]),
+    "kzn_cmd_copy_buffer_to_image": (i32, [vp, u64, u64, P(ImageDesc), u32, P(BufferImageCopy)]),
+    "kzn_cmd_copy_image_to_buffer": (i32, [vp, P(ImageDesc), u64, u64, u32, P(BufferImageCopy)]),
+    "kzn_cmd_copy_buffer": (i32, [vp, u64, u64, u64, u64, u32, P(BufferCopy)]),
+    "kzn_cmd_fill_buffer": (i32, [vp, u64, u64, u64, u64, u32]),
+    "kzn_cmd_update_buffer": (i32, [vp, u64, u64, u64, u64, vp]),
+    "kzn_cmd_copy_image": (i32, [vp, P(ImageDesc), P(ImageDesc), u32, P(ImageCopy)]),
+    "kzn_cmd_blit_image": (i32, [vp, P(ImageDesc), P(ImageDesc), u32, P(ImageBlit), u32]),
+    "kzn_cmd_convert_tiling": (i32, [vp, P(ImageDesc), P(ImageDesc)]),
+    "kzn_cmd_draw": (i32, [vp, P(GraphicsPipelineState), P(Framebuffer), P(Viewport), P(Rect2D), P(VertexInput),
+                           u32, u32, u32, u32]),
+    "kzn_cmd_draw_indexed": (i32, [vp, P(GraphicsPipelineState), P(Framebuffer), P(Viewport), P(Rect2D),
+                                   P(VertexInput), u64, u64, u32, u32, u32, u32, i32, u32]),
+    "kzn_queue_set_draw_statistics": (i32, [vp, u64]),
+}
+
+
+def declared_symbols(header: Path = HEADER) -> list[str]:
+    """Every function the C header declares with KZN_API (what the library must export)."""
+    text = header.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"KZN_API\s+[^;(]*?\b(kzn_\w+)\s*\(", text)
+
+
+def bind(lib: C.CDLL, prototypes: dict | None = None) -> C.CDLL:
+    for name, (res, args) in (prototypes or PROTOTYPES).items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

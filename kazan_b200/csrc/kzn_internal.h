@@ -1,0 +1,85 @@
+// kzn_internal.h — shared by the translation units of libkazan_b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kazan_b200.h"
+
+struct KznDevice {
+    int ordinal;
+    int sm_count;
+    int l2_bytes;
+    int cc_major, cc_minor;
+};
+
+struct KznRasterScratch;  // raster.cu
+
+struct KznQueue {
+    KznDevice* device;
+    cudaStream_t stream;
+    bool owns_stream;
+    uint64_t launches;
+    uint64_t stats_address;
+    KznRasterScratch* raster;  // lazily created, grows to the largest draw seen
+};
+
+struct KznMemory {
+    KznDevice* device;
+    uint32_t type;
+    uint64_t size;  // rounded up to KZN_MIN_MEMORY_MAP_ALIGNMENT
+    void* device_ptr;
+    void* host_ptr;  // HOST_COHERENT only
+};
+
+struct KznFence {
+    KznDevice* device;
+    cudaEvent_t event;
+    bool signaled_without_work;  // created signaled, or reset and never submitted
+    bool pending;                // an event record has been enqueued
+};
+
+// error plumbing -----------------------------------------------------------------------------
+void kzn_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int line);
+
+#define KZN_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return kzn_cuda_failed(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define KZN_REQUIRE(cond, code, ...)   \
+    do {                               \
+        if (!(cond)) {                 \
+            kzn_set_error(__VA_ARGS__); \
+            return (code);             \
+        }                              \
+    } while (0)
+
+#define KZN_VALID(cond, ...) KZN_REQUIRE(cond, KZN_ERROR_VALIDATION_FAILED, __VA_ARGS__)
+
+// make the queue's device current and check the queue is usable
+KznResult kzn_queue_enter(KznQueue* q);
+// call after every kernel launch: counts it and maps launch errors
+KznResult kzn_launched(KznQueue* q, const char* kernel);
+
+// layout helpers (image.rs:58-88 + SURVEY.md E.10) ----------------------------------------------
+static inline uint32_t kzn_texel_size(uint32_t format) {
+    return (format == KZN_FORMAT_R8G8B8A8_UNORM || format == KZN_FORMAT_D32_SFLOAT) ? 4u : 0u;
+}
+static inline uint64_t kzn_round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+static inline uint32_t kzn_tiles(uint32_t texels) { return (texels + KZN_TILE_DIM - 1) / KZN_TILE_DIM; }
+static inline uint64_t kzn_row_pitch(const KznImageDesc* im) {  // LINEAR only
+    return (uint64_t)kzn_texel_size(im->format) * im->width;
+}
+static inline uint64_t kzn_slice_pitch(const KznImageDesc* im) {
+    uint64_t ts = kzn_texel_size(im->format);
+    if (im->tiling == KZN_TILING_TILED)
+        return (uint64_t)kzn_tiles(im->width) * kzn_tiles(im->height) * KZN_TILE_DIM * KZN_TILE_DIM * ts;
+    return ts * im->width * im->height;
+}
+KznResult kzn_check_image(const KznImageDesc* im, const char* what);
+
+// E.1 on the host (used for the one-off clear colour conversion)
+uint32_t kzn_pack_rgba8_host(const float rgba[4]);

@@ -1,0 +1,772 @@
+// raster.cu — the draw path as hand-written sm_100a kernels.
+//
+// Replaces the `unimplemented!()` bodies of vkCmdDraw / vkCmdDrawIndexed
+// (vulkan-driver/src/api_impl.rs:4632-4652) and GraphicsPipeline::create (vulkan-driver/src/pipeline.rs:167-183).
+// Limits honoured: subPixelPrecisionBits 4 (api_impl.rs:1559), single sample at the pixel centre
+// (standardSampleLocations, api_impl.rs:1609), one viewport (api_impl.rs:1566), no depth clamp (api_impl.rs:887).
+//
+// Pipeline (one stream, no host round trip):
+//   setup_kernel   1 thread / triangle: index + vertex fetch, passthrough VS, clip->window (R1), snap to 1/16 px (R2),
+//                  signed area / cull (R4), sign-normalised integer edge equations + top-left bias (R5), pixel bbox.
+//                  Writes one 144-byte TriRec per triangle.
+//   bin_count / bin_scan / bin_fill   screen-tile binning: per 32x8-pixel tile, the list of overlapping triangles
+//                  (atomics give an unordered list; the raster kernel sorts it in shared memory so that per-pixel
+//                  fragment order == primitive order, R7).
+//   raster_kernel  1 CTA / screen tile, 1 thread / pixel: the tile's colour and depth live in REGISTERS for the whole
+//                  triangle list (each framebuffer byte is read at most once and written at most once per draw);
+//                  fixed-point coverage (int64 edge functions, bias test), barycentric depth (R6), z clip, early-Z,
+//                  fragment program, blend (R8), one coalesced 128-byte row store per warp.
+// Numerics are the oracle's rules R1-R8 (oracle/raster.c): every fp32 operation is written out; the file is compiled
+// with -fmad=false so only the explicit fmaf() calls fuse.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "kzn_internal.h"
+
+namespace {
+
+constexpr int kTileW = 32, kTileH = 8;   // pixels per raster tile: one warp per row -> 128 B row stores
+constexpr int kRasterThreads = kTileW * kTileH;
+constexpr int kRecs = 128;               // triangle records staged in shared memory per round
+constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
+constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
+constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
+
+struct __align__(16) TriRec {
+    int32_t minx, maxx, miny, maxy;  // inclusive, scissored; minx > maxx => produces no fragments
+    int32_t a[3], b[3];
+    uint32_t bias_bits;
+    float inv2a;
+    long long c[3];
+    float z[3], iw[3];
+    float col[3][4];  // colour * iw
+};
+static_assert(sizeof(TriRec) == 144, "TriRec layout");
+
+struct DrawParams {
+    // geometry
+    unsigned long long vertex_base, vertex_size;
+    unsigned long long index_base;  // 0 => non-indexed
+    uint32_t stride, pos_off, pos_comps, col_off;
+    uint32_t index_type;
+    uint32_t first;  // firstIndex / firstVertex
+    int32_t vertex_offset;
+    uint32_t tris_per_instance, total_tris;
+    // state
+    KznGraphicsPipelineState st;
+    float hw, hh, ox, oy, dz, zmin_vp;  // viewport transform (R1)
+    float zclip_lo, zclip_hi;
+    int32_t cx0, cy0, cx1, cy1;  // inclusive clip rectangle (scissor ∩ viewport ∩ framebuffer ∩ band)
+    // framebuffer
+    unsigned long long color_base, depth_base;  // layer already applied; 0 => absent
+    uint32_t fb_w, fb_h, color_tiled, color_tiles_x;
+    float inv_fb_w, inv_fb_h;
+    // scratch
+    TriRec* tris;
+    uint32_t* tile_counts;   // [tiles]  (bin_count)
+    uint32_t* tile_offsets;  // [tiles+1] (bin_scan)
+    uint32_t* tile_cursor;   // [tiles]  (bin_fill)
+    uint32_t* bin_entries;   // [bin_capacity]
+    uint32_t bin_capacity;
+    uint32_t tiles_x, tiles_y, tile_x0, tile_y0;  // tile grid covering the clip rectangle
+    uint32_t binned;                               // 0 => every tile walks all triangles
+    unsigned long long* stats;                     // KznDrawStatistics or null
+};
+
+// ---- setup ------------------------------------------------------------------------------------------------
+
+struct VsOut {
+    float x, y, z, w;
+    float rgba[4];
+};
+
+__device__ __forceinline__ void fetch_vertex(const DrawParams& p, long long vidx, VsOut& o) {
+    o.x = o.y = o.z = 0.0f;
+    o.w = 1.0f;
+    o.rgba[0] = o.rgba[1] = o.rgba[2] = o.rgba[3] = 1.0f;
+    bool neg = vidx < 0;
+    unsigned long long off = (unsigned long long)vidx * p.stride;
+    if (!neg && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size) {
+        const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off);
+        o.x = __ldg(s);
+        o.y = __ldg(s + 1);
+        o.z = __ldg(s + 2);
+        if (p.pos_comps == 4) o.w = __ldg(s + 3);
+    }
+    if (p.col_off != ~0u) {
+        if (!neg && off + p.col_off + 16ull <= p.vertex_size) {
+            const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.col_off);
+            o.rgba[0] = __ldg(s);
+            o.rgba[1] = __ldg(s + 1);
+            o.rgba[2] = __ldg(s + 2);
+            o.rgba[3] = __ldg(s + 3);
+        } else {
+            o.rgba[0] = o.rgba[1] = o.rgba[2] = 0.0f;
+        }
+    }
+}
+
+__device__ __forceinline__ bool finite_f(float f) { return (f - f) == 0.0f; }
+
+__global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
+    uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= p.tris_per_instance) return;
+    TriRec r;
+    r.minx = 1;
+    r.maxx = 0;
+    r.miny = 1;
+    r.maxy = 0;
+    bool ok = true;
+    int32_t X[3], Y[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long i = (unsigned long long)p.first + 3ull * t + k;
+        long long vidx;
+        if (p.index_base) {
+            unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
+                                         ? (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(p.index_base) + i)
+                                         : (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(p.index_base) + i);
+            vidx = (long long)raw + p.vertex_offset;
+        } else {
+            vidx = (long long)i;
+        }
+        VsOut v;
+        fetch_vertex(p, vidx, v);
+        if (!(v.w > 0.0f)) ok = false;  // R3
+        float iw = 1.0f / v.w;
+        float xf = fmaf(p.hw, v.x * iw, p.ox);
+        float yf = fmaf(p.hh, v.y * iw, p.oy);
+        float zf = fmaf(p.dz, v.z * iw, p.zmin_vp);
+        if (!finite_f(xf) || !finite_f(yf) || !finite_f(zf) || !finite_f(iw)) ok = false;
+        if (fabsf(xf) > kGuardBand || fabsf(yf) > kGuardBand) ok = false;
+        X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+        Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;
+        r.z[k] = zf;
+        r.iw[k] = iw;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) r.col[k][ch] = v.rgba[ch] * iw;
+    }
+    long long two_a = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);  // R4
+    if (two_a == 0) ok = false;
+    bool front = p.st.front_face == 0 ? (two_a < 0) : (two_a > 0);
+    if ((front && (p.st.cull_mode & 1u)) || (!front && (p.st.cull_mode & 2u))) ok = false;
+    long long s = two_a < 0 ? -1 : 1;
+    r.bias_bits = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // R5
+        int ia = (i + 1) % 3, ib = (i + 2) % 3;
+        long long dx = X[ib] - X[ia], dy = Y[ib] - Y[ia];
+        long long a = -dy * s, b = dx * s;
+        r.a[i] = (int32_t)a;
+        r.b[i] = (int32_t)b;
+        r.c[i] = s * (dy * X[ia] - dx * Y[ia]);
+        if (a > 0 || (a == 0 && b > 0)) r.bias_bits |= 1u << i;
+    }
+    r.inv2a = 1.0f / (float)(two_a * s);
+    if (ok) {
+        int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+        int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+        r.minx = max((minX - 8 + 15) >> 4, p.cx0);
+        r.maxx = min((maxX - 8) >> 4, p.cx1);
+        r.miny = max((minY - 8 + 15) >> 4, p.cy0);
+        r.maxy = min((maxY - 8) >> 4, p.cy1);
+        if (r.minx > r.maxx || r.miny > r.maxy) {
+            r.minx = 1; r.maxx = 0; r.miny = 1; r.maxy = 0;
+            ok = false;
+        }
+    }
+    // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    for (uint32_t inst = 0; inst * p.tris_per_instance < p.total_tris; ++inst) {
+        uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) dst[q] = src[q];
+    }
+    if (p.stats) {
+        unsigned long long n_inst = p.total_tris / p.tris_per_instance;
+        atomicAdd(&p.stats[0], n_inst);
+        if (!ok) atomicAdd(&p.stats[1], n_inst);
+    }
+}
+
+// ---- binning --------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool tile_range(const DrawParams& p, const TriRec* r, int& tx0, int& tx1, int& ty0, int& ty1) {
+    int4 bb = *reinterpret_cast<const int4*>(r);  // minx, maxx, miny, maxy
+    if (bb.x > bb.y) return false;
+    tx0 = bb.x / kTileW - (int)p.tile_x0;
+    tx1 = bb.y / kTileW - (int)p.tile_x0;
+    ty0 = bb.z / kTileH - (int)p.tile_y0;
+    ty1 = bb.w / kTileH - (int)p.tile_y0;
+    return true;
+}
+
+// FILL == false: count entries per tile; FILL == true: write triangle ids into the tile segments.
+// One warp per triangle so that wide triangles spread their tiles over the lanes.
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_kernel(const __grid_constant__ DrawParams p) {
+    uint32_t warp = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    uint32_t nwarps = (gridDim.x * 256u) >> 5;
+    for (uint32_t t = warp; t < p.total_tris; t += nwarps) {
+        int tx0, tx1, ty0, ty1;
+        if (!tile_range(p, &p.tris[t], tx0, tx1, ty0, ty1)) continue;
+        int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+        for (int k = lane; k < n; k += 32) {
+            int ty = ty0 + k / w, tx = tx0 + k % w;
+            uint32_t tile = (uint32_t)ty * p.tiles_x + (uint32_t)tx;
+            if (!FILL) {
+                atomicAdd(&p.tile_counts[tile], 1u);
+            } else {
+                uint32_t pos = p.tile_offsets[tile] + atomicAdd(&p.tile_cursor[tile], 1u);
+                if (pos < p.bin_capacity) p.bin_entries[pos] = t;
+            }
+        }
+    }
+}
+
+// exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ DrawParams p) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    uint32_t tiles = p.tiles_x * p.tiles_y;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < tiles ? p.tile_counts[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], xs = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, xs, d);
+                if (threadIdx.x >= d) xs += y;
+            }
+            warp_sums[threadIdx.x] = xs - w;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < tiles) p.tile_offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.tile_offsets[tiles] = carry;
+        if (p.stats) atomicAdd(&p.stats[3], (unsigned long long)carry);
+    }
+}
+
+// ---- per-fragment helpers ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float clamp01(float f) { return __saturatef(f); }  // NaN -> 0
+__device__ __forceinline__ float unorm8_to_float(uint32_t u) { return __fdiv_rn((float)u, 255.0f); }
+__device__ __forceinline__ uint32_t float_to_unorm8(float f) { return __float2uint_rn(clamp01(f) * 255.0f); }
+
+__device__ __forceinline__ bool depth_compare(uint32_t op, float z, float zs) {
+    switch (op) {
+    case 0: return false;
+    case 1: return z < zs;
+    case 2: return z == zs;
+    case 3: return z <= zs;
+    case 4: return z > zs;
+    case 5: return z != zs;
+    case 6: return z >= zs;
+    default: return true;
+    }
+}
+
+__device__ __forceinline__ float blend_factor(uint32_t f, int ch, const float s[4], const float d[4]) {
+    switch (f) {
+    case 0: return 0.0f;
+    case 1: return 1.0f;
+    case 2: return s[ch];
+    case 3: return 1.0f - s[ch];
+    case 4: return d[ch];
+    case 5: return 1.0f - d[ch];
+    case 6: return s[3];
+    case 7: return 1.0f - s[3];
+    case 8: return d[3];
+    default: return 1.0f - d[3];
+    }
+}
+
+__device__ __forceinline__ float blend_op(uint32_t op, float cs, float sf, float cd, float df) {
+    float t0 = cs * sf, t1 = cd * df;
+    switch (op) {
+    case 0: return t0 + t1;
+    case 1: return t0 - t1;
+    case 2: return t1 - t0;
+    case 3: return cs < cd ? cs : cd;
+    default: return cs > cd ? cs : cd;
+    }
+}
+
+__device__ __forceinline__ uint32_t output_merge(const KznGraphicsPipelineState& st, const float src[4], uint32_t dst_word) {
+    float s[4], o[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) s[ch] = clamp01(src[ch]);
+    if (st.blend_enable) {
+        float d[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) d[ch] = unorm8_to_float((dst_word >> (8 * ch)) & 255u);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            o[ch] = blend_op(st.color_blend_op, s[ch], blend_factor(st.src_color_blend_factor, ch, s, d), d[ch],
+                             blend_factor(st.dst_color_blend_factor, ch, s, d));
+        o[3] = blend_op(st.alpha_blend_op, s[3], blend_factor(st.src_alpha_blend_factor, 3, s, d), d[3],
+                        blend_factor(st.dst_alpha_blend_factor, 3, s, d));
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) o[ch] = s[ch];
+    }
+    uint32_t out = dst_word;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+        if (st.color_write_mask & (1u << ch)) out = (out & ~(0xffu << (8 * ch))) | (float_to_unorm8(o[ch]) << (8 * ch));
+    return out;
+}
+
+__device__ __forceinline__ void fs_procedural_orbit(int px, int py, float inv_w, float inv_h, float rgba[4]) {
+    float u = ((float)px + 0.5f) * inv_w;
+    float v = ((float)py + 0.5f) * inv_h;
+    float cx = fmaf(u, 3.5f, -2.5f);
+    float cy = fmaf(v, 2.0f, -1.0f);
+    float zx = 0.0f, zy = 0.0f;
+#pragma unroll 8
+    for (uint32_t k = 0; k < KZN_FS_ORBIT_ITERATIONS; ++k) {
+        float t = fmaf(zx, zx, cx);
+        float nzx = fmaf(-zy, zy, t);
+        float nzy = fmaf(zx + zx, zy, cy);
+        zx = nzx;
+        zy = nzy;
+    }
+    float m = fmaf(zx, zx, zy * zy);
+    rgba[0] = 0.25f * m;
+    rgba[1] = fmaf(zx, 0.5f, 0.5f);
+    rgba[2] = fmaf(zy, 0.5f, 0.5f);
+    rgba[3] = 1.0f;
+}
+
+__device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, int px, int py) {
+    if (p.color_tiled) {
+        unsigned long long tile = (unsigned long long)(py >> 4) * p.color_tiles_x + (px >> 4);
+        return p.color_base + ((tile << 8) + ((py & 15) << 4) + (px & 15)) * 4ull;
+    }
+    return p.color_base + ((unsigned long long)py * p.fb_w + px) * 4ull;
+}
+
+// ---- raster ------------------------------------------------------------------------------------------------------------
+
+struct RasterShared {
+    TriRec recs[kRecs];
+    uint32_t list[kSortCap];  // binned: the tile's sorted triangle ids; direct: ids surviving the current round
+    uint32_t warp_counts[kTileH];
+    uint32_t round_count;
+};
+
+template <uint32_t FS>
+__global__ void __launch_bounds__(kRasterThreads) raster_kernel(const __grid_constant__ DrawParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
+    const int px = tile_px0 + (int)lane, py = tile_py0 + (int)warp;
+    const bool in_clip = px >= p.cx0 && px <= p.cx1 && py >= p.cy0 && py <= p.cy1;
+    const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
+    const bool depth_test = has_depth && p.st.depth_test_enable;
+    const bool depth_write = depth_test && p.st.depth_write_enable;
+    // only read the destination colour when the result depends on it
+    const bool need_dst = has_color && (p.st.blend_enable || (p.st.color_write_mask & 15u) != 15u);
+
+    uint32_t color = 0;
+    float depth = 0.0f;
+    bool color_dirty = false, depth_dirty = false;
+    unsigned long long caddr = 0, daddr = 0;
+    if (in_clip) {
+        if (has_color) {
+            caddr = color_addr(p, px, py);
+            if (need_dst) color = *reinterpret_cast<const uint32_t*>(caddr);
+        }
+        if (has_depth) {
+            daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px) * 4ull;
+            if (depth_test) depth = *reinterpret_cast<const float*>(daddr);
+        }
+    }
+    const int32_t sx = 16 * px + 8, sy = 16 * py + 8;  // fixed-point sample position (R2)
+    uint32_t n_covered = 0, n_passed = 0;
+
+    // triangle source
+    uint32_t list_len = 0;
+    bool direct = true;
+    if (p.binned) {
+        uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
+        list_len = end - beg;
+        if (list_len == 0) return;
+        if (list_len <= (uint32_t)kSortCap && end <= p.bin_capacity) {
+            direct = false;
+            // load and bitonic-sort the tile's triangle ids (ascending = primitive order)
+            uint32_t n2 = 1;
+            while (n2 < list_len) n2 <<= 1;
+            for (uint32_t i = tid; i < n2; i += kRasterThreads) sh.list[i] = i < list_len ? p.bin_entries[beg + i] : 0xffffffffu;
+            __syncthreads();
+            for (uint32_t k = 2; k <= n2; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = tid; i < n2; i += kRasterThreads) {
+                        uint32_t l = i ^ j;
+                        if (l > i) {
+                            uint32_t a = sh.list[i], b = sh.list[l];
+                            bool up = (i & k) == 0;
+                            if ((a > b) == up) {
+                                sh.list[i] = b;
+                                sh.list[l] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+        } else if (p.stats && tid == 0) {
+            atomicAdd(&p.stats[7], 1ull);
+        }
+    }
+    const uint32_t n_source = direct ? p.total_tris : list_len;
+
+    for (uint32_t base = 0; base < n_source; base += kRecs) {
+        // ---- stage up to kRecs triangle records that touch this tile, in primitive order ----
+        uint32_t n_round;
+        if (direct) {
+            // candidates base .. base+kRecs-1: bbox test, order-preserving compaction
+            bool hit = false;
+            uint32_t cand = base + tid;
+            if (tid < kRecs && cand < n_source) {
+                int4 bb = *reinterpret_cast<const int4*>(&p.tris[cand]);
+                hit = bb.x <= bb.y && bb.x <= tile_px0 + kTileW - 1 && bb.y >= tile_px0 && bb.z <= tile_py0 + kTileH - 1 &&
+                      bb.w >= tile_py0;
+            }
+            uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) sh.warp_counts[warp] = __popc(ballot);
+            __syncthreads();
+            uint32_t offset = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kRecs / 32; ++w) {
+                uint32_t c = sh.warp_counts[w];
+                if ((uint32_t)w < warp) offset += c;
+                total += c;
+            }
+            if (hit) sh.list[offset + __popc(ballot & ((1u << lane) - 1u))] = cand;
+            n_round = total;
+            __syncthreads();
+        } else {
+            n_round = min((uint32_t)kRecs, n_source - base);
+        }
+        if (n_round == 0) continue;  // uniform across the CTA
+        {
+            const uint32_t* ids = direct ? sh.list : sh.list + base;
+            for (uint32_t q = tid; q < n_round * 9u; q += kRasterThreads) {
+                uint32_t r = q / 9u, part = q - r * 9u;
+                reinterpret_cast<uint4*>(&sh.recs[r])[part] = reinterpret_cast<const uint4*>(&p.tris[ids[r]])[part];
+            }
+        }
+        __syncthreads();
+
+        // ---- every pixel walks the staged triangles in order ----
+        if (in_clip) {
+            for (uint32_t r = 0; r < n_round; ++r) {
+                const TriRec& t = sh.recs[r];
+                if (py < t.miny || py > t.maxy) continue;  // warp-uniform (one row per warp)
+                if (px < t.minx || px > t.maxx) continue;
+                long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);
+                long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
+                long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
+                uint32_t bias = t.bias_bits;
+                if (e0 + (long long)(bias & 1u) <= 0 || e1 + (long long)((bias >> 1) & 1u) <= 0 ||
+                    e2 + (long long)((bias >> 2) & 1u) <= 0)
+                    continue;
+                float inv2a = t.inv2a;
+                float l0 = (float)e0 * inv2a, l1 = (float)e1 * inv2a, l2 = (float)e2 * inv2a;  // R6
+                float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+                if (!(z >= p.zclip_lo && z <= p.zclip_hi)) continue;  // R3
+                ++n_covered;
+                if (depth_test && !depth_compare(p.st.depth_compare_op, z, depth)) continue;  // R7: early-Z
+                ++n_passed;
+                if (depth_write) {
+                    depth = z;
+                    depth_dirty = true;
+                }
+                if (!has_color) continue;
+                float src[4];
+                if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                    fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
+                } else {
+                    float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        float num = fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch]));
+                        src[ch] = __fdiv_rn(num, den);
+                    }
+                }
+                color = output_merge(p.st, src, color);
+                color_dirty = true;
+            }
+        }
+        __syncthreads();  // before the next round overwrites recs / list
+    }
+
+    if (color_dirty) *reinterpret_cast<uint32_t*>(caddr) = color;
+    if (depth_dirty) *reinterpret_cast<float*>(daddr) = depth;
+    if (p.stats) {
+        // warp-reduce then one atomic per warp
+        for (int d = 16; d > 0; d >>= 1) {
+            n_covered += __shfl_xor_sync(0xffffffffu, n_covered, d);
+            n_passed += __shfl_xor_sync(0xffffffffu, n_passed, d);
+        }
+        if (lane == 0) {
+            if (n_covered) atomicAdd(&p.stats[4], (unsigned long long)n_covered);
+            if (n_passed) atomicAdd(&p.stats[5], (unsigned long long)n_passed);
+            if (warp == 0) atomicAdd(&p.stats[6], 1ull);
+        }
+    }
+}
+
+}  // namespace
+
+// ---- scratch --------------------------------------------------------------------------------------------------------------
+
+struct KznRasterScratch {
+    TriRec* tris = nullptr;
+    size_t tri_capacity = 0;
+    uint32_t* tile_words = nullptr;  // counts | offsets | cursor
+    size_t tile_capacity = 0;
+    uint32_t* bin_entries = nullptr;
+    size_t bin_capacity = 0;
+    bool attrs_set = false;
+};
+
+void kzn_raster_scratch_destroy(KznRasterScratch* s) {
+    if (!s) return;
+    cudaFree(s->tris);
+    cudaFree(s->tile_words);
+    cudaFree(s->bin_entries);
+    delete s;
+}
+
+namespace {
+
+// Scratch grows monotonically; growth happens before any kernel of this draw is enqueued and the old buffer
+// is freed with cudaFree, which synchronises with work still using it.
+template <typename T>
+KznResult grow(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return KZN_SUCCESS;
+    size_t n = need + need / 2;
+    T* fresh = nullptr;
+    KZN_CUDA(cudaMalloc(&fresh, n * sizeof(T)));
+    if (*ptr) cudaFree(*ptr);
+    *ptr = fresh;
+    *cap = n;
+    return KZN_SUCCESS;
+}
+
+bool finite_host(float f) { return (f - f) == 0.0f; }
+
+KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp, const KznRect2D* sc,
+                     const KznVertexInput* vi, uint32_t* W, uint32_t* H) {
+    KZN_VALID(st && fb && vp && sc && vi, "draw: null argument");
+    KZN_REQUIRE(st->vertex_program == KZN_VS_PASSTHROUGH, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown vertex program %u", st->vertex_program);
+    KZN_REQUIRE(st->fragment_program <= KZN_FS_PROCEDURAL_ORBIT, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown fragment program %u",
+                st->fragment_program);
+    KZN_VALID(st->cull_mode <= 3 && st->front_face <= 1 && st->depth_compare_op <= 7, "draw: bad rasterization / depth state");
+    KZN_REQUIRE(st->src_color_blend_factor <= 9 && st->dst_color_blend_factor <= 9 && st->src_alpha_blend_factor <= 9 &&
+                    st->dst_alpha_blend_factor <= 9,
+                KZN_ERROR_FEATURE_NOT_PRESENT, "draw: blend factor not supported (dualSrcBlend is FALSE, api_impl.rs:883)");
+    KZN_VALID(st->color_blend_op <= 4 && st->alpha_blend_op <= 4, "draw: bad blend op");
+    bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
+    KZN_VALID(has_color || has_depth, "draw: framebuffer has no attachment");
+    if (has_color) {
+        KZN_REQUIRE(fb->color.format == KZN_FORMAT_R8G8B8A8_UNORM, KZN_ERROR_FORMAT_NOT_SUPPORTED, "draw: colour attachment format %u",
+                    fb->color.format);
+        KZN_VALID(fb->color.mip_levels == 1 && fb->color.depth == 1 && fb->color.tiling <= 1, "draw: bad colour attachment");
+        KZN_VALID(fb->color_layer < fb->color.array_layers, "draw: colour layer out of range");
+        KZN_VALID(fb->color.address && fb->color.address % 4 == 0, "draw: colour attachment has no memory");
+        *W = fb->color.width;
+        *H = fb->color.height;
+    }
+    if (has_depth) {
+        KZN_REQUIRE(fb->depth.format == KZN_FORMAT_D32_SFLOAT, KZN_ERROR_FORMAT_NOT_SUPPORTED, "draw: depth attachment format %u",
+                    fb->depth.format);
+        KZN_VALID(fb->depth.mip_levels == 1 && fb->depth.depth == 1 && fb->depth.tiling == 0, "draw: bad depth attachment");
+        KZN_VALID(fb->depth_layer < fb->depth.array_layers, "draw: depth layer out of range");
+        KZN_VALID(fb->depth.address && fb->depth.address % 4 == 0, "draw: depth attachment has no memory");
+        KZN_VALID(!has_color || (fb->depth.width == fb->color.width && fb->depth.height == fb->color.height),
+                  "draw: attachment sizes differ");
+        *W = fb->depth.width;
+        *H = fb->depth.height;
+    }
+    KZN_VALID(!fb->band_y1 || (fb->band_y0 < fb->band_y1 && fb->band_y1 <= *H), "draw: bad band");
+    KZN_VALID(sc->offset.x >= 0 && sc->offset.y >= 0, "draw: negative scissor offset (VUID 00598)");
+    KZN_VALID(vp->width > 0.0f && vp->height != 0.0f && finite_host(vp->height), "draw: bad viewport size");
+    KZN_VALID(vp->minDepth >= 0.0f && vp->minDepth <= 1.0f && vp->maxDepth >= 0.0f && vp->maxDepth <= 1.0f, "draw: bad viewport depth range");
+    KZN_VALID(vi->position_components == 3 || vi->position_components == 4, "draw: position must have 3 or 4 components");
+    KZN_VALID(vi->stride % 4 == 0 && vi->position_offset % 4 == 0 && (vi->color_offset == ~0u || vi->color_offset % 4 == 0),
+              "draw: vertex layout must be 4-byte aligned");
+    KZN_VALID(vi->buffer_address && vi->buffer_address % 4 == 0, "draw: bad vertex buffer address");
+    return KZN_SUCCESS;
+}
+
+void make_clip(const KznFramebuffer* fb, const KznViewport* vp, const KznRect2D* sc, uint32_t W, uint32_t H, DrawParams* p) {
+    float vx0 = vp->x, vx1 = vp->x + vp->width;
+    float vy0 = vp->height < 0.0f ? vp->y + vp->height : vp->y;
+    float vy1 = vp->height < 0.0f ? vp->y : vp->y + vp->height;
+    long long x0 = (long long)ceilf(vx0 - 0.5f), x1 = (long long)floorf(vx1 - 0.5f);
+    long long y0 = (long long)ceilf(vy0 - 0.5f), y1 = (long long)floorf(vy1 - 0.5f);
+    long long sx1 = (long long)sc->offset.x + sc->extent.width - 1, sy1 = (long long)sc->offset.y + sc->extent.height - 1;
+    if (x0 < sc->offset.x) x0 = sc->offset.x;
+    if (y0 < sc->offset.y) y0 = sc->offset.y;
+    if (x1 > sx1) x1 = sx1;
+    if (y1 > sy1) y1 = sy1;
+    long long by0 = fb->band_y1 ? fb->band_y0 : 0, by1 = fb->band_y1 ? fb->band_y1 : H;
+    if (x0 < 0) x0 = 0;
+    if (y0 < by0) y0 = by0;
+    if (x1 > (long long)W - 1) x1 = (long long)W - 1;
+    if (y1 > by1 - 1) y1 = by1 - 1;
+    if (x1 < x0 || y1 < y0) { x0 = y0 = 0; x1 = y1 = -1; }
+    p->cx0 = (int32_t)x0; p->cy0 = (int32_t)y0; p->cx1 = (int32_t)x1; p->cy1 = (int32_t)y1;
+    p->zclip_lo = vp->minDepth < vp->maxDepth ? vp->minDepth : vp->maxDepth;
+    p->zclip_hi = vp->minDepth < vp->maxDepth ? vp->maxDepth : vp->minDepth;
+}
+
+KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp,
+                      const KznRect2D* sc, const KznVertexInput* vi, uint64_t index_base, uint32_t index_type, uint32_t first,
+                      uint32_t count, int32_t vertex_offset, uint32_t instance_count) {
+    KznResult r = kzn_queue_enter(q);
+    if (r) return r;
+    uint32_t W = 0, H = 0;
+    if ((r = check_draw(st, fb, vp, sc, vi, &W, &H))) return r;
+    DrawParams p;
+    memset(&p, 0, sizeof p);
+    make_clip(fb, vp, sc, W, H, &p);
+    uint64_t ntri = count / 3, total = ntri * instance_count;
+    if (total == 0 || p.cx1 < p.cx0) return KZN_SUCCESS;
+    KZN_REQUIRE(total <= 0x7fffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: more than 2^31 triangles in one draw");
+
+    p.vertex_base = vi->buffer_address;
+    p.vertex_size = vi->buffer_size;
+    p.index_base = index_base;
+    p.stride = vi->stride;
+    p.pos_off = vi->position_offset;
+    p.pos_comps = vi->position_components;
+    p.col_off = vi->color_offset;
+    p.index_type = index_type;
+    p.first = first;
+    p.vertex_offset = vertex_offset;
+    p.tris_per_instance = (uint32_t)ntri;
+    p.total_tris = (uint32_t)total;
+    p.st = *st;
+    p.hw = vp->width * 0.5f;
+    p.hh = vp->height * 0.5f;
+    p.ox = vp->x + p.hw;
+    p.oy = vp->y + p.hh;
+    p.dz = vp->maxDepth - vp->minDepth;
+    p.zmin_vp = vp->minDepth;
+    bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
+    if (has_color) {
+        p.color_base = fb->color.address + kzn_slice_pitch(&fb->color) * fb->color_layer;
+        p.color_tiled = fb->color.tiling == KZN_TILING_TILED;
+        p.color_tiles_x = kzn_tiles(fb->color.width);
+    }
+    if (has_depth) p.depth_base = fb->depth.address + kzn_slice_pitch(&fb->depth) * fb->depth_layer;
+    p.fb_w = W;
+    p.fb_h = H;
+    p.inv_fb_w = 1.0f / (float)W;
+    p.inv_fb_h = 1.0f / (float)H;
+    p.tile_x0 = (uint32_t)p.cx0 / kTileW;
+    p.tile_y0 = (uint32_t)p.cy0 / kTileH;
+    p.tiles_x = (uint32_t)p.cx1 / kTileW - p.tile_x0 + 1;
+    p.tiles_y = (uint32_t)p.cy1 / kTileH - p.tile_y0 + 1;
+    KZN_REQUIRE(p.tiles_y <= 65535u, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer taller than 524280 rows");
+    p.stats = reinterpret_cast<unsigned long long*>(q->stats_address);
+
+    if (!q->raster) {
+        q->raster = new (std::nothrow) KznRasterScratch();
+        KZN_REQUIRE(q->raster, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    }
+    KznRasterScratch* s = q->raster;
+    if ((r = grow(&s->tris, &s->tri_capacity, (size_t)total))) return r;
+    p.tris = s->tris;
+    size_t tiles = (size_t)p.tiles_x * p.tiles_y;
+    p.binned = total > kDirectMax;
+    if (p.binned) {
+        if ((r = grow(&s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
+        // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
+        // segment does not fit fall back to walking the whole triangle list (still exact, only slower)
+        size_t want = (size_t)total * 8 + tiles;
+        if (want > 0xfffffff0ull) want = 0xfffffff0ull;
+        if ((r = grow(&s->bin_entries, &s->bin_capacity, want))) return r;
+        p.tile_counts = s->tile_words;
+        p.tile_cursor = s->tile_words + tiles;
+        p.tile_offsets = s->tile_words + 2 * tiles;
+        p.bin_entries = s->bin_entries;
+        p.bin_capacity = (uint32_t)(s->bin_capacity > 0xfffffff0ull ? 0xfffffff0ull : s->bin_capacity);
+    }
+    if (!s->attrs_set) {
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        s->attrs_set = true;
+    }
+
+    setup_kernel<<<(uint32_t)((ntri + 255) / 256), 256, 0, q->stream>>>(p);
+    if ((r = kzn_launched(q, "setup_kernel"))) return r;
+    if (p.binned) {
+        KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
+        uint32_t bin_blocks = (uint32_t)((total * 32 + 255) / 256);
+        uint32_t cap = (uint32_t)q->device->sm_count * 16;
+        if (bin_blocks > cap) bin_blocks = cap;
+        bin_kernel<false><<<bin_blocks, 256, 0, q->stream>>>(p);
+        if ((r = kzn_launched(q, "bin_kernel<count>"))) return r;
+        bin_scan_kernel<<<1, 1024, 0, q->stream>>>(p);
+        if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
+        bin_kernel<true><<<bin_blocks, 256, 0, q->stream>>>(p);
+        if ((r = kzn_launched(q, "bin_kernel<fill>"))) return r;
+    }
+    dim3 grid(p.tiles_x, p.tiles_y);
+    if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT)
+        raster_kernel<KZN_FS_PROCEDURAL_ORBIT><<<grid, kRasterThreads, sizeof(RasterShared), q->stream>>>(p);
+    else
+        raster_kernel<KZN_FS_VERTEX_COLOR><<<grid, kRasterThreads, sizeof(RasterShared), q->stream>>>(p);
+    return kzn_launched(q, "raster_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+KznResult kzn_cmd_draw(KznQueue* queue, const KznGraphicsPipelineState* state, const KznFramebuffer* framebuffer,
+                       const KznViewport* viewport, const KznRect2D* scissor, const KznVertexInput* vertices, uint32_t vertex_count,
+                       uint32_t instance_count, uint32_t first_vertex, uint32_t first_instance) {
+    (void)first_instance;
+    return draw_common(queue, state, framebuffer, viewport, scissor, vertices, 0, 0, first_vertex, vertex_count, 0, instance_count);
+}
+
+KznResult kzn_cmd_draw_indexed(KznQueue* queue, const KznGraphicsPipelineState* state, const KznFramebuffer* framebuffer,
+                               const KznViewport* viewport, const KznRect2D* scissor, const KznVertexInput* vertices,
+                               uint64_t index_buffer_address, uint64_t index_buffer_size, uint32_t index_type, uint32_t index_count,
+                               uint32_t instance_count, uint32_t first_index, int32_t vertex_offset, uint32_t first_instance) {
+    (void)first_instance;
+    KZN_VALID(index_buffer_address && index_type <= KZN_INDEX_TYPE_UINT32, "vkCmdDrawIndexed: bad index buffer");
+    uint64_t isz = index_type == KZN_INDEX_TYPE_UINT16 ? 2 : 4;
+    KZN_VALID(index_buffer_address % isz == 0, "vkCmdDrawIndexed: index buffer misaligned");
+    KZN_VALID(((uint64_t)first_index + index_count) * isz <= index_buffer_size, "vkCmdDrawIndexed: indices outside the index buffer");
+    return draw_common(queue, state, framebuffer, viewport, scissor, vertices, index_buffer_address, index_type, first_index, index_count,
+                       vertex_offset, instance_count);
+}
+
+}  // extern "C"

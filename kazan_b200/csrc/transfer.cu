@@ -1,0 +1,822 @@
+// transfer.cu — the transfer family as HBM-bound sm_100a kernels.
+//
+// Replaces the `unimplemented!()` bodies of (vulkan-driver/src/api_impl.rs):
+//   vkCmdCopyBuffer :4696  vkCmdCopyImage :4707  vkCmdBlitImage :4720  vkCmdCopyBufferToImage :4734
+//   vkCmdCopyImageToBuffer :4746  vkCmdUpdateBuffer :4758  vkCmdFillBuffer :4769
+//   vkCmdClearColorImage :4780  vkCmdClearDepthStencilImage :4792  vkCmdClearAttachments :4804
+// Image addressing follows vulkan-driver/src/image.rs:58-88 (LINEAR: tightly packed) and the
+// 16x16-texel tile layout of SURVEY.md E.10 (TILED).
+//
+// Kernels
+//   fill_contig_kernel   contiguous word fill: 128-bit st.global, grid = k x SM count, grid-stride
+//   fill_bulk_kernel     same job through the TMA engine: the CTA paints 32 KiB of shared memory once,
+//                        then one thread streams it out with cp.async.bulk.global.shared::cta
+//   copy_bulk_kernel     contiguous copy through the TMA engine: cp.async.bulk global->shared (mbarrier
+//                        complete_tx) then shared->global (bulk_group), 4-stage ring per CTA, no registers
+//   box_kernel<...>      general box copy/fill between LINEAR (pitched) and TILED surfaces,
+//                        16-byte vectors when alignment allows, 4-byte texels otherwise
+//   blit_kernel          scaled RGBA8 copy, NEAREST (integer path) or LINEAR (fp32, no contraction)
+// All of them are bandwidth bound; algorithmic bytes per texel are 4 (fill) or 8 (copy).
+#include <stdlib.h>
+#include <string.h>
+
+#include "kzn_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// ---- device helpers -----------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t ld_stream4(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA (bulk async-proxy) copies; SASS: UBLKCP
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- contiguous fill -------------------------------------------------------------------------------
+
+// dst is 4-byte aligned, `words` 32-bit words.  Head/tail words are peeled so the body is 16-byte stores.
+__global__ void __launch_bounds__(kThreads) fill_contig_kernel(uint32_t* __restrict__ dst, uint64_t words, uint32_t value) {
+    uint64_t head = ((16 - ((uintptr_t)dst & 15)) & 15) >> 2;
+    if (head > words) head = words;
+    uint64_t body = (words - head) >> 2;  // uint4 count
+    uint64_t tail = words - head - (body << 2);
+    uint64_t tid = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    if (tid < head) dst[tid] = value;
+    if (tid < tail) dst[head + (body << 2) + tid] = value;
+    uint4* b = reinterpret_cast<uint4*>(dst + head);
+    const uint4 v = make_uint4(value, value, value, value);
+    uint64_t i = tid;
+    for (; i + (kUnroll - 1) * nthreads < body; i += kUnroll * nthreads) {
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) st_stream16(b + i + k * nthreads, v);
+    }
+    for (; i < body; i += nthreads) st_stream16(b + i, v);
+}
+
+constexpr uint32_t kBulkChunk = 32768;  // bytes per TMA bulk operation
+
+// dst 16-byte aligned, bytes a multiple of 16.  One CTA per SM slot; CTA c handles chunks c, c+grid, ...
+__global__ void __launch_bounds__(kThreads) fill_bulk_kernel(uint8_t* __restrict__ dst, uint64_t bytes, uint32_t value) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint4* s4 = reinterpret_cast<uint4*>(smem);
+    const uint4 v = make_uint4(value, value, value, value);
+    for (uint32_t i = threadIdx.x; i < kBulkChunk / 16; i += kThreads) s4[i] = v;
+    fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
+        for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+            uint64_t off = c * kBulkChunk;
+            uint32_t n = (uint32_t)(bytes - off < kBulkChunk ? bytes - off : kBulkChunk);
+            bulk_s2g(dst + off, smem, n);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();  // shared memory must stay live until every bulk read of it is done
+    }
+}
+
+// ---- contiguous copy through TMA ---------------------------------------------------------------------
+
+constexpr int kCopyStages = 4;
+constexpr uint32_t kCopyChunk = 32768;
+
+// src/dst 16-byte aligned, bytes a multiple of 16.  Thread 0 of each CTA drives a 4-stage ring:
+//   wait(stage free: its last store has finished reading smem) -> bulk load (mbarrier tx) ...
+//   wait(load landed) -> bulk store -> commit
+__global__ void __launch_bounds__(32) copy_bulk_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[kCopyStages];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kCopyStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint64_t chunks = (bytes + kCopyChunk - 1) / kCopyChunk;
+    // chunks owned by this CTA: blockIdx.x, +grid, ...
+    uint64_t n_mine = chunks > blockIdx.x ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto chunk_off = [&](uint64_t k) { return (blockIdx.x + k * (uint64_t)gridDim.x) * kCopyChunk; };
+    auto chunk_len = [&](uint64_t off) { return (uint32_t)(bytes - off < kCopyChunk ? bytes - off : kCopyChunk); };
+    // prologue: fill the ring
+    for (uint64_t j = 0; j < n_mine && j < kCopyStages; ++j) {
+        uint64_t off = chunk_off(j);
+        uint32_t n = chunk_len(off);
+        mbar_expect_tx(&full[j], n);
+        bulk_g2s(smem + j * kCopyChunk, src + off, n, &full[j]);
+    }
+    for (uint64_t k = 0; k < n_mine; ++k) {
+        int s = (int)(k % kCopyStages);
+        mbar_wait(&full[s], (uint32_t)((k / kCopyStages) & 1));
+        uint64_t off = chunk_off(k);
+        bulk_s2g(dst + off, smem + s * kCopyChunk, chunk_len(off));
+        bulk_commit();
+        // refill the stage drained one iteration ago: all but the newest store group have finished
+        // reading shared memory after wait_group.read 1
+        uint64_t j = k + kCopyStages - 1;
+        if (k >= 1 && j < n_mine) {
+            bulk_wait_read<1>();
+            int sj = (int)(j % kCopyStages);
+            uint64_t off2 = chunk_off(j);
+            uint32_t n2 = chunk_len(off2);
+            mbar_expect_tx(&full[sj], n2);
+            bulk_g2s(smem + sj * kCopyChunk, src + off2, n2, &full[sj]);
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ---- general box copy / fill ----------------------------------------------------------------------------
+
+struct Surf {
+    unsigned long long base;         // byte address of (x=0,y=0) of the box's first slice
+    unsigned long long row_pitch;    // bytes, LINEAR
+    unsigned long long slice_pitch;  // bytes
+    uint32_t x0, y0;                 // TILED: box origin in texels (LINEAR folds it into base)
+    uint32_t tiles_x;                // TILED
+};
+
+template <bool TILED>
+__device__ __forceinline__ unsigned long long surf_addr(const Surf& s, uint32_t x, uint32_t y, uint32_t slice) {
+    if (TILED) {
+        uint32_t X = s.x0 + x, Y = s.y0 + y;
+        unsigned long long tile = (unsigned long long)(Y >> 4) * s.tiles_x + (X >> 4);
+        return s.base + slice * s.slice_pitch + ((tile << 8) + ((Y & 15u) << 4) + (X & 15u)) * 4ull;
+    }
+    return s.base + slice * s.slice_pitch + y * s.row_pitch + x * 4ull;
+}
+
+struct BoxParams {
+    Surf src, dst;
+    uint32_t wv;      // items per row (texels / VEC)
+    uint32_t h;       // rows per slice
+    uint32_t slices;
+    uint32_t fill_value;
+    unsigned long long total;  // wv*h*slices
+};
+
+template <int VEC, bool SRC_TILED, bool DST_TILED, bool FILL>
+__global__ void __launch_bounds__(kThreads) box_kernel(const __grid_constant__ BoxParams p) {
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * kThreads;
+    unsigned long long i0 = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    const bool narrow = p.total <= 0xffffffffull;
+    for (; i0 < p.total; i0 += kUnroll * nthreads) {
+        unsigned long long sa[kUnroll], da[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned long long i = i0 + k * nthreads;
+            ok[k] = i < p.total;
+            uint32_t xv, y, s;
+            if (p.h == 1 && p.slices == 1) {
+                // collapsed contiguous run: wv may exceed 32 bits of bytes, keep 64-bit x
+                sa[k] = p.src.base + i * (4ull * VEC);
+                da[k] = p.dst.base + i * (4ull * VEC);
+                continue;
+            }
+            if (narrow) {
+                uint32_t ii = (uint32_t)i;
+                uint32_t row = ii / p.wv;
+                xv = ii - row * p.wv;
+                s = row / p.h;
+                y = row - s * p.h;
+            } else {
+                unsigned long long row = i / p.wv;
+                xv = (uint32_t)(i - row * p.wv);
+                s = (uint32_t)(row / p.h);
+                y = (uint32_t)(row - (unsigned long long)s * p.h);
+            }
+            if (!FILL) sa[k] = surf_addr<SRC_TILED>(p.src, xv * VEC, y, s);
+            da[k] = surf_addr<DST_TILED>(p.dst, xv * VEC, y, s);
+        }
+        if (VEC == 4) {
+            uint4 v[kUnroll];
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k) {
+                if (FILL) v[k] = make_uint4(p.fill_value, p.fill_value, p.fill_value, p.fill_value);
+                else if (ok[k]) v[k] = ld_stream16((const void*)sa[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k)
+                if (ok[k]) st_stream16((void*)da[k], v[k]);
+        } else {
+            uint32_t v[kUnroll];
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k) {
+                if (FILL) v[k] = p.fill_value;
+                else if (ok[k]) v[k] = ld_stream4((const void*)sa[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k)
+                if (ok[k]) st_stream4((void*)da[k], v[k]);
+        }
+    }
+}
+
+// ---- blit ------------------------------------------------------------------------------
+
+struct BlitParams {
+    Surf src, dst;  // whole image surfaces: base = image address (+ layer), x0=y0=0
+    uint32_t src_tiled, dst_tiled;
+    int32_t src_w, src_h;
+    int32_t dx0, dx1, dy0, dy1;  // destination box corners as given (may be reversed)
+    int32_t sx0, sx1, sy0, sy1;  // source box corners as given
+    int32_t x_lo, y_lo;          // min corner of the destination box
+    uint32_t w, h;               // destination box size
+    uint32_t filter;
+};
+
+__device__ __forceinline__ float blit_coord(int32_t i, int32_t d0, int32_t d1, int32_t s0, int32_t s1) {
+    float scale = __fdiv_rn((float)(s1 - s0), (float)(d1 - d0));
+    return __fmaf_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), (float)d0), scale, (float)s0);
+}
+__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ unsigned long long surf_addr_rt(const Surf& s, uint32_t tiled, uint32_t x, uint32_t y) {
+    return tiled ? surf_addr<true>(s, x, y, 0) : surf_addr<false>(s, x, y, 0);
+}
+__device__ __forceinline__ float unorm8_to_float(uint32_t u) { return __fdiv_rn((float)u, 255.0f); }
+__device__ __forceinline__ uint32_t float_to_unorm8(float f) {
+    // E.1: NaN -> 0, clamp, single multiply, round to nearest even
+    return __float2uint_rn(__fmul_rn(__saturatef(f), 255.0f));
+}
+
+__global__ void __launch_bounds__(kThreads) blit_kernel(const __grid_constant__ BlitParams p) {
+    uint32_t i = blockIdx.x * 32u + (threadIdx.x & 31u);
+    uint32_t j = blockIdx.y * (kThreads / 32) + (threadIdx.x >> 5);
+    if (i >= p.w || j >= p.h) return;
+    int32_t dx = p.x_lo + (int32_t)i, dy = p.y_lo + (int32_t)j;
+    float u = blit_coord(dx, p.dx0, p.dx1, p.sx0, p.sx1);
+    float v = blit_coord(dy, p.dy0, p.dy1, p.sy0, p.sy1);
+    uint32_t out;
+    if (p.filter == KZN_FILTER_NEAREST) {
+        int32_t sx = clampi((int32_t)floorf(u), 0, p.src_w - 1);
+        int32_t sy = clampi((int32_t)floorf(v), 0, p.src_h - 1);
+        out = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, sx, sy);
+    } else {
+        float uu = __fsub_rn(u, 0.5f), vv = __fsub_rn(v, 0.5f);
+        float fu = floorf(uu), fv = floorf(vv);
+        float a = __fsub_rn(uu, fu), b = __fsub_rn(vv, fv);
+        int32_t x0 = clampi((int32_t)fu, 0, p.src_w - 1), x1 = clampi((int32_t)fu + 1, 0, p.src_w - 1);
+        int32_t y0 = clampi((int32_t)fv, 0, p.src_h - 1), y1 = clampi((int32_t)fv + 1, 0, p.src_h - 1);
+        uint32_t t00 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x0, y0);
+        uint32_t t10 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x1, y0);
+        uint32_t t01 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x0, y1);
+        uint32_t t11 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x1, y1);
+        float na = __fsub_rn(1.0f, a), nb = __fsub_rn(1.0f, b);
+        float w00 = __fmul_rn(na, nb), w10 = __fmul_rn(a, nb), w01 = __fmul_rn(na, b), w11 = __fmul_rn(a, b);
+        out = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float acc = __fmul_rn(w00, unorm8_to_float((t00 >> (8 * ch)) & 255u));
+            acc = __fadd_rn(acc, __fmul_rn(w10, unorm8_to_float((t10 >> (8 * ch)) & 255u)));
+            acc = __fadd_rn(acc, __fmul_rn(w01, unorm8_to_float((t01 >> (8 * ch)) & 255u)));
+            acc = __fadd_rn(acc, __fmul_rn(w11, unorm8_to_float((t11 >> (8 * ch)) & 255u)));
+            out |= float_to_unorm8(acc) << (8 * ch);
+        }
+    }
+    *(uint32_t*)surf_addr_rt(p.dst, p.dst_tiled, dx, dy) = out;
+}
+
+// ---- host-side launch logic ------------------------------------------------------------------------------
+
+enum class Path { Auto, LdSt, Tma };
+Path transfer_path() {
+    static Path p = [] {
+        const char* e = getenv("KZN_TRANSFER_PATH");
+        if (e && !strcmp(e, "ldst")) return Path::LdSt;
+        if (e && !strcmp(e, "tma")) return Path::Tma;
+        return Path::Auto;
+    }();
+    return p;
+}
+
+int grid_for(const KznQueue* q, unsigned long long items) {
+    unsigned long long blocks = (items + (unsigned long long)kThreads * kUnroll - 1) / ((unsigned long long)kThreads * kUnroll);
+    unsigned long long cap = (unsigned long long)q->device->sm_count * 8;  // multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    return blocks ? (int)blocks : 1;
+}
+
+KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint32_t value) {
+    if (bytes == 0) return KZN_SUCCESS;
+    bool aligned = (address % 16 == 0) && (bytes % 16 == 0);
+    Path path = transfer_path();
+    bool tma = aligned && (path == Path::Tma || (path == Path::Auto && bytes >= (64ull << 20)));
+    if (tma) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            KZN_CUDA(cudaFuncSetAttribute(fill_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkChunk));
+            attr_set = true;
+        }
+        uint64_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
+        uint64_t cap = (uint64_t)q->device->sm_count * 4;
+        int grid = (int)(chunks < cap ? chunks : cap);
+        fill_bulk_kernel<<<grid, kThreads, kBulkChunk, q->stream>>>((uint8_t*)(uintptr_t)address, bytes, value);
+        return kzn_launched(q, "fill_bulk_kernel");
+    }
+    uint64_t words = bytes / 4;
+    fill_contig_kernel<<<grid_for(q, words / 4 + 1), kThreads, 0, q->stream>>>((uint32_t*)(uintptr_t)address, words, value);
+    return kzn_launched(q, "fill_contig_kernel");
+}
+
+KznResult launch_copy_bulk(KznQueue* q, uint64_t dst, uint64_t src, uint64_t bytes) {
+    static bool attr_set = false;
+    const int smem = kCopyStages * kCopyChunk;
+    if (!attr_set) {
+        KZN_CUDA(cudaFuncSetAttribute(copy_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    uint64_t chunks = (bytes + kCopyChunk - 1) / kCopyChunk;
+    uint64_t cap = q->device->sm_count;  // one 128 KiB ring per SM
+    int grid = (int)(chunks < cap ? chunks : cap);
+    copy_bulk_kernel<<<grid, 32, smem, q->stream>>>((uint8_t*)(uintptr_t)dst, (const uint8_t*)(uintptr_t)src, bytes);
+    return kzn_launched(q, "copy_bulk_kernel");
+}
+
+struct Box {
+    // one side of a box transfer, before lowering to Surf
+    uint64_t base;         // surface origin (image address or buffer address + bufferOffset)
+    bool tiled;
+    uint64_t row_pitch;    // LINEAR bytes
+    uint64_t slice_pitch;  // bytes
+    uint32_t x0, y0;       // texel origin inside the surface
+    uint64_t slice0;
+    uint32_t tiles_x;
+};
+
+Surf lower(const Box& b) {
+    Surf s;
+    s.slice_pitch = b.slice_pitch;
+    s.row_pitch = b.row_pitch;
+    s.tiles_x = b.tiles_x;
+    if (b.tiled) {
+        s.base = b.base + b.slice0 * b.slice_pitch;
+        s.x0 = b.x0;
+        s.y0 = b.y0;
+    } else {
+        s.base = b.base + b.slice0 * b.slice_pitch + (uint64_t)b.y0 * b.row_pitch + (uint64_t)b.x0 * 4;
+        s.x0 = s.y0 = 0;
+    }
+    return s;
+}
+
+bool vec4_ok(const Box& b, const Surf& s, uint32_t w) {
+    if (w % 4) return false;
+    if (s.base % 16 || s.slice_pitch % 16) return false;
+    if (b.tiled) return b.x0 % 4 == 0;
+    return s.row_pitch % 16 == 0;
+}
+
+template <int VEC, bool FILL>
+KznResult launch_box_t(KznQueue* q, const BoxParams& p, bool st, bool dt) {
+    int grid = grid_for(q, p.total);
+#define KZN_BOX(ST, DT)                                                          \
+    box_kernel<VEC, ST, DT, FILL><<<grid, kThreads, 0, q->stream>>>(p);           \
+    return kzn_launched(q, "box_kernel");
+    if (st && dt) { KZN_BOX(true, true) }
+    if (st) { KZN_BOX(true, false) }
+    if (dt) { KZN_BOX(false, true) }
+    KZN_BOX(false, false)
+#undef KZN_BOX
+}
+
+// copy (fill == false) or fill a w x h x slices box
+KznResult launch_box(KznQueue* q, const Box* src, const Box& dst, uint32_t w, uint32_t h, uint32_t slices,
+                     bool fill, uint32_t fill_value) {
+    if (!w || !h || !slices) return KZN_SUCCESS;
+    BoxParams p;
+    memset(&p, 0, sizeof p);
+    p.dst = lower(dst);
+    bool st = false, dt = dst.tiled;
+    bool v4 = vec4_ok(dst, p.dst, w);
+    if (!fill) {
+        p.src = lower(*src);
+        st = src->tiled;
+        v4 = v4 && vec4_ok(*src, p.src, w);
+    }
+    uint64_t wt = w;  // texels per row after collapsing
+    uint32_t hh = h, ss = slices;
+    if (!st && !dt) {
+        // collapse contiguous rows / slices into longer runs
+        uint64_t row_bytes = (uint64_t)w * 4;
+        bool rows_contig = hh == 1 || (p.dst.row_pitch == row_bytes && (fill || p.src.row_pitch == row_bytes));
+        if (rows_contig && hh > 1) {
+            wt *= hh;
+            hh = 1;
+        }
+        if (hh == 1) {
+            uint64_t run_bytes = wt * 4;
+            bool slices_contig = ss == 1 || (p.dst.slice_pitch == run_bytes && (fill || p.src.slice_pitch == run_bytes));
+            if (slices_contig && ss > 1) {
+                wt *= ss;
+                ss = 1;
+            }
+        }
+        if (hh == 1 && ss == 1) {
+            // one contiguous run
+            uint64_t bytes = wt * 4;
+            if (fill) return launch_fill_contig(q, p.dst.base, bytes, fill_value);
+            Path path = transfer_path();
+            bool aligned = p.dst.base % 16 == 0 && p.src.base % 16 == 0 && bytes % 16 == 0;
+            if (aligned && path == Path::Tma) return launch_copy_bulk(q, p.dst.base, p.src.base, bytes);
+        }
+    }
+    p.h = hh;
+    p.slices = ss;
+    p.fill_value = fill_value;
+    if (v4) {
+        KZN_REQUIRE(wt / 4 <= 0xffffffffull || (hh == 1 && ss == 1), KZN_ERROR_FEATURE_NOT_PRESENT, "row too long");
+        p.wv = (uint32_t)((wt / 4) & 0xffffffffull);
+        p.total = (wt / 4) * hh * ss;
+        return fill ? launch_box_t<4, true>(q, p, st, dt) : launch_box_t<4, false>(q, p, st, dt);
+    }
+    KZN_REQUIRE(wt <= 0xffffffffull || (hh == 1 && ss == 1), KZN_ERROR_FEATURE_NOT_PRESENT, "row too long");
+    p.wv = (uint32_t)(wt & 0xffffffffull);
+    p.total = wt * hh * ss;
+    return fill ? launch_box_t<1, true>(q, p, st, dt) : launch_box_t<1, false>(q, p, st, dt);
+}
+
+Box image_box(const KznImageDesc* im, int32_t x, int32_t y, int32_t z, uint32_t base_layer) {
+    Box b;
+    b.base = im->address;
+    b.tiled = im->tiling == KZN_TILING_TILED;
+    b.row_pitch = kzn_row_pitch(im);
+    b.slice_pitch = kzn_slice_pitch(im);
+    b.x0 = (uint32_t)x;
+    b.y0 = (uint32_t)y;
+    b.slice0 = (uint64_t)z + (uint64_t)im->depth * base_layer;
+    b.tiles_x = kzn_tiles(im->width);
+    return b;
+}
+
+uint32_t aspect_of(uint32_t format) {
+    return format == KZN_FORMAT_D32_SFLOAT ? KZN_IMAGE_ASPECT_DEPTH_BIT : KZN_IMAGE_ASPECT_COLOR_BIT;
+}
+
+KznResult resolve_range(const KznImageDesc* im, const KznImageSubresourceRange* r, uint32_t aspect, uint32_t* l0, uint32_t* n) {
+    KZN_VALID(r->aspectMask == aspect, "clear: aspectMask %#x must be %#x (VUID 02498)", r->aspectMask, aspect);
+    KZN_VALID(r->baseMipLevel == 0, "clear: baseMipLevel %u out of range (mip_levels is 1)", r->baseMipLevel);
+    KZN_VALID(r->levelCount == KZN_REMAINING_MIP_LEVELS || r->levelCount == 1, "clear: levelCount %u out of range", r->levelCount);
+    KZN_VALID(r->baseArrayLayer < im->array_layers, "clear: baseArrayLayer %u out of range", r->baseArrayLayer);
+    uint32_t cnt = r->layerCount == KZN_REMAINING_ARRAY_LAYERS ? im->array_layers - r->baseArrayLayer : r->layerCount;
+    KZN_VALID(cnt != 0 && cnt <= im->array_layers - r->baseArrayLayer, "clear: layerCount %u out of range", r->layerCount);
+    *l0 = r->baseArrayLayer;
+    *n = cnt;
+    return KZN_SUCCESS;
+}
+
+KznResult clear_image(KznQueue* q, const KznImageDesc* im, uint32_t word, uint32_t aspect, uint32_t range_count,
+                      const KznImageSubresourceRange* ranges) {
+    for (uint32_t i = 0; i < range_count; ++i) {
+        uint32_t l0, n;
+        KznResult r = resolve_range(im, &ranges[i], aspect, &l0, &n);
+        if (r) return r;
+    }
+    uint64_t layer_pitch = kzn_slice_pitch(im) * im->depth;
+    for (uint32_t i = 0; i < range_count; ++i) {
+        uint32_t l0 = 0, n = 0;
+        resolve_range(im, &ranges[i], aspect, &l0, &n);
+        // whole layers are contiguous in both layouts (E.2; TILED padding texels are written too)
+        KznResult r = launch_fill_contig(q, im->address + layer_pitch * l0, layer_pitch * n, word);
+        if (r) return r;
+    }
+    return KZN_SUCCESS;
+}
+
+KznResult check_subresource_box(const KznImageDesc* im, const KznImageSubresourceLayers* s, const KznOffset3D* off,
+                                const KznExtent3D* ext, const char* what) {
+    KZN_VALID(s->aspectMask == aspect_of(im->format), "%s: aspectMask %#x does not match the format (VUID 00212)", what, s->aspectMask);
+    KZN_VALID(s->mipLevel == 0, "%s: mipLevel %u out of range", what, s->mipLevel);
+    KZN_VALID(s->layerCount != 0 && (uint64_t)s->baseArrayLayer + s->layerCount <= im->array_layers, "%s: layers out of range", what);
+    KZN_VALID(off->x >= 0 && off->y >= 0 && off->z >= 0, "%s: negative image offset", what);
+    KZN_VALID((uint64_t)off->x + ext->width <= im->width, "%s: x range outside the image (VUID 00197)", what);
+    KZN_VALID((uint64_t)off->y + ext->height <= im->height, "%s: y range outside the image (VUID 00198)", what);
+    KZN_VALID((uint64_t)off->z + ext->depth <= im->depth, "%s: z range outside the image (VUID 00200)", what);
+    KZN_VALID(!(im->depth > 1 && (s->baseArrayLayer != 0 || s->layerCount != 1)), "%s: 3D images have one layer", what);
+    return KZN_SUCCESS;
+}
+
+KznResult check_buffer_image_region(const KznImageDesc* im, uint64_t buffer_size, const KznBufferImageCopy* c, const char* what) {
+    KznResult r = check_subresource_box(im, &c->imageSubresource, &c->imageOffset, &c->imageExtent, what);
+    if (r) return r;
+    uint64_t ts = kzn_texel_size(im->format);
+    KZN_VALID(c->bufferOffset % 4 == 0 && c->bufferOffset % ts == 0, "%s: bufferOffset %llu not a multiple of 4 (VUID 00194)", what,
+              (unsigned long long)c->bufferOffset);
+    KZN_VALID(!c->bufferRowLength || c->bufferRowLength >= c->imageExtent.width, "%s: bufferRowLength < width (VUID 00195)", what);
+    KZN_VALID(!c->bufferImageHeight || c->bufferImageHeight >= c->imageExtent.height, "%s: bufferImageHeight < height (VUID 00196)", what);
+    uint64_t w = c->imageExtent.width, h = c->imageExtent.height;
+    uint64_t slices = (uint64_t)c->imageExtent.depth * c->imageSubresource.layerCount;
+    if (w && h && slices) {
+        uint64_t row_len = c->bufferRowLength ? c->bufferRowLength : w;
+        uint64_t img_h = c->bufferImageHeight ? c->bufferImageHeight : h;
+        uint64_t end = c->bufferOffset + ((((slices - 1) * img_h) + (h - 1)) * row_len + w) * ts;
+        KZN_VALID(end <= buffer_size, "%s: region needs %llu bytes, buffer has %llu (VUID 00171)", what,
+                  (unsigned long long)end, (unsigned long long)buffer_size);
+    }
+    return KZN_SUCCESS;
+}
+
+Box buffer_box(uint64_t buffer_address, const KznBufferImageCopy* c) {
+    uint64_t row_len = c->bufferRowLength ? c->bufferRowLength : c->imageExtent.width;
+    uint64_t img_h = c->bufferImageHeight ? c->bufferImageHeight : c->imageExtent.height;
+    Box b;
+    b.base = buffer_address + c->bufferOffset;
+    b.tiled = false;
+    b.row_pitch = row_len * 4;
+    b.slice_pitch = row_len * img_h * 4;
+    b.x0 = b.y0 = 0;
+    b.slice0 = 0;
+    b.tiles_x = 0;
+    return b;
+}
+
+KznResult copy_buffer_image(KznQueue* q, uint64_t buffer_address, uint64_t buffer_size, const KznImageDesc* im,
+                            uint32_t region_count, const KznBufferImageCopy* regions, bool to_image, const char* what) {
+    KznResult r = kzn_queue_enter(q);
+    if (r) return r;
+    if ((r = kzn_check_image(im, what))) return r;
+    KZN_VALID(buffer_address && buffer_address % 4 == 0, "%s: buffer address must be 4-byte aligned", what);
+    KZN_VALID(region_count && regions, "%s: regionCount must be > 0", what);
+    for (uint32_t i = 0; i < region_count; ++i)
+        if ((r = check_buffer_image_region(im, buffer_size, &regions[i], what))) return r;
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznBufferImageCopy* c = &regions[i];
+        Box ib = image_box(im, c->imageOffset.x, c->imageOffset.y, c->imageOffset.z, c->imageSubresource.baseArrayLayer);
+        Box bb = buffer_box(buffer_address, c);
+        uint32_t slices = c->imageExtent.depth * c->imageSubresource.layerCount;
+        r = to_image ? launch_box(q, &bb, ib, c->imageExtent.width, c->imageExtent.height, slices, false, 0)
+                     : launch_box(q, &ib, bb, c->imageExtent.width, c->imageExtent.height, slices, false, 0);
+        if (r) return r;
+    }
+    return KZN_SUCCESS;
+}
+
+}  // namespace
+
+// ---- C ABI ----------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+KznResult kzn_cmd_clear_color_image(KznQueue* queue, const KznImageDesc* image, const KznClearColorValue* color,
+                                    uint32_t range_count, const KznImageSubresourceRange* ranges) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(image, "vkCmdClearColorImage"))) return r;
+    KZN_REQUIRE(image->format == KZN_FORMAT_R8G8B8A8_UNORM, KZN_ERROR_FORMAT_NOT_SUPPORTED,
+                "vkCmdClearColorImage: format %u is not a colour format (VUID 00007)", image->format);
+    KZN_VALID(color && range_count && ranges, "vkCmdClearColorImage: null argument or rangeCount == 0");
+    return clear_image(queue, image, kzn_pack_rgba8_host(color->float32), KZN_IMAGE_ASPECT_COLOR_BIT, range_count, ranges);
+}
+
+KznResult kzn_cmd_clear_depth_stencil_image(KznQueue* queue, const KznImageDesc* image, const KznClearDepthStencilValue* value,
+                                            uint32_t range_count, const KznImageSubresourceRange* ranges) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(image, "vkCmdClearDepthStencilImage"))) return r;
+    KZN_REQUIRE(image->format == KZN_FORMAT_D32_SFLOAT, KZN_ERROR_FORMAT_NOT_SUPPORTED,
+                "vkCmdClearDepthStencilImage: format %u is not a depth format", image->format);
+    KZN_VALID(value && range_count && ranges, "vkCmdClearDepthStencilImage: null argument or rangeCount == 0");
+    uint32_t word;
+    memcpy(&word, &value->depth, 4);
+    return clear_image(queue, image, word, KZN_IMAGE_ASPECT_DEPTH_BIT, range_count, ranges);
+}
+
+KznResult kzn_cmd_clear_attachment(KznQueue* queue, const KznImageDesc* image, const KznClearColorValue* v,
+                                   uint32_t rect_count, const KznClearRect* rects) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(image, "vkCmdClearAttachments"))) return r;
+    KZN_VALID(v && rect_count && rects, "vkCmdClearAttachments: null argument or rectCount == 0");
+    KZN_VALID(image->depth == 1, "vkCmdClearAttachments: attachment must be 2D");
+    uint32_t word = image->format == KZN_FORMAT_R8G8B8A8_UNORM ? kzn_pack_rgba8_host(v->float32) : v->uint32[0];
+    for (uint32_t i = 0; i < rect_count; ++i) {
+        const KznClearRect* c = &rects[i];
+        KZN_VALID(c->rect.offset.x >= 0 && c->rect.offset.y >= 0, "vkCmdClearAttachments: negative rect offset");
+        KZN_VALID((uint64_t)c->rect.offset.x + c->rect.extent.width <= image->width, "vkCmdClearAttachments: rect outside attachment");
+        KZN_VALID((uint64_t)c->rect.offset.y + c->rect.extent.height <= image->height, "vkCmdClearAttachments: rect outside attachment");
+        KZN_VALID(c->layerCount != 0 && (uint64_t)c->baseArrayLayer + c->layerCount <= image->array_layers,
+                  "vkCmdClearAttachments: layers out of range");
+    }
+    for (uint32_t i = 0; i < rect_count; ++i) {
+        const KznClearRect* c = &rects[i];
+        Box b = image_box(image, c->rect.offset.x, c->rect.offset.y, 0, c->baseArrayLayer);
+        if ((r = launch_box(queue, nullptr, b, c->rect.extent.width, c->rect.extent.height, c->layerCount, true, word))) return r;
+    }
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_copy_buffer_to_image(KznQueue* queue, uint64_t buffer_address, uint64_t buffer_size, const KznImageDesc* image,
+                                       uint32_t region_count, const KznBufferImageCopy* regions) {
+    return copy_buffer_image(queue, buffer_address, buffer_size, image, region_count, regions, true, "vkCmdCopyBufferToImage");
+}
+
+KznResult kzn_cmd_copy_image_to_buffer(KznQueue* queue, const KznImageDesc* image, uint64_t buffer_address, uint64_t buffer_size,
+                                       uint32_t region_count, const KznBufferImageCopy* regions) {
+    return copy_buffer_image(queue, buffer_address, buffer_size, image, region_count, regions, false, "vkCmdCopyImageToBuffer");
+}
+
+KznResult kzn_cmd_copy_buffer(KznQueue* queue, uint64_t src_address, uint64_t src_size, uint64_t dst_address, uint64_t dst_size,
+                              uint32_t region_count, const KznBufferCopy* regions) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(src_address && dst_address && region_count && regions, "vkCmdCopyBuffer: null argument or regionCount == 0");
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznBufferCopy* c = &regions[i];
+        KZN_VALID(c->size != 0, "vkCmdCopyBuffer: region size must be > 0 (VUID 01988)");
+        KZN_VALID(c->srcOffset <= src_size && c->size <= src_size - c->srcOffset, "vkCmdCopyBuffer: source range outside the buffer");
+        KZN_VALID(c->dstOffset <= dst_size && c->size <= dst_size - c->dstOffset, "vkCmdCopyBuffer: destination range outside the buffer");
+    }
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznBufferCopy* c = &regions[i];
+        uint64_t s = src_address + c->srcOffset, d = dst_address + c->dstOffset;
+        if (s % 4 == 0 && d % 4 == 0 && c->size % 4 == 0) {
+            Box sb = {s, false, c->size, c->size, 0, 0, 0, 0}, db = {d, false, c->size, c->size, 0, 0, 0, 0};
+            // a buffer is a 1-row box of size/4 "texels"
+            uint64_t texels = c->size / 4;
+            KZN_REQUIRE(texels <= 0xffffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "vkCmdCopyBuffer: region larger than 16 GiB");
+            if ((r = launch_box(queue, &sb, db, (uint32_t)texels, 1, 1, false, 0))) return r;
+        } else {
+            // byte-granular regions are legal for vkCmdCopyBuffer: the copy engine handles them
+            KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)d, (const void*)(uintptr_t)s, c->size, cudaMemcpyDeviceToDevice, queue->stream));
+        }
+    }
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_fill_buffer(KznQueue* queue, uint64_t dst_address, uint64_t dst_size, uint64_t offset, uint64_t size, uint32_t data) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(dst_address && dst_address % 4 == 0, "vkCmdFillBuffer: bad buffer address");
+    KZN_VALID(offset < dst_size && offset % 4 == 0, "vkCmdFillBuffer: dstOffset must be < size and a multiple of 4 (VUID 00024/00025)");
+    if (size == KZN_WHOLE_SIZE) size = (dst_size - offset) & ~3ull;
+    else KZN_VALID(size != 0 && size % 4 == 0 && size <= dst_size - offset, "vkCmdFillBuffer: bad size (VUID 00026-00028)");
+    return launch_fill_contig(queue, dst_address + offset, size, data);
+}
+
+KznResult kzn_cmd_update_buffer(KznQueue* queue, uint64_t dst_address, uint64_t dst_size, uint64_t offset, uint64_t size, const void* data) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(dst_address && data, "vkCmdUpdateBuffer: null argument");
+    KZN_VALID(offset % 4 == 0 && size % 4 == 0 && size != 0 && size <= 65536, "vkCmdUpdateBuffer: dstOffset/dataSize rules (VUID 00036-00038)");
+    KZN_VALID(offset < dst_size && size <= dst_size - offset, "vkCmdUpdateBuffer: range outside the buffer");
+    // pageable source: the runtime stages it before returning, which is the "captured at record time" rule
+    KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)(dst_address + offset), data, size, cudaMemcpyHostToDevice, queue->stream));
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_copy_image(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst, uint32_t region_count, const KznImageCopy* regions) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(src, "vkCmdCopyImage(src)")) || (r = kzn_check_image(dst, "vkCmdCopyImage(dst)"))) return r;
+    KZN_VALID(region_count && regions, "vkCmdCopyImage: regionCount must be > 0");
+    KZN_VALID(kzn_texel_size(src->format) == kzn_texel_size(dst->format), "vkCmdCopyImage: formats are not size-compatible");
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznImageCopy* c = &regions[i];
+        if ((r = check_subresource_box(src, &c->srcSubresource, &c->srcOffset, &c->extent, "vkCmdCopyImage(src)"))) return r;
+        if ((r = check_subresource_box(dst, &c->dstSubresource, &c->dstOffset, &c->extent, "vkCmdCopyImage(dst)"))) return r;
+        KZN_VALID(c->srcSubresource.layerCount == c->dstSubresource.layerCount, "vkCmdCopyImage: layerCount mismatch");
+    }
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznImageCopy* c = &regions[i];
+        Box sb = image_box(src, c->srcOffset.x, c->srcOffset.y, c->srcOffset.z, c->srcSubresource.baseArrayLayer);
+        Box db = image_box(dst, c->dstOffset.x, c->dstOffset.y, c->dstOffset.z, c->dstSubresource.baseArrayLayer);
+        if ((r = launch_box(queue, &sb, db, c->extent.width, c->extent.height, c->extent.depth * c->srcSubresource.layerCount, false, 0))) return r;
+    }
+    return KZN_SUCCESS;
+}
+
+static KznResult check_blit_box(const KznImageDesc* im, const KznImageSubresourceLayers* s, const KznOffset3D o[2], const char* what) {
+    KZN_VALID(s->aspectMask == KZN_IMAGE_ASPECT_COLOR_BIT && s->mipLevel == 0, "%s: bad subresource", what);
+    KZN_VALID(s->layerCount != 0 && (uint64_t)s->baseArrayLayer + s->layerCount <= im->array_layers, "%s: layers out of range", what);
+    for (int k = 0; k < 2; ++k) {
+        KZN_VALID(o[k].x >= 0 && (uint32_t)o[k].x <= im->width, "%s: x offset outside [0,width] (VUID 00243)", what);
+        KZN_VALID(o[k].y >= 0 && (uint32_t)o[k].y <= im->height, "%s: y offset outside [0,height] (VUID 00244)", what);
+        KZN_VALID(o[k].z >= 0 && (uint32_t)o[k].z <= im->depth, "%s: z offset outside [0,depth] (VUID 00246)", what);
+    }
+    KZN_VALID(!(im->depth > 1 && (s->baseArrayLayer != 0 || s->layerCount != 1)), "%s: 3D images have one layer", what);
+    return KZN_SUCCESS;
+}
+
+static float blit_coord_host(int32_t i, int32_t d0, int32_t d1, int32_t s0, int32_t s1) {
+    float scale = (float)(s1 - s0) / (float)(d1 - d0);
+    return __builtin_fmaf(((float)i + 0.5f) - (float)d0, scale, (float)s0);
+}
+
+KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst, uint32_t region_count,
+                             const KznImageBlit* regions, uint32_t filter) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(src, "vkCmdBlitImage(src)")) || (r = kzn_check_image(dst, "vkCmdBlitImage(dst)"))) return r;
+    KZN_REQUIRE(src->format == KZN_FORMAT_R8G8B8A8_UNORM && dst->format == KZN_FORMAT_R8G8B8A8_UNORM, KZN_ERROR_FORMAT_NOT_SUPPORTED,
+                "vkCmdBlitImage: only R8G8B8A8_UNORM has BLIT_SRC/BLIT_DST features (VUID 01999/02000)");
+    KZN_VALID(region_count && regions && filter <= KZN_FILTER_LINEAR, "vkCmdBlitImage: bad argument");
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznImageBlit* b = &regions[i];
+        if ((r = check_blit_box(src, &b->srcSubresource, b->srcOffsets, "vkCmdBlitImage(src)"))) return r;
+        if ((r = check_blit_box(dst, &b->dstSubresource, b->dstOffsets, "vkCmdBlitImage(dst)"))) return r;
+        KZN_VALID(b->srcSubresource.layerCount == b->dstSubresource.layerCount, "vkCmdBlitImage: layerCount mismatch");
+    }
+    for (uint32_t i = 0; i < region_count; ++i) {
+        const KznImageBlit* b = &regions[i];
+        const KznOffset3D *s0 = &b->srcOffsets[0], *s1 = &b->srcOffsets[1], *d0 = &b->dstOffsets[0], *d1 = &b->dstOffsets[1];
+        if (d0->x == d1->x || d0->y == d1->y || d0->z == d1->z) continue;
+        BlitParams p;
+        memset(&p, 0, sizeof p);
+        p.src_tiled = src->tiling == KZN_TILING_TILED;
+        p.dst_tiled = dst->tiling == KZN_TILING_TILED;
+        p.src_w = (int32_t)src->width;
+        p.src_h = (int32_t)src->height;
+        p.dx0 = d0->x; p.dx1 = d1->x; p.dy0 = d0->y; p.dy1 = d1->y;
+        p.sx0 = s0->x; p.sx1 = s1->x; p.sy0 = s0->y; p.sy1 = s1->y;
+        p.x_lo = d0->x < d1->x ? d0->x : d1->x;
+        p.y_lo = d0->y < d1->y ? d0->y : d1->y;
+        p.w = (uint32_t)(d0->x < d1->x ? d1->x - d0->x : d0->x - d1->x);
+        p.h = (uint32_t)(d0->y < d1->y ? d1->y - d0->y : d0->y - d1->y);
+        p.filter = filter;
+        int32_t z_lo = d0->z < d1->z ? d0->z : d1->z, z_hi = d0->z < d1->z ? d1->z : d0->z;
+        for (uint32_t l = 0; l < b->srcSubresource.layerCount; ++l)
+            for (int32_t k = z_lo; k < z_hi; ++k) {
+                // third coordinate point-sampled on the host: one launch per destination slice
+                float wf = blit_coord_host(k, d0->z, d1->z, s0->z, s1->z);
+                int32_t sz = (int32_t)__builtin_floorf(wf);
+                sz = sz < 0 ? 0 : (sz > (int32_t)src->depth - 1 ? (int32_t)src->depth - 1 : sz);
+                p.src = lower(image_box(src, 0, 0, sz, b->srcSubresource.baseArrayLayer + l));
+                p.dst = lower(image_box(dst, 0, 0, k, b->dstSubresource.baseArrayLayer + l));
+                dim3 grid((p.w + 31) / 32, (p.h + kThreads / 32 - 1) / (kThreads / 32));
+                blit_kernel<<<grid, kThreads, 0, queue->stream>>>(p);
+                if ((r = kzn_launched(queue, "blit_kernel"))) return r;
+            }
+    }
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if ((r = kzn_check_image(src, "convert_tiling(src)")) || (r = kzn_check_image(dst, "convert_tiling(dst)"))) return r;
+    KZN_VALID(src->format == dst->format && src->width == dst->width && src->height == dst->height && src->depth == dst->depth &&
+                  src->array_layers == dst->array_layers,
+              "convert_tiling: images differ in more than tiling");
+    Box sb = image_box(src, 0, 0, 0, 0), db = image_box(dst, 0, 0, 0, 0);
+    return launch_box(queue, &sb, db, src->width, src->height, src->depth * src->array_layers, false, 0);
+}
+
+}  // extern "C"

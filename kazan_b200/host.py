@@ -1,0 +1,290 @@
+"""Thin host-side harness over the C ABI (include/kazan_b200.h), used by tests and bench.
+
+The product's host layer is C++ (the ICD, kazan_b200/csrc/icd) because the reference's host is
+compiled Rust; this module only lets Python drive the same entry points with the reference's
+names: Queue.cmd_clear_color_image <-> vkCmdClearColorImage (vulkan-driver/src/api_impl.rs:4780) etc.
+
+There is no fallback: if libkazan_b200.so is missing or no CUDA device exists, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterable, Sequence
+
+from . import abi
+
+_LIB_PATH = Path(__file__).resolve().parent / "libkazan_b200.so"
+_lib = None
+
+
+class KazanError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        self.code = code
+        super().__init__(f"{abi.RESULT_NAMES.get(code, code)}: {message}")
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA extension.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise ImportError(
+                f"{_LIB_PATH} is missing: build it with `python -m kazan_b200.build` "
+                "(kazan_b200 has no CPU or PyTorch fallback)")
+        _lib = abi.bind(C.CDLL(str(_LIB_PATH)))
+    return _lib
+
+
+def _check(code: int) -> int:
+    if code < 0:
+        raise KazanError(code, load_library().kzn_last_error().decode())
+    return code
+
+
+def _array(ctype, items: Sequence):
+    items = list(items)
+    return (ctype * max(len(items), 1))(*items), len(items)
+
+
+@dataclass
+class Image:
+    """vulkan-driver/src/image.rs `ImageProperties` + bound memory address."""
+    address: int
+    width: int
+    height: int
+    depth: int = 1
+    array_layers: int = 1
+    format: int = abi.FORMAT_R8G8B8A8_UNORM
+    tiling: int = abi.TILING_LINEAR
+    mip_levels: int = 1
+
+    def desc(self) -> abi.ImageDesc:
+        return abi.ImageDesc(self.address, self.format, self.tiling, self.width, self.height, self.depth,
+                             self.array_layers, self.mip_levels, 0)
+
+    def memory_requirements(self) -> tuple[int, int]:
+        size, align = abi.u64(), abi.u64()
+        d = self.desc()
+        _check(load_library().kzn_image_memory_requirements(C.byref(d), C.byref(size), C.byref(align)))
+        return size.value, align.value
+
+
+def color_range(base_layer=0, layer_count=abi.REMAINING, aspect=abi.ASPECT_COLOR, base_mip=0, level_count=abi.REMAINING):
+    return abi.ImageSubresourceRange(aspect, base_mip, level_count, base_layer, layer_count)
+
+
+def buffer_image_copy(width, height, depth=1, buffer_offset=0, row_length=0, image_height=0, offset=(0, 0, 0),
+                      base_layer=0, layer_count=1, aspect=abi.ASPECT_COLOR, mip=0) -> abi.BufferImageCopy:
+    return abi.BufferImageCopy(buffer_offset, row_length, image_height,
+                               abi.ImageSubresourceLayers(aspect, mip, base_layer, layer_count),
+                               abi.Offset3D(*offset), abi.Extent3D(width, height, depth))
+
+
+class Device:
+    def __init__(self, ordinal: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.kzn_device_create(ordinal, C.byref(h)))
+        self.handle = h
+        self.ordinal = ordinal
+
+    @staticmethod
+    def count() -> int:
+        n = abi.i32()
+        code = load_library().kzn_device_count(C.byref(n))
+        return n.value if code == 0 else 0
+
+    @property
+    def sm_count(self) -> int:
+        return self._lib.kzn_device_sm_count(self.handle)
+
+    def wait_idle(self):
+        _check(self._lib.kzn_device_wait_idle(self.handle))
+
+    def create_queue(self) -> "Queue":
+        h = C.c_void_p()
+        _check(self._lib.kzn_queue_create(self.handle, C.byref(h)))
+        return Queue(self, h)
+
+    def wrap_stream(self, cuda_stream: int) -> "Queue":
+        h = C.c_void_p()
+        _check(self._lib.kzn_queue_wrap_stream(self.handle, C.c_void_p(cuda_stream), C.byref(h)))
+        return Queue(self, h)
+
+    def allocate(self, size: int, memory_type: int = abi.MEMORY_TYPE_DEVICE_LOCAL) -> "Memory":
+        h = C.c_void_p()
+        _check(self._lib.kzn_memory_allocate(self.handle, size, memory_type, C.byref(h)))
+        return Memory(self, h)
+
+    def create_fence(self, signaled: bool = False) -> "Fence":
+        h = C.c_void_p()
+        _check(self._lib.kzn_fence_create(self.handle, int(signaled), C.byref(h)))
+        return Fence(self, h)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_device_destroy(self.handle)
+            self.handle = None
+
+
+class Memory:
+    def __init__(self, device: Device, handle):
+        self.device, self.handle, self._lib = device, handle, device._lib
+
+    @property
+    def address(self) -> int:
+        return self._lib.kzn_memory_device_address(self.handle)
+
+    @property
+    def size(self) -> int:
+        return self._lib.kzn_memory_size(self.handle)
+
+    def map(self, offset: int = 0) -> int:
+        p = C.c_void_p()
+        _check(self._lib.kzn_memory_map(self.handle, offset, C.byref(p)))
+        return p.value
+
+    def free(self):
+        if self.handle:
+            self._lib.kzn_memory_free(self.handle)
+            self.handle = None
+
+
+class Fence:
+    def __init__(self, device: Device, handle):
+        self.device, self.handle, self._lib = device, handle, device._lib
+
+    def status(self) -> int:
+        return _check(self._lib.kzn_fence_status(self.handle))
+
+    def wait(self, timeout_ns: int = 2**64 - 1) -> int:
+        return _check(self._lib.kzn_fence_wait(self.handle, timeout_ns))
+
+    def reset(self):
+        _check(self._lib.kzn_fence_reset(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_fence_destroy(self.handle)
+            self.handle = None
+
+
+class Queue:
+    """One VkQueue == one CUDA stream.  Method names follow the Vulkan commands they implement."""
+
+    def __init__(self, device: Device, handle):
+        self.device, self.handle, self._lib = device, handle, device._lib
+
+    # -- queue -------------------------------------------------------------------------------
+    def wait_idle(self):
+        _check(self._lib.kzn_queue_wait_idle(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.kzn_queue_launch_count(self.handle)
+
+    @property
+    def stream(self) -> int:
+        return self._lib.kzn_queue_stream(self.handle) or 0
+
+    def signal_fence(self, fence: Fence):
+        _check(self._lib.kzn_queue_signal_fence(self.handle, fence.handle))
+
+    def upload(self, dst_address: int, src_ptr: int, size: int):
+        _check(self._lib.kzn_queue_upload(self.handle, dst_address, C.c_void_p(src_ptr), size))
+
+    def download(self, dst_ptr: int, src_address: int, size: int):
+        _check(self._lib.kzn_queue_download(self.handle, C.c_void_p(dst_ptr), src_address, size))
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_queue_destroy(self.handle)
+            self.handle = None
+
+    # -- transfer ------------------------------------------------------------------------------
+    def cmd_clear_color_image(self, image: Image, color: Sequence[float], ranges: Iterable | None = None):
+        d = image.desc()
+        c = abi.ClearColorValue()
+        c.float32[:] = list(color)
+        arr, n = _array(abi.ImageSubresourceRange, ranges if ranges is not None else [color_range()])
+        _check(self._lib.kzn_cmd_clear_color_image(self.handle, C.byref(d), C.byref(c), n, arr))
+
+    def cmd_clear_depth_stencil_image(self, image: Image, depth: float, ranges: Iterable | None = None):
+        d = image.desc()
+        v = abi.ClearDepthStencilValue(depth, 0)
+        arr, n = _array(abi.ImageSubresourceRange,
+                        ranges if ranges is not None else [color_range(aspect=abi.ASPECT_DEPTH)])
+        _check(self._lib.kzn_cmd_clear_depth_stencil_image(self.handle, C.byref(d), C.byref(v), n, arr))
+
+    def cmd_clear_attachment(self, image: Image, value: Sequence[float], rects: Iterable[abi.ClearRect]):
+        d = image.desc()
+        c = abi.ClearColorValue()
+        c.float32[:] = (list(value) + [0.0] * 4)[:4]
+        arr, n = _array(abi.ClearRect, rects)
+        _check(self._lib.kzn_cmd_clear_attachment(self.handle, C.byref(d), C.byref(c), n, arr))
+
+    def cmd_copy_buffer_to_image(self, buffer_address: int, buffer_size: int, image: Image,
+                                 regions: Iterable[abi.BufferImageCopy]):
+        d = image.desc()
+        arr, n = _array(abi.BufferImageCopy, regions)
+        _check(self._lib.kzn_cmd_copy_buffer_to_image(self.handle, buffer_address, buffer_size, C.byref(d), n, arr))
+
+    def cmd_copy_image_to_buffer(self, image: Image, buffer_address: int, buffer_size: int,
+                                 regions: Iterable[abi.BufferImageCopy]):
+        d = image.desc()
+        arr, n = _array(abi.BufferImageCopy, regions)
+        _check(self._lib.kzn_cmd_copy_image_to_buffer(self.handle, C.byref(d), buffer_address, buffer_size, n, arr))
+
+    def cmd_copy_buffer(self, src_address: int, src_size: int, dst_address: int, dst_size: int,
+                        regions: Iterable[abi.BufferCopy]):
+        arr, n = _array(abi.BufferCopy, regions)
+        _check(self._lib.kzn_cmd_copy_buffer(self.handle, src_address, src_size, dst_address, dst_size, n, arr))
+
+    def cmd_fill_buffer(self, dst_address: int, dst_size: int, offset: int, size: int, data: int):
+        _check(self._lib.kzn_cmd_fill_buffer(self.handle, dst_address, dst_size, offset, size, data))
+
+    def cmd_update_buffer(self, dst_address: int, dst_size: int, offset: int, data: bytes):
+        buf = C.create_string_buffer(data, len(data))
+        _check(self._lib.kzn_cmd_update_buffer(self.handle, dst_address, dst_size, offset, len(data),
+                                               C.cast(buf, C.c_void_p)))
+
+    def cmd_copy_image(self, src: Image, dst: Image, regions: Iterable[abi.ImageCopy]):
+        s, d = src.desc(), dst.desc()
+        arr, n = _array(abi.ImageCopy, regions)
+        _check(self._lib.kzn_cmd_copy_image(self.handle, C.byref(s), C.byref(d), n, arr))
+
+    def cmd_blit_image(self, src: Image, dst: Image, regions: Iterable[abi.ImageBlit], filter: int):
+        s, d = src.desc(), dst.desc()
+        arr, n = _array(abi.ImageBlit, regions)
+        _check(self._lib.kzn_cmd_blit_image(self.handle, C.byref(s), C.byref(d), n, arr, filter))
+
+    def cmd_convert_tiling(self, src: Image, dst: Image):
+        s, d = src.desc(), dst.desc()
+        _check(self._lib.kzn_cmd_convert_tiling(self.handle, C.byref(s), C.byref(d)))
+
+    # -- draw -----------------------------------------------------------------------------------
+    def set_draw_statistics(self, address: int):
+        _check(self._lib.kzn_queue_set_draw_statistics(self.handle, address))
+
+    def cmd_draw(self, state: abi.GraphicsPipelineState, framebuffer: abi.Framebuffer, viewport: abi.Viewport,
+                 scissor: abi.Rect2D, vertices: abi.VertexInput, vertex_count: int, instance_count: int = 1,
+                 first_vertex: int = 0, first_instance: int = 0):
+        _check(self._lib.kzn_cmd_draw(self.handle, C.byref(state), C.byref(framebuffer), C.byref(viewport),
+                                      C.byref(scissor), C.byref(vertices), vertex_count, instance_count,
+                                      first_vertex, first_instance))
+
+    def cmd_draw_indexed(self, state: abi.GraphicsPipelineState, framebuffer: abi.Framebuffer,
+                         viewport: abi.Viewport, scissor: abi.Rect2D, vertices: abi.VertexInput,
+                         index_buffer_address: int, index_buffer_size: int, index_type: int, index_count: int,
+                         instance_count: int = 1, first_index: int = 0, vertex_offset: int = 0,
+                         first_instance: int = 0):
+        _check(self._lib.kzn_cmd_draw_indexed(self.handle, C.byref(state), C.byref(framebuffer), C.byref(viewport),
+                                              C.byref(scissor), C.byref(vertices), index_buffer_address,
+                                              index_buffer_size, index_type, index_count, instance_count,
+                                              first_index, vertex_offset, first_instance))

@@ -1,0 +1,215 @@
+"""Case tables shared by the oracle tests (CPU), the GPU parity tests and the golden generator.
+
+Transfer cases follow SURVEY.md §8d config #1 and its stress variants; draw scenes are small versions of
+configs #3/#4 plus the edge cases of SURVEY.md Appendix E (top-left rule, degenerate input, clipping by
+scissor/viewport, depth ops, blend ops, tiled attachments, bands).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from kazan_b200 import abi
+from kazan_b200.host import buffer_image_copy
+from tests import util
+from tests.util import Scene, pipeline_state
+
+L, T = abi.TILING_LINEAR, abi.TILING_TILED
+
+# (name, image dict, regions, buffer_bytes)
+BUFFER_IMAGE_CASES = [
+    ("cfg1_1024", dict(width=1024, height=1024), [buffer_image_copy(1024, 1024)], 1024 * 1024 * 4),
+    ("padded_pitch_1056", dict(width=1024, height=256), [buffer_image_copy(1024, 256, row_length=1056)], 1056 * 256 * 4),
+    ("subrect_16_8", dict(width=1024, height=1024),
+     [buffer_image_copy(992, 1000, offset=(16, 8, 0))], 992 * 1000 * 4),
+    ("misaligned_offset_4", dict(width=256, height=64), [buffer_image_copy(256, 64, buffer_offset=4)], 256 * 64 * 4 + 4),
+    ("odd_width_13", dict(width=13, height=7), [buffer_image_copy(13, 7)], 13 * 7 * 4),
+    ("odd_subrect", dict(width=67, height=33), [buffer_image_copy(31, 17, offset=(5, 3, 0), row_length=40, image_height=20)],
+     40 * 20 * 4),
+    ("two_regions", dict(width=128, height=128),
+     [buffer_image_copy(64, 128), buffer_image_copy(64, 128, buffer_offset=64 * 128 * 4, offset=(64, 0, 0))],
+     128 * 128 * 4),
+    ("array_layers", dict(width=64, height=32, array_layers=5),
+     [buffer_image_copy(64, 32, base_layer=1, layer_count=3, image_height=40)], 64 * 40 * 3 * 4),
+    ("volume_3d", dict(width=32, height=16, depth=6), [buffer_image_copy(20, 10, depth=4, offset=(4, 2, 1))], 20 * 10 * 4 * 4),
+    ("single_texel", dict(width=9, height=9), [buffer_image_copy(1, 1, offset=(8, 8, 0))], 4),
+    ("empty_extent", dict(width=16, height=16), [buffer_image_copy(0, 16)], 64),
+    ("tiled_full", dict(width=128, height=64, tiling=T), [buffer_image_copy(128, 64)], 128 * 64 * 4),
+    ("tiled_odd", dict(width=50, height=37, tiling=T), [buffer_image_copy(50, 37)], 50 * 37 * 4),
+    ("tiled_subrect", dict(width=100, height=70, tiling=T, array_layers=2),
+     [buffer_image_copy(41, 23, offset=(7, 19, 0), base_layer=1, row_length=48)], 48 * 23 * 4),
+    ("tiled_aligned_subrect", dict(width=128, height=64, tiling=T), [buffer_image_copy(64, 32, offset=(32, 16, 0))],
+     64 * 32 * 4),
+    ("depth_format", dict(width=96, height=40, format=abi.FORMAT_D32_SFLOAT),
+     [buffer_image_copy(96, 40, aspect=abi.ASPECT_DEPTH)], 96 * 40 * 4),
+]
+
+# (name, image dict, clear ranges) — ranges as (base_layer, layer_count)
+CLEAR_CASES = [
+    ("cfg1_1024", dict(width=1024, height=1024), [(0, abi.REMAINING)]),
+    ("odd_3x5", dict(width=3, height=5), [(0, 1)]),
+    ("layers_1_2_of_4", dict(width=33, height=17, array_layers=4), [(1, 2)]),
+    ("two_ranges", dict(width=16, height=16, array_layers=4), [(0, 1), (3, 1)]),
+    ("tiled_50x37", dict(width=50, height=37, tiling=T), [(0, abi.REMAINING)]),
+    ("volume", dict(width=20, height=10, depth=3), [(0, 1)]),
+]
+
+CLEAR_COLOR = (0.25, 0.5, 0.75, 1.0)  # -> bytes 40 80 BF FF
+
+
+def image_desc_fields(spec: dict) -> dict:
+    d = dict(width=1, height=1, depth=1, array_layers=1, format=abi.FORMAT_R8G8B8A8_UNORM, tiling=L)
+    d.update(spec)
+    return d
+
+
+# (name, src image, dst image, regions, filter)
+def blit_cases():
+    B = util.blit_region
+    return [
+        ("nearest_identity", dict(width=64, height=48), dict(width=64, height=48), [B((0, 0, 0), (64, 48, 1), (0, 0, 0), (64, 48, 1))],
+         abi.FILTER_NEAREST),
+        ("nearest_up2", dict(width=32, height=24), dict(width=64, height=48), [B((0, 0, 0), (32, 24, 1), (0, 0, 0), (64, 48, 1))],
+         abi.FILTER_NEAREST),
+        ("nearest_down3_mirror_x", dict(width=96, height=60), dict(width=40, height=40),
+         [B((96, 0, 0), (0, 60, 1), (4, 10, 0), (36, 30, 1))], abi.FILTER_NEAREST),
+        ("linear_up", dict(width=17, height=13), dict(width=64, height=48), [B((0, 0, 0), (17, 13, 1), (0, 0, 0), (64, 48, 1))],
+         abi.FILTER_LINEAR),
+        ("linear_down_mirror_y", dict(width=80, height=50), dict(width=33, height=21),
+         [B((3, 2, 0), (77, 47, 1), (1, 20, 0), (32, 0, 1))], abi.FILTER_LINEAR),
+        ("linear_tiled_src", dict(width=50, height=37, tiling=T), dict(width=70, height=50),
+         [B((0, 0, 0), (50, 37, 1), (0, 0, 0), (70, 50, 1))], abi.FILTER_LINEAR),
+        ("nearest_tiled_dst_layers", dict(width=20, height=20, array_layers=2), dict(width=45, height=31, tiling=T, array_layers=3),
+         [B((0, 0, 0), (20, 20, 1), (5, 1, 0), (45, 31, 1), src_layer=0, dst_layer=1, layers=2)], abi.FILTER_NEAREST),
+    ]
+
+
+def copy_image_cases():
+    Cp = util.image_copy
+    return [
+        ("linear_to_linear", dict(width=64, height=32), dict(width=80, height=40), [Cp((40, 20, 1), (3, 5, 0), (17, 9, 0))]),
+        ("linear_to_tiled", dict(width=50, height=37), dict(width=50, height=37, tiling=T), [Cp((50, 37, 1))]),
+        ("tiled_to_tiled_layers", dict(width=48, height=32, tiling=T, array_layers=3), dict(width=64, height=64, tiling=T, array_layers=3),
+         [Cp((32, 16, 1), (16, 16, 0), (4, 32, 0), src_layer=1, dst_layer=0, layers=2)]),
+        ("volume", dict(width=16, height=16, depth=4), dict(width=16, height=16, depth=4), [Cp((8, 8, 3), (0, 0, 1), (8, 8, 0))]),
+        ("depth_to_depth", dict(width=31, height=9, format=abi.FORMAT_D32_SFLOAT), dict(width=31, height=9, format=abi.FORMAT_D32_SFLOAT),
+         [Cp((31, 9, 1), aspect=abi.ASPECT_DEPTH)]),
+    ]
+
+
+CONVERT_TILING_CASES = [
+    ("50x37", dict(width=50, height=37)), ("128x64_layers2", dict(width=128, height=64, array_layers=2)),
+    ("1x1", dict(width=1, height=1)), ("16x16", dict(width=16, height=16)), ("17x33_vol2", dict(width=17, height=33, depth=2)),
+]
+
+
+# ---- draw scenes ------------------------------------------------------------------------------------------------
+
+def _quad(color, z=0.5, x0=-1.0, y0=-1.0, x1=1.0, y1=1.0):
+    c = list(color)
+    return [[x0, y0, z] + c, [x1, y0, z] + c, [x1, y1, z] + c, [x0, y0, z] + c, [x1, y1, z] + c, [x0, y1, z] + c]
+
+
+def draw_scenes() -> list[Scene]:
+    rng = np.random.default_rng(20261017)
+    scenes: list[Scene] = []
+    # config #3 in small: fullscreen triangle + procedural fragment program
+    scenes.append(Scene("fill_orbit_256x144", 256, 144, util.FULLSCREEN_TRIANGLE,
+                        state=pipeline_state(fs=abi.FS_PROCEDURAL_ORBIT)))
+    scenes.append(Scene("fill_orbit_odd_131x77_tiled", 131, 77, util.FULLSCREEN_TRIANGLE,
+                        state=pipeline_state(fs=abi.FS_PROCEDURAL_ORBIT), color_tiling=T))
+    # shared edges: every pixel exactly once (additive blend makes double hits visible)
+    q = _quad((0.25, 0.25, 0.25, 0.25))
+    scenes.append(Scene("quad_shared_diagonal", 64, 48, q, state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    ctr = [0.013, -0.027, 0.5, 0.25, 0.25, 0.25, 0.25]
+    ang = np.sort(rng.uniform(0, 2 * np.pi, 11))
+    pts = [[float(np.cos(a)) * 1.7 + 0.01, float(np.sin(a)) * 1.9, 0.5, 0.25, 0.25, 0.25, 0.25] for a in ang]
+    fan = []
+    for i in range(len(pts)):
+        fan += [ctr, pts[i], pts[(i + 1) % len(pts)]]
+    scenes.append(Scene("fan_subpixel_vertices", 97, 61, fan, state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # config #4 in small: jittered grid mesh, D32 LESS + alpha blend (binned path: > 256 triangles)
+    v, i = util.grid_mesh(40, 20, 4)
+    scenes.append(Scene("mesh_40x20_depth_blend", 320, 180, v, i, state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND),
+                        use_depth=True))
+    v, i = util.grid_mesh(200, 100, 5)
+    scenes.append(Scene("mesh_200x100_depth_blend", 480, 270, v, i, state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND),
+                        use_depth=True))
+    v, i = util.grid_mesh(24, 12, 6)
+    scenes.append(Scene("mesh_cull_back_cw", 200, 120, v, i, state=pipeline_state(cull=abi.CULL_BACK, front=abi.FRONT_FACE_CW)))
+    scenes.append(Scene("mesh_cull_front_ccw_tiled", 200, 120, v, i, state=pipeline_state(cull=abi.CULL_FRONT), color_tiling=T))
+    # viewport / scissor clipping, negative-height viewport, band
+    v, i = util.grid_mesh(30, 30, 7)
+    scenes.append(Scene("viewport_offset_scissor", 160, 120, v, i, viewport=abi.Viewport(21.5, 10.25, 100.0, 80.5, 0.1, 0.9),
+                        scissor=abi.Rect2D(abi.Offset2D(30, 20), abi.Extent2D(77, 55)),
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1)), use_depth=True))
+    scenes.append(Scene("viewport_negative_height", 128, 96, v, i, viewport=abi.Viewport(0, 96, 128, -96, 0, 1),
+                        state=pipeline_state(blend=util.ALPHA_BLEND)))
+    scenes.append(Scene("band_rows_40_72", 128, 96, v, i, band=(40, 72), state=pipeline_state(blend=util.ALPHA_BLEND)))
+    # index variants
+    v16, i32 = util.grid_mesh(12, 9, 8)
+    pad = np.zeros((5, 7), dtype=np.float32)
+    scenes.append(Scene("uint16_first_index_vertex_offset", 90, 70, np.concatenate([pad, v16]), i32.astype(np.uint16),
+                        index_type=abi.INDEX_TYPE_UINT16, first=6, vertex_offset=5))
+    scenes.append(Scene("non_indexed_instances2", 64, 48, _quad((0.125, 0.25, 0.5, 0.125)), instances=2,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # perspective: vec4 positions with varying w
+    pv = []
+    for k in range(60):
+        w = rng.uniform(0.5, 4.0, 3)
+        xy = rng.uniform(-1.2, 1.2, (3, 2))
+        z = rng.uniform(0, 1, 3)
+        col = rng.uniform(0, 1, (3, 4))
+        for j in range(3):
+            pv.append([xy[j, 0] * w[j], xy[j, 1] * w[j], z[j] * w[j], w[j], *col[j]])
+    scenes.append(Scene("perspective_w", 150, 110, np.array(pv, dtype=np.float32), pos_comps=4, color_offset=16,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS, 1)), use_depth=True))
+    # degenerate / invalid input mixed with valid triangles
+    bad = np.array(pv[:30], dtype=np.float32)
+    bad[0, 3] = 0.0           # w == 0
+    bad[4, 3] = -1.0          # w < 0
+    bad[6, 0] = np.nan        # NaN position
+    bad[9, 1] = np.inf
+    bad[12:15, :4] = bad[12, :4]  # zero area
+    bad[15, 0] = 3.0e7        # beyond the guard band
+    bad[18:21, 2] = 2.0 * bad[18:21, 3]  # z > w: clipped away per fragment
+    scenes.append(Scene("degenerate_mix", 150, 110, bad, pos_comps=4, color_offset=16,
+                        state=pipeline_state(blend=util.ALPHA_BLEND)))
+    # out-of-range indices fetch zeros
+    vo, io = util.grid_mesh(6, 6, 9)
+    io = io.copy()
+    io[5] = 1000
+    io[20] = 0xFFFFFFF0
+    scenes.append(Scene("robust_index_fetch", 64, 64, vo, io))
+    # depth ops and masks
+    v, i = util.grid_mesh(20, 20, 10)
+    scenes.append(Scene("depth_greater_nowrite_mask_rb", 100, 100, v, i, clear_depth=0.5, use_depth=True,
+                        state=pipeline_state(depth=(abi.COMPARE_GREATER, 0), write_mask=5), clear_color=(0.2, 0.4, 0.6, 0.8)))
+    scenes.append(Scene("depth_always_write", 100, 100, v, i, use_depth=True, state=pipeline_state(depth=(abi.COMPARE_ALWAYS, 1))))
+    scenes.append(Scene("depth_never", 100, 100, v, i, use_depth=True, state=pipeline_state(depth=(abi.COMPARE_NEVER, 1))))
+    scenes.append(Scene("depth_not_equal_blend_minmax", 100, 100, v, i, use_depth=True, clear_depth=0.5, clear_color=(0.5, 0.5, 0.5, 0.5),
+                        state=pipeline_state(depth=(abi.COMPARE_NOT_EQUAL, 1),
+                                             blend=(abi.BLEND_ONE, abi.BLEND_ONE, abi.BLEND_OP_MIN, abi.BLEND_ONE, abi.BLEND_ONE, abi.BLEND_OP_MAX))))
+    scenes.append(Scene("blend_dst_factors_revsub", 100, 100, v, i, clear_color=(0.9, 0.6, 0.3, 0.7),
+                        state=pipeline_state(blend=(abi.BLEND_DST_ALPHA, abi.BLEND_ONE_MINUS_SRC_COLOR, abi.BLEND_OP_REVERSE_SUBTRACT,
+                                                    abi.BLEND_ONE_MINUS_DST_ALPHA, abi.BLEND_DST_COLOR, abi.BLEND_OP_SUBTRACT))))
+    # one tile hammered by more triangles than the in-shared-memory sort holds (binned-list overflow path)
+    many = []
+    for k in range(4500):
+        x0, y0 = rng.uniform(-1.0, 0.2, 2)
+        many += [[x0, y0, 0.5, 0.01, 0.02, 0.03, 0.004], [x0 + 0.9, y0 + 0.1, 0.5, 0.01, 0.02, 0.03, 0.004],
+                 [x0 + 0.2, y0 + 0.8, 0.5, 0.01, 0.02, 0.03, 0.004]]
+    scenes.append(Scene("overflow_4500_tris_one_tile", 40, 24, np.array(many, dtype=np.float32),
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # thin slivers and large triangles mixed, > 256 triangles so that wide triangles go through binning
+    sl = []
+    for k in range(300):
+        a = rng.uniform(-1.3, 1.3, 2)
+        d = rng.uniform(-1, 1, 2) * (2.0 if k % 7 == 0 else 0.3)
+        n = np.array([-d[1], d[0]]) * (0.5 if k % 11 == 0 else 0.004)
+        col = rng.uniform(0, 1, 4)
+        zz = rng.uniform(0, 1)
+        for pnt in (a, a + d, a + d + n):
+            sl.append([pnt[0], pnt[1], zz, *col])
+    scenes.append(Scene("slivers_and_large", 256, 160, np.array(sl, dtype=np.float32),
+                        state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    return scenes

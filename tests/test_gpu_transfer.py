@@ -1,0 +1,181 @@
+"""GPU parity: the CUDA transfer kernels, called through the C ABI, against the CPU oracle — bit exact."""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from kazan_b200 import abi, host
+from kazan_b200.host import buffer_image_copy as bic
+from oracle import binding as ob
+from tests import cases, runners
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "oracle_golden.json").read_text())
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def same(gpu_bytes, oracle_bytes, key):
+    assert gpu_bytes == oracle_bytes, f"{key}: CUDA result differs from the oracle"
+    assert sha(gpu_bytes) == GOLDEN[key], f"{key}: result differs from the committed golden digest"
+
+
+@pytest.mark.parametrize("case", cases.CLEAR_CASES, ids=lambda c: c[0])
+def test_clear_color_image(gpu, case):
+    name, spec, ranges = case
+    same(runners.gpu_clear(gpu, spec, ranges), runners.oracle_clear(spec, ranges), f"clear/{name}")
+
+
+@pytest.mark.parametrize("case", cases.BUFFER_IMAGE_CASES, ids=lambda c: c[0])
+def test_copy_buffer_to_image(gpu, case):
+    name, spec, regions, nbytes = case
+    same(runners.gpu_buffer_to_image(gpu, spec, regions, nbytes), runners.oracle_buffer_to_image(spec, regions, nbytes), f"b2i/{name}")
+
+
+@pytest.mark.parametrize("case", cases.BUFFER_IMAGE_CASES, ids=lambda c: c[0])
+def test_copy_image_to_buffer(gpu, case):
+    name, spec, regions, nbytes = case
+    same(runners.gpu_image_to_buffer(gpu, spec, regions, nbytes), runners.oracle_image_to_buffer(spec, regions, nbytes), f"i2b/{name}")
+
+
+@pytest.mark.parametrize("case", cases.blit_cases(), ids=lambda c: c[0])
+def test_blit_image(gpu, case):
+    name, s, d, regions, filt = case
+    # NEAREST is an integer path; LINEAR is fp32 with the oracle's operation order and is bit exact as well
+    same(runners.gpu_blit(gpu, s, d, regions, filt), runners.oracle_blit(s, d, regions, filt), f"blit/{name}")
+
+
+@pytest.mark.parametrize("case", cases.copy_image_cases(), ids=lambda c: c[0])
+def test_copy_image(gpu, case):
+    name, s, d, regions = case
+    same(runners.gpu_copy_image(gpu, s, d, regions), runners.oracle_copy_image(s, d, regions), f"copy_image/{name}")
+
+
+@pytest.mark.parametrize("case", cases.CONVERT_TILING_CASES, ids=lambda c: c[0])
+def test_convert_tiling(gpu, case):
+    name, spec = case
+    same(runners.gpu_convert_tiling(gpu, spec, True), runners.oracle_convert_tiling(spec, True), f"to_tiled/{name}")
+    same(runners.gpu_convert_tiling(gpu, spec, False), runners.oracle_convert_tiling(spec, False), f"to_linear/{name}")
+
+
+def test_depth_clear_and_attachment_clear(gpu, oracle):
+    import ctypes as C
+    spec = dict(width=70, height=33, array_layers=3, format=abi.FORMAT_D32_SFLOAT)
+    size = runners._size(spec)
+    init = ob.random_bytes(size, 31)
+    mem = gpu.buffer(size, init)
+    img = runners._host_img(spec, mem.address)
+    gpu.queue.cmd_clear_depth_stencil_image(img, 0.625, [abi.ImageSubresourceRange(abi.ASPECT_DEPTH, 0, 1, 1, 2)])
+    rects = [abi.ClearRect(abi.Rect2D(abi.Offset2D(3, 4), abi.Extent2D(50, 20)), 0, 1),
+             abi.ClearRect(abi.Rect2D(abi.Offset2D(64, 0), abi.Extent2D(6, 33)), 2, 1)]
+    gpu.queue.cmd_clear_attachment(img, [0.25], rects)
+    out = mem.download().tobytes()
+    gpu.release()
+    ref = init.copy()
+    d = runners._img(spec, ob.ptr(ref))
+    v = abi.ClearDepthStencilValue(0.625, 0)
+    a, n = ob.array_of(abi.ImageSubresourceRange, [abi.ImageSubresourceRange(abi.ASPECT_DEPTH, 0, 1, 1, 2)])
+    assert oracle.kzo_clear_depth_stencil_image(C.byref(d), C.byref(v), n, a) == 0
+    c = abi.ClearColorValue(); c.float32[0] = 0.25
+    a, n = ob.array_of(abi.ClearRect, rects)
+    assert oracle.kzo_clear_attachment(C.byref(d), C.byref(c), n, a) == 0
+    assert out == ref.tobytes()
+
+
+def test_buffer_commands(gpu, oracle):
+    import ctypes as C
+    src_h, dst_h = ob.random_bytes(1 << 20, 1), ob.random_bytes(1 << 20, 2)
+    src, dst = gpu.buffer(1 << 20, src_h), gpu.buffer(1 << 20, dst_h)
+    regions = [abi.BufferCopy(3, 1001, 777), abi.BufferCopy(4096, 65536, 262144), abi.BufferCopy(8, 400000, 40),
+               abi.BufferCopy(500004, 600004, 4000)]
+    gpu.queue.cmd_copy_buffer(src.address, 1 << 20, dst.address, 1 << 20, regions)
+    gpu.queue.cmd_fill_buffer(dst.address, (1 << 20) - 2, 900000, abi.WHOLE_SIZE, 0xDEADBEEF)
+    gpu.queue.cmd_fill_buffer(dst.address, 1 << 20, 12, 20, 0x01020304)
+    gpu.queue.cmd_update_buffer(dst.address, 1 << 20, 128, bytes(range(200)))
+    out = dst.download().tobytes()
+    gpu.release()
+    ref = dst_h.copy()
+    a, n = ob.array_of(abi.BufferCopy, regions)
+    assert oracle.kzo_copy_buffer(C.c_void_p(ob.ptr(src_h)), 1 << 20, C.c_void_p(ob.ptr(ref)), 1 << 20, n, a) == 0
+    assert oracle.kzo_fill_buffer(C.c_void_p(ob.ptr(ref)), (1 << 20) - 2, 900000, abi.WHOLE_SIZE, 0xDEADBEEF) == 0
+    assert oracle.kzo_fill_buffer(C.c_void_p(ob.ptr(ref)), 1 << 20, 12, 20, 0x01020304) == 0
+    assert oracle.kzo_update_buffer(C.c_void_p(ob.ptr(ref)), 1 << 20, 128, 200, bytes(range(200))) == 0
+    assert out == ref.tobytes()
+
+
+def test_invalid_usage_returns_the_oracles_error_codes(gpu):
+    mem = gpu.buffer(64 * 64 * 4)
+    buf = gpu.buffer(64 * 64 * 4)
+    img = host.Image(mem.address, 64, 64)
+    V = abi.ERROR_VALIDATION_FAILED
+
+    def code(fn):
+        with pytest.raises(host.KazanError) as e:
+            fn()
+        return e.value.code
+
+    q = gpu.queue
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [bic(64, 64, buffer_offset=2)])) == V
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [bic(64, 64, row_length=32)])) == V
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [bic(64, 64, image_height=8)])) == V
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [bic(64, 64, offset=(1, 0, 0))])) == V
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes - 4, img, [bic(64, 64)])) == V
+    assert code(lambda: q.cmd_copy_image_to_buffer(img, buf.address, buf.nbytes, [bic(64, 64, aspect=abi.ASPECT_DEPTH)])) == V
+    assert code(lambda: q.cmd_clear_color_image(img, (0, 0, 0, 0), [abi.ImageSubresourceRange(abi.ASPECT_DEPTH, 0, 1, 0, 1)])) == V
+    dimg = host.Image(mem.address, 64, 64, format=abi.FORMAT_D32_SFLOAT)
+    assert code(lambda: q.cmd_clear_color_image(dimg, (0, 0, 0, 0))) == abi.ERROR_FORMAT_NOT_SUPPORTED
+    assert code(lambda: q.cmd_fill_buffer(buf.address, buf.nbytes, 6, 8, 0)) == V
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [])) == V
+    gpu.release()
+
+
+def test_full_size_properties_4k_and_8k(gpu):
+    """BASELINE sizes, through size-independent properties (no oracle pass over 132 MB needed):
+    clear -> every word equals the packed colour; copy b2i -> i2b round trip is the identity; checksum of
+    checksums of a padded-pitch copy equals numpy's."""
+    for (w, h) in [(3840, 2160), (7680, 4320)]:
+        n = w * h * 4
+        img_mem, buf_a, buf_b = gpu.buffer(n), gpu.buffer(n), gpu.buffer(n)
+        img = host.Image(img_mem.address, w, h)
+        gpu.queue.cmd_clear_color_image(img, cases.CLEAR_COLOR)
+        words = img_mem.download().view(np.uint32)
+        assert words.min() == words.max() == 0xFFBF8040
+        data = ob.random_bytes(n, w)
+        buf_a.upload(data)
+        gpu.queue.cmd_copy_buffer_to_image(buf_a.address, n, img, [bic(w, h)])
+        gpu.queue.cmd_copy_image_to_buffer(img, buf_b.address, n, [bic(w, h)])
+        assert np.array_equal(buf_b.download(), data)
+        # sub-rectangle with padded pitch into a cleared image: digest against numpy slicing
+        gpu.queue.cmd_clear_color_image(img, (0, 0, 0, 0))
+        rw, rh, pitch = w - 48, h - 40, w - 16
+        gpu.queue.cmd_copy_buffer_to_image(buf_a.address, n, img, [bic(rw, rh, row_length=pitch, offset=(16, 8, 0))])
+        got = img_mem.download().view(np.uint32).reshape(h, w)
+        exp = np.zeros((h, w), dtype=np.uint32)
+        src = data.view(np.uint32)[:pitch * rh].reshape(rh, pitch)[:, :rw]
+        exp[8:8 + rh, 16:16 + rw] = src
+        assert sha(got.tobytes()) == sha(exp.tobytes())
+        gpu.release()
+
+
+def test_tma_and_ldst_paths_agree(gpu):
+    """KZN_TRANSFER_PATH picks the engine for contiguous runs; results must be identical."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.');"
+        "from tests.util import GpuContext; from tests import runners, cases; import hashlib;"
+        "g = GpuContext();"
+        "n, spec, regions, nb = cases.BUFFER_IMAGE_CASES[0];"
+        "print(hashlib.sha256(runners.gpu_buffer_to_image(g, spec, regions, nb)).hexdigest(),"
+        "      hashlib.sha256(runners.gpu_clear(g, *cases.CLEAR_CASES[0][1:])).hexdigest())")
+    outs = []
+    for path in ("ldst", "tma"):
+        env = dict(os.environ, KZN_TRANSFER_PATH=path)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True,
+                                   cwd=str(Path(__file__).parent.parent)).stdout.split())
+    assert outs[0] == outs[1] == [GOLDEN["b2i/cfg1_1024"], GOLDEN["clear/cfg1_1024"]]
