@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the kazan_b200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one frame of BASELINE.json configs[2]: a fullscreen triangle rasterised and shaded with the
+procedural fragment program into a 3840x2160 R8G8B8A8_UNORM target, through the C ABI
+(kzn_cmd_draw -> setup_kernel + raster_kernel).  `value` is Gpixels/s shaded with everything resident in HBM;
+`e2e` is the same frame through the same call with HOST buffers (vertex upload + frame read-back inside the
+timed region).  `extra` carries the second half of the metric: clear / copy GB/s against the measured HBM peak.
+With N > 1 (torchrun) every rank renders one 3840x2160 band of a 3840 x (2160*N) frame (sort-first split) and the
+bands are composited to rank 0 over NCCL; value = all pixels of all bands / max-over-ranks time (weak scaling).
+
+--impl reference times the reference's CPU path.  The reference (kazan-3d/kazan) cannot be built here and leaves
+this path unimplemented, so — as the task's tier rules prescribe — this arm times the CPU oracle port (oracle/)
+on all host threads, on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FRAME_W, FRAME_H = 3840, 2160
+# algorithmic work of the fill-rate shader per pixel: fp32-pipe instructions (an fma counts once)
+FP32_INSTR_PER_PIXEL = 148
+METRIC = "Gpixels/s shaded (4K fill)"
+UNIT = "Gpixels/s"
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.06)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload construction (no test helpers: the bench talks to the product API only)
+
+def fill_state(abi):
+    st = abi.GraphicsPipelineState()
+    st.fragment_program = abi.FS_PROCEDURAL_ORBIT
+    st.color_write_mask = 15
+    return st
+
+
+FULLSCREEN_TRIANGLE = np.array([[-1, -1, 0, 1, 1, 1, 1], [3, -1, 0, 1, 1, 1, 1], [-1, 3, 0, 1, 1, 1, 1]], dtype=np.float32)
+
+
+def framebuffer(abi, address, width, height, band=(0, 0)):
+    fb = abi.Framebuffer()
+    fb.color = abi.ImageDesc(address, abi.FORMAT_R8G8B8A8_UNORM, abi.TILING_LINEAR, width, height, 1, 1, 1, 0)
+    fb.band_y0, fb.band_y1 = band
+    return fb
+
+
+def time_region(torch, stream, fn, steps, warmup, barrier=None):
+    """W warm-up steps, then EXACTLY `steps` steps between two events on `stream`; returns milliseconds."""
+    for k in range(warmup):
+        fn(k)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record(stream)
+    for k in range(steps):
+        fn(warmup + k)
+    end.record(stream)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return start.elapsed_time(end)
+
+
+def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
+    """clear / copy GB/s (the second half of BASELINE's metric) at config #1's size and at HBM-resident sizes."""
+    out = {}
+    sizes = [("1024x1024", 1024, 1024), ("3840x2160", 3840, 2160), ("7680x4320", 7680, 4320), ("16384x16384", 16384, 16384)]
+    for label, w, h in sizes:
+        nbytes = w * h * 4
+        # rotate over enough images that the footprint exceeds L2 (126 MB): no L2 flush kernels needed
+        n_img = max(2, min(64, (768 << 20) // nbytes))
+        images = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(n_img)]
+        buffers = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(n_img)]
+        for b in buffers:
+            b.random_(0, 256)
+        imgs = [host.Image(t.data_ptr(), w, h) for t in images]
+        region = [host.buffer_image_copy(w, h)]
+        reps = max(8, min(400, (24 << 30) // nbytes))
+        ms = time_region(torch, stream, lambda k: queue.cmd_clear_color_image(imgs[k % n_img], (0.25, 0.5, 0.75, 1.0)), reps, 3)
+        clear = nbytes * reps / ms / 1e6
+        ms = time_region(torch, stream, lambda k: queue.cmd_copy_buffer_to_image(buffers[k % n_img].data_ptr(), nbytes, imgs[k % n_img], region), reps, 3)
+        copy = 2 * nbytes * reps / ms / 1e6
+        ms = time_region(torch, stream, lambda k: queue.cmd_copy_image_to_buffer(imgs[k % n_img], buffers[(k + 1) % n_img].data_ptr(), nbytes, region), reps, 3)
+        copy_back = 2 * nbytes * reps / ms / 1e6
+        out[label] = {"clear_GBps": round(clear, 1), "clear_frac_hbm": round(clear / hbm_peak, 3),
+                      "copy_b2i_GBps": round(copy, 1), "copy_b2i_frac_hbm": round(copy / hbm_peak, 3),
+                      "copy_i2b_GBps": round(copy_back, 1), "copy_i2b_frac_hbm": round(copy_back / hbm_peak, 3),
+                      "bytes": nbytes, "rotating_images": n_img, "reps": reps}
+        del images, buffers
+        torch.cuda.empty_cache()
+    return out
+
+
+def oracle_fill(width, height, threads, rows=None):
+    """The CPU port of the same frame (oracle/raster.c); returns (seconds, colour bytes)."""
+    from oracle import binding as ob
+    from kazan_b200 import abi
+    lib = ob.load()
+    lib.kzo_set_threads(threads)
+    color = ob.aligned_empty(width * height * 4)
+    color[:] = 0
+    fb = framebuffer(abi, ob.ptr(color), width, height, band=(0, rows) if rows else (0, 0))
+    st = fill_state(abi)
+    vp = abi.Viewport(0, 0, width, height, 0, 1)
+    sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(width, height))
+    verts = FULLSCREEN_TRIANGLE.copy()
+    vi = abi.VertexInput(ob.ptr(verts), verts.nbytes, 28, 0, 3, 12)
+    t0 = time.perf_counter()
+    code = lib.kzo_draw(C.byref(st), C.byref(fb), C.byref(vp), C.byref(sc), C.byref(vi), 3, 1, 0, 0, None)
+    dt = time.perf_counter() - t0
+    assert code == 0
+    return dt, color
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port, all host threads) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import binding as ob
+    threads = ob.load().kzo_hardware_threads()
+    # bounded sample: as many rows of the 4K frame as keep one step around a second
+    probe_rows = 64
+    dt, _ = oracle_fill(FRAME_W, FRAME_H, threads, rows=probe_rows)
+    rows = int(min(FRAME_H, max(probe_rows, probe_rows * (1.0 / max(dt, 1e-6)))))
+    rows -= rows % 8
+    for k in range(args.warmup):
+        oracle_fill(FRAME_W, FRAME_H, threads, rows=rows)
+    t = 0.0
+    for k in range(args.steps):
+        dt, _ = oracle_fill(FRAME_W, FRAME_H, threads, rows=rows)
+        t += dt
+    value = FRAME_W * rows * args.steps / t / 1e9
+    sample = f"rows [0,{rows}) of the 3840x2160 frame per step ({FRAME_W * rows} pixels)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fullscreen-triangle procedural fragment shader at 3840x2160 R8G8B8A8_UNORM (configs[2])",
+                   "note": "reference path is unimplemented!() upstream and cannot be built here; CPU oracle port timed instead"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kazan_b200 import abi, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — kazan_b200 has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+
+    dev = host.Device(local_rank)
+    stream = torch.cuda.Stream()
+    queue = dev.wrap_stream(stream.cuda_stream)
+    hbm_peak, peak_src = measured_peaks()
+
+    W, H = FRAME_W, FRAME_H
+    frame_bytes = W * H * 4
+    n_targets = 8  # 265 MB of render targets > 126 MB L2: every step writes lines that are not L2 resident
+    total_h = H * world
+    st = fill_state(abi)
+    vp = abi.Viewport(0, 0, W, total_h, 0, 1)
+    sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, total_h))
+    verts = torch.from_numpy(FULLSCREEN_TRIANGLE.copy()).cuda()
+    vi = abi.VertexInput(verts.data_ptr(), verts.numel() * 4, 28, 0, 3, 12)
+
+    with torch.cuda.stream(stream):
+        if world == 1:
+            targets = [torch.zeros(frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
+            fbs = [framebuffer(abi, t.data_ptr(), W, H) for t in targets]
+
+            def step(k):
+                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
+        else:
+            # sort-first split: rank r owns rows [r*H, (r+1)*H) of a W x (H*world) frame; rank 0 presents.
+            # Every rank renders into a full-size image (only its band is touched), then the band is sent to
+            # rank 0's image: one exchange step per frame.
+            n_targets = 2
+            full = [torch.zeros(frame_bytes * world, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
+            fbs = [framebuffer(abi, t.data_ptr(), W, total_h, band=(rank * H, (rank + 1) * H)) for t in full]
+
+            def step(k):
+                t = full[k % n_targets]
+                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
+                if rank == 0:
+                    ops = [dist.P2POp(dist.irecv, t[r * frame_bytes:(r + 1) * frame_bytes], r) for r in range(1, world)]
+                else:
+                    ops = [dist.P2POp(dist.isend, t[rank * frame_bytes:(rank + 1) * frame_bytes], 0)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+
+        launches0 = queue.launch_count
+        with ClockSampler(local_rank) as clocks:
+            ms = time_region(torch, stream, step, args.steps, args.warmup, barrier)
+        launches = queue.launch_count - launches0 - 0
+        # launches counted over warm-up + timed steps: keep only the timed share
+        launches = launches * args.steps // (args.steps + args.warmup)
+
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    pixels_per_step = W * H * world
+    value = pixels_per_step * args.steps / ms / 1e6  # Gpixels/s
+    ms_per_step = ms / args.steps
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "fullscreen-triangle procedural fragment shader at 3840x2160 R8G8B8A8_UNORM (configs[2])"
+                               + ("" if world == 1 else f"; {world} bands of 3840x2160, NCCL composite to rank 0"),
+                   "frame": [W, total_h], "fragment_program": "procedural orbit, 32 fp32 fma iterations",
+                   "l2": f"rotating {n_targets} render targets ({n_targets * frame_bytes * world >> 20} MiB > 126 MiB L2)"},
+        "gpu_launches": int(launches),
+    }
+
+    if rank == 0 and world == 1:
+        # roofline of the dominant kernel (raster_kernel).  Its duration is bounded above by the step time
+        # (the step is setup_kernel on one triangle + raster_kernel), so `achieved` is a lower bound.
+        sec = ms_per_step / 1e3
+        clk = clocks.summary()
+        line["clocks"] = clk
+        achieved = frame_bytes / sec / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": None, "peak_source": peak_src,
+                            "note": "4 B written per pixel; the kernel is fp32-issue bound, see `issue`"}
+        sm_mhz = clk["sm_mhz"] or 1965.0
+        issue_peak = dev.sm_count * 128 * sm_mhz * 1e6 / 1e12  # T fp32 instr/s at the sampled clock
+        issue = W * H * FP32_INSTR_PER_PIXEL / sec / 1e12
+        line["issue"] = {"bound": "fp32_issue", "achieved": issue, "peak": issue_peak, "unit": "Tinstr/s", "frac": issue / issue_peak,
+                         "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL, "sm_mhz": sm_mhz}
+
+        if args.profile:
+            print(json.dumps(line))
+            return 0
+        # ---- e2e: host buffers, copies inside the timed region ----
+        with torch.cuda.stream(stream):
+            h_verts = torch.from_numpy(FULLSCREEN_TRIANGLE.copy()).pin_memory()
+            h_frame = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
+            d_verts = torch.empty(21, dtype=torch.float32, device="cuda")
+            vi2 = abi.VertexInput(d_verts.data_ptr(), 84, 28, 0, 3, 12)
+
+            def e2e_step(k):
+                queue.upload(d_verts.data_ptr(), h_verts.data_ptr(), 84)
+                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi2, 3)
+                queue.download(h_frame.data_ptr(), targets[k % n_targets].data_ptr(), frame_bytes)
+                queue.wait_idle()  # the frame is in host memory
+
+            e_steps = max(5, min(args.steps, 20))
+            ems = time_region(torch, stream, e2e_step, e_steps, 3)
+        line["e2e"] = {"value": W * H * e_steps / ems / 1e6, "unit": UNIT, "h2d_bytes_per_step": 84, "d2h_bytes_per_step": frame_bytes,
+                       "steps": e_steps}
+
+        # ---- CPU baseline (oracle port) + full-frame parity ----
+        from oracle import binding as ob
+        threads = ob.load().kzo_hardware_threads()
+        dt, ocolor = oracle_fill(W, H, threads)
+        same = bool(np.array_equal(h_frame.numpy(), ocolor))
+        line["cpu_baseline"] = {"value": W * H / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "one full 3840x2160 frame, oracle/raster.c, all host threads"}
+        line["parity"] = "bit-exact vs oracle on the full 4K frame" if same else "MISMATCH vs oracle"
+
+        # ---- clear / copy GB/s vs HBM peak ----
+        with torch.cuda.stream(stream):
+            line["extra"] = {"transfer": transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak),
+                             "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src}
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e, CPU baseline or transfer sweep")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
