@@ -163,6 +163,111 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
     return out
 
 
+def grid_mesh(quads_x, quads_y, seed):
+    """Jittered grid mesh of SURVEY.md §8d config #4 (same numbers as oracle/raster.c kzo_make_grid_mesh, restated in
+    numpy so that the bench does not call the oracle for its inputs): vertex = x,y,z,r,g,b,a f32; u32 indices."""
+    vx, vy = quads_x + 1, quads_y + 1
+    n = vx * vy
+    with np.errstate(over="ignore"):
+        k = np.arange(1, 7 * n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + k * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = ((z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)).reshape(n, 7)
+    f = np.float32
+    i = np.tile(np.arange(vx, dtype=np.float32), vy)
+    j = np.repeat(np.arange(vy, dtype=np.float32), vx)
+    cell_x, cell_y = f(2.0) / f(quads_x), f(2.0) / f(quads_y)
+    v = np.empty((n, 7), dtype=np.float32)
+    v[:, 0] = f(-1.0) + (i + (u[:, 0] - f(0.5)) * f(3.0)) * cell_x
+    v[:, 1] = f(-1.0) + (j + (u[:, 1] - f(0.5)) * f(3.0)) * cell_y
+    v[:, 2] = f(0.05) + f(0.9) * u[:, 2]
+    v[:, 3:6] = u[:, 3:6]
+    v[:, 6] = f(0.25) + f(0.75) * u[:, 6]
+    qi = np.tile(np.arange(quads_x, dtype=np.uint32), quads_y)
+    qj = np.repeat(np.arange(quads_y, dtype=np.uint32), quads_x)
+    v00 = qj * np.uint32(vx) + qi
+    v10, v01 = v00 + 1, v00 + np.uint32(vx)
+    v11 = v01 + 1
+    idx = np.stack([v00, v10, v11, v00, v11, v01], axis=1).reshape(-1).astype(np.uint32)
+    return v, idx
+
+
+def mesh_state(abi):
+    st = abi.GraphicsPipelineState()
+    st.fragment_program = abi.FS_VERTEX_COLOR
+    st.color_write_mask = 15
+    st.depth_test_enable = st.depth_write_enable = 1
+    st.depth_compare_op = abi.COMPARE_LESS
+    st.blend_enable = 1
+    st.src_color_blend_factor = st.src_alpha_blend_factor = abi.BLEND_SRC_ALPHA
+    st.dst_color_blend_factor = st.dst_alpha_blend_factor = abi.BLEND_ONE_MINUS_SRC_ALPHA
+    return st
+
+
+def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1080), seed=4, check_oracle=True):
+    """BASELINE configs[3]: 1M-triangle indexed mesh, D32 LESS + alpha blend, 1920x1080.  One frame = clear colour +
+    clear depth + vkCmdDrawIndexed."""
+    W, H = size
+    verts, idx = grid_mesh(*quads, seed)
+    ntri = len(idx) // 3
+    d_verts, d_idx = torch.from_numpy(verts).cuda(), torch.from_numpy(idx.view(np.int32)).cuda()
+    color = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
+    depth = torch.empty(W * H, dtype=torch.float32, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    cimg = host.Image(color.data_ptr(), W, H)
+    dimg = host.Image(depth.data_ptr(), W, H, format=abi.FORMAT_D32_SFLOAT)
+    fb = abi.Framebuffer()
+    fb.color, fb.depth = cimg.desc(), dimg.desc()
+    st = mesh_state(abi)
+    vp = abi.Viewport(0, 0, W, H, 0, 1)
+    sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, H))
+    vi = abi.VertexInput(d_verts.data_ptr(), verts.nbytes, 28, 0, 3, 12)
+
+    def frame(k):
+        queue.cmd_clear_color_image(cimg, (0, 0, 0, 0))
+        queue.cmd_clear_depth_stencil_image(dimg, 1.0)
+        queue.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+
+    queue.set_draw_statistics(stats.data_ptr())
+    frame(0)
+    queue.set_draw_statistics(0)
+    torch.cuda.synchronize()
+    s = stats.cpu().numpy()
+    reps = 20
+    ms = time_region(torch, stream, frame, reps, 3) / reps
+    out = {"triangles": ntri, "frame": [W, H], "ms_per_frame": ms, "Mtri_per_s": ntri / ms / 1e3,
+           "Gpix_shaded_per_s": int(s[5]) / ms / 1e6, "fragments_covered": int(s[4]), "fragments_depth_passed": int(s[5]),
+           "triangles_culled": int(s[1]), "bin_entries": int(s[3]), "bin_overflow_tiles": int(s[7]),
+           "depth_complexity": int(s[4]) / (W * H)}
+    if check_oracle:
+        from oracle import binding as ob
+        lib = ob.load()
+        threads = lib.kzo_hardware_threads()
+        lib.kzo_set_threads(threads)
+        ocolor = ob.aligned_empty(W * H * 4); ocolor[:] = 0
+        odepth = ob.aligned_empty(W * H * 4); odepth.view(np.float32)[:] = 1.0
+        ofb = abi.Framebuffer()
+        ofb.color = abi.ImageDesc(ob.ptr(ocolor), abi.FORMAT_R8G8B8A8_UNORM, 0, W, H, 1, 1, 1, 0)
+        ofb.depth = abi.ImageDesc(ob.ptr(odepth), abi.FORMAT_D32_SFLOAT, 0, W, H, 1, 1, 1, 0)
+        ovi = abi.VertexInput(ob.ptr(verts), verts.nbytes, 28, 0, 3, 12)
+        ostats = abi.DrawStatistics()
+        t0 = time.perf_counter()
+        code = lib.kzo_draw_indexed(C.byref(st), C.byref(ofb), C.byref(vp), C.byref(sc), C.byref(ovi), C.c_void_p(ob.ptr(idx)),
+                                    idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx), 1, 0, 0, 0, C.byref(ostats))
+        dt = time.perf_counter() - t0
+        assert code == 0
+        same_c = bool(np.array_equal(color.cpu().numpy(), ocolor))
+        same_d = bool(np.array_equal(depth.cpu().numpy().view(np.uint8), odepth))
+        out["cpu_baseline"] = {"ms_per_frame": dt * 1e3, "Mtri_per_s": ntri / dt / 1e6, "cores": threads, "kind": "port"}
+        out["parity"] = ("bit-exact colour+depth vs oracle at full size" if same_c and same_d else
+                         f"MISMATCH colour_equal={same_c} depth_equal={same_d}")
+        out["stats_match_oracle"] = (int(s[4]), int(s[5]), int(s[1])) == (ostats.fragments_covered, ostats.fragments_depth_passed,
+                                                                            ostats.triangles_culled)
+    return out
+
+
 def oracle_fill(width, height, threads, rows=None):
     """The CPU port of the same frame (oracle/raster.c); returns (seconds, colour bytes)."""
     from oracle import binding as ob
@@ -347,7 +452,8 @@ def run_ours(args):
         # ---- clear / copy GB/s vs HBM peak ----
         with torch.cuda.stream(stream):
             line["extra"] = {"transfer": transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak),
-                             "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src}
+                             "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src,
+                             "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream)}
     elif rank == 0:
         line["e2e"] = None
     if rank == 0:
@@ -361,8 +467,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e, CPU baseline or transfer sweep")
     args = ap.parse_args()

@@ -9,13 +9,13 @@
 //   setup_kernel   1 thread / triangle: index + vertex fetch, passthrough VS, clip->window (R1), snap to 1/16 px (R2),
 //                  signed area / cull (R4), sign-normalised integer edge equations + top-left bias (R5), pixel bbox.
 //                  Writes one 144-byte TriRec per triangle.
-//   bin_count / bin_scan / bin_fill   screen-tile binning: per 32x8-pixel tile, the list of overlapping triangles
+//   bin_count / bin_scan / bin_fill   screen-tile binning: per 128x8-pixel tile, the list of overlapping triangles
 //                  (atomics give an unordered list; the raster kernel sorts it in shared memory so that per-pixel
 //                  fragment order == primitive order, R7).
-//   raster_kernel  1 CTA / screen tile, 1 thread / pixel: the tile's colour and depth live in REGISTERS for the whole
+//   raster_kernel  1 CTA / 128x8 screen tile, 1 thread / 4 adjacent pixels: the tile's colour and depth live in REGISTERS for the whole
 //                  triangle list (each framebuffer byte is read at most once and written at most once per draw);
 //                  fixed-point coverage (int64 edge functions, bias test), barycentric depth (R6), z clip, early-Z,
-//                  fragment program, blend (R8), one coalesced 128-byte row store per warp.
+//                  fragment program, blend (R8), one 16-byte vector store per thread (512 B contiguous per warp).
 // Numerics are the oracle's rules R1-R8 (oracle/raster.c): every fp32 operation is written out; the file is compiled
 // with -fmad=false so only the explicit fmaf() calls fuse.
 #include <math.h>
@@ -27,8 +27,9 @@
 
 namespace {
 
-constexpr int kTileW = 32, kTileH = 8;   // pixels per raster tile: one warp per row -> 128 B row stores
-constexpr int kRasterThreads = kTileW * kTileH;
+constexpr int kPx = 4;                   // horizontally adjacent pixels per thread: one 16-byte colour vector
+constexpr int kTileW = 32 * kPx, kTileH = 8;  // pixels per raster tile: one warp per row -> 512 B row stores
+constexpr int kRasterThreads = 32 * kTileH;
 constexpr int kRecs = 128;               // triangle records staged in shared memory per round
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
@@ -371,39 +372,97 @@ struct RasterShared {
     TriRec recs[kRecs];
     uint32_t list[kSortCap];  // binned: the tile's sorted triangle ids; direct: ids surviving the current round
     uint32_t warp_counts[kTileH];
-    uint32_t round_count;
 };
 
+// 4 interleaved orbits (independent dependency chains keep the fma pipe busy at any occupancy)
+__device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_w, float inv_h, float rgba[kPx][4]) {
+    float cx[kPx], zx[kPx], zy[kPx];
+    float v = ((float)py + 0.5f) * inv_h;
+    float cy = fmaf(v, 2.0f, -1.0f);
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        float u = ((float)(px0 + k) + 0.5f) * inv_w;
+        cx[k] = fmaf(u, 3.5f, -2.5f);
+        zx[k] = 0.0f;
+        zy[k] = 0.0f;
+    }
+#pragma unroll 4
+    for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) {
+            float t = fmaf(zx[k], zx[k], cx[k]);
+            float nzx = fmaf(-zy[k], zy[k], t);
+            float nzy = fmaf(zx[k] + zx[k], zy[k], cy);
+            zx[k] = nzx;
+            zy[k] = nzy;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        float m = fmaf(zx[k], zx[k], zy[k] * zy[k]);
+        rgba[k][0] = 0.25f * m;
+        rgba[k][1] = fmaf(zx[k], 0.5f, 0.5f);
+        rgba[k][2] = fmaf(zy[k], 0.5f, 0.5f);
+        rgba[k][3] = 1.0f;
+    }
+}
+
+// One CTA per 128x8-pixel screen tile; warp w owns row w, lane l owns the 4 pixels x0 = 4*l .. 4*l+3 of that row
+// (one 16-byte colour vector).  Colour and depth of the tile stay in registers across the whole triangle list.
 template <uint32_t FS>
-__global__ void __launch_bounds__(kRasterThreads) raster_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
     const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
-    const int px = tile_px0 + (int)lane, py = tile_py0 + (int)warp;
-    const bool in_clip = px >= p.cx0 && px <= p.cx1 && py >= p.cy0 && py <= p.cy1;
+    const int px0 = tile_px0 + (int)lane * kPx, py = tile_py0 + (int)warp;
+    const bool row_in = py >= p.cy0 && py <= p.cy1;
+    uint32_t clip_mask = 0;  // bit k: pixel px0+k is inside the clip rectangle
+#pragma unroll
+    for (int k = 0; k < kPx; ++k)
+        if (row_in && px0 + k >= p.cx0 && px0 + k <= p.cx1) clip_mask |= 1u << k;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
     // only read the destination colour when the result depends on it
     const bool need_dst = has_color && (p.st.blend_enable || (p.st.color_write_mask & 15u) != 15u);
+    // the 4 pixels are one aligned 16-byte vector when the row pitch keeps 16-byte alignment
+    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kPx <= (int)p.fb_w;
 
-    uint32_t color = 0;
-    float depth = 0.0f;
-    bool color_dirty = false, depth_dirty = false;
+    uint32_t color[kPx] = {0, 0, 0, 0};
+    float depth[kPx] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t color_dirty = 0, depth_dirty = 0;
     unsigned long long caddr = 0, daddr = 0;
-    if (in_clip) {
+    if (clip_mask) {
         if (has_color) {
-            caddr = color_addr(p, px, py);
-            if (need_dst) color = *reinterpret_cast<const uint32_t*>(caddr);
+            caddr = color_addr(p, px0, py);
+            if (need_dst) {
+                if (vec_ok && (p.color_base & 15ull) == 0) {
+                    uint4 v = *reinterpret_cast<const uint4*>(caddr);
+                    color[0] = v.x; color[1] = v.y; color[2] = v.z; color[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kPx; ++k)
+                        if (clip_mask & (1u << k)) color[k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+                }
+            }
         }
         if (has_depth) {
-            daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px) * 4ull;
-            if (depth_test) depth = *reinterpret_cast<const float*>(daddr);
+            daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px0) * 4ull;
+            if (depth_test) {
+                if (vec_ok && (p.depth_base & 15ull) == 0) {
+                    float4 v = *reinterpret_cast<const float4*>(daddr);
+                    depth[0] = v.x; depth[1] = v.y; depth[2] = v.z; depth[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kPx; ++k)
+                        if (clip_mask & (1u << k)) depth[k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+                }
+            }
         }
     }
-    const int32_t sx = 16 * px + 8, sy = 16 * py + 8;  // fixed-point sample position (R2)
+    const int32_t sx = 16 * px0 + 8, sy = 16 * py + 8;  // fixed-point sample position of pixel 0 (R2)
     uint32_t n_covered = 0, n_passed = 0;
 
     // triangle source
@@ -479,51 +538,86 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(const __grid_con
         }
         __syncthreads();
 
-        // ---- every pixel walks the staged triangles in order ----
-        if (in_clip) {
+        // ---- every thread walks the staged triangles in order ----
+        if (clip_mask) {
             for (uint32_t r = 0; r < n_round; ++r) {
                 const TriRec& t = sh.recs[r];
-                if (py < t.miny || py > t.maxy) continue;  // warp-uniform (one row per warp)
-                if (px < t.minx || px > t.maxx) continue;
+                if (py < t.miny || py > t.maxy) continue;               // warp-uniform (one row per warp)
+                if (px0 > t.maxx || px0 + kPx - 1 < t.minx) continue;  // none of my 4 pixels
+                // edge functions at pixel 0, then +16*a per pixel to the right (exact integer arithmetic, R5)
                 long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);
                 long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
                 long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
-                uint32_t bias = t.bias_bits;
-                if (e0 + (long long)(bias & 1u) <= 0 || e1 + (long long)((bias >> 1) & 1u) <= 0 ||
-                    e2 + (long long)((bias >> 2) & 1u) <= 0)
-                    continue;
-                float inv2a = t.inv2a;
-                float l0 = (float)e0 * inv2a, l1 = (float)e1 * inv2a, l2 = (float)e2 * inv2a;  // R6
-                float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
-                if (!(z >= p.zclip_lo && z <= p.zclip_hi)) continue;  // R3
-                ++n_covered;
-                if (depth_test && !depth_compare(p.st.depth_compare_op, z, depth)) continue;  // R7: early-Z
-                ++n_passed;
-                if (depth_write) {
-                    depth = z;
-                    depth_dirty = true;
-                }
-                if (!has_color) continue;
-                float src[4];
-                if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-                    fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
-                } else {
-                    float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
+                const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
+                const uint32_t bias = t.bias_bits;
+                const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
+                const float inv2a = t.inv2a;
+                uint32_t live = 0;  // pixels that reach shading
+                float l0[kPx], l1[kPx], l2[kPx], z[kPx];
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        float num = fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch]));
-                        src[ch] = __fdiv_rn(num, den);
+                for (int k = 0; k < kPx; ++k) {
+                    long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
+                    bool cov = (clip_mask >> k & 1u) && px0 + k >= t.minx && px0 + k <= t.maxx && f0 + b0 > 0 && f1 + b1 > 0 &&
+                               f2 + b2 > 0;
+                    l0[k] = (float)f0 * inv2a;  // R6
+                    l1[k] = (float)f1 * inv2a;
+                    l2[k] = (float)f2 * inv2a;
+                    z[k] = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
+                    cov = cov && z[k] >= p.zclip_lo && z[k] <= p.zclip_hi;  // R3 (false for NaN)
+                    if (cov) {
+                        ++n_covered;
+                        if (!depth_test || depth_compare(p.st.depth_compare_op, z[k], depth[k])) {  // R7: early-Z
+                            ++n_passed;
+                            live |= 1u << k;
+                            if (depth_write) {
+                                depth[k] = z[k];
+                                depth_dirty |= 1u << k;
+                            }
+                        }
                     }
                 }
-                color = output_merge(p.st, src, color);
-                color_dirty = true;
+                if (!live || !has_color) continue;
+                float src[kPx][4];
+                if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                    fs_procedural_orbit4(px0, py, p.inv_fb_w, p.inv_fb_h, src);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kPx; ++k) {
+                        float den = fmaf(l2[k], t.iw[2], fmaf(l1[k], t.iw[1], l0[k] * t.iw[0]));
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) {
+                            float num = fmaf(l2[k], t.col[2][ch], fmaf(l1[k], t.col[1][ch], l0[k] * t.col[0][ch]));
+                            src[k][ch] = __fdiv_rn(num, den);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kPx; ++k)
+                    if (live >> k & 1u) color[k] = output_merge(p.st, src[k], color[k]);
+                color_dirty |= live;
             }
         }
         __syncthreads();  // before the next round overwrites recs / list
     }
 
-    if (color_dirty) *reinterpret_cast<uint32_t*>(caddr) = color;
-    if (depth_dirty) *reinterpret_cast<float*>(daddr) = depth;
+    if (color_dirty) {
+        if (color_dirty == 15u && vec_ok && (p.color_base & 15ull) == 0) {
+            *reinterpret_cast<uint4*>(caddr) = make_uint4(color[0], color[1], color[2], color[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (color_dirty >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = color[k];
+        }
+    }
+    if (depth_dirty) {
+        if (depth_dirty == 15u && vec_ok && (p.depth_base & 15ull) == 0) {
+            *reinterpret_cast<float4*>(daddr) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (depth_dirty >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = depth[k];
+        }
+    }
     if (p.stats) {
         // warp-reduce then one atomic per warp
         for (int d = 16; d > 0; d >>= 1) {
