@@ -370,100 +370,69 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 
 struct RasterShared {
     TriRec recs[kRecs];
-    uint32_t list[kSortCap];  // binned: the tile's sorted triangle ids; direct: ids surviving the current round
+    uint32_t list[kSortCap];         // binned: the tile's sorted triangle ids; direct: ids surviving the current round
+    uint32_t color[kTileH][kTileW];  // the tile's colour and depth live here for the whole triangle list
+    float depth[kTileH][kTileW];
+    uint32_t color_dirty[kTileH][kTileW / 32];
+    uint32_t depth_dirty[kTileH][kTileW / 32];
+    float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
     uint32_t warp_counts[kTileH];
 };
 
-// 4 interleaved orbits (independent dependency chains keep the fma pipe busy at any occupancy)
-__device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_w, float inv_h, float rgba[kPx][4]) {
-    float cx[kPx], zx[kPx], zy[kPx];
-    float v = ((float)py + 0.5f) * inv_h;
-    float cy = fmaf(v, 2.0f, -1.0f);
+// blend with the destination held as UNORM8 in shared memory; same operation order as oracle/raster.c output_merge
+template <bool NEED_DST>
+__device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineState& st, const float* lut, const float src[4],
+                                                     uint32_t dst_word) {
+    float s[4], o[4];
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        float u = ((float)(px0 + k) + 0.5f) * inv_w;
-        cx[k] = fmaf(u, 3.5f, -2.5f);
-        zx[k] = 0.0f;
-        zy[k] = 0.0f;
+    for (int ch = 0; ch < 4; ++ch) s[ch] = clamp01(src[ch]);
+    if (!NEED_DST) {  // no blending, all channels written
+        return float_to_unorm8(s[0]) | (float_to_unorm8(s[1]) << 8) | (float_to_unorm8(s[2]) << 16) | (float_to_unorm8(s[3]) << 24);
     }
-#pragma unroll 4
-    for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
+    if (st.blend_enable) {
+        float d[4];
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) {
-            float t = fmaf(zx[k], zx[k], cx[k]);
-            float nzx = fmaf(-zy[k], zy[k], t);
-            float nzy = fmaf(zx[k] + zx[k], zy[k], cy);
-            zx[k] = nzx;
-            zy[k] = nzy;
-        }
-    }
+        for (int ch = 0; ch < 4; ++ch) d[ch] = lut[(dst_word >> (8 * ch)) & 255u];
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        float m = fmaf(zx[k], zx[k], zy[k] * zy[k]);
-        rgba[k][0] = 0.25f * m;
-        rgba[k][1] = fmaf(zx[k], 0.5f, 0.5f);
-        rgba[k][2] = fmaf(zy[k], 0.5f, 0.5f);
-        rgba[k][3] = 1.0f;
+        for (int ch = 0; ch < 3; ++ch)
+            o[ch] = blend_op(st.color_blend_op, s[ch], blend_factor(st.src_color_blend_factor, ch, s, d), d[ch],
+                             blend_factor(st.dst_color_blend_factor, ch, s, d));
+        o[3] = blend_op(st.alpha_blend_op, s[3], blend_factor(st.src_alpha_blend_factor, 3, s, d), d[3],
+                        blend_factor(st.dst_alpha_blend_factor, 3, s, d));
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) o[ch] = s[ch];
     }
+    uint32_t out = dst_word;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+        if (st.color_write_mask & (1u << ch)) out = (out & ~(0xffu << (8 * ch))) | (float_to_unorm8(o[ch]) << (8 * ch));
+    return out;
 }
 
-// One CTA per 128x8-pixel screen tile; warp w owns row w, lane l owns the 4 pixels x0 = 4*l .. 4*l+3 of that row
-// (one 16-byte colour vector).  Colour and depth of the tile stay in registers across the whole triangle list.
-template <uint32_t FS>
+// One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
+// for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
+// time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
+// Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
+template <uint32_t FS, bool NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
     const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
-    const int px0 = tile_px0 + (int)lane * kPx, py = tile_py0 + (int)warp;
+    const int py = tile_py0 + (int)warp;
     const bool row_in = py >= p.cy0 && py <= p.cy1;
-    uint32_t clip_mask = 0;  // bit k: pixel px0+k is inside the clip rectangle
-#pragma unroll
-    for (int k = 0; k < kPx; ++k)
-        if (row_in && px0 + k >= p.cx0 && px0 + k <= p.cx1) clip_mask |= 1u << k;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
-    // only read the destination colour when the result depends on it
-    const bool need_dst = has_color && (p.st.blend_enable || (p.st.color_write_mask & 15u) != 15u);
-    // the 4 pixels are one aligned 16-byte vector when the row pitch keeps 16-byte alignment
-    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kPx <= (int)p.fb_w;
-
-    uint32_t color[kPx] = {0, 0, 0, 0};
-    float depth[kPx] = {0.0f, 0.0f, 0.0f, 0.0f};
-    uint32_t color_dirty = 0, depth_dirty = 0;
-    unsigned long long caddr = 0, daddr = 0;
-    if (clip_mask) {
-        if (has_color) {
-            caddr = color_addr(p, px0, py);
-            if (need_dst) {
-                if (vec_ok && (p.color_base & 15ull) == 0) {
-                    uint4 v = *reinterpret_cast<const uint4*>(caddr);
-                    color[0] = v.x; color[1] = v.y; color[2] = v.z; color[3] = v.w;
-                } else {
+    // a lane's 4 pixels of the row (final load/store) are one aligned 16-byte vector when the row pitch allows it
+    const int qx0 = tile_px0 + (int)lane * kPx;
+    const bool vec_ok = (p.fb_w & 3u) == 0 && qx0 + kPx <= (int)p.fb_w;
+    uint32_t quad_clip = 0;
 #pragma unroll
-                    for (int k = 0; k < kPx; ++k)
-                        if (clip_mask & (1u << k)) color[k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
-                }
-            }
-        }
-        if (has_depth) {
-            daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px0) * 4ull;
-            if (depth_test) {
-                if (vec_ok && (p.depth_base & 15ull) == 0) {
-                    float4 v = *reinterpret_cast<const float4*>(daddr);
-                    depth[0] = v.x; depth[1] = v.y; depth[2] = v.z; depth[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kPx; ++k)
-                        if (clip_mask & (1u << k)) depth[k] = *reinterpret_cast<const float*>(daddr + 4 * k);
-                }
-            }
-        }
-    }
-    const int32_t sx = 16 * px0 + 8, sy = 16 * py + 8;  // fixed-point sample position of pixel 0 (R2)
-    uint32_t n_covered = 0, n_passed = 0;
+    for (int k = 0; k < kPx; ++k)
+        if (row_in && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
 
     // triangle source
     uint32_t list_len = 0;
@@ -499,6 +468,40 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
         }
     }
     const uint32_t n_source = direct ? p.total_tris : list_len;
+
+    // ---- tile prologue: destination values the result depends on, dirty masks, the UNORM8 -> float table ----
+    unsigned long long caddr = 0, daddr = 0;
+    if (quad_clip) {
+        if (has_color) caddr = color_addr(p, qx0, py);
+        if (has_depth) daddr = p.depth_base + ((unsigned long long)py * p.fb_w + qx0) * 4ull;
+    }
+    if (NEED_DST && quad_clip && has_color) {
+        if (vec_ok && (p.color_base & 15ull) == 0) {
+            *reinterpret_cast<uint4*>(&sh.color[warp][lane * kPx]) = *reinterpret_cast<const uint4*>(caddr);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (quad_clip >> k & 1u) sh.color[warp][lane * kPx + k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+        }
+    }
+    if (depth_test && quad_clip) {
+        if (vec_ok && (p.depth_base & 15ull) == 0) {
+            *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = *reinterpret_cast<const float4*>(daddr);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (quad_clip >> k & 1u) sh.depth[warp][lane * kPx + k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+        }
+    }
+    if (lane < kTileW / 32) {
+        sh.color_dirty[warp][lane] = 0;
+        sh.depth_dirty[warp][lane] = 0;
+    }
+    if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
+    __syncthreads();
+
+    const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
+    uint32_t n_covered = 0, n_passed = 0;
 
     for (uint32_t base = 0; base < n_source; base += kRecs) {
         // ---- stage up to kRecs triangle records that touch this tile, in primitive order ----
@@ -538,84 +541,131 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
         }
         __syncthreads();
 
-        // ---- every thread walks the staged triangles in order ----
-        if (clip_mask) {
-            for (uint32_t r = 0; r < n_round; ++r) {
-                const TriRec& t = sh.recs[r];
-                if (py < t.miny || py > t.maxy) continue;               // warp-uniform (one row per warp)
-                if (px0 > t.maxx || px0 + kPx - 1 < t.minx) continue;  // none of my 4 pixels
-                // edge functions at pixel 0, then +16*a per pixel to the right (exact integer arithmetic, R5)
-                long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);
-                long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
-                long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
-                const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
-                const uint32_t bias = t.bias_bits;
-                const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
-                const float inv2a = t.inv2a;
-                uint32_t live = 0;  // pixels that reach shading
-                float l0[kPx], l1[kPx], l2[kPx], z[kPx];
+        // ---- my row: stream the candidate pixels of the staged triangles, 32 per step ----
+        if (row_in) {
+            for (uint32_t chunk = 0; chunk < n_round; chunk += 32) {
+                // lane j looks at triangle chunk+j: which pixels of my row are in its bounding box?
+                int xa = 0;
+                uint32_t width = 0;
+                if (chunk + lane < n_round) {
+                    int4 bb = *reinterpret_cast<const int4*>(&sh.recs[chunk + lane]);  // minx maxx miny maxy (already scissored)
+                    if (py >= bb.z && py <= bb.w) {
+                        xa = max(bb.x, tile_px0);
+                        int xb = min(bb.y, tile_px0 + kTileW - 1);
+                        width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+                    }
+                }
+                uint32_t incl = width;
 #pragma unroll
-                for (int k = 0; k < kPx; ++k) {
-                    long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
-                    bool cov = (clip_mask >> k & 1u) && px0 + k >= t.minx && px0 + k <= t.maxx && f0 + b0 > 0 && f1 + b1 > 0 &&
-                               f2 + b2 > 0;
-                    l0[k] = (float)f0 * inv2a;  // R6
-                    l1[k] = (float)f1 * inv2a;
-                    l2[k] = (float)f2 * inv2a;
-                    z[k] = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
-                    cov = cov && z[k] >= p.zclip_lo && z[k] <= p.zclip_hi;  // R3 (false for NaN)
-                    if (cov) {
-                        ++n_covered;
-                        if (!depth_test || depth_compare(p.st.depth_compare_op, z[k], depth[k])) {  // R7: early-Z
-                            ++n_passed;
-                            live |= 1u << k;
-                            if (depth_write) {
-                                depth[k] = z[k];
-                                depth_dirty |= 1u << k;
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)lane >= d) incl += y;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t excl = incl - width;
+                for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    const bool active = c < total;
+                    // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
+                    uint32_t pos = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        uint32_t e = __shfl_sync(0xffffffffu, excl, (pos + step) & 31u);
+                        if (e <= c) pos += step;
+                    }
+                    const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
+                    const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
+                    const int px = o_xa + (int)(c - o_excl);
+                    const TriRec& t = sh.recs[chunk + pos];
+                    bool cov = false;
+                    float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
+                    if (active) {
+                        const int32_t sx = 16 * px + 8;
+                        long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
+                        long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
+                        long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
+                        const uint32_t bias = t.bias_bits;
+                        cov = e0 + (long long)(bias & 1u) > 0 && e1 + (long long)((bias >> 1) & 1u) > 0 &&
+                              e2 + (long long)((bias >> 2) & 1u) > 0;
+                        if (cov) {
+                            const float inv2a = t.inv2a;
+                            l0 = (float)e0 * inv2a;  // R6
+                            l1 = (float)e1 * inv2a;
+                            l2 = (float)e2 * inv2a;
+                            z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+                            cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, cov)) continue;
+                    if (cov) ++n_covered;
+                    const uint32_t key = cov ? (uint32_t)(px - tile_px0) : (0x80000000u | lane);
+                    // fragments of this batch on the same pixel: apply in lane order
+                    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                    const uint32_t max_rank = __reduce_max_sync(0xffffffffu, cov ? rank : 0u);
+                    float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    bool shaded = false;
+                    for (uint32_t rk = 0; rk <= max_rank; ++rk) {
+                        if (cov && rank == rk) {
+                            const uint32_t kx = key;
+                            bool pass = true;
+                            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.depth[warp][kx]);  // R7: early-Z
+                            if (pass) {
+                                ++n_passed;
+                                if (depth_write) {
+                                    sh.depth[warp][kx] = z;
+                                    atomicOr(&sh.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                                }
+                                if (has_color) {
+                                    if (!shaded) {
+                                        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                                            fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
+                                        } else {
+                                            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
+#pragma unroll
+                                            for (int ch = 0; ch < 4; ++ch) {
+                                                float num = fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch]));
+                                                src[ch] = __fdiv_rn(num, den);
+                                            }
+                                        }
+                                        shaded = true;
+                                    }
+                                    const uint32_t dst = NEED_DST ? sh.color[warp][kx] : 0u;
+                                    sh.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                                    atomicOr(&sh.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                                }
                             }
                         }
+                        __syncwarp();
                     }
                 }
-                if (!live || !has_color) continue;
-                float src[kPx][4];
-                if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-                    fs_procedural_orbit4(px0, py, p.inv_fb_w, p.inv_fb_h, src);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kPx; ++k) {
-                        float den = fmaf(l2[k], t.iw[2], fmaf(l1[k], t.iw[1], l0[k] * t.iw[0]));
-#pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) {
-                            float num = fmaf(l2[k], t.col[2][ch], fmaf(l1[k], t.col[1][ch], l0[k] * t.col[0][ch]));
-                            src[k][ch] = __fdiv_rn(num, den);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    if (live >> k & 1u) color[k] = output_merge(p.st, src[k], color[k]);
-                color_dirty |= live;
             }
         }
         __syncthreads();  // before the next round overwrites recs / list
     }
 
-    if (color_dirty) {
-        if (color_dirty == 15u && vec_ok && (p.color_base & 15ull) == 0) {
-            *reinterpret_cast<uint4*>(caddr) = make_uint4(color[0], color[1], color[2], color[3]);
-        } else {
+    // ---- tile epilogue: each lane writes back its 4 pixels of the row where they changed ----
+    __syncwarp();
+    if (quad_clip) {
+        const uint32_t cd = (sh.color_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
+        const uint32_t dd = (sh.depth_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
+        if (cd) {
+            if (cd == 15u && vec_ok && (p.color_base & 15ull) == 0) {
+                *reinterpret_cast<uint4*>(caddr) = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (color_dirty >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = color[k];
+                for (int k = 0; k < kPx; ++k)
+                    if (cd >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = sh.color[warp][lane * kPx + k];
+            }
         }
-    }
-    if (depth_dirty) {
-        if (depth_dirty == 15u && vec_ok && (p.depth_base & 15ull) == 0) {
-            *reinterpret_cast<float4*>(daddr) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        } else {
+        if (dd) {
+            if (dd == 15u && vec_ok && (p.depth_base & 15ull) == 0) {
+                *reinterpret_cast<float4*>(daddr) = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (depth_dirty >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = depth[k];
+                for (int k = 0; k < kPx; ++k)
+                    if (dd >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = sh.depth[warp][lane * kPx + k];
+            }
         }
     }
     if (p.stats) {
@@ -812,8 +862,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         p.bin_capacity = (uint32_t)(s->bin_capacity > 0xfffffff0ull ? 0xfffffff0ull : s->bin_capacity);
     }
     if (!s->attrs_set) {
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
         s->attrs_set = true;
     }
 
@@ -832,10 +884,16 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         if ((r = kzn_launched(q, "bin_kernel<fill>"))) return r;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
-    if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT)
-        raster_kernel<KZN_FS_PROCEDURAL_ORBIT><<<grid, kRasterThreads, sizeof(RasterShared), q->stream>>>(p);
-    else
-        raster_kernel<KZN_FS_VERTEX_COLOR><<<grid, kRasterThreads, sizeof(RasterShared), q->stream>>>(p);
+    // the destination colour is only read when the result depends on it
+    const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
+    const size_t smem = sizeof(RasterShared);
+    if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
+        if (need_dst) raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, smem, q->stream>>>(p);
+        else raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, smem, q->stream>>>(p);
+    } else {
+        if (need_dst) raster_kernel<KZN_FS_VERTEX_COLOR, true><<<grid, kRasterThreads, smem, q->stream>>>(p);
+        else raster_kernel<KZN_FS_VERTEX_COLOR, false><<<grid, kRasterThreads, smem, q->stream>>>(p);
+    }
     return kzn_launched(q, "raster_kernel");
 }
 
