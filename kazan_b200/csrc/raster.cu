@@ -111,9 +111,51 @@ __device__ __forceinline__ void fetch_vertex(const DrawParams& p, long long vidx
 
 __device__ __forceinline__ bool finite_f(float f) { return (f - f) == 0.0f; }
 
+__device__ __forceinline__ bool tile_range(const DrawParams& p, const TriRec* r, int& tx0, int& tx1, int& ty0, int& ty1) {
+    int4 bb = *reinterpret_cast<const int4*>(r);  // minx, maxx, miny, maxy
+    if (bb.x > bb.y) return false;
+    tx0 = bb.x / kTileW - (int)p.tile_x0;
+    tx1 = bb.y / kTileW - (int)p.tile_x0;
+    ty0 = bb.z / kTileH - (int)p.tile_y0;
+    ty1 = bb.w / kTileH - (int)p.tile_y0;
+    return true;
+}
+
+// Emit the (tile, triangle) pairs of one triangle PER LANE; must be called by all 32 lanes of a converged warp.
+// FILL == false: add `weight` to the tile counters; FILL == true: append triangle id `t` to the tile segments.
+// Triangles touching few tiles are handled by their own lane; wide ones are spread over the whole warp.
+template <bool FILL>
+__device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32_t t, uint32_t weight, int tx0, int tx1, int ty0,
+                                         int ty1) {
+    constexpr int kSmall = 8;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int w = tx1 - tx0 + 1;
+    const int n = valid ? w * (ty1 - ty0 + 1) : 0;
+    auto emit = [&](uint32_t tile, uint32_t tri, uint32_t wgt) {
+        if (!FILL) {
+            atomicAdd(&p.tile_counts[tile], wgt);
+        } else {
+            uint32_t pos = p.tile_offsets[tile] + atomicAdd(&p.tile_cursor[tile], 1u);
+            if (pos < p.bin_capacity) p.bin_entries[pos] = tri;
+        }
+    };
+    if (n <= kSmall)
+        for (int k = 0; k < n; ++k) emit((uint32_t)(ty0 + k / w) * p.tiles_x + (uint32_t)(tx0 + k % w), t, weight);
+    uint32_t big = __ballot_sync(0xffffffffu, n > kSmall);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int s_tx0 = __shfl_sync(0xffffffffu, tx0, src), s_ty0 = __shfl_sync(0xffffffffu, ty0, src);
+        const int s_w = __shfl_sync(0xffffffffu, w, src), s_n = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t s_t = __shfl_sync(0xffffffffu, t, src), s_wgt = __shfl_sync(0xffffffffu, weight, src);
+        for (int k = (int)lane; k < s_n; k += 32) emit((uint32_t)(s_ty0 + k / s_w) * p.tiles_x + (uint32_t)(s_tx0 + k % s_w), s_t, s_wgt);
+    }
+}
+
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
-    uint32_t t = blockIdx.x * 256u + threadIdx.x;
-    if (t >= p.tris_per_instance) return;
+    const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
+    const bool in_range = t_raw < p.tris_per_instance;
+    const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
     TriRec r;
     r.minx = 1;
     r.maxx = 0;
@@ -179,52 +221,34 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         }
     }
     // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
-    const uint4* src = reinterpret_cast<const uint4*>(&r);
-    for (uint32_t inst = 0; inst * p.tris_per_instance < p.total_tris; ++inst) {
-        uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
+    const uint32_t n_inst = p.total_tris / p.tris_per_instance;
+    if (in_range) {
+        const uint4* src = reinterpret_cast<const uint4*>(&r);
+        for (uint32_t inst = 0; inst < n_inst; ++inst) {
+            uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) dst[q] = src[q];
+            for (int q = 0; q < 9; ++q) dst[q] = src[q];
+        }
+        if (p.stats) {
+            atomicAdd(&p.stats[0], (unsigned long long)n_inst);
+            if (!ok) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
+        }
     }
-    if (p.stats) {
-        unsigned long long n_inst = p.total_tris / p.tris_per_instance;
-        atomicAdd(&p.stats[0], n_inst);
-        if (!ok) atomicAdd(&p.stats[1], n_inst);
+    if (p.binned) {  // first binning pass fused here: count the tiles each triangle overlaps
+        int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+        bool valid = in_range && tile_range(p, &r, tx0, tx1, ty0, ty1);
+        bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
 
 // ---- binning --------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ bool tile_range(const DrawParams& p, const TriRec* r, int& tx0, int& tx1, int& ty0, int& ty1) {
-    int4 bb = *reinterpret_cast<const int4*>(r);  // minx, maxx, miny, maxy
-    if (bb.x > bb.y) return false;
-    tx0 = bb.x / kTileW - (int)p.tile_x0;
-    tx1 = bb.y / kTileW - (int)p.tile_x0;
-    ty0 = bb.z / kTileH - (int)p.tile_y0;
-    ty1 = bb.w / kTileH - (int)p.tile_y0;
-    return true;
-}
-
-// FILL == false: count entries per tile; FILL == true: write triangle ids into the tile segments.
-// One warp per triangle so that wide triangles spread their tiles over the lanes.
-template <bool FILL>
-__global__ void __launch_bounds__(256) bin_kernel(const __grid_constant__ DrawParams p) {
-    uint32_t warp = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    uint32_t nwarps = (gridDim.x * 256u) >> 5;
-    for (uint32_t t = warp; t < p.total_tris; t += nwarps) {
-        int tx0, tx1, ty0, ty1;
-        if (!tile_range(p, &p.tris[t], tx0, tx1, ty0, ty1)) continue;
-        int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
-        for (int k = lane; k < n; k += 32) {
-            int ty = ty0 + k / w, tx = tx0 + k % w;
-            uint32_t tile = (uint32_t)ty * p.tiles_x + (uint32_t)tx;
-            if (!FILL) {
-                atomicAdd(&p.tile_counts[tile], 1u);
-            } else {
-                uint32_t pos = p.tile_offsets[tile] + atomicAdd(&p.tile_cursor[tile], 1u);
-                if (pos < p.bin_capacity) p.bin_entries[pos] = t;
-            }
-        }
-    }
+// second binning pass: one thread per triangle record writes its id into every tile segment it overlaps
+__global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+    bool valid = t < p.total_tris && tile_range(p, &p.tris[t], tx0, tx1, ty0, ty1);
+    bin_emit<true>(p, valid, t, 1u, tx0, tx1, ty0, ty1);
 }
 
 // exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
@@ -368,8 +392,14 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 
 // ---- raster ------------------------------------------------------------------------------------------------------------
 
+struct FragQueue {  // covered fragments of one row waiting for a full 32-lane shading batch, in primitive order
+    uint32_t key[64];  // staged-record slot << 8 | x within the tile
+    float z[64], l0[64], l1[64], l2[64];
+};
+
 struct RasterShared {
     TriRec recs[kRecs];
+    FragQueue queue[kTileH];
     uint32_t list[kSortCap];         // binned: the tile's sorted triangle ids; direct: ids surviving the current round
     uint32_t color[kTileH][kTileW];  // the tile's colour and depth live here for the whole triangle list
     float depth[kTileH][kTileW];
@@ -410,12 +440,78 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
     return out;
 }
 
+// Depth test, fragment program and blend for the first `n` (<= 32) queued fragments of a warp's row, one fragment per lane.
+// Fragments of the batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
+template <uint32_t FS, bool NEED_DST>
+__device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n,
+                                                int tile_px0, int py, bool depth_test, bool depth_write, bool has_color,
+                                                uint32_t& n_passed) {
+    const FragQueue& fq = sh.queue[warp];
+    const bool have = lane < n;
+    uint32_t kx = 0x80000000u | lane;  // unique key for idle lanes
+    uint32_t slot = 0;
+    float z = 0.0f, l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
+    if (have) {
+        const uint32_t key = fq.key[lane];
+        kx = key & 255u;
+        slot = key >> 8;
+        z = fq.z[lane];
+        l0 = fq.l0[lane];
+        l1 = fq.l1[lane];
+        l2 = fq.l2[lane];
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, kx);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    const uint32_t max_rank = __reduce_max_sync(0xffffffffu, have ? rank : 0u);
+    const TriRec& t = sh.recs[slot];
+    float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (have && has_color && (max_rank > 0 || !depth_test)) {
+        // several fragments per pixel in this batch (or no depth test): shade up front, all lanes together
+        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+            fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+        } else {
+            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) src[ch] = __fdiv_rn(fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch])), den);
+        }
+    }
+    for (uint32_t rk = 0; rk <= max_rank; ++rk) {
+        if (have && rank == rk) {
+            bool pass = true;
+            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.depth[warp][kx]);  // R7: early-Z
+            if (pass) {
+                ++n_passed;
+                if (depth_write) {
+                    sh.depth[warp][kx] = z;
+                    atomicOr(&sh.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                }
+                if (has_color) {
+                    if (max_rank == 0 && depth_test) {  // one fragment per pixel: shade only what passed the depth test
+                        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                            fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+                        } else {
+                            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch)
+                                src[ch] = __fdiv_rn(fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch])), den);
+                        }
+                    }
+                    const uint32_t dst = NEED_DST ? sh.color[warp][kx] : 0u;
+                    sh.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                    atomicOr(&sh.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
 // for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
 // time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
 // Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
 template <uint32_t FS, bool NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -502,6 +598,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
 
     const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
     uint32_t n_covered = 0, n_passed = 0;
+    uint32_t q_n = 0;  // fragments waiting in my warp's queue (warp-uniform)
 
     for (uint32_t base = 0; base < n_source; base += kRecs) {
         // ---- stage up to kRecs triangle records that touch this tile, in primitive order ----
@@ -541,7 +638,7 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
         }
         __syncthreads();
 
-        // ---- my row: stream the candidate pixels of the staged triangles, 32 per step ----
+        // ---- my row: stream the candidate pixels of the staged triangles, 32 per step; covered ones are queued ----
         if (row_in) {
             for (uint32_t chunk = 0; chunk < n_round; chunk += 32) {
                 // lane j looks at triangle chunk+j: which pixels of my row are in its bounding box?
@@ -576,7 +673,8 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
                     const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
                     const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
                     const int px = o_xa + (int)(c - o_excl);
-                    const TriRec& t = sh.recs[chunk + pos];
+                    const uint32_t slot = chunk + pos;
+                    const TriRec& t = sh.recs[slot];
                     bool cov = false;
                     float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
                     if (active) {
@@ -596,49 +694,39 @@ __global__ void __launch_bounds__(kRasterThreads, 3) raster_kernel(const __grid_
                             cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
                         }
                     }
-                    if (!__any_sync(0xffffffffu, cov)) continue;
-                    if (cov) ++n_covered;
-                    const uint32_t key = cov ? (uint32_t)(px - tile_px0) : (0x80000000u | lane);
-                    // fragments of this batch on the same pixel: apply in lane order
-                    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-                    const uint32_t max_rank = __reduce_max_sync(0xffffffffu, cov ? rank : 0u);
-                    float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    bool shaded = false;
-                    for (uint32_t rk = 0; rk <= max_rank; ++rk) {
-                        if (cov && rank == rk) {
-                            const uint32_t kx = key;
-                            bool pass = true;
-                            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.depth[warp][kx]);  // R7: early-Z
-                            if (pass) {
-                                ++n_passed;
-                                if (depth_write) {
-                                    sh.depth[warp][kx] = z;
-                                    atomicOr(&sh.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
-                                }
-                                if (has_color) {
-                                    if (!shaded) {
-                                        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-                                            fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
-                                        } else {
-                                            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
-#pragma unroll
-                                            for (int ch = 0; ch < 4; ++ch) {
-                                                float num = fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch]));
-                                                src[ch] = __fdiv_rn(num, den);
-                                            }
-                                        }
-                                        shaded = true;
-                                    }
-                                    const uint32_t dst = NEED_DST ? sh.color[warp][kx] : 0u;
-                                    sh.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                                    atomicOr(&sh.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
-                                }
-                            }
-                        }
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, cov);
+                    if (!ballot) continue;
+                    if (cov) {  // append to my warp's fragment queue, keeping primitive order
+                        ++n_covered;
+                        FragQueue& fq = sh.queue[warp];
+                        const uint32_t at = q_n + __popc(ballot & ((1u << lane) - 1u));
+                        fq.key[at] = (slot << 8) | (uint32_t)(px - tile_px0);
+                        fq.z[at] = z;
+                        fq.l0[at] = l0;
+                        fq.l1[at] = l1;
+                        fq.l2[at] = l2;
+                    }
+                    q_n += __popc(ballot);
+                    __syncwarp();
+                    if (q_n >= 32) {
+                        shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+                        // move the remainder (< 32 entries) to the front
+                        FragQueue& fq = sh.queue[warp];
+                        const bool mv = lane < q_n - 32u;
+                        uint32_t k = 0;
+                        float fz = 0, f0 = 0, f1 = 0, f2 = 0;
+                        if (mv) { k = fq.key[32 + lane]; fz = fq.z[32 + lane]; f0 = fq.l0[32 + lane]; f1 = fq.l1[32 + lane]; f2 = fq.l2[32 + lane]; }
+                        __syncwarp();
+                        if (mv) { fq.key[lane] = k; fq.z[lane] = fz; fq.l0[lane] = f0; fq.l1[lane] = f1; fq.l2[lane] = f2; }
+                        q_n -= 32u;
                         __syncwarp();
                     }
                 }
+            }
+            // the staged records go away at the end of the round: drain the queue
+            if (q_n) {
+                shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+                q_n = 0;
             }
         }
         __syncthreads();  // before the next round overwrites recs / list
@@ -869,19 +957,14 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         s->attrs_set = true;
     }
 
+    if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
     setup_kernel<<<(uint32_t)((ntri + 255) / 256), 256, 0, q->stream>>>(p);
     if ((r = kzn_launched(q, "setup_kernel"))) return r;
     if (p.binned) {
-        KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
-        uint32_t bin_blocks = (uint32_t)((total * 32 + 255) / 256);
-        uint32_t cap = (uint32_t)q->device->sm_count * 16;
-        if (bin_blocks > cap) bin_blocks = cap;
-        bin_kernel<false><<<bin_blocks, 256, 0, q->stream>>>(p);
-        if ((r = kzn_launched(q, "bin_kernel<count>"))) return r;
         bin_scan_kernel<<<1, 1024, 0, q->stream>>>(p);
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
-        bin_kernel<true><<<bin_blocks, 256, 0, q->stream>>>(p);
-        if ((r = kzn_launched(q, "bin_kernel<fill>"))) return r;
+        bin_fill_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, q->stream>>>(p);
+        if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     // the destination colour is only read when the result depends on it
