@@ -31,6 +31,7 @@ constexpr int kPx = 4;                   // horizontally adjacent pixels per thr
 constexpr int kTileW = 32 * kPx, kTileH = 8;  // pixels per raster tile: one warp per row -> 512 B row stores
 constexpr int kRasterThreads = 32 * kTileH;
 constexpr int kRecs = 128;               // triangle records staged in shared memory per round
+constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -139,8 +140,26 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
             if (pos < p.bin_capacity) p.bin_entries[pos] = tri;
         }
     };
-    if (n <= kSmall)
-        for (int k = 0; k < n; ++k) emit((uint32_t)(ty0 + k / w) * p.tiles_x + (uint32_t)(tx0 + k % w), t, weight);
+    // small triangles: lane-per-triangle, but lanes that hit the same tile in the same step share ONE atomic
+    // (neighbouring triangles of a mesh mostly fall into the same tile, which would otherwise serialise at the L2)
+    const int n_small = n <= kSmall ? n : 0;
+    const int steps = __reduce_max_sync(0xffffffffu, n_small);
+    for (int k = 0; k < steps; ++k) {
+        const bool act = k < n_small;
+        const uint32_t tile = act ? (uint32_t)(ty0 + k / w) * p.tiles_x + (uint32_t)(tx0 + k % w) : (0xffffffffu - lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (act && (int)lane == leader) {
+            if (!FILL) atomicAdd(&p.tile_counts[tile], weight * (uint32_t)__popc(peers));
+            else base = p.tile_offsets[tile] + atomicAdd(&p.tile_cursor[tile], (uint32_t)__popc(peers));
+        }
+        if (FILL) {
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (act && base + rank < p.bin_capacity) p.bin_entries[base + rank] = t;
+        }
+    }
     uint32_t big = __ballot_sync(0xffffffffu, n > kSmall);
     while (big) {
         const int src = __ffs(big) - 1;
@@ -506,6 +525,110 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
     }
 }
 
+// 4 interleaved orbits (independent dependency chains keep the fma pipe busy at any occupancy)
+__device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_w, float inv_h, float rgba[kPx][4]) {
+    float cx[kPx], zx[kPx], zy[kPx];
+    float v = ((float)py + 0.5f) * inv_h;
+    float cy = fmaf(v, 2.0f, -1.0f);
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        float u = ((float)(px0 + k) + 0.5f) * inv_w;
+        cx[k] = fmaf(u, 3.5f, -2.5f);
+        zx[k] = 0.0f;
+        zy[k] = 0.0f;
+    }
+#pragma unroll 4
+    for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) {
+            float t = fmaf(zx[k], zx[k], cx[k]);
+            float nzx = fmaf(-zy[k], zy[k], t);
+            float nzy = fmaf(zx[k] + zx[k], zy[k], cy);
+            zx[k] = nzx;
+            zy[k] = nzy;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        float m = fmaf(zx[k], zx[k], zy[k] * zy[k]);
+        rgba[k][0] = 0.25f * m;
+        rgba[k][1] = fmaf(zx[k], 0.5f, 0.5f);
+        rgba[k][2] = fmaf(zy[k], 0.5f, 0.5f);
+        rgba[k][3] = 1.0f;
+    }
+}
+
+// A triangle whose span covers at least half of the warp's row: lane l handles the 4 pixels 4l..4l+3 of the row directly
+// (edge functions stepped by +16a per pixel, 16-byte shared-memory accesses), the way a full-screen fill wants it.
+template <uint32_t FS, bool NEED_DST>
+__device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
+                                           int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
+                                           uint32_t& n_covered, uint32_t& n_passed) {
+    const TriRec& t = sh.recs[slot];
+    const int px0 = tile_px0 + (int)lane * kPx;
+    const int32_t sx = 16 * px0 + 8;
+    long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
+    long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
+    long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
+    const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
+    const uint32_t bias = t.bias_bits;
+    const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
+    const float inv2a = t.inv2a;
+    const int minx = t.minx, maxx = t.maxx;
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
+    float depth[kPx] = {dq.x, dq.y, dq.z, dq.w};
+    float l0[kPx], l1[kPx], l2[kPx];
+    uint32_t live = 0, zwrite = 0;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+        const long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
+        bool cov = px0 + k >= minx && px0 + k <= maxx && f0 + b0 > 0 && f1 + b1 > 0 && f2 + b2 > 0;
+        l0[k] = (float)f0 * inv2a;  // R6
+        l1[k] = (float)f1 * inv2a;
+        l2[k] = (float)f2 * inv2a;
+        const float z = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
+        cov = cov && z >= p.zclip_lo && z <= p.zclip_hi;  // R3
+        if (cov) {
+            ++n_covered;
+            if (!depth_test || depth_compare(p.st.depth_compare_op, z, depth[k])) {  // R7: early-Z
+                ++n_passed;
+                live |= 1u << k;
+                if (depth_write) {
+                    depth[k] = z;
+                    zwrite |= 1u << k;
+                }
+            }
+        }
+    }
+    if (zwrite) {
+        *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+        atomicOr(&sh.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
+    }
+    if (live && has_color) {
+        float src[kPx][4];
+        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+            fs_procedural_orbit4(px0, py, p.inv_fb_w, p.inv_fb_h, src);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k) {
+                float den = fmaf(l2[k], t.iw[2], fmaf(l1[k], t.iw[1], l0[k] * t.iw[0]));
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    src[k][ch] = __fdiv_rn(fmaf(l2[k], t.col[2][ch], fmaf(l1[k], t.col[1][ch], l0[k] * t.col[0][ch])), den);
+            }
+        }
+        uint4 cq = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);  // pixels not live keep their value
+        uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+        for (int k = 0; k < kPx; ++k)
+            if (live >> k & 1u) col[k] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src[k], col[k]);
+        *reinterpret_cast<uint4*>(&sh.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
+        atomicOr(&sh.color_dirty[warp][lane >> 3], live << ((lane & 7u) * 4u));
+    }
+    __syncwarp();
+}
+
 // One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
 // for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
 // time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
@@ -652,6 +775,10 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
                         width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
                     }
                 }
+                // spans covering at least half the row go through the quad path (4 pixels per lane, no queue);
+                // they split the chunk into segments of ordinary candidates so that primitive order is kept
+                uint32_t wide_mask = __ballot_sync(0xffffffffu, width >= (uint32_t)kWideSpan);
+                if (width >= (uint32_t)kWideSpan) width = 0;
                 uint32_t incl = width;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -660,9 +787,13 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
                 }
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t excl = incl - width;
-                for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+                uint32_t seg_begin = 0;
+                for (;;) {
+                    const int wide_lane = wide_mask ? __ffs(wide_mask) - 1 : -1;
+                    const uint32_t seg_end = wide_lane >= 0 ? __shfl_sync(0xffffffffu, excl, wide_lane) : total;
+                for (uint32_t c0 = seg_begin; c0 < seg_end; c0 += 32) {
                     const uint32_t c = c0 + lane;
-                    const bool active = c < total;
+                    const bool active = c < seg_end;
                     // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
                     uint32_t pos = 0;
 #pragma unroll
@@ -721,6 +852,17 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
                         q_n -= 32u;
                         __syncwarp();
                     }
+                }
+                    if (wide_lane < 0) break;
+                    // a wide span: everything queued so far comes first, then the span itself, 4 pixels per lane
+                    if (q_n) {
+                        shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+                        q_n = 0;
+                    }
+                    shade_wide<FS, NEED_DST>(p, sh, warp, lane, chunk + (uint32_t)wide_lane, tile_px0, py, sy, depth_test, depth_write,
+                                             has_color, n_covered, n_passed);
+                    wide_mask &= wide_mask - 1;
+                    seg_begin = seg_end;
                 }
             }
             // the staged records go away at the end of the round: drain the queue

@@ -212,4 +212,17 @@ def draw_scenes() -> list[Scene]:
             sl.append([pnt[0], pnt[1], zz, *col])
     scenes.append(Scene("slivers_and_large", 256, 160, np.array(sl, dtype=np.float32),
                         state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    # wide spans (>= 64 px of a row: quad path) interleaved with small triangles, order-dependent state
+    mx = []
+    for k in range(400):
+        c = rng.uniform(-1.1, 1.1, 2)
+        size = 1.6 if k % 5 == 0 else (0.5 if k % 3 == 0 else 0.05)
+        col = rng.uniform(0, 1, 4)
+        for _ in range(3):
+            o = rng.uniform(-size, size, 2)
+            mx.append([c[0] + o[0], c[1] + o[1], rng.uniform(0, 1), *col])
+    scenes.append(Scene("mixed_sizes_blend_depth", 300, 170, np.array(mx, dtype=np.float32),
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    scenes.append(Scene("mixed_sizes_additive_tiled", 300, 170, np.array(mx[:600], dtype=np.float32) * np.array([1, 1, 1, 0.1, 0.1, 0.1, 0.1], dtype=np.float32),
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND), color_tiling=T))
     return scenes
