@@ -89,6 +89,8 @@ typedef struct KznCallable {
     void* self;
 } KznCallable;
 
+/* Compiler::name (lib.rs:249): "PTX (sm_100a)" where the reference's only back end answers "LLVM 7" */
+KZN_API const char* kzn_backend_compiler_name(void);
 KZN_API KznResult kzn_backend_context_create(KznBackendContext** context); /* the Context handed to CompilerUser::run */
 KZN_API void kzn_backend_context_destroy(KznBackendContext* context);
 /* TypeBuilder (types.rs:113-153) */
@@ -106,11 +108,17 @@ KZN_API KznBackendType* kzn_backend_type_function(KznBackendContext* c, KznBacke
 KZN_API uint64_t kzn_backend_type_size(const KznBackendType* type);
 /* Context::create_module / Module::add_function / Function::append_new_basic_block / Context::create_builder */
 KZN_API KznBackendModule* kzn_backend_create_module(KznBackendContext* c, const char* name);
+KZN_API KznResult kzn_backend_module_set_source_file_name(KznBackendModule* m, const char* source_file_name); /* lib.rs:136 */
 /* names must match [A-Za-z_.$-][A-Za-z0-9_.$-]* and be unique, as backend.rs:444-459 checks; NULL otherwise */
 KZN_API KznBackendFunction* kzn_backend_add_function(KznBackendModule* m, const char* name, KznBackendType* function_type);
-KZN_API KznBackendBlock* kzn_backend_append_new_basic_block(KznBackendFunction* f, const char* name);
+KZN_API KznBackendBlock* kzn_backend_append_new_basic_block(KznBackendFunction* f, const char* name); /* name may be NULL */
+KZN_API uint64_t kzn_backend_function_parameter_count(const KznBackendFunction* f);                   /* Function::parameters lib.rs:123 */
+KZN_API KznBackendValue* kzn_backend_function_parameter(KznBackendFunction* f, uint64_t index);
+KZN_API KznBackendValue* kzn_backend_function_as_value(KznBackendFunction* f); /* Function::as_value lib.rs:116 */
+KZN_API KznBackendValue* kzn_backend_block_as_value(KznBackendBlock* b);       /* BasicBlock::as_value lib.rs:99 */
 KZN_API KznBackendBuilder* kzn_backend_create_builder(KznBackendContext* c);
 KZN_API KznResult kzn_backend_builder_attach(KznBackendBuilder* b, KznBackendBlock* block);
+KZN_API KznBackendBlock* kzn_backend_builder_current_basic_block(KznBackendBuilder* b); /* lib.rs:19; NULL when detached */
 /* AttachedBuilder::build_alloca (lib.rs:25) / build_return (lib.rs:26-29); value NULL = `ret void` */
 KZN_API KznBackendValue* kzn_backend_build_alloca(KznBackendBuilder* b, KznBackendType* variable_type);
 KZN_API KznResult kzn_backend_build_return(KznBackendBuilder* b, KznBackendValue* value);

@@ -12,6 +12,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 HEADER = ROOT / "include" / "kazan_b200.h"
+BACKEND_HEADER = ROOT / "include" / "kazan_b200_backend.h"
+HEADERS = (HEADER, BACKEND_HEADER)
 
 # results -------------------------------------------------------------------------------------
 SUCCESS = 0
@@ -218,15 +220,80 @@ PROTOTYPES = {
 }
 
 
-def declared_symbols(header: Path = HEADER) -> list[str]:
-    """Every function the C header declares with KZN_API (what the library must export)."""
-    text = header.read_text()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return re.findall(r"KZN_API\s+[^;(]*?\b(kzn_\w+)\s*\(", text)
+class LaunchDims(C.Structure):  # kazan_b200_backend.h KznLaunchDims
+    _fields_ = [("grid", u32 * 3), ("block", u32 * 3)]
+
+
+CALLABLE_FN = C.CFUNCTYPE(i32, vp, vp, P(LaunchDims), P(vp))
+
+
+class Callable(C.Structure):  # kazan_b200_backend.h KznCallable
+    _fields_ = [("call", CALLABLE_FN), ("self", vp)]
+
+
+sz = C.c_size_t
+cp = C.c_char_p
+# include/kazan_b200_backend.h
+BACKEND_PROTOTYPES = {
+    "kzn_ir_parse": (i32, [cp, sz, P(vp)]),
+    "kzn_ir_module_destroy": (None, [vp]),
+    "kzn_ir_to_text": (i32, [vp, P(vp), P(sz)]),
+    "kzn_ir_round_trip": (i32, [cp, cp, sz, P(vp), P(sz)]),
+    "kzn_free": (None, [vp]),
+    "kzn_translate_spirv_to_ir": (i32, [P(u32), sz, cp, u32, P(vp), P(u32)]),
+    "kzn_ptx_from_ir": (i32, [vp, P(vp), P(sz)]),
+    "kzn_compute_pipeline_create": (i32, [vp, vp, P(u32), P(vp)]),
+    "kzn_pipeline_destroy": (None, [vp]),
+    "kzn_cmd_dispatch": (i32, [vp, vp, P(u32), P(u32), u64, u64, u64]),
+    "kzn_pipeline_inputs_size": (u64, [vp]),
+    "kzn_pipeline_outputs_size": (u64, [vp]),
+    "kzn_backend_compiler_name": (cp, []),
+    "kzn_backend_context_create": (i32, [P(vp)]),
+    "kzn_backend_context_destroy": (None, [vp]),
+    "kzn_backend_type_bool": (vp, [vp]),
+    "kzn_backend_type_int": (vp, [vp, u32, i32]),
+    "kzn_backend_type_f32": (vp, [vp]),
+    "kzn_backend_type_f64": (vp, [vp]),
+    "kzn_backend_type_pointer": (vp, [vp, vp]),
+    "kzn_backend_type_array": (vp, [vp, vp, u64]),
+    "kzn_backend_type_vector": (vp, [vp, vp, u64]),
+    "kzn_backend_type_struct": (vp, [vp, P(vp), u64]),
+    "kzn_backend_type_function": (vp, [vp, vp, P(vp), u64]),
+    "kzn_backend_type_size": (u64, [vp]),
+    "kzn_backend_create_module": (vp, [vp, cp]),
+    "kzn_backend_module_set_source_file_name": (i32, [vp, cp]),
+    "kzn_backend_add_function": (vp, [vp, cp, vp]),
+    "kzn_backend_append_new_basic_block": (vp, [vp, cp]),
+    "kzn_backend_function_parameter_count": (u64, [vp]),
+    "kzn_backend_function_parameter": (vp, [vp, u64]),
+    "kzn_backend_function_as_value": (vp, [vp]),
+    "kzn_backend_block_as_value": (vp, [vp]),
+    "kzn_backend_create_builder": (vp, [vp]),
+    "kzn_backend_builder_attach": (i32, [vp, vp]),
+    "kzn_backend_builder_current_basic_block": (vp, [vp]),
+    "kzn_backend_build_alloca": (vp, [vp, vp]),
+    "kzn_backend_build_return": (i32, [vp, vp]),
+    "kzn_backend_module_verify": (i32, [vp]),
+    "kzn_backend_module_to_ptx": (i32, [vp, P(vp), P(sz)]),
+    "kzn_backend_compile": (i32, [vp, vp, P(cp), P(vp), u64, P(vp)]),
+    "kzn_compiled_code_get": (i32, [vp, cp, P(Callable)]),
+    "kzn_compiled_code_destroy": (None, [vp]),
+}
+ALL_PROTOTYPES = {**PROTOTYPES, **BACKEND_PROTOTYPES}
+
+
+def declared_symbols(header: Path | None = None) -> list[str]:
+    """Every function the C headers declare with KZN_API (what the library must export)."""
+    out = []
+    for h in ((header,) if header else HEADERS):
+        text = h.read_text()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        out += re.findall(r"KZN_API\s+[^;(]*?\b(kzn_\w+)\s*\(", text)
+    return out
 
 
 def bind(lib: C.CDLL, prototypes: dict | None = None) -> C.CDLL:
-    for name, (res, args) in (prototypes or PROTOTYPES).items():
+    for name, (res, args) in (prototypes or ALL_PROTOTYPES).items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

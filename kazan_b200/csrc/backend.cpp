@@ -1,0 +1,746 @@
+// backend.cpp — C ABI of `shader-compiler-backend-ptx` (include/kazan_b200_backend.h).
+//
+// Replaces / mirrors (paths in the kazan-3d/kazan tree):
+//   shader-compiler-backend/src/lib.rs:15-257      the backend trait surface (Context, Module, Function, BasicBlock,
+//                                                  Attached/DetachedBuilder, Compiler::run, CompiledCode::get)
+//   shader-compiler-backend/src/types.rs:113-153   TypeBuilder
+//   shader-compiler-backend-llvm-7/src/backend.rs  the LLVM-7 implementation of that surface (:444-459 name rule,
+//                                                  :477 verify, :553-690 Compiler::run, :645-657 symbol lookup)
+//   shader-compiler/src/lib.rs:753-821             ComputePipeline::new
+//   vulkan-driver/src/api_impl.rs:4677-4684,:5079-5089   vkCmdDispatch / vkCmdDispatchBase (unimplemented!())
+// Code is loaded with the CUDA *driver* API (cuModuleLoadDataEx / cuModuleGetFunction / cuLaunchKernel), resolved with
+// dlopen at first use so that everything that only produces PTX text works without a GPU or a driver.
+#include <dlfcn.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/kazan_b200_backend.h"
+#include "kzn_internal.h"
+#include "ptx_emit.h"
+
+// ---- CUDA driver API, bound at run time -------------------------------------------------------------------------------
+namespace {
+
+typedef int CUresult_;
+typedef void* CUmodule_;
+typedef void* CUfunction_;
+typedef void* CUcontext_;
+enum { CU_JIT_INFO_LOG_BUFFER_ = 3, CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES_ = 4, CU_JIT_ERROR_LOG_BUFFER_ = 5, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES_ = 6 };
+
+struct DriverApi {
+    void* handle = nullptr;
+    CUresult_ (*cuInit)(unsigned) = nullptr;
+    CUresult_ (*cuCtxGetCurrent)(CUcontext_*) = nullptr;
+    CUresult_ (*cuModuleLoadDataEx)(CUmodule_*, const void*, unsigned, int*, void**) = nullptr;
+    CUresult_ (*cuModuleGetFunction)(CUfunction_*, CUmodule_, const char*) = nullptr;
+    CUresult_ (*cuModuleUnload)(CUmodule_) = nullptr;
+    CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+    CUresult_ (*cuGetErrorString)(CUresult_, const char**) = nullptr;
+    std::string error;
+};
+
+DriverApi* driver() {
+    static DriverApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libcuda.so.1", "libcuda.so"}) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = "libcuda.so.1 cannot be loaded: no NVIDIA driver on this machine";
+            return;
+        }
+        auto sym = [&](const char* n) {
+            void* p = dlsym(api.handle, n);
+            if (!p && api.error.empty()) api.error = std::string("libcuda is missing ") + n;
+            return p;
+        };
+        api.cuInit = (decltype(api.cuInit))sym("cuInit");
+        api.cuCtxGetCurrent = (decltype(api.cuCtxGetCurrent))sym("cuCtxGetCurrent");
+        api.cuModuleLoadDataEx = (decltype(api.cuModuleLoadDataEx))sym("cuModuleLoadDataEx");
+        api.cuModuleGetFunction = (decltype(api.cuModuleGetFunction))sym("cuModuleGetFunction");
+        api.cuModuleUnload = (decltype(api.cuModuleUnload))sym("cuModuleUnload");
+        api.cuLaunchKernel = (decltype(api.cuLaunchKernel))sym("cuLaunchKernel");
+        api.cuGetErrorString = (decltype(api.cuGetErrorString))sym("cuGetErrorString");
+    });
+    return &api;
+}
+
+KznResult driver_failed(CUresult_ r, const char* what) {
+    const char* s = nullptr;
+    DriverApi* d = driver();
+    if (d->cuGetErrorString) d->cuGetErrorString(r, &s);
+    kzn_set_error("CUDA driver error %d (%s) in %s", r, s ? s : "?", what);
+    return r == 100 /* NO_DEVICE */ || r == 3 /* NOT_INITIALIZED */ ? KZN_ERROR_INITIALIZATION_FAILED : KZN_ERROR_DEVICE_LOST;
+}
+
+// PTX text -> module in the device's primary context
+KznResult load_ptx(KznDevice* device, const std::string& ptx, CUmodule_* module) {
+    KZN_VALID(device, "null device");
+    DriverApi* d = driver();
+    KZN_REQUIRE(d->error.empty(), KZN_ERROR_INITIALIZATION_FAILED, "%s", d->error.c_str());
+    KZN_CUDA(cudaSetDevice(device->ordinal));
+    KZN_CUDA(cudaFree(0));
+    CUcontext_ ctx = nullptr;
+    CUresult_ r = d->cuCtxGetCurrent(&ctx);
+    if (r != 0) return driver_failed(r, "cuCtxGetCurrent");
+    KZN_REQUIRE(ctx, KZN_ERROR_INITIALIZATION_FAILED, "no current CUDA context");
+    char info[4096] = "", err[4096] = "";
+    int opts[4] = {CU_JIT_INFO_LOG_BUFFER_, CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES_, CU_JIT_ERROR_LOG_BUFFER_, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES_};
+    void* vals[4] = {info, (void*)(uintptr_t)sizeof info, err, (void*)(uintptr_t)sizeof err};
+    r = d->cuModuleLoadDataEx(module, ptx.c_str(), 4, opts, vals);
+    if (r != 0) {
+        const char* s = nullptr;
+        d->cuGetErrorString(r, &s);
+        kzn_set_error("cuModuleLoadDataEx failed: %d (%s): %.300s", r, s ? s : "?", err);
+        return KZN_ERROR_DEVICE_LOST;
+    }
+    return KZN_SUCCESS;
+}
+
+char* dup_text(const std::string& s, size_t* length) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) return nullptr;
+    memcpy(p, s.c_str(), s.size() + 1);
+    if (length) *length = s.size();
+    return p;
+}
+
+// run `fn`, mapping the IR library's exceptions to result codes (text goes to kzn_last_error)
+template <typename F>
+KznResult guarded(F&& fn) {
+    try {
+        return fn();
+    } catch (const kir::Unsupported& e) {
+        kzn_set_error("%s", e.what());
+        return KZN_ERROR_FEATURE_NOT_PRESENT;
+    } catch (const kir::Error& e) {
+        kzn_set_error("%s", e.what());
+        return KZN_ERROR_VALIDATION_FAILED;
+    } catch (const std::bad_alloc&) {
+        kzn_set_error("out of host memory");
+        return KZN_ERROR_OUT_OF_HOST_MEMORY;
+    } catch (const std::exception& e) {
+        kzn_set_error("%s", e.what());
+        return KZN_ERROR_VALIDATION_FAILED;
+    }
+}
+
+}  // namespace
+
+struct KznIrModule {
+    std::unique_ptr<kir::Module> module;
+};
+
+struct KznPipeline {
+    KznDevice* device = nullptr;
+    CUmodule_ module = nullptr;
+    CUfunction_ function = nullptr;
+    uint32_t local_size[3] = {1, 1, 1};
+    uint64_t inputs_size = 0, outputs_size = 0;
+    std::string ptx;
+};
+
+// ---- backend trait objects ----------------------------------------------------------------------------------------------
+enum class BtKind { Void, Bool, Int, F32, F64, Pointer, Array, Vector, Struct, Function };
+
+struct KznBackendType {
+    BtKind kind;
+    uint32_t bits = 0;
+    bool is_signed = false;
+    KznBackendType* element = nullptr;  // pointer target / array, vector element / function return (null = void)
+    uint64_t count = 0;
+    std::vector<KznBackendType*> members;  // struct members / function arguments
+    uint64_t size = 0, align = 1;
+};
+
+enum class BvKind { Parameter, Alloca, Function, Block };
+struct KznBackendValue {
+    BvKind kind;
+    KznBackendType* type = nullptr;
+    KznBackendFunction* function = nullptr;
+    uint32_t index = 0;  // parameter index / alloca slot
+};
+
+struct BackendInstr {
+    bool is_return = false;
+    KznBackendValue* value = nullptr;  // alloca result / returned value (may be null)
+    KznBackendType* type = nullptr;    // alloca type
+};
+
+struct KznBackendBlock {
+    KznBackendFunction* function = nullptr;
+    std::string name;
+    std::vector<BackendInstr> instrs;
+    bool terminated = false;
+    KznBackendValue* as_value = nullptr;
+};
+
+struct KznBackendFunction {
+    KznBackendModule* module = nullptr;
+    std::string name, symbol;
+    KznBackendType* type = nullptr;
+    std::vector<KznBackendValue*> parameters;
+    std::vector<KznBackendBlock*> blocks;
+    uint32_t allocas = 0;
+    KznBackendValue* as_value = nullptr;
+};
+
+struct KznBackendModule {
+    KznBackendContext* context = nullptr;
+    std::string name, source_file_name;
+    std::vector<KznBackendFunction*> functions;
+};
+
+struct KznBackendBuilder {
+    KznBackendContext* context = nullptr;
+    KznBackendBlock* block = nullptr;  // null = detached
+};
+
+struct KznBackendContext {  // owns everything created through it (the trait's 'a lifetime)
+    std::vector<std::unique_ptr<KznBackendType>> types;
+    std::vector<std::unique_ptr<KznBackendValue>> values;
+    std::vector<std::unique_ptr<KznBackendBlock>> blocks;
+    std::vector<std::unique_ptr<KznBackendFunction>> functions;
+    std::vector<std::unique_ptr<KznBackendModule>> modules;
+    std::vector<std::unique_ptr<KznBackendBuilder>> builders;
+
+    KznBackendType* type(KznBackendType t) {
+        types.push_back(std::make_unique<KznBackendType>(std::move(t)));
+        return types.back().get();
+    }
+    KznBackendValue* value(KznBackendValue v) {
+        values.push_back(std::make_unique<KznBackendValue>(v));
+        return values.back().get();
+    }
+};
+
+struct CompiledFunction {
+    CUfunction_ function = nullptr;
+    bool has_return_slot = false;
+    size_t parameter_count = 0;
+};
+
+struct KznCompiledCode {
+    KznDevice* device = nullptr;
+    CUmodule_ module = nullptr;
+    std::map<std::string, CompiledFunction> by_key;
+};
+
+namespace {
+
+bool valid_function_name(const char* s) {  // backend.rs:444-459: [A-Za-z_.$-][A-Za-z0-9_.$-]*
+    if (!s || !*s) return false;
+    for (const char* p = s; *p; ++p) {
+        unsigned char c = (unsigned char)*p;
+        bool head = isalpha(c) || c == '_' || c == '.' || c == '$' || c == '-';
+        if (!(head || (p != s && isdigit(c)))) return false;
+    }
+    return true;
+}
+
+std::string param_decl(const KznBackendType* t, const std::string& name) {
+    std::ostringstream o;
+    switch (t->kind) {
+        case BtKind::Bool: o << ".param .u8 " << name; break;
+        case BtKind::Int: o << ".param ." << (t->is_signed ? "s" : "u") << t->bits << " " << name; break;
+        case BtKind::F32: o << ".param .f32 " << name; break;
+        case BtKind::F64: o << ".param .f64 " << name; break;
+        case BtKind::Pointer:
+        case BtKind::Function: o << ".param .u64 " << name; break;
+        default: o << ".param .align " << t->align << " .b8 " << name << "[" << (t->size ? t->size : 1) << "]"; break;
+    }
+    return o.str();
+}
+
+// PTX of a module built through the trait surface: every function is a kernel; a non-void function gets a trailing
+// `.u64 kzn_return_slot` parameter where build_return stores its value
+std::string backend_module_ptx(const KznBackendModule* m) {
+    std::ostringstream o;
+    o << "//\n// Generated by kazan_b200 shader-compiler-backend-ptx; module '" << m->name << "'";
+    if (!m->source_file_name.empty()) o << ", source '" << m->source_file_name << "'";
+    o << "\n//\n.version 8.7\n.target sm_100a\n.address_size 64\n";
+    for (const KznBackendFunction* f : m->functions) {
+        if (f->blocks.empty()) continue;  // a declaration
+        const KznBackendType* ret = f->type->element;
+        o << "\n// " << f->name << "\n.visible .entry " << f->symbol << "(";
+        size_t np = f->type->members.size();
+        for (size_t i = 0; i < np; ++i) o << (i ? ",\n    " : "\n    ") << param_decl(f->type->members[i], "kzn_arg" + std::to_string(i));
+        if (ret) o << (np ? ",\n    " : "\n    ") << ".param .u64 kzn_return_slot";
+        o << (np || ret ? "\n)\n{\n" : ")\n{\n");
+        o << "    .reg .b16 %h<2>;\n    .reg .b32 %r<2>;\n    .reg .b64 %rd<4>;\n";
+        uint32_t slot = 0;
+        for (const KznBackendBlock* b : f->blocks)
+            for (const BackendInstr& in : b->instrs)
+                if (!in.is_return)
+                    o << "    .local .align " << (in.type->align ? in.type->align : 1) << " .b8 kzn_alloca" << slot++ << "[" << (in.type->size ? in.type->size : 1) << "];\n";
+        size_t bi = 0;
+        for (const KznBackendBlock* b : f->blocks) {
+            o << "$bb" << bi++ << "_" << kir::ptx_mangle(b->name) << ":\n";
+            for (const BackendInstr& in : b->instrs) {
+                if (!in.is_return) continue;
+                if (in.value && ret) {
+                    const KznBackendValue* v = in.value;
+                    o << "    ld.param.u64 %rd0, [kzn_return_slot];\n";
+                    if (v->kind == BvKind::Alloca) {
+                        o << "    mov.u64 %rd1, kzn_alloca" << v->index << ";\n    cvta.local.u64 %rd1, %rd1;\n    st.u64 [%rd0], %rd1;\n";
+                    } else if (v->kind == BvKind::Parameter) {
+                        const KznBackendType* t = v->type;
+                        std::string p = "[kzn_arg" + std::to_string(v->index) + "]";
+                        uint64_t sz = t->size;
+                        bool scalar = t->kind == BtKind::Bool || t->kind == BtKind::Int || t->kind == BtKind::F32 || t->kind == BtKind::F64 ||
+                                      t->kind == BtKind::Pointer || t->kind == BtKind::Function;
+                        if (scalar && sz == 8) o << "    ld.param.u64 %rd1, " << p << ";\n    st.u64 [%rd0], %rd1;\n";
+                        else if (scalar && sz == 4) o << "    ld.param.u32 %r0, " << p << ";\n    st.u32 [%rd0], %r0;\n";
+                        else if (scalar && sz == 2) o << "    ld.param.u16 %h0, " << p << ";\n    st.u16 [%rd0], %h0;\n";
+                        else if (scalar && sz == 1) o << "    ld.param.u8 %h0, " << p << ";\n    st.u8 [%rd0], %h0;\n";
+                        else
+                            for (uint64_t k = 0; k < sz; ++k)
+                                o << "    ld.param.u8 %h0, [kzn_arg" << v->index << "+" << k << "];\n    st.u8 [%rd0+" << k << "], %h0;\n";
+                    }
+                }
+                o << "    ret;\n";
+            }
+        }
+        o << "}\n";
+    }
+    return o.str();
+}
+
+KznResult verify_module(const KznBackendModule* m) {
+    KZN_VALID(m, "null module");
+    for (const KznBackendFunction* f : m->functions) {
+        for (const KznBackendBlock* b : f->blocks) {
+            KZN_VALID(b->terminated, "module verification failure: basic block '%s' of function '%s' does not have a terminator", b->name.c_str(),
+                      f->name.c_str());
+            for (const BackendInstr& in : b->instrs) {
+                if (!in.is_return) continue;
+                const KznBackendType* ret = f->type->element;
+                KZN_VALID(!!ret == !!in.value, "module verification failure: function '%s' return value does not match its return type", f->name.c_str());
+                if (in.value) {
+                    KZN_VALID(in.value->kind == BvKind::Alloca || in.value->kind == BvKind::Parameter,
+                              "module verification failure: function '%s' returns a value that is not first-class in this back end", f->name.c_str());
+                    KZN_VALID(in.value->function == f, "module verification failure: function '%s' returns a value of another function", f->name.c_str());
+                    KZN_VALID(in.value->type->size == ret->size, "module verification failure: function '%s' return value does not match its return type",
+                              f->name.c_str());
+                }
+            }
+        }
+    }
+    return KZN_SUCCESS;
+}
+
+KznResult callable_trampoline(void* self, KznQueue* queue, const KznLaunchDims* dims, void** arguments) {
+    CompiledFunction* f = (CompiledFunction*)self;
+    KZN_VALID(f && queue && dims, "KznCallable: null argument");
+    KznResult r = kzn_queue_enter(queue);
+    if (r != KZN_SUCCESS) return r;
+    for (int i = 0; i < 3; ++i) KZN_VALID(dims->grid[i] > 0 && dims->block[i] > 0, "KznCallable: empty launch dimension");
+    KZN_VALID(arguments || f->parameter_count + f->has_return_slot == 0, "KznCallable: null argument array");
+    CUresult_ cr = driver()->cuLaunchKernel(f->function, dims->grid[0], dims->grid[1], dims->grid[2], dims->block[0], dims->block[1], dims->block[2], 0,
+                                            (void*)queue->stream, arguments, nullptr);
+    if (cr != 0) return driver_failed(cr, "cuLaunchKernel");
+    queue->launches++;
+    return KZN_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- IR text ------------------------------------------------------------------------------------------------------------
+
+KznResult kzn_ir_parse(const char* text, size_t length, KznIrModule** module) {
+    KZN_VALID(text && module, "kzn_ir_parse: null argument");
+    *module = nullptr;
+    return guarded([&] {
+        auto m = kir::parse_module(std::string(text, length));
+        *module = new KznIrModule{std::move(m)};
+        return KZN_SUCCESS;
+    });
+}
+
+void kzn_ir_module_destroy(KznIrModule* module) { delete module; }
+
+KznResult kzn_ir_to_text(const KznIrModule* module, char** text, size_t* length) {
+    KZN_VALID(module && text, "kzn_ir_to_text: null argument");
+    *text = nullptr;
+    return guarded([&] {
+        *text = dup_text(kir::module_to_text(*module->module), length);
+        KZN_REQUIRE(*text, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
+KznResult kzn_ir_round_trip(const char* kind, const char* text, size_t length, char** out, size_t* out_length) {
+    KZN_VALID(kind && text && out, "kzn_ir_round_trip: null argument");
+    *out = nullptr;
+    return guarded([&] {
+        *out = dup_text(kir::round_trip(kind, std::string(text, length)), out_length);
+        KZN_REQUIRE(*out, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
+void kzn_free(void* ptr) { free(ptr); }
+
+// ---- SPIR-V -> IR -> PTX ---------------------------------------------------------------------------------------------------
+
+KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, const char* entry_point, uint32_t execution_model,
+                                    KznIrModule** module, uint32_t local_size[3]) {
+    KZN_VALID(words && entry_point && module, "kzn_translate_spirv_to_ir: null argument");
+    *module = nullptr;
+    return guarded([&] {
+        auto m = kir::translate_spirv(words, word_count, entry_point, execution_model, local_size);
+        *module = new KznIrModule{std::move(m)};
+        return KZN_SUCCESS;
+    });
+}
+
+KznResult kzn_ptx_from_ir(const KznIrModule* module, char** ptx, size_t* length) {
+    KZN_VALID(module && ptx, "kzn_ptx_from_ir: null argument");
+    *ptx = nullptr;
+    return guarded([&] {
+        *ptx = dup_text(kir::emit_ptx(*module->module, nullptr), length);
+        KZN_REQUIRE(*ptx, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
+// ---- compute pipelines -------------------------------------------------------------------------------------------------------
+
+KznResult kzn_compute_pipeline_create(KznDevice* device, const KznIrModule* module, const uint32_t local_size[3], KznPipeline** pipeline) {
+    KZN_VALID(device && module && pipeline, "kzn_compute_pipeline_create: null argument");
+    *pipeline = nullptr;
+    auto p = std::make_unique<KznPipeline>();
+    p->device = device;
+    for (int i = 0; i < 3; ++i) {
+        p->local_size[i] = local_size ? local_size[i] : 1;
+        KZN_VALID(p->local_size[i] > 0, "LocalSize component %d is zero", i);
+    }
+    kir::EntryInfo info;
+    KznResult r = guarded([&] {
+        p->ptx = kir::emit_ptx(*module->module, &info);
+        return KZN_SUCCESS;
+    });
+    if (r != KZN_SUCCESS) return r;
+    p->inputs_size = info.inputs_size;
+    p->outputs_size = info.outputs_size;
+    r = load_ptx(device, p->ptx, &p->module);
+    if (r != KZN_SUCCESS) return r;
+    CUresult_ cr = driver()->cuModuleGetFunction(&p->function, p->module, info.entry_name.c_str());
+    if (cr != 0) {
+        driver()->cuModuleUnload(p->module);
+        return driver_failed(cr, "cuModuleGetFunction");
+    }
+    *pipeline = p.release();
+    return KZN_SUCCESS;
+}
+
+void kzn_pipeline_destroy(KznPipeline* pipeline) {
+    if (!pipeline) return;
+    if (pipeline->module) {
+        cudaSetDevice(pipeline->device->ordinal);
+        driver()->cuModuleUnload(pipeline->module);
+    }
+    delete pipeline;
+}
+
+uint64_t kzn_pipeline_inputs_size(const KznPipeline* pipeline) { return pipeline ? pipeline->inputs_size : 0; }
+uint64_t kzn_pipeline_outputs_size(const KznPipeline* pipeline) { return pipeline ? pipeline->outputs_size : 0; }
+
+KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const uint32_t base_group[3], const uint32_t group_count[3],
+                           uint64_t user_inputs_address, uint64_t user_outputs_address, uint64_t first_invocation) {
+    KZN_VALID(queue && pipeline && group_count, "kzn_cmd_dispatch: null argument");
+    KznResult r = kzn_queue_enter(queue);
+    if (r != KZN_SUCCESS) return r;
+    KZN_VALID(queue->device->ordinal == pipeline->device->ordinal, "pipeline was created for another device");
+    // invocation count = groups * LocalSize; the base group only renumbers WorkgroupId (api_impl.rs:5079-5089), which
+    // the IR cannot observe (interface.rs:61-67 has no compute built-ins), so it does not move the interface slots
+    unsigned __int128 total = 1;
+    for (int i = 0; i < 3; ++i) {
+        if (base_group) KZN_VALID((uint64_t)base_group[i] + group_count[i] <= 0xffffffffull, "baseGroup + groupCount overflows in dimension %d", i);
+        total *= group_count[i];
+        total *= pipeline->local_size[i];
+    }
+    if (total == 0) return KZN_SUCCESS;  // a zero-sized dispatch is valid and does nothing
+    KZN_VALID(total <= (unsigned __int128)1 << 62, "dispatch of more than 2^62 invocations");
+    uint64_t count = (uint64_t)total;
+    KZN_VALID(pipeline->inputs_size == 0 || user_inputs_address, "pipeline reads user_inputs_block but no address was bound");
+    KZN_VALID(pipeline->outputs_size == 0 || user_outputs_address, "pipeline writes user_outputs_block but no address was bound");
+    // one invocation per thread, 256 per CTA whatever the LocalSize; CTAs folded into 2-D past the 2^31-1 x-limit
+    const unsigned threads = 256;
+    uint64_t ctas = (count + threads - 1) / threads;
+    uint64_t gx = ctas, gy = 1;
+    if (ctas > 0x7fffffffull) {
+        gx = 1ull << 30;
+        gy = (ctas + gx - 1) / gx;
+        KZN_VALID(gy <= 65535, "dispatch too large for one launch");
+    }
+    void* args[4] = {&user_inputs_address, &user_outputs_address, &count, &first_invocation};
+    CUresult_ cr = driver()->cuLaunchKernel(pipeline->function, (unsigned)gx, (unsigned)gy, 1, threads, 1, 1, 0, (void*)queue->stream, args, nullptr);
+    if (cr != 0) return driver_failed(cr, "cuLaunchKernel");
+    queue->launches++;
+    return KZN_SUCCESS;
+}
+
+// ---- the backend trait surface --------------------------------------------------------------------------------------------------
+
+const char* kzn_backend_compiler_name(void) { return "PTX (sm_100a)"; }  // Compiler::name lib.rs:249; LLVM's is "LLVM 7"
+
+KznResult kzn_backend_context_create(KznBackendContext** context) {
+    KZN_VALID(context, "null out pointer");
+    *context = new (std::nothrow) KznBackendContext();
+    KZN_REQUIRE(*context, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    return KZN_SUCCESS;
+}
+void kzn_backend_context_destroy(KznBackendContext* context) { delete context; }
+
+static KznBackendType* scalar_type(KznBackendContext* c, BtKind k, uint32_t bits, bool sgn) {
+    if (!c) return nullptr;
+    KznBackendType t{k};
+    t.bits = bits;
+    t.is_signed = sgn;
+    t.size = t.align = bits / 8;
+    return c->type(t);
+}
+KznBackendType* kzn_backend_type_bool(KznBackendContext* c) { return scalar_type(c, BtKind::Bool, 8, false); }
+KznBackendType* kzn_backend_type_int(KznBackendContext* c, uint32_t bits, int32_t is_signed) {
+    if (bits != 8 && bits != 16 && bits != 32 && bits != 64) {
+        kzn_set_error("integer types are 8, 16, 32 or 64 bits wide (types.rs:117-132)");
+        return nullptr;
+    }
+    return scalar_type(c, BtKind::Int, bits, is_signed != 0);
+}
+KznBackendType* kzn_backend_type_f32(KznBackendContext* c) { return scalar_type(c, BtKind::F32, 32, true); }
+KznBackendType* kzn_backend_type_f64(KznBackendContext* c) { return scalar_type(c, BtKind::F64, 64, true); }
+KznBackendType* kzn_backend_type_pointer(KznBackendContext* c, KznBackendType* target) {
+    if (!c || !target) return nullptr;
+    KznBackendType t{BtKind::Pointer};
+    t.element = target;
+    t.size = t.align = 8;
+    return c->type(t);
+}
+KznBackendType* kzn_backend_type_array(KznBackendContext* c, KznBackendType* element, uint64_t count) {
+    if (!c || !element) return nullptr;
+    KznBackendType t{BtKind::Array};
+    t.element = element;
+    t.count = count;
+    t.size = element->size * count;
+    t.align = element->align;
+    return c->type(t);
+}
+KznBackendType* kzn_backend_type_vector(KznBackendContext* c, KznBackendType* element, uint64_t length) {
+    if (!c || !element || length == 0) return nullptr;
+    KznBackendType t{BtKind::Vector};
+    t.element = element;
+    t.count = length;
+    t.size = element->size * length;
+    uint64_t a = 1;  // LLVM aligns a vector to its size rounded up to a power of two
+    while (a < t.size) a *= 2;
+    t.align = a > 16 ? 16 : a;
+    return c->type(t);
+}
+KznBackendType* kzn_backend_type_struct(KznBackendContext* c, KznBackendType* const* members, uint64_t count) {
+    if (!c || (count && !members)) return nullptr;
+    KznBackendType t{BtKind::Struct};
+    uint64_t off = 0, align = 1;
+    for (uint64_t i = 0; i < count; ++i) {
+        if (!members[i]) return nullptr;
+        t.members.push_back(members[i]);
+        uint64_t a = members[i]->align ? members[i]->align : 1;
+        off = (off + a - 1) / a * a;
+        off += members[i]->size;
+        if (a > align) align = a;
+    }
+    t.size = (off + align - 1) / align * align;
+    t.align = align;
+    return c->type(t);
+}
+KznBackendType* kzn_backend_type_function(KznBackendContext* c, KznBackendType* return_type, KznBackendType* const* arguments, uint64_t count) {
+    if (!c || (count && !arguments)) return nullptr;
+    KznBackendType t{BtKind::Function};
+    t.element = return_type;
+    for (uint64_t i = 0; i < count; ++i) {
+        if (!arguments[i]) return nullptr;
+        t.members.push_back(arguments[i]);
+    }
+    t.size = t.align = 8;
+    return c->type(t);
+}
+uint64_t kzn_backend_type_size(const KznBackendType* type) { return type ? type->size : 0; }
+
+KznBackendModule* kzn_backend_create_module(KznBackendContext* c, const char* name) {
+    if (!c || !name) return nullptr;
+    c->modules.push_back(std::make_unique<KznBackendModule>());
+    KznBackendModule* m = c->modules.back().get();
+    m->context = c;
+    m->name = name;
+    return m;
+}
+KznResult kzn_backend_module_set_source_file_name(KznBackendModule* m, const char* source_file_name) {
+    KZN_VALID(m && source_file_name, "null argument");
+    m->source_file_name = source_file_name;
+    return KZN_SUCCESS;
+}
+KznBackendFunction* kzn_backend_add_function(KznBackendModule* m, const char* name, KznBackendType* function_type) {
+    if (!m || !function_type || function_type->kind != BtKind::Function) {
+        kzn_set_error("add_function: the type is not a function type");
+        return nullptr;
+    }
+    if (!valid_function_name(name)) {
+        kzn_set_error("invalid function name '%s' (backend.rs:444-459)", name ? name : "");
+        return nullptr;
+    }
+    for (auto* f : m->functions)
+        if (f->name == name) {
+            kzn_set_error("function '%s' is already defined in module '%s'", name, m->name.c_str());
+            return nullptr;
+        }
+    KznBackendContext* c = m->context;
+    c->functions.push_back(std::make_unique<KznBackendFunction>());
+    KznBackendFunction* f = c->functions.back().get();
+    f->module = m;
+    f->name = name;
+    f->symbol = kir::ptx_mangle(name);
+    f->type = function_type;
+    for (uint32_t i = 0; i < function_type->members.size(); ++i)
+        f->parameters.push_back(c->value({BvKind::Parameter, function_type->members[i], f, i}));
+    f->as_value = c->value({BvKind::Function, function_type, f, 0});
+    m->functions.push_back(f);
+    return f;
+}
+uint64_t kzn_backend_function_parameter_count(const KznBackendFunction* f) { return f ? f->parameters.size() : 0; }
+KznBackendValue* kzn_backend_function_parameter(KznBackendFunction* f, uint64_t index) {
+    return f && index < f->parameters.size() ? f->parameters[index] : nullptr;
+}
+KznBackendValue* kzn_backend_function_as_value(KznBackendFunction* f) { return f ? f->as_value : nullptr; }
+KznBackendBlock* kzn_backend_append_new_basic_block(KznBackendFunction* f, const char* name) {
+    if (!f) return nullptr;
+    KznBackendContext* c = f->module->context;
+    c->blocks.push_back(std::make_unique<KznBackendBlock>());
+    KznBackendBlock* b = c->blocks.back().get();
+    b->function = f;
+    b->name = name ? name : "";
+    b->as_value = c->value({BvKind::Block, nullptr, f, (uint32_t)f->blocks.size()});
+    f->blocks.push_back(b);
+    return b;
+}
+KznBackendValue* kzn_backend_block_as_value(KznBackendBlock* b) { return b ? b->as_value : nullptr; }
+KznBackendBuilder* kzn_backend_create_builder(KznBackendContext* c) {
+    if (!c) return nullptr;
+    c->builders.push_back(std::make_unique<KznBackendBuilder>());
+    c->builders.back()->context = c;
+    return c->builders.back().get();
+}
+KznResult kzn_backend_builder_attach(KznBackendBuilder* b, KznBackendBlock* block) {
+    KZN_VALID(b && block, "null argument");
+    KZN_VALID(!b->block, "builder is already attached (DetachedBuilder::attach consumes a detached builder, lib.rs:33-41)");
+    KZN_VALID(!block->terminated, "basic block already has a terminator");
+    b->block = block;
+    return KZN_SUCCESS;
+}
+KznBackendBlock* kzn_backend_builder_current_basic_block(KznBackendBuilder* b) { return b ? b->block : nullptr; }
+KznBackendValue* kzn_backend_build_alloca(KznBackendBuilder* b, KznBackendType* variable_type) {
+    if (!b || !b->block || !variable_type) {
+        kzn_set_error("build_alloca needs an attached builder and a type");
+        return nullptr;
+    }
+    if (variable_type->kind == BtKind::Function || variable_type->kind == BtKind::Void) {
+        kzn_set_error("build_alloca: the type has no size");
+        return nullptr;
+    }
+    KznBackendContext* c = b->context;
+    KznBackendFunction* f = b->block->function;
+    KznBackendType* ptr = kzn_backend_type_pointer(c, variable_type);
+    KznBackendValue* v = c->value({BvKind::Alloca, ptr, f, f->allocas++});
+    BackendInstr in;
+    in.value = v;
+    in.type = variable_type;
+    b->block->instrs.push_back(in);
+    return v;
+}
+KznResult kzn_backend_build_return(KznBackendBuilder* b, KznBackendValue* value) {
+    KZN_VALID(b && b->block, "build_return needs an attached builder");
+    BackendInstr in;
+    in.is_return = true;
+    in.value = value;
+    b->block->instrs.push_back(in);
+    b->block->terminated = true;
+    b->block = nullptr;  // build_return hands back a DetachedBuilder (lib.rs:26-29)
+    return KZN_SUCCESS;
+}
+KznResult kzn_backend_module_verify(KznBackendModule* m) { return verify_module(m); }
+
+KznResult kzn_backend_module_to_ptx(KznBackendModule* m, char** ptx, size_t* length) {
+    KZN_VALID(m && ptx, "null argument");
+    *ptx = nullptr;
+    KznResult r = verify_module(m);
+    if (r != KZN_SUCCESS) return r;
+    *ptx = dup_text(backend_module_ptx(m), length);
+    KZN_REQUIRE(*ptx, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_backend_compile(KznDevice* device, KznBackendModule* m, const char* const* keys, KznBackendFunction* const* callable_functions,
+                              uint64_t count, KznCompiledCode** code) {
+    KZN_VALID(device && m && code && (count == 0 || (keys && callable_functions)), "kzn_backend_compile: null argument");
+    *code = nullptr;
+    KznResult r = verify_module(m);
+    if (r != KZN_SUCCESS) return r;
+    for (uint64_t i = 0; i < count; ++i) {
+        KZN_VALID(keys[i] && callable_functions[i], "callable function %llu is null", (unsigned long long)i);
+        KZN_VALID(callable_functions[i]->module == m, "callable function '%s' belongs to another module", callable_functions[i]->name.c_str());
+        KZN_VALID(!callable_functions[i]->blocks.empty(), "callable function '%s' has no body", callable_functions[i]->name.c_str());
+    }
+    auto cc = std::make_unique<KznCompiledCode>();
+    cc->device = device;
+    r = load_ptx(device, backend_module_ptx(m), &cc->module);
+    if (r != KZN_SUCCESS) return r;
+    for (uint64_t i = 0; i < count; ++i) {
+        CompiledFunction f;
+        CUresult_ cr = driver()->cuModuleGetFunction(&f.function, cc->module, callable_functions[i]->symbol.c_str());  // backend.rs:645-657
+        if (cr != 0) {
+            driver()->cuModuleUnload(cc->module);
+            return driver_failed(cr, "cuModuleGetFunction");
+        }
+        f.has_return_slot = callable_functions[i]->type->element != nullptr;
+        f.parameter_count = callable_functions[i]->parameters.size();
+        cc->by_key[keys[i]] = f;
+    }
+    *code = cc.release();
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_compiled_code_get(KznCompiledCode* code, const char* key, KznCallable* callable) {
+    KZN_VALID(code && key && callable, "null argument");
+    auto it = code->by_key.find(key);
+    if (it == code->by_key.end()) {  // CompiledCode::get returns None (lib.rs:204)
+        callable->call = nullptr;
+        callable->self = nullptr;
+        kzn_set_error("no callable function with key '%s'", key);
+        return KZN_NOT_READY;
+    }
+    callable->call = callable_trampoline;
+    callable->self = &it->second;
+    return KZN_SUCCESS;
+}
+
+void kzn_compiled_code_destroy(KznCompiledCode* code) {
+    if (!code) return;
+    if (code->module) {
+        cudaSetDevice(code->device->ordinal);
+        driver()->cuModuleUnload(code->module);
+    }
+    delete code;
+}
+
+}  // extern "C"

@@ -488,7 +488,7 @@ struct Parser {
         if (k.kind == Tk::Int) {
             Token v = next();
             if (v.suffix.empty()) fail("integer constant needs a type suffix", v.pos);
-            IntKind ik;
+            IntKind ik = IntKind::I32;
             int_kind_from(v.suffix, &ik);
             int bits = int_bits(ik);
             if (bits < 64 && (v.value >> bits)) fail("constant does not fit its type", v.pos);
@@ -812,7 +812,7 @@ struct Parser {
             std::string k = word();
             expect(":");
             std::string v = word();
-            IntKind ik;
+            IntKind ik = IntKind::I32;
             if (!int_kind_from(v, &ik)) throw Error("pointer underlying type must be an integer type");
             if (k == "data_pointer_underlying_type") *dp = ik;
             else if (k == "function_pointer_underlying_type") *fp = ik;

@@ -52,7 +52,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(declared) >= 40
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/kazan_b200.h but not exported"
-    assert set(declared) == set(abi.PROTOTYPES), "abi.PROTOTYPES and the header disagree"
+    assert set(declared) == set(abi.ALL_PROTOTYPES), "abi prototypes and the headers disagree"
+    assert set(abi.declared_symbols(abi.BACKEND_HEADER)) == set(abi.BACKEND_PROTOTYPES)
     assert lib.kzn_abi_version() == 1
 
 
