@@ -81,7 +81,7 @@ def build_product(force: bool = False, verbose_ptxas: bool = False) -> Path:
     for s, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    _run([_nvcc(), "-shared", "-cudart", "static", "-o", str(LIB), *map(str, objs), "-ldl", "-lpthread"])
+    _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", str(LIB), *map(str, objs), "-ldl", "-lpthread"])
     return LIB
 
 

@@ -227,6 +227,17 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         if (a > 0 || (a == 0 && b > 0)) r.bias_bits |= 1u << i;
     }
     r.inv2a = 1.0f / (float)(two_a * s);
+    {
+        // bit 3: the interpolated depth of every covered fragment is certainly inside the depth-clip range, so the
+        // raster kernel may skip the per-fragment z clip (R3).  Inside the triangle the barycentrics are in [0,1] and
+        // the R6 expression is within a few ulp of a convex combination of the vertex depths: either all three are
+        // exactly 0 (then every product and sum is exactly 0), or they keep a margin of 2^-16 from both ends.
+        const float zlo = fminf(r.z[0], fminf(r.z[1], r.z[2])), zhi = fmaxf(r.z[0], fmaxf(r.z[1], r.z[2]));
+        const float margin = 1.52587890625e-05f;
+        const bool all_zero = zlo == 0.0f && zhi == 0.0f && p.zclip_lo <= 0.0f && p.zclip_hi >= 0.0f;
+        const bool inside = zlo >= p.zclip_lo + margin && zhi <= p.zclip_hi - margin && fabsf(zlo) <= 1.0f && fabsf(zhi) <= 1.0f;
+        if (all_zero || inside) r.bias_bits |= 8u;
+    }
     if (ok) {
         int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
         int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
@@ -353,31 +364,6 @@ __device__ __forceinline__ float blend_op(uint32_t op, float cs, float sf, float
     case 3: return cs < cd ? cs : cd;
     default: return cs > cd ? cs : cd;
     }
-}
-
-__device__ __forceinline__ uint32_t output_merge(const KznGraphicsPipelineState& st, const float src[4], uint32_t dst_word) {
-    float s[4], o[4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) s[ch] = clamp01(src[ch]);
-    if (st.blend_enable) {
-        float d[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) d[ch] = unorm8_to_float((dst_word >> (8 * ch)) & 255u);
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-            o[ch] = blend_op(st.color_blend_op, s[ch], blend_factor(st.src_color_blend_factor, ch, s, d), d[ch],
-                             blend_factor(st.dst_color_blend_factor, ch, s, d));
-        o[3] = blend_op(st.alpha_blend_op, s[3], blend_factor(st.src_alpha_blend_factor, 3, s, d), d[3],
-                        blend_factor(st.dst_alpha_blend_factor, 3, s, d));
-    } else {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) o[ch] = s[ch];
-    }
-    uint32_t out = dst_word;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-        if (st.color_write_mask & (1u << ch)) out = (out & ~(0xffu << (8 * ch))) | (float_to_unorm8(o[ch]) << (8 * ch));
-    return out;
 }
 
 __device__ __forceinline__ void fs_procedural_orbit(int px, int py, float inv_w, float inv_h, float rgba[4]) {
@@ -525,87 +511,103 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
     }
 }
 
-// 4 interleaved orbits (independent dependency chains keep the fma pipe busy at any occupancy)
+// 4 interleaved orbits as two packed pairs: fma.rn.f32x2 / add.rn.f32x2 (FFMA2 / FADD2) do two IEEE fp32 operations per
+// issue slot with per-lane results identical to the scalar instructions, so the shader is still the oracle's sequence.
 __device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_w, float inv_h, float rgba[kPx][4]) {
-    float cx[kPx], zx[kPx], zy[kPx];
-    float v = ((float)py + 0.5f) * inv_h;
-    float cy = fmaf(v, 2.0f, -1.0f);
+    static_assert(kPx == 4, "two f32x2 pairs");
+    float2 cx[2], zx[2], zy[2];
+    const float v = ((float)py + 0.5f) * inv_h;
+    const float cys = fmaf(v, 2.0f, -1.0f);
+    const float2 cy = make_float2(cys, cys);
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        float u = ((float)(px0 + k) + 0.5f) * inv_w;
-        cx[k] = fmaf(u, 3.5f, -2.5f);
-        zx[k] = 0.0f;
-        zy[k] = 0.0f;
+    for (int k = 0; k < 2; ++k) {
+        const float u0 = ((float)(px0 + 2 * k) + 0.5f) * inv_w, u1 = ((float)(px0 + 2 * k + 1) + 0.5f) * inv_w;
+        cx[k] = make_float2(fmaf(u0, 3.5f, -2.5f), fmaf(u1, 3.5f, -2.5f));
+        zx[k] = make_float2(0.0f, 0.0f);
+        zy[k] = make_float2(0.0f, 0.0f);
     }
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) {
-            float t = fmaf(zx[k], zx[k], cx[k]);
-            float nzx = fmaf(-zy[k], zy[k], t);
-            float nzy = fmaf(zx[k] + zx[k], zy[k], cy);
+        for (int k = 0; k < 2; ++k) {
+            const float2 t = __ffma2_rn(zx[k], zx[k], cx[k]);
+            const float2 nzx = __ffma2_rn(make_float2(-zy[k].x, -zy[k].y), zy[k], t);
+            const float2 nzy = __ffma2_rn(__fadd2_rn(zx[k], zx[k]), zy[k], cy);
             zx[k] = nzx;
             zy[k] = nzy;
         }
     }
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
-        float m = fmaf(zx[k], zx[k], zy[k] * zy[k]);
+        const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
+        float m = fmaf(x, x, y * y);
         rgba[k][0] = 0.25f * m;
-        rgba[k][1] = fmaf(zx[k], 0.5f, 0.5f);
-        rgba[k][2] = fmaf(zy[k], 0.5f, 0.5f);
+        rgba[k][1] = fmaf(x, 0.5f, 0.5f);
+        rgba[k][2] = fmaf(y, 0.5f, 0.5f);
         rgba[k][3] = 1.0f;
     }
 }
 
-// A triangle whose span covers at least half of the warp's row: lane l handles the 4 pixels 4l..4l+3 of the row directly
-// (edge functions stepped by +16a per pixel, 16-byte shared-memory accesses), the way a full-screen fill wants it.
+// One triangle against the 4 adjacent pixels px0..px0+3 of row py that a lane owns, destination values in registers:
+// edge functions evaluated once and stepped by +16a per pixel (exact, R5), barycentric depth (R6), z clip (R3), early-Z
+// (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the 4 pixels got a new colour / depth.
+// [xa, xb] is the triangle's pixel span in this row (bbox, already scissored) clipped to the 128-pixel tile row; it is
+// warp-uniform, and so is the trivial-accept branch.
 template <uint32_t FS, bool NEED_DST>
-__device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
-                                           int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
-                                           uint32_t& n_covered, uint32_t& n_passed) {
-    const TriRec& t = sh.recs[slot];
-    const int px0 = tile_px0 + (int)lane * kPx;
-    const int32_t sx = 16 * px0 + 8;
-    long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
-    long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
-    long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
-    const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
+__device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, const float* lut, int px0, int py, int32_t sy, int xa, int xb,
+                                          bool depth_test, bool depth_write, bool has_color, uint32_t col[kPx], float depth[kPx],
+                                          uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed) {
     const uint32_t bias = t.bias_bits;
     const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
-    const float inv2a = t.inv2a;
-    const int minx = t.minx, maxx = t.maxx;
-    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
-    float depth[kPx] = {dq.x, dq.y, dq.z, dq.w};
-    float l0[kPx], l1[kPx], l2[kPx];
-    uint32_t live = 0, zwrite = 0;
+    const long long r0 = (long long)t.b[0] * sy + t.c[0], r1 = (long long)t.b[1] * sy + t.c[1], r2 = (long long)t.b[2] * sy + t.c[2];
+    live = 0;
+    zwrite = 0;
+    bool trivial = false;
+    if (FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test && (bias & 8u)) {
+        // Trivial accept of the whole span: the covered pixels of a row are an interval (each biased edge test is a
+        // half-plane), so if both end pixels of the span are covered, every pixel between them is; the depth clip cannot
+        // reject (bit 3, set at setup) and this fragment program reads no interpolant — no per-pixel coverage work at all.
+        const int32_t sa = 16 * xa + 8, sb = 16 * xb + 8;
+        trivial = (long long)t.a[0] * sa + r0 + b0 > 0 && (long long)t.a[1] * sa + r1 + b1 > 0 && (long long)t.a[2] * sa + r2 + b2 > 0 &&
+                  (long long)t.a[0] * sb + r0 + b0 > 0 && (long long)t.a[1] * sb + r1 + b1 > 0 && (long long)t.a[2] * sb + r2 + b2 > 0;
+        if (trivial) {
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
-        const long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
-        bool cov = px0 + k >= minx && px0 + k <= maxx && f0 + b0 > 0 && f1 + b1 > 0 && f2 + b2 > 0;
-        l0[k] = (float)f0 * inv2a;  // R6
-        l1[k] = (float)f1 * inv2a;
-        l2[k] = (float)f2 * inv2a;
-        const float z = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
-        cov = cov && z >= p.zclip_lo && z <= p.zclip_hi;  // R3
-        if (cov) {
-            ++n_covered;
-            if (!depth_test || depth_compare(p.st.depth_compare_op, z, depth[k])) {  // R7: early-Z
-                ++n_passed;
-                live |= 1u << k;
-                if (depth_write) {
-                    depth[k] = z;
-                    zwrite |= 1u << k;
+            for (int k = 0; k < kPx; ++k)
+                if (px0 + k >= xa && px0 + k <= xb) live |= 1u << k;
+            n_covered += __popc(live);
+            n_passed += __popc(live);
+        }
+    }
+    float l0[kPx], l1[kPx], l2[kPx];
+    if (!trivial) {
+        const int32_t sx = 16 * px0 + 8;
+        const long long e0 = (long long)t.a[0] * sx + r0, e1 = (long long)t.a[1] * sx + r1, e2 = (long long)t.a[2] * sx + r2;  // R5, exact
+        const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
+        const float inv2a = t.inv2a;
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) {
+            const long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
+            bool cov = px0 + k >= xa && px0 + k <= xb && f0 + b0 > 0 && f1 + b1 > 0 && f2 + b2 > 0;
+            l0[k] = (float)f0 * inv2a;  // R6
+            l1[k] = (float)f1 * inv2a;
+            l2[k] = (float)f2 * inv2a;
+            const float z = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
+            cov = cov && z >= p.zclip_lo && z <= p.zclip_hi;  // R3
+            if (cov) {
+                ++n_covered;
+                if (!depth_test || depth_compare(p.st.depth_compare_op, z, depth[k])) {  // R7: early-Z
+                    ++n_passed;
+                    live |= 1u << k;
+                    if (depth_write) {
+                        depth[k] = z;
+                        zwrite |= 1u << k;
+                    }
                 }
             }
         }
     }
-    if (zwrite) {
-        *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        atomicOr(&sh.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
-    }
-    if (live && has_color) {
+    if (!has_color) live = 0;
+    if (live) {
         float src[kPx][4];
         if (FS == KZN_FS_PROCEDURAL_ORBIT) {
             fs_procedural_orbit4(px0, py, p.inv_fb_w, p.inv_fb_h, src);
@@ -618,15 +620,139 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
                     src[k][ch] = __fdiv_rn(fmaf(l2[k], t.col[2][ch], fmaf(l1[k], t.col[1][ch], l0[k] * t.col[0][ch])), den);
             }
         }
-        uint4 cq = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);  // pixels not live keep their value
-        uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
 #pragma unroll
         for (int k = 0; k < kPx; ++k)
-            if (live >> k & 1u) col[k] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src[k], col[k]);
+            if (live >> k & 1u) col[k] = output_merge_lut<NEED_DST>(p.st, lut, src[k], col[k]);  // pixels not live keep their value
+    }
+}
+
+// A triangle whose span covers at least half of the warp's row inside the streaming kernel: lane l handles the 4 pixels
+// 4l..4l+3 of the row directly (16-byte shared-memory accesses, no fragment queue).
+template <uint32_t FS, bool NEED_DST>
+__device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
+                                           int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
+                                           uint32_t& n_covered, uint32_t& n_passed) {
+    const TriRec& t = sh.recs[slot];
+    const int px0 = tile_px0 + (int)lane * kPx;
+    const int xa = max(t.minx, tile_px0), xb = min(t.maxx, tile_px0 + kTileW - 1);
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
+    float depth[kPx] = {dq.x, dq.y, dq.z, dq.w};
+    uint4 cq = make_uint4(0u, 0u, 0u, 0u);
+    if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);
+    uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
+    uint32_t live, zwrite;
+    span_quad<FS, NEED_DST>(p, t, sh.unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
+                            n_passed);
+    if (zwrite) {
+        *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+        atomicOr(&sh.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
+    }
+    if (live) {
         *reinterpret_cast<uint4*>(&sh.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
         atomicOr(&sh.color_dirty[warp][lane >> 3], live << ((lane & 7u) * 4u));
     }
     __syncwarp();
+}
+
+// Draws of a few triangles (total <= kDirectMax: fullscreen passes, quads, UI): no binning, no staging, no fragment queue.
+// One CTA per 128x8 tile, warp w = row w, lane l = pixels 4l..4l+3; the lane keeps its 4 colour and depth values in
+// REGISTERS while it walks the triangle records in primitive order (uniform loads: every lane reads the same record),
+// so per-pixel fragment order is the primitive order by construction and the tile needs no shared memory beyond the
+// UNORM8 table.  Rows and tiles a triangle's bounding box misses are rejected on the 16-byte bbox alone.
+template <uint32_t FS, bool NEED_DST>
+__global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __grid_constant__ DrawParams p) {
+    __shared__ float unorm_lut[NEED_DST ? 256 : 1];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW;
+    const int py = (int)(p.tile_y0 + blockIdx.y) * kTileH + (int)warp;
+    const int px0 = tile_px0 + (int)lane * kPx;
+    const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
+    const bool depth_test = has_depth && p.st.depth_test_enable;
+    const bool depth_write = depth_test && p.st.depth_write_enable;
+    if (NEED_DST) {
+        unorm_lut[threadIdx.x] = unorm8_to_float(threadIdx.x);
+        __syncthreads();
+    }
+    if (py < p.cy0 || py > p.cy1) return;  // whole warp
+    uint32_t quad_clip = 0;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k)
+        if (px0 + k >= p.cx0 && px0 + k <= p.cx1) quad_clip |= 1u << k;
+    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kPx <= (int)p.fb_w;
+    const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
+    unsigned long long caddr = 0, daddr = 0;
+    uint32_t col[kPx] = {0u, 0u, 0u, 0u};
+    float depth[kPx] = {0.f, 0.f, 0.f, 0.f};
+    if (quad_clip) {
+        if (has_color) caddr = color_addr(p, px0, py);
+        if (has_depth) daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px0) * 4ull;
+        if (NEED_DST && has_color) {
+            if (cvec) {
+                const uint4 q = *reinterpret_cast<const uint4*>(caddr);
+                col[0] = q.x; col[1] = q.y; col[2] = q.z; col[3] = q.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < kPx; ++k)
+                    if (quad_clip >> k & 1u) col[k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+            }
+        }
+        if (depth_test) {
+            if (dvec) {
+                const float4 q = *reinterpret_cast<const float4*>(daddr);
+                depth[0] = q.x; depth[1] = q.y; depth[2] = q.z; depth[3] = q.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < kPx; ++k)
+                    if (quad_clip >> k & 1u) depth[k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+            }
+        }
+    }
+    const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
+    uint32_t cdirty = 0, zdirty = 0, n_covered = 0, n_passed = 0;
+    for (uint32_t i = 0; i < p.total_tris; ++i) {
+        const TriRec& t = p.tris[i];
+        const int4 bb = __ldg(reinterpret_cast<const int4*>(&t));  // minx maxx miny maxy, already scissored
+        if (bb.x > bb.y || py < bb.z || py > bb.w) continue;
+        const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kTileW - 1);
+        if (xa > xb) continue;
+        uint32_t live, zwrite;
+        span_quad<FS, NEED_DST>(p, t, unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
+                                n_passed);
+        cdirty |= live;
+        zdirty |= zwrite;
+    }
+    cdirty &= quad_clip;
+    zdirty &= quad_clip;
+    if (cdirty) {
+        if (cdirty == 15u && cvec) {
+            *reinterpret_cast<uint4*>(caddr) = make_uint4(col[0], col[1], col[2], col[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (cdirty >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = col[k];
+        }
+    }
+    if (zdirty) {
+        if (zdirty == 15u && dvec) {
+            *reinterpret_cast<float4*>(daddr) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPx; ++k)
+                if (zdirty >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = depth[k];
+        }
+    }
+    if (p.stats) {
+        for (int d = 16; d > 0; d >>= 1) {
+            n_covered += __shfl_xor_sync(0xffffffffu, n_covered, d);
+            n_passed += __shfl_xor_sync(0xffffffffu, n_passed, d);
+        }
+        if (lane == 0) {
+            if (n_covered) atomicAdd(&p.stats[4], (unsigned long long)n_covered);
+            if (n_passed) atomicAdd(&p.stats[5], (unsigned long long)n_passed);
+        }
+    }
+    if (p.stats && threadIdx.x == 0) atomicAdd(&p.stats[6], 1ull);
 }
 
 // One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
@@ -1112,6 +1238,16 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     // the destination colour is only read when the result depends on it
     const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
     const size_t smem = sizeof(RasterShared);
+    if (!p.binned) {  // a few triangles: register-resident tiles, no staging
+        if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
+            if (need_dst) raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, 0, q->stream>>>(p);
+            else raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, 0, q->stream>>>(p);
+        } else {
+            if (need_dst) raster_direct_kernel<KZN_FS_VERTEX_COLOR, true><<<grid, kRasterThreads, 0, q->stream>>>(p);
+            else raster_direct_kernel<KZN_FS_VERTEX_COLOR, false><<<grid, kRasterThreads, 0, q->stream>>>(p);
+        }
+        return kzn_launched(q, "raster_direct_kernel");
+    }
     if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
         if (need_dst) raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, smem, q->stream>>>(p);
         else raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, smem, q->stream>>>(p);
