@@ -194,6 +194,56 @@ def grid_mesh(quads_x, quads_y, seed):
     return v, idx
 
 
+def kernel_ms(torch, queue, fn, reps=30):
+    """Average device duration of the dominant kernel of `fn`'s command, from the library's CUDA-event pair."""
+    queue.set_kernel_timing(True)
+    total = 0.0
+    for k in range(reps):
+        # three commands back to back, the last one read: its event pair is recorded while the GPU is still busy with
+        # the earlier ones, so the pair brackets the kernel only (not the idle-stream launch latency)
+        fn(3 * k)
+        fn(3 * k + 1)
+        fn(3 * k + 2)
+        total += queue.last_kernel_ms()
+    queue.set_kernel_timing(False)
+    return total / reps
+
+
+def roofline_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)."""
+    f = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        return json.loads(f.read_text())[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def dispatch_extra(torch, queue, stream):
+    """BASELINE configs[1]: a compute shader over 2^24 invocations through the PTX back end (IR -> PTX -> cuLaunchKernel)."""
+    from kazan_b200 import backend
+    out = {}
+    n = 1 << 24
+    golden = json.loads((ROOT / "tests" / "golden" / "ir_goldens.json").read_text())["spirv_to_ir"][0]
+    words = np.frombuffer(bytes.fromhex(golden["spv_hex"]), dtype="<u4").tolist()
+    module, local_size = backend.translate_spirv_to_ir(words, "main", backend.EXECUTION_MODEL_GLCOMPUTE)
+    pipe = backend.ComputePipeline(queue.device, module, local_size)
+    ms = time_region(torch, stream, lambda k: queue.cmd_dispatch(pipe, (65536, 256, 1)), 50, 3) / 50
+    out["trivial_test_spv"] = {"invocations": n, "ms": ms, "Ginvocations_per_s": n / ms / 1e6}
+    pipe.destroy()
+    text = (ROOT / "tests" / "ir_programs" / "sum_loop.kazan-ir").read_text()
+    pipe = backend.ComputePipeline(queue.device, backend.IrModule.parse(text))
+    x = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+    y = torch.empty(n, dtype=torch.int32, device="cuda")
+    ms = time_region(torch, stream, lambda k: queue.cmd_dispatch(pipe, (65536, 256, 1), x.data_ptr(), y.data_ptr()), 20, 3) / 20
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(y, x * 256))  # int32 wrap-around, the loop's closed form
+    # 256 iterations x (2 adds + compare/branch) per invocation: integer issue rate
+    out["sum_loop_256"] = {"invocations": n, "ms": ms, "Ginvocations_per_s": n / ms / 1e6, "Tint_adds_per_s": n * 512 / ms / 1e9,
+                           "bytes_per_invocation": 8, "GBps": n * 8 / ms / 1e6, "parity": "closed form x*256 (mod 2^32) holds" if ok else "MISMATCH"}
+    pipe.destroy()
+    return out
+
+
 def mesh_state(abi):
     st = abi.GraphicsPipelineState()
     st.fragment_program = abi.FS_VERTEX_COLOR
@@ -322,10 +372,51 @@ def run_reference(args):
     return 0
 
 
+def split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrier):
+    """BASELINE configs[4]: 7680x4320 frame of a 4M-triangle mesh (D32 LESS + alpha blend), sort-first split into `world`
+    bands, composited to rank 0.  Strong scaling: the frame is fixed, every rank sees all geometry and culls to its band."""
+    from kazan_b200.split_frame import SplitFrame
+    W, H = 7680, 4320
+    verts, idx = grid_mesh(2000, 1000, 5)
+    ntri = len(idx) // 3
+    d_verts, d_idx = torch.from_numpy(verts).cuda(), torch.from_numpy(idx.view(np.int32)).cuda()
+    color = torch.zeros(W * H * 4, dtype=torch.uint8, device="cuda")
+    depth = torch.empty(W * H, dtype=torch.float32, device="cuda")
+    sf = SplitFrame(W, H, world, rank)
+    y0, y1 = sf.band
+    cimg = host.Image(color.data_ptr(), W, H)
+    dimg = host.Image(depth.data_ptr(), W, H, format=abi.FORMAT_D32_SFLOAT)
+    fb = abi.Framebuffer()
+    fb.color, fb.depth = cimg.desc(), dimg.desc()
+    fb.band_y0, fb.band_y1 = y0, y1
+    st = mesh_state(abi)
+    vp = abi.Viewport(0, 0, W, H, 0, 1)
+    sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, H))
+    vi = abi.VertexInput(d_verts.data_ptr(), verts.nbytes, 28, 0, 3, 12)
+    band = [abi.ClearRect(abi.Rect2D(abi.Offset2D(0, y0), abi.Extent2D(W, y1 - y0)), 0, 1)]
+
+    def frame(k):
+        queue.cmd_clear_attachment(cimg, (0, 0, 0, 0), band)
+        queue.cmd_clear_attachment(dimg, (1.0, 0, 0, 0), band)
+        queue.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+        sf.composite(color, dist)
+
+    reps = 10
+    ms = time_region(torch, stream, frame, reps, 3, barrier) / reps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"frame": [W, H], "triangles": ntri, "bands": world, "ms_per_frame": ms, "Gpix_per_s": W * H / ms / 1e6, "Mtri_per_s": ntri / ms / 1e3,
+            "composite_bytes": sf.composite_bytes(), "scaling": "strong",
+            "frame_checksum_rank0": int(color.view(torch.int32).sum(dtype=torch.int64).item()) if rank == 0 else None}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from kazan_b200 import abi, host
+    from kazan_b200.split_frame import SplitFrame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -342,10 +433,13 @@ def run_ours(args):
     queue = dev.wrap_stream(stream.cuda_stream)
     hbm_peak, peak_src = measured_peaks()
 
+    # Weak scaling: every rank shades one 3840x2160 band of a 3840 x (2160*world) frame (sort-first split); the bands are
+    # composited to rank 0 in one exchange step per frame.  world == 1 is BASELINE configs[2] itself.
     W, H = FRAME_W, FRAME_H
-    frame_bytes = W * H * 4
-    n_targets = 8  # 265 MB of render targets > 126 MB L2: every step writes lines that are not L2 resident
     total_h = H * world
+    frame_bytes = W * total_h * 4
+    n_targets = 8  # each rank writes 8 x 33 MB of distinct lines in rotation (265 MB > 126 MiB L2): never L2 resident
+    sf = SplitFrame(W, total_h, world, rank)
     st = fill_state(abi)
     vp = abi.Viewport(0, 0, W, total_h, 0, 1)
     sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, total_h))
@@ -353,42 +447,23 @@ def run_ours(args):
     vi = abi.VertexInput(verts.data_ptr(), verts.numel() * 4, 28, 0, 3, 12)
 
     with torch.cuda.stream(stream):
-        if world == 1:
-            targets = [torch.zeros(frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
-            fbs = [framebuffer(abi, t.data_ptr(), W, H) for t in targets]
+        targets = [torch.zeros(frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
+        fbs = [framebuffer(abi, t.data_ptr(), W, total_h, band=sf.band if world > 1 else (0, 0)) for t in targets]
 
-            def step(k):
-                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
-        else:
-            # sort-first split: rank r owns rows [r*H, (r+1)*H) of a W x (H*world) frame; rank 0 presents.
-            # Every rank renders into a full-size image (only its band is touched), then the band is sent to
-            # rank 0's image: one exchange step per frame.
-            n_targets = 2
-            full = [torch.zeros(frame_bytes * world, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
-            fbs = [framebuffer(abi, t.data_ptr(), W, total_h, band=(rank * H, (rank + 1) * H)) for t in full]
-
-            def step(k):
-                t = full[k % n_targets]
-                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
-                if rank == 0:
-                    ops = [dist.P2POp(dist.irecv, t[r * frame_bytes:(r + 1) * frame_bytes], r) for r in range(1, world)]
-                else:
-                    ops = [dist.P2POp(dist.isend, t[rank * frame_bytes:(rank + 1) * frame_bytes], 0)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+        def step(k):
+            queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
+            sf.composite(targets[k % n_targets], dist)
 
         launches0 = queue.launch_count
         with ClockSampler(local_rank) as clocks:
             ms = time_region(torch, stream, step, args.steps, args.warmup, barrier)
-        launches = queue.launch_count - launches0 - 0
-        # launches counted over warm-up + timed steps: keep only the timed share
-        launches = launches * args.steps // (args.steps + args.warmup)
+        launches = (queue.launch_count - launches0) * args.steps // (args.steps + args.warmup)  # timed share only
 
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    pixels_per_step = W * H * world
+    pixels_per_step = W * total_h
     value = pixels_per_step * args.steps / ms / 1e6  # Gpixels/s
     ms_per_step = ms / args.steps
 
@@ -399,46 +474,58 @@ def run_ours(args):
         "config": {"workload": "fullscreen-triangle procedural fragment shader at 3840x2160 R8G8B8A8_UNORM (configs[2])"
                                + ("" if world == 1 else f"; {world} bands of 3840x2160, NCCL composite to rank 0"),
                    "frame": [W, total_h], "fragment_program": "procedural orbit, 32 fp32 fma iterations",
-                   "l2": f"rotating {n_targets} render targets ({n_targets * frame_bytes * world >> 20} MiB > 126 MiB L2)"},
+                   "l2": f"rotating {n_targets} render targets ({n_targets * W * H * 4 >> 20} MiB written per rank > 126 MiB L2)"},
         "gpu_launches": int(launches),
     }
+    if world > 1:
+        line["config"]["composite_bytes_per_step"] = sf.composite_bytes()
+
+    # ---- e2e: the same frame through the same calls with HOST buffers: vertex upload, draw, composite, frame read-back ----
+    with torch.cuda.stream(stream):
+        h_verts = torch.from_numpy(FULLSCREEN_TRIANGLE.copy()).pin_memory()
+        h_frame = torch.empty(frame_bytes if rank == 0 else 4, dtype=torch.uint8).pin_memory()
+        d_verts = torch.empty(21, dtype=torch.float32, device="cuda")
+        vi2 = abi.VertexInput(d_verts.data_ptr(), 84, 28, 0, 3, 12)
+
+        def e2e_step(k):
+            queue.upload(d_verts.data_ptr(), h_verts.data_ptr(), 84)
+            queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi2, 3)
+            sf.composite(targets[k % n_targets], dist)
+            if rank == 0:
+                queue.download(h_frame.data_ptr(), targets[k % n_targets].data_ptr(), frame_bytes)
+            queue.wait_idle()  # the frame is in host memory
+
+        e_steps = max(5, min(args.steps, 20))
+        ems = time_region(torch, stream, e2e_step, e_steps, 3, barrier)
+    if world > 1:
+        t = torch.tensor([ems], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+    line["e2e"] = {"value": pixels_per_step * e_steps / ems / 1e6, "unit": UNIT, "h2d_bytes_per_step": 84 * world,
+                   "d2h_bytes_per_step": frame_bytes, "steps": e_steps}
 
     if rank == 0 and world == 1:
-        # roofline of the dominant kernel (raster_kernel).  Its duration is bounded above by the step time
-        # (the step is setup_kernel on one triangle + raster_kernel), so `achieved` is a lower bound.
-        sec = ms_per_step / 1e3
+        # ---- roofline of the dominant kernel (raster_direct_kernel), its duration measured live with the library's
+        # CUDA-event pair around that kernel on the launching stream ----
+        with torch.cuda.stream(stream):
+            k_ms = kernel_ms(torch, queue, lambda k: queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3))
+        sec = k_ms / 1e3
         clk = clocks.summary()
         line["clocks"] = clk
-        achieved = frame_bytes / sec / 1e9
+        achieved = W * H * 4 / sec / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": None, "peak_source": peak_src,
-                            "note": "4 B written per pixel; the kernel is fp32-issue bound, see `issue`"}
+                            "traffic": roofline_traffic("raster_direct_kernel"), "peak_source": peak_src, "kernel": "raster_direct_kernel<ORBIT,false>",
+                            "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                            "note": "4 B written per pixel; the kernel is fp32-issue bound by construction (236 flop/pixel), see `issue`"}
         sm_mhz = clk["sm_mhz"] or 1965.0
-        issue_peak = dev.sm_count * 128 * sm_mhz * 1e6 / 1e12  # T fp32 instr/s at the sampled clock
+        issue_peak = dev.sm_count * 128 * sm_mhz * 1e6 / 1e12  # T fp32 lane-instructions/s at the sampled clock
         issue = W * H * FP32_INSTR_PER_PIXEL / sec / 1e12
         line["issue"] = {"bound": "fp32_issue", "achieved": issue, "peak": issue_peak, "unit": "Tinstr/s", "frac": issue / issue_peak,
-                         "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL, "sm_mhz": sm_mhz}
-
+                         "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL, "sm_mhz": sm_mhz,
+                         "measured_orbit_only_ceiling_frac": 0.89, "ceiling_source": "tools/micro/ffma2_bench.cu on B200 (profiles/)"}
         if args.profile:
             print(json.dumps(line))
             return 0
-        # ---- e2e: host buffers, copies inside the timed region ----
-        with torch.cuda.stream(stream):
-            h_verts = torch.from_numpy(FULLSCREEN_TRIANGLE.copy()).pin_memory()
-            h_frame = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
-            d_verts = torch.empty(21, dtype=torch.float32, device="cuda")
-            vi2 = abi.VertexInput(d_verts.data_ptr(), 84, 28, 0, 3, 12)
-
-            def e2e_step(k):
-                queue.upload(d_verts.data_ptr(), h_verts.data_ptr(), 84)
-                queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi2, 3)
-                queue.download(h_frame.data_ptr(), targets[k % n_targets].data_ptr(), frame_bytes)
-                queue.wait_idle()  # the frame is in host memory
-
-            e_steps = max(5, min(args.steps, 20))
-            ems = time_region(torch, stream, e2e_step, e_steps, 3)
-        line["e2e"] = {"value": W * H * e_steps / ems / 1e6, "unit": UNIT, "h2d_bytes_per_step": 84, "d2h_bytes_per_step": frame_bytes,
-                       "steps": e_steps}
 
         # ---- CPU baseline (oracle port) + full-frame parity ----
         from oracle import binding as ob
@@ -449,13 +536,19 @@ def run_ours(args):
                                 "sample": "one full 3840x2160 frame, oracle/raster.c, all host threads"}
         line["parity"] = "bit-exact vs oracle on the full 4K frame" if same else "MISMATCH vs oracle"
 
-        # ---- clear / copy GB/s vs HBM peak ----
+        # ---- the rest of BASELINE's metric: clear / copy GB/s vs HBM peak, compute dispatch, 1M-triangle mesh ----
         with torch.cuda.stream(stream):
             line["extra"] = {"transfer": transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak),
                              "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src,
+                             "dispatch_2p24": dispatch_extra(torch, queue, stream),
                              "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream)}
-    elif rank == 0:
-        line["e2e"] = None
+    if not args.profile:
+        del targets, fbs
+        torch.cuda.empty_cache()
+        with torch.cuda.stream(stream):
+            sfx = split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrier)
+        if rank == 0:
+            line.setdefault("extra", {})["split_frame_8k_4Mtri"] = sfx
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -214,6 +214,12 @@ KZN_API void* kzn_queue_stream(const KznQueue* queue);
 /* number of kernels this library has launched on the queue since creation (bench `gpu_launches`) */
 KZN_API uint64_t kzn_queue_launch_count(const KznQueue* queue);
 
+/* Device-side duration of the kernel that dominates a command (raster kernel of a draw; the fill / copy / box / blit
+ * kernel of a transfer), measured with a CUDA event pair on the queue's stream — what the benchmark's roofline uses.
+ * kzn_queue_last_kernel_ms waits for the last timed kernel; KZN_NOT_READY if none was launched since enabling. */
+KZN_API KznResult kzn_queue_set_kernel_timing(KznQueue* queue, int32_t enable);
+KZN_API KznResult kzn_queue_last_kernel_ms(KznQueue* queue, float* ms);
+
 /* plain transfers between host memory and device addresses on the queue (used by the ICD for
  * HOST_COHERENT emulation and by the end-to-end benchmark); host memory should be pinned */
 KZN_API KznResult kzn_queue_upload(KznQueue* queue, uint64_t dst_address, const void* src, uint64_t size);

@@ -190,6 +190,8 @@ PROTOTYPES = {
     "kzn_queue_wait_idle": (i32, [vp]),
     "kzn_queue_stream": (vp, [vp]),
     "kzn_queue_launch_count": (u64, [vp]),
+    "kzn_queue_set_kernel_timing": (i32, [vp, i32]),
+    "kzn_queue_last_kernel_ms": (i32, [vp, P(f32)]),
     "kzn_queue_upload": (i32, [vp, u64, vp, u64]),
     "kzn_queue_download": (i32, [vp, vp, u64, u64]),
     "kzn_host_alloc_pinned": (i32, [u64, P(vp)]),

@@ -160,8 +160,18 @@ KznResult kzn_queue_enter(KznQueue* q) {
     return KZN_SUCCESS;
 }
 
+void kzn_timing_begin(KznQueue* q) {
+    if (!q->timing) return;
+    cudaEventRecord(q->time_begin, q->stream);
+    q->timing_armed = true;
+}
+
 KznResult kzn_launched(KznQueue* q, const char* kernel) {
     q->launches++;
+    if (q->timing_armed) {
+        cudaEventRecord(q->time_end, q->stream);
+        q->timing_armed = false;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         kzn_set_error("launch of %s failed: %s", kernel, cudaGetErrorString(e));
@@ -181,6 +191,8 @@ static KznResult make_queue(KznDevice* device, cudaStream_t stream, bool owns, K
     q->launches = 0;
     q->stats_address = 0;
     q->raster = nullptr;
+    q->timing = q->timing_armed = false;
+    q->time_begin = q->time_end = nullptr;
     *queue = q;
     return KZN_SUCCESS;
 }
@@ -206,6 +218,8 @@ void kzn_queue_destroy(KznQueue* queue) {
     cudaSetDevice(queue->device->ordinal);
     cudaStreamSynchronize(queue->stream);
     kzn_raster_scratch_destroy(queue->raster);
+    if (queue->time_begin) cudaEventDestroy(queue->time_begin);
+    if (queue->time_end) cudaEventDestroy(queue->time_end);
     if (queue->owns_stream) cudaStreamDestroy(queue->stream);
     delete queue;
 }
@@ -219,6 +233,33 @@ KznResult kzn_queue_wait_idle(KznQueue* queue) {
 
 void* kzn_queue_stream(const KznQueue* queue) { return queue ? (void*)queue->stream : nullptr; }
 uint64_t kzn_queue_launch_count(const KznQueue* queue) { return queue ? queue->launches : 0; }
+
+KznResult kzn_queue_set_kernel_timing(KznQueue* queue, int32_t enable) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    if (enable && !queue->time_begin) {
+        KZN_CUDA(cudaEventCreate(&queue->time_begin));
+        KZN_CUDA(cudaEventCreate(&queue->time_end));
+    }
+    queue->timing = enable != 0;
+    queue->timing_armed = false;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_queue_last_kernel_ms(KznQueue* queue, float* ms) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(ms, "null out pointer");
+    KZN_VALID(queue->timing && queue->time_begin, "kernel timing is not enabled on this queue");
+    cudaError_t e = cudaEventSynchronize(queue->time_end);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, queue->time_begin, queue->time_end);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        kzn_set_error("no timed kernel has been launched on this queue yet (%s)", cudaGetErrorString(e));
+        return KZN_NOT_READY;
+    }
+    return KZN_SUCCESS;
+}
 
 KznResult kzn_queue_set_draw_statistics(KznQueue* queue, uint64_t stats_address) {
     KZN_VALID(queue, "null queue");

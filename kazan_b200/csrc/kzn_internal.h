@@ -22,6 +22,10 @@ struct KznQueue {
     uint64_t launches;
     uint64_t stats_address;
     KznRasterScratch* raster;  // lazily created, grows to the largest draw seen
+    // kzn_queue_set_kernel_timing: event pair around the dominant kernel of the last command
+    bool timing;
+    bool timing_armed;  // begin recorded, the next kzn_launched records the end
+    cudaEvent_t time_begin, time_end;
 };
 
 struct KznMemory {
@@ -63,6 +67,8 @@ KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int
 KznResult kzn_queue_enter(KznQueue* q);
 // call after every kernel launch: counts it and maps launch errors
 KznResult kzn_launched(KznQueue* q, const char* kernel);
+// call right before launching the kernel that dominates a command (no-op unless kernel timing is enabled)
+void kzn_timing_begin(KznQueue* q);
 
 // layout helpers (image.rs:58-88 + SURVEY.md E.10) ----------------------------------------------
 static inline uint32_t kzn_texel_size(uint32_t format) {

@@ -1238,6 +1238,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     // the destination colour is only read when the result depends on it
     const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
     const size_t smem = sizeof(RasterShared);
+    kzn_timing_begin(q);  // the raster kernel dominates a draw
     if (!p.binned) {  // a few triangles: register-resident tiles, no staging
         if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
             if (need_dst) raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, 0, q->stream>>>(p);

@@ -369,10 +369,12 @@ KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint
         uint64_t chunks = (bytes + kBulkChunk - 1) / kBulkChunk;
         uint64_t cap = (uint64_t)q->device->sm_count * 4;
         int grid = (int)(chunks < cap ? chunks : cap);
+        kzn_timing_begin(q);
         fill_bulk_kernel<<<grid, kThreads, kBulkChunk, q->stream>>>((uint8_t*)(uintptr_t)address, bytes, value);
         return kzn_launched(q, "fill_bulk_kernel");
     }
     uint64_t words = bytes / 4;
+    kzn_timing_begin(q);
     fill_contig_kernel<<<grid_for(q, words / 4 + 1), kThreads, 0, q->stream>>>((uint32_t*)(uintptr_t)address, words, value);
     return kzn_launched(q, "fill_contig_kernel");
 }
@@ -387,6 +389,7 @@ KznResult launch_copy_bulk(KznQueue* q, uint64_t dst, uint64_t src, uint64_t byt
     uint64_t chunks = (bytes + kCopyChunk - 1) / kCopyChunk;
     uint64_t cap = q->device->sm_count;  // one 128 KiB ring per SM
     int grid = (int)(chunks < cap ? chunks : cap);
+    kzn_timing_begin(q);
     copy_bulk_kernel<<<grid, 32, smem, q->stream>>>((uint8_t*)(uintptr_t)dst, (const uint8_t*)(uintptr_t)src, bytes);
     return kzn_launched(q, "copy_bulk_kernel");
 }
@@ -429,6 +432,7 @@ template <int VEC, bool FILL>
 KznResult launch_box_t(KznQueue* q, const BoxParams& p, bool st, bool dt) {
     int grid = grid_for(q, p.total);
 #define KZN_BOX(ST, DT)                                                          \
+    kzn_timing_begin(q);                                                          \
     box_kernel<VEC, ST, DT, FILL><<<grid, kThreads, 0, q->stream>>>(p);           \
     return kzn_launched(q, "box_kernel");
     if (st && dt) { KZN_BOX(true, true) }
@@ -801,6 +805,7 @@ KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const Kzn
                 p.src = lower(image_box(src, 0, 0, sz, b->srcSubresource.baseArrayLayer + l));
                 p.dst = lower(image_box(dst, 0, 0, k, b->dstSubresource.baseArrayLayer + l));
                 dim3 grid((p.w + 31) / 32, (p.h + kThreads / 32 - 1) / (kThreads / 32));
+                kzn_timing_begin(queue);
                 blit_kernel<<<grid, kThreads, 0, queue->stream>>>(p);
                 if ((r = kzn_launched(queue, "blit_kernel"))) return r;
             }

@@ -193,6 +193,17 @@ class Queue:
     def stream(self) -> int:
         return self._lib.kzn_queue_stream(self.handle) or 0
 
+    def set_kernel_timing(self, enable: bool = True):
+        _check(self._lib.kzn_queue_set_kernel_timing(self.handle, int(enable)))
+
+    def last_kernel_ms(self) -> float:
+        """Device duration of the dominant kernel of the last command (waits for it)."""
+        ms = abi.f32()
+        code = _check(self._lib.kzn_queue_last_kernel_ms(self.handle, C.byref(ms)))
+        if code != 0:
+            raise KazanError(code, self._lib.kzn_last_error().decode())
+        return ms.value
+
     def signal_fence(self, fence: Fence):
         _check(self._lib.kzn_queue_signal_fence(self.handle, fence.handle))
 

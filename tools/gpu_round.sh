@@ -13,7 +13,7 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/bench_r
 # launch list of the same command (short run)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_fill.csv python bench.py --steps 20 --warmup 3 --profile > $OUT/ncu_fill.log 2>&1
 # full capture of the dominant kernel of the fill bench
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 3 -c 2 -f -o $OUT/prof_fill python bench.py --steps 5 --warmup 3 --profile > $OUT/ncu_fill_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:raster_ -s 3 -c 2 -f -o $OUT/prof_fill python bench.py --steps 5 --warmup 3 --profile > $OUT/ncu_fill_full.log 2>&1
 # mesh: launch list + full capture of its kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_mesh.csv python tools/prof_mesh.py > $OUT/ncu_mesh.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|setup_kernel|bin_' -s 4 -c 4 -f -o $OUT/prof_mesh python tools/prof_mesh.py > $OUT/ncu_mesh_full.log 2>&1
