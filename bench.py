@@ -372,7 +372,49 @@ def run_reference(args):
     return 0
 
 
-def split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrier):
+class FrameTargets:
+    """The colour targets of a (split) frame and its per-frame composite, in the three ways the bench can run it:
+    one GPU; `peer` — targets live on rank 0 and every rank's raster kernel stores its band there over NVLink peer
+    memory, flags complete the frame (kazan_b200.split_frame.PeerSplitFrame); `nccl` — every rank renders locally and the
+    bands are sent to rank 0 with grouped NCCL send/recv (SplitFrame.composite)."""
+
+    def __init__(self, torch, dist, dev, queue, width, height, world, rank, n_targets, mode):
+        from kazan_b200.split_frame import PeerSplitFrame, SplitFrame
+        self.mode = "single" if world == 1 else mode
+        self.dist, self.world, self.rank, self.n = dist, world, rank, n_targets
+        self.split = SplitFrame(width, height, world, rank)
+        self.frame_bytes = width * height * 4
+        self.frames = 0
+        if self.mode == "peer":
+            self.peer = PeerSplitFrame(dev, queue, width, height, world, rank, dist, n_targets=n_targets)
+            self.addresses = self.peer.target_addresses
+        else:
+            self.tensors = [torch.zeros(self.frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
+            self.addresses = [t.data_ptr() for t in self.tensors]
+
+    def begin(self):
+        if self.mode == "peer":
+            self.peer.begin_frame()
+        return self.frames % self.n  # index of the target this frame renders into
+
+    def end(self):
+        i = self.frames % self.n
+        self.frames += 1
+        if self.mode == "peer":
+            self.peer.end_frame()
+        elif self.mode == "nccl":
+            self.split.composite(self.tensors[i], self.dist)
+        return i
+
+    def close(self):
+        if self.mode == "peer":
+            self.peer.check()
+            self.peer.close()
+        else:
+            self.tensors = []
+
+
+def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, mode):
     """BASELINE configs[4]: 7680x4320 frame of a 4M-triangle mesh (D32 LESS + alpha blend), sort-first split into `world`
     bands, composited to rank 0.  Strong scaling: the frame is fixed, every rank sees all geometry and culls to its band."""
     from kazan_b200.split_frame import SplitFrame
@@ -380,15 +422,18 @@ def split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrie
     verts, idx = grid_mesh(2000, 1000, 5)
     ntri = len(idx) // 3
     d_verts, d_idx = torch.from_numpy(verts).cuda(), torch.from_numpy(idx.view(np.int32)).cuda()
-    color = torch.zeros(W * H * 4, dtype=torch.uint8, device="cuda")
     depth = torch.empty(W * H, dtype=torch.float32, device="cuda")
-    sf = SplitFrame(W, H, world, rank)
+    ft = FrameTargets(torch, dist, dev, queue, W, H, world, rank, 2, mode)
+    sf = ft.split
     y0, y1 = sf.band
-    cimg = host.Image(color.data_ptr(), W, H)
     dimg = host.Image(depth.data_ptr(), W, H, format=abi.FORMAT_D32_SFLOAT)
-    fb = abi.Framebuffer()
-    fb.color, fb.depth = cimg.desc(), dimg.desc()
-    fb.band_y0, fb.band_y1 = y0, y1
+    cimgs = [host.Image(a, W, H) for a in ft.addresses]
+    fbs = []
+    for c in cimgs:
+        fb = abi.Framebuffer()
+        fb.color, fb.depth = c.desc(), dimg.desc()
+        fb.band_y0, fb.band_y1 = y0, y1
+        fbs.append(fb)
     st = mesh_state(abi)
     vp = abi.Viewport(0, 0, W, H, 0, 1)
     sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, H))
@@ -396,10 +441,11 @@ def split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrie
     band = [abi.ClearRect(abi.Rect2D(abi.Offset2D(0, y0), abi.Extent2D(W, y1 - y0)), 0, 1)]
 
     def frame(k):
-        queue.cmd_clear_attachment(cimg, (0, 0, 0, 0), band)
+        i = ft.begin()
+        queue.cmd_clear_attachment(cimgs[i], (0, 0, 0, 0), band)
         queue.cmd_clear_attachment(dimg, (1.0, 0, 0, 0), band)
-        queue.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
-        sf.composite(color, dist)
+        queue.cmd_draw_indexed(st, fbs[i], vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+        ft.end()
 
     reps = 10
     ms = time_region(torch, stream, frame, reps, 3, barrier) / reps
@@ -407,9 +453,16 @@ def split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrie
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"frame": [W, H], "triangles": ntri, "bands": world, "ms_per_frame": ms, "Gpix_per_s": W * H / ms / 1e6, "Mtri_per_s": ntri / ms / 1e3,
-            "composite_bytes": sf.composite_bytes(), "scaling": "strong",
-            "frame_checksum_rank0": int(color.view(torch.int32).sum(dtype=torch.int64).item()) if rank == 0 else None}
+    out = {"frame": [W, H], "triangles": ntri, "bands": world, "ms_per_frame": ms, "Gpix_per_s": W * H / ms / 1e6, "Mtri_per_s": ntri / ms / 1e3,
+            "composite_bytes": sf.composite_bytes(), "scaling": "strong", "composite": ft.mode}
+    if rank == 0:  # checksum of the assembled frame (the same number whatever the band count)
+        last = (ft.frames - 1) % ft.n
+        h = torch.empty(W * H, dtype=torch.int32).pin_memory()
+        queue.download(h.data_ptr(), ft.addresses[last], W * H * 4)
+        queue.wait_idle()
+        out["frame_checksum_rank0"] = int(h.sum(dtype=torch.int64).item())
+    ft.close()
+    return out
 
 
 def run_ours(args):
@@ -439,7 +492,6 @@ def run_ours(args):
     total_h = H * world
     frame_bytes = W * total_h * 4
     n_targets = 8  # each rank writes 8 x 33 MB of distinct lines in rotation (265 MB > 126 MiB L2): never L2 resident
-    sf = SplitFrame(W, total_h, world, rank)
     st = fill_state(abi)
     vp = abi.Viewport(0, 0, W, total_h, 0, 1)
     sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, total_h))
@@ -447,12 +499,14 @@ def run_ours(args):
     vi = abi.VertexInput(verts.data_ptr(), verts.numel() * 4, 28, 0, 3, 12)
 
     with torch.cuda.stream(stream):
-        targets = [torch.zeros(frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
-        fbs = [framebuffer(abi, t.data_ptr(), W, total_h, band=sf.band if world > 1 else (0, 0)) for t in targets]
+        ft = FrameTargets(torch, dist, dev, queue, W, total_h, world, rank, n_targets, args.composite)
+        sf = ft.split
+        fbs = [framebuffer(abi, a, W, total_h, band=sf.band if world > 1 else (0, 0)) for a in ft.addresses]
 
         def step(k):
-            queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3)
-            sf.composite(targets[k % n_targets], dist)
+            i = ft.begin()
+            queue.cmd_draw(st, fbs[i], vp, sc, vi, 3)
+            ft.end()
 
         launches0 = queue.launch_count
         with ClockSampler(local_rank) as clocks:
@@ -479,6 +533,12 @@ def run_ours(args):
     }
     if world > 1:
         line["config"]["composite_bytes_per_step"] = sf.composite_bytes()
+        line["config"]["composite"] = ("bands stored by the raster kernels straight into rank 0's image over NVLink peer memory; flag signal/wait per frame"
+                                       if ft.mode == "peer" else "grouped NCCL send/recv of the bands to rank 0")
+        # the presenter ingests (world-1) bands per frame over its NVLink port: measured peer-copy bandwidth 770 GB/s per direction
+        ingest_gbps = sf.composite_bytes() / (ms_per_step * 1e-3) / 1e9
+        line["nvlink"] = {"presenter_ingest_GBps": ingest_gbps, "peak": 770.0, "frac": ingest_gbps / 770.0,
+                          "peak_source": "B200_PROFILING.md measured peer copy, per direction"}
 
     # ---- e2e: the same frame through the same calls with HOST buffers: vertex upload, draw, composite, frame read-back ----
     with torch.cuda.stream(stream):
@@ -489,10 +549,11 @@ def run_ours(args):
 
         def e2e_step(k):
             queue.upload(d_verts.data_ptr(), h_verts.data_ptr(), 84)
-            queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi2, 3)
-            sf.composite(targets[k % n_targets], dist)
+            i = ft.begin()
+            queue.cmd_draw(st, fbs[i], vp, sc, vi2, 3)
+            ft.end()
             if rank == 0:
-                queue.download(h_frame.data_ptr(), targets[k % n_targets].data_ptr(), frame_bytes)
+                queue.download(h_frame.data_ptr(), ft.addresses[i], frame_bytes)
             queue.wait_idle()  # the frame is in host memory
 
         e_steps = max(5, min(args.steps, 20))
@@ -502,7 +563,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = float(t.item())
     line["e2e"] = {"value": pixels_per_step * e_steps / ems / 1e6, "unit": UNIT, "h2d_bytes_per_step": 84 * world,
-                   "d2h_bytes_per_step": frame_bytes, "steps": e_steps}
+                   "d2h_bytes_per_step": frame_bytes, "steps": e_steps,
+                   "note": "bounded by the frame read-back: 4 B/pixel over PCIe (55 GB/s measured, tools/pcie_probe.py) = 13.8 Gpixels/s"}
 
     if rank == 0 and world == 1:
         # ---- roofline of the dominant kernel (raster_direct_kernel), its duration measured live with the library's
@@ -543,10 +605,11 @@ def run_ours(args):
                              "dispatch_2p24": dispatch_extra(torch, queue, stream),
                              "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream)}
     if not args.profile:
-        del targets, fbs
-        torch.cuda.empty_cache()
         with torch.cuda.stream(stream):
-            sfx = split_frame_extra(torch, dist, abi, host, queue, stream, world, rank, barrier)
+            ft.close()
+            del fbs
+            torch.cuda.empty_cache()
+            sfx = split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, args.composite)
         if rank == 0:
             line.setdefault("extra", {})["split_frame_8k_4Mtri"] = sfx
     if rank == 0:
@@ -563,6 +626,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: bands written into rank 0's image over NVLink peer memory (default) or sent with NCCL send/recv")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e, CPU baseline or transfer sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

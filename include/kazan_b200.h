@@ -204,6 +204,14 @@ KZN_API uint64_t kzn_memory_size(const KznMemory* memory); /* rounded up to 128,
 /* host pointer = base + offset (api_impl.rs:3488-3500); KZN_ERROR_VALIDATION_FAILED for DEVICE_LOCAL */
 KZN_API KznResult kzn_memory_map(KznMemory* memory, uint64_t offset, void** host_ptr);
 
+/* Split-frame rendering (the reference has one physical device, api_impl.rs:5092-5119): a DEVICE_LOCAL
+ * allocation can be exported to the other per-GPU processes of the box and imported there as peer memory (NVLink).
+ * A rank that binds an imported image as its colour attachment renders its band straight into the presenting GPU. */
+#define KZN_MEMORY_HANDLE_BYTES 64u
+KZN_API KznResult kzn_memory_export(KznMemory* memory, uint8_t handle[KZN_MEMORY_HANDLE_BYTES]);
+KZN_API KznResult kzn_memory_import(KznDevice* device, const uint8_t handle[KZN_MEMORY_HANDLE_BYTES], uint64_t size,
+                                    KznMemory** memory); /* release with kzn_memory_free */
+
 /* -- queue: vkGetDeviceQueue :3394, vkQueueSubmit :3414, vkQueueWaitIdle :3424 ---------------- */
 KZN_API KznResult kzn_queue_create(KznDevice* device, KznQueue** queue);
 /* run on a stream owned by the host (e.g. the framework's current stream); not destroyed with the queue */
@@ -219,6 +227,13 @@ KZN_API uint64_t kzn_queue_launch_count(const KznQueue* queue);
  * kzn_queue_last_kernel_ms waits for the last timed kernel; KZN_NOT_READY if none was launched since enabling. */
 KZN_API KznResult kzn_queue_set_kernel_timing(KznQueue* queue, int32_t enable);
 KZN_API KznResult kzn_queue_last_kernel_ms(KznQueue* queue, float* ms);
+
+/* Stream-ordered flags in (peer) device memory, the composite step of a split frame: kzn_cmd_signal_flag makes all prior
+ * work of the queue visible system-wide and then adds `add` to the 64-bit flag; kzn_cmd_wait_flag holds the queue until
+ * the flag is >= expected.  A wait that sees no progress for 5 s gives up and writes 1 to the u32 at status_address
+ * (0 = none) instead of hanging the GPU. */
+KZN_API KznResult kzn_cmd_signal_flag(KznQueue* queue, uint64_t flag_address, uint64_t add);
+KZN_API KznResult kzn_cmd_wait_flag(KznQueue* queue, uint64_t flag_address, uint64_t expected, uint64_t status_address);
 
 /* plain transfers between host memory and device addresses on the queue (used by the ICD for
  * HOST_COHERENT emulation and by the end-to-end benchmark); host memory should be pinned */

@@ -184,6 +184,10 @@ PROTOTYPES = {
     "kzn_memory_device_address": (u64, [vp]),
     "kzn_memory_size": (u64, [vp]),
     "kzn_memory_map": (i32, [vp, u64, P(vp)]),
+    "kzn_memory_export": (i32, [vp, P(C.c_uint8)]),
+    "kzn_memory_import": (i32, [vp, P(C.c_uint8), u64, P(vp)]),
+    "kzn_cmd_signal_flag": (i32, [vp, u64, u64]),
+    "kzn_cmd_wait_flag": (i32, [vp, u64, u64, u64]),
     "kzn_queue_create": (i32, [vp, P(vp)]),
     "kzn_queue_wrap_stream": (i32, [vp, vp, P(vp)]),
     "kzn_queue_destroy": (None, [vp]),

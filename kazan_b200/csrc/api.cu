@@ -108,6 +108,7 @@ KznResult kzn_memory_allocate(KznDevice* device, uint64_t size, uint32_t memory_
     m->device = device;
     m->type = memory_type;
     m->size = rounded;
+    m->imported = false;
     cudaError_t e;
     if (memory_type == KZN_MEMORY_TYPE_HOST_COHERENT) {
         // the reference's single memory type is DEVICE_LOCAL|HOST_VISIBLE|HOST_COHERENT|HOST_CACHED
@@ -131,7 +132,8 @@ KznResult kzn_memory_allocate(KznDevice* device, uint64_t size, uint32_t memory_
 void kzn_memory_free(KznMemory* memory) {
     if (!memory) return;
     cudaSetDevice(memory->device->ordinal);
-    if (memory->type == KZN_MEMORY_TYPE_HOST_COHERENT) cudaFreeHost(memory->host_ptr);
+    if (memory->imported) cudaIpcCloseMemHandle(memory->device_ptr);
+    else if (memory->type == KZN_MEMORY_TYPE_HOST_COHERENT) cudaFreeHost(memory->host_ptr);
     else cudaFree(memory->device_ptr);
     delete memory;
 }

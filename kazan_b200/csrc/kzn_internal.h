@@ -34,6 +34,7 @@ struct KznMemory {
     uint64_t size;  // rounded up to KZN_MIN_MEMORY_MAP_ALIGNMENT
     void* device_ptr;
     void* host_ptr;  // HOST_COHERENT only
+    bool imported;   // opened from another process's export (kzn_memory_import): closed, not freed
 };
 
 struct KznFence {

@@ -122,6 +122,13 @@ class Device:
         _check(self._lib.kzn_memory_allocate(self.handle, size, memory_type, C.byref(h)))
         return Memory(self, h)
 
+    def import_memory(self, handle: bytes, size: int) -> "Memory":
+        """Open another process's exported DEVICE_LOCAL allocation as peer memory (kzn_memory_import)."""
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        h = C.c_void_p()
+        _check(self._lib.kzn_memory_import(self.handle, buf, size, C.byref(h)))
+        return Memory(self, h)
+
     def create_fence(self, signaled: bool = False) -> "Fence":
         h = C.c_void_p()
         _check(self._lib.kzn_fence_create(self.handle, int(signaled), C.byref(h)))
@@ -144,6 +151,11 @@ class Memory:
     @property
     def size(self) -> int:
         return self._lib.kzn_memory_size(self.handle)
+
+    def export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _check(self._lib.kzn_memory_export(self.handle, buf))
+        return bytes(buf)
 
     def map(self, offset: int = 0) -> int:
         p = C.c_void_p()
@@ -203,6 +215,12 @@ class Queue:
         if code != 0:
             raise KazanError(code, self._lib.kzn_last_error().decode())
         return ms.value
+
+    def cmd_signal_flag(self, flag_address: int, add: int = 1):
+        _check(self._lib.kzn_cmd_signal_flag(self.handle, flag_address, add))
+
+    def cmd_wait_flag(self, flag_address: int, expected: int, status_address: int = 0):
+        _check(self._lib.kzn_cmd_wait_flag(self.handle, flag_address, expected, status_address))
 
     def signal_fence(self, fence: Fence):
         _check(self._lib.kzn_queue_signal_fence(self.handle, fence.handle))
