@@ -73,7 +73,7 @@ def build_product(force: bool = False, verbose_ptxas: bool = False) -> Path:
     for s in srcs:
         o = objdir / (s.stem + ".o")
         objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", str(s), "-o", str(o)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("KZN_NVCC_EXTRA", "").split(), "-x", "cu", "-c", str(s), "-o", str(o)]
         if verbose_ptxas:
             cmd[1:1] = ["-Xptxas", "-v"]
         print("+", " ".join(cmd), flush=True)

@@ -548,6 +548,12 @@ __device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_
     }
 }
 
+// bits k of the quad px0..px0+3 whose pixel lies in [xa, xb]
+__device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
+    const int lo = max(xa - px0, 0), hi = min(xb - px0, kPx - 1);
+    return hi >= lo ? ((2u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+}
+
 // One triangle against the 4 adjacent pixels px0..px0+3 of row py that a lane owns, destination values in registers:
 // edge functions evaluated once and stepped by +16a per pixel (exact, R5), barycentric depth (R6), z clip (R3), early-Z
 // (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the 4 pixels got a new colour / depth.
@@ -558,8 +564,6 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
                                           bool depth_test, bool depth_write, bool has_color, uint32_t col[kPx], float depth[kPx],
                                           uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed) {
     const uint32_t bias = t.bias_bits;
-    const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
-    const long long r0 = (long long)t.b[0] * sy + t.c[0], r1 = (long long)t.b[1] * sy + t.c[1], r2 = (long long)t.b[2] * sy + t.c[2];
     live = 0;
     zwrite = 0;
     bool trivial = false;
@@ -567,19 +571,22 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
         // Trivial accept of the whole span: the covered pixels of a row are an interval (each biased edge test is a
         // half-plane), so if both end pixels of the span are covered, every pixel between them is; the depth clip cannot
         // reject (bit 3, set at setup) and this fragment program reads no interpolant — no per-pixel coverage work at all.
-        const int32_t sa = 16 * xa + 8, sb = 16 * xb + 8;
-        trivial = (long long)t.a[0] * sa + r0 + b0 > 0 && (long long)t.a[1] * sa + r1 + b1 > 0 && (long long)t.a[2] * sa + r2 + b2 > 0 &&
-                  (long long)t.a[0] * sb + r0 + b0 > 0 && (long long)t.a[1] * sb + r1 + b1 > 0 && (long long)t.a[2] * sb + r2 + b2 > 0;
+        // The six (edge, end pixel) tests are spread over lanes 0..5 — lane j tests edge j%3 at xa (j < 3) or xb — and
+        // combined with one vote; all 32 lanes of the warp are converged here (span bounds are warp-uniform).
+        const uint32_t lane = threadIdx.x & 31u, e = lane % 3u;
+        const int32_t sx_t = 16 * (lane < 3u ? xa : xb) + 8;
+        const bool ok = (long long)t.a[e] * sx_t + ((long long)t.b[e] * sy + t.c[e]) + (long long)((bias >> e) & 1u) > 0;
+        trivial = (__ballot_sync(0xffffffffu, ok) & 0x3fu) == 0x3fu;
         if (trivial) {
-#pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (px0 + k >= xa && px0 + k <= xb) live |= 1u << k;
+            live = quad_mask(px0, xa, xb);
             n_covered += __popc(live);
             n_passed += __popc(live);
         }
     }
     float l0[kPx], l1[kPx], l2[kPx];
     if (!trivial) {
+        const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
+        const long long r0 = (long long)t.b[0] * sy + t.c[0], r1 = (long long)t.b[1] * sy + t.c[1], r2 = (long long)t.b[2] * sy + t.c[2];
         const int32_t sx = 16 * px0 + 8;
         const long long e0 = (long long)t.a[0] * sx + r0, e1 = (long long)t.a[1] * sx + r1, e2 = (long long)t.a[2] * sx + r2;  // R5, exact
         const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
@@ -675,10 +682,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __g
         __syncthreads();
     }
     if (py < p.cy0 || py > p.cy1) return;  // whole warp
-    uint32_t quad_clip = 0;
-#pragma unroll
-    for (int k = 0; k < kPx; ++k)
-        if (px0 + k >= p.cx0 && px0 + k <= p.cx1) quad_clip |= 1u << k;
+    const uint32_t quad_clip = quad_mask(px0, p.cx0, p.cx1);  // pixels of my quad inside the clip rectangle
     const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kPx <= (int)p.fb_w;
     const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
     unsigned long long caddr = 0, daddr = 0;
