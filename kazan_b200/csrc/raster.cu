@@ -30,6 +30,8 @@ namespace {
 constexpr int kPx = 4;                   // horizontally adjacent pixels per thread: one 16-byte colour vector
 constexpr int kTileW = 32 * kPx, kTileH = 8;  // pixels per raster tile: one warp per row -> 512 B row stores
 constexpr int kRasterThreads = 32 * kTileH;
+constexpr int kDirectPx = 8;                   // raster_direct_kernel: pixels per lane (two 16-byte vectors)
+constexpr int kDirectTileW = 32 * kDirectPx;   // its tiles are 256x8 pixels
 constexpr int kRecs = 128;               // triangle records staged in shared memory per round
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
@@ -511,16 +513,17 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
     }
 }
 
-// 4 interleaved orbits as two packed pairs: fma.rn.f32x2 / add.rn.f32x2 (FFMA2 / FADD2) do two IEEE fp32 operations per
-// issue slot with per-lane results identical to the scalar instructions, so the shader is still the oracle's sequence.
-__device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_w, float inv_h, float rgba[kPx][4]) {
-    static_assert(kPx == 4, "two f32x2 pairs");
-    float2 cx[2], zx[2], zy[2];
+// PX interleaved orbits as PX/2 packed pairs: fma.rn.f32x2 / add.rn.f32x2 (FFMA2 / FADD2) do two IEEE fp32 operations per
+// instruction with per-lane results identical to the scalar instructions, so the shader is still the oracle's sequence.
+template <int PX>
+__device__ __forceinline__ void fs_procedural_orbit_n(int px0, int py, float inv_w, float inv_h, float rgba[PX][4]) {
+    static_assert(PX % 2 == 0, "packed pairs");
+    float2 cx[PX / 2], zx[PX / 2], zy[PX / 2];
     const float v = ((float)py + 0.5f) * inv_h;
     const float cys = fmaf(v, 2.0f, -1.0f);
     const float2 cy = make_float2(cys, cys);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < PX / 2; ++k) {
         const float u0 = ((float)(px0 + 2 * k) + 0.5f) * inv_w, u1 = ((float)(px0 + 2 * k + 1) + 0.5f) * inv_w;
         cx[k] = make_float2(fmaf(u0, 3.5f, -2.5f), fmaf(u1, 3.5f, -2.5f));
         zx[k] = make_float2(0.0f, 0.0f);
@@ -529,7 +532,7 @@ __device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_
 #pragma unroll 8
     for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PX / 2; ++k) {
             const float2 t = __ffma2_rn(zx[k], zx[k], cx[k]);
             const float2 nzx = __ffma2_rn(make_float2(-zy[k].x, -zy[k].y), zy[k], t);
             const float2 nzy = __ffma2_rn(__fadd2_rn(zx[k], zx[k]), zy[k], cy);
@@ -538,7 +541,7 @@ __device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_
         }
     }
 #pragma unroll
-    for (int k = 0; k < kPx; ++k) {
+    for (int k = 0; k < PX; ++k) {
         const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
         float m = fmaf(x, x, y * y);
         rgba[k][0] = 0.25f * m;
@@ -548,20 +551,21 @@ __device__ __forceinline__ void fs_procedural_orbit4(int px0, int py, float inv_
     }
 }
 
-// bits k of the quad px0..px0+3 whose pixel lies in [xa, xb]
+// bits k of the pixel group px0..px0+PX-1 whose pixel lies in [xa, xb]
+template <int PX>
 __device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
-    const int lo = max(xa - px0, 0), hi = min(xb - px0, kPx - 1);
+    const int lo = max(xa - px0, 0), hi = min(xb - px0, PX - 1);
     return hi >= lo ? ((2u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
 }
 
-// One triangle against the 4 adjacent pixels px0..px0+3 of row py that a lane owns, destination values in registers:
+// One triangle against the PX adjacent pixels px0..px0+PX-1 of row py that a lane owns, destination values in registers:
 // edge functions evaluated once and stepped by +16a per pixel (exact, R5), barycentric depth (R6), z clip (R3), early-Z
-// (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the 4 pixels got a new colour / depth.
+// (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the PX pixels got a new colour / depth.
 // [xa, xb] is the triangle's pixel span in this row (bbox, already scissored) clipped to the 128-pixel tile row; it is
 // warp-uniform, and so is the trivial-accept branch.
-template <uint32_t FS, bool NEED_DST>
+template <uint32_t FS, bool NEED_DST, int PX>
 __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, const float* lut, int px0, int py, int32_t sy, int xa, int xb,
-                                          bool depth_test, bool depth_write, bool has_color, uint32_t col[kPx], float depth[kPx],
+                                          bool depth_test, bool depth_write, bool has_color, uint32_t col[PX], float depth[PX],
                                           uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed) {
     const uint32_t bias = t.bias_bits;
     live = 0;
@@ -578,12 +582,12 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
         const bool ok = (long long)t.a[e] * sx_t + ((long long)t.b[e] * sy + t.c[e]) + (long long)((bias >> e) & 1u) > 0;
         trivial = (__ballot_sync(0xffffffffu, ok) & 0x3fu) == 0x3fu;
         if (trivial) {
-            live = quad_mask(px0, xa, xb);
+            live = quad_mask<PX>(px0, xa, xb);
             n_covered += __popc(live);
             n_passed += __popc(live);
         }
     }
-    float l0[kPx], l1[kPx], l2[kPx];
+    float l0[PX], l1[PX], l2[PX];
     if (!trivial) {
         const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
         const long long r0 = (long long)t.b[0] * sy + t.c[0], r1 = (long long)t.b[1] * sy + t.c[1], r2 = (long long)t.b[2] * sy + t.c[2];
@@ -592,7 +596,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
         const long long s0 = 16ll * t.a[0], s1 = 16ll * t.a[1], s2 = 16ll * t.a[2];
         const float inv2a = t.inv2a;
 #pragma unroll
-        for (int k = 0; k < kPx; ++k) {
+        for (int k = 0; k < PX; ++k) {
             const long long f0 = e0 + k * s0, f1 = e1 + k * s1, f2 = e2 + k * s2;
             bool cov = px0 + k >= xa && px0 + k <= xb && f0 + b0 > 0 && f1 + b1 > 0 && f2 + b2 > 0;
             l0[k] = (float)f0 * inv2a;  // R6
@@ -615,12 +619,12 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     }
     if (!has_color) live = 0;
     if (live) {
-        float src[kPx][4];
+        float src[PX][4];
         if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-            fs_procedural_orbit4(px0, py, p.inv_fb_w, p.inv_fb_h, src);
+            fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
         } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k) {
+            for (int k = 0; k < PX; ++k) {
                 float den = fmaf(l2[k], t.iw[2], fmaf(l1[k], t.iw[1], l0[k] * t.iw[0]));
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
@@ -628,7 +632,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             }
         }
 #pragma unroll
-        for (int k = 0; k < kPx; ++k)
+        for (int k = 0; k < PX; ++k)
             if (live >> k & 1u) col[k] = output_merge_lut<NEED_DST>(p.st, lut, src[k], col[k]);  // pixels not live keep their value
     }
 }
@@ -649,7 +653,7 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
     if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);
     uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
     uint32_t live, zwrite;
-    span_quad<FS, NEED_DST>(p, t, sh.unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
+    span_quad<FS, NEED_DST, kPx>(p, t, sh.unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
                             n_passed);
     if (zwrite) {
         *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
@@ -671,9 +675,9 @@ template <uint32_t FS, bool NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __grid_constant__ DrawParams p) {
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW;
+    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kDirectTileW;
     const int py = (int)(p.tile_y0 + blockIdx.y) * kTileH + (int)warp;
-    const int px0 = tile_px0 + (int)lane * kPx;
+    const int px0 = tile_px0 + (int)lane * kDirectPx;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
@@ -682,33 +686,46 @@ __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __g
         __syncthreads();
     }
     if (py < p.cy0 || py > p.cy1) return;  // whole warp
-    const uint32_t quad_clip = quad_mask(px0, p.cx0, p.cx1);  // pixels of my quad inside the clip rectangle
-    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kPx <= (int)p.fb_w;
+    const uint32_t quad_clip = quad_mask<kDirectPx>(px0, p.cx0, p.cx1);  // pixels of my quad inside the clip rectangle
+    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kDirectPx <= (int)p.fb_w;
     const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
     unsigned long long caddr = 0, daddr = 0;
-    uint32_t col[kPx] = {0u, 0u, 0u, 0u};
-    float depth[kPx] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t col[kDirectPx];
+    float depth[kDirectPx];
+#pragma unroll
+    for (int k = 0; k < kDirectPx; ++k) {
+        col[k] = 0u;
+        depth[k] = 0.f;
+    }
     if (quad_clip) {
         if (has_color) caddr = color_addr(p, px0, py);
         if (has_depth) daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px0) * 4ull;
         if (NEED_DST && has_color) {
-            if (cvec) {
-                const uint4 q = *reinterpret_cast<const uint4*>(caddr);
-                col[0] = q.x; col[1] = q.y; col[2] = q.z; col[3] = q.w;
-            } else {
 #pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    if (quad_clip >> k & 1u) col[k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+            for (int h = 0; h < kDirectPx / 4; ++h) {  // 16-byte vectors where the whole group of 4 is inside
+                const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
+                if (m4 == 15u && cvec) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(caddr + 16 * h);
+                    col[4 * h] = q.x; col[4 * h + 1] = q.y; col[4 * h + 2] = q.z; col[4 * h + 3] = q.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (m4 >> k & 1u) col[4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
+                }
             }
         }
         if (depth_test) {
-            if (dvec) {
-                const float4 q = *reinterpret_cast<const float4*>(daddr);
-                depth[0] = q.x; depth[1] = q.y; depth[2] = q.z; depth[3] = q.w;
-            } else {
 #pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    if (quad_clip >> k & 1u) depth[k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+            for (int h = 0; h < kDirectPx / 4; ++h) {
+                const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
+                if (m4 == 15u && dvec) {
+                    const float4 q = *reinterpret_cast<const float4*>(daddr + 16 * h);
+                    depth[4 * h] = q.x; depth[4 * h + 1] = q.y; depth[4 * h + 2] = q.z; depth[4 * h + 3] = q.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (m4 >> k & 1u) depth[4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
+                }
             }
         }
     }
@@ -718,32 +735,32 @@ __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __g
         const TriRec& t = p.tris[i];
         const int4 bb = __ldg(reinterpret_cast<const int4*>(&t));  // minx maxx miny maxy, already scissored
         if (bb.x > bb.y || py < bb.z || py > bb.w) continue;
-        const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kTileW - 1);
+        const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kDirectTileW - 1);
         if (xa > xb) continue;
         uint32_t live, zwrite;
-        span_quad<FS, NEED_DST>(p, t, unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
+        span_quad<FS, NEED_DST, kDirectPx>(p, t, unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
                                 n_passed);
         cdirty |= live;
         zdirty |= zwrite;
     }
     cdirty &= quad_clip;
     zdirty &= quad_clip;
-    if (cdirty) {
-        if (cdirty == 15u && cvec) {
-            *reinterpret_cast<uint4*>(caddr) = make_uint4(col[0], col[1], col[2], col[3]);
-        } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (cdirty >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = col[k];
+    for (int h = 0; h < kDirectPx / 4; ++h) {
+        const uint32_t c4 = (cdirty >> (4 * h)) & 15u, z4 = (zdirty >> (4 * h)) & 15u;
+        if (c4 == 15u && cvec) {
+            *reinterpret_cast<uint4*>(caddr + 16 * h) = make_uint4(col[4 * h], col[4 * h + 1], col[4 * h + 2], col[4 * h + 3]);
+        } else if (c4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = col[4 * h + k];
         }
-    }
-    if (zdirty) {
-        if (zdirty == 15u && dvec) {
-            *reinterpret_cast<float4*>(daddr) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        } else {
+        if (z4 == 15u && dvec) {
+            *reinterpret_cast<float4*>(daddr + 16 * h) = make_float4(depth[4 * h], depth[4 * h + 1], depth[4 * h + 2], depth[4 * h + 3]);
+        } else if (z4) {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (zdirty >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = depth[k];
+            for (int k = 0; k < 4; ++k)
+                if (z4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = depth[4 * h + k];
         }
     }
     if (p.stats) {
@@ -1243,7 +1260,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
     const size_t smem = sizeof(RasterShared);
     kzn_timing_begin(q);  // the raster kernel dominates a draw
-    if (!p.binned) {  // a few triangles: register-resident tiles, no staging
+    if (!p.binned) {  // a few triangles: register-resident tiles, no staging; 256x8 tiles
+        p.tile_x0 = (uint32_t)p.cx0 / kDirectTileW;
+        p.tiles_x = (uint32_t)p.cx1 / kDirectTileW - p.tile_x0 + 1;
+        grid = dim3(p.tiles_x, p.tiles_y);
         if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
             if (need_dst) raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, 0, q->stream>>>(p);
             else raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, 0, q->stream>>>(p);
