@@ -154,7 +154,30 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
         copy = 2 * nbytes * reps / ms / 1e6
         ms = time_region(torch, stream, lambda k: queue.cmd_copy_image_to_buffer(imgs[k % n_img], buffers[(k + 1) % n_img].data_ptr(), nbytes, region), reps, 3)
         copy_back = 2 * nbytes * reps / ms / 1e6
-        out[label] = {"clear_GBps": round(clear, 1), "clear_frac_hbm": round(clear / hbm_peak, 3),
+        # the same three commands, kernel only (CUDA-event pair around the kernel inside the library): separates the
+        # kernel's bandwidth from per-command launch cost, which dominates below ~32 MB
+        kc = nbytes / kernel_ms(torch, queue, lambda k: queue.cmd_clear_color_image(imgs[k % n_img], (0.25, 0.5, 0.75, 1.0)), 10) / 1e6
+        kb = 2 * nbytes / kernel_ms(torch, queue, lambda k: queue.cmd_copy_buffer_to_image(buffers[k % n_img].data_ptr(), nbytes, imgs[k % n_img], region), 10) / 1e6
+        # and recorded into ONE command buffer (vkBeginCommandBuffer .. vkQueueSubmit): a replay costs one host launch
+        # whatever the number of commands, which is how a Vulkan application submits them
+        batch = max(2, min(64, n_img))
+        with queue.record() as cb_clear:
+            for k in range(batch):
+                queue.cmd_clear_color_image(imgs[k % n_img], (0.25, 0.5, 0.75, 1.0))
+        with queue.record() as cb_copy:
+            for k in range(batch):
+                queue.cmd_copy_buffer_to_image(buffers[k % n_img].data_ptr(), nbytes, imgs[k % n_img], region)
+        sub = max(3, reps // batch)
+        ms = time_region(torch, stream, lambda k: queue.submit([cb_clear]), sub, 2)
+        gclear = nbytes * batch * sub / ms / 1e6
+        ms = time_region(torch, stream, lambda k: queue.submit([cb_copy]), sub, 2)
+        gcopy = 2 * nbytes * batch * sub / ms / 1e6
+        cb_clear.destroy(); cb_copy.destroy()
+        out[label] = {"clear_submit_GBps": round(gclear, 1), "clear_submit_frac_hbm": round(gclear / hbm_peak, 3),
+                      "copy_b2i_submit_GBps": round(gcopy, 1), "copy_b2i_submit_frac_hbm": round(gcopy / hbm_peak, 3),
+                      "commands_per_submit": batch,
+                      "clear_kernel_GBps": round(kc, 1), "copy_b2i_kernel_GBps": round(kb, 1),
+                      "clear_GBps": round(clear, 1), "clear_frac_hbm": round(clear / hbm_peak, 3),
                       "copy_b2i_GBps": round(copy, 1), "copy_b2i_frac_hbm": round(copy / hbm_peak, 3),
                       "copy_i2b_GBps": round(copy_back, 1), "copy_i2b_frac_hbm": round(copy_back / hbm_peak, 3),
                       "bytes": nbytes, "rotating_images": n_img, "reps": reps}

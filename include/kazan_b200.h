@@ -242,6 +242,21 @@ KZN_API KznResult kzn_queue_download(KznQueue* queue, void* dst, uint64_t src_ad
 KZN_API KznResult kzn_host_alloc_pinned(uint64_t size, void** ptr);
 KZN_API void kzn_host_free_pinned(void* ptr);
 
+/* -- command buffers: vkAllocateCommandBuffers api_impl.rs:4464, vkBeginCommandBuffer :4483, vkEndCommandBuffer :4491,
+ * vkQueueSubmit :3414 (handle.rs:315 `CommandBuffer {}` is a placeholder upstream).
+ * Between begin and end every kzn_cmd_* call on the queue is RECORDED (a CUDA graph captured from the queue's stream)
+ * instead of executed; kzn_queue_submit replays recorded command buffers in order and then signals `fence` (may be NULL).
+ * Replays cost one launch on the host whatever the number of commands.  Not recordable: waits on the host, fence
+ * signalling, and anything that allocates — a draw recorded into a command buffer needs its raster scratch reserved
+ * first with kzn_queue_reserve_draw (largest triangle count and framebuffer it will see). */
+typedef struct KznCommandBuffer KznCommandBuffer;
+KZN_API KznResult kzn_command_buffer_begin(KznQueue* queue, KznCommandBuffer** command_buffer);
+KZN_API KznResult kzn_command_buffer_end(KznCommandBuffer* command_buffer);
+KZN_API void kzn_command_buffer_destroy(KznCommandBuffer* command_buffer);
+KZN_API uint64_t kzn_command_buffer_launch_count(const KznCommandBuffer* command_buffer); /* kernels per replay */
+KZN_API KznResult kzn_queue_submit(KznQueue* queue, uint32_t count, KznCommandBuffer* const* command_buffers, KznFence* fence);
+KZN_API KznResult kzn_queue_reserve_draw(KznQueue* queue, uint64_t max_triangles, uint32_t width, uint32_t height);
+
 /* -- fences: vkCreateFence..vkWaitForFences api_impl.rs:3653-3697 ----------------------------- */
 KZN_API KznResult kzn_fence_create(KznDevice* device, int32_t signaled, KznFence** fence);
 KZN_API void kzn_fence_destroy(KznFence* fence);

@@ -200,6 +200,12 @@ PROTOTYPES = {
     "kzn_queue_download": (i32, [vp, vp, u64, u64]),
     "kzn_host_alloc_pinned": (i32, [u64, P(vp)]),
     "kzn_host_free_pinned": (None, [vp]),
+    "kzn_command_buffer_begin": (i32, [vp, P(vp)]),
+    "kzn_command_buffer_end": (i32, [vp]),
+    "kzn_command_buffer_destroy": (None, [vp]),
+    "kzn_command_buffer_launch_count": (u64, [vp]),
+    "kzn_queue_submit": (i32, [vp, u32, P(vp), vp]),
+    "kzn_queue_reserve_draw": (i32, [vp, u64, u32, u32]),
     "kzn_fence_create": (i32, [vp, i32, P(vp)]),
     "kzn_fence_destroy": (None, [vp]),
     "kzn_fence_reset": (i32, [vp]),

@@ -11,8 +11,21 @@
 #include <time.h>
 
 #include <new>
+#include <vector>
 
 #include "kzn_internal.h"
+
+// vulkan-driver/src/handle.rs:315 `CommandBuffer {}` (a placeholder upstream): here a CUDA graph captured from the queue's
+// stream between vkBeginCommandBuffer and vkEndCommandBuffer, instantiated once and replayed by vkQueueSubmit.
+struct KznCommandBuffer {
+    KznQueue* queue = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool recording = false;
+    uint64_t launches = 0;            // kernels per replay
+    uint64_t launches_at_begin = 0;
+    std::vector<void*> host_copies;   // vkCmdUpdateBuffer data, captured at record time
+};
 
 void kzn_raster_scratch_destroy(KznRasterScratch* s);  // raster.cu
 
@@ -162,8 +175,17 @@ KznResult kzn_queue_enter(KznQueue* q) {
     return KZN_SUCCESS;
 }
 
+const void* kzn_recorded_host_copy(KznQueue* q, const void* data, size_t size) {
+    if (!q->recording) return data;
+    void* copy = malloc(size ? size : 1);
+    if (!copy) return nullptr;
+    memcpy(copy, data, size);
+    q->recording->host_copies.push_back(copy);
+    return copy;
+}
+
 void kzn_timing_begin(KznQueue* q) {
-    if (!q->timing) return;
+    if (!q->timing || q->recording) return;
     cudaEventRecord(q->time_begin, q->stream);
     q->timing_armed = true;
 }
@@ -195,6 +217,7 @@ static KznResult make_queue(KznDevice* device, cudaStream_t stream, bool owns, K
     q->raster = nullptr;
     q->timing = q->timing_armed = false;
     q->time_begin = q->time_end = nullptr;
+    q->recording = nullptr;
     *queue = q;
     return KZN_SUCCESS;
 }
@@ -229,6 +252,7 @@ void kzn_queue_destroy(KznQueue* queue) {
 KznResult kzn_queue_wait_idle(KznQueue* queue) {
     KznResult r = kzn_queue_enter(queue);
     if (r) return r;
+    KZN_VALID(!queue->recording, "vkQueueWaitIdle while a command buffer is being recorded on this queue");
     KZN_CUDA(cudaStreamSynchronize(queue->stream));
     return KZN_SUCCESS;
 }
@@ -336,6 +360,7 @@ KznResult kzn_queue_signal_fence(KznQueue* queue, KznFence* fence) {
     KznResult r = kzn_queue_enter(queue);
     if (r) return r;
     KZN_VALID(fence, "null fence");
+    KZN_VALID(!queue->recording, "a fence is signalled by vkQueueSubmit, not from inside a command buffer");
     KZN_VALID(!fence->pending && !fence->signaled_without_work, "fence must be unsignaled when submitted");
     KZN_CUDA(cudaEventRecord(fence->event, queue->stream));
     fence->pending = true;
@@ -394,6 +419,86 @@ KznResult kzn_image_memory_requirements(const KznImageDesc* image, uint64_t* siz
     if (size) *size = kzn_round_up(bytes, KZN_IMAGE_ALIGNMENT);
     if (alignment) *alignment = KZN_IMAGE_ALIGNMENT;
     return KZN_SUCCESS;
+}
+
+// ---- command buffers: vkAllocateCommandBuffers :4464, vkBeginCommandBuffer :4483, vkEndCommandBuffer :4491, ------------
+// ---- vkQueueSubmit :3414 (all unimplemented!() upstream) ---------------------------------------------------------------
+
+KznResult kzn_command_buffer_begin(KznQueue* queue, KznCommandBuffer** command_buffer) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(command_buffer, "null out pointer");
+    *command_buffer = nullptr;
+    KZN_VALID(!queue->recording, "another command buffer is already being recorded on this queue");
+    KznCommandBuffer* cb = new (std::nothrow) KznCommandBuffer();
+    KZN_REQUIRE(cb, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    cudaError_t e = cudaStreamBeginCapture(queue->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        delete cb;
+        return kzn_cuda_failed(e, "cudaStreamBeginCapture", __FILE__, __LINE__);
+    }
+    cb->queue = queue;
+    cb->recording = true;
+    cb->launches_at_begin = queue->launches;
+    queue->recording = cb;
+    *command_buffer = cb;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_command_buffer_end(KznCommandBuffer* cb) {
+    KZN_VALID(cb && cb->recording, "vkEndCommandBuffer: the command buffer is not in the recording state");
+    KznQueue* queue = cb->queue;
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    queue->recording = nullptr;
+    cb->recording = false;
+    cb->launches = queue->launches - cb->launches_at_begin;
+    queue->launches = cb->launches_at_begin;  // recording launches nothing
+    cudaError_t e = cudaStreamEndCapture(queue->stream, &cb->graph);
+    if (e != cudaSuccess || !cb->graph) {
+        cudaGetLastError();
+        kzn_set_error("recording failed: %s (a command that cannot be recorded was issued)", cudaGetErrorString(e));
+        return KZN_ERROR_VALIDATION_FAILED;
+    }
+    KZN_CUDA(cudaGraphInstantiate(&cb->exec, cb->graph, 0));
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_queue_submit(KznQueue* queue, uint32_t count, KznCommandBuffer* const* command_buffers, KznFence* fence) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(!queue->recording, "vkQueueSubmit while a command buffer is being recorded on this queue");
+    KZN_VALID(count == 0 || command_buffers, "null command buffer array");
+    for (uint32_t i = 0; i < count; ++i) {
+        KznCommandBuffer* cb = command_buffers[i];
+        KZN_VALID(cb && cb->exec && !cb->recording, "command buffer %u is not in the executable state", i);
+        KZN_VALID(cb->queue->device == queue->device, "command buffer %u was recorded for another device", i);
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        KZN_CUDA(cudaGraphLaunch(command_buffers[i]->exec, queue->stream));
+        queue->launches += command_buffers[i]->launches;
+    }
+    if (fence) return kzn_queue_signal_fence(queue, fence);
+    return KZN_SUCCESS;
+}
+
+uint64_t kzn_command_buffer_launch_count(const KznCommandBuffer* cb) { return cb ? cb->launches : 0; }
+
+void kzn_command_buffer_destroy(KznCommandBuffer* cb) {
+    if (!cb) return;
+    cudaSetDevice(cb->queue->device->ordinal);
+    if (cb->recording) {  // abandoned mid-recording
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(cb->queue->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        cb->queue->recording = nullptr;
+        cb->queue->launches = cb->launches_at_begin;
+        cudaGetLastError();
+    }
+    if (cb->exec) cudaGraphExecDestroy(cb->exec);
+    if (cb->graph) cudaGraphDestroy(cb->graph);
+    for (void* p : cb->host_copies) free(p);
+    delete cb;
 }
 
 }  // extern "C"

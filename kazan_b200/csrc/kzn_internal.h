@@ -14,6 +14,7 @@ struct KznDevice {
 };
 
 struct KznRasterScratch;  // raster.cu
+struct KznCommandBuffer;  // api.cu
 
 struct KznQueue {
     KznDevice* device;
@@ -26,6 +27,7 @@ struct KznQueue {
     bool timing;
     bool timing_armed;  // begin recorded, the next kzn_launched records the end
     cudaEvent_t time_begin, time_end;
+    KznCommandBuffer* recording;  // non-null between kzn_command_buffer_begin and _end: kzn_cmd_* are captured, not run
 };
 
 struct KznMemory {
@@ -70,6 +72,9 @@ KznResult kzn_queue_enter(KznQueue* q);
 KznResult kzn_launched(KznQueue* q, const char* kernel);
 // call right before launching the kernel that dominates a command (no-op unless kernel timing is enabled)
 void kzn_timing_begin(KznQueue* q);
+// host memory whose contents a recorded command reads at replay time: copied into storage owned by the command buffer
+// being recorded (returns `data` itself when the queue is not recording)
+const void* kzn_recorded_host_copy(KznQueue* q, const void* data, size_t size);
 
 // layout helpers (image.rs:58-88 + SURVEY.md E.10) ----------------------------------------------
 static inline uint32_t kzn_texel_size(uint32_t format) {

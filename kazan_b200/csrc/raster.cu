@@ -1086,8 +1086,10 @@ namespace {
 // Scratch grows monotonically; growth happens before any kernel of this draw is enqueued and the old buffer
 // is freed with cudaFree, which synchronises with work still using it.
 template <typename T>
-KznResult grow(T** ptr, size_t* cap, size_t need) {
+KznResult grow(const KznQueue* q, T** ptr, size_t* cap, size_t need) {
     if (need <= *cap) return KZN_SUCCESS;
+    KZN_VALID(!q->recording, "draw needs more raster scratch than is reserved and allocation cannot be recorded: call "
+                             "kzn_queue_reserve_draw(queue, triangles, width, height) before vkBeginCommandBuffer");
     size_t n = need + need / 2;
     T* fresh = nullptr;
     KZN_CUDA(cudaMalloc(&fresh, n * sizeof(T)));
@@ -1165,6 +1167,33 @@ void make_clip(const KznFramebuffer* fb, const KznViewport* vp, const KznRect2D*
     p->zclip_hi = vp->minDepth < vp->maxDepth ? vp->maxDepth : vp->minDepth;
 }
 
+// the queue's raster scratch, grown to hold `total` triangle records and (binned draws) the tile tables
+KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
+    KznResult r;
+    if (!q->raster) {
+        q->raster = new (std::nothrow) KznRasterScratch();
+        KZN_REQUIRE(q->raster, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    }
+    KznRasterScratch* s = q->raster;
+    if ((r = grow(q, &s->tris, &s->tri_capacity, total))) return r;
+    if (binned) {
+        if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
+        // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
+        // segment does not fit fall back to walking the whole triangle list (still exact, only slower)
+        size_t want = total * 8 + tiles;
+        if (want > 0xfffffff0ull) want = 0xfffffff0ull;
+        if ((r = grow(q, &s->bin_entries, &s->bin_capacity, want))) return r;
+    }
+    if (!s->attrs_set) {
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        s->attrs_set = true;
+    }
+    return KZN_SUCCESS;
+}
+
 KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp,
                       const KznRect2D* sc, const KznVertexInput* vi, uint64_t index_base, uint32_t index_type, uint32_t first,
                       uint32_t count, int32_t vertex_offset, uint32_t instance_count) {
@@ -1216,34 +1245,17 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     KZN_REQUIRE(p.tiles_y <= 65535u, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer taller than 524280 rows");
     p.stats = reinterpret_cast<unsigned long long*>(q->stats_address);
 
-    if (!q->raster) {
-        q->raster = new (std::nothrow) KznRasterScratch();
-        KZN_REQUIRE(q->raster, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
-    }
-    KznRasterScratch* s = q->raster;
-    if ((r = grow(&s->tris, &s->tri_capacity, (size_t)total))) return r;
-    p.tris = s->tris;
     size_t tiles = (size_t)p.tiles_x * p.tiles_y;
     p.binned = total > kDirectMax;
+    if ((r = ensure_scratch(q, (size_t)total, tiles, p.binned != 0))) return r;
+    KznRasterScratch* s = q->raster;
+    p.tris = s->tris;
     if (p.binned) {
-        if ((r = grow(&s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
-        // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
-        // segment does not fit fall back to walking the whole triangle list (still exact, only slower)
-        size_t want = (size_t)total * 8 + tiles;
-        if (want > 0xfffffff0ull) want = 0xfffffff0ull;
-        if ((r = grow(&s->bin_entries, &s->bin_capacity, want))) return r;
         p.tile_counts = s->tile_words;
         p.tile_cursor = s->tile_words + tiles;
         p.tile_offsets = s->tile_words + 2 * tiles;
         p.bin_entries = s->bin_entries;
         p.bin_capacity = (uint32_t)(s->bin_capacity > 0xfffffff0ull ? 0xfffffff0ull : s->bin_capacity);
-    }
-    if (!s->attrs_set) {
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        s->attrs_set = true;
     }
 
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
@@ -1286,6 +1298,15 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
 }  // namespace
 
 extern "C" {
+
+KznResult kzn_queue_reserve_draw(KznQueue* queue, uint64_t max_triangles, uint32_t width, uint32_t height) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(!queue->recording, "kzn_queue_reserve_draw allocates: call it before vkBeginCommandBuffer");
+    KZN_VALID(max_triangles > 0 && max_triangles <= 0x7fffffffull && width && height, "kzn_queue_reserve_draw: bad argument");
+    size_t tiles = (size_t)((width + kTileW - 1) / kTileW) * ((height + kTileH - 1) / kTileH);
+    return ensure_scratch(queue, (size_t)max_triangles, tiles, max_triangles > kDirectMax);
+}
 
 KznResult kzn_cmd_draw(KznQueue* queue, const KznGraphicsPipelineState* state, const KznFramebuffer* framebuffer,
                        const KznViewport* viewport, const KznRect2D* scissor, const KznVertexInput* vertices, uint32_t vertex_count,

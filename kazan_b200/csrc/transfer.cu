@@ -721,8 +721,11 @@ KznResult kzn_cmd_update_buffer(KznQueue* queue, uint64_t dst_address, uint64_t 
     KZN_VALID(dst_address && data, "vkCmdUpdateBuffer: null argument");
     KZN_VALID(offset % 4 == 0 && size % 4 == 0 && size != 0 && size <= 65536, "vkCmdUpdateBuffer: dstOffset/dataSize rules (VUID 00036-00038)");
     KZN_VALID(offset < dst_size && size <= dst_size - offset, "vkCmdUpdateBuffer: range outside the buffer");
-    // pageable source: the runtime stages it before returning, which is the "captured at record time" rule
-    KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)(dst_address + offset), data, size, cudaMemcpyHostToDevice, queue->stream));
+    // "the data is copied at record time": outside a command buffer the runtime stages the pageable source before
+    // returning; inside one the command buffer keeps its own copy for the replays
+    const void* src = kzn_recorded_host_copy(queue, data, size);
+    KZN_REQUIRE(src, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)(dst_address + offset), src, size, cudaMemcpyHostToDevice, queue->stream));
     return KZN_SUCCESS;
 }
 

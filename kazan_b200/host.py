@@ -187,6 +187,33 @@ class Fence:
             self.handle = None
 
 
+class CommandBuffer:
+    """vkBeginCommandBuffer .. vkEndCommandBuffer: commands issued on the queue inside the `with` block are recorded."""
+
+    def __init__(self, queue: "Queue"):
+        self.queue, self._lib, self.handle = queue, queue._lib, C.c_void_p()
+
+    def __enter__(self):
+        _check(self._lib.kzn_command_buffer_begin(self.queue.handle, C.byref(self.handle)))
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None:
+            self.destroy()
+            return False
+        _check(self._lib.kzn_command_buffer_end(self.handle))
+        return False
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.kzn_command_buffer_launch_count(self.handle)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_command_buffer_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class Queue:
     """One VkQueue == one CUDA stream.  Method names follow the Vulkan commands they implement."""
 
@@ -204,6 +231,17 @@ class Queue:
     @property
     def stream(self) -> int:
         return self._lib.kzn_queue_stream(self.handle) or 0
+
+    def record(self) -> CommandBuffer:
+        """with queue.record() as cb: queue.cmd_...()   then   queue.submit([cb])"""
+        return CommandBuffer(self)
+
+    def submit(self, command_buffers, fence: "Fence | None" = None):
+        arr = (C.c_void_p * max(len(command_buffers), 1))(*[cb.handle.value for cb in command_buffers])
+        _check(self._lib.kzn_queue_submit(self.handle, len(command_buffers), arr, fence.handle if fence else None))
+
+    def reserve_draw(self, max_triangles: int, width: int, height: int):
+        _check(self._lib.kzn_queue_reserve_draw(self.handle, max_triangles, width, height))
 
     def set_kernel_timing(self, enable: bool = True):
         _check(self._lib.kzn_queue_set_kernel_timing(self.handle, int(enable)))
