@@ -342,30 +342,28 @@ __device__ __forceinline__ bool depth_compare(uint32_t op, float z, float zs) {
     }
 }
 
+// VkBlendFactor 0..9 = {ZERO, ONE, SRC_COLOR, 1-SRC_COLOR, DST_COLOR, 1-DST_COLOR, SRC_ALPHA, 1-SRC_ALPHA, DST_ALPHA,
+// 1-DST_ALPHA}: bit 0 selects "one minus", the upper bits the operand — written as selects (the state is warp-uniform but a
+// switch per channel per fragment costs a branch chain).  Same values as oracle/raster.c: ONE is 1.0f - 0.0f.
 __device__ __forceinline__ float blend_factor(uint32_t f, int ch, const float s[4], const float d[4]) {
-    switch (f) {
-    case 0: return 0.0f;
-    case 1: return 1.0f;
-    case 2: return s[ch];
-    case 3: return 1.0f - s[ch];
-    case 4: return d[ch];
-    case 5: return 1.0f - d[ch];
-    case 6: return s[3];
-    case 7: return 1.0f - s[3];
-    case 8: return d[3];
-    default: return 1.0f - d[3];
-    }
+    const uint32_t sel = f >> 1;
+    float x = 0.0f;
+    x = sel == 1u ? s[ch] : x;
+    x = sel == 2u ? d[ch] : x;
+    x = sel == 3u ? s[3] : x;
+    x = sel == 4u ? d[3] : x;
+    return (f & 1u) ? 1.0f - x : x;
 }
 
+// VkBlendOp 0..4 = {ADD, SUBTRACT, REVERSE_SUBTRACT, MIN, MAX}
 __device__ __forceinline__ float blend_op(uint32_t op, float cs, float sf, float cd, float df) {
-    float t0 = cs * sf, t1 = cd * df;
-    switch (op) {
-    case 0: return t0 + t1;
-    case 1: return t0 - t1;
-    case 2: return t1 - t0;
-    case 3: return cs < cd ? cs : cd;
-    default: return cs > cd ? cs : cd;
-    }
+    const float t0 = cs * sf, t1 = cd * df;
+    float r = t0 + t1;
+    r = op == 1u ? t0 - t1 : r;
+    r = op == 2u ? t1 - t0 : r;
+    r = op == 3u ? (cs < cd ? cs : cd) : r;
+    r = op == 4u ? (cs > cd ? cs : cd) : r;
+    return r;
 }
 
 __device__ __forceinline__ void fs_procedural_orbit(int px, int py, float inv_w, float inv_h, float rgba[4]) {
@@ -415,6 +413,109 @@ struct RasterShared {
     float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
     uint32_t warp_counts[kTileH];
 };
+
+// Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.list, by the whole CTA.  The binning
+// atomics deliver each tile's list in arbitrary order; primitive order (R7) is restored here.  Only the bits in which the
+// ids of this tile differ are sorted (ids of one tile come from a narrow range of a mesh: typically 2 passes).
+// Warp w owns a contiguous slice of the list and walks it 32 ids at a time; match.any ranks equal digits inside a batch
+// in lane order, a [digit][warp] table of running offsets orders batches and warps, so every pass is stable.
+// Scratch aliases parts of the tile state that are not live yet: sh.recs (second id buffer), sh.queue (offset table).
+__device__ __forceinline__ void sort_tile_list(RasterShared& sh, uint32_t n) {
+    static_assert(sizeof(sh.recs) >= kSortCap * sizeof(uint32_t), "second id buffer aliases recs");
+    static_assert(sizeof(sh.queue) >= 256 * kTileH * sizeof(uint32_t), "offset table aliases the fragment queues");
+    constexpr uint32_t kFull = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t* a = sh.list;
+    uint32_t* b = reinterpret_cast<uint32_t*>(sh.recs);
+    uint32_t* table = reinterpret_cast<uint32_t*>(sh.queue);  // [256 digits][kTileH warps]
+    // range of the ids
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = tid; i < n; i += kRasterThreads) {
+        const uint32_t v = a[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    if (lane == 0) {
+        sh.warp_counts[warp] = lo;
+        table[warp] = hi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kTileH; ++w) {
+        lo = min(lo, sh.warp_counts[w]);
+        hi = max(hi, table[w]);
+    }
+    __syncthreads();
+    const uint32_t span = hi - lo;
+    const uint32_t bits = span ? 32u - (uint32_t)__clz(span) : 0u;
+    const uint32_t per = ((n + kRasterThreads - 1) / kRasterThreads) * 32u;  // ids per warp, whole batches
+    const uint32_t w_beg = min(warp * per, n), w_end = min(w_beg + per, n);
+    for (uint32_t shift = 0; shift < bits; shift += 8) {
+        for (uint32_t i = tid; i < 256u * kTileH; i += kRasterThreads) table[i] = 0;
+        __syncthreads();
+        // digit counts per warp
+        for (uint32_t base = w_beg; base < w_end; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < w_end;
+            const uint32_t d = valid ? ((a[i] - lo) >> shift) & 255u : 256u + lane;
+            const uint32_t peers = __match_any_sync(kFull, d);
+            if (valid && (int)lane == __ffs(peers) - 1) table[d * kTileH + warp] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan in (digit, warp) order: thread t owns digit t
+        {
+            uint32_t v[kTileH], total = 0;
+#pragma unroll
+            for (int k = 0; k < kTileH; ++k) {
+                v[k] = total;
+                total += table[tid * kTileH + k];
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            if (lane == 31) sh.warp_counts[warp] = incl;
+            __syncthreads();
+            uint32_t before = incl - total;
+#pragma unroll
+            for (int w = 0; w < kTileH; ++w)
+                if ((uint32_t)w < warp) before += sh.warp_counts[w];
+#pragma unroll
+            for (int k = 0; k < kTileH; ++k) table[tid * kTileH + k] = before + v[k];
+        }
+        __syncthreads();
+        // stable scatter
+        for (uint32_t base = w_beg; base < w_end; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < w_end;
+            const uint32_t v = valid ? a[i] : 0u;
+            const uint32_t d = valid ? ((v - lo) >> shift) & 255u : 256u + lane;
+            const uint32_t peers = __match_any_sync(kFull, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t start = 0;
+            if (valid && (int)lane == leader) {
+                start = table[d * kTileH + warp];
+                table[d * kTileH + warp] = start + __popc(peers);
+            }
+            start = __shfl_sync(kFull, start, leader);
+            if (valid) b[start + __popc(peers & ((1u << lane) - 1u))] = v;
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t* t = a;
+        a = b;
+        b = t;
+    }
+    if (a != sh.list) {
+        for (uint32_t i = tid; i < n; i += kRasterThreads) sh.list[i] = a[i];
+        __syncthreads();
+    }
+}
 
 // blend with the destination held as UNORM8 in shared memory; same operation order as oracle/raster.c output_merge
 template <bool NEED_DST>
@@ -809,26 +910,10 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
         if (list_len == 0) return;
         if (list_len <= (uint32_t)kSortCap && end <= p.bin_capacity) {
             direct = false;
-            // load and bitonic-sort the tile's triangle ids (ascending = primitive order)
-            uint32_t n2 = 1;
-            while (n2 < list_len) n2 <<= 1;
-            for (uint32_t i = tid; i < n2; i += kRasterThreads) sh.list[i] = i < list_len ? p.bin_entries[beg + i] : 0xffffffffu;
+            // load and sort the tile's triangle ids (ascending = primitive order)
+            for (uint32_t i = tid; i < list_len; i += kRasterThreads) sh.list[i] = p.bin_entries[beg + i];
             __syncthreads();
-            for (uint32_t k = 2; k <= n2; k <<= 1)
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = tid; i < n2; i += kRasterThreads) {
-                        uint32_t l = i ^ j;
-                        if (l > i) {
-                            uint32_t a = sh.list[i], b = sh.list[l];
-                            bool up = (i & k) == 0;
-                            if ((a > b) == up) {
-                                sh.list[i] = b;
-                                sh.list[l] = a;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
+            sort_tile_list(sh, list_len);
         } else if (p.stats && tid == 0) {
             atomicAdd(&p.stats[7], 1ull);
         }

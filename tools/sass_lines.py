@@ -19,6 +19,9 @@ for l in txt[start + 1:]:
     if m:
         seq.append((m.group(2).strip(), cur))
 rows = list(csv.reader(open(prof_csv)))
+ends = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+if len(ends) > 1:  # several launches in the report: the first one
+    rows = rows[:ends[1]]
 hdr = rows[1]
 ia, ie, iss = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Warp Stall Sampling (All Samples)')
 prof = [(r[ia].strip(), int(r[ie]), int(r[iss]) if r[iss].isdigit() else 0) for r in rows[2:] if len(r) >= len(hdr)]
