@@ -37,6 +37,10 @@ constexpr int kWideSpan = 64;            // spans of at least this many pixels i
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
+// how a kernel instantiation treats the destination colour (template parameter NEED_DST)
+constexpr int kDstNone = 0;       // no blending, all channels written: the destination is never read
+constexpr int kDstGeneric = 1;    // any blend state / write mask, resolved per fragment
+constexpr int kDstAlphaOver = 2;  // SRC_ALPHA, ONE_MINUS_SRC_ALPHA, ADD for colour and alpha, write mask RGBA
 
 struct __align__(16) TriRec {
     int32_t minx, maxx, miny, maxy;  // inclusive, scissored; minx > maxx => produces no fragments
@@ -518,7 +522,7 @@ __device__ __forceinline__ void sort_tile_list(RasterShared& sh, uint32_t n) {
 }
 
 // blend with the destination held as UNORM8 in shared memory; same operation order as oracle/raster.c output_merge
-template <bool NEED_DST>
+template <int NEED_DST>
 __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineState& st, const float* lut, const float src[4],
                                                      uint32_t dst_word) {
     float s[4], o[4];
@@ -526,6 +530,18 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
     for (int ch = 0; ch < 4; ++ch) s[ch] = clamp01(src[ch]);
     if (!NEED_DST) {  // no blending, all channels written
         return float_to_unorm8(s[0]) | (float_to_unorm8(s[1]) << 8) | (float_to_unorm8(s[2]) << 16) | (float_to_unorm8(s[3]) << 24);
+    }
+    if (NEED_DST == kDstAlphaOver) {
+        // SRC_ALPHA / ONE_MINUS_SRC_ALPHA / ADD on colour and alpha, all channels written (the usual "over" blend):
+        // the generic expression of R8 with the factors resolved at compile time — same operations, same order
+        const float sf = s[3], df = 1.0f - s[3];
+        uint32_t out = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float t0 = s[ch] * sf, t1 = lut[(dst_word >> (8 * ch)) & 255u] * df;
+            out |= float_to_unorm8(t0 + t1) << (8 * ch);
+        }
+        return out;
     }
     if (st.blend_enable) {
         float d[4];
@@ -550,7 +566,7 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
 
 // Depth test, fragment program and blend for the first `n` (<= 32) queued fragments of a warp's row, one fragment per lane.
 // Fragments of the batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
-template <uint32_t FS, bool NEED_DST>
+template <uint32_t FS, int NEED_DST>
 __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n,
                                                 int tile_px0, int py, bool depth_test, bool depth_write, bool has_color,
                                                 uint32_t& n_passed) {
@@ -664,7 +680,7 @@ __device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
 // (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the PX pixels got a new colour / depth.
 // [xa, xb] is the triangle's pixel span in this row (bbox, already scissored) clipped to the 128-pixel tile row; it is
 // warp-uniform, and so is the trivial-accept branch.
-template <uint32_t FS, bool NEED_DST, int PX>
+template <uint32_t FS, int NEED_DST, int PX>
 __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, const float* lut, int px0, int py, int32_t sy, int xa, int xb,
                                           bool depth_test, bool depth_write, bool has_color, uint32_t col[PX], float depth[PX],
                                           uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed) {
@@ -740,7 +756,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
 
 // A triangle whose span covers at least half of the warp's row inside the streaming kernel: lane l handles the 4 pixels
 // 4l..4l+3 of the row directly (16-byte shared-memory accesses, no fragment queue).
-template <uint32_t FS, bool NEED_DST>
+template <uint32_t FS, int NEED_DST>
 __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
                                            int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
                                            uint32_t& n_covered, uint32_t& n_passed) {
@@ -772,7 +788,7 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
 // REGISTERS while it walks the triangle records in primitive order (uniform loads: every lane reads the same record),
 // so per-pixel fragment order is the primitive order by construction and the tile needs no shared memory beyond the
 // UNORM8 table.  Rows and tiles a triangle's bounding box misses are rejected on the 16-byte bbox alone.
-template <uint32_t FS, bool NEED_DST>
+template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __grid_constant__ DrawParams p) {
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -881,7 +897,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __g
 // for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
 // time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
 // Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
-template <uint32_t FS, bool NEED_DST>
+template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
@@ -1270,10 +1286,13 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
         if ((r = grow(q, &s->bin_entries, &s->bin_capacity, want))) return r;
     }
     if (!s->attrs_set) {
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
-        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterShared)));
+        const int bytes = (int)sizeof(RasterShared);
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, kDstNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, kDstGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_VERTEX_COLOR, kDstAlphaOver>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         s->attrs_set = true;
     }
     return KZN_SUCCESS;
@@ -1357,26 +1376,32 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
     const size_t smem = sizeof(RasterShared);
     kzn_timing_begin(q);  // the raster kernel dominates a draw
+    const bool alpha_over = need_dst && st->blend_enable && (st->color_write_mask & 15u) == 15u && st->src_color_blend_factor == 6 &&
+                            st->dst_color_blend_factor == 7 && st->color_blend_op == 0 && st->src_alpha_blend_factor == 6 &&
+                            st->dst_alpha_blend_factor == 7 && st->alpha_blend_op == 0;
+    const int mode = !need_dst ? kDstNone : alpha_over ? kDstAlphaOver : kDstGeneric;
+    const bool orbit = st->fragment_program == KZN_FS_PROCEDURAL_ORBIT;
+#define KZN_RASTER_LAUNCH(KERNEL, SMEM)                                                                      \
+    do {                                                                                                     \
+        if (orbit) {                                                                                         \
+            if (mode == kDstNone) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstNone><<<grid, kRasterThreads, SMEM, q->stream>>>(p);             \
+            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver><<<grid, kRasterThreads, SMEM, q->stream>>>(p); \
+            else KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric><<<grid, kRasterThreads, SMEM, q->stream>>>(p);   \
+        } else {                                                                                             \
+            if (mode == kDstNone) KERNEL<KZN_FS_VERTEX_COLOR, kDstNone><<<grid, kRasterThreads, SMEM, q->stream>>>(p);                 \
+            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_VERTEX_COLOR, kDstAlphaOver><<<grid, kRasterThreads, SMEM, q->stream>>>(p);     \
+            else KERNEL<KZN_FS_VERTEX_COLOR, kDstGeneric><<<grid, kRasterThreads, SMEM, q->stream>>>(p);       \
+        }                                                                                                    \
+    } while (0)
     if (!p.binned) {  // a few triangles: register-resident tiles, no staging; 256x8 tiles
         p.tile_x0 = (uint32_t)p.cx0 / kDirectTileW;
         p.tiles_x = (uint32_t)p.cx1 / kDirectTileW - p.tile_x0 + 1;
         grid = dim3(p.tiles_x, p.tiles_y);
-        if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
-            if (need_dst) raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, 0, q->stream>>>(p);
-            else raster_direct_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, 0, q->stream>>>(p);
-        } else {
-            if (need_dst) raster_direct_kernel<KZN_FS_VERTEX_COLOR, true><<<grid, kRasterThreads, 0, q->stream>>>(p);
-            else raster_direct_kernel<KZN_FS_VERTEX_COLOR, false><<<grid, kRasterThreads, 0, q->stream>>>(p);
-        }
+        KZN_RASTER_LAUNCH(raster_direct_kernel, 0);
         return kzn_launched(q, "raster_direct_kernel");
     }
-    if (st->fragment_program == KZN_FS_PROCEDURAL_ORBIT) {
-        if (need_dst) raster_kernel<KZN_FS_PROCEDURAL_ORBIT, true><<<grid, kRasterThreads, smem, q->stream>>>(p);
-        else raster_kernel<KZN_FS_PROCEDURAL_ORBIT, false><<<grid, kRasterThreads, smem, q->stream>>>(p);
-    } else {
-        if (need_dst) raster_kernel<KZN_FS_VERTEX_COLOR, true><<<grid, kRasterThreads, smem, q->stream>>>(p);
-        else raster_kernel<KZN_FS_VERTEX_COLOR, false><<<grid, kRasterThreads, smem, q->stream>>>(p);
-    }
+    KZN_RASTER_LAUNCH(raster_kernel, smem);
+#undef KZN_RASTER_LAUNCH
     return kzn_launched(q, "raster_kernel");
 }
 
