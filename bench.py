@@ -397,9 +397,10 @@ def run_reference(args):
 
 class FrameTargets:
     """The colour targets of a (split) frame and its per-frame composite, in the three ways the bench can run it:
-    one GPU; `peer` — targets live on rank 0 and every rank's raster kernel stores its band there over NVLink peer
-    memory, flags complete the frame (kazan_b200.split_frame.PeerSplitFrame); `nccl` — every rank renders locally and the
-    bands are sent to rank 0 with grouped NCCL send/recv (SplitFrame.composite)."""
+    one GPU; `push` — every rank renders locally and its copy queue pushes the band into rank 0's image with the copy
+    engines over NVLink peer memory while the next frame renders; `store` — the raster kernels store the band straight into
+    rank 0's image; both complete a frame with flag signal/wait (kazan_b200.split_frame.PeerSplitFrame); `nccl` — the bands
+    are sent to rank 0 with grouped NCCL send/recv after the draw (SplitFrame.composite)."""
 
     def __init__(self, torch, dist, dev, queue, width, height, world, rank, n_targets, mode):
         from kazan_b200.split_frame import PeerSplitFrame, SplitFrame
@@ -408,29 +409,39 @@ class FrameTargets:
         self.split = SplitFrame(width, height, world, rank)
         self.frame_bytes = width * height * 4
         self.frames = 0
-        if self.mode == "peer":
-            self.peer = PeerSplitFrame(dev, queue, width, height, world, rank, dist, n_targets=n_targets)
-            self.addresses = self.peer.target_addresses
+        if self.mode in ("push", "store"):
+            self.peer = PeerSplitFrame(dev, queue, width, height, world, rank, dist, n_targets=n_targets, mode=self.mode)
+            self.addresses = self.peer.target_addresses    # the presenter's images (rank 0 reads frames from these)
+            self.render = self.peer.render_addresses()     # what this rank's draws may be pointed at
         else:
             self.tensors = [torch.zeros(self.frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(n_targets)]
             self.addresses = [t.data_ptr() for t in self.tensors]
+            self.render = self.addresses
 
     def begin(self):
-        if self.mode == "peer":
-            self.peer.begin_frame()
-        return self.frames % self.n  # index of the target this frame renders into
+        """Index into `render` of the image this frame's band is drawn into."""
+        if self.mode in ("push", "store"):
+            return self.render.index(self.peer.begin_frame())
+        return self.frames % self.n
 
     def end(self):
+        """Publishes the band; returns the index into `addresses` of the frame's image on rank 0."""
         i = self.frames % self.n
         self.frames += 1
-        if self.mode == "peer":
+        if self.mode in ("push", "store"):
             self.peer.end_frame()
         elif self.mode == "nccl":
             self.split.composite(self.tensors[i], self.dist)
         return i
 
+    def wait_idle(self, queue):
+        if self.mode in ("push", "store"):
+            self.peer.wait_idle()
+        else:
+            queue.wait_idle()
+
     def close(self):
-        if self.mode == "peer":
+        if self.mode in ("push", "store"):
             self.peer.check()
             self.peer.close()
         else:
@@ -450,7 +461,7 @@ def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, b
     sf = ft.split
     y0, y1 = sf.band
     dimg = host.Image(depth.data_ptr(), W, H, format=abi.FORMAT_D32_SFLOAT)
-    cimgs = [host.Image(a, W, H) for a in ft.addresses]
+    cimgs = [host.Image(a, W, H) for a in ft.render]
     fbs = []
     for c in cimgs:
         fb = abi.Framebuffer()
@@ -481,6 +492,7 @@ def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, b
     if rank == 0:  # checksum of the assembled frame (the same number whatever the band count)
         last = (ft.frames - 1) % ft.n
         h = torch.empty(W * H, dtype=torch.int32).pin_memory()
+        ft.wait_idle(queue)
         queue.download(h.data_ptr(), ft.addresses[last], W * H * 4)
         queue.wait_idle()
         out["frame_checksum_rank0"] = int(h.sum(dtype=torch.int64).item())
@@ -501,6 +513,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — kazan_b200 has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
@@ -524,7 +537,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         ft = FrameTargets(torch, dist, dev, queue, W, total_h, world, rank, n_targets, args.composite)
         sf = ft.split
-        fbs = [framebuffer(abi, a, W, total_h, band=sf.band if world > 1 else (0, 0)) for a in ft.addresses]
+        fbs = [framebuffer(abi, a, W, total_h, band=sf.band if world > 1 else (0, 0)) for a in ft.render]
 
         def step(k):
             i = ft.begin()
@@ -556,8 +569,10 @@ def run_ours(args):
     }
     if world > 1:
         line["config"]["composite_bytes_per_step"] = sf.composite_bytes()
-        line["config"]["composite"] = ("bands stored by the raster kernels straight into rank 0's image over NVLink peer memory; flag signal/wait per frame"
-                                       if ft.mode == "peer" else "grouped NCCL send/recv of the bands to rank 0")
+        line["config"]["composite"] = {
+            "push": "bands rendered locally, pushed into rank 0's image by the copy engines over NVLink peer memory while the next frame renders; flag signal/wait per frame",
+            "store": "bands stored by the raster kernels straight into rank 0's image over NVLink peer memory; flag signal/wait per frame",
+            "nccl": "grouped NCCL send/recv of the bands to rank 0 after the draw"}[ft.mode]
         # the presenter ingests (world-1) bands per frame over its NVLink port: measured peer-copy bandwidth 770 GB/s per direction
         ingest_gbps = sf.composite_bytes() / (ms_per_step * 1e-3) / 1e9
         line["nvlink"] = {"presenter_ingest_GBps": ingest_gbps, "peak": 770.0, "frac": ingest_gbps / 770.0,
@@ -574,10 +589,10 @@ def run_ours(args):
             queue.upload(d_verts.data_ptr(), h_verts.data_ptr(), 84)
             i = ft.begin()
             queue.cmd_draw(st, fbs[i], vp, sc, vi2, 3)
-            ft.end()
+            j = ft.end()
             if rank == 0:
-                queue.download(h_frame.data_ptr(), ft.addresses[i], frame_bytes)
-            queue.wait_idle()  # the frame is in host memory
+                queue.download(h_frame.data_ptr(), ft.addresses[j], frame_bytes)
+            ft.wait_idle(queue)  # the frame is in host memory
 
         e_steps = max(5, min(args.steps, 20))
         ems = time_region(torch, stream, e2e_step, e_steps, 3, barrier)
@@ -649,8 +664,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: bands written into rank 0's image over NVLink peer memory (default) or sent with NCCL send/recv")
+    ap.add_argument("--composite", default="push", choices=["push", "store", "nccl"],
+                    help="N > 1: how bands reach rank 0 (see FrameTargets)")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e, CPU baseline or transfer sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -235,6 +235,10 @@ KZN_API KznResult kzn_queue_last_kernel_ms(KznQueue* queue, float* ms);
 KZN_API KznResult kzn_cmd_signal_flag(KznQueue* queue, uint64_t flag_address, uint64_t add);
 KZN_API KznResult kzn_cmd_wait_flag(KznQueue* queue, uint64_t flag_address, uint64_t expected, uint64_t status_address);
 
+/* device-to-device copy on the copy engines (no SM time): local or imported peer addresses; used to push a rendered band
+ * to the presenting GPU while the SMs already render the next frame */
+KZN_API KznResult kzn_queue_copy_dma(KznQueue* queue, uint64_t dst_address, uint64_t src_address, uint64_t size);
+
 /* plain transfers between host memory and device addresses on the queue (used by the ICD for
  * HOST_COHERENT emulation and by the end-to-end benchmark); host memory should be pinned */
 KZN_API KznResult kzn_queue_upload(KznQueue* queue, uint64_t dst_address, const void* src, uint64_t size);
@@ -256,6 +260,16 @@ KZN_API void kzn_command_buffer_destroy(KznCommandBuffer* command_buffer);
 KZN_API uint64_t kzn_command_buffer_launch_count(const KznCommandBuffer* command_buffer); /* kernels per replay */
 KZN_API KznResult kzn_queue_submit(KznQueue* queue, uint32_t count, KznCommandBuffer* const* command_buffers, KznFence* fence);
 KZN_API KznResult kzn_queue_reserve_draw(KznQueue* queue, uint64_t max_triangles, uint32_t width, uint32_t height);
+
+/* -- semaphores: vkCreateSemaphore api_impl.rs:3700 (unimplemented!() upstream; handle.rs `Semaphore {}`) — binary,
+ * device-side ordering between two queues of one device, as vkQueueSubmit's pSignalSemaphores / pWaitSemaphores:
+ * work enqueued on `queue` after the wait starts only when everything enqueued before the matching signal has finished.
+ * A signal must be enqueued (on the host) before the wait that consumes it. */
+typedef struct KznSemaphore KznSemaphore;
+KZN_API KznResult kzn_semaphore_create(KznDevice* device, KznSemaphore** semaphore);
+KZN_API void kzn_semaphore_destroy(KznSemaphore* semaphore);
+KZN_API KznResult kzn_queue_signal_semaphore(KznQueue* queue, KznSemaphore* semaphore);
+KZN_API KznResult kzn_queue_wait_semaphore(KznQueue* queue, KznSemaphore* semaphore);
 
 /* -- fences: vkCreateFence..vkWaitForFences api_impl.rs:3653-3697 ----------------------------- */
 KZN_API KznResult kzn_fence_create(KznDevice* device, int32_t signaled, KznFence** fence);

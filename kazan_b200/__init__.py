@@ -5,6 +5,6 @@ include/kazan_b200.h).  This package holds its sources (csrc/), the build recipe
 harness used by tests and bench.  Nothing here falls back to the CPU or to PyTorch.
 """
 from . import abi  # noqa: F401
-from .host import Device, Fence, Image, KazanError, Memory, Queue, library_path, load_library  # noqa: F401
+from .host import CommandBuffer, Device, Fence, Image, KazanError, Memory, Queue, Semaphore, library_path, load_library  # noqa: F401
 
 __all__ = ["abi", "Device", "Fence", "Image", "KazanError", "Memory", "Queue", "library_path", "load_library"]

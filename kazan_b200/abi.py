@@ -206,6 +206,11 @@ PROTOTYPES = {
     "kzn_command_buffer_launch_count": (u64, [vp]),
     "kzn_queue_submit": (i32, [vp, u32, P(vp), vp]),
     "kzn_queue_reserve_draw": (i32, [vp, u64, u32, u32]),
+    "kzn_semaphore_create": (i32, [vp, P(vp)]),
+    "kzn_semaphore_destroy": (None, [vp]),
+    "kzn_queue_signal_semaphore": (i32, [vp, vp]),
+    "kzn_queue_wait_semaphore": (i32, [vp, vp]),
+    "kzn_queue_copy_dma": (i32, [vp, u64, u64, u64]),
     "kzn_fence_create": (i32, [vp, i32, P(vp)]),
     "kzn_fence_destroy": (None, [vp]),
     "kzn_fence_reset": (i32, [vp]),

@@ -421,6 +421,62 @@ KznResult kzn_image_memory_requirements(const KznImageDesc* image, uint64_t* siz
     return KZN_SUCCESS;
 }
 
+// ---- semaphores ------------------------------------------------------------------------------------------------
+
+KznResult kzn_semaphore_create(KznDevice* device, KznSemaphore** semaphore) {
+    KZN_VALID(device && semaphore, "kzn_semaphore_create: null argument");
+    *semaphore = nullptr;
+    KZN_CUDA(cudaSetDevice(device->ordinal));
+    KznSemaphore* s = new (std::nothrow) KznSemaphore();
+    KZN_REQUIRE(s, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    s->device = device;
+    s->signaled = false;
+    cudaError_t e = cudaEventCreateWithFlags(&s->event, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete s;
+        return kzn_cuda_failed(e, "cudaEventCreateWithFlags", __FILE__, __LINE__);
+    }
+    *semaphore = s;
+    return KZN_SUCCESS;
+}
+
+void kzn_semaphore_destroy(KznSemaphore* semaphore) {
+    if (!semaphore) return;
+    cudaSetDevice(semaphore->device->ordinal);
+    cudaEventDestroy(semaphore->event);
+    delete semaphore;
+}
+
+KznResult kzn_queue_signal_semaphore(KznQueue* queue, KznSemaphore* semaphore) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(semaphore, "null semaphore");
+    KZN_VALID(!queue->recording, "semaphores belong to vkQueueSubmit, not to a command buffer");
+    KZN_CUDA(cudaEventRecord(semaphore->event, queue->stream));
+    semaphore->signaled = true;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_queue_wait_semaphore(KznQueue* queue, KznSemaphore* semaphore) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(semaphore, "null semaphore");
+    KZN_VALID(!queue->recording, "semaphores belong to vkQueueSubmit, not to a command buffer");
+    KZN_VALID(semaphore->signaled, "semaphore wait without a pending signal (binary semaphore rules)");
+    KZN_CUDA(cudaStreamWaitEvent(queue->stream, semaphore->event, 0));
+    semaphore->signaled = false;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_queue_copy_dma(KznQueue* queue, uint64_t dst_address, uint64_t src_address, uint64_t size) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(dst_address && src_address, "kzn_queue_copy_dma: null address");
+    if (size == 0) return KZN_SUCCESS;
+    KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)dst_address, (const void*)(uintptr_t)src_address, size, cudaMemcpyDeviceToDevice, queue->stream));
+    return KZN_SUCCESS;
+}
+
 // ---- command buffers: vkAllocateCommandBuffers :4464, vkBeginCommandBuffer :4483, vkEndCommandBuffer :4491, ------------
 // ---- vkQueueSubmit :3414 (all unimplemented!() upstream) ---------------------------------------------------------------
 

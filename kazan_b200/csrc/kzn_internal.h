@@ -46,6 +46,12 @@ struct KznFence {
     bool pending;                // an event record has been enqueued
 };
 
+struct KznSemaphore {
+    KznDevice* device;
+    cudaEvent_t event;
+    bool signaled;  // a signal has been enqueued and not yet consumed by a wait
+};
+
 // error plumbing -----------------------------------------------------------------------------
 void kzn_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
 KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int line);

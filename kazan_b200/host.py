@@ -168,6 +168,21 @@ class Memory:
             self.handle = None
 
 
+class Semaphore:
+    """VkSemaphore (binary): orders work between two queues of one device."""
+
+    def __init__(self, device: Device):
+        self.device, self._lib = device, device._lib
+        h = C.c_void_p()
+        _check(self._lib.kzn_semaphore_create(device.handle, C.byref(h)))
+        self.handle = h
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_semaphore_destroy(self.handle)
+            self.handle = None
+
+
 class Fence:
     def __init__(self, device: Device, handle):
         self.device, self.handle, self._lib = device, handle, device._lib
@@ -253,6 +268,15 @@ class Queue:
         if code != 0:
             raise KazanError(code, self._lib.kzn_last_error().decode())
         return ms.value
+
+    def signal_semaphore(self, semaphore: "Semaphore"):
+        _check(self._lib.kzn_queue_signal_semaphore(self.handle, semaphore.handle))
+
+    def wait_semaphore(self, semaphore: "Semaphore"):
+        _check(self._lib.kzn_queue_wait_semaphore(self.handle, semaphore.handle))
+
+    def copy_dma(self, dst_address: int, src_address: int, size: int):
+        _check(self._lib.kzn_queue_copy_dma(self.handle, dst_address, src_address, size))
 
     def cmd_signal_flag(self, flag_address: int, add: int = 1):
         _check(self._lib.kzn_cmd_signal_flag(self.handle, flag_address, add))

@@ -80,12 +80,18 @@ class SplitFrame:
 
 
 class PeerSplitFrame:
-    """Split frame whose render targets live on the presenting GPU and are written by every rank over NVLink peer memory.
+    """Split frame whose render targets live on the presenting GPU and are filled by every rank over NVLink peer memory.
 
     The presenter allocates the colour targets and one flag block and exports them (kzn_memory_export); the other ranks
-    import them (kzn_memory_import) and bind the imported image as their colour attachment, so the raster kernels' tile
-    epilogue stores the band directly into the presenter's HBM.  Per frame:
-        band rank : [wait credit] -> draw band -> signal `arrived` (+1, after a system-scope fence)
+    import them (kzn_memory_import).  Two ways to move a band (`mode`):
+      "push"  (default) the band rank renders into a local image and its COPY QUEUE pushes the band into the presenter's
+              image with the copy engines (kzn_queue_copy_dma) while the SMs already render the next frame; semaphores
+              order the two queues, two local images rotate.  No SM time is spent on the transfer.
+      "store" the band rank binds the imported image as its colour attachment, so the raster kernels' tile epilogue stores
+              the band directly into the presenter's HBM (no copy at all).  Best at 2 GPUs; with more writers the remote
+              stores back-pressure the raster kernels (measured: profiles/).
+    Per frame:
+        band rank : [wait credit] -> draw band -> (push) -> signal `arrived` (+1, after a system-scope fence)
         presenter : draw own band -> wait `arrived` >= (world-1) * frames -> frame complete -> signal each rank's `credit`
     `credit` bounds how far a band rank may run ahead of the presenter (the number of rotating targets), so a target is
     never overwritten before the presenter has seen the frame that used it.  No collective is on the data path;
@@ -93,10 +99,15 @@ class PeerSplitFrame:
     """
 
     FLAG_BYTES = 256
+    LOCAL_IMAGES = 2
 
-    def __init__(self, device, queue, width: int, height: int, world: int, rank: int, dist, n_targets: int = 2, presenter: int = 0):
+    def __init__(self, device, queue, width: int, height: int, world: int, rank: int, dist, n_targets: int = 2, presenter: int = 0,
+                 mode: str = "push"):
+        from .host import Semaphore
+        if mode not in ("push", "store"):
+            raise ValueError(mode)
         self.split = SplitFrame(width, height, world, rank, presenter)
-        self.device, self.queue, self.dist = device, queue, dist
+        self.device, self.queue, self.dist, self.mode = device, queue, dist, mode
         self.world, self.rank, self.presenter, self.n_targets = world, rank, presenter, n_targets
         self.frame_bytes = width * height * 4
         self.frames = 0
@@ -106,13 +117,21 @@ class PeerSplitFrame:
         self.flags = device.allocate(self.FLAG_BYTES)
         self._owned.append(self.flags)
         queue.cmd_fill_buffer(self.flags.address, self.FLAG_BYTES, 0, self.FLAG_BYTES, 0)
+        self.targets = []
         if is_presenter:
             self.targets = [device.allocate(self.frame_bytes) for _ in range(n_targets)]
             self._owned += self.targets
             for t in self.targets:
                 queue.cmd_fill_buffer(t.address, self.frame_bytes, 0, self.frame_bytes, 0)
+        self.copy_queue, self.local, self.rendered, self.copied = None, [], [], []
+        if not is_presenter and mode == "push":
+            self.copy_queue = device.create_queue()
+            self.local = [device.allocate(self.frame_bytes) for _ in range(self.LOCAL_IMAGES)]
+            self._owned += self.local
+            self.rendered = [Semaphore(device) for _ in range(self.LOCAL_IMAGES)]
+            self.copied = [Semaphore(device) for _ in range(self.LOCAL_IMAGES)]
         queue.wait_idle()
-        mine = {"flags": self.flags.export(), "targets": [t.export() for t in self.targets] if is_presenter else []}
+        mine = {"flags": self.flags.export(), "targets": [t.export() for t in self.targets]}
         if world > 1:
             everyone = [None] * world
             dist.all_gather_object(everyone, mine)
@@ -140,39 +159,72 @@ class PeerSplitFrame:
         if world > 1:
             dist.barrier()
 
+    @property
+    def pushes(self) -> bool:
+        return self.copy_queue is not None
+
+    def render_addresses(self) -> list[int]:
+        """Every address begin_frame() can return on this rank (to prepare framebuffer descriptions once)."""
+        return [m.address for m in self.local] if self.pushes else list(self.target_addresses)
+
     def target(self, frame: int | None = None) -> int:
-        """Address, in THIS rank's address space, of the colour target used by frame number `frame` (default: the next one)."""
+        """Address, in THIS rank's address space, of the presenter's colour target used by frame number `frame`."""
         return self.target_addresses[(self.frames if frame is None else frame) % self.n_targets]
 
-    def begin_frame(self):
-        """Band ranks: do not start frame f before the presenter has completed frame f - n_targets."""
-        if self.rank != self.presenter and self.frames >= self.n_targets:
-            self.queue.cmd_wait_flag(self.flags.address, self.frames - self.n_targets + 1, self.status_address)
+    def begin_frame(self) -> int:
+        """Returns the address of the image this rank renders the next frame's band into."""
+        f = self.frames
+        if self.pushes:
+            slot = f % self.LOCAL_IMAGES
+            if f >= self.LOCAL_IMAGES:
+                self.queue.wait_semaphore(self.copied[slot])  # the push of frame f - 2 has left this image
+            return self.local[slot].address
+        if self.rank != self.presenter and f >= self.n_targets:
+            # do not start frame f before the presenter has completed frame f - n_targets
+            self.queue.cmd_wait_flag(self.flags.address, f - self.n_targets + 1, self.status_address)
+        return self.target(f)
 
     def end_frame(self):
         """After the band's draws were enqueued: publish the band / collect all bands."""
+        f = self.frames
         self.frames += 1
         if self.world == 1:
             return
-        if self.rank != self.presenter:
-            self.queue.cmd_signal_flag(self.arrived_address, 1)
-        else:
+        if self.rank == self.presenter:
             self.queue.cmd_wait_flag(self.arrived_address, (self.world - 1) * self.frames, self.status_address)
             for addr in self.credit_addresses.values():
                 self.queue.cmd_signal_flag(addr, 1)
+        elif self.pushes:
+            slot = f % self.LOCAL_IMAGES
+            a, b = self.split.byte_range(self.rank)
+            cq = self.copy_queue
+            self.queue.signal_semaphore(self.rendered[slot])
+            cq.wait_semaphore(self.rendered[slot])
+            if f >= self.n_targets:
+                cq.cmd_wait_flag(self.flags.address, f - self.n_targets + 1, self.status_address)
+            cq.copy_dma(self.target(f) + a, self.local[slot].address + a, b - a)
+            cq.cmd_signal_flag(self.arrived_address, 1)
+            cq.signal_semaphore(self.copied[slot])
+        else:
+            self.queue.cmd_signal_flag(self.arrived_address, 1)
+
+    def wait_idle(self):
+        self.queue.wait_idle()
+        if self.copy_queue:
+            self.copy_queue.wait_idle()
 
     def check(self):
         """Raise if any wait on this rank gave up (a peer stopped making progress)."""
         import ctypes as C
         word = (C.c_uint32 * 1)()
-        self.queue.wait_idle()
+        self.wait_idle()
         self.queue.download(C.addressof(word), self.status_address, 4)
         self.queue.wait_idle()
         if word[0]:
             raise RuntimeError(f"rank {self.rank}: a split-frame flag wait timed out")
 
     def close(self):
-        self.queue.wait_idle()
+        self.wait_idle()
         if self.world > 1:
             self.dist.barrier()  # nobody frees memory a peer may still be writing
         for m in self._imported:
@@ -181,4 +233,8 @@ class PeerSplitFrame:
             self.dist.barrier()
         for m in self._owned:
             m.free()
-        self._imported, self._owned = [], []
+        for sem in self.rendered + self.copied:
+            sem.destroy()
+        if self.copy_queue:
+            self.copy_queue.destroy()
+        self._imported, self._owned, self.rendered, self.copied, self.copy_queue = [], [], [], [], None

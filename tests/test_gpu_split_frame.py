@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch.multiprocessing as mp
 
+from kazan_b200 import host
+
 pytestmark = pytest.mark.gpu
 
 
@@ -20,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, result):
+def _worker(rank, world, port, mode, result):
     import ctypes as C
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -33,7 +35,7 @@ def _worker(rank, world, port, result):
         W, H, frames = 256, 144, 5
         dev = host.Device(0)
         q = dev.create_queue()
-        pf = PeerSplitFrame(dev, q, W, H, world, rank, dist, n_targets=2)
+        pf = PeerSplitFrame(dev, q, W, H, world, rank, dist, n_targets=2, mode=mode)
         verts = dev.allocate(FULLSCREEN_TRIANGLE.nbytes)
         q.upload(verts.address, FULLSCREEN_TRIANGLE.ctypes.data, FULLSCREEN_TRIANGLE.nbytes)
         st = pipeline_state(fs=abi.FS_PROCEDURAL_ORBIT)
@@ -42,9 +44,8 @@ def _worker(rank, world, port, result):
         vi = abi.VertexInput(verts.address, FULLSCREEN_TRIANGLE.nbytes, 28, 0, 3, 12)
         for f in range(frames):  # more frames than targets: exercises the credit back-pressure
             fb = abi.Framebuffer()
-            fb.color = abi.ImageDesc(pf.target(), abi.FORMAT_R8G8B8A8_UNORM, 0, W, H, 1, 1, 1, 0)
+            fb.color = abi.ImageDesc(pf.begin_frame(), abi.FORMAT_R8G8B8A8_UNORM, 0, W, H, 1, 1, 1, 0)
             fb.band_y0, fb.band_y1 = pf.split.band
-            pf.begin_frame()
             q.cmd_draw(st, fb, vp, sc, vi, 3)
             pf.end_frame()
         pf.check()
@@ -64,17 +65,39 @@ def _worker(rank, world, port, result):
         dist.destroy_process_group()
 
 
-def test_two_ranks_render_bands_into_the_presenters_image():
+@pytest.mark.parametrize("mode", ["push", "store"])
+def test_two_ranks_render_bands_into_the_presenters_image(mode):
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, result)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, result)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(180)
         assert p.exitcode == 0
     assert result.get(timeout=10) is True
+
+
+def test_semaphore_orders_two_queues(gpu):
+    """vkQueueSubmit semaphores: the second queue's copy starts only after the first queue's fill has finished."""
+    from kazan_b200.host import Semaphore
+    n = 64 << 20
+    a, b = gpu.device.allocate(n), gpu.device.allocate(n)
+    q2 = gpu.device.create_queue()
+    sem = Semaphore(gpu.device)
+    with pytest.raises(host.KazanError):
+        q2.wait_semaphore(sem)  # no signal pending
+    gpu.queue.cmd_fill_buffer(a.address, n, 0, n, 0x01020304)
+    gpu.queue.signal_semaphore(sem)
+    q2.wait_semaphore(sem)
+    q2.copy_dma(b.address, a.address, n)
+    q2.wait_idle()
+    out = np.empty(n // 4, dtype=np.uint32)
+    q2.download(out.ctypes.data, b.address, n)
+    q2.wait_idle()
+    assert (out == 0x01020304).all()
+    sem.destroy(); q2.destroy(); a.free(); b.free()
 
 
 def test_flags_order_work_on_one_queue(gpu):
