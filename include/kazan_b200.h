@@ -239,6 +239,17 @@ KZN_API KznResult kzn_cmd_wait_flag(KznQueue* queue, uint64_t flag_address, uint
  * to the presenting GPU while the SMs already render the next frame */
 KZN_API KznResult kzn_queue_copy_dma(KznQueue* queue, uint64_t dst_address, uint64_t src_address, uint64_t size);
 
+/* Measured fp32 issue rate of the device (tera lane-operations per second, an fma counting once): independent packed
+ * fma.rn.f32x2 chains and nothing else.  The denominator of the shader-bound roofline. */
+KZN_API KznResult kzn_calibrate_fp32_issue(KznQueue* queue, float* tera_lane_ops_per_second);
+
+/* vkCmdPipelineBarrier api_impl.rs:4863 (unimplemented!() upstream).  A queue is one in-order CUDA stream: every command
+ * already executes after all earlier commands of the queue have completed and made their writes visible, so execution
+ * and memory barriers need no device work; the entry point exists so that a host can forward the call (and it is
+ * recorded as nothing inside a command buffer).  Image layout transitions between LINEAR and TILED images are explicit:
+ * kzn_cmd_convert_tiling. */
+KZN_API KznResult kzn_cmd_pipeline_barrier(KznQueue* queue);
+
 /* plain transfers between host memory and device addresses on the queue (used by the ICD for
  * HOST_COHERENT emulation and by the end-to-end benchmark); host memory should be pinned */
 KZN_API KznResult kzn_queue_upload(KznQueue* queue, uint64_t dst_address, const void* src, uint64_t size);
@@ -328,8 +339,8 @@ KZN_API KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* sr
 /* vkCreateGraphicsPipelines :4018 -> GraphicsPipeline::create pipeline.rs:167-183 (all stubs)  */
 
 /* Shader stages.  The reference cannot translate any shader with a body, so the
- * programmable stages are selected from built-in programs defined by the oracle (oracle/raster.c);
- * KZN_FS_IR runs a fragment entry point compiled by the PTX backend (kazan_b200_backend.h). */
+ * programmable stages are selected from built-in programs defined by the oracle (oracle/raster.c).  Compute entry
+ * points go through the PTX back end (kazan_b200_backend.h). */
 #define KZN_VS_PASSTHROUGH 0u      /* gl_Position = vec4(pos.xyz, pos.w or 1); colour passed through */
 #define KZN_FS_VERTEX_COLOR 0u     /* out = perspective-correct interpolated vertex rgba */
 #define KZN_FS_PROCEDURAL_ORBIT 1u /* the fill-rate shader of BASELINE.json configs[2] (fp32 fma orbit, K=32) */

@@ -211,6 +211,8 @@ PROTOTYPES = {
     "kzn_queue_signal_semaphore": (i32, [vp, vp]),
     "kzn_queue_wait_semaphore": (i32, [vp, vp]),
     "kzn_queue_copy_dma": (i32, [vp, u64, u64, u64]),
+    "kzn_calibrate_fp32_issue": (i32, [vp, P(f32)]),
+    "kzn_cmd_pipeline_barrier": (i32, [vp]),
     "kzn_fence_create": (i32, [vp, i32, P(vp)]),
     "kzn_fence_destroy": (None, [vp]),
     "kzn_fence_reset": (i32, [vp]),

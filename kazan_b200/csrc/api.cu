@@ -421,6 +421,11 @@ KznResult kzn_image_memory_requirements(const KznImageDesc* image, uint64_t* siz
     return KZN_SUCCESS;
 }
 
+KznResult kzn_cmd_pipeline_barrier(KznQueue* queue) {
+    // in-order stream: nothing to enqueue (see the header)
+    return kzn_queue_enter(queue);
+}
+
 // ---- semaphores ------------------------------------------------------------------------------------------------
 
 KznResult kzn_semaphore_create(KznDevice* device, KznSemaphore** semaphore) {

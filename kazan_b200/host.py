@@ -275,6 +275,15 @@ class Queue:
     def wait_semaphore(self, semaphore: "Semaphore"):
         _check(self._lib.kzn_queue_wait_semaphore(self.handle, semaphore.handle))
 
+    def calibrate_fp32_issue(self) -> float:
+        """Measured fp32 issue rate, tera lane-operations per second."""
+        v = abi.f32()
+        _check(self._lib.kzn_calibrate_fp32_issue(self.handle, C.byref(v)))
+        return v.value
+
+    def cmd_pipeline_barrier(self):
+        _check(self._lib.kzn_cmd_pipeline_barrier(self.handle))
+
     def copy_dma(self, dst_address: int, src_address: int, size: int):
         _check(self._lib.kzn_queue_copy_dma(self.handle, dst_address, src_address, size))
 
