@@ -31,7 +31,15 @@ constexpr int kPx = 4;                   // horizontally adjacent pixels per thr
 constexpr int kTileW = 32 * kPx, kTileH = 8;  // pixels per raster tile: one warp per row -> 512 B row stores
 constexpr int kRasterThreads = 32 * kTileH;
 constexpr int kDirectPx = 8;                   // raster_direct_kernel: pixels per lane (two 16-byte vectors)
-constexpr int kDirectTileW = 32 * kDirectPx;   // its tiles are 256x8 pixels
+constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels wide ...
+#ifndef KZN_DIRECT_ROWS
+#define KZN_DIRECT_ROWS 4
+#endif
+#ifndef KZN_DIRECT_WARPS
+#define KZN_DIRECT_WARPS 20
+#endif
+constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows high
+constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
 constexpr int kRecs = 128;               // triangle records staged in shared memory per round
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
@@ -81,6 +89,7 @@ struct DrawParams {
     uint32_t tiles_x, tiles_y, tile_x0, tile_y0;  // tile grid covering the clip rectangle
     uint32_t binned;                               // 0 => every tile walks all triangles
     unsigned long long* stats;                     // KznDrawStatistics or null
+    uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
 };
 
 // ---- setup ------------------------------------------------------------------------------------------------
@@ -179,6 +188,7 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
 
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
     const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
+    if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
     const bool in_range = t_raw < p.tris_per_instance;
     const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
     TriRec r;
@@ -632,22 +642,34 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
 
 // PX interleaved orbits as PX/2 packed pairs: fma.rn.f32x2 / add.rn.f32x2 (FFMA2 / FADD2) do two IEEE fp32 operations per
 // instruction with per-lane results identical to the scalar instructions, so the shader is still the oracle's sequence.
+// orbit_cx: the row-independent part (c.x of the PX pixels), hoisted out of row loops by the direct kernel.
 template <int PX>
-__device__ __forceinline__ void fs_procedural_orbit_n(int px0, int py, float inv_w, float inv_h, float rgba[PX][4]) {
+__device__ __forceinline__ void orbit_cx(int px0, float inv_w, float2 cx[PX / 2]) {
     static_assert(PX % 2 == 0, "packed pairs");
-    float2 cx[PX / 2], zx[PX / 2], zy[PX / 2];
+    const float base = (float)px0;  // px0 + k + 0.5 is exact in fp32 (|px| < 2^22): same value as (float)(px0 + k) + 0.5f
+#pragma unroll
+    for (int k = 0; k < PX / 2; ++k) {
+        const float u0 = (base + ((float)(2 * k) + 0.5f)) * inv_w, u1 = (base + ((float)(2 * k + 1) + 0.5f)) * inv_w;
+        cx[k] = make_float2(fmaf(u0, 3.5f, -2.5f), fmaf(u1, 3.5f, -2.5f));
+    }
+}
+
+template <int PX>
+__device__ __forceinline__ void fs_procedural_orbit_n(const float2 cx[PX / 2], int py, float inv_h, float rgba[PX][4]) {
+    float2 zx[PX / 2], zy[PX / 2];
     const float v = ((float)py + 0.5f) * inv_h;
     const float cys = fmaf(v, 2.0f, -1.0f);
     const float2 cy = make_float2(cys, cys);
+    // Iteration 1 from z = (+0, +0) is the identity z <- c: fma(0,0,cx) = cx, fma(-0,0,cx) = cx, fma(0+0,0,cy) = cy, exactly,
+    // because cx and cy are fma results and an exact-zero fma result is +0 under round-to-nearest (never -0).  So the
+    // chains start at z = c and run the remaining ITERATIONS-1 steps: bit-identical to the oracle's loop.
 #pragma unroll
     for (int k = 0; k < PX / 2; ++k) {
-        const float u0 = ((float)(px0 + 2 * k) + 0.5f) * inv_w, u1 = ((float)(px0 + 2 * k + 1) + 0.5f) * inv_w;
-        cx[k] = make_float2(fmaf(u0, 3.5f, -2.5f), fmaf(u1, 3.5f, -2.5f));
-        zx[k] = make_float2(0.0f, 0.0f);
-        zy[k] = make_float2(0.0f, 0.0f);
+        zx[k] = cx[k];
+        zy[k] = cy;
     }
-#pragma unroll 8
-    for (uint32_t it = 0; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
+#pragma unroll
+    for (uint32_t it = 1; it < KZN_FS_ORBIT_ITERATIONS; ++it) {
 #pragma unroll
         for (int k = 0; k < PX / 2; ++k) {
             const float2 t = __ffma2_rn(zx[k], zx[k], cx[k]);
@@ -668,6 +690,13 @@ __device__ __forceinline__ void fs_procedural_orbit_n(int px0, int py, float inv
     }
 }
 
+template <int PX>
+__device__ __forceinline__ void fs_procedural_orbit_n(int px0, int py, float inv_w, float inv_h, float rgba[PX][4]) {
+    float2 cx[PX / 2];
+    orbit_cx<PX>(px0, inv_w, cx);
+    fs_procedural_orbit_n<PX>(cx, py, inv_h, rgba);
+}
+
 // bits k of the pixel group px0..px0+PX-1 whose pixel lies in [xa, xb]
 template <int PX>
 __device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
@@ -683,7 +712,8 @@ __device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
 template <uint32_t FS, int NEED_DST, int PX>
 __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, const float* lut, int px0, int py, int32_t sy, int xa, int xb,
                                           bool depth_test, bool depth_write, bool has_color, uint32_t col[PX], float depth[PX],
-                                          uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed) {
+                                          uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed,
+                                          const float2* orbit_cx_pre = nullptr) {
     const uint32_t bias = t.bias_bits;
     live = 0;
     zwrite = 0;
@@ -738,7 +768,8 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     if (live) {
         float src[PX][4];
         if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-            fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
+            if (orbit_cx_pre) fs_procedural_orbit_n<PX>(orbit_cx_pre, py, p.inv_fb_h, src);
+            else fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
         } else {
 #pragma unroll
             for (int k = 0; k < PX; ++k) {
@@ -749,8 +780,10 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             }
         }
 #pragma unroll
-        for (int k = 0; k < PX; ++k)
-            if (live >> k & 1u) col[k] = output_merge_lut<NEED_DST>(p.st, lut, src[k], col[k]);  // pixels not live keep their value
+        for (int k = 0; k < PX; ++k) {  // branch-free: pixels not live keep their value
+            const uint32_t merged = output_merge_lut<NEED_DST>(p.st, lut, src[k], col[k]);
+            col[k] = (live >> k & 1u) ? merged : col[k];
+        }
     }
 }
 
@@ -784,101 +817,171 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
 }
 
 // Draws of a few triangles (total <= kDirectMax: fullscreen passes, quads, UI): no binning, no staging, no fragment queue.
-// One CTA per 128x8 tile, warp w = row w, lane l = pixels 4l..4l+3; the lane keeps its 4 colour and depth values in
-// REGISTERS while it walks the triangle records in primitive order (uniform loads: every lane reads the same record),
-// so per-pixel fragment order is the primitive order by construction and the tile needs no shared memory beyond the
-// UNORM8 table.  Rows and tiles a triangle's bounding box misses are rejected on the 16-byte bbox alone.
+// Persistent one-warp CTAs (kDirectWarpsPerSM per SM).  A warp takes *blocks* of 256 x kDirectRows pixels from a global
+// work counter (zeroed by setup_kernel) until none are left, so all SM sub-partitions stay busy to the end whatever the
+// frame size — with a static grid the last wave of equal-cost blocks lands on a subset of the SMs.  Blocks are numbered
+// column-major, so a warp mostly stays in one 256-pixel column and everything that depends on the column only (clip masks,
+// the c.x of the fill-rate shader) is recomputed only when the column changes.  Within a block the warp walks its rows one
+// after the other, lane l = pixels 8l..8l+7 of the row, colour and depth of the row held in REGISTERS while the lane walks
+// the triangle records in primitive order (uniform loads: every lane reads the same record) — per-pixel fragment order is
+// the primitive order by construction and nothing is shared between warps but the UNORM8 table.
+// *Block-level trivial accept*: lane i tests triangle i (the first 32) at the corner of the block where each edge function
+// is smallest; if all three are positive the whole block is inside the triangle and its rows skip coverage entirely.
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(const __grid_constant__ DrawParams p) {
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kDirectTileW;
-    const int py = (int)(p.tile_y0 + blockIdx.y) * kTileH + (int)warp;
-    const int px0 = tile_px0 + (int)lane * kDirectPx;
+    const uint32_t lane = threadIdx.x;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
     if (NEED_DST) {
-        unorm_lut[threadIdx.x] = unorm8_to_float(threadIdx.x);
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) unorm_lut[lane + 32 * i] = unorm8_to_float(lane + 32 * i);
+        __syncwarp();
     }
-    if (py < p.cy0 || py > p.cy1) return;  // whole warp
-    const uint32_t quad_clip = quad_mask<kDirectPx>(px0, p.cx0, p.cx1);  // pixels of my quad inside the clip rectangle
-    const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kDirectPx <= (int)p.fb_w;
-    const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
-    unsigned long long caddr = 0, daddr = 0;
+    const uint32_t n_blocks = p.tiles_x * p.tiles_y;
+    const unsigned long long pitch = (unsigned long long)p.fb_w * 4ull;
+    uint32_t n_covered = 0, n_passed = 0;
+    int cur_col = -1, tile_px0 = 0, px0 = 0;
+    uint32_t quad_clip = 0;
+    bool cvec = false, dvec = false;
+    float2 cxp[kDirectPx / 2];
     uint32_t col[kDirectPx];
     float depth[kDirectPx];
 #pragma unroll
-    for (int k = 0; k < kDirectPx; ++k) {
+    for (int k = 0; k < kDirectPx; ++k) {  // values of pixels that are never live are never stored either
         col[k] = 0u;
         depth[k] = 0.f;
     }
-    if (quad_clip) {
-        if (has_color) caddr = color_addr(p, px0, py);
-        if (has_depth) daddr = p.depth_base + ((unsigned long long)py * p.fb_w + px0) * 4ull;
-        if (NEED_DST && has_color) {
 #pragma unroll
-            for (int h = 0; h < kDirectPx / 4; ++h) {  // 16-byte vectors where the whole group of 4 is inside
-                const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
-                if (m4 == 15u && cvec) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(caddr + 16 * h);
-                    col[4 * h] = q.x; col[4 * h + 1] = q.y; col[4 * h + 2] = q.z; col[4 * h + 3] = q.w;
-                } else {
+    for (int k = 0; k < kDirectPx / 2; ++k) cxp[k] = make_float2(0.f, 0.f);
+
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(p.work_counter, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_blocks) break;
+        const int bcol = (int)(u / p.tiles_y), brow = (int)(u - (uint32_t)bcol * p.tiles_y);
+        if (bcol != cur_col) {  // per-column state
+            cur_col = bcol;
+            tile_px0 = (int)(p.tile_x0 + (uint32_t)bcol) * kDirectTileW;
+            px0 = tile_px0 + (int)lane * kDirectPx;
+            quad_clip = quad_mask<kDirectPx>(px0, p.cx0, p.cx1);  // pixels of my group inside the clip rectangle
+            const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kDirectPx <= (int)p.fb_w;
+            cvec = vec_ok && (p.color_base & 15ull) == 0;
+            dvec = vec_ok && (p.depth_base & 15ull) == 0;
+            if (FS == KZN_FS_PROCEDURAL_ORBIT) orbit_cx<kDirectPx>(px0, p.inv_fb_w, cxp);
+        }
+        const int row0 = (int)(p.tile_y0 + (uint32_t)brow) * kDirectRows;
+        uint32_t full = 0;  // bit i: triangle i covers every pixel centre of this block (and needs no per-fragment work)
+        if (FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test) {
+            bool ok = false;
+            if (lane < p.total_tris) {
+                const TriRec& t = p.tris[lane];
+                const uint32_t bias = t.bias_bits;
+                ok = t.minx <= t.maxx && (bias & 8u);  // produces fragments; the depth clip cannot reject (setup)
+                const int32_t sx_lo = 16 * tile_px0 + 8, sx_hi = 16 * (tile_px0 + kDirectTileW - 1) + 8;
+                const int32_t sy_lo = 16 * row0 + 8, sy_hi = 16 * (row0 + kDirectRows - 1) + 8;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (m4 >> k & 1u) col[4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
+                for (int e = 0; e < 3; ++e) {  // the edge function is linear: its minimum over the block is at one corner
+                    const int32_t a = t.a[e], b = t.b[e];
+                    const long long v = (long long)a * (a >= 0 ? sx_lo : sx_hi) + (long long)b * (b >= 0 ? sy_lo : sy_hi) + t.c[e] +
+                                        (long long)((bias >> e) & 1u);
+                    ok = ok && v > 0;
                 }
             }
+            full = __ballot_sync(0xffffffffu, ok);
         }
-        if (depth_test) {
+        const int r_lo = max(row0, p.cy0), r_hi = min(row0 + kDirectRows - 1, p.cy1);
+        unsigned long long caddr = 0, daddr = 0;
+        if (has_color) caddr = p.color_tiled ? 0ull : p.color_base + ((unsigned long long)r_lo * p.fb_w + px0) * 4ull;
+        if (has_depth) daddr = p.depth_base + ((unsigned long long)r_lo * p.fb_w + px0) * 4ull;
+#pragma unroll 1
+        for (int py = r_lo; py <= r_hi; ++py, caddr += pitch, daddr += pitch) {
+            if (has_color && p.color_tiled) caddr = color_addr(p, px0, py);
+            if (quad_clip) {
+                if (NEED_DST && has_color) {
+#pragma unroll
+                    for (int h = 0; h < kDirectPx / 4; ++h) {  // 16-byte vectors where the whole group of 4 is inside
+                        const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
+                        if (m4 == 15u && cvec) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(caddr + 16 * h);
+                            col[4 * h] = q.x; col[4 * h + 1] = q.y; col[4 * h + 2] = q.z; col[4 * h + 3] = q.w;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (m4 >> k & 1u) col[4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
+                        }
+                    }
+                }
+                if (depth_test) {
+#pragma unroll
+                    for (int h = 0; h < kDirectPx / 4; ++h) {
+                        const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
+                        if (m4 == 15u && dvec) {
+                            const float4 q = *reinterpret_cast<const float4*>(daddr + 16 * h);
+                            depth[4 * h] = q.x; depth[4 * h + 1] = q.y; depth[4 * h + 2] = q.z; depth[4 * h + 3] = q.w;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (m4 >> k & 1u) depth[4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
+                        }
+                    }
+                }
+            }
+            const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
+            uint32_t cdirty = 0, zdirty = 0;
+            for (uint32_t i = 0; i < p.total_tris; ++i) {
+                if (FS == KZN_FS_PROCEDURAL_ORBIT && i < 32u && (full >> i & 1u)) {  // warp-uniform
+                    // block-level trivial accept: every pixel of the row inside the clip rectangle is covered and passes
+                    n_covered += __popc(quad_clip);
+                    n_passed += __popc(quad_clip);
+                    if (has_color && quad_clip) {
+                        float src[kDirectPx][4];
+                        fs_procedural_orbit_n<kDirectPx>(cxp, py, p.inv_fb_h, src);
+#pragma unroll
+                        for (int k = 0; k < kDirectPx; ++k) {
+                            const uint32_t merged = output_merge_lut<NEED_DST>(p.st, unorm_lut, src[k], col[k]);
+                            // without a destination read the pixels outside the clip mask are never stored: no select needed
+                            col[k] = (NEED_DST == kDstNone || (quad_clip >> k & 1u)) ? merged : col[k];
+                        }
+                        cdirty |= quad_clip;
+                    }
+                    continue;
+                }
+                const TriRec& t = p.tris[i];
+                const int4 bb = __ldg(reinterpret_cast<const int4*>(&t));  // minx maxx miny maxy, already scissored
+                if (bb.x > bb.y || py < bb.z || py > bb.w) continue;
+                const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kDirectTileW - 1);
+                if (xa > xb) continue;
+                uint32_t live, zwrite;
+                span_quad<FS, NEED_DST, kDirectPx>(p, t, unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live,
+                                                   zwrite, n_covered, n_passed, FS == KZN_FS_PROCEDURAL_ORBIT ? cxp : nullptr);
+                cdirty |= live;
+                zdirty |= zwrite;
+            }
+            cdirty &= quad_clip;
+            zdirty &= quad_clip;
 #pragma unroll
             for (int h = 0; h < kDirectPx / 4; ++h) {
-                const uint32_t m4 = (quad_clip >> (4 * h)) & 15u;
-                if (m4 == 15u && dvec) {
-                    const float4 q = *reinterpret_cast<const float4*>(daddr + 16 * h);
-                    depth[4 * h] = q.x; depth[4 * h + 1] = q.y; depth[4 * h + 2] = q.z; depth[4 * h + 3] = q.w;
-                } else {
+                const uint32_t c4 = (cdirty >> (4 * h)) & 15u, z4 = (zdirty >> (4 * h)) & 15u;
+                if (c4 == 15u && cvec) {
+                    *reinterpret_cast<uint4*>(caddr + 16 * h) = make_uint4(col[4 * h], col[4 * h + 1], col[4 * h + 2], col[4 * h + 3]);
+                } else if (c4) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (m4 >> k & 1u) depth[4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
+                        if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = col[4 * h + k];
+                }
+                if (z4 == 15u && dvec) {
+                    *reinterpret_cast<float4*>(daddr + 16 * h) = make_float4(depth[4 * h], depth[4 * h + 1], depth[4 * h + 2], depth[4 * h + 3]);
+                } else if (z4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (z4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = depth[4 * h + k];
                 }
             }
         }
-    }
-    const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
-    uint32_t cdirty = 0, zdirty = 0, n_covered = 0, n_passed = 0;
-    for (uint32_t i = 0; i < p.total_tris; ++i) {
-        const TriRec& t = p.tris[i];
-        const int4 bb = __ldg(reinterpret_cast<const int4*>(&t));  // minx maxx miny maxy, already scissored
-        if (bb.x > bb.y || py < bb.z || py > bb.w) continue;
-        const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kDirectTileW - 1);
-        if (xa > xb) continue;
-        uint32_t live, zwrite;
-        span_quad<FS, NEED_DST, kDirectPx>(p, t, unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
-                                n_passed);
-        cdirty |= live;
-        zdirty |= zwrite;
-    }
-    cdirty &= quad_clip;
-    zdirty &= quad_clip;
-#pragma unroll
-    for (int h = 0; h < kDirectPx / 4; ++h) {
-        const uint32_t c4 = (cdirty >> (4 * h)) & 15u, z4 = (zdirty >> (4 * h)) & 15u;
-        if (c4 == 15u && cvec) {
-            *reinterpret_cast<uint4*>(caddr + 16 * h) = make_uint4(col[4 * h], col[4 * h + 1], col[4 * h + 2], col[4 * h + 3]);
-        } else if (c4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = col[4 * h + k];
-        }
-        if (z4 == 15u && dvec) {
-            *reinterpret_cast<float4*>(daddr + 16 * h) = make_float4(depth[4 * h], depth[4 * h + 1], depth[4 * h + 2], depth[4 * h + 3]);
-        } else if (z4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (z4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = depth[4 * h + k];
-        }
+        if (p.stats && lane == 0) atomicAdd(&p.stats[6], 1ull);
     }
     if (p.stats) {
         for (int d = 16; d > 0; d >>= 1) {
@@ -890,7 +993,6 @@ __global__ void __launch_bounds__(kRasterThreads) raster_direct_kernel(const __g
             if (n_passed) atomicAdd(&p.stats[5], (unsigned long long)n_passed);
         }
     }
-    if (p.stats && threadIdx.x == 0) atomicAdd(&p.stats[6], 1ull);
 }
 
 // One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
@@ -1171,6 +1273,8 @@ struct KznRasterScratch {
     size_t tile_capacity = 0;
     uint32_t* bin_entries = nullptr;
     size_t bin_capacity = 0;
+    uint32_t* counters = nullptr;  // [4]: work counter of the direct kernel
+    size_t counter_capacity = 0;
     bool attrs_set = false;
 };
 
@@ -1179,6 +1283,7 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->tris);
     cudaFree(s->tile_words);
     cudaFree(s->bin_entries);
+    cudaFree(s->counters);
     delete s;
 }
 
@@ -1277,6 +1382,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     }
     KznRasterScratch* s = q->raster;
     if ((r = grow(q, &s->tris, &s->tri_capacity, total))) return r;
+    if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
     if (binned) {
         if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
         // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
@@ -1354,6 +1460,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     if ((r = ensure_scratch(q, (size_t)total, tiles, p.binned != 0))) return r;
     KznRasterScratch* s = q->raster;
     p.tris = s->tris;
+    p.work_counter = s->counters;
     if (p.binned) {
         p.tile_counts = s->tile_words;
         p.tile_cursor = s->tile_words + tiles;
@@ -1381,26 +1488,30 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
                             st->dst_alpha_blend_factor == 7 && st->alpha_blend_op == 0;
     const int mode = !need_dst ? kDstNone : alpha_over ? kDstAlphaOver : kDstGeneric;
     const bool orbit = st->fragment_program == KZN_FS_PROCEDURAL_ORBIT;
-#define KZN_RASTER_LAUNCH(KERNEL, SMEM)                                                                      \
+#define KZN_RASTER_LAUNCH(KERNEL, THREADS, SMEM)                                                                      \
     do {                                                                                                     \
         if (orbit) {                                                                                         \
-            if (mode == kDstNone) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstNone><<<grid, kRasterThreads, SMEM, q->stream>>>(p);             \
-            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver><<<grid, kRasterThreads, SMEM, q->stream>>>(p); \
-            else KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric><<<grid, kRasterThreads, SMEM, q->stream>>>(p);   \
+            if (mode == kDstNone) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstNone><<<grid, THREADS, SMEM, q->stream>>>(p);             \
+            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver><<<grid, THREADS, SMEM, q->stream>>>(p); \
+            else KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric><<<grid, THREADS, SMEM, q->stream>>>(p);   \
         } else {                                                                                             \
-            if (mode == kDstNone) KERNEL<KZN_FS_VERTEX_COLOR, kDstNone><<<grid, kRasterThreads, SMEM, q->stream>>>(p);                 \
-            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_VERTEX_COLOR, kDstAlphaOver><<<grid, kRasterThreads, SMEM, q->stream>>>(p);     \
-            else KERNEL<KZN_FS_VERTEX_COLOR, kDstGeneric><<<grid, kRasterThreads, SMEM, q->stream>>>(p);       \
+            if (mode == kDstNone) KERNEL<KZN_FS_VERTEX_COLOR, kDstNone><<<grid, THREADS, SMEM, q->stream>>>(p);                 \
+            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_VERTEX_COLOR, kDstAlphaOver><<<grid, THREADS, SMEM, q->stream>>>(p);     \
+            else KERNEL<KZN_FS_VERTEX_COLOR, kDstGeneric><<<grid, THREADS, SMEM, q->stream>>>(p);       \
         }                                                                                                    \
     } while (0)
-    if (!p.binned) {  // a few triangles: register-resident tiles, no staging; 256x8 tiles
+    if (!p.binned) {  // a few triangles: register-resident rows, no staging; one warp per 256 x kDirectRows block
         p.tile_x0 = (uint32_t)p.cx0 / kDirectTileW;
         p.tiles_x = (uint32_t)p.cx1 / kDirectTileW - p.tile_x0 + 1;
-        grid = dim3(p.tiles_x, p.tiles_y);
-        KZN_RASTER_LAUNCH(raster_direct_kernel, 0);
+        p.tile_y0 = (uint32_t)p.cy0 / kDirectRows;
+        p.tiles_y = (uint32_t)p.cy1 / kDirectRows - p.tile_y0 + 1;
+        const uint64_t blocks = (uint64_t)p.tiles_x * p.tiles_y, resident = (uint64_t)q->device->sm_count * kDirectWarpsPerSM;
+        KZN_REQUIRE(blocks <= 0xffffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer too large");
+        grid = dim3((uint32_t)(blocks < resident ? blocks : resident));
+        KZN_RASTER_LAUNCH(raster_direct_kernel, 32, 0);
         return kzn_launched(q, "raster_direct_kernel");
     }
-    KZN_RASTER_LAUNCH(raster_kernel, smem);
+    KZN_RASTER_LAUNCH(raster_kernel, kRasterThreads, smem);
 #undef KZN_RASTER_LAUNCH
     return kzn_launched(q, "raster_kernel");
 }
