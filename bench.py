@@ -167,6 +167,7 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
         with queue.record() as cb_copy:
             for k in range(batch):
                 queue.cmd_copy_buffer_to_image(buffers[k % n_img].data_ptr(), nbytes, imgs[k % n_img], region)
+        launches_per_submit = [cb_clear.launch_count, cb_copy.launch_count]  # disjoint commands merge (transfer.cu)
         sub = max(3, reps // batch)
         ms = time_region(torch, stream, lambda k: queue.submit([cb_clear]), sub, 2)
         gclear = nbytes * batch * sub / ms / 1e6
@@ -175,7 +176,7 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
         cb_clear.destroy(); cb_copy.destroy()
         out[label] = {"clear_submit_GBps": round(gclear, 1), "clear_submit_frac_hbm": round(gclear / hbm_peak, 3),
                       "copy_b2i_submit_GBps": round(gcopy, 1), "copy_b2i_submit_frac_hbm": round(gcopy / hbm_peak, 3),
-                      "commands_per_submit": batch,
+                      "commands_per_submit": batch, "launches_per_submit": launches_per_submit,
                       "clear_kernel_GBps": round(kc, 1), "copy_b2i_kernel_GBps": round(kb, 1),
                       "clear_GBps": round(clear, 1), "clear_frac_hbm": round(clear / hbm_peak, 3),
                       "copy_b2i_GBps": round(copy, 1), "copy_b2i_frac_hbm": round(copy / hbm_peak, 3),

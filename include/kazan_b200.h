@@ -246,7 +246,8 @@ KZN_API KznResult kzn_calibrate_fp32_issue(KznQueue* queue, float* tera_lane_ops
 /* vkCmdPipelineBarrier api_impl.rs:4863 (unimplemented!() upstream).  A queue is one in-order CUDA stream: every command
  * already executes after all earlier commands of the queue have completed and made their writes visible, so execution
  * and memory barriers need no device work; the entry point exists so that a host can forward the call (and it is
- * recorded as nothing inside a command buffer).  Image layout transitions between LINEAR and TILED images are explicit:
+ * recorded as nothing inside a command buffer, where it only ends the current batch of merged transfers — see the
+ * command buffer notes below).  Image layout transitions between LINEAR and TILED images are explicit:
  * kzn_cmd_convert_tiling. */
 KZN_API KznResult kzn_cmd_pipeline_barrier(KznQueue* queue);
 
@@ -261,7 +262,13 @@ KZN_API void kzn_host_free_pinned(void* ptr);
  * vkQueueSubmit :3414 (handle.rs:315 `CommandBuffer {}` is a placeholder upstream).
  * Between begin and end every kzn_cmd_* call on the queue is RECORDED (a CUDA graph captured from the queue's stream)
  * instead of executed; kzn_queue_submit replays recorded command buffers in order and then signals `fence` (may be NULL).
- * Replays cost one launch on the host whatever the number of commands.  Not recordable: waits on the host, fence
+ * Replays cost one launch on the host whatever the number of commands.  While recording, consecutive contiguous
+ * 16-byte-aligned fills and copies (whole-image clears, tightly packed buffer<->image copies, vkCmdFillBuffer,
+ * vkCmdCopyBuffer) whose address ranges are pairwise disjoint are merged into ONE kernel launch of up to 96 commands:
+ * Vulkan orders nothing between transfer commands without a barrier, and with disjoint ranges the result is the
+ * in-order result anyway.  A command that reads or overwrites a range the batch touches, any other command, or
+ * kzn_cmd_pipeline_barrier starts a new launch (KZN_MERGE_TRANSFERS=0 in the environment disables merging).
+ * Not recordable: waits on the host, fence
  * signalling, and anything that allocates — a draw recorded into a command buffer needs its raster scratch reserved
  * first with kzn_queue_reserve_draw (largest triangle count and framebuffer it will see). */
 typedef struct KznCommandBuffer KznCommandBuffer;

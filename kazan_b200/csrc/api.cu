@@ -169,10 +169,16 @@ KznResult kzn_memory_map(KznMemory* memory, uint64_t offset, void** host_ptr) {
 
 }  // extern "C"
 
-KznResult kzn_queue_enter(KznQueue* q) {
+KznResult kzn_queue_enter_transfer(KznQueue* q) {
     KZN_VALID(q && q->device, "null queue");
     KZN_CUDA(cudaSetDevice(q->device->ordinal));
     return KZN_SUCCESS;
+}
+
+KznResult kzn_queue_enter(KznQueue* q) {
+    KznResult r = kzn_queue_enter_transfer(q);
+    if (r) return r;
+    return q->n_pending ? kzn_flush_transfers(q) : KZN_SUCCESS;
 }
 
 const void* kzn_recorded_host_copy(KznQueue* q, const void* data, size_t size) {
@@ -218,6 +224,8 @@ static KznResult make_queue(KznDevice* device, cudaStream_t stream, bool owns, K
     q->timing = q->timing_armed = false;
     q->time_begin = q->time_end = nullptr;
     q->recording = nullptr;
+    q->n_pending = 0;
+    q->merged_commands = 0;
     *queue = q;
     return KZN_SUCCESS;
 }
@@ -553,6 +561,7 @@ void kzn_command_buffer_destroy(KznCommandBuffer* cb) {
         cudaStreamEndCapture(cb->queue->stream, &g);
         if (g) cudaGraphDestroy(g);
         cb->queue->recording = nullptr;
+        cb->queue->n_pending = 0;
         cb->queue->launches = cb->launches_at_begin;
         cudaGetLastError();
     }

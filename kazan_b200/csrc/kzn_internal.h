@@ -16,6 +16,15 @@ struct KznDevice {
 struct KznRasterScratch;  // raster.cu
 struct KznCommandBuffer;  // api.cu
 
+// Contiguous, 16-byte aligned fills and copies recorded back to back into a command buffer whose address ranges are
+// disjoint run as ONE launch (merged_transfer_kernel, transfer.cu): Vulkan orders nothing between transfer commands
+// that no barrier separates, and disjoint ranges make the merged result identical to in-order execution anyway.
+#define KZN_MAX_MERGED 96
+struct KznPendingTransfer {
+    uint64_t dst, src, bytes;  // src == 0: fill with `value`
+    uint32_t value;
+};
+
 struct KznQueue {
     KznDevice* device;
     cudaStream_t stream;
@@ -28,6 +37,9 @@ struct KznQueue {
     bool timing_armed;  // begin recorded, the next kzn_launched records the end
     cudaEvent_t time_begin, time_end;
     KznCommandBuffer* recording;  // non-null between kzn_command_buffer_begin and _end: kzn_cmd_* are captured, not run
+    KznPendingTransfer pending[KZN_MAX_MERGED];  // recorded, not yet captured (only while recording)
+    uint32_t n_pending;
+    uint64_t merged_commands;  // commands that went into a merged launch (statistics)
 };
 
 struct KznMemory {
@@ -72,8 +84,12 @@ KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int
 
 #define KZN_VALID(cond, ...) KZN_REQUIRE(cond, KZN_ERROR_VALIDATION_FAILED, __VA_ARGS__)
 
-// make the queue's device current and check the queue is usable
+// make the queue's device current and check the queue is usable; captures any pending merged transfers first
 KznResult kzn_queue_enter(KznQueue* q);
+// the same for the transfer commands themselves, which may join the pending batch instead of flushing it
+KznResult kzn_queue_enter_transfer(KznQueue* q);
+// capture the pending batch now (transfer.cu); no-op when nothing is pending
+KznResult kzn_flush_transfers(KznQueue* q);
 // call after every kernel launch: counts it and maps launch errors
 KznResult kzn_launched(KznQueue* q, const char* kernel);
 // call right before launching the kernel that dominates a command (no-op unless kernel timing is enabled)

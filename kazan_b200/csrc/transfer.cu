@@ -184,6 +184,59 @@ __global__ void __launch_bounds__(32) copy_bulk_kernel(uint8_t* __restrict__ dst
     bulk_wait_read<0>();
 }
 
+// ---- merged contiguous fills / copies (command buffers) ----------------------------------------------------
+
+// Up to KZN_MAX_MERGED recorded commands as one launch.  Work is cut into 16 KiB units numbered across the commands
+// (first_unit = prefix sum); CTA b takes units b, b + grid, ...; a unit is 4 x 16 bytes per thread, loads issued before
+// the stores.  Every address is 16-byte aligned and every length a multiple of 16 (checked at record time).
+constexpr uint32_t kUnitVecs = 1024;  // uint4 per unit
+struct MergedOps {
+    uint32_t n, total_units;
+    uint32_t first_unit[KZN_MAX_MERGED + 1];
+    uint32_t vecs[KZN_MAX_MERGED];   // length in uint4
+    uint32_t value[KZN_MAX_MERGED];  // fills
+    unsigned long long dst[KZN_MAX_MERGED];
+    unsigned long long src[KZN_MAX_MERGED];  // 0: fill
+};
+static_assert(sizeof(MergedOps) <= 4096, "kernel parameter space");
+
+__global__ void __launch_bounds__(kThreads) merged_transfer_kernel(const __grid_constant__ MergedOps m) {
+    for (uint32_t u = blockIdx.x; u < m.total_units; u += gridDim.x) {
+        uint32_t lo = 0, hi = m.n;  // the command this unit belongs to: last i with first_unit[i] <= u
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (m.first_unit[mid] <= u) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t v0 = (u - m.first_unit[lo]) * kUnitVecs;
+        const uint32_t cnt = min(kUnitVecs, m.vecs[lo] - v0);
+        uint4* d = reinterpret_cast<uint4*>(m.dst[lo]) + v0;
+        const unsigned long long src = m.src[lo];
+        if (src == 0) {
+            const uint32_t w = m.value[lo];
+            const uint4 v = make_uint4(w, w, w, w);
+#pragma unroll
+            for (uint32_t k = 0; k < kUnitVecs / kThreads; ++k) {
+                const uint32_t i = threadIdx.x + k * kThreads;
+                if (i < cnt) st_stream16(d + i, v);
+            }
+        } else {
+            const uint4* s = reinterpret_cast<const uint4*>(src) + v0;
+            uint4 v[kUnitVecs / kThreads];
+#pragma unroll
+            for (uint32_t k = 0; k < kUnitVecs / kThreads; ++k) {
+                const uint32_t i = threadIdx.x + k * kThreads;
+                if (i < cnt) v[k] = ld_stream16(s + i);
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kUnitVecs / kThreads; ++k) {
+                const uint32_t i = threadIdx.x + k * kThreads;
+                if (i < cnt) st_stream16(d + i, v[k]);
+            }
+        }
+    }
+}
+
 // ---- general box copy / fill ----------------------------------------------------------------------------
 
 struct Surf {
@@ -355,8 +408,45 @@ int grid_for(const KznQueue* q, unsigned long long items) {
     return blocks ? (int)blocks : 1;
 }
 
-KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint32_t value) {
+// ---- merging of recorded commands ---------------------------------------------------------------------------
+
+bool merge_enabled() {
+    static bool on = [] {
+        const char* e = getenv("KZN_MERGE_TRANSFERS");
+        return !(e && !strcmp(e, "0"));
+    }();
+    return on;
+}
+
+bool ranges_overlap(uint64_t a, uint64_t an, uint64_t b, uint64_t bn) { return a < b + bn && b < a + an; }
+
+KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint32_t value, bool may_merge = true);
+
+// Queue a contiguous fill (src == 0) or copy for the next merged launch.  false: the caller launches it itself.
+bool merge_transfer(KznQueue* q, uint64_t dst, uint64_t src, uint64_t bytes, uint32_t value, KznResult* result) {
+    *result = KZN_SUCCESS;
+    if (!q->recording || !merge_enabled()) return false;
+    if (dst % 16 || src % 16 || bytes % 16 || bytes == 0 || bytes > (64ull << 20)) return false;
+    bool conflict = q->n_pending == KZN_MAX_MERGED;
+    for (uint32_t i = 0; i < q->n_pending && !conflict; ++i) {
+        const KznPendingTransfer& o = q->pending[i];
+        conflict = ranges_overlap(dst, bytes, o.dst, o.bytes) || (o.src && ranges_overlap(dst, bytes, o.src, o.bytes)) ||
+                   (src && ranges_overlap(src, bytes, o.dst, o.bytes));
+    }
+    if (conflict && (*result = kzn_flush_transfers(q))) return true;
+    KznPendingTransfer& t = q->pending[q->n_pending++];
+    t.dst = dst;
+    t.src = src;
+    t.bytes = bytes;
+    t.value = value;
+    return true;
+}
+
+KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint32_t value, bool may_merge) {
     if (bytes == 0) return KZN_SUCCESS;
+    KznResult r;
+    if (may_merge && merge_transfer(q, address, 0, bytes, value, &r)) return r;
+    if (may_merge && (r = kzn_flush_transfers(q))) return r;
     bool aligned = (address % 16 == 0) && (bytes % 16 == 0);
     Path path = transfer_path();
     bool tma = aligned && (path == Path::Tma || (path == Path::Auto && bytes >= (64ull << 20)));
@@ -380,6 +470,8 @@ KznResult launch_fill_contig(KznQueue* q, uint64_t address, uint64_t bytes, uint
 }
 
 KznResult launch_copy_bulk(KznQueue* q, uint64_t dst, uint64_t src, uint64_t bytes) {
+    KznResult r = kzn_flush_transfers(q);
+    if (r) return r;
     static bool attr_set = false;
     const int smem = kCopyStages * kCopyChunk;
     if (!attr_set) {
@@ -430,6 +522,8 @@ bool vec4_ok(const Box& b, const Surf& s, uint32_t w) {
 
 template <int VEC, bool FILL>
 KznResult launch_box_t(KznQueue* q, const BoxParams& p, bool st, bool dt) {
+    KznResult r = kzn_flush_transfers(q);
+    if (r) return r;
     int grid = grid_for(q, p.total);
 #define KZN_BOX(ST, DT)                                                          \
     kzn_timing_begin(q);                                                          \
@@ -480,6 +574,8 @@ KznResult launch_box(KznQueue* q, const Box* src, const Box& dst, uint32_t w, ui
             if (fill) return launch_fill_contig(q, p.dst.base, bytes, fill_value);
             Path path = transfer_path();
             bool aligned = p.dst.base % 16 == 0 && p.src.base % 16 == 0 && bytes % 16 == 0;
+            KznResult mr;
+            if (aligned && merge_transfer(q, p.dst.base, p.src.base, bytes, 0, &mr)) return mr;
             if (aligned && path == Path::Tma) return launch_copy_bulk(q, p.dst.base, p.src.base, bytes);
         }
     }
@@ -594,7 +690,7 @@ Box buffer_box(uint64_t buffer_address, const KznBufferImageCopy* c) {
 
 KznResult copy_buffer_image(KznQueue* q, uint64_t buffer_address, uint64_t buffer_size, const KznImageDesc* im,
                             uint32_t region_count, const KznBufferImageCopy* regions, bool to_image, const char* what) {
-    KznResult r = kzn_queue_enter(q);
+    KznResult r = kzn_queue_enter_transfer(q);
     if (r) return r;
     if ((r = kzn_check_image(im, what))) return r;
     KZN_VALID(buffer_address && buffer_address % 4 == 0, "%s: buffer address must be 4-byte aligned", what);
@@ -615,13 +711,53 @@ KznResult copy_buffer_image(KznQueue* q, uint64_t buffer_address, uint64_t buffe
 
 }  // namespace
 
+// Capture the pending batch: one command goes down its usual path, several become one merged launch.
+KznResult kzn_flush_transfers(KznQueue* q) {
+    const uint32_t n = q->n_pending;
+    if (n == 0) return KZN_SUCCESS;
+    q->n_pending = 0;  // first: the launch helpers below call back into this function
+    if (n == 1) {
+        const KznPendingTransfer& t = q->pending[0];
+        if (t.src == 0) return launch_fill_contig(q, t.dst, t.bytes, t.value, false);
+        if (transfer_path() == Path::Tma) return launch_copy_bulk(q, t.dst, t.src, t.bytes);
+        Box sb = {t.src, false, t.bytes, t.bytes, 0, 0, 0, 0}, db = {t.dst, false, t.bytes, t.bytes, 0, 0, 0, 0};
+        BoxParams p;
+        memset(&p, 0, sizeof p);
+        p.src = lower(sb);
+        p.dst = lower(db);
+        p.h = p.slices = 1;
+        p.wv = (uint32_t)(t.bytes / 16);
+        p.total = t.bytes / 16;
+        return launch_box_t<4, false>(q, p, false, false);
+    }
+    MergedOps m;
+    memset(&m, 0, sizeof m);
+    m.n = n;
+    uint32_t units = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const KznPendingTransfer& t = q->pending[i];
+        m.first_unit[i] = units;
+        m.vecs[i] = (uint32_t)(t.bytes / 16);
+        m.value[i] = t.value;
+        m.dst[i] = t.dst;
+        m.src[i] = t.src;
+        units += (m.vecs[i] + kUnitVecs - 1) / kUnitVecs;
+    }
+    m.first_unit[n] = units;
+    m.total_units = units;
+    const uint32_t cap = (uint32_t)q->device->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+    merged_transfer_kernel<<<units < cap ? units : cap, kThreads, 0, q->stream>>>(m);
+    q->merged_commands += n;
+    return kzn_launched(q, "merged_transfer_kernel");
+}
+
 // ---- C ABI ----------------------------------------------------------------------------------------------------
 
 extern "C" {
 
 KznResult kzn_cmd_clear_color_image(KznQueue* queue, const KznImageDesc* image, const KznClearColorValue* color,
                                     uint32_t range_count, const KznImageSubresourceRange* ranges) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     if ((r = kzn_check_image(image, "vkCmdClearColorImage"))) return r;
     KZN_REQUIRE(image->format == KZN_FORMAT_R8G8B8A8_UNORM, KZN_ERROR_FORMAT_NOT_SUPPORTED,
@@ -632,7 +768,7 @@ KznResult kzn_cmd_clear_color_image(KznQueue* queue, const KznImageDesc* image, 
 
 KznResult kzn_cmd_clear_depth_stencil_image(KznQueue* queue, const KznImageDesc* image, const KznClearDepthStencilValue* value,
                                             uint32_t range_count, const KznImageSubresourceRange* ranges) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     if ((r = kzn_check_image(image, "vkCmdClearDepthStencilImage"))) return r;
     KZN_REQUIRE(image->format == KZN_FORMAT_D32_SFLOAT, KZN_ERROR_FORMAT_NOT_SUPPORTED,
@@ -645,7 +781,7 @@ KznResult kzn_cmd_clear_depth_stencil_image(KznQueue* queue, const KznImageDesc*
 
 KznResult kzn_cmd_clear_attachment(KznQueue* queue, const KznImageDesc* image, const KznClearColorValue* v,
                                    uint32_t rect_count, const KznClearRect* rects) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     if ((r = kzn_check_image(image, "vkCmdClearAttachments"))) return r;
     KZN_VALID(v && rect_count && rects, "vkCmdClearAttachments: null argument or rectCount == 0");
@@ -679,7 +815,7 @@ KznResult kzn_cmd_copy_image_to_buffer(KznQueue* queue, const KznImageDesc* imag
 
 KznResult kzn_cmd_copy_buffer(KznQueue* queue, uint64_t src_address, uint64_t src_size, uint64_t dst_address, uint64_t dst_size,
                               uint32_t region_count, const KznBufferCopy* regions) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     KZN_VALID(src_address && dst_address && region_count && regions, "vkCmdCopyBuffer: null argument or regionCount == 0");
     for (uint32_t i = 0; i < region_count; ++i) {
@@ -699,6 +835,7 @@ KznResult kzn_cmd_copy_buffer(KznQueue* queue, uint64_t src_address, uint64_t sr
             if ((r = launch_box(queue, &sb, db, (uint32_t)texels, 1, 1, false, 0))) return r;
         } else {
             // byte-granular regions are legal for vkCmdCopyBuffer: the copy engine handles them
+            if ((r = kzn_flush_transfers(queue))) return r;
             KZN_CUDA(cudaMemcpyAsync((void*)(uintptr_t)d, (const void*)(uintptr_t)s, c->size, cudaMemcpyDeviceToDevice, queue->stream));
         }
     }
@@ -706,7 +843,7 @@ KznResult kzn_cmd_copy_buffer(KznQueue* queue, uint64_t src_address, uint64_t sr
 }
 
 KznResult kzn_cmd_fill_buffer(KznQueue* queue, uint64_t dst_address, uint64_t dst_size, uint64_t offset, uint64_t size, uint32_t data) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     KZN_VALID(dst_address && dst_address % 4 == 0, "vkCmdFillBuffer: bad buffer address");
     KZN_VALID(offset < dst_size && offset % 4 == 0, "vkCmdFillBuffer: dstOffset must be < size and a multiple of 4 (VUID 00024/00025)");
@@ -730,7 +867,7 @@ KznResult kzn_cmd_update_buffer(KznQueue* queue, uint64_t dst_address, uint64_t 
 }
 
 KznResult kzn_cmd_copy_image(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst, uint32_t region_count, const KznImageCopy* regions) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     if ((r = kzn_check_image(src, "vkCmdCopyImage(src)")) || (r = kzn_check_image(dst, "vkCmdCopyImage(dst)"))) return r;
     KZN_VALID(region_count && regions, "vkCmdCopyImage: regionCount must be > 0");
@@ -817,7 +954,7 @@ KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const Kzn
 }
 
 KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst) {
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter_transfer(queue);
     if (r) return r;
     if ((r = kzn_check_image(src, "convert_tiling(src)")) || (r = kzn_check_image(dst, "convert_tiling(dst)"))) return r;
     KZN_VALID(src->format == dst->format && src->width == dst->width && src->height == dst->height && src->depth == dst->depth &&

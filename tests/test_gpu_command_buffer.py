@@ -128,3 +128,94 @@ def test_recording_rules(gpu):
     q.submit([cb])  # an empty command buffer is valid
     q.wait_idle()
     cb.destroy(); f.destroy()
+
+
+def test_disjoint_transfers_merge_into_one_launch_and_match_the_oracle(gpu):
+    """Recorded clears / copies with disjoint address ranges run as ONE merged launch (transfer.cu
+    merged_transfer_kernel); results are the oracle's, byte for byte, on replay."""
+    w = h = 256
+    n = 12
+    lib = ob.load()
+    q = gpu.queue
+    images = [gpu.buffer(w * h * 4, np.full(w * h * 4, 0x11 * (i % 15), dtype=np.uint8)) for i in range(n)]
+    sources = [gpu.buffer(w * h * 4, ob.random_bytes(w * h * 4, 100 + i)) for i in range(n // 2)]
+    readback = gpu.buffer(w * h * 4, np.zeros(w * h * 4, dtype=np.uint8))
+    colors = [(i / 16.0, 1.0 - i / 16.0, 0.5, (i % 3) / 2.0) for i in range(n)]
+    region = buffer_image_copy(w, h)
+    want = []
+    for i in range(n):
+        mem = ob.aligned_empty(w * h * 4)
+        d = abi.ImageDesc(ob.ptr(mem), abi.FORMAT_R8G8B8A8_UNORM, 0, w, h, 1, 1, 1, 0)
+        if i % 2 == 0:
+            c = abi.ClearColorValue()
+            c.float32[:] = list(colors[i])
+            rng, k = util.arr(abi.ImageSubresourceRange,
+                              [abi.ImageSubresourceRange(abi.ASPECT_COLOR, 0, abi.REMAINING, 0, abi.REMAINING)])
+            check(lib.kzo_clear_color_image(C.byref(d), C.byref(c), k, rng))
+        else:
+            src = ob.random_bytes(w * h * 4, 100 + i // 2)
+            reg, k = util.arr(abi.BufferImageCopy, [region])
+            check(lib.kzo_copy_buffer_to_image(C.c_void_p(ob.ptr(src)), src.nbytes, C.byref(d), k, reg))
+        want.append(mem.copy())
+    before = q.launch_count
+    with q.record() as cb:
+        for i in range(n):
+            img = host.Image(images[i].address, w, h)
+            if i % 2 == 0:
+                q.cmd_clear_color_image(img, colors[i])
+            else:
+                q.cmd_copy_buffer_to_image(sources[i // 2].address, w * h * 4, img, [region])
+        # image 1 -> buffer: reads what the merged batch wrote, so it must start a new launch
+        q.cmd_copy_image_to_buffer(host.Image(images[1].address, w, h), readback.address, w * h * 4, [region])
+    assert cb.launch_count == 2 and q.launch_count == before
+    for rep in range(2):
+        q.submit([cb])
+        q.wait_idle()
+        for i in range(n):
+            assert np.array_equal(images[i].download(), want[i]), f"image {i} replay {rep}"
+        assert np.array_equal(readback.download(), want[1])
+        for i in range(n):
+            images[i].upload(np.full(w * h * 4, 0xEE, dtype=np.uint8))
+    cb.destroy()
+    gpu.release()
+
+
+def test_dependent_transfers_are_not_merged(gpu):
+    """fill A; copy A -> B; fill A again: each reads or overwrites what the previous one wrote -> 3 launches, in order."""
+    size = 1 << 16
+    a = gpu.buffer(size, np.zeros(size, dtype=np.uint8))
+    b = gpu.buffer(size, np.zeros(size, dtype=np.uint8))
+    q = gpu.queue
+    with q.record() as cb:
+        q.cmd_fill_buffer(a.address, size, 0, size, 0x01020304)
+        q.cmd_copy_buffer(a.address, size, b.address, size, [abi.BufferCopy(0, 0, size)])
+        q.cmd_fill_buffer(a.address, size, 0, size, 0xA0B0C0D0)
+    assert cb.launch_count == 3
+    q.submit([cb])
+    q.wait_idle()
+    assert np.all(b.download().view(np.uint32) == 0x01020304)
+    assert np.all(a.download().view(np.uint32) == 0xA0B0C0D0)
+    cb.destroy()
+    gpu.release()
+
+
+def test_merged_batch_is_flushed_by_a_draw_and_by_odd_sizes(gpu):
+    """Ragged (non 16-byte) fills and a barrier end a batch; more than KZN_MAX_MERGED commands split into batches."""
+    size = 4096
+    n = 200  # > 96 commands: three merged launches
+    bufs = gpu.buffer(size * n, np.zeros(size * n, dtype=np.uint8))
+    odd = gpu.buffer(64, np.zeros(64, dtype=np.uint8))
+    q = gpu.queue
+    with q.record() as cb:
+        for i in range(n):
+            q.cmd_fill_buffer(bufs.address, size * n, i * size, size, i + 1)
+        q.cmd_pipeline_barrier()
+        q.cmd_fill_buffer(odd.address, 64, 4, 8, 0xFFFFFFFF)  # 4-byte aligned only: its own launch
+    assert cb.launch_count == 3 + 1
+    q.submit([cb])
+    q.wait_idle()
+    got = bufs.download().view(np.uint32).reshape(n, size // 4)
+    assert np.array_equal(got, np.repeat(np.arange(1, n + 1, dtype=np.uint32)[:, None], size // 4, axis=1))
+    assert odd.download().tolist() == [0] * 4 + [255] * 8 + [0] * 52
+    cb.destroy()
+    gpu.release()
