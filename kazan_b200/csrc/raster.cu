@@ -19,6 +19,7 @@
 // Numerics are the oracle's rules R1-R8 (oracle/raster.c): every fp32 operation is written out; the file is compiled
 // with -fmad=false so only the explicit fmaf() calls fuse.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -43,6 +44,7 @@ constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTA
 constexpr int kRecs = 128;               // triangle records staged in shared memory per round
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
+constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
@@ -90,6 +92,7 @@ struct DrawParams {
     uint32_t binned;                               // 0 => every tile walks all triangles
     unsigned long long* stats;                     // KznDrawStatistics or null
     uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
+    uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
 };
 
 // ---- setup ------------------------------------------------------------------------------------------------
@@ -426,6 +429,7 @@ struct RasterShared {
     uint32_t depth_dirty[kTileH][kTileW / 32];
     float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
     uint32_t warp_counts[kTileH];
+    uint8_t row_list[kTileH][kRecs];  // per row: slots of the staged records whose bounding box contains the row, in order
 };
 
 // Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.list, by the whole CTA.  The binning
@@ -1113,16 +1117,57 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
 
         // ---- my row: stream the candidate pixels of the staged triangles, 32 per step; covered ones are queued ----
         if (row_in) {
-            for (uint32_t chunk = 0; chunk < n_round; chunk += 32) {
-                // lane j looks at triangle chunk+j: which pixels of my row are in its bounding box?
+            // the staged triangles whose bounding box contains my row, compacted in primitive order: with small
+            // triangles only a fraction of a tile's list touches any one row, and the chunks below stay full
+            uint32_t n_mine = 0;
+            for (uint32_t c = 0; c < n_round; c += 32) {
+                bool hit = false;
+                if (c + lane < n_round) {
+                    const int2 yy = *reinterpret_cast<const int2*>(&sh.recs[c + lane].miny);  // miny maxy (already scissored)
+                    hit = py >= yy.x && py <= yy.y;
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                if (hit) sh.row_list[warp][n_mine + __popc(b & ((1u << lane) - 1u))] = (uint8_t)(c + lane);
+                n_mine += __popc(b);
+            }
+            __syncwarp();
+            for (uint32_t chunk = 0; chunk < n_mine; chunk += 32) {
+                // lane j looks at the j-th of them: which pixels of my row can it cover?
                 int xa = 0;
-                uint32_t width = 0;
-                if (chunk + lane < n_round) {
-                    int4 bb = *reinterpret_cast<const int4*>(&sh.recs[chunk + lane]);  // minx maxx miny maxy (already scissored)
-                    if (py >= bb.z && py <= bb.w) {
-                        xa = max(bb.x, tile_px0);
-                        int xb = min(bb.y, tile_px0 + kTileW - 1);
-                        width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+                uint32_t width = 0, my_slot = 0;
+                if (chunk + lane < n_mine) {
+                    my_slot = sh.row_list[warp][chunk + lane];
+                    const int2 xx = *reinterpret_cast<const int2*>(&sh.recs[my_slot]);  // minx maxx
+                    xa = max(xx.x, tile_px0);
+                    const int xb = min(xx.y, tile_px0 + kTileW - 1);
+                    width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+                }
+                if (p.exact_spans) {
+                    // Narrow spans are cut down to the pixels that are really covered: the covered pixels of a row are
+                    // an interval (three half-planes), found by stepping the biased integer edge functions (R5) along
+                    // the span, one triangle per lane.  F_i = e_i + bias_i - 1 >= 0  <=>  e_i + bias_i > 0.
+                    const bool narrow = width != 0 && width <= (uint32_t)kExactSpan;
+                    const uint32_t steps = __reduce_max_sync(0xffffffffu, narrow ? width : 0u);
+                    if (steps) {
+                        const TriRec& t = sh.recs[my_slot];
+                        const int32_t sx = 16 * xa + 8;
+                        const uint32_t bias = t.bias_bits;
+                        long long f0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]) + (long long)(bias & 1u) - 1;
+                        long long f1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]) + (long long)((bias >> 1) & 1u) - 1;
+                        long long f2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]) + (long long)((bias >> 2) & 1u) - 1;
+                        const long long d0 = 16ll * t.a[0], d1 = 16ll * t.a[1], d2 = 16ll * t.a[2];
+                        uint32_t m = 0;
+                        for (uint32_t k = 0; k < steps; ++k) {
+                            if ((f0 | f1 | f2) >= 0) m |= 1u << k;
+                            f0 += d0;
+                            f1 += d1;
+                            f2 += d2;
+                        }
+                        if (narrow) {
+                            m &= (1u << width) - 1u;
+                            xa += m ? __ffs(m) - 1 : 0;
+                            width = __popc(m);
+                        }
                     }
                 }
                 // spans covering at least half the row go through the quad path (4 pixels per lane, no queue);
@@ -1154,7 +1199,7 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
                     const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
                     const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
                     const int px = o_xa + (int)(c - o_excl);
-                    const uint32_t slot = chunk + pos;
+                    const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, pos);
                     const TriRec& t = sh.recs[slot];
                     bool cov = false;
                     float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
@@ -1209,7 +1254,7 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
                         shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
                         q_n = 0;
                     }
-                    shade_wide<FS, NEED_DST>(p, sh, warp, lane, chunk + (uint32_t)wide_lane, tile_px0, py, sy, depth_test, depth_write,
+                    shade_wide<FS, NEED_DST>(p, sh, warp, lane, __shfl_sync(0xffffffffu, my_slot, wide_lane), tile_px0, py, sy, depth_test, depth_write,
                                              has_color, n_covered, n_passed);
                     wide_mask &= wide_mask - 1;
                     seg_begin = seg_end;
@@ -1461,6 +1506,13 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     KznRasterScratch* s = q->raster;
     p.tris = s->tris;
     p.work_counter = s->counters;
+    {
+        static const bool exact = [] {
+            const char* e = getenv("KZN_RASTER_EXACT_SPANS");
+            return !(e && e[0] == '0');
+        }();
+        p.exact_spans = exact;
+    }
     if (p.binned) {
         p.tile_counts = s->tile_words;
         p.tile_cursor = s->tile_words + tiles;
