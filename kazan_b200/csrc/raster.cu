@@ -41,9 +41,17 @@ constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels w
 #endif
 constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows high
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
-constexpr int kRecs = 128;               // triangle records staged in shared memory per round
+#ifndef KZN_RECS
+#define KZN_RECS 128
+#endif
+constexpr int kRecs = KZN_RECS;          // triangle records staged in shared memory per round
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
+#ifndef KZN_STAGES
+#define KZN_STAGES 8
+#endif
+constexpr int kStages = KZN_STAGES;      // ring of kStages x 32 record slots fed by bulk async copies (binned tiles)
+constexpr int kRingSlots = kStages * 32 > kRecs ? kStages * 32 : kRecs;
 constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -412,6 +420,40 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
     return p.color_base + ((unsigned long long)py * p.fb_w + px) * 4ull;
 }
 
+// ---- mbarrier / bulk async copy (TMA engine; SASS: SYNCS, UBLKCP) ---------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spins until the phase with the given parity has completed.  A wait that outlives any possible frame is a bug in the
+// release protocol: trap (the launch fails with an error) rather than hang the device.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- raster ------------------------------------------------------------------------------------------------------------
 
 struct FragQueue {  // covered fragments of one row waiting for a full 32-lane shading batch, in primitive order
@@ -420,7 +462,7 @@ struct FragQueue {  // covered fragments of one row waiting for a full 32-lane s
 };
 
 struct RasterShared {
-    TriRec recs[kRecs];
+    TriRec recs[kRingSlots];  // binned tiles: ring of kStages stages x 32 records; overflow tiles: kRecs records per round
     FragQueue queue[kTileH];
     uint32_t list[kSortCap];         // binned: the tile's sorted triangle ids; direct: ids surviving the current round
     uint32_t color[kTileH][kTileW];  // the tile's colour and depth live here for the whole triangle list
@@ -430,7 +472,10 @@ struct RasterShared {
     float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
     uint32_t warp_counts[kTileH];
     uint8_t row_list[kTileH][kRecs];  // per row: slots of the staged records whose bounding box contains the row, in order
+    unsigned long long full[kStages];  // mbarriers: the stage's records have landed (expect_tx / complete_tx)
+    uint32_t done[kStages];            // rows that have released the stage's current round; the last one refills it
 };
+static_assert(kStages <= kTileH && (kStages & (kStages - 1)) == 0 && kRingSlots <= 256 && kRecs >= 64, "ring geometry");
 
 // Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.list, by the whole CTA.  The binning
 // atomics deliver each tile's list in arbitrary order; primitive order (R7) is restored here.  Only the bits in which the
@@ -1003,8 +1048,144 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
 // for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
 // time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
 // Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
+// One chunk of a row's work: lane j holds (have, my_slot) = the j-th triangle of the chunk whose bounding box contains
+// row py, slots in primitive order.  Candidate pixels of all 32 spans are streamed 32 per step whatever triangle they
+// belong to; covered fragments go to the warp's queue and are shaded in full batches of 32.
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_constant__ DrawParams p) {
+__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, bool have,
+                                             uint32_t my_slot, int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write,
+                                             bool has_color, uint32_t& q_n, uint32_t& n_covered, uint32_t& n_passed) {
+    // lane j looks at the j-th of them: which pixels of my row can it cover?
+    int xa = 0;
+    uint32_t width = 0;
+    if (have) {
+        const int2 xx = *reinterpret_cast<const int2*>(&sh.recs[my_slot]);  // minx maxx
+        xa = max(xx.x, tile_px0);
+        const int xb = min(xx.y, tile_px0 + kTileW - 1);
+        width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+    }
+    if (p.exact_spans) {
+        // Narrow spans are cut down to the pixels that are really covered: the covered pixels of a row are
+        // an interval (three half-planes), found by stepping the biased integer edge functions (R5) along
+        // the span, one triangle per lane.  F_i = e_i + bias_i - 1 >= 0  <=>  e_i + bias_i > 0.
+        const bool narrow = width != 0 && width <= (uint32_t)kExactSpan;
+        const uint32_t steps = __reduce_max_sync(0xffffffffu, narrow ? width : 0u);
+        if (steps) {
+            const TriRec& t = sh.recs[my_slot];
+            const int32_t sx = 16 * xa + 8;
+            const uint32_t bias = t.bias_bits;
+            long long f0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]) + (long long)(bias & 1u) - 1;
+            long long f1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]) + (long long)((bias >> 1) & 1u) - 1;
+            long long f2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]) + (long long)((bias >> 2) & 1u) - 1;
+            const long long d0 = 16ll * t.a[0], d1 = 16ll * t.a[1], d2 = 16ll * t.a[2];
+            uint32_t m = 0;
+            for (uint32_t k = 0; k < steps; ++k) {
+                if ((f0 | f1 | f2) >= 0) m |= 1u << k;
+                f0 += d0;
+                f1 += d1;
+                f2 += d2;
+            }
+            if (narrow) {
+                m &= (1u << width) - 1u;
+                xa += m ? __ffs(m) - 1 : 0;
+                width = __popc(m);
+            }
+        }
+    }
+    // spans covering at least half the row go through the quad path (4 pixels per lane, no queue);
+    // they split the chunk into segments of ordinary candidates so that primitive order is kept
+    uint32_t wide_mask = __ballot_sync(0xffffffffu, width >= (uint32_t)kWideSpan);
+    if (width >= (uint32_t)kWideSpan) width = 0;
+    uint32_t incl = width;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - width;
+    uint32_t seg_begin = 0;
+    for (;;) {
+        const int wide_lane = wide_mask ? __ffs(wide_mask) - 1 : -1;
+        const uint32_t seg_end = wide_lane >= 0 ? __shfl_sync(0xffffffffu, excl, wide_lane) : total;
+    for (uint32_t c0 = seg_begin; c0 < seg_end; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const bool active = c < seg_end;
+        // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
+        uint32_t pos = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t e = __shfl_sync(0xffffffffu, excl, (pos + step) & 31u);
+            if (e <= c) pos += step;
+        }
+        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
+        const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
+        const int px = o_xa + (int)(c - o_excl);
+        const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, pos);
+        const TriRec& t = sh.recs[slot];
+        bool cov = false;
+        float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
+        if (active) {
+            const int32_t sx = 16 * px + 8;
+            long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
+            long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
+            long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
+            const uint32_t bias = t.bias_bits;
+            cov = e0 + (long long)(bias & 1u) > 0 && e1 + (long long)((bias >> 1) & 1u) > 0 &&
+                  e2 + (long long)((bias >> 2) & 1u) > 0;
+            if (cov) {
+                const float inv2a = t.inv2a;
+                l0 = (float)e0 * inv2a;  // R6
+                l1 = (float)e1 * inv2a;
+                l2 = (float)e2 * inv2a;
+                z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+                cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, cov);
+        if (!ballot) continue;
+        if (cov) {  // append to my warp's fragment queue, keeping primitive order
+            ++n_covered;
+            FragQueue& fq = sh.queue[warp];
+            const uint32_t at = q_n + __popc(ballot & ((1u << lane) - 1u));
+            fq.key[at] = (slot << 8) | (uint32_t)(px - tile_px0);
+            fq.z[at] = z;
+            fq.l0[at] = l0;
+            fq.l1[at] = l1;
+            fq.l2[at] = l2;
+        }
+        q_n += __popc(ballot);
+        __syncwarp();
+        if (q_n >= 32) {
+            shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+            // move the remainder (< 32 entries) to the front
+            FragQueue& fq = sh.queue[warp];
+            const bool mv = lane < q_n - 32u;
+            uint32_t k = 0;
+            float fz = 0, f0 = 0, f1 = 0, f2 = 0;
+            if (mv) { k = fq.key[32 + lane]; fz = fq.z[32 + lane]; f0 = fq.l0[32 + lane]; f1 = fq.l1[32 + lane]; f2 = fq.l2[32 + lane]; }
+            __syncwarp();
+            if (mv) { fq.key[lane] = k; fq.z[lane] = fz; fq.l0[lane] = f0; fq.l1[lane] = f1; fq.l2[lane] = f2; }
+            q_n -= 32u;
+            __syncwarp();
+        }
+    }
+        if (wide_lane < 0) break;
+        // a wide span: everything queued so far comes first, then the span itself, 4 pixels per lane
+        if (q_n) {
+            shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+            q_n = 0;
+        }
+        shade_wide<FS, NEED_DST>(p, sh, warp, lane, __shfl_sync(0xffffffffu, my_slot, wide_lane), tile_px0, py, sy, depth_test, depth_write,
+                                 has_color, n_covered, n_passed);
+        wide_mask &= wide_mask - 1;
+        seg_begin = seg_end;
+    }
+}
+
+
+template <uint32_t FS, int NEED_DST>
+__global__ void __launch_bounds__(kRasterThreads, kStages > 4 ? 3 : 4) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1071,13 +1252,120 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
         sh.depth_dirty[warp][lane] = 0;
     }
     if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
+    if (tid < kStages) {
+        mbar_init(&sh.full[tid], 1);
+        sh.done[tid] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();  // the sort wrote the record area through the generic proxy; bulk copies land there next
     __syncthreads();
 
     const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
     uint32_t n_covered = 0, n_passed = 0;
     uint32_t q_n = 0;  // fragments waiting in my warp's queue (warp-uniform)
 
-    for (uint32_t base = 0; base < n_source; base += kRecs) {
+    if (!direct) {
+        // ---- binned tiles: the sorted list streams through a ring of kStages stages x 32 records.  Records arrive by
+        // bulk async copy (one 144-byte cp.async.bulk per record, mbarrier complete_tx), kStages rounds ahead of the
+        // slowest row; there is no CTA-wide barrier: every row warp runs at its own pace and is at most kStages rounds
+        // ahead of the slowest.  A warp keeps the slots of the triangles that touch its row in a pending list and works
+        // on them 32 at a time (full chunks whatever the density); it releases a round when neither its pending list
+        // nor its fragment queue refers to it any more, and the last row to release a round refills the stage with
+        // round + kStages.
+        const uint32_t n_rounds = (list_len + 31u) / 32u;
+        const uint32_t n_part = (uint32_t)(min(p.cy1, tile_py0 + kTileH - 1) - max(p.cy0, tile_py0) + 1);  // rows taking part
+        auto refill = [&](uint32_t stage, uint32_t round) {  // whole warp
+            const uint32_t first = round * 32u;
+            const uint32_t cnt = min(32u, list_len - first);
+            if (lane == 0) mbar_expect_tx(&sh.full[stage], cnt * (uint32_t)sizeof(TriRec));
+            __syncwarp();
+            if (lane < cnt)
+                bulk_g2s(&sh.recs[stage * 32u + lane], &p.tris[sh.list[first + lane]], (uint32_t)sizeof(TriRec), &sh.full[stage]);
+        };
+        if (warp < (uint32_t)kStages && warp < n_rounds) refill(warp, warp);
+        if (row_in) {
+            uint8_t* pend = sh.row_list[warp];
+            uint32_t pend_n = 0;   // < 32 between rounds
+            uint32_t released = 0;  // rounds below this one are released by me
+            auto release_to = [&](uint32_t upto) {
+                for (; released < upto; ++released) {
+                    const uint32_t stage = released % (uint32_t)kStages;
+                    __syncwarp();  // every lane's reads of the stage are done
+                    uint32_t last = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        last = atomicAdd(&sh.done[stage], 1u) == n_part - 1u;
+                        if (last) sh.done[stage] = 0;
+                    }
+                    last = __shfl_sync(0xffffffffu, last, 0);
+                    if (last && released + (uint32_t)kStages < n_rounds) {
+                        __threadfence_block();
+                        fence_proxy_async();
+                        refill(stage, released + (uint32_t)kStages);
+                    }
+                }
+            };
+            auto round_of = [&](uint32_t slot, uint32_t newest) {  // the round a referenced slot belongs to
+                return newest - ((newest - (slot >> 5)) & (uint32_t)(kStages - 1));
+            };
+            auto drain_queue = [&]() {
+                if (q_n) {
+                    shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+                    q_n = 0;
+                }
+            };
+            for (uint32_t k = 0; k < n_rounds; ++k) {
+                const uint32_t stage = k % (uint32_t)kStages;
+                if (released + (uint32_t)kStages <= k) {
+                    // round k lands where round k - kStages is, which my leftovers still pin: finish them first
+                    if (pend_n) {
+                        const bool have = lane < pend_n;
+                        raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? pend[lane] : 0u, tile_px0, py, sy, depth_test,
+                                                   depth_write, has_color, q_n, n_covered, n_passed);
+                        pend_n = 0;
+                    }
+                    drain_queue();
+                    release_to(k);
+                }
+                mbar_wait(&sh.full[stage], (k / (uint32_t)kStages) & 1u);
+                // which of the round's records touch my row?
+                const uint32_t cnt = min(32u, list_len - k * 32u);
+                bool hit = false;
+                if (lane < cnt) {
+                    const int2 yy = *reinterpret_cast<const int2*>(&sh.recs[stage * 32u + lane].miny);  // miny maxy (scissored)
+                    hit = py >= yy.x && py <= yy.y;
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = (uint8_t)(stage * 32u + lane);
+                pend_n += __popc(b);
+                __syncwarp();
+                if (pend_n >= 32u) {
+                    raster_chunk<FS, NEED_DST>(p, sh, warp, lane, true, pend[lane], tile_px0, py, sy, depth_test, depth_write, has_color,
+                                               q_n, n_covered, n_passed);
+                    const bool mv = lane < pend_n - 32u;
+                    const uint8_t v = mv ? pend[32u + lane] : (uint8_t)0;
+                    __syncwarp();
+                    if (mv) pend[lane] = v;
+                    pend_n -= 32u;
+                    __syncwarp();
+                }
+                // release every round that neither the pending list nor the fragment queue refers to (both are FIFO)
+                uint32_t oldest = k + 1u;
+                if (pend_n) oldest = round_of(pend[0], k);
+                if (q_n) oldest = min(oldest, round_of(sh.queue[warp].key[0] >> 8, k));
+                release_to(oldest);
+            }
+            if (pend_n) {
+                const bool have = lane < pend_n;
+                raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? pend[lane] : 0u, tile_px0, py, sy, depth_test, depth_write,
+                                           has_color, q_n, n_covered, n_passed);
+            }
+            drain_queue();
+        }
+    }
+
+    // overflow tiles (list longer than kSortCap, or the bins overflowed): walk every triangle of the draw in rounds
+    for (uint32_t base = 0; direct && base < n_source; base += kRecs) {
         // ---- stage up to kRecs triangle records that touch this tile, in primitive order ----
         uint32_t n_round;
         if (direct) {
@@ -1132,133 +1420,9 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_
             }
             __syncwarp();
             for (uint32_t chunk = 0; chunk < n_mine; chunk += 32) {
-                // lane j looks at the j-th of them: which pixels of my row can it cover?
-                int xa = 0;
-                uint32_t width = 0, my_slot = 0;
-                if (chunk + lane < n_mine) {
-                    my_slot = sh.row_list[warp][chunk + lane];
-                    const int2 xx = *reinterpret_cast<const int2*>(&sh.recs[my_slot]);  // minx maxx
-                    xa = max(xx.x, tile_px0);
-                    const int xb = min(xx.y, tile_px0 + kTileW - 1);
-                    width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
-                }
-                if (p.exact_spans) {
-                    // Narrow spans are cut down to the pixels that are really covered: the covered pixels of a row are
-                    // an interval (three half-planes), found by stepping the biased integer edge functions (R5) along
-                    // the span, one triangle per lane.  F_i = e_i + bias_i - 1 >= 0  <=>  e_i + bias_i > 0.
-                    const bool narrow = width != 0 && width <= (uint32_t)kExactSpan;
-                    const uint32_t steps = __reduce_max_sync(0xffffffffu, narrow ? width : 0u);
-                    if (steps) {
-                        const TriRec& t = sh.recs[my_slot];
-                        const int32_t sx = 16 * xa + 8;
-                        const uint32_t bias = t.bias_bits;
-                        long long f0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]) + (long long)(bias & 1u) - 1;
-                        long long f1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]) + (long long)((bias >> 1) & 1u) - 1;
-                        long long f2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]) + (long long)((bias >> 2) & 1u) - 1;
-                        const long long d0 = 16ll * t.a[0], d1 = 16ll * t.a[1], d2 = 16ll * t.a[2];
-                        uint32_t m = 0;
-                        for (uint32_t k = 0; k < steps; ++k) {
-                            if ((f0 | f1 | f2) >= 0) m |= 1u << k;
-                            f0 += d0;
-                            f1 += d1;
-                            f2 += d2;
-                        }
-                        if (narrow) {
-                            m &= (1u << width) - 1u;
-                            xa += m ? __ffs(m) - 1 : 0;
-                            width = __popc(m);
-                        }
-                    }
-                }
-                // spans covering at least half the row go through the quad path (4 pixels per lane, no queue);
-                // they split the chunk into segments of ordinary candidates so that primitive order is kept
-                uint32_t wide_mask = __ballot_sync(0xffffffffu, width >= (uint32_t)kWideSpan);
-                if (width >= (uint32_t)kWideSpan) width = 0;
-                uint32_t incl = width;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                    if ((int)lane >= d) incl += y;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t excl = incl - width;
-                uint32_t seg_begin = 0;
-                for (;;) {
-                    const int wide_lane = wide_mask ? __ffs(wide_mask) - 1 : -1;
-                    const uint32_t seg_end = wide_lane >= 0 ? __shfl_sync(0xffffffffu, excl, wide_lane) : total;
-                for (uint32_t c0 = seg_begin; c0 < seg_end; c0 += 32) {
-                    const uint32_t c = c0 + lane;
-                    const bool active = c < seg_end;
-                    // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
-                    uint32_t pos = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        uint32_t e = __shfl_sync(0xffffffffu, excl, (pos + step) & 31u);
-                        if (e <= c) pos += step;
-                    }
-                    const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
-                    const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
-                    const int px = o_xa + (int)(c - o_excl);
-                    const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, pos);
-                    const TriRec& t = sh.recs[slot];
-                    bool cov = false;
-                    float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
-                    if (active) {
-                        const int32_t sx = 16 * px + 8;
-                        long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
-                        long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
-                        long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
-                        const uint32_t bias = t.bias_bits;
-                        cov = e0 + (long long)(bias & 1u) > 0 && e1 + (long long)((bias >> 1) & 1u) > 0 &&
-                              e2 + (long long)((bias >> 2) & 1u) > 0;
-                        if (cov) {
-                            const float inv2a = t.inv2a;
-                            l0 = (float)e0 * inv2a;  // R6
-                            l1 = (float)e1 * inv2a;
-                            l2 = (float)e2 * inv2a;
-                            z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
-                            cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
-                        }
-                    }
-                    const uint32_t ballot = __ballot_sync(0xffffffffu, cov);
-                    if (!ballot) continue;
-                    if (cov) {  // append to my warp's fragment queue, keeping primitive order
-                        ++n_covered;
-                        FragQueue& fq = sh.queue[warp];
-                        const uint32_t at = q_n + __popc(ballot & ((1u << lane) - 1u));
-                        fq.key[at] = (slot << 8) | (uint32_t)(px - tile_px0);
-                        fq.z[at] = z;
-                        fq.l0[at] = l0;
-                        fq.l1[at] = l1;
-                        fq.l2[at] = l2;
-                    }
-                    q_n += __popc(ballot);
-                    __syncwarp();
-                    if (q_n >= 32) {
-                        shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color, n_passed);
-                        // move the remainder (< 32 entries) to the front
-                        FragQueue& fq = sh.queue[warp];
-                        const bool mv = lane < q_n - 32u;
-                        uint32_t k = 0;
-                        float fz = 0, f0 = 0, f1 = 0, f2 = 0;
-                        if (mv) { k = fq.key[32 + lane]; fz = fq.z[32 + lane]; f0 = fq.l0[32 + lane]; f1 = fq.l1[32 + lane]; f2 = fq.l2[32 + lane]; }
-                        __syncwarp();
-                        if (mv) { fq.key[lane] = k; fq.z[lane] = fz; fq.l0[lane] = f0; fq.l1[lane] = f1; fq.l2[lane] = f2; }
-                        q_n -= 32u;
-                        __syncwarp();
-                    }
-                }
-                    if (wide_lane < 0) break;
-                    // a wide span: everything queued so far comes first, then the span itself, 4 pixels per lane
-                    if (q_n) {
-                        shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
-                        q_n = 0;
-                    }
-                    shade_wide<FS, NEED_DST>(p, sh, warp, lane, __shfl_sync(0xffffffffu, my_slot, wide_lane), tile_px0, py, sy, depth_test, depth_write,
-                                             has_color, n_covered, n_passed);
-                    wide_mask &= wide_mask - 1;
-                    seg_begin = seg_end;
-                }
+                const bool have = chunk + lane < n_mine;
+                raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? sh.row_list[warp][chunk + lane] : 0u, tile_px0, py, sy,
+                                           depth_test, depth_write, has_color, q_n, n_covered, n_passed);
             }
             // the staged records go away at the end of the round: drain the queue
             if (q_n) {

@@ -40,7 +40,7 @@ src = {}
 for (f, ln), e in by.most_common(top):
     if f not in src:
         try:
-            src[f] = open('/root/repo/kazan_b200/csrc/' + f).read().splitlines()
+            src[f] = open(__import__('os').environ.get('KZN_SRC_DIR', '/root/repo/kazan_b200/csrc/') + f).read().splitlines()
         except OSError:
             src[f] = None
     text = src[f][ln - 1].strip()[:95] if src[f] and ln <= len(src[f]) else ''
