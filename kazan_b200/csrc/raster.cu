@@ -41,17 +41,8 @@ constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels w
 #endif
 constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows high
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
-#ifndef KZN_RECS
-#define KZN_RECS 128
-#endif
-constexpr int kRecs = KZN_RECS;          // triangle records staged in shared memory per round
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
-#ifndef KZN_STAGES
-#define KZN_STAGES 8
-#endif
-constexpr int kStages = KZN_STAGES;      // ring of kStages x 32 record slots fed by bulk async copies (binned tiles)
-constexpr int kRingSlots = kStages * 32 > kRecs ? kStages * 32 : kRecs;
 constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -91,6 +82,7 @@ struct DrawParams {
     float inv_fb_w, inv_fb_h;
     // scratch
     TriRec* tris;
+    uint2* boxes;            // [total_tris] minx | maxx << 16, miny | maxy << 16 (the records' pixel boxes, packed: the row filter reads only these)
     uint32_t* tile_counts;   // [tiles]  (bin_count)
     uint32_t* tile_offsets;  // [tiles+1] (bin_scan)
     uint32_t* tile_cursor;   // [tiles]  (bin_fill)
@@ -285,6 +277,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
             uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
 #pragma unroll
             for (int q = 0; q < 9; ++q) dst[q] = src[q];
+            p.boxes[(size_t)inst * p.tris_per_instance + t] =
+                make_uint2((uint32_t)r.minx | ((uint32_t)r.maxx << 16), (uint32_t)r.miny | ((uint32_t)r.maxy << 16));
         }
         if (p.stats) {
             atomicAdd(&p.stats[0], (unsigned long long)n_inst);
@@ -420,77 +414,49 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
     return p.color_base + ((unsigned long long)py * p.fb_w + px) * 4ull;
 }
 
-// ---- mbarrier / bulk async copy (TMA engine; SASS: SYNCS, UBLKCP) ---------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Spins until the phase with the given parity has completed.  A wait that outlives any possible frame is a bug in the
-// release protocol: trap (the launch fails with an error) rather than hang the device.
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spins = 0; !ok; ++spins) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (spins > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ---- raster ------------------------------------------------------------------------------------------------------------
 
 struct FragQueue {  // covered fragments of one row waiting for a full 32-lane shading batch, in primitive order
-    uint32_t key[64];  // staged-record slot << 8 | x within the tile
+    uint32_t key[64];  // slot of the triangle in the row's chunk << 8 | x within the tile
     float z[64], l0[64], l1[64], l2[64];
 };
 
-struct RasterShared {
-    TriRec recs[kRingSlots];  // binned tiles: ring of kStages stages x 32 records; overflow tiles: kRecs records per round
+struct TileState {  // live from the tile prologue to the epilogue
+    TriRec recs[kTileH][32];          // per row: the records of the chunk being rasterised (private to the row's warp)
     FragQueue queue[kTileH];
-    uint32_t list[kSortCap];         // binned: the tile's sorted triangle ids; direct: ids surviving the current round
-    uint32_t color[kTileH][kTileW];  // the tile's colour and depth live here for the whole triangle list
+    uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
+    uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
     float depth[kTileH][kTileW];
     uint32_t color_dirty[kTileH][kTileW / 32];
     uint32_t depth_dirty[kTileH][kTileW / 32];
+};
+struct SortScratch {  // live only while the tile's id list is sorted (before the prologue); the result goes back to global memory
+    uint32_t list[kSortCap];
+    uint32_t second[kSortCap];
+    uint32_t table[256 * kTileH];  // [digit][warp]
+};
+
+struct RasterShared {
+    union {
+        TileState tile;
+        SortScratch sort;
+    };
     float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
     uint32_t warp_counts[kTileH];
-    uint8_t row_list[kTileH][kRecs];  // per row: slots of the staged records whose bounding box contains the row, in order
-    unsigned long long full[kStages];  // mbarriers: the stage's records have landed (expect_tx / complete_tx)
-    uint32_t done[kStages];            // rows that have released the stage's current round; the last one refills it
 };
-static_assert(kStages <= kTileH && (kStages & (kStages - 1)) == 0 && kRingSlots <= 256 && kRecs >= 64, "ring geometry");
 
-// Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.list, by the whole CTA.  The binning
+// Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.sort.list, by the whole CTA.  The binning
 // atomics deliver each tile's list in arbitrary order; primitive order (R7) is restored here.  Only the bits in which the
 // ids of this tile differ are sorted (ids of one tile come from a narrow range of a mesh: typically 2 passes).
 // Warp w owns a contiguous slice of the list and walks it 32 ids at a time; match.any ranks equal digits inside a batch
 // in lane order, a [digit][warp] table of running offsets orders batches and warps, so every pass is stable.
-// Scratch aliases parts of the tile state that are not live yet: sh.recs (second id buffer), sh.queue (offset table).
-__device__ __forceinline__ void sort_tile_list(RasterShared& sh, uint32_t n) {
-    static_assert(sizeof(sh.recs) >= kSortCap * sizeof(uint32_t), "second id buffer aliases recs");
-    static_assert(sizeof(sh.queue) >= 256 * kTileH * sizeof(uint32_t), "offset table aliases the fragment queues");
+// Scratch (second id buffer, offset table) shares memory with the tile state, which is not live yet.
+__device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint32_t n) {
     constexpr uint32_t kFull = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t* a = sh.list;
-    uint32_t* b = reinterpret_cast<uint32_t*>(sh.recs);
-    uint32_t* table = reinterpret_cast<uint32_t*>(sh.queue);  // [256 digits][kTileH warps]
+    uint32_t* a = sh.sort.list;
+    uint32_t* b = sh.sort.second;
+    uint32_t* table = sh.sort.table;  // [256 digits][kTileH warps]
     // range of the ids
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (uint32_t i = tid; i < n; i += kRasterThreads) {
@@ -574,10 +540,7 @@ __device__ __forceinline__ void sort_tile_list(RasterShared& sh, uint32_t n) {
         a = b;
         b = t;
     }
-    if (a != sh.list) {
-        for (uint32_t i = tid; i < n; i += kRasterThreads) sh.list[i] = a[i];
-        __syncthreads();
-    }
+    return a;  // the buffer holding the sorted ids
 }
 
 // blend with the destination held as UNORM8 in shared memory; same operation order as oracle/raster.c output_merge
@@ -625,11 +588,12 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
 
 // Depth test, fragment program and blend for the first `n` (<= 32) queued fragments of a warp's row, one fragment per lane.
 // Fragments of the batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
+// Not inlined: it is called from four places of raster_kernel and the copies pushed the kernel out of the instruction cache.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n,
-                                                int tile_px0, int py, bool depth_test, bool depth_write, bool has_color,
-                                                uint32_t& n_passed) {
-    const FragQueue& fq = sh.queue[warp];
+__device__ __noinline__ uint32_t shade_fragments(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n,
+                                                 int tile_px0, int py, bool depth_test, bool depth_write, bool has_color) {
+    uint32_t n_passed = 0;
+    const FragQueue& fq = sh.tile.queue[warp];
     const bool have = lane < n;
     uint32_t kx = 0x80000000u | lane;  // unique key for idle lanes
     uint32_t slot = 0;
@@ -646,7 +610,7 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
     const uint32_t peers = __match_any_sync(0xffffffffu, kx);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     const uint32_t max_rank = __reduce_max_sync(0xffffffffu, have ? rank : 0u);
-    const TriRec& t = sh.recs[slot];
+    const TriRec& t = sh.tile.recs[warp][slot];
     float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (have && has_color && (max_rank > 0 || !depth_test)) {
         // several fragments per pixel in this batch (or no depth test): shade up front, all lanes together
@@ -661,12 +625,12 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
     for (uint32_t rk = 0; rk <= max_rank; ++rk) {
         if (have && rank == rk) {
             bool pass = true;
-            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.depth[warp][kx]);  // R7: early-Z
+            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][kx]);  // R7: early-Z
             if (pass) {
                 ++n_passed;
                 if (depth_write) {
-                    sh.depth[warp][kx] = z;
-                    atomicOr(&sh.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                    sh.tile.depth[warp][kx] = z;
+                    atomicOr(&sh.tile.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
                 }
                 if (has_color) {
                     if (max_rank == 0 && depth_test) {  // one fragment per pixel: shade only what passed the depth test
@@ -679,14 +643,15 @@ __device__ __forceinline__ void shade_fragments(const DrawParams& p, RasterShare
                                 src[ch] = __fdiv_rn(fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch])), den);
                         }
                     }
-                    const uint32_t dst = NEED_DST ? sh.color[warp][kx] : 0u;
-                    sh.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                    atomicOr(&sh.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                    const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
+                    sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                    atomicOr(&sh.tile.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
                 }
             }
         }
         __syncwarp();
     }
+    return n_passed;
 }
 
 // PX interleaved orbits as PX/2 packed pairs: fma.rn.f32x2 / add.rn.f32x2 (FFMA2 / FADD2) do two IEEE fp32 operations per
@@ -842,25 +807,25 @@ template <uint32_t FS, int NEED_DST>
 __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
                                            int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
                                            uint32_t& n_covered, uint32_t& n_passed) {
-    const TriRec& t = sh.recs[slot];
+    const TriRec& t = sh.tile.recs[warp][slot];
     const int px0 = tile_px0 + (int)lane * kPx;
     const int xa = max(t.minx, tile_px0), xb = min(t.maxx, tile_px0 + kTileW - 1);
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
+    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][lane * kPx]);
     float depth[kPx] = {dq.x, dq.y, dq.z, dq.w};
     uint4 cq = make_uint4(0u, 0u, 0u, 0u);
-    if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);
+    if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][lane * kPx]);
     uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
     uint32_t live, zwrite;
     span_quad<FS, NEED_DST, kPx>(p, t, sh.unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
                             n_passed);
     if (zwrite) {
-        *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        atomicOr(&sh.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
+        *reinterpret_cast<float4*>(&sh.tile.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
+        atomicOr(&sh.tile.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
     }
     if (live) {
-        *reinterpret_cast<uint4*>(&sh.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
-        atomicOr(&sh.color_dirty[warp][lane >> 3], live << ((lane & 7u) * 4u));
+        *reinterpret_cast<uint4*>(&sh.tile.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
+        atomicOr(&sh.tile.color_dirty[warp][lane >> 3], live << ((lane & 7u) * 4u));
     }
     __syncwarp();
 }
@@ -1048,8 +1013,8 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
 // for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
 // time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
 // Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
-// One chunk of a row's work: lane j holds (have, my_slot) = the j-th triangle of the chunk whose bounding box contains
-// row py, slots in primitive order.  Candidate pixels of all 32 spans are streamed 32 per step whatever triangle they
+// One chunk of a row's work: lane j holds (have, my_slot) = the j-th triangle of the chunk (its record is in the
+// row's private sh.tile.recs[warp][my_slot]); every triangle's bounding box contains row py; slots are in primitive order.  Candidate pixels of all 32 spans are streamed 32 per step whatever triangle they
 // belong to; covered fragments go to the warp's queue and are shaded in full batches of 32.
 template <uint32_t FS, int NEED_DST>
 __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, bool have,
@@ -1059,7 +1024,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
     int xa = 0;
     uint32_t width = 0;
     if (have) {
-        const int2 xx = *reinterpret_cast<const int2*>(&sh.recs[my_slot]);  // minx maxx
+        const int2 xx = *reinterpret_cast<const int2*>(&sh.tile.recs[warp][my_slot]);  // minx maxx
         xa = max(xx.x, tile_px0);
         const int xb = min(xx.y, tile_px0 + kTileW - 1);
         width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
@@ -1071,7 +1036,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
         const bool narrow = width != 0 && width <= (uint32_t)kExactSpan;
         const uint32_t steps = __reduce_max_sync(0xffffffffu, narrow ? width : 0u);
         if (steps) {
-            const TriRec& t = sh.recs[my_slot];
+            const TriRec& t = sh.tile.recs[warp][my_slot];
             const int32_t sx = 16 * xa + 8;
             const uint32_t bias = t.bias_bits;
             long long f0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]) + (long long)(bias & 1u) - 1;
@@ -1122,7 +1087,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
         const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
         const int px = o_xa + (int)(c - o_excl);
         const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, pos);
-        const TriRec& t = sh.recs[slot];
+        const TriRec& t = sh.tile.recs[warp][slot];
         bool cov = false;
         float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
         if (active) {
@@ -1146,7 +1111,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
         if (!ballot) continue;
         if (cov) {  // append to my warp's fragment queue, keeping primitive order
             ++n_covered;
-            FragQueue& fq = sh.queue[warp];
+            FragQueue& fq = sh.tile.queue[warp];
             const uint32_t at = q_n + __popc(ballot & ((1u << lane) - 1u));
             fq.key[at] = (slot << 8) | (uint32_t)(px - tile_px0);
             fq.z[at] = z;
@@ -1157,9 +1122,9 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
         q_n += __popc(ballot);
         __syncwarp();
         if (q_n >= 32) {
-            shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+            n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color);
             // move the remainder (< 32 entries) to the front
-            FragQueue& fq = sh.queue[warp];
+            FragQueue& fq = sh.tile.queue[warp];
             const bool mv = lane < q_n - 32u;
             uint32_t k = 0;
             float fz = 0, f0 = 0, f1 = 0, f2 = 0;
@@ -1173,7 +1138,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
         if (wide_lane < 0) break;
         // a wide span: everything queued so far comes first, then the span itself, 4 pixels per lane
         if (q_n) {
-            shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+            n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
             q_n = 0;
         }
         shade_wide<FS, NEED_DST>(p, sh, warp, lane, __shfl_sync(0xffffffffu, my_slot, wide_lane), tile_px0, py, sy, depth_test, depth_write,
@@ -1185,7 +1150,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
 
 
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, kStages > 4 ? 3 : 4) raster_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1205,18 +1170,23 @@ __global__ void __launch_bounds__(kRasterThreads, kStages > 4 ? 3 : 4) raster_ke
         if (row_in && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
 
     // triangle source
-    uint32_t list_len = 0;
+    uint32_t list_len = 0, beg = 0;
     bool direct = true;
     if (p.binned) {
-        uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
+        beg = p.tile_offsets[tile];
+        const uint32_t end = p.tile_offsets[tile + 1];
         list_len = end - beg;
         if (list_len == 0) return;
         if (list_len <= (uint32_t)kSortCap && end <= p.bin_capacity) {
             direct = false;
             // load and sort the tile's triangle ids (ascending = primitive order)
-            for (uint32_t i = tid; i < list_len; i += kRasterThreads) sh.list[i] = p.bin_entries[beg + i];
+            for (uint32_t i = tid; i < list_len; i += kRasterThreads) sh.sort.list[i] = p.bin_entries[beg + i];
             __syncthreads();
-            sort_tile_list(sh, list_len);
+            const uint32_t* sorted = sort_tile_list(sh, list_len);
+            // the tile's segment of the bins is private to this CTA: the sorted list goes back in place and is streamed
+            // from there, which frees the sort's shared memory for the tile state
+            for (uint32_t i = tid; i < list_len; i += kRasterThreads) p.bin_entries[beg + i] = sorted[i];
+            __syncthreads();
         } else if (p.stats && tid == 0) {
             atomicAdd(&p.stats[7], 1ull);
         }
@@ -1231,229 +1201,118 @@ __global__ void __launch_bounds__(kRasterThreads, kStages > 4 ? 3 : 4) raster_ke
     }
     if (NEED_DST && quad_clip && has_color) {
         if (vec_ok && (p.color_base & 15ull) == 0) {
-            *reinterpret_cast<uint4*>(&sh.color[warp][lane * kPx]) = *reinterpret_cast<const uint4*>(caddr);
+            *reinterpret_cast<uint4*>(&sh.tile.color[warp][lane * kPx]) = *reinterpret_cast<const uint4*>(caddr);
         } else {
 #pragma unroll
             for (int k = 0; k < kPx; ++k)
-                if (quad_clip >> k & 1u) sh.color[warp][lane * kPx + k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+                if (quad_clip >> k & 1u) sh.tile.color[warp][lane * kPx + k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
         }
     }
     if (depth_test && quad_clip) {
         if (vec_ok && (p.depth_base & 15ull) == 0) {
-            *reinterpret_cast<float4*>(&sh.depth[warp][lane * kPx]) = *reinterpret_cast<const float4*>(daddr);
+            *reinterpret_cast<float4*>(&sh.tile.depth[warp][lane * kPx]) = *reinterpret_cast<const float4*>(daddr);
         } else {
 #pragma unroll
             for (int k = 0; k < kPx; ++k)
-                if (quad_clip >> k & 1u) sh.depth[warp][lane * kPx + k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+                if (quad_clip >> k & 1u) sh.tile.depth[warp][lane * kPx + k] = *reinterpret_cast<const float*>(daddr + 4 * k);
         }
     }
     if (lane < kTileW / 32) {
-        sh.color_dirty[warp][lane] = 0;
-        sh.depth_dirty[warp][lane] = 0;
+        sh.tile.color_dirty[warp][lane] = 0;
+        sh.tile.depth_dirty[warp][lane] = 0;
     }
     if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
-    if (tid < kStages) {
-        mbar_init(&sh.full[tid], 1);
-        sh.done[tid] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    fence_proxy_async();  // the sort wrote the record area through the generic proxy; bulk copies land there next
     __syncthreads();
 
     const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
     uint32_t n_covered = 0, n_passed = 0;
     uint32_t q_n = 0;  // fragments waiting in my warp's queue (warp-uniform)
 
-    if (!direct) {
-        // ---- binned tiles: the sorted list streams through a ring of kStages stages x 32 records.  Records arrive by
-        // bulk async copy (one 144-byte cp.async.bulk per record, mbarrier complete_tx), kStages rounds ahead of the
-        // slowest row; there is no CTA-wide barrier: every row warp runs at its own pace and is at most kStages rounds
-        // ahead of the slowest.  A warp keeps the slots of the triangles that touch its row in a pending list and works
-        // on them 32 at a time (full chunks whatever the density); it releases a round when neither its pending list
-        // nor its fragment queue refers to it any more, and the last row to release a round refills the stage with
-        // round + kStages.
-        const uint32_t n_rounds = (list_len + 31u) / 32u;
-        const uint32_t n_part = (uint32_t)(min(p.cy1, tile_py0 + kTileH - 1) - max(p.cy0, tile_py0) + 1);  // rows taking part
-        auto refill = [&](uint32_t stage, uint32_t round) {  // whole warp
-            const uint32_t first = round * 32u;
-            const uint32_t cnt = min(32u, list_len - first);
-            if (lane == 0) mbar_expect_tx(&sh.full[stage], cnt * (uint32_t)sizeof(TriRec));
-            __syncwarp();
-            if (lane < cnt)
-                bulk_g2s(&sh.recs[stage * 32u + lane], &p.tris[sh.list[first + lane]], (uint32_t)sizeof(TriRec), &sh.full[stage]);
-        };
-        if (warp < (uint32_t)kStages && warp < n_rounds) refill(warp, warp);
-        if (row_in) {
-            uint8_t* pend = sh.row_list[warp];
-            uint32_t pend_n = 0;   // < 32 between rounds
-            uint32_t released = 0;  // rounds below this one are released by me
-            auto release_to = [&](uint32_t upto) {
-                for (; released < upto; ++released) {
-                    const uint32_t stage = released % (uint32_t)kStages;
-                    __syncwarp();  // every lane's reads of the stage are done
-                    uint32_t last = 0;
-                    if (lane == 0) {
-                        __threadfence_block();
-                        last = atomicAdd(&sh.done[stage], 1u) == n_part - 1u;
-                        if (last) sh.done[stage] = 0;
-                    }
-                    last = __shfl_sync(0xffffffffu, last, 0);
-                    if (last && released + (uint32_t)kStages < n_rounds) {
-                        __threadfence_block();
-                        fence_proxy_async();
-                        refill(stage, released + (uint32_t)kStages);
-                    }
-                }
-            };
-            auto round_of = [&](uint32_t slot, uint32_t newest) {  // the round a referenced slot belongs to
-                return newest - ((newest - (slot >> 5)) & (uint32_t)(kStages - 1));
-            };
-            auto drain_queue = [&]() {
-                if (q_n) {
-                    shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
-                    q_n = 0;
-                }
-            };
-            for (uint32_t k = 0; k < n_rounds; ++k) {
-                const uint32_t stage = k % (uint32_t)kStages;
-                if (released + (uint32_t)kStages <= k) {
-                    // round k lands where round k - kStages is, which my leftovers still pin: finish them first
-                    if (pend_n) {
-                        const bool have = lane < pend_n;
-                        raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? pend[lane] : 0u, tile_px0, py, sy, depth_test,
-                                                   depth_write, has_color, q_n, n_covered, n_passed);
-                        pend_n = 0;
-                    }
-                    drain_queue();
-                    release_to(k);
-                }
-                mbar_wait(&sh.full[stage], (k / (uint32_t)kStages) & 1u);
-                // which of the round's records touch my row?
-                const uint32_t cnt = min(32u, list_len - k * 32u);
-                bool hit = false;
-                if (lane < cnt) {
-                    const int2 yy = *reinterpret_cast<const int2*>(&sh.recs[stage * 32u + lane].miny);  // miny maxy (scissored)
-                    hit = py >= yy.x && py <= yy.y;
-                }
+    // ---- my row: every row warp streams the tile's whole triangle list on its own; there is no CTA-wide barrier from
+    // here on.  Mesh order and screen position go together, so at any list position only a few rows of a tile have work:
+    // lock-stepped rounds of staged records left most warps waiting (37 % of all stall samples at the round barrier).
+    // Lanes test 4 x 32 packed pixel boxes per step (8 bytes per triangle, coalesced for mesh-ordered ids; the next
+    // step's ids are in flight meanwhile); the ids that touch my row collect in a pending list and are rasterised 32 at
+    // a time, so chunks are full whatever the density.  A chunk's 32 records are copied to the warp's private slots in
+    // shared memory first (one L2 round trip per chunk, 9 x 16 bytes per lane).
+    if (row_in) {
+        uint32_t* pend = sh.tile.pend[warp];
+        uint32_t pend_n = 0;
+        const uint32_t* ids = p.bin_entries + beg;
+        auto load_id = [&](uint32_t i) { return i < n_source ? (direct ? i : ids[i]) : 0xffffffffu; };
+        auto load_box = [&](uint32_t id) { return id != 0xffffffffu ? __ldg(&p.boxes[id]) : make_uint2(1u, 1u); };  // 1 > 0: empty
+        const uint32_t n_steps = (n_source + 31u) / 32u;
+        // software pipeline of the filter: ids three steps ahead, boxes two steps ahead
+        uint32_t id0 = load_id(lane), id1 = load_id(32u + lane), id2 = load_id(64u + lane);
+        uint2 box0 = load_box(id0), box1 = load_box(id1);
+        uint32_t step = 0;
+        const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
+        for (;;) {
+            while (pend_n < 32u && step < n_steps) {
+                const int minx = (int)(box0.x & 0xffffu), maxx = (int)(box0.x >> 16);
+                const int miny = (int)(box0.y & 0xffffu), maxy = (int)(box0.y >> 16);
+                const bool hit = minx <= maxx && py >= miny && py <= maxy && minx <= tile_px0 + kTileW - 1 && maxx >= tile_px0;
                 const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = (uint8_t)(stage * 32u + lane);
+                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = id0;
                 pend_n += __popc(b);
-                __syncwarp();
-                if (pend_n >= 32u) {
-                    raster_chunk<FS, NEED_DST>(p, sh, warp, lane, true, pend[lane], tile_px0, py, sy, depth_test, depth_write, has_color,
-                                               q_n, n_covered, n_passed);
-                    const bool mv = lane < pend_n - 32u;
-                    const uint8_t v = mv ? pend[32u + lane] : (uint8_t)0;
-                    __syncwarp();
-                    if (mv) pend[lane] = v;
-                    pend_n -= 32u;
-                    __syncwarp();
-                }
-                // release every round that neither the pending list nor the fragment queue refers to (both are FIFO)
-                uint32_t oldest = k + 1u;
-                if (pend_n) oldest = round_of(pend[0], k);
-                if (q_n) oldest = min(oldest, round_of(sh.queue[warp].key[0] >> 8, k));
-                release_to(oldest);
+                id0 = id1;
+                box0 = box1;
+                id1 = id2;
+                box1 = load_box(id1);
+                ++step;
+                id2 = load_id((step + 2u) * 32u + lane);
             }
-            if (pend_n) {
-                const bool have = lane < pend_n;
-                raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? pend[lane] : 0u, tile_px0, py, sy, depth_test, depth_write,
-                                           has_color, q_n, n_covered, n_passed);
-            }
-            drain_queue();
-        }
-    }
-
-    // overflow tiles (list longer than kSortCap, or the bins overflowed): walk every triangle of the draw in rounds
-    for (uint32_t base = 0; direct && base < n_source; base += kRecs) {
-        // ---- stage up to kRecs triangle records that touch this tile, in primitive order ----
-        uint32_t n_round;
-        if (direct) {
-            // candidates base .. base+kRecs-1: bbox test, order-preserving compaction
-            bool hit = false;
-            uint32_t cand = base + tid;
-            if (tid < kRecs && cand < n_source) {
-                int4 bb = *reinterpret_cast<const int4*>(&p.tris[cand]);
-                hit = bb.x <= bb.y && bb.x <= tile_px0 + kTileW - 1 && bb.y >= tile_px0 && bb.z <= tile_py0 + kTileH - 1 &&
-                      bb.w >= tile_py0;
-            }
-            uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) sh.warp_counts[warp] = __popc(ballot);
-            __syncthreads();
-            uint32_t offset = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kRecs / 32; ++w) {
-                uint32_t c = sh.warp_counts[w];
-                if ((uint32_t)w < warp) offset += c;
-                total += c;
-            }
-            if (hit) sh.list[offset + __popc(ballot & ((1u << lane) - 1u))] = cand;
-            n_round = total;
-            __syncthreads();
-        } else {
-            n_round = min((uint32_t)kRecs, n_source - base);
-        }
-        if (n_round == 0) continue;  // uniform across the CTA
-        {
-            const uint32_t* ids = direct ? sh.list : sh.list + base;
-            for (uint32_t q = tid; q < n_round * 9u; q += kRasterThreads) {
-                uint32_t r = q / 9u, part = q - r * 9u;
-                reinterpret_cast<uint4*>(&sh.recs[r])[part] = reinterpret_cast<const uint4*>(&p.tris[ids[r]])[part];
-            }
-        }
-        __syncthreads();
-
-        // ---- my row: stream the candidate pixels of the staged triangles, 32 per step; covered ones are queued ----
-        if (row_in) {
-            // the staged triangles whose bounding box contains my row, compacted in primitive order: with small
-            // triangles only a fraction of a tile's list touches any one row, and the chunks below stay full
-            uint32_t n_mine = 0;
-            for (uint32_t c = 0; c < n_round; c += 32) {
-                bool hit = false;
-                if (c + lane < n_round) {
-                    const int2 yy = *reinterpret_cast<const int2*>(&sh.recs[c + lane].miny);  // miny maxy (already scissored)
-                    hit = py >= yy.x && py <= yy.y;
-                }
-                const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                if (hit) sh.row_list[warp][n_mine + __popc(b & ((1u << lane) - 1u))] = (uint8_t)(c + lane);
-                n_mine += __popc(b);
-            }
-            __syncwarp();
-            for (uint32_t chunk = 0; chunk < n_mine; chunk += 32) {
-                const bool have = chunk + lane < n_mine;
-                raster_chunk<FS, NEED_DST>(p, sh, warp, lane, have, have ? sh.row_list[warp][chunk + lane] : 0u, tile_px0, py, sy,
-                                           depth_test, depth_write, has_color, q_n, n_covered, n_passed);
-            }
-            // the staged records go away at the end of the round: drain the queue
-            if (q_n) {
-                shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color, n_passed);
+            if (pend_n == 0) break;
+            const uint32_t n = min(pend_n, 32u);
+            if (q_n) {  // fragments still queued refer to the records that are about to be replaced
+                n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
                 q_n = 0;
             }
+            __syncwarp();
+            // the chunk's records: global -> my warp's slots, 9 x 16 bytes per lane, asynchronous copies (LDGSTS, no registers)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const uint32_t q = lane + 32u * i, r = q / 9u;
+                if (r < n) {
+                    const uint4* src = reinterpret_cast<const uint4*>(&p.tris[pend[r]]) + (q - 9u * r);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
+                                       n_covered, n_passed);
+            const bool mv = lane + 32u < pend_n;
+            const uint32_t v = mv ? pend[32u + lane] : 0u;
+            __syncwarp();
+            if (mv) pend[lane] = v;
+            pend_n -= n;
+            __syncwarp();
         }
-        __syncthreads();  // before the next round overwrites recs / list
+        if (q_n) n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
     }
 
     // ---- tile epilogue: each lane writes back its 4 pixels of the row where they changed ----
     __syncwarp();
     if (quad_clip) {
-        const uint32_t cd = (sh.color_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
-        const uint32_t dd = (sh.depth_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
+        const uint32_t cd = (sh.tile.color_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
+        const uint32_t dd = (sh.tile.depth_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
         if (cd) {
             if (cd == 15u && vec_ok && (p.color_base & 15ull) == 0) {
-                *reinterpret_cast<uint4*>(caddr) = *reinterpret_cast<const uint4*>(&sh.color[warp][lane * kPx]);
+                *reinterpret_cast<uint4*>(caddr) = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][lane * kPx]);
             } else {
 #pragma unroll
                 for (int k = 0; k < kPx; ++k)
-                    if (cd >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = sh.color[warp][lane * kPx + k];
+                    if (cd >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = sh.tile.color[warp][lane * kPx + k];
             }
         }
         if (dd) {
             if (dd == 15u && vec_ok && (p.depth_base & 15ull) == 0) {
-                *reinterpret_cast<float4*>(daddr) = *reinterpret_cast<const float4*>(&sh.depth[warp][lane * kPx]);
+                *reinterpret_cast<float4*>(daddr) = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][lane * kPx]);
             } else {
 #pragma unroll
                 for (int k = 0; k < kPx; ++k)
-                    if (dd >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = sh.depth[warp][lane * kPx + k];
+                    if (dd >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = sh.tile.depth[warp][lane * kPx + k];
             }
         }
     }
@@ -1478,6 +1337,8 @@ __global__ void __launch_bounds__(kRasterThreads, kStages > 4 ? 3 : 4) raster_ke
 struct KznRasterScratch {
     TriRec* tris = nullptr;
     size_t tri_capacity = 0;
+    uint2* boxes = nullptr;  // packed pixel boxes, one per record
+    size_t box_capacity = 0;
     uint32_t* tile_words = nullptr;  // counts | offsets | cursor
     size_t tile_capacity = 0;
     uint32_t* bin_entries = nullptr;
@@ -1490,6 +1351,7 @@ struct KznRasterScratch {
 void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     if (!s) return;
     cudaFree(s->tris);
+    cudaFree(s->boxes);
     cudaFree(s->tile_words);
     cudaFree(s->bin_entries);
     cudaFree(s->counters);
@@ -1591,6 +1453,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     }
     KznRasterScratch* s = q->raster;
     if ((r = grow(q, &s->tris, &s->tri_capacity, total))) return r;
+    if ((r = grow(q, &s->boxes, &s->box_capacity, total))) return r;
     if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
     if (binned) {
         if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
@@ -1625,6 +1488,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     make_clip(fb, vp, sc, W, H, &p);
     uint64_t ntri = count / 3, total = ntri * instance_count;
     if (total == 0 || p.cx1 < p.cx0) return KZN_SUCCESS;
+    KZN_REQUIRE(p.cx1 <= 65535 && p.cy1 <= 65535, KZN_ERROR_FEATURE_NOT_PRESENT,
+                "draw: render area reaches beyond pixel 65535 (pixel boxes are packed into 16 bits per coordinate)");
     KZN_REQUIRE(total <= 0x7fffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: more than 2^31 triangles in one draw");
 
     p.vertex_base = vi->buffer_address;
@@ -1669,6 +1534,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     if ((r = ensure_scratch(q, (size_t)total, tiles, p.binned != 0))) return r;
     KznRasterScratch* s = q->raster;
     p.tris = s->tris;
+    p.boxes = s->boxes;
     p.work_counter = s->counters;
     {
         static const bool exact = [] {
