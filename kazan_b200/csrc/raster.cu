@@ -43,6 +43,9 @@ constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows 
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
 constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
+#ifndef KZN_RASTER_CTAS
+#define KZN_RASTER_CTAS 3
+#endif
 constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -429,6 +432,9 @@ struct TileState {  // live from the tile prologue to the epilogue
     float depth[kTileH][kTileW];
     uint32_t color_dirty[kTileH][kTileW / 32];
     uint32_t depth_dirty[kTileH][kTileW / 32];
+#ifdef KZN_PAD_SMEM
+    unsigned char pad[KZN_PAD_SMEM];  // occupancy experiments
+#endif
 };
 struct SortScratch {  // live only while the tile's id list is sorted (before the prologue); the result goes back to global memory
     uint32_t list[kSortCap];
@@ -1150,7 +1156,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
 
 
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, 4) raster_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
