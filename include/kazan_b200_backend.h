@@ -51,6 +51,14 @@ KZN_API void kzn_free(void* ptr);
 KZN_API KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, const char* entry_point,
                                             uint32_t execution_model, KznIrModule** module, uint32_t local_size[3]);
 
+/* ---- SPIR-V reader (spirv-parser crate: Parser::start / iteration / Display, spirv-parser/src/lib.rs:26-44) --------- */
+/* Parses a SPIR-V module and writes its disassembly in the reference's text format: "; SPIR-V / ; Version / ; Generator
+ * / ; Bound / ; Schema" header lines, then one line per instruction ("%id = " right-aligned in 15 columns, operands,
+ * " ; 0x%08x" byte offset).  Reproduces the reference's goldens for test_inputs/test{,2,3}.spv byte for byte
+ * (spirv-parser/src/lib.rs:46-215).  Malformed input returns KZN_ERROR_VALIDATION_FAILED with the reference's message in
+ * kzn_last_error().  *text is malloc()ed, release with kzn_free. */
+KZN_API KznResult kzn_spirv_disassemble(const uint32_t* words, size_t word_count, char** text, size_t* length);
+
 /* ---- IR -> PTX ------------------------------------------------------------------------------------------------------ */
 /* PTX text for sm_100a of the module's entry point; needs no GPU.  *ptx is malloc()ed, release with kzn_free. */
 KZN_API KznResult kzn_ptx_from_ir(const KznIrModule* module, char** ptx, size_t* length);

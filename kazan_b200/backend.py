@@ -71,6 +71,14 @@ def translate_spirv_to_ir(words: Sequence[int], entry_point: str, execution_mode
     return IrModule(h), tuple(ls)
 
 
+def disassemble_spirv(words: Sequence[int]) -> str:
+    """spirv-parser's parse-and-dump (spirv-parser/src/lib.rs:26-44): header block + one line per instruction."""
+    arr = (abi.u32 * len(words))(*words)
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(load_library().kzn_spirv_disassemble(arr, len(words), C.byref(out), C.byref(n)))
+    return _take_text(out, n)
+
+
 class ComputePipeline:
     def __init__(self, device: Device, module: IrModule, local_size=(1, 1, 1)):
         self._lib, self.device = load_library(), device

@@ -405,6 +405,16 @@ KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, co
     });
 }
 
+KznResult kzn_spirv_disassemble(const uint32_t* words, size_t word_count, char** text, size_t* length) {
+    KZN_VALID(words && text, "kzn_spirv_disassemble: null argument");
+    *text = nullptr;
+    return guarded([&] {
+        *text = dup_text(kir::disassemble_spirv(words, word_count), length);
+        KZN_REQUIRE(*text, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
 KznResult kzn_ptx_from_ir(const KznIrModule* module, char** ptx, size_t* length) {
     KZN_VALID(module && ptx, "kzn_ptx_from_ir: null argument");
     *ptx = nullptr;
