@@ -351,17 +351,13 @@ __device__ __forceinline__ float clamp01(float f) { return __saturatef(f); }  //
 __device__ __forceinline__ float unorm8_to_float(uint32_t u) { return __fdiv_rn((float)u, 255.0f); }
 __device__ __forceinline__ uint32_t float_to_unorm8(float f) { return __float2uint_rn(clamp01(f) * 255.0f); }
 
+// VkCompareOp 0..7 = {NEVER, LESS, EQUAL, LESS_OR_EQUAL, GREATER, NOT_EQUAL, GREATER_OR_EQUAL, ALWAYS}: bit 0 = "less passes",
+// bit 1 = "equal passes", bit 2 = "greater passes"; an unordered pair (NaN in the depth buffer) passes NOT_EQUAL and ALWAYS
+// only.  Branch-free form of the oracle's switch (oracle/raster.c depth_compare), same truth table.
 __device__ __forceinline__ bool depth_compare(uint32_t op, float z, float zs) {
-    switch (op) {
-    case 0: return false;
-    case 1: return z < zs;
-    case 2: return z == zs;
-    case 3: return z <= zs;
-    case 4: return z > zs;
-    case 5: return z != zs;
-    case 6: return z >= zs;
-    default: return true;
-    }
+    const bool lt = z < zs, eq = z == zs, gt = z > zs;
+    const bool un = !(lt || eq || gt);
+    return ((op & 1u) && lt) || ((op & 2u) && eq) || ((op & 4u) && gt) || (un && (op == 5u || op == 7u));
 }
 
 // VkBlendFactor 0..9 = {ZERO, ONE, SRC_COLOR, 1-SRC_COLOR, DST_COLOR, 1-DST_COLOR, SRC_ALPHA, 1-SRC_ALPHA, DST_ALPHA,
@@ -419,6 +415,10 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 
 // ---- raster ------------------------------------------------------------------------------------------------------------
 
+// 4 flag bits <-> 4 flag bytes (0 / 1) of a lane's pixel quad
+__device__ __forceinline__ uint32_t bits_to_bytes(uint32_t m) { return (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21); }
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); }
+
 struct FragQueue {  // covered fragments of one row waiting for a full 32-lane shading batch, in primitive order
     uint32_t key[64];  // slot of the triangle in the row's chunk << 8 | x within the tile
     float z[64], l0[64], l1[64], l2[64];
@@ -430,8 +430,8 @@ struct TileState {  // live from the tile prologue to the epilogue
     uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
     uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
     float depth[kTileH][kTileW];
-    uint32_t color_dirty[kTileH][kTileW / 32];
-    uint32_t depth_dirty[kTileH][kTileW / 32];
+    uint8_t color_dirty[kTileH][kTileW];  // one byte per pixel (plain stores: a row belongs to one warp), 4 per lane
+    uint8_t depth_dirty[kTileH][kTileW];
 #ifdef KZN_PAD_SMEM
     unsigned char pad[KZN_PAD_SMEM];  // occupancy experiments
 #endif
@@ -636,7 +636,7 @@ __device__ __noinline__ uint32_t shade_fragments(const DrawParams& p, RasterShar
                 ++n_passed;
                 if (depth_write) {
                     sh.tile.depth[warp][kx] = z;
-                    atomicOr(&sh.tile.depth_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                    sh.tile.depth_dirty[warp][kx] = 1;
                 }
                 if (has_color) {
                     if (max_rank == 0 && depth_test) {  // one fragment per pixel: shade only what passed the depth test
@@ -651,7 +651,7 @@ __device__ __noinline__ uint32_t shade_fragments(const DrawParams& p, RasterShar
                     }
                     const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
                     sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                    atomicOr(&sh.tile.color_dirty[warp][kx >> 5], 1u << (kx & 31u));
+                    sh.tile.color_dirty[warp][kx] = 1;
                 }
             }
         }
@@ -827,11 +827,11 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
                             n_passed);
     if (zwrite) {
         *reinterpret_cast<float4*>(&sh.tile.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        atomicOr(&sh.tile.depth_dirty[warp][lane >> 3], zwrite << ((lane & 7u) * 4u));
+        reinterpret_cast<uint32_t*>(sh.tile.depth_dirty[warp])[lane] |= bits_to_bytes(zwrite);
     }
     if (live) {
         *reinterpret_cast<uint4*>(&sh.tile.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
-        atomicOr(&sh.tile.color_dirty[warp][lane >> 3], live << ((lane & 7u) * 4u));
+        reinterpret_cast<uint32_t*>(sh.tile.color_dirty[warp])[lane] |= bits_to_bytes(live);
     }
     __syncwarp();
 }
@@ -1223,10 +1223,8 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
                 if (quad_clip >> k & 1u) sh.tile.depth[warp][lane * kPx + k] = *reinterpret_cast<const float*>(daddr + 4 * k);
         }
     }
-    if (lane < kTileW / 32) {
-        sh.tile.color_dirty[warp][lane] = 0;
-        sh.tile.depth_dirty[warp][lane] = 0;
-    }
+    reinterpret_cast<uint32_t*>(sh.tile.color_dirty[warp])[lane] = 0;  // my 4 pixels' flags
+    reinterpret_cast<uint32_t*>(sh.tile.depth_dirty[warp])[lane] = 0;
     if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
     __syncthreads();
 
@@ -1301,8 +1299,8 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
     // ---- tile epilogue: each lane writes back its 4 pixels of the row where they changed ----
     __syncwarp();
     if (quad_clip) {
-        const uint32_t cd = (sh.tile.color_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
-        const uint32_t dd = (sh.tile.depth_dirty[warp][lane >> 3] >> ((lane & 7u) * 4u)) & 15u & quad_clip;
+        const uint32_t cd = bytes_to_bits(reinterpret_cast<const uint32_t*>(sh.tile.color_dirty[warp])[lane]) & quad_clip;
+        const uint32_t dd = bytes_to_bits(reinterpret_cast<const uint32_t*>(sh.tile.depth_dirty[warp])[lane]) & quad_clip;
         if (cd) {
             if (cd == 15u && vec_ok && (p.color_base & 15ull) == 0) {
                 *reinterpret_cast<uint4*>(caddr) = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][lane * kPx]);

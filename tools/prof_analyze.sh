@@ -16,4 +16,4 @@ for i,h in enumerate(hdr):
         v=float([r[i] for r in rows[2:]][-1])
         if v>0.3: print('  stall',h.replace('smsp__average_warps_issue_stalled_','').replace('_per_issue_active.ratio',''),round(v,2))
 P
-python /root/repo/tools/sass_regions.py raster.disasm src_raster.csv raster_kernelILj0ELi2E 16200 /root/repo/kazan_b200/csrc/raster.cu 2>&1 | cut -c1-170 | head -${2:-40}
+python /root/repo/tools/sass_regions.py raster.disasm src_raster.csv raster_kernelILj0ELi2E ${3:-16200} /root/repo/kazan_b200/csrc/raster.cu 2>&1 | cut -c1-170 | head -${2:-40}
