@@ -46,6 +46,10 @@ constexpr int kSortCap = 4096;           // largest binned list sorted in shared
 #ifndef KZN_RASTER_CTAS
 #define KZN_RASTER_CTAS 3
 #endif
+#ifndef KZN_CHUNK_BUFFERS
+#define KZN_CHUNK_BUFFERS 1
+#endif
+constexpr int kChunkBuffers = KZN_CHUNK_BUFFERS;  // record slots per row warp = 32 x this (2: fragments queued from the last chunk stay valid)
 constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -425,7 +429,7 @@ struct FragQueue {  // covered fragments of one row waiting for a full 32-lane s
 };
 
 struct TileState {  // live from the tile prologue to the epilogue
-    TriRec recs[kTileH][32];          // per row: the records of the chunk being rasterised (private to the row's warp)
+    TriRec recs[kTileH][kChunkBuffers * 32];  // per row: the records of the chunks being rasterised (private to the row's warp)
     FragQueue queue[kTileH];
     uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
     uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
@@ -1156,7 +1160,12 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
 
 
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
+#ifdef KZN_RASTER_REGS
+__global__ void __maxnreg__(KZN_RASTER_REGS) raster_kernel(
+#else
+__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(
+#endif
+    const __grid_constant__ DrawParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1249,7 +1258,7 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
         // software pipeline of the filter: ids three steps ahead, boxes two steps ahead
         uint32_t id0 = load_id(lane), id1 = load_id(32u + lane), id2 = load_id(64u + lane);
         uint2 box0 = load_box(id0), box1 = load_box(id1);
-        uint32_t step = 0;
+        uint32_t step = 0, chunk_no = 0;
         const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
         for (;;) {
             while (pend_n < 32u && step < n_steps) {
@@ -1268,7 +1277,10 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             }
             if (pend_n == 0) break;
             const uint32_t n = min(pend_n, 32u);
-            if (q_n) {  // fragments still queued refer to the records that are about to be replaced
+            // chunks alternate between the warp's record buffers; fragments still queued from the chunk that used this
+            // buffer last (the queue is first-in first-out: look at its head) must be shaded before it is overwritten
+            const uint32_t buf = kChunkBuffers > 1 ? (chunk_no++ & 1u) * 32u : 0u;
+            if (q_n && (kChunkBuffers == 1 || ((sh.tile.queue[warp].key[0] >> 8) & 32u) == buf)) {
                 n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
                 q_n = 0;
             }
@@ -1279,12 +1291,12 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
                 const uint32_t q = lane + 32u * i, r = q / 9u;
                 if (r < n) {
                     const uint4* src = reinterpret_cast<const uint4*>(&p.tris[pend[r]]) + (q - 9u * r);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + (buf * 9u + q) * 16u), "l"(src) : "memory");
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
+            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, buf + lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
                                        n_covered, n_passed);
             const bool mv = lane + 32u < pend_n;
             const uint32_t v = mv ? pend[32u + lane] : 0u;
