@@ -137,8 +137,8 @@ __device__ __forceinline__ void fetch_vertex(const DrawParams& p, long long vidx
 
 __device__ __forceinline__ bool finite_f(float f) { return (f - f) == 0.0f; }
 
-__device__ __forceinline__ bool tile_range(const DrawParams& p, const TriRec* r, int& tx0, int& tx1, int& ty0, int& ty1) {
-    int4 bb = *reinterpret_cast<const int4*>(r);  // minx, maxx, miny, maxy
+__device__ __forceinline__ bool tile_range(const DrawParams& p, const int4 bb, int& tx0, int& tx1, int& ty0, int& ty1) {
+    // bb = minx, maxx, miny, maxy
     if (bb.x > bb.y) return false;
     tx0 = bb.x / kTileW - (int)p.tile_x0;
     tx1 = bb.y / kTileW - (int)p.tile_x0;
@@ -281,9 +281,13 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     if (in_range) {
         const uint4* src = reinterpret_cast<const uint4*>(&r);
         for (uint32_t inst = 0; inst < n_inst; ++inst) {
-            uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
+            // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
+            // degenerate, outside the clip rectangle or this GPU's band) needs no record
+            if (ok || !p.binned) {
+                uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
 #pragma unroll
-            for (int q = 0; q < 9; ++q) dst[q] = src[q];
+                for (int q = 0; q < 9; ++q) dst[q] = src[q];
+            }
             p.boxes[(size_t)inst * p.tris_per_instance + t] =
                 make_uint2((uint32_t)r.minx | ((uint32_t)r.maxx << 16), (uint32_t)r.miny | ((uint32_t)r.maxy << 16));
         }
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     }
     if (p.binned) {  // first binning pass fused here: count the tiles each triangle overlaps
         int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-        bool valid = in_range && tile_range(p, &r, tx0, tx1, ty0, ty1);
+        bool valid = in_range && tile_range(p, make_int4(r.minx, r.maxx, r.miny, r.maxy), tx0, tx1, ty0, ty1);
         bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
@@ -305,7 +309,12 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-    bool valid = t < p.total_tris && tile_range(p, &p.tris[t], tx0, tx1, ty0, ty1);
+    bool valid = false;
+    if (t < p.total_tris) {
+        const uint2 box = __ldg(&p.boxes[t]);  // minx | maxx << 16, miny | maxy << 16
+        valid = tile_range(p, make_int4((int)(box.x & 0xffffu), (int)(box.x >> 16), (int)(box.y & 0xffffu), (int)(box.y >> 16)), tx0, tx1,
+                           ty0, ty1);
+    }
     bin_emit<true>(p, valid, t, 1u, tx0, tx1, ty0, ty1);
 }
 
