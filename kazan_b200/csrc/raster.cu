@@ -278,19 +278,30 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     }
     // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
     const uint32_t n_inst = p.total_tris / p.tris_per_instance;
-    if (in_range) {
+    // The CTA's 256 records are contiguous in memory (36 KiB): they are transposed through shared memory and written
+    // with coalesced 16-byte stores (a thread writing its own 144 bytes makes 9 store instructions of 32 scattered
+    // sectors each: the LSU queue was the top stall of this kernel).
+    __shared__ uint4 stage[256 * 9];
+    __shared__ uint8_t keep[256];
+    {
         const uint4* src = reinterpret_cast<const uint4*>(&r);
-        for (uint32_t inst = 0; inst < n_inst; ++inst) {
-            // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
-            // degenerate, outside the clip rectangle or this GPU's band) needs no record
-            if (ok || !p.binned) {
-                uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + t]);
 #pragma unroll
-                for (int q = 0; q < 9; ++q) dst[q] = src[q];
-            }
+        for (int q = 0; q < 9; ++q) stage[threadIdx.x * 9 + q] = src[q];
+        // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
+        // degenerate, outside the clip rectangle or this GPU's band) needs no record
+        keep[threadIdx.x] = in_range && (ok || !p.binned);
+    }
+    __syncthreads();
+    const uint32_t block_first = blockIdx.x * 256u;
+    for (uint32_t inst = 0; inst < n_inst; ++inst) {
+        uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + block_first]);
+        for (uint32_t i = threadIdx.x; i < 256u * 9u; i += 256u)
+            if (keep[i / 9u]) dst[i] = stage[i];
+    }
+    if (in_range) {
+        for (uint32_t inst = 0; inst < n_inst; ++inst)
             p.boxes[(size_t)inst * p.tris_per_instance + t] =
                 make_uint2((uint32_t)r.minx | ((uint32_t)r.maxx << 16), (uint32_t)r.miny | ((uint32_t)r.maxy << 16));
-        }
         if (p.stats) {
             atomicAdd(&p.stats[0], (unsigned long long)n_inst);
             if (!ok) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
