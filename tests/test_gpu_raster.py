@@ -89,3 +89,31 @@ def test_draw_is_idempotent_for_opaque_state(gpu):
     a = sc.run_gpu(gpu)[0].tobytes()
     b = sc.run_gpu(gpu)[0].tobytes()
     assert a == b
+
+
+def test_render_area_limit_of_the_packed_pixel_boxes(gpu):
+    """Pixel boxes are packed into 16 bits per coordinate: a draw whose clip rectangle reaches beyond pixel
+    65535 is refused with FEATURE_NOT_PRESENT, and on the same 70000-pixel-wide image a scissor that ends at pixel 65535
+    renders exactly like the oracle — including triangles that straddle the scissor edge."""
+    from kazan_b200 import host
+    W, H = 70000, 3
+    rng = np.random.default_rng(65535)
+    tris = []
+    for k in range(300):  # > 256 triangles: the binned path; clustered around the right-hand scissor edge
+        cx = rng.uniform(65400.0, 65600.0) / W * 2.0 - 1.0
+        cy = rng.uniform(-1.0, 1.0)
+        for _ in range(3):
+            tris.append([cx + rng.uniform(-40, 40) / W * 2.0, cy + rng.uniform(-1.5, 1.5), rng.uniform(0, 1),
+                         *rng.uniform(0, 1, 4)])
+    verts = np.array(tris, dtype=np.float32)
+    too_far = util.Scene("beyond_65535", W, H, verts, state=util.pipeline_state(blend=util.ADDITIVE_BLEND))
+    with pytest.raises(host.KazanError) as e:
+        too_far.run_gpu(gpu)
+    assert e.value.code == abi.ERROR_FEATURE_NOT_PRESENT and "65535" in str(e.value)
+    ok = util.Scene("scissored_to_65535", W, H, verts, state=util.pipeline_state(blend=util.ADDITIVE_BLEND),
+                    scissor=abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(65536, H)))
+    oc, od, os_ = ok.run_oracle()
+    gc, gd, gs = ok.run_gpu(gpu)
+    assert os_.fragments_covered > 0 and gs.fragments_covered == os_.fragments_covered
+    assert gc.tobytes() == oc.tobytes() and gd.tobytes() == od.tobytes()
+    assert not gc.view(np.uint32)[:W * H].reshape(H, W)[:, 65536:].any()  # nothing right of the scissor

@@ -18,5 +18,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rast
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_mesh.csv python tools/prof_mesh.py > $OUT/ncu_mesh.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|setup_kernel|bin_' -s 4 -c 4 -f -o $OUT/prof_mesh python tools/prof_mesh.py > $OUT/ncu_mesh_full.log 2>&1
 # transfer kernels: full capture
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fill_|copy_bulk|box_kernel' -c 12 -f -o $OUT/prof_transfer python tools/prof_transfer.py > $OUT/ncu_transfer_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fill_|copy_bulk|box_kernel|merged_transfer' -c 16 -f -o $OUT/prof_transfer python tools/prof_transfer.py > $OUT/ncu_transfer_full.log 2>&1
+# the 8K / 4M-triangle frame: launch list
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches_8k.csv python tools/prof_8k.py > $OUT/ncu_8k.log 2>&1
 ls -la $OUT
