@@ -392,7 +392,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -514,7 +514,6 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — kazan_b200 has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
@@ -663,7 +662,7 @@ def run_ours(args):
                                 "traffic": roofline_traffic("raster_direct_kernel"), "peak_source": peak_src,
                                 "note": "4 B written per pixel (33 177 600 B per launch); not the binding resource of this shader"}
         if args.profile:
-            print(json.dumps(line))
+            emit(line)
             return 0
 
         # ---- CPU baseline (oracle port) + full-frame parity ----
@@ -690,14 +689,33 @@ def run_ours(args):
         if rank == 0:
             line.setdefault("extra", {})["split_frame_8k_4Mtri"] = sfx
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print while the bench runs (NCCL's version banner when
+    # NCCL_DEBUG is set, ...) goes to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
