@@ -699,8 +699,7 @@ __device__ __forceinline__ void orbit_cx(int px0, float inv_w, float2 cx[PX / 2]
 }
 
 template <int PX>
-__device__ __forceinline__ void fs_procedural_orbit_n(const float2 cx[PX / 2], int py, float inv_h, float rgba[PX][4]) {
-    float2 zx[PX / 2], zy[PX / 2];
+__device__ __forceinline__ void orbit_run(const float2 cx[PX / 2], int py, float inv_h, float2 zx[PX / 2], float2 zy[PX / 2]) {
     const float v = ((float)py + 0.5f) * inv_h;
     const float cys = fmaf(v, 2.0f, -1.0f);
     const float2 cy = make_float2(cys, cys);
@@ -723,6 +722,11 @@ __device__ __forceinline__ void fs_procedural_orbit_n(const float2 cx[PX / 2], i
             zy[k] = nzy;
         }
     }
+}
+template <int PX>
+__device__ __forceinline__ void fs_procedural_orbit_n(const float2 cx[PX / 2], int py, float inv_h, float rgba[PX][4]) {
+    float2 zx[PX / 2], zy[PX / 2];
+    orbit_run<PX>(cx, py, inv_h, zx, zy);
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
         const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
@@ -733,7 +737,28 @@ __device__ __forceinline__ void fs_procedural_orbit_n(const float2 cx[PX / 2], i
         rgba[k][3] = 1.0f;
     }
 }
-
+// The same fragment program with the opaque output merge (no blend, all channels written) folded in: PX packed RGBA8
+// words.  Each channel is the oracle's sequence clamp01 -> * 255.0f -> round to nearest even; the rounding is done by
+// adding 1.5 * 2^23 (every fp32 in [2^23, 2^24) is an integer, so the add rounds t in [0, 255] exactly like cvt.rni) and the
+// integer is the low byte of the sum's bit pattern.  Blue is added to 1.5 * 2^23 + 0xFF00 instead, which leaves 0xFF — the
+// alpha of this shader, 1.0 -> 255 — in the byte above it, so two byte permutes assemble the word: 3 FADD + 2 PRMT per
+// pixel where F2I + shifts + ors were 8 issue slots.
+template <int PX>
+__device__ __forceinline__ void fs_procedural_orbit_rgba8(const float2 cx[PX / 2], int py, float inv_h, uint32_t out[PX]) {
+    float2 zx[PX / 2], zy[PX / 2];
+    orbit_run<PX>(cx, py, inv_h, zx, zy);
+    const float kRound = 12582912.0f, kRoundAlpha = 12648192.0f;  // 1.5 * 2^23 (+ 0xFF00)
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
+        const float m = fmaf(x, x, y * y);
+        const float r = clamp01(0.25f * m), g = clamp01(fmaf(x, 0.5f, 0.5f)), b = clamp01(fmaf(y, 0.5f, 0.5f));
+        const uint32_t rb = __float_as_uint(__fadd_rn(__fmul_rn(r, 255.0f), kRound));
+        const uint32_t gb = __float_as_uint(__fadd_rn(__fmul_rn(g, 255.0f), kRound));
+        const uint32_t bb = __float_as_uint(__fadd_rn(__fmul_rn(b, 255.0f), kRoundAlpha));
+        out[k] = __byte_perm(__byte_perm(rb, gb, 0x4440), bb, 0x5410);  // [r, g] then [r, g, b, 0xFF]
+    }
+}
 template <int PX>
 __device__ __forceinline__ void fs_procedural_orbit_n(int px0, int py, float inv_w, float inv_h, float rgba[PX][4]) {
     float2 cx[PX / 2];
@@ -889,6 +914,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
     int cur_col = -1, tile_px0 = 0, px0 = 0;
     uint32_t quad_clip = 0;
     bool cvec = false, dvec = false;
+    bool col_whole = false;  // every lane's 8 pixels of this column are inside the clip rectangle and go out as vectors
     float2 cxp[kDirectPx / 2];
     uint32_t col[kDirectPx];
     float depth[kDirectPx];
@@ -914,6 +940,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
             const bool vec_ok = (p.fb_w & 3u) == 0 && px0 + kDirectPx <= (int)p.fb_w;
             cvec = vec_ok && (p.color_base & 15ull) == 0;
             dvec = vec_ok && (p.depth_base & 15ull) == 0;
+            col_whole = __all_sync(0xffffffffu, quad_clip == (1u << kDirectPx) - 1u && cvec);
             if (FS == KZN_FS_PROCEDURAL_ORBIT) orbit_cx<kDirectPx>(px0, p.inv_fb_w, cxp);
         }
         const int row0 = (int)(p.tile_y0 + (uint32_t)brow) * kDirectRows;
@@ -937,6 +964,29 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
             full = __ballot_sync(0xffffffffu, ok);
         }
         const int r_lo = max(row0, p.cy0), r_hi = min(row0 + kDirectRows - 1, p.cy1);
+        if (FS == KZN_FS_PROCEDURAL_ORBIT && NEED_DST == kDstNone) {
+            // The block is nothing but shader work when the LAST triangle of the draw covers it completely and opaquely
+            // (whatever earlier triangles produced is overwritten; statistics still need their fragments, so with
+            // statistics on this is limited to single-triangle draws) and the block lies inside the clip rectangle:
+            // four rows of orbit + packed conversion + two 16-byte stores per lane, no per-row bookkeeping.
+            const uint32_t last = p.total_tris - 1u;
+            if (last < 32u && (full >> last & 1u) && (last == 0u || !p.stats) && has_color && !p.color_tiled && col_whole &&
+                r_lo == row0 && r_hi == row0 + kDirectRows - 1) {
+                unsigned long long a = p.color_base + ((unsigned long long)row0 * p.fb_w + px0) * 4ull;
+#pragma unroll 1
+                for (int r = 0; r < kDirectRows; ++r, a += pitch) {
+                    uint32_t out[kDirectPx];
+                    fs_procedural_orbit_rgba8<kDirectPx>(cxp, row0 + r, p.inv_fb_h, out);
+#pragma unroll
+                    for (int h = 0; h < kDirectPx / 4; ++h)
+                        *reinterpret_cast<uint4*>(a + 16 * h) = make_uint4(out[4 * h], out[4 * h + 1], out[4 * h + 2], out[4 * h + 3]);
+                }
+                n_covered += (last + 1u) * kDirectPx * kDirectRows;  // last > 0 only without statistics
+                n_passed += (last + 1u) * kDirectPx * kDirectRows;
+                if (p.stats && lane == 0) atomicAdd(&p.stats[6], 1ull);
+                continue;
+            }
+        }
         unsigned long long caddr = 0, daddr = 0;
         if (has_color) caddr = p.color_tiled ? 0ull : p.color_base + ((unsigned long long)r_lo * p.fb_w + px0) * 4ull;
         if (has_depth) daddr = p.depth_base + ((unsigned long long)r_lo * p.fb_w + px0) * 4ull;
