@@ -174,6 +174,25 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
         ms = time_region(torch, stream, lambda k: queue.submit([cb_copy]), sub, 2)
         gcopy = 2 * nbytes * batch * sub / ms / 1e6
         cb_clear.destroy(); cb_copy.destroy()
+        variants = {}
+        if label in ("3840x2160", "7680x4320"):
+            # SURVEY.md §8d stress variants of the same copy (algorithmic bytes = 2 x 4 x extent; padding is not counted),
+            # recorded 8 per command buffer like the rows above: padded source pitch, sub-rectangle, bufferOffset 4
+            def recorded(regions, extent_bytes, buf_bytes, src_off=0):
+                big = [torch.empty(buf_bytes, dtype=torch.uint8, device="cuda") for _ in range(min(n_img, 8))]
+                with queue.record() as cb:
+                    for k in range(8):
+                        queue.cmd_copy_buffer_to_image(big[k % len(big)].data_ptr() + src_off, buf_bytes - src_off, imgs[k % n_img], regions)
+                ms_v = time_region(torch, stream, lambda k: queue.submit([cb]), max(3, sub), 2)
+                n_launch = cb.launch_count
+                cb.destroy()
+                return {"GBps": round(2 * extent_bytes * 8 * max(3, sub) / ms_v / 1e6, 1),
+                        "frac_hbm": round(2 * extent_bytes * 8 * max(3, sub) / ms_v / 1e6 / hbm_peak, 3), "launches_per_submit": n_launch}
+            pitch = w + 32
+            variants["padded_pitch"] = recorded([host.buffer_image_copy(w, h, row_length=pitch)], nbytes, pitch * h * 4)
+            variants["sub_rect"] = recorded([host.buffer_image_copy(w - 32, h - 16, row_length=w, offset=(16, 8, 0))],
+                                            (w - 32) * (h - 16) * 4, nbytes)
+            variants["buffer_offset_4"] = recorded([host.buffer_image_copy(w, h, buffer_offset=4)], nbytes, nbytes + 16)
         out[label] = {"clear_submit_GBps": round(gclear, 1), "clear_submit_frac_hbm": round(gclear / hbm_peak, 3),
                       "copy_b2i_submit_GBps": round(gcopy, 1), "copy_b2i_submit_frac_hbm": round(gcopy / hbm_peak, 3),
                       "commands_per_submit": batch, "launches_per_submit": launches_per_submit,
@@ -182,6 +201,8 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
                       "copy_b2i_GBps": round(copy, 1), "copy_b2i_frac_hbm": round(copy / hbm_peak, 3),
                       "copy_i2b_GBps": round(copy_back, 1), "copy_i2b_frac_hbm": round(copy_back / hbm_peak, 3),
                       "bytes": nbytes, "rotating_images": n_img, "reps": reps}
+        if variants:
+            out[label]["copy_b2i_variants_submit"] = variants
         del images, buffers
         torch.cuda.empty_cache()
     return out
@@ -497,6 +518,24 @@ def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, b
         queue.download(h.data_ptr(), ft.addresses[last], W * H * 4)
         queue.wait_idle()
         out["frame_checksum_rank0"] = int(h.sum(dtype=torch.int64).item())
+        # full-size parity of the composited frame: the oracle renders the same 4M-triangle scene in one piece
+        from oracle import binding as ob
+        lib = ob.load()
+        lib.kzo_set_threads(lib.kzo_hardware_threads())
+        ocolor = ob.aligned_empty(W * H * 4); ocolor[:] = 0
+        odepth = ob.aligned_empty(W * H * 4); odepth.view(np.float32)[:] = 1.0
+        ofb = abi.Framebuffer()
+        ofb.color = abi.ImageDesc(ob.ptr(ocolor), abi.FORMAT_R8G8B8A8_UNORM, 0, W, H, 1, 1, 1, 0)
+        ofb.depth = abi.ImageDesc(ob.ptr(odepth), abi.FORMAT_D32_SFLOAT, 0, W, H, 1, 1, 1, 0)
+        ovi = abi.VertexInput(ob.ptr(verts), verts.nbytes, 28, 0, 3, 12)
+        ostats = abi.DrawStatistics()
+        t0 = time.perf_counter()
+        code = lib.kzo_draw_indexed(C.byref(st), C.byref(ofb), C.byref(vp), C.byref(sc), C.byref(ovi), C.c_void_p(ob.ptr(idx)),
+                                    idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx), 1, 0, 0, 0, C.byref(ostats))
+        dt = time.perf_counter() - t0
+        same = code == 0 and bool(np.array_equal(h.numpy().view(np.uint8), ocolor[:W * H * 4]))
+        out["parity"] = (f"bit-exact colour vs oracle at full size ({world} band(s) composited)" if same else "MISMATCH vs oracle")
+        out["cpu_baseline"] = {"ms_per_frame": dt * 1e3, "cores": int(lib.kzo_hardware_threads()), "kind": "port"}
     ft.close()
     return out
 
