@@ -184,6 +184,48 @@ __global__ void __launch_bounds__(32) copy_bulk_kernel(uint8_t* __restrict__ dst
     bulk_wait_read<0>();
 }
 
+// ---- contiguous copy from a source that is only 4-byte aligned --------------------------------------------------
+
+// vkCmdCopyBufferToImage allows any bufferOffset that is a multiple of the texel size (4): the destination image row is
+// 16-byte aligned but the source is not.  Instead of falling back to 4-byte accesses, every lane loads the ALIGNED
+// 16-byte vector under its destination vector, takes the next one from its neighbour with four shuffles (lane 31 and
+// the end of the run load it themselves; the last, partial vector is read word by word so that nothing beyond the source
+// range is touched) and stores one realigned 16-byte vector.  shift = (src & 15) / 4 in {1, 2, 3}.
+__global__ void __launch_bounds__(kThreads) copy_realign_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t vecs) {
+    const uint32_t shift = (uint32_t)(((uintptr_t)src & 15u) >> 2);
+    const uint4* a_base = reinterpret_cast<const uint4*>((uintptr_t)src & ~(uintptr_t)15);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    const uint64_t first = (uint64_t)blockIdx.x * kThreads + (threadIdx.x & ~31u);  // my warp's first vector
+    for (uint64_t w0 = first; w0 < vecs; w0 += nthreads) {  // uniform per warp
+        const uint64_t i = w0 + lane;
+        const bool ok = i < vecs;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        if (ok) a = ld_stream16(a_base + i);
+        b.x = __shfl_down_sync(0xffffffffu, a.x, 1);
+        b.y = __shfl_down_sync(0xffffffffu, a.y, 1);
+        b.z = __shfl_down_sync(0xffffffffu, a.z, 1);
+        if (ok && (lane == 31u || i + 1 >= vecs)) {
+            if (i + 1 < vecs) {
+                const uint4 n = ld_stream16(a_base + i + 1);
+                b.x = n.x; b.y = n.y; b.z = n.z;
+            } else {  // the vector after the last one holds only `shift` valid words
+                const uint32_t* t = reinterpret_cast<const uint32_t*>(a_base + i + 1);
+                b.x = ld_stream4(t);
+                if (shift > 1) b.y = ld_stream4(t + 1);
+                if (shift > 2) b.z = ld_stream4(t + 2);
+            }
+        }
+        if (ok) {
+            uint4 v;
+            if (shift == 1) v = make_uint4(a.y, a.z, a.w, b.x);
+            else if (shift == 2) v = make_uint4(a.z, a.w, b.x, b.y);
+            else v = make_uint4(a.w, b.x, b.y, b.z);
+            st_stream16(dst + i, v);
+        }
+    }
+}
+
 // ---- merged contiguous fills / copies (command buffers) ----------------------------------------------------
 
 // Up to KZN_MAX_MERGED recorded commands as one launch.  Work is cut into 16 KiB units numbered across the commands
@@ -577,6 +619,15 @@ KznResult launch_box(KznQueue* q, const Box* src, const Box& dst, uint32_t w, ui
             KznResult mr;
             if (aligned && merge_transfer(q, p.dst.base, p.src.base, bytes, 0, &mr)) return mr;
             if (aligned && path == Path::Tma) return launch_copy_bulk(q, p.dst.base, p.src.base, bytes);
+            if (!aligned && p.dst.base % 16 == 0 && p.src.base % 16 != 0 && p.src.base % 4 == 0 && bytes % 16 == 0) {
+                KznResult fr = kzn_flush_transfers(q);
+                if (fr) return fr;
+                const uint64_t vecs = bytes / 16;
+                kzn_timing_begin(q);
+                copy_realign_kernel<<<grid_for(q, vecs * kUnroll), kThreads, 0, q->stream>>>(
+                    (uint4*)(uintptr_t)p.dst.base, (const uint32_t*)(uintptr_t)p.src.base, vecs);
+                return kzn_launched(q, "copy_realign_kernel");
+            }
         }
     }
     p.h = hh;

@@ -22,6 +22,10 @@ BUFFER_IMAGE_CASES = [
     ("subrect_16_8", dict(width=1024, height=1024),
      [buffer_image_copy(992, 1000, offset=(16, 8, 0))], 992 * 1000 * 4),
     ("misaligned_offset_4", dict(width=256, height=64), [buffer_image_copy(256, 64, buffer_offset=4)], 256 * 64 * 4 + 4),
+    # source 4 / 8 / 12 bytes off a 16-byte boundary, destination aligned: the realigning copy (transfer.cu
+    # copy_realign_kernel); 257 x 60 texels = 3855 vectors: a partial last warp and a partial tail vector
+    ("misaligned_offset_8", dict(width=256, height=64), [buffer_image_copy(256, 64, buffer_offset=8)], 256 * 64 * 4 + 8),
+    ("misaligned_offset_12_ragged", dict(width=257 * 4, height=15), [buffer_image_copy(257 * 4, 15, buffer_offset=12)], 257 * 4 * 15 * 4 + 12),
     ("odd_width_13", dict(width=13, height=7), [buffer_image_copy(13, 7)], 13 * 7 * 4),
     ("odd_subrect", dict(width=67, height=33), [buffer_image_copy(31, 17, offset=(5, 3, 0), row_length=40, image_height=20)],
      40 * 20 * 4),
