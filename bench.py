@@ -678,7 +678,13 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (raster_direct_kernel), its duration measured live with the library's
         # CUDA-event pair around that kernel on the launching stream ----
         with torch.cuda.stream(stream):
-            k_ms = kernel_ms(torch, queue, lambda k: queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3))
+            k_ms_events = kernel_ms(torch, queue, lambda k: queue.cmd_draw(st, fbs[k % n_targets], vp, sc, vi, 3))
+        # The draw's kernels are launched with programmatic dependent launch: in the timed region the raster kernel's
+        # launch latency is hidden behind setup_kernel, while an event pair recorded around it sits between the two kernels
+        # and brackets that latency too.  The kernel cannot take longer than the whole step (setup_kernel + raster kernel,
+        # back to back on one stream), so the smaller of the two is its duration (a lower bound on its rate when the step
+        # time is used).
+        k_ms = min(k_ms_events, ms_per_step)
         sec = k_ms / 1e3
         clk = clocks.summary()
         line["clocks"] = clk
@@ -692,7 +698,10 @@ def run_ours(args):
         issue = W * H * FP32_INSTR_PER_PIXEL / sec / 1e12
         line["roofline"] = {"bound": "fp32_issue", "achieved": issue, "peak": measured_issue, "unit": "Tinstr/s", "frac": issue / measured_issue,
                             "traffic": roofline_traffic("raster_direct_kernel"), "kernel": "raster_direct_kernel<ORBIT,0>",
-                            "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                            "kernel_ms": k_ms, "kernel_ms_event_pair": k_ms_events,
+                            "kernel_ms_source": ("event pair around the kernel" if k_ms_events <= ms_per_step else
+                                                 "step time: upper bound of the kernel's duration (the event pair also brackets the launch latency that programmatic dependent launch hides)"),
+                            "kernel_share_of_step": k_ms / ms_per_step,
                             "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL, "peak_source": "measured in this run: kzn_calibrate_fp32_issue (FFMA2 chains)",
                             "nominal_peak": nominal_issue, "frac_of_nominal": issue / nominal_issue, "sm_mhz": sm_mhz,
                             "note": "north_star: 'FP32 issue rate for shader-bound work'; the HBM side of the same kernel is `roofline_hbm`"}

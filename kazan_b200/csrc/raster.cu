@@ -102,6 +102,15 @@ struct DrawParams {
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
 };
 
+// Programmatic dependent launch: the kernels of a draw are launched with programmatic stream serialization, so the next
+// kernel's CTAs may be resident before the previous kernel has drained.  Every one of them starts with pdl_wait(), which
+// returns once the preceding kernel of the stream has completed and its writes are visible (a no-op for an ordinary
+// launch), and then allows its own successor to be staged.  What is saved is the launch gap between dependent kernels.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- setup ------------------------------------------------------------------------------------------------
 
 struct VsOut {
@@ -197,6 +206,7 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
 }
 
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
+    pdl_wait();
     const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
     if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
     const bool in_range = t_raw < p.tris_per_instance;
@@ -318,6 +328,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 
 // second binning pass: one thread per triangle record writes its id into every tile segment it overlaps
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
+    pdl_wait();
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
     bool valid = false;
@@ -331,6 +342,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
 
 // exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ DrawParams p) {
+    pdl_wait();
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     uint32_t tiles = p.tiles_x * p.tiles_y;
@@ -905,6 +917,7 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
 // is smallest; if all three are positive the whole block is inside the triangle and its rows skip coverage entirely.
 template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(const __grid_constant__ DrawParams p) {
+    pdl_wait();
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
     const uint32_t lane = threadIdx.x;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
@@ -1243,6 +1256,7 @@ __global__ void __maxnreg__(KZN_RASTER_REGS) raster_kernel(
 __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(
 #endif
     const __grid_constant__ DrawParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1569,6 +1583,26 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     return KZN_SUCCESS;
 }
 
+// Launch one kernel of a draw with programmatic stream serialization (see pdl_wait); KZN_PDL=0 in the environment
+// falls back to ordinary launches.
+void launch_draw_kernel(void (*kernel)(DrawParams), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const DrawParams& p) {
+    static const bool pdl = [] {
+        const char* e = getenv("KZN_PDL");
+        return !(e && e[0] == '0');
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, p);  // errors surface through kzn_launched (cudaGetLastError)
+}
+
 KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp,
                       const KznRect2D* sc, const KznVertexInput* vi, uint64_t index_base, uint32_t index_type, uint32_t first,
                       uint32_t count, int32_t vertex_offset, uint32_t instance_count) {
@@ -1645,12 +1679,12 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
 
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
-    setup_kernel<<<(uint32_t)((ntri + 255) / 256), 256, 0, q->stream>>>(p);
+    launch_draw_kernel(setup_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
     if ((r = kzn_launched(q, "setup_kernel"))) return r;
     if (p.binned) {
-        bin_scan_kernel<<<1, 1024, 0, q->stream>>>(p);
+        launch_draw_kernel(bin_scan_kernel, dim3(1), dim3(1024), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
-        bin_fill_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, q->stream>>>(p);
+        launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
@@ -1666,13 +1700,13 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
 #define KZN_RASTER_LAUNCH(KERNEL, THREADS, SMEM)                                                                      \
     do {                                                                                                     \
         if (orbit) {                                                                                         \
-            if (mode == kDstNone) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstNone><<<grid, THREADS, SMEM, q->stream>>>(p);             \
-            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver><<<grid, THREADS, SMEM, q->stream>>>(p); \
-            else KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric><<<grid, THREADS, SMEM, q->stream>>>(p);   \
+            if (mode == kDstNone) launch_draw_kernel(KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstNone>, grid, dim3(THREADS), SMEM, q->stream, p);             \
+            else if (mode == kDstAlphaOver) launch_draw_kernel(KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver>, grid, dim3(THREADS), SMEM, q->stream, p); \
+            else launch_draw_kernel(KERNEL<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric>, grid, dim3(THREADS), SMEM, q->stream, p);   \
         } else {                                                                                             \
-            if (mode == kDstNone) KERNEL<KZN_FS_VERTEX_COLOR, kDstNone><<<grid, THREADS, SMEM, q->stream>>>(p);                 \
-            else if (mode == kDstAlphaOver) KERNEL<KZN_FS_VERTEX_COLOR, kDstAlphaOver><<<grid, THREADS, SMEM, q->stream>>>(p);     \
-            else KERNEL<KZN_FS_VERTEX_COLOR, kDstGeneric><<<grid, THREADS, SMEM, q->stream>>>(p);       \
+            if (mode == kDstNone) launch_draw_kernel(KERNEL<KZN_FS_VERTEX_COLOR, kDstNone>, grid, dim3(THREADS), SMEM, q->stream, p);                 \
+            else if (mode == kDstAlphaOver) launch_draw_kernel(KERNEL<KZN_FS_VERTEX_COLOR, kDstAlphaOver>, grid, dim3(THREADS), SMEM, q->stream, p);     \
+            else launch_draw_kernel(KERNEL<KZN_FS_VERTEX_COLOR, kDstGeneric>, grid, dim3(THREADS), SMEM, q->stream, p);       \
         }                                                                                                    \
     } while (0)
     if (!p.binned) {  // a few triangles: register-resident rows, no staging; one warp per 256 x kDirectRows block
