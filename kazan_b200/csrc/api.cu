@@ -13,6 +13,8 @@
 #include <new>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "kzn_internal.h"
 
 // vulkan-driver/src/handle.rs:315 `CommandBuffer {}` (a placeholder upstream): here a CUDA graph captured from the queue's
@@ -188,6 +190,14 @@ const void* kzn_recorded_host_copy(KznQueue* q, const void* data, size_t size) {
     memcpy(copy, data, size);
     q->recording->host_copies.push_back(copy);
     return copy;
+}
+
+bool kzn_pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KZN_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 void kzn_timing_begin(KznQueue* q) {

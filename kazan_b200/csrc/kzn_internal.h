@@ -117,3 +117,30 @@ KznResult kzn_check_image(const KznImageDesc* im, const char* what);
 
 // E.1 on the host (used for the one-off clear colour conversion)
 uint32_t kzn_pack_rgba8_host(const float rgba[4]);
+
+#ifdef __CUDACC__
+// Programmatic dependent launch (used by the transfer and draw kernels): a kernel launched through kzn_launch_pdl may
+// become resident before the preceding kernel of the stream has drained; it must call kzn_pdl_wait() before it touches
+// memory.  The wait returns once that kernel has completed and its writes are visible (a no-op for an ordinary launch), so
+// in-order semantics are unchanged and only the launch gap between consecutive kernels is hidden.  KZN_PDL=0 in the
+// environment falls back to ordinary launches.
+__device__ __forceinline__ void kzn_pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool kzn_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void kzn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kzn_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through kzn_launched (cudaGetLastError)
+}
+#endif

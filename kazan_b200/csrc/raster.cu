@@ -102,15 +102,6 @@ struct DrawParams {
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
 };
 
-// Programmatic dependent launch: the kernels of a draw are launched with programmatic stream serialization, so the next
-// kernel's CTAs may be resident before the previous kernel has drained.  Every one of them starts with pdl_wait(), which
-// returns once the preceding kernel of the stream has completed and its writes are visible (a no-op for an ordinary
-// launch), and then allows its own successor to be staged.  What is saved is the launch gap between dependent kernels.
-__device__ __forceinline__ void pdl_wait() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
 // ---- setup ------------------------------------------------------------------------------------------------
 
 struct VsOut {
@@ -206,7 +197,7 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
 }
 
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
-    pdl_wait();
+    kzn_pdl_wait();
     const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
     if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
     const bool in_range = t_raw < p.tris_per_instance;
@@ -328,7 +319,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 
 // second binning pass: one thread per triangle record writes its id into every tile segment it overlaps
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
-    pdl_wait();
+    kzn_pdl_wait();
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
     bool valid = false;
@@ -342,7 +333,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
 
 // exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ DrawParams p) {
-    pdl_wait();
+    kzn_pdl_wait();
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     uint32_t tiles = p.tiles_x * p.tiles_y;
@@ -917,7 +908,7 @@ __device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh
 // is smallest; if all three are positive the whole block is inside the triangle and its rows skip coverage entirely.
 template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(const __grid_constant__ DrawParams p) {
-    pdl_wait();
+    kzn_pdl_wait();
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
     const uint32_t lane = threadIdx.x;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
@@ -1256,7 +1247,7 @@ __global__ void __maxnreg__(KZN_RASTER_REGS) raster_kernel(
 __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(
 #endif
     const __grid_constant__ DrawParams p) {
-    pdl_wait();
+    kzn_pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1583,24 +1574,9 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     return KZN_SUCCESS;
 }
 
-// Launch one kernel of a draw with programmatic stream serialization (see pdl_wait); KZN_PDL=0 in the environment
-// falls back to ordinary launches.
+// the kernels of a draw are launched with programmatic dependent launch (kzn_internal.h)
 void launch_draw_kernel(void (*kernel)(DrawParams), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const DrawParams& p) {
-    static const bool pdl = [] {
-        const char* e = getenv("KZN_PDL");
-        return !(e && e[0] == '0');
-    }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, p);  // errors surface through kzn_launched (cudaGetLastError)
+    kzn_launch_pdl(kernel, grid, block, smem, stream, p);
 }
 
 KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp,
