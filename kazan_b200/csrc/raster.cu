@@ -576,6 +576,28 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
     return a;  // the buffer holding the sorted ids
 }
 
+// VkLogicOp 0..15 on the UNORM8 bit patterns, all four channels at once (oracle/raster.c logic_op); the state is warp-uniform
+__device__ __forceinline__ uint32_t logic_op(uint32_t op, uint32_t s, uint32_t d) {
+    switch (op) {
+    case 0: return 0u;
+    case 1: return s & d;
+    case 2: return s & ~d;
+    case 3: return s;
+    case 4: return ~s & d;
+    case 5: return d;
+    case 6: return s ^ d;
+    case 7: return s | d;
+    case 8: return ~(s | d);
+    case 9: return ~(s ^ d);
+    case 10: return ~d;
+    case 11: return s | ~d;
+    case 12: return ~s;
+    case 13: return ~s | d;
+    case 14: return ~(s & d);
+    default: return 0xffffffffu;
+    }
+}
+
 // blend with the destination held as UNORM8 in shared memory; same operation order as oracle/raster.c output_merge
 template <int NEED_DST>
 __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineState& st, const float* lut, const float src[4],
@@ -597,6 +619,15 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
             out |= float_to_unorm8(t0 + t1) << (8 * ch);
         }
         return out;
+    }
+    if (st.logic_op) {  // logicOpEnable: no blending; the write mask still applies (kDstGeneric only)
+        uint32_t sw = 0, mask = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            sw |= float_to_unorm8(s[ch]) << (8 * ch);
+            if (st.color_write_mask & (1u << ch)) mask |= 0xffu << (8 * ch);
+        }
+        return (dst_word & ~mask) | (logic_op(st.logic_op - 1u, sw, dst_word) & mask);
     }
     if (st.blend_enable) {
         float d[4];
@@ -1487,6 +1518,7 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
                     st->dst_alpha_blend_factor <= 9,
                 KZN_ERROR_FEATURE_NOT_PRESENT, "draw: blend factor not supported (dualSrcBlend is FALSE, api_impl.rs:883)");
     KZN_VALID(st->color_blend_op <= 4 && st->alpha_blend_op <= 4, "draw: bad blend op");
+    KZN_VALID(st->logic_op <= 16, "draw: logic_op is 0 (disabled) or 1 + VkLogicOp");
     bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     KZN_VALID(has_color || has_depth, "draw: framebuffer has no attachment");
     if (has_color) {
@@ -1665,10 +1697,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     // the destination colour is only read when the result depends on it
-    const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u);
+    const bool need_dst = has_color && (st->blend_enable || (st->color_write_mask & 15u) != 15u || st->logic_op != 0);
     const size_t smem = sizeof(RasterShared);
     kzn_timing_begin(q);  // the raster kernel dominates a draw
-    const bool alpha_over = need_dst && st->blend_enable && (st->color_write_mask & 15u) == 15u && st->src_color_blend_factor == 6 &&
+    const bool alpha_over = need_dst && !st->logic_op && st->blend_enable && (st->color_write_mask & 15u) == 15u && st->src_color_blend_factor == 6 &&
                             st->dst_color_blend_factor == 7 && st->color_blend_op == 0 && st->src_alpha_blend_factor == 6 &&
                             st->dst_alpha_blend_factor == 7 && st->alpha_blend_op == 0;
     const int mode = !need_dst ? kDstNone : alpha_over ? kDstAlphaOver : kDstGeneric;

@@ -205,8 +205,38 @@ static float blend_op(uint32_t op, float cs, float sf, float cd, float df) {
     }
 }
 
+/* VkLogicOp 0..15 on the UNORM8 bit patterns (all four channels at once: the operations are bitwise) */
+static uint32_t logic_op(uint32_t op, uint32_t s, uint32_t d) {
+    switch (op) {
+    case 0: return 0u;            /* CLEAR */
+    case 1: return s & d;         /* AND */
+    case 2: return s & ~d;        /* AND_REVERSE */
+    case 3: return s;             /* COPY */
+    case 4: return ~s & d;        /* AND_INVERTED */
+    case 5: return d;             /* NO_OP */
+    case 6: return s ^ d;         /* XOR */
+    case 7: return s | d;         /* OR */
+    case 8: return ~(s | d);      /* NOR */
+    case 9: return ~(s ^ d);      /* EQUIVALENT */
+    case 10: return ~d;           /* INVERT */
+    case 11: return s | ~d;       /* OR_REVERSE */
+    case 12: return ~s;           /* COPY_INVERTED */
+    case 13: return ~s | d;       /* OR_INVERTED */
+    case 14: return ~(s & d);     /* NAND */
+    default: return 0xffffffffu;  /* SET */
+    }
+}
+
 static uint32_t output_merge(const KznGraphicsPipelineState* st, const float src_in[4], uint32_t dst_word) {
     float s[4], d[4], o[4];
+    if (st->logic_op) { /* logicOpEnable: blending is treated as disabled; the write mask still applies */
+        uint32_t sw = 0, mask = 0;
+        for (int ch = 0; ch < 4; ++ch) {
+            sw |= (uint32_t)kzo_float_to_unorm8(clamp01(src_in[ch])) << (8 * ch);
+            if (st->color_write_mask & (1u << ch)) mask |= 0xffu << (8 * ch);
+        }
+        return (dst_word & ~mask) | (logic_op(st->logic_op - 1u, sw, dst_word) & mask);
+    }
     for (int ch = 0; ch < 4; ++ch) {
         s[ch] = clamp01(src_in[ch]);
         d[ch] = kzo_unorm8_to_float((uint8_t)(dst_word >> (8 * ch)));
@@ -239,6 +269,7 @@ static KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebu
         st->dst_alpha_blend_factor > 9)
         return KZN_ERROR_FEATURE_NOT_PRESENT;
     if (st->color_blend_op > 4 || st->alpha_blend_op > 4) return KZN_ERROR_VALIDATION_FAILED;
+    if (st->logic_op > 16) return KZN_ERROR_VALIDATION_FAILED;
     int has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     if (!has_color && !has_depth) return KZN_ERROR_VALIDATION_FAILED;
     if (has_color) {

@@ -216,6 +216,15 @@ def draw_scenes() -> list[Scene]:
             sl.append([pnt[0], pnt[1], zz, *col])
     scenes.append(Scene("slivers_and_large", 256, 160, np.array(sl, dtype=np.float32),
                         state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    # logic ops (logicOpEnable): order-dependent XOR over the binned path, masked OR_REVERSE over the direct path (few
+    # triangles), both on top of a non-trivial clear colour; blending state is set but must be ignored
+    scenes.append(Scene("logic_xor_slivers", 256, 160, np.array(sl, dtype=np.float32),
+                        state=pipeline_state(blend=util.ALPHA_BLEND, logic_op=6), clear_color=(0.3, 0.6, 0.9, 0.5)))
+    scenes.append(Scene("logic_or_reverse_masked_quad", 64, 48, _quad((0.7, 0.1, 0.55, 0.35)),
+                        state=pipeline_state(logic_op=11, write_mask=0b0111), clear_color=(0.2, 0.8, 0.4, 0.6)))
+    scenes.append(Scene("logic_and_inverted_mesh_tiled", 200, 120, *util.grid_mesh(30, 16, 7),
+                        state=pipeline_state(logic_op=4, depth=(abi.COMPARE_LESS_OR_EQUAL, 1)), use_depth=True,
+                        clear_color=(0.9, 0.5, 0.1, 1.0), color_tiling=T))
     # wide spans (>= 64 px of a row: quad path) interleaved with small triangles, order-dependent state
     mx = []
     for k in range(400):

@@ -107,6 +107,25 @@ def test_write_mask_and_no_blend_clamps_source():
     assert tuple(color[:4]) == (255, 0, 51, 128)  # R clamped to 1, G clamped to 0, B masked (keeps 0.2), A = 0.5
 
 
+def test_logic_ops_known_answers():
+    """VkLogicOp on the UNORM8 bits: source (1, 0.2, 0.6, 0.4) -> FF 33 99 66, destination cleared to
+    (0.0588.., 0.9411.., 0.3333.., 1) -> 0F F0 55 FF; blending is ignored when a logic op is enabled."""
+    s, d = (0xFF, 0x33, 0x99, 0x66), (0x0F, 0xF0, 0x55, 0xFF)
+    table = {0: lambda a, b: 0, 1: lambda a, b: a & b, 2: lambda a, b: a & ~b, 3: lambda a, b: a, 4: lambda a, b: ~a & b,
+             5: lambda a, b: b, 6: lambda a, b: a ^ b, 7: lambda a, b: a | b, 8: lambda a, b: ~(a | b), 9: lambda a, b: ~(a ^ b),
+             10: lambda a, b: ~b, 11: lambda a, b: a | ~b, 12: lambda a, b: ~a, 13: lambda a, b: ~a | b, 14: lambda a, b: ~(a & b),
+             15: lambda a, b: 0xFF}
+    t = tri([(0, 0), (8, 0), (0, 8)], color=[1.0, 0.2, 0.6, 0.4])
+    clear = (15 / 255, 240 / 255, 85 / 255, 1.0)
+    for op, fn in table.items():
+        st = pipeline_state(blend=util.ALPHA_BLEND, logic_op=op)
+        color, _, _ = Scene("l", 8, 8, t, state=st, clear_color=clear).run_oracle()
+        assert tuple(color[:4]) == tuple(fn(a, b) & 0xFF for a, b in zip(s, d)), op
+    # the write mask still applies: XOR on R and A only
+    color, _, _ = Scene("l", 8, 8, t, state=pipeline_state(logic_op=6, write_mask=0b1001), clear_color=clear).run_oracle()
+    assert tuple(color[:4]) == (0xFF ^ 0x0F, 0xF0, 0x55, 0x66 ^ 0xFF)
+
+
 def test_scissor_viewport_and_band_limit_fragments():
     full = util.FULLSCREEN_TRIANGLE
     m = covered(Scene("s", 32, 32, full, scissor=abi.Rect2D(abi.Offset2D(3, 5), abi.Extent2D(7, 11))))
@@ -154,5 +173,8 @@ def test_invalid_draw_state_is_rejected():
     vi = abi.VertexInput(sc.vertices.ctypes.data, sc.vertices.nbytes, 28, 0, 3, 12)
     args = lambda st, vp: lib.kzo_draw(C.byref(st), C.byref(fb), C.byref(vp), C.byref(sc.scissor), C.byref(vi), 3, 1, 0, 0, None)
     assert args(sc.state, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
+    bad = pipeline_state()
+    bad.logic_op = 17
+    assert args(bad, sc.viewport) == abi.ERROR_VALIDATION_FAILED
     assert args(pipeline_state(), abi.Viewport(0, 0, 0, 8, 0, 1)) == abi.ERROR_VALIDATION_FAILED
     assert args(pipeline_state(), abi.Viewport(0, 0, 8, 8, 0, 2)) == abi.ERROR_VALIDATION_FAILED
