@@ -370,7 +370,7 @@ typedef struct KznGraphicsPipelineState {
     uint32_t alpha_blend_op;
     uint32_t color_write_mask; /* VkColorComponentFlags, R=1 G=2 B=4 A=8 */
     /* VkPipelineColorBlendStateCreateInfo logicOpEnable / logicOp (the reference advertises the logicOp feature,
-     * api_impl.rs:890): 0 = disabled, otherwise 1 + VkLogicOp (CLEAR = 1 ... SET = 16).  Applied to the UNORM8 bits of the
+     * api_impl.rs:884): 0 = disabled, otherwise 1 + VkLogicOp (CLEAR = 1 ... SET = 16).  Applied to the UNORM8 bits of the
      * converted source and of the destination; when enabled, blending is treated as disabled (Vulkan 1.1 "Logical
      * Operations"); the write mask still applies. */
     uint32_t logic_op;
