@@ -374,7 +374,16 @@ typedef struct KznGraphicsPipelineState {
      * converted source and of the destination; when enabled, blending is treated as disabled (Vulkan 1.1 "Logical
      * Operations"); the write mask still applies. */
     uint32_t logic_op;
+    /* VkPipelineInputAssemblyStateCreateInfo::topology: VK_PRIMITIVE_TOPOLOGY_TRIANGLE_LIST (3, and 0 is accepted as the
+     * default), TRIANGLE_STRIP (4) or TRIANGLE_FAN (5), assembled as the specification's "Primitive Topologies" section
+     * defines: strip triangle i = {v[i], v[i+(1+i%2)], v[i+(2-i%2)]}, fan triangle i = {v[i+1], v[i+2], v[0]}
+     * (primitive restart is not supported).  Points and lines return VK_ERROR_FEATURE_NOT_PRESENT. */
+    uint32_t topology;
+    uint32_t reserved;
 } KznGraphicsPipelineState;
+#define KZN_TOPOLOGY_TRIANGLE_LIST 3u
+#define KZN_TOPOLOGY_TRIANGLE_STRIP 4u
+#define KZN_TOPOLOGY_TRIANGLE_FAN 5u
 
 typedef struct KznVertexInput { /* one binding, VkVertexInputBindingDescription + 2 attributes */
     uint64_t buffer_address;

@@ -146,7 +146,7 @@ class GraphicsPipelineState(C.Structure):
     _fields_ = [(n, u32) for n in (
         "vertex_program", "fragment_program", "cull_mode", "front_face", "depth_test_enable", "depth_write_enable",
         "depth_compare_op", "blend_enable", "src_color_blend_factor", "dst_color_blend_factor", "color_blend_op",
-        "src_alpha_blend_factor", "dst_alpha_blend_factor", "alpha_blend_op", "color_write_mask", "logic_op")]
+        "src_alpha_blend_factor", "dst_alpha_blend_factor", "alpha_blend_op", "color_write_mask", "logic_op", "topology", "reserved")]
 
 
 class VertexInput(C.Structure):

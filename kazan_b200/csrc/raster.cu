@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     int32_t X[3], Y[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        unsigned long long i = (unsigned long long)p.first + 3ull * t + k;
+        // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
+        unsigned long long rel = 3ull * t + k;
+        if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
+        if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
+        unsigned long long i = (unsigned long long)p.first + rel;
         long long vidx;
         if (p.index_base) {
             unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
@@ -1519,6 +1523,9 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
                 KZN_ERROR_FEATURE_NOT_PRESENT, "draw: blend factor not supported (dualSrcBlend is FALSE, api_impl.rs:883)");
     KZN_VALID(st->color_blend_op <= 4 && st->alpha_blend_op <= 4, "draw: bad blend op");
     KZN_VALID(st->logic_op <= 16, "draw: logic_op is 0 (disabled) or 1 + VkLogicOp");
+    KZN_VALID(st->topology <= 10, "draw: bad primitive topology");
+    KZN_REQUIRE(st->topology == 0 || (st->topology >= KZN_TOPOLOGY_TRIANGLE_LIST && st->topology <= KZN_TOPOLOGY_TRIANGLE_FAN),
+                KZN_ERROR_FEATURE_NOT_PRESENT, "draw: only triangle list / strip / fan topologies are rasterised");
     bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     KZN_VALID(has_color || has_depth, "draw: framebuffer has no attachment");
     if (has_color) {
@@ -1621,7 +1628,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     DrawParams p;
     memset(&p, 0, sizeof p);
     make_clip(fb, vp, sc, W, H, &p);
-    uint64_t ntri = count / 3, total = ntri * instance_count;
+    const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
+    uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0), total = ntri * instance_count;
     if (total == 0 || p.cx1 < p.cx0) return KZN_SUCCESS;
     KZN_REQUIRE(p.cx1 <= 65535 && p.cy1 <= 65535, KZN_ERROR_FEATURE_NOT_PRESENT,
                 "draw: render area reaches beyond pixel 65535 (pixel boxes are packed into 16 bits per coordinate)");

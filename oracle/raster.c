@@ -270,6 +270,9 @@ static KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebu
         return KZN_ERROR_FEATURE_NOT_PRESENT;
     if (st->color_blend_op > 4 || st->alpha_blend_op > 4) return KZN_ERROR_VALIDATION_FAILED;
     if (st->logic_op > 16) return KZN_ERROR_VALIDATION_FAILED;
+    if (st->topology > 10) return KZN_ERROR_VALIDATION_FAILED;
+    if (st->topology != 0 && (st->topology < KZN_TOPOLOGY_TRIANGLE_LIST || st->topology > KZN_TOPOLOGY_TRIANGLE_FAN))
+        return KZN_ERROR_FEATURE_NOT_PRESENT; /* points, lines, adjacency, patches */
     int has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     if (!has_color && !has_depth) return KZN_ERROR_VALIDATION_FAILED;
     if (has_color) {
@@ -387,7 +390,8 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
     if (r) return r;
     ClipRect clip;
     make_clip(fb, vp, sc, W, H, &clip);
-    uint64_t ntri = count / 3;
+    const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
+    uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0);
     uint64_t total = ntri * instance_count;
     if (total == 0) return KZN_SUCCESS;
     TriSetup* tris = (TriSetup*)malloc(total * sizeof(TriSetup));
@@ -398,7 +402,11 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
     for (int64_t t = 0; t < (int64_t)ntri; ++t) {
         VsOut v[3];
         for (int k = 0; k < 3; ++k) {
-            uint64_t i = first + 3 * (uint64_t)t + k;
+            /* Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0} */
+            uint64_t rel = 3 * (uint64_t)t + k;
+            if (topo == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (uint64_t)t + (k == 0 ? 0 : k == 1 ? 1 + (uint64_t)t % 2 : 2 - (uint64_t)t % 2);
+            if (topo == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0 : (uint64_t)t + 1 + k;
+            uint64_t i = first + rel;
             int64_t vidx;
             if (indices) {
                 uint64_t raw = index_type == KZN_INDEX_TYPE_UINT16 ? ((const uint16_t*)indices)[i] : ((const uint32_t*)indices)[i];

@@ -225,6 +225,28 @@ def draw_scenes() -> list[Scene]:
     scenes.append(Scene("logic_and_inverted_mesh_tiled", 200, 120, *util.grid_mesh(30, 16, 7),
                         state=pipeline_state(logic_op=4, depth=(abi.COMPARE_LESS_OR_EQUAL, 1)), use_depth=True,
                         clear_color=(0.9, 0.5, 0.1, 1.0), color_tiling=T))
+    # triangle strips and fans (Vulkan "Primitive Topologies"): a ribbon whose odd triangles would be culled if the strip
+    # were assembled as {i, i+1, i+2}; an indexed (uint16) strip over the binned path; a fan around an off-centre hub
+    rib = []
+    for k in range(24):
+        x = -0.95 + 1.9 * k / 23
+        rib.append([x, -0.5 + 0.1 * np.sin(k), 0.5, *rng.uniform(0.1, 0.9, 4)])
+        rib.append([x + 0.03, 0.55 + 0.1 * np.cos(k), 0.5, *rng.uniform(0.1, 0.9, 4)])
+    scenes.append(Scene("strip_ribbon_cull_back", 160, 96, np.array(rib, dtype=np.float32),
+                        state=pipeline_state(topology=4, cull=abi.CULL_BACK, front=abi.FRONT_FACE_CCW, blend=util.ADDITIVE_BLEND)))
+    gv, _ = util.grid_mesh(24, 12, 9)
+    strip_idx = []
+    for row in range(12):  # one long strip, rows joined by degenerate triangles
+        for col in range(25):
+            strip_idx += [row * 25 + col, (row + 1) * 25 + col]
+        strip_idx += [(row + 1) * 25 + 24, (row + 1) * 25]
+    scenes.append(Scene("strip_indexed_u16_mesh", 240, 140, gv, np.array(strip_idx, dtype=np.uint16), index_type=abi.INDEX_TYPE_UINT16,
+                        state=pipeline_state(topology=4, depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    hub = [[0.21, -0.13, 0.4, 1.0, 1.0, 1.0, 0.5]]
+    rim = [[0.21 + 0.9 * float(np.cos(a)), -0.13 + 0.8 * float(np.sin(a)), 0.6, *rng.uniform(0, 1, 4)]
+           for a in np.linspace(0, 2 * np.pi, 41)]
+    scenes.append(Scene("fan_disc", 128, 128, np.array(hub + rim, dtype=np.float32),
+                        state=pipeline_state(topology=5, blend=util.ADDITIVE_BLEND)))
     # wide spans (>= 64 px of a row: quad path) interleaved with small triangles, order-dependent state
     mx = []
     for k in range(400):

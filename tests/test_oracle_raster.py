@@ -126,6 +126,28 @@ def test_logic_ops_known_answers():
     assert tuple(color[:4]) == (0xFF ^ 0x0F, 0xF0, 0x55, 0x66 ^ 0xFF)
 
 
+def test_strip_and_fan_assemble_the_triangles_of_the_specification():
+    """Strip triangle i = {v[i], v[i+(1+i%2)], v[i+(2-i%2)]}, fan triangle i = {v[i+1], v[i+2], v[0]} (Vulkan 1.1 "Primitive
+    Topologies"): the same picture as the equivalent triangle list, winding included (back faces culled)."""
+    rng = np.random.default_rng(5)
+    v = np.array([[x, y, 0.5, *rng.uniform(0.1, 0.9, 4)] for x, y in
+                  [(-0.9, -0.8), (-0.7, 0.8), (-0.2, -0.7), (0.0, 0.9), (0.5, -0.9), (0.6, 0.7), (0.9, -0.6)]], dtype=np.float32)
+    st = lambda topo, front=abi.FRONT_FACE_CCW: pipeline_state(topology=topo, cull=abi.CULL_BACK, front=front, blend=util.ADDITIVE_BLEND)
+    n = len(v) - 2
+    as_list = np.array([v[j] for i in range(n) for j in (i, i + (1 + i % 2), i + (2 - i % 2))], dtype=np.float32)
+    strip, _, s_st = Scene("s", 64, 64, v, state=st(4)).run_oracle()
+    lst, _, l_st = Scene("l", 64, 64, as_list, state=st(3)).run_oracle()
+    assert strip.tobytes() == lst.tobytes() and s_st.triangles_in == n == l_st.triangles_in
+    assert s_st.triangles_culled == l_st.triangles_culled == 0 and s_st.fragments_covered > 0  # one winding for all of them
+    assert Scene("s", 64, 64, v, state=st(4, abi.FRONT_FACE_CW)).run_oracle()[2].triangles_culled == n
+    fan_list = np.array([v[j] for i in range(n) for j in (i + 1, i + 2, 0)], dtype=np.float32)
+    fan, _, f_st = Scene("f", 64, 64, v, state=pipeline_state(topology=5, blend=util.ADDITIVE_BLEND)).run_oracle()
+    lst, _, l_st = Scene("l", 64, 64, fan_list, state=pipeline_state(blend=util.ADDITIVE_BLEND)).run_oracle()
+    assert fan.tobytes() == lst.tobytes() and f_st.fragments_covered == l_st.fragments_covered > 0
+    # fewer than three vertices: nothing; points and lines are not rasterised
+    assert Scene("e", 8, 8, v[:2], state=st(4)).run_oracle()[2].triangles_in == 0
+
+
 def test_scissor_viewport_and_band_limit_fragments():
     full = util.FULLSCREEN_TRIANGLE
     m = covered(Scene("s", 32, 32, full, scissor=abi.Rect2D(abi.Offset2D(3, 5), abi.Extent2D(7, 11))))
@@ -173,6 +195,8 @@ def test_invalid_draw_state_is_rejected():
     vi = abi.VertexInput(sc.vertices.ctypes.data, sc.vertices.nbytes, 28, 0, 3, 12)
     args = lambda st, vp: lib.kzo_draw(C.byref(st), C.byref(fb), C.byref(vp), C.byref(sc.scissor), C.byref(vi), 3, 1, 0, 0, None)
     assert args(sc.state, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
+    lines = pipeline_state(topology=1)
+    assert args(lines, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
     bad = pipeline_state()
     bad.logic_op = 17
     assert args(bad, sc.viewport) == abi.ERROR_VALIDATION_FAILED

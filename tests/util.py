@@ -98,9 +98,10 @@ def image_copy(extent, src_off=(0, 0, 0), dst_off=(0, 0, 0), src_layer=0, dst_la
 # ---- draw scenes (shared by oracle tests, GPU parity tests, golden generation, bench) ----------------------
 
 def pipeline_state(fs=abi.FS_VERTEX_COLOR, cull=abi.CULL_NONE, front=abi.FRONT_FACE_CCW, depth=None, blend=None,
-                   write_mask=15, logic_op=None) -> abi.GraphicsPipelineState:
-    """logic_op: a VkLogicOp 0..15 (logicOpEnable = TRUE) or None."""
+                   write_mask=15, logic_op=None, topology=0) -> abi.GraphicsPipelineState:
+    """logic_op: a VkLogicOp 0..15 (logicOpEnable = TRUE) or None; topology: 0 / 3 list, 4 strip, 5 fan."""
     st = abi.GraphicsPipelineState()
+    st.topology = topology
     st.logic_op = 0 if logic_op is None else 1 + logic_op
     st.fragment_program = fs
     st.cull_mode = cull
