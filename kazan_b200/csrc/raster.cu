@@ -46,10 +46,6 @@ constexpr int kSortCap = 4096;           // largest binned list sorted in shared
 #ifndef KZN_RASTER_CTAS
 #define KZN_RASTER_CTAS 3
 #endif
-#ifndef KZN_CHUNK_BUFFERS
-#define KZN_CHUNK_BUFFERS 1
-#endif
-constexpr int kChunkBuffers = KZN_CHUNK_BUFFERS;  // record slots per row warp = 32 x this (2: fragments queued from the last chunk stay valid)
 constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
@@ -456,16 +452,13 @@ struct FragQueue {  // covered fragments of one row waiting for a full 32-lane s
 };
 
 struct TileState {  // live from the tile prologue to the epilogue
-    TriRec recs[kTileH][kChunkBuffers * 32];  // per row: the records of the chunks being rasterised (private to the row's warp)
+    TriRec recs[kTileH][32];  // per row: the records of the chunk being rasterised (private to the row's warp)
     FragQueue queue[kTileH];
     uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
     uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
     float depth[kTileH][kTileW];
     uint8_t color_dirty[kTileH][kTileW];  // one byte per pixel (plain stores: a row belongs to one warp), 4 per lane
     uint8_t depth_dirty[kTileH][kTileW];
-#ifdef KZN_PAD_SMEM
-    unsigned char pad[KZN_PAD_SMEM];  // occupancy experiments
-#endif
 };
 struct SortScratch {  // live only while the tile's id list is sorted (before the prologue); the result goes back to global memory
     uint32_t list[kSortCap];
@@ -791,17 +784,10 @@ __device__ __forceinline__ void fs_procedural_orbit_rgba8(const float2 cx[PX / 2
         const float x = (k & 1) ? zx[k >> 1].y : zx[k >> 1].x, y = (k & 1) ? zy[k >> 1].y : zy[k >> 1].x;
         const float m = fmaf(x, x, y * y);
         const float r = clamp01(0.25f * m), g = clamp01(fmaf(x, 0.5f, 0.5f)), b = clamp01(fmaf(y, 0.5f, 0.5f));
-#ifdef KZN_ORBIT_F2I
-        // variant: conversions on the XU pipe (F2I), alpha or-ed in — measured 184 against 193 Gpixel/s for the default
-        const uint32_t rb = __float2uint_rn(__fmul_rn(r, 255.0f)), gb = __float2uint_rn(__fmul_rn(g, 255.0f)), bb = __float2uint_rn(__fmul_rn(b, 255.0f));
-        out[k] = __byte_perm(__byte_perm(rb, gb, 0x4440), bb, 0x4410) | 0xff000000u;
-        (void)kRound; (void)kRoundAlpha;
-#else
         const uint32_t rb = __float_as_uint(__fadd_rn(__fmul_rn(r, 255.0f), kRound));
         const uint32_t gb = __float_as_uint(__fadd_rn(__fmul_rn(g, 255.0f), kRound));
         const uint32_t bb = __float_as_uint(__fadd_rn(__fmul_rn(b, 255.0f), kRoundAlpha));
         out[k] = __byte_perm(__byte_perm(rb, gb, 0x4440), bb, 0x5410);  // [r, g] then [r, g, b, 0xFF]
-#endif
     }
 }
 template <int PX>
@@ -1276,12 +1262,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
 
 
 template <uint32_t FS, int NEED_DST>
-#ifdef KZN_RASTER_REGS
-__global__ void __maxnreg__(KZN_RASTER_REGS) raster_kernel(
-#else
-__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(
-#endif
-    const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
@@ -1375,7 +1356,7 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
         // software pipeline of the filter: ids three steps ahead, boxes two steps ahead
         uint32_t id0 = load_id(lane), id1 = load_id(32u + lane), id2 = load_id(64u + lane);
         uint2 box0 = load_box(id0), box1 = load_box(id1);
-        uint32_t step = 0, chunk_no = 0;
+        uint32_t step = 0;
         const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
         for (;;) {
             while (pend_n < 32u && step < n_steps) {
@@ -1394,10 +1375,7 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             }
             if (pend_n == 0) break;
             const uint32_t n = min(pend_n, 32u);
-            // chunks alternate between the warp's record buffers; fragments still queued from the chunk that used this
-            // buffer last (the queue is first-in first-out: look at its head) must be shaded before it is overwritten
-            const uint32_t buf = kChunkBuffers > 1 ? (chunk_no++ & 1u) * 32u : 0u;
-            if (q_n && (kChunkBuffers == 1 || ((sh.tile.queue[warp].key[0] >> 8) & 32u) == buf)) {
+            if (q_n) {  // fragments still queued refer to the records that are about to be replaced: shade them first
                 n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
                 q_n = 0;
             }
@@ -1408,12 +1386,12 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
                 const uint32_t q = lane + 32u * i, r = q / 9u;
                 if (r < n) {
                     const uint4* src = reinterpret_cast<const uint4*>(&p.tris[pend[r]]) + (q - 9u * r);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + (buf * 9u + q) * 16u), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, buf + lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
+            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
                                        n_covered, n_passed);
             const bool mv = lane + 32u < pend_n;
             const uint32_t v = mv ? pend[32u + lane] : 0u;
