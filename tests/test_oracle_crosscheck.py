@@ -1,0 +1,95 @@
+"""CPU: an independent restatement of the coverage rules, checked against the C oracle on random triangles.
+
+The reference holds no known answers for rasterisation, so the oracle is the only definition of "correct"
+the GPU kernels are held to.  This file derives coverage a second time, straight from the Vulkan 1.1 text
+("Basic Polygon Rasterization": fixed-point vertices with subPixelPrecisionBits = 4, sample at the pixel centre, a sample
+on an edge belongs to the triangle only if that edge is a top or a left edge) and in a different way from oracle/raster.c:
+
+* exact integers in 1/16-pixel units for everything (no floating point after the snap);
+* "top" and "left" are decided GEOMETRICALLY from the position of the opposite vertex (a top edge is horizontal with the
+  triangle below it; a left edge is non-horizontal with the triangle to its right), not from the signs of the
+  orientation-normalised edge coefficients the oracle uses;
+* inside/outside by comparing the sample's side of each edge with the opposite vertex's side.
+
+Triangles are drawn on a coarse vertex grid so that many samples fall exactly on edges and vertices.
+"""
+import numpy as np
+import pytest
+
+from tests.test_oracle_raster import covered, tri
+from tests.util import Scene
+
+SIZE = 32  # a power of two: pixel -> NDC -> window is exact in fp32 for the 1/32-pixel positions used below
+
+
+def snap(v: float) -> int:
+    """Window coordinate -> 1/16 pixel units, round to nearest even (the rule of the fixed-point snap, E.6)."""
+    return int(np.rint(np.float32(v) * np.float32(16.0)))  # np.rint rounds half to even, as cvt.rni / lrintf do
+
+
+def side(ax, ay, bx, by, px, py):
+    """Twice the signed area of (A, B, P): which side of the line A->B the point is on (exact integers)."""
+    return (bx - ax) * (py - ay) - (by - ay) * (px - ax)
+
+
+def owns_its_boundary(ax, ay, bx, by, cx, cy) -> bool:
+    """Is edge AB of triangle ABC (C the opposite vertex, y pointing down) a top or a left edge?"""
+    if ay == by:
+        return cy > ay  # horizontal: top edge if the triangle is below it
+    # non-horizontal: x of the edge's line at the height of C, compared with C (cross-multiplied: exact)
+    # x_edge = ax + (cy - ay) * (bx - ax) / (by - ay);  left edge  <=>  cx > x_edge
+    num = (cx - ax) * (by - ay) - (cy - ay) * (bx - ax)
+    return num > 0 if by > ay else num < 0
+
+
+def reference_coverage(points_px, size=SIZE) -> np.ndarray:
+    pts = [(snap(x), snap(y)) for x, y in points_px]
+    (x0, y0), (x1, y1), (x2, y2) = pts
+    out = np.zeros((size, size), bool)
+    if side(x0, y0, x1, y1, x2, y2) == 0:
+        return out  # zero area after snapping: no fragments
+    edges = [(pts[0], pts[1], pts[2]), (pts[1], pts[2], pts[0]), (pts[2], pts[0], pts[1])]
+    for py in range(size):
+        for px in range(size):
+            sx, sy = 16 * px + 8, 16 * py + 8
+            inside = True
+            for (a, b, c) in edges:
+                s_p = side(*a, *b, sx, sy)
+                s_c = side(*a, *b, *c)
+                if s_p == 0:
+                    inside = inside and owns_its_boundary(*a, *b, *c)
+                else:
+                    inside = inside and ((s_p > 0) == (s_c > 0))
+            out[py, px] = inside
+    return out
+
+
+def _random_triangles(n, seed):
+    rng = np.random.default_rng(seed)
+    for k in range(n):
+        if k % 3 == 0:   # vertices on half-pixel positions: edges and vertices through pixel centres
+            pts = rng.integers(-2, 2 * SIZE + 4, (3, 2)) / 2.0
+        elif k % 3 == 1:  # vertices on the 1/16 grid
+            pts = rng.integers(-32, 16 * SIZE + 32, (3, 2)) / 16.0
+        else:             # the 1/32 grid: exercises the snap itself (odd multiples of 1/32 are ties -> round to even)
+            pts = rng.integers(-64, 32 * SIZE + 64, (3, 2)) / 32.0
+        yield [(float(x), float(y)) for x, y in pts]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_coverage_matches_the_independent_restatement(seed):
+    checked = on_edge_cases = 0
+    for pts in _random_triangles(80, seed):
+        want = reference_coverage(pts)
+        got = covered(Scene("x", SIZE, SIZE, tri(pts, size=(SIZE, SIZE))))
+        assert np.array_equal(got, want), f"triangle {pts}: {np.argwhere(got != want)[:5].tolist()}"
+        checked += int(want.sum())
+        on_edge_cases += 1
+    assert checked > 2000 and on_edge_cases == 80
+
+
+def test_shared_edge_is_covered_exactly_once_by_the_restatement_too():
+    # the property the top-left rule exists for, on the restatement itself: two triangles sharing an edge partition the quad
+    a = reference_coverage([(2, 3), (28, 5), (4, 27)])
+    b = reference_coverage([(28, 5), (30, 29), (4, 27)])
+    assert not (a & b).any() and (a | b).sum() > 200
