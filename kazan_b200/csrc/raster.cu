@@ -96,6 +96,7 @@ struct DrawParams {
     unsigned long long* stats;                     // KznDrawStatistics or null
     uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
+    uint32_t fused_setup;                          // direct draws of <= 32 triangles: raster_direct_kernel makes the records itself
 };
 
 // ---- setup ------------------------------------------------------------------------------------------------
@@ -192,13 +193,9 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
     }
 }
 
-__global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
-    kzn_pdl_wait();
-    const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
-    if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
-    const bool in_range = t_raw < p.tris_per_instance;
-    const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
-    TriRec r;
+// Triangle t of an instance -> its record (R1-R5: fetch, passthrough VS, viewport, snap, cull, edge equations, pixel box).
+// false: the triangle produces no fragments (its box is left empty).
+__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r) {
     r.minx = 1;
     r.maxx = 0;
     r.miny = 1;
@@ -277,6 +274,17 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
             ok = false;
         }
     }
+    return ok;
+}
+
+__global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
+    if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
+    const bool in_range = t_raw < p.tris_per_instance;
+    const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
+    TriRec r;
+    const bool ok = make_record(p, t, r);
     // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
     const uint32_t n_inst = p.total_tris / p.tris_per_instance;
     // The CTA's 256 records are contiguous in memory (36 KiB): they are transposed through shared memory and written
@@ -940,6 +948,23 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
         for (int i = 0; i < 8; ++i) unorm_lut[lane + 32 * i] = unorm8_to_float(lane + 32 * i);
         __syncwarp();
     }
+    // Draws of at most 32 triangles (fullscreen passes, quads) have no setup_kernel launch: every warp makes the records
+    // itself, lane i = triangle i, into its own shared memory — a few hundred instructions per warp against a dependent
+    // kernel launch per draw.  The work counter is then handed back by the last warp to leave (see the end of the kernel).
+    __shared__ TriRec own_recs[32];
+    if (p.fused_setup) {
+        if (lane < p.total_tris) {
+            TriRec r;
+            const bool ok = make_record(p, lane % p.tris_per_instance, r);
+            own_recs[lane] = r;
+            if (p.stats && blockIdx.x == 0) {
+                atomicAdd(&p.stats[0], 1ull);
+                if (!ok) atomicAdd(&p.stats[1], 1ull);
+            }
+        }
+        __syncwarp();
+    }
+    const TriRec* recs = p.fused_setup ? own_recs : p.tris;
     const uint32_t n_blocks = p.tiles_x * p.tiles_y;
     const unsigned long long pitch = (unsigned long long)p.fb_w * 4ull;
     uint32_t n_covered = 0, n_passed = 0;
@@ -980,7 +1005,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
         if (FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test) {
             bool ok = false;
             if (lane < p.total_tris) {
-                const TriRec& t = p.tris[lane];
+                const TriRec& t = recs[lane];
                 const uint32_t bias = t.bias_bits;
                 ok = t.minx <= t.maxx && (bias & 8u);  // produces fragments; the depth clip cannot reject (setup)
                 const int32_t sx_lo = 16 * tile_px0 + 8, sx_hi = 16 * (tile_px0 + kDirectTileW - 1) + 8;
@@ -1075,8 +1100,8 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
                     }
                     continue;
                 }
-                const TriRec& t = p.tris[i];
-                const int4 bb = __ldg(reinterpret_cast<const int4*>(&t));  // minx maxx miny maxy, already scissored
+                const TriRec& t = recs[i];
+                const int4 bb = *reinterpret_cast<const int4*>(&t);  // minx maxx miny maxy, already scissored
                 if (bb.x > bb.y || py < bb.z || py > bb.w) continue;
                 const int xa = max(bb.x, tile_px0), xb = min(bb.y, tile_px0 + kDirectTileW - 1);
                 if (xa > xb) continue;
@@ -1117,6 +1142,15 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
         if (lane == 0) {
             if (n_covered) atomicAdd(&p.stats[4], (unsigned long long)n_covered);
             if (n_passed) atomicAdd(&p.stats[5], (unsigned long long)n_passed);
+        }
+    }
+    if (lane == 0) {
+        // The block dispenser must be zero again for the next direct draw, which may have no setup_kernel to zero it: the
+        // last warp to leave (every warp has made its last request by then) resets it and the count of leavers
+        __threadfence();
+        if (atomicAdd(p.work_counter + 1, 1u) == gridDim.x - 1u) {
+            p.work_counter[0] = 0u;
+            p.work_counter[1] = 0u;
         }
     }
 }
@@ -1569,7 +1603,10 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     KznRasterScratch* s = q->raster;
     if ((r = grow(q, &s->tris, &s->tri_capacity, total))) return r;
     if ((r = grow(q, &s->boxes, &s->box_capacity, total))) return r;
-    if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
+    if (!s->counters) {  // [0] block dispenser of the direct kernel, [1] warps that have left it (fused setup): start at zero
+        if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
+        KZN_CUDA(cudaMemset(s->counters, 0, s->counter_capacity * sizeof(uint32_t)));
+    }
     if (binned) {
         if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
         // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
@@ -1673,8 +1710,11 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
 
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
-    launch_draw_kernel(setup_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
-    if ((r = kzn_launched(q, "setup_kernel"))) return r;
+    p.fused_setup = !p.binned && total <= 32u;
+    if (!p.fused_setup) {
+        launch_draw_kernel(setup_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
+        if ((r = kzn_launched(q, "setup_kernel"))) return r;
+    }
     if (p.binned) {
         launch_draw_kernel(bin_scan_kernel, dim3(1), dim3(1024), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
