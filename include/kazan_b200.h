@@ -212,7 +212,11 @@ KZN_API KznResult kzn_memory_export(KznMemory* memory, uint8_t handle[KZN_MEMORY
 KZN_API KznResult kzn_memory_import(KznDevice* device, const uint8_t handle[KZN_MEMORY_HANDLE_BYTES], uint64_t size,
                                     KznMemory** memory); /* release with kzn_memory_free */
 
-/* -- queue: vkGetDeviceQueue :3394, vkQueueSubmit :3414, vkQueueWaitIdle :3424 ---------------- */
+/* -- queue: vkGetDeviceQueue :3394, vkQueueSubmit :3414, vkQueueWaitIdle :3424 ----------------
+ * A queue is one in-order CUDA stream: a command sees the results of every earlier command of the queue.  The transfer
+ * and draw kernels are launched with programmatic dependent launch (each begins with griddepcontrol.wait, which returns
+ * once the previous kernel of the stream has completed and its writes are visible), so that order is kept while the launch
+ * gap between consecutive kernels is hidden; KZN_PDL=0 in the environment restores ordinary launches. */
 KZN_API KznResult kzn_queue_create(KznDevice* device, KznQueue** queue);
 /* run on a stream owned by the host (e.g. the framework's current stream); not destroyed with the queue */
 KZN_API KznResult kzn_queue_wrap_stream(KznDevice* device, void* cuda_stream, KznQueue** queue);
