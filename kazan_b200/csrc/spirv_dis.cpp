@@ -343,6 +343,44 @@ uint32_t id_ref(Cursor& c, const State& st) {
     return v;
 }
 
+// The reference builds a Rust String from the bytes (String::from_utf8, generate.rs:372) and reports std's Utf8Error:
+// "invalid utf-8 sequence of N bytes from index I" / "incomplete utf-8 byte sequence from index I".
+void check_utf8(const std::string& s) {
+    const size_t n = s.size();
+    size_t i = 0;
+    auto invalid = [&](size_t len) { throw Error("invalid utf-8 sequence of " + std::to_string(len) + " bytes from index " + std::to_string(i)); };
+    auto incomplete = [&]() { throw Error("incomplete utf-8 byte sequence from index " + std::to_string(i)); };
+    while (i < n) {
+        const unsigned char b0 = (unsigned char)s[i];
+        if (b0 < 0x80) {
+            ++i;
+            continue;
+        }
+        size_t need;
+        unsigned char lo = 0x80, hi = 0xBF;  // allowed range of the second byte (excludes overlong forms and surrogates)
+        if (b0 >= 0xC2 && b0 <= 0xDF) need = 1;
+        else if (b0 >= 0xE0 && b0 <= 0xEF) {
+            need = 2;
+            if (b0 == 0xE0) lo = 0xA0;
+            if (b0 == 0xED) hi = 0x9F;
+        } else if (b0 >= 0xF0 && b0 <= 0xF4) {
+            need = 3;
+            if (b0 == 0xF0) lo = 0x90;
+            if (b0 == 0xF4) hi = 0x8F;
+        } else {
+            invalid(1);
+            return;
+        }
+        for (size_t k = 1; k <= need; ++k) {
+            if (i + k >= n) incomplete();
+            const unsigned char b = (unsigned char)s[i + k];
+            const bool ok = k == 1 ? (b >= lo && b <= hi) : (b >= 0x80 && b <= 0xBF);
+            if (!ok) invalid(k);
+        }
+        i += need + 1;
+    }
+}
+
 std::string literal_string(Cursor& c) {
     std::string s;
     for (;;) {
@@ -352,6 +390,7 @@ std::string literal_string(Cursor& c) {
             if (!ch) {
                 for (int r = b + 1; r < 4; ++r)
                     if ((word >> (8 * r)) & 0xff) throw Error("SPIR-V LiteralString has an invalid termination word");
+                check_utf8(s);
                 return s;
             }
             s += ch;
@@ -484,6 +523,9 @@ std::string disassemble_spirv(const uint32_t* words, size_t count) {
     if (words[0] != 0x07230203u) throw Error("SPIR-V source has an invalid file header");
     State st;
     st.bound = words[3];
+    // the reference sizes its id table from this word unchecked; the specification's universal limit keeps a damaged header
+    // from asking for gigabytes here
+    if (st.bound > 0x3FFFFFu) throw Error("SPIR-V id bound " + std::to_string(st.bound) + " exceeds the universal limit of 4194303");
     st.type_width.assign(st.bound, Width::None);
     st.value_type.assign(st.bound, 0);
     st.defined.assign(st.bound, 0);

@@ -93,6 +93,9 @@ def test_decorations_with_parameters():
     (_module((17, 9999), bound=4), "enum has invalid value"),
     (_module((43, 1, 2, 5), bound=4), "undefined type 1"),
     (_module((21, 1, 128, 0), bound=4), "unsupported int size"),
+    (_module((5, 1, 0x00FF41), bound=4), "invalid utf-8 sequence of 1 bytes from index 1"),
+    (_module((5, 1, 0x00C341), bound=4), "incomplete utf-8 byte sequence from index 1"),
+    (_module((19, 1), bound=0x400000), "exceeds the universal limit"),
 ])
 def test_malformed_modules_report_the_reference_errors(words, message):
     with pytest.raises(host.KazanError) as e:
