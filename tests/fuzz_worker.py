@@ -47,7 +47,8 @@ def mutate_text(rng, text):
         elif kind < 0.5 and t:
             del t[i:i + rng.randint(1, 12)]
         elif kind < 0.7:
-            t[i:i] = list(rng.choice(["loop", "block", "i32", "<4 x f32>", "data_ptr", "->", "fn", "0x", "-1", "struct", "\"", "{", "}"]))
+            t[i:i] = list(rng.choice(["loop", "block", "i32", "<4 x f32>", "data_ptr", "->", "fn", "0x", "-1", "struct", "\"", "{", "}",
+                                         "18446744073709551616", "<4294967296 x i8>", "vscale x ", "<0 x i8>"]))
         elif kind < 0.85 and t:
             j = rng.randrange(len(t))
             t[i], t[j] = t[j], t[i]
@@ -63,6 +64,8 @@ def main(seed, iterations):
     ir = json.loads((ROOT / "tests/golden/ir_goldens.json").read_text())
     texts = [p.read_text() for p in sorted((ROOT / "tests/ir_programs").glob("*.kazan-ir"))]
     texts += [v for v in json.dumps(ir).split('"') if "fn " in v or "block" in v][:20]
+    pairs = [(v["kind"], v["text"]) for v in ir["text_round_trips"]]  # (grammar production, text) of the reference's vectors
+    lib, C = backend.load_library(), backend.C
     outcomes = {"ok": 0, "error": 0}
 
     def attempt(fn):
@@ -87,6 +90,14 @@ def main(seed, iterations):
             finally:
                 m.destroy()
         attempt(parse_and_emit)
+        kind, text = rng.choice(pairs)
+        damaged = mutate_text(rng, text).encode()
+
+        def round_trip():
+            out, n = C.c_void_p(), C.c_size_t()
+            backend._check(lib.kzn_ir_round_trip(kind.encode(), damaged, len(damaged), C.byref(out), C.byref(n)))
+            backend._take_text(out, n)
+        attempt(round_trip)
     print(json.dumps(outcomes))
 
 
