@@ -327,8 +327,9 @@ __global__ void __launch_bounds__(kThreads) box_kernel(const __grid_constant__ B
             unsigned long long i = i0 + k * nthreads;
             ok[k] = i < p.total;
             uint32_t xv, y, s;
-            if (p.h == 1 && p.slices == 1) {
-                // collapsed contiguous run: wv may exceed 32 bits of bytes, keep 64-bit x
+            if (!SRC_TILED && !DST_TILED && p.h == 1 && p.slices == 1) {
+                // one contiguous run of LINEAR memory (a single row, or rows collapsed by the host): wv may exceed 32 bits of
+                // bytes, keep 64-bit x.  A TILED side always goes through surf_addr, also for a single row.
                 sa[k] = p.src.base + i * (4ull * VEC);
                 da[k] = p.dst.base + i * (4ull * VEC);
                 continue;

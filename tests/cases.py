@@ -41,6 +41,10 @@ BUFFER_IMAGE_CASES = [
     ("tiled_odd", dict(width=50, height=37, tiling=T), [buffer_image_copy(50, 37)], 50 * 37 * 4),
     ("tiled_subrect", dict(width=100, height=70, tiling=T, array_layers=2),
      [buffer_image_copy(41, 23, offset=(7, 19, 0), base_layer=1, row_length=48)], 48 * 23 * 4),
+    # a single row into a TILED image: once took the contiguous-run shortcut of box_kernel and landed at texel (0, 0)
+    # (found by the random differential test in tests/test_gpu_transfer.py)
+    ("tiled_single_row", dict(width=70, height=41, tiling=T, array_layers=2),
+     [buffer_image_copy(64, 1, buffer_offset=8, row_length=64, offset=(6, 3, 0), base_layer=1)], 8 + 64 * 4),
     ("tiled_aligned_subrect", dict(width=128, height=64, tiling=T), [buffer_image_copy(64, 32, offset=(32, 16, 0))],
      64 * 32 * 4),
     ("depth_format", dict(width=96, height=40, format=abi.FORMAT_D32_SFLOAT),

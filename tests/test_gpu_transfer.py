@@ -9,7 +9,7 @@ import pytest
 from kazan_b200 import abi, host
 from kazan_b200.host import buffer_image_copy as bic
 from oracle import binding as ob
-from tests import cases, runners
+from tests import cases, runners, util
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "oracle_golden.json").read_text())
@@ -179,3 +179,75 @@ def test_tma_and_ldst_paths_agree(gpu):
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True,
                                    cwd=str(Path(__file__).parent.parent)).stdout.split())
     assert outs[0] == outs[1] == [GOLDEN["b2i/cfg1_1024"], GOLDEN["clear/cfg1_1024"]]
+
+
+def _random_region(rng, spec):
+    """A vkCmdCopyBufferToImage region that is usually legal and sometimes breaks exactly one rule."""
+    f = cases.image_desc_fields(spec)
+    w, h, d, layers = f["width"], f["height"], f["depth"], f["array_layers"]
+    ew, eh = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+    ox, oy = int(rng.integers(0, w - ew + 1)), int(rng.integers(0, h - eh + 1))
+    ed = int(rng.integers(1, d + 1))
+    oz = int(rng.integers(0, d - ed + 1))
+    base = int(rng.integers(0, layers))
+    count = int(rng.integers(1, layers - base + 1))
+    row_length = 0 if rng.random() < 0.5 else ew + int(rng.integers(0, 9))
+    image_height = 0 if rng.random() < 0.5 else eh + int(rng.integers(0, 5))
+    offset = 4 * int(rng.integers(0, 9))
+    flaw = rng.random()
+    if flaw < 0.06:
+        ox = w - ew + 1 + int(rng.integers(0, 3))          # extent sticks out of the image
+    elif flaw < 0.12:
+        base = layers                                      # layer out of range
+    elif flaw < 0.18 and row_length:
+        row_length = max(ew - 1, 0)                        # bufferRowLength smaller than the extent (0 means tight)
+    elif flaw < 0.24:
+        offset += 2                                        # bufferOffset not a multiple of the texel size
+    elif flaw < 0.30:
+        ew = 0                                             # empty extent: legal, copies nothing
+    return bic(ew, eh, depth=ed, buffer_offset=offset, row_length=row_length, image_height=image_height,
+                             offset=(ox, oy, oz), base_layer=base, layer_count=count)
+
+
+def test_random_regions_agree_with_the_oracle_in_result_code_and_bytes(gpu):
+    """Differential test on 150 random regions over four image shapes: the GPU path and the oracle must return the same
+    VkResult, and when they accept the region, the same bytes (buffer -> image and back)."""
+    import ctypes as C
+    rng = np.random.default_rng(20261018)
+    lib = ob.load()
+    shapes = [dict(width=61, height=37), dict(width=128, height=24, array_layers=3), dict(width=20, height=12, depth=5),
+              dict(width=70, height=41, tiling=abi.TILING_TILED, array_layers=2)]
+    accepted = rejected = 0
+    for k in range(150):
+        spec = shapes[k % len(shapes)]
+        region = _random_region(rng, spec)
+        buffer_bytes = 64 + 4 * (spec["width"] + 8) * (spec["height"] + 4) * spec.get("depth", 1) * spec.get("array_layers", 1)
+        size = runners._size(spec)
+        img0, buf0 = ob.random_bytes(size, 100 + k), ob.random_bytes(buffer_bytes, 500 + k)
+        # oracle
+        o_img, o_buf = img0.copy(), buf0.copy()
+        d = runners._img(spec, ob.ptr(o_img))
+        a, n = util.arr(abi.BufferImageCopy, [region])
+        code_in = lib.kzo_copy_buffer_to_image(C.c_void_p(ob.ptr(o_buf)), buffer_bytes, C.byref(d), n, a)
+        code_out = lib.kzo_copy_image_to_buffer(C.byref(d), C.c_void_p(ob.ptr(o_buf)), buffer_bytes, n, a)
+        # GPU
+        g_img, g_buf = gpu.buffer(size, img0), gpu.buffer(buffer_bytes, buf0)
+        himg = runners._host_img(spec, g_img.address)
+        got_in = got_out = abi.SUCCESS
+        try:
+            gpu.queue.cmd_copy_buffer_to_image(g_buf.address, buffer_bytes, himg, [region])
+        except host.KazanError as e:
+            got_in = e.code
+        try:
+            gpu.queue.cmd_copy_image_to_buffer(himg, g_buf.address, buffer_bytes, [region])
+        except host.KazanError as e:
+            got_out = e.code
+        assert (got_in, got_out) == (code_in, code_out), (k, spec, region.bufferOffset, region.bufferRowLength)
+        if code_in == abi.SUCCESS:
+            accepted += 1
+            assert g_img.download().tobytes() == o_img.tobytes(), (k, "image")
+            assert g_buf.download().tobytes() == o_buf.tobytes(), (k, "buffer")
+        else:
+            rejected += 1
+        gpu.release()
+    assert accepted > 90 and rejected > 15
