@@ -1628,6 +1628,13 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     return KZN_SUCCESS;
 }
 
+// a draw whose clip rectangle is empty rasterises nothing, but its triangles still count as submitted and culled
+__global__ void count_unrasterised_kernel(unsigned long long* stats, unsigned long long triangles) {
+    kzn_pdl_wait();
+    atomicAdd(&stats[0], triangles);
+    atomicAdd(&stats[1], triangles);
+}
+
 // the kernels of a draw are launched with programmatic dependent launch (kzn_internal.h)
 void launch_draw_kernel(void (*kernel)(DrawParams), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const DrawParams& p) {
     kzn_launch_pdl(kernel, grid, block, smem, stream, p);
@@ -1645,7 +1652,15 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     make_clip(fb, vp, sc, W, H, &p);
     const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
     uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0), total = ntri * instance_count;
-    if (total == 0 || p.cx1 < p.cx0) return KZN_SUCCESS;
+    if (total == 0) return KZN_SUCCESS;
+    if (p.cx1 < p.cx0 || p.cy1 < p.cy0) {  // empty clip rectangle (scissor, viewport, framebuffer and band do not meet)
+        if (q->stats_address) {
+            kzn_launch_pdl(count_unrasterised_kernel, dim3(1), dim3(1), 0, q->stream, reinterpret_cast<unsigned long long*>(q->stats_address),
+                           (unsigned long long)total);
+            return kzn_launched(q, "count_unrasterised_kernel");
+        }
+        return KZN_SUCCESS;
+    }
     KZN_REQUIRE(p.cx1 <= 65535 && p.cy1 <= 65535, KZN_ERROR_FEATURE_NOT_PRESENT,
                 "draw: render area reaches beyond pixel 65535 (pixel boxes are packed into 16 bits per coordinate)");
     KZN_REQUIRE(total <= 0x7fffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: more than 2^31 triangles in one draw");

@@ -209,16 +209,21 @@ def _random_region(rng, spec):
                              offset=(ox, oy, oz), base_layer=base, layer_count=count)
 
 
-def test_random_regions_agree_with_the_oracle_in_result_code_and_bytes(gpu):
+import os  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KZN_FUZZ_SEEDS", "20261018").split(",")])
+def test_random_regions_agree_with_the_oracle_in_result_code_and_bytes(gpu, seed):
     """Differential test on 150 random regions over four image shapes: the GPU path and the oracle must return the same
     VkResult, and when they accept the region, the same bytes (buffer -> image and back)."""
     import ctypes as C
-    rng = np.random.default_rng(20261018)
+    rng = np.random.default_rng(seed)
     lib = ob.load()
     shapes = [dict(width=61, height=37), dict(width=128, height=24, array_layers=3), dict(width=20, height=12, depth=5),
               dict(width=70, height=41, tiling=abi.TILING_TILED, array_layers=2)]
     accepted = rejected = 0
-    for k in range(150):
+    n_regions = int(os.environ.get("KZN_FUZZ_REGIONS", "150"))
+    for k in range(n_regions):
         spec = shapes[k % len(shapes)]
         region = _random_region(rng, spec)
         buffer_bytes = 64 + 4 * (spec["width"] + 8) * (spec["height"] + 4) * spec.get("depth", 1) * spec.get("array_layers", 1)
@@ -250,4 +255,4 @@ def test_random_regions_agree_with_the_oracle_in_result_code_and_bytes(gpu):
         else:
             rejected += 1
         gpu.release()
-    assert accepted > 90 and rejected > 15
+    assert accepted > 0.6 * n_regions and rejected > 0.1 * n_regions
