@@ -256,3 +256,87 @@ def test_random_regions_agree_with_the_oracle_in_result_code_and_bytes(gpu, seed
             rejected += 1
         gpu.release()
     assert accepted > 0.6 * n_regions and rejected > 0.1 * n_regions
+
+
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KZN_FUZZ_SEEDS", "20261018").split(",")])
+def test_random_image_copies_blits_and_rect_clears_agree_with_the_oracle(gpu, seed):
+    """Differential test of vkCmdCopyImage, vkCmdBlitImage (NEAREST and LINEAR, flips and scales included) and
+    vkCmdClearAttachments on random boxes between LINEAR / TILED images of different shapes: result code and bytes."""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    lib = ob.load()
+    shapes = [dict(width=45, height=33), dict(width=64, height=20, array_layers=2), dict(width=18, height=10, depth=4),
+              dict(width=50, height=37, tiling=abi.TILING_TILED), dict(width=96, height=16, tiling=abi.TILING_TILED, array_layers=2)]
+    n_cases = int(os.environ.get("KZN_FUZZ_REGIONS", "150"))
+    done = {"copy": 0, "blit": 0, "clear": 0, "rejected": 0}
+
+    def box(spec_f, rng):
+        w, h, d = spec_f["width"], spec_f["height"], spec_f["depth"]
+        ew, eh, ed = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1)), int(rng.integers(1, d + 1))
+        return (int(rng.integers(0, w - ew + 1)), int(rng.integers(0, h - eh + 1)), int(rng.integers(0, d - ed + 1))), (ew, eh, ed)
+
+    for k in range(n_cases):
+        s_spec, d_spec = shapes[int(rng.integers(0, len(shapes)))], shapes[int(rng.integers(0, len(shapes)))]
+        sf, df = cases.image_desc_fields(s_spec), cases.image_desc_fields(d_spec)
+        s0, d0 = ob.random_bytes(runners._size(s_spec), 900 + k), ob.random_bytes(runners._size(d_spec), 1900 + k)
+        o_s, o_d = s0.copy(), d0.copy()
+        g_s, g_d = gpu.buffer(s0.nbytes, s0), gpu.buffer(d0.nbytes, d0)
+        osd, odd = runners._img(s_spec, ob.ptr(o_s)), runners._img(d_spec, ob.ptr(o_d))
+        hs, hd = runners._host_img(s_spec, g_s.address), runners._host_img(d_spec, g_d.address)
+        kind = ("copy", "blit", "clear")[k % 3]
+        sl = abi.ImageSubresourceLayers(abi.ASPECT_COLOR, 0, int(rng.integers(0, sf["array_layers"])), 1)
+        dl = abi.ImageSubresourceLayers(abi.ASPECT_COLOR, 0, int(rng.integers(0, df["array_layers"] + (rng.random() < 0.1))), 1)
+        if kind == "copy":
+            (sx, sy, sz), (ew, eh, ed) = box(sf, rng)
+            dx, dy, dz = int(rng.integers(0, df["width"])), int(rng.integers(0, df["height"])), int(rng.integers(0, df["depth"]))
+            if rng.random() < 0.75:  # usually make the destination box fit
+                ew, eh, ed = min(ew, df["width"] - dx), min(eh, df["height"] - dy), min(ed, df["depth"] - dz)
+            reg = abi.ImageCopy(sl, abi.Offset3D(sx, sy, sz), dl, abi.Offset3D(dx, dy, dz), abi.Extent3D(ew, eh, ed))
+            a, n = util.arr(abi.ImageCopy, [reg])
+            want = lib.kzo_copy_image(C.byref(osd), C.byref(odd), n, a)
+            run = lambda: gpu.queue.cmd_copy_image(hs, hd, [reg])
+        elif kind == "blit":
+            (sx, sy, sz), (sw, sh, sd_) = box(sf, rng)
+            (dx, dy, dz), (dw, dh, dd_) = box(df, rng)
+            so = [abi.Offset3D(sx, sy, sz), abi.Offset3D(sx + sw, sy + sh, sz + sd_)]
+            do = [abi.Offset3D(dx, dy, dz), abi.Offset3D(dx + dw, dy + dh, dz + dd_)]
+            if rng.random() < 0.3:
+                so[0].x, so[1].x = so[1].x, so[0].x  # mirrored source
+            if rng.random() < 0.3:
+                do[0].y, do[1].y = do[1].y, do[0].y  # mirrored destination
+            reg = abi.ImageBlit(sl, (abi.Offset3D * 2)(*so), dl, (abi.Offset3D * 2)(*do))
+            filt = int(rng.integers(0, 2))
+            a, n = util.arr(abi.ImageBlit, [reg])
+            want = lib.kzo_blit_image(C.byref(osd), C.byref(odd), n, a, filt)
+            run = lambda: gpu.queue.cmd_blit_image(hs, hd, [reg], filt)
+        else:
+            if df["depth"] != 1:
+                d_spec = shapes[0]
+                df = cases.image_desc_fields(d_spec)
+                d0 = ob.random_bytes(runners._size(d_spec), 1900 + k)
+                o_d = d0.copy()
+                g_d = gpu.buffer(d0.nbytes, d0)
+                odd, hd = runners._img(d_spec, ob.ptr(o_d)), runners._host_img(d_spec, g_d.address)
+            (dx, dy, _), (dw, dh, _) = box(df, rng)
+            if rng.random() < 0.1:
+                dw = df["width"] - dx + 1  # sticks out
+            rect = abi.ClearRect(abi.Rect2D(abi.Offset2D(dx, dy), abi.Extent2D(dw, dh)), int(rng.integers(0, df["array_layers"])), 1)
+            value = tuple(float(v) for v in rng.uniform(-0.2, 1.2, 4))
+            cv = abi.ClearColorValue()
+            cv.float32[:] = list(value)
+            a, n = util.arr(abi.ClearRect, [rect])
+            want = lib.kzo_clear_attachment(C.byref(odd), C.byref(cv), n, a)
+            run = lambda: gpu.queue.cmd_clear_attachment(hd, value, [rect])
+        got = abi.SUCCESS
+        try:
+            run()
+        except host.KazanError as e:
+            got = e.code
+        assert got == want, (k, kind, s_spec, d_spec)
+        if want == abi.SUCCESS:
+            done[kind] += 1
+            assert g_d.download().tobytes() == o_d.tobytes(), (k, kind, s_spec, d_spec)
+        else:
+            done["rejected"] += 1
+        gpu.release()
+    assert min(done["copy"], done["blit"], done["clear"]) > 0.15 * n_cases and done["rejected"] > 0
