@@ -183,3 +183,21 @@ def test_backend_trait_surface_rules():
     b.build_return(slot)
     assert "kzn_return_slot" in m2.verify().to_ptx()
     ctx.destroy()
+
+
+def test_ptx_of_random_programs_assembles_for_sm_100a(tmp_path):
+    """CPU: the PTX emitted for 25 random programs (tests/ir_random.py) is accepted by ptxas for sm_100a."""
+    import os
+    from tests import ir_random
+    ptxas = PTXAS
+    if not os.path.exists(ptxas):
+        pytest.skip("ptxas not available")
+    for seed in range(25):
+        text, _, _ = ir_random.make_program(seed)
+        module = backend.IrModule.parse(text)
+        ptx = module.to_ptx()
+        module.destroy()
+        f = tmp_path / f"p{seed}.ptx"
+        f.write_text(ptx)
+        r = subprocess.run([ptxas, "-arch=sm_100a", "-o", "/dev/null", str(f)], capture_output=True, text=True)
+        assert r.returncode == 0, (seed, r.stderr[:500])
