@@ -14,7 +14,7 @@
 //   errors                       generate.rs:1600-1642  (same messages)
 // Goldens: spirv-parser/src/lib.rs:46-215 (test_inputs/test.spv, test2.spv, test3.spv), reproduced byte for byte in
 // tests/test_spirv_dis.py.  The instruction table below is hand-written from the SPIR-V 1.3 specification (core
-// instructions 0-403 without the OpenCL pipe/enqueue and group instructions); an opcode outside it is reported as the
+// instructions 0-403 without the OpenCL pipe / device-enqueue instructions); an opcode outside it is reported as the
 // reference reports an unknown opcode.
 #include <cstdio>
 #include <map>
@@ -116,6 +116,7 @@ const EnumEntry kCapability[] = {
     E(4450, "StoragePushConstant8")};
 const EnumEntry kScope[] = {E(0, "CrossDevice"), E(1, "Device"), E(2, "Workgroup"), E(3, "Subgroup"), E(4, "Invocation"), E(5, "QueueFamily")};
 const EnumEntry kGroupOperation[] = {E(0, "Reduce"), E(1, "InclusiveScan"), E(2, "ExclusiveScan"), E(3, "ClusteredReduce")};
+// (OpGroupNonUniform* with ClusteredReduce carry the cluster size as a further id: the optional last operand)
 
 // bit enums (value = one bit; entry with value 0 names the empty mask)
 const EnumEntry kImageOperands[] = {E(0, "None"), EP(0x1, "Bias", "I"), EP(0x2, "Lod", "I"), EP(0x4, "Grad", "I I"), EP(0x8, "ConstOffset", "I"),
@@ -240,12 +241,36 @@ const OpInfo kOps[] = {
     {317, "OpNoLine", ""}, {318, "OpAtomicFlagTestAndSet", "T R I I I"}, {319, "OpAtomicFlagClear", "I I I"},
     {320, "OpImageSparseRead", "T R I I BImageOperands?"}, {321, "OpSizeOf", "T R I"}, {330, "OpModuleProcessed", "S"},
     {331, "OpExecutionModeId", "I EExecutionMode"}, {332, "OpDecorateId", "I EDecoration"},
+    // subgroup operations of Vulkan 1.1 (the scope operand is an id)
     {333, "OpGroupNonUniformElect", "T R I"}, {334, "OpGroupNonUniformAll", "T R I I"}, {335, "OpGroupNonUniformAny", "T R I I"},
     {336, "OpGroupNonUniformAllEqual", "T R I I"}, {337, "OpGroupNonUniformBroadcast", "T R I I I"},
     {338, "OpGroupNonUniformBroadcastFirst", "T R I I"}, {339, "OpGroupNonUniformBallot", "T R I I"},
+    {340, "OpGroupNonUniformInverseBallot", "T R I I"}, {341, "OpGroupNonUniformBallotBitExtract", "T R I I I"},
+    {342, "OpGroupNonUniformBallotBitCount", "T R I EGroupOperation I"}, {343, "OpGroupNonUniformBallotFindLSB", "T R I I"},
+    {344, "OpGroupNonUniformBallotFindMSB", "T R I I"},
     {345, "OpGroupNonUniformShuffle", "T R I I I"}, {346, "OpGroupNonUniformShuffleXor", "T R I I I"},
     {347, "OpGroupNonUniformShuffleUp", "T R I I I"}, {348, "OpGroupNonUniformShuffleDown", "T R I I I"},
     {349, "OpGroupNonUniformIAdd", "T R I EGroupOperation I I?"}, {350, "OpGroupNonUniformFAdd", "T R I EGroupOperation I I?"},
+    {351, "OpGroupNonUniformIMul", "T R I EGroupOperation I I?"}, {352, "OpGroupNonUniformFMul", "T R I EGroupOperation I I?"},
+    {353, "OpGroupNonUniformSMin", "T R I EGroupOperation I I?"}, {354, "OpGroupNonUniformUMin", "T R I EGroupOperation I I?"},
+    {355, "OpGroupNonUniformFMin", "T R I EGroupOperation I I?"}, {356, "OpGroupNonUniformSMax", "T R I EGroupOperation I I?"},
+    {357, "OpGroupNonUniformUMax", "T R I EGroupOperation I I?"}, {358, "OpGroupNonUniformFMax", "T R I EGroupOperation I I?"},
+    {359, "OpGroupNonUniformBitwiseAnd", "T R I EGroupOperation I I?"}, {360, "OpGroupNonUniformBitwiseOr", "T R I EGroupOperation I I?"},
+    {361, "OpGroupNonUniformBitwiseXor", "T R I EGroupOperation I I?"}, {362, "OpGroupNonUniformLogicalAnd", "T R I EGroupOperation I I?"},
+    {363, "OpGroupNonUniformLogicalOr", "T R I EGroupOperation I I?"}, {364, "OpGroupNonUniformLogicalXor", "T R I EGroupOperation I I?"},
+    {365, "OpGroupNonUniformQuadBroadcast", "T R I I I"}, {366, "OpGroupNonUniformQuadSwap", "T R I I I"},
+    // group instructions (Groups capability) and sparse image instructions
+    {259, "OpGroupAsyncCopy", "T R I I I I I I"}, {260, "OpGroupWaitEvents", "I I I"}, {261, "OpGroupAll", "T R I I"},
+    {262, "OpGroupAny", "T R I I"}, {263, "OpGroupBroadcast", "T R I I I"}, {264, "OpGroupIAdd", "T R I EGroupOperation I"},
+    {265, "OpGroupFAdd", "T R I EGroupOperation I"}, {266, "OpGroupFMin", "T R I EGroupOperation I"},
+    {267, "OpGroupUMin", "T R I EGroupOperation I"}, {268, "OpGroupSMin", "T R I EGroupOperation I"},
+    {269, "OpGroupFMax", "T R I EGroupOperation I"}, {270, "OpGroupUMax", "T R I EGroupOperation I"},
+    {271, "OpGroupSMax", "T R I EGroupOperation I"},
+    {305, "OpImageSparseSampleImplicitLod", "T R I I BImageOperands?"}, {306, "OpImageSparseSampleExplicitLod", "T R I I BImageOperands"},
+    {307, "OpImageSparseSampleDrefImplicitLod", "T R I I I BImageOperands?"},
+    {308, "OpImageSparseSampleDrefExplicitLod", "T R I I I BImageOperands"}, {313, "OpImageSparseFetch", "T R I I BImageOperands?"},
+    {314, "OpImageSparseGather", "T R I I I BImageOperands?"}, {315, "OpImageSparseDrefGather", "T R I I I BImageOperands?"},
+    {316, "OpImageSparseTexelsResident", "T R I"},
     {400, "OpCopyLogical", "T R I"}, {401, "OpPtrEqual", "T R I I"}, {402, "OpPtrNotEqual", "T R I I"}, {403, "OpPtrDiff", "T R I I"},
     {5632, "OpDecorateString", "I EDecoration"}, {5633, "OpMemberDecorateString", "I L EDecoration"}};
 

@@ -101,3 +101,14 @@ def test_malformed_modules_report_the_reference_errors(words, message):
     with pytest.raises(host.KazanError) as e:
         backend.disassemble_spirv(words)
     assert e.value.code == abi.ERROR_VALIDATION_FAILED and message in str(e.value)
+
+
+def test_subgroup_instructions_of_vulkan_1_1():
+    """OpGroupNonUniform*: the scope is an id, the group operation an enumerant, ClusteredReduce carries a cluster size."""
+    m = _module((21, 1, 32, 0), (43, 1, 2, 3), (339, 1, 4, 2, 5), (349, 1, 6, 2, 3, 7, 8), (366, 1, 9, 2, 7, 10),
+                (342, 1, 11, 2, 0, 12), bound=16, version=0x00010300)
+    text = backend.disassemble_spirv(m)
+    assert "%4 = OpGroupNonUniformBallot %1 %2 %5 ;" in text
+    assert "%6 = OpGroupNonUniformIAdd %1 %2 ClusteredReduce %7 %8 ;" in text
+    assert "%9 = OpGroupNonUniformQuadSwap %1 %2 %7 %10 ;" in text
+    assert "%11 = OpGroupNonUniformBallotBitCount %1 %2 Reduce %12 ;" in text
