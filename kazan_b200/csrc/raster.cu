@@ -5,17 +5,26 @@
 // Limits honoured: subPixelPrecisionBits 4 (api_impl.rs:1559), single sample at the pixel centre
 // (standardSampleLocations, api_impl.rs:1609), one viewport (api_impl.rs:1566), no depth clamp (api_impl.rs:887).
 //
-// Pipeline (one stream, no host round trip):
-//   setup_kernel   1 thread / triangle: index + vertex fetch, passthrough VS, clip->window (R1), snap to 1/16 px (R2),
-//                  signed area / cull (R4), sign-normalised integer edge equations + top-left bias (R5), pixel bbox.
-//                  Writes one 144-byte TriRec per triangle.
-//   bin_count / bin_scan / bin_fill   screen-tile binning: per 128x8-pixel tile, the list of overlapping triangles
-//                  (atomics give an unordered list; the raster kernel sorts it in shared memory so that per-pixel
-//                  fragment order == primitive order, R7).
-//   raster_kernel  1 CTA / 128x8 screen tile, 1 thread / 4 adjacent pixels: the tile's colour and depth live in REGISTERS for the whole
-//                  triangle list (each framebuffer byte is read at most once and written at most once per draw);
-//                  fixed-point coverage (int64 edge functions, bias test), barycentric depth (R6), z clip, early-Z,
-//                  fragment program, blend (R8), one 16-byte vector store per thread (512 B contiguous per warp).
+// Pipeline (one stream, no host round trip; the kernels of a draw are chained by programmatic dependent launch):
+//   setup_kernel   1 thread / triangle: primitive assembly (list / strip / fan), index + vertex fetch, passthrough VS,
+//                  clip->window (R1), snap to 1/16 px (R2), signed area / cull (R4), sign-normalised integer edge equations
+//                  + top-left bias (R5), pixel box.  One 144-byte TriRec per triangle that can produce fragments (written
+//                  through shared memory as coalesced 16-byte stores) and one packed 8-byte pixel box per triangle; the first
+//                  binning pass (tile counts) is fused in.
+//   bin_scan / bin_fill   screen-tile binning from the packed boxes: per 128x8-pixel tile, the list of overlapping triangles
+//                  (atomics give an unordered list; the raster kernel sorts it so that per-pixel fragment order == primitive
+//                  order, R7).
+//   raster_kernel  binned draws.  1 CTA / 128x8 tile, warp w = row w; the tile's colour and depth live in shared memory for
+//                  the whole list (each framebuffer byte read at most once, written at most once).  After the in-tile radix
+//                  sort every row warp streams the list on its own (no CTA barrier): box filter -> pending list -> chunks of
+//                  32 triangles copied to private slots by cp.async -> exact spans -> candidate pixels -> fragment queue ->
+//                  shading in full 32-lane batches.  Spans of >= 64 pixels take a 4-pixels-per-lane path.
+//   raster_direct_kernel  draws of <= 256 triangles (fullscreen passes, quads).  Persistent one-warp CTAs over a work counter,
+//                  256x4-pixel blocks, 8 pixels per lane in registers; blocks that the last triangle covers completely and
+//                  opaquely are pure shader work (packed FFMA2 orbit, magic-add UNORM8 conversion).  Draws of <= 32
+//                  triangles have no setup_kernel: each warp makes the records itself.
+// Coverage: int64 edge functions with a bias test (R5); depth: barycentric fp32 (R6), z clip, early-Z (R7); then the fragment
+// program, blend or logic op, write mask (R8).
 // Numerics are the oracle's rules R1-R8 (oracle/raster.c): every fp32 operation is written out; the file is compiled
 // with -fmad=false so only the explicit fmaf() calls fuse.
 #include <math.h>
