@@ -16,6 +16,10 @@
 //   box_kernel<...>      general box copy/fill between LINEAR (pitched) and TILED surfaces,
 //                        16-byte vectors when alignment allows, 4-byte texels otherwise
 //   blit_kernel          scaled RGBA8 copy, NEAREST (integer path) or LINEAR (fp32, no contraction)
+//   copy_realign_kernel  contiguous copy whose source is only 4-byte aligned: aligned 16-byte loads, the neighbour's
+//                        vector by shuffle, realigned 16-byte stores
+//   merged_transfer_kernel  up to 96 recorded contiguous fills / copies with disjoint ranges as one launch
+// Except for the two bulk (TMA) kernels, launches use programmatic dependent launch (kzn_internal.h).
 // All of them are bandwidth bound; algorithmic bytes per texel are 4 (fill) or 8 (copy).
 #include <stdlib.h>
 #include <string.h>
