@@ -539,8 +539,20 @@ KznBackendType* kzn_backend_type_pointer(KznBackendContext* c, KznBackendType* t
     t.size = t.align = 8;
     return c->type(t);
 }
+// No type of this back end can be larger than what a kernel could ever address as one variable; the bound also keeps the
+// size arithmetic below from wrapping around (an array of 2^62 i64 "had" size 0).
+static const uint64_t kMaxTypeBytes = 1ull << 40;
+static bool sized_ok(uint64_t element_size, uint64_t count) {
+    if (element_size != 0 && count > kMaxTypeBytes / element_size) {
+        kzn_set_error("type of %llu x %llu bytes is larger than the back end's limit of 2^40 bytes", (unsigned long long)count,
+                      (unsigned long long)element_size);
+        return false;
+    }
+    return true;
+}
+
 KznBackendType* kzn_backend_type_array(KznBackendContext* c, KznBackendType* element, uint64_t count) {
-    if (!c || !element) return nullptr;
+    if (!c || !element || !sized_ok(element->size, count)) return nullptr;
     KznBackendType t{BtKind::Array};
     t.element = element;
     t.count = count;
@@ -549,7 +561,12 @@ KznBackendType* kzn_backend_type_array(KznBackendContext* c, KznBackendType* ele
     return c->type(t);
 }
 KznBackendType* kzn_backend_type_vector(KznBackendContext* c, KznBackendType* element, uint64_t length) {
-    if (!c || !element || length == 0) return nullptr;
+    if (!c || !element) return nullptr;
+    if (length == 0) {
+        kzn_set_error("a vector type has at least one element");
+        return nullptr;
+    }
+    if (!sized_ok(element->size, length)) return nullptr;
     KznBackendType t{BtKind::Vector};
     t.element = element;
     t.count = length;
@@ -568,6 +585,7 @@ KznBackendType* kzn_backend_type_struct(KznBackendContext* c, KznBackendType* co
         t.members.push_back(members[i]);
         uint64_t a = members[i]->align ? members[i]->align : 1;
         off = (off + a - 1) / a * a;
+        if (!sized_ok(1, off) || !sized_ok(1, members[i]->size)) return nullptr;
         off += members[i]->size;
         if (a > align) align = a;
     }

@@ -201,3 +201,20 @@ def test_ptx_of_random_programs_assembles_for_sm_100a(tmp_path):
         f.write_text(ptx)
         r = subprocess.run([ptxas, "-arch=sm_100a", "-o", "/dev/null", str(f)], capture_output=True, text=True)
         assert r.returncode == 0, (seed, r.stderr[:500])
+
+
+def test_backend_types_are_bounded():
+    """Type sizes may not wrap around or loop: the constructors refuse anything larger than 2^40 bytes and empty vectors."""
+    ctx = backend.Context()
+    i8, i64 = ctx.build_i8(), ctx.build_i64()
+    assert ctx.type_size(ctx.build_array(i64, 1000)) == 8000
+    assert ctx.type_size(ctx.build_array(i8, 0)) == 0
+    for make in (lambda: ctx.build_array(i64, 2**62),                       # 2^65 bytes used to wrap to size 0
+                 lambda: ctx.build_array(ctx.build_array(i64, 2**30), 2**30),
+                 lambda: ctx.build_vector(i64, 2**60 + 1),                  # the alignment loop never ended for this one
+                 lambda: ctx.build_vector(i8, 0),
+                 lambda: ctx.build_struct([ctx.build_array(i8, 2**39)] * 4)):
+        with pytest.raises(host.KazanError) as e:
+            make()
+        assert e.value.code == abi.ERROR_VALIDATION_FAILED and str(e.value).split(": ", 1)[1]
+    ctx.destroy()
