@@ -433,6 +433,7 @@ KznResult kzn_image_memory_requirements(const KznImageDesc* image, uint64_t* siz
     KZN_REQUIRE(image->mip_levels == 1, KZN_ERROR_FEATURE_NOT_PRESENT, "mip_levels must be 1 (image.rs:65)");
     KZN_VALID(image->tiling <= KZN_TILING_TILED, "bad tiling %u", image->tiling);
     KZN_VALID(image->width && image->height && image->depth && image->array_layers, "zero image extent");
+    KZN_VALID(kzn_image_size_fits(image), "image byte size overflows (checked_mul in image.rs:74-82 panics)");
     uint64_t bytes = kzn_slice_pitch(image) * image->depth * image->array_layers;
     if (size) *size = kzn_round_up(bytes, KZN_IMAGE_ALIGNMENT);
     if (alignment) *alignment = KZN_IMAGE_ALIGNMENT;
@@ -590,6 +591,7 @@ KznResult kzn_check_image(const KznImageDesc* im, const char* what) {
     KZN_REQUIRE(im->mip_levels == 1, KZN_ERROR_FEATURE_NOT_PRESENT, "%s: mip_levels must be 1 (image.rs:65)", what);
     KZN_VALID(im->tiling <= KZN_TILING_TILED, "%s: bad tiling %u", what, im->tiling);
     KZN_VALID(im->width && im->height && im->depth && im->array_layers, "%s: zero image extent", what);
+    KZN_VALID(kzn_image_size_fits(im), "%s: image byte size overflows (checked_mul in image.rs:74-82 panics)", what);
     KZN_VALID(im->address != 0, "%s: image has no memory bound", what);
     KZN_VALID(im->address % 4 == 0, "%s: image address must be texel aligned", what);
     return KZN_SUCCESS;

@@ -103,7 +103,7 @@ static inline uint32_t kzn_texel_size(uint32_t format) {
     return (format == KZN_FORMAT_R8G8B8A8_UNORM || format == KZN_FORMAT_D32_SFLOAT) ? 4u : 0u;
 }
 static inline uint64_t kzn_round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
-static inline uint32_t kzn_tiles(uint32_t texels) { return (texels + KZN_TILE_DIM - 1) / KZN_TILE_DIM; }
+static inline uint32_t kzn_tiles(uint32_t texels) { return (uint32_t)(((uint64_t)texels + KZN_TILE_DIM - 1) / KZN_TILE_DIM); }
 static inline uint64_t kzn_row_pitch(const KznImageDesc* im) {  // LINEAR only
     return (uint64_t)kzn_texel_size(im->format) * im->width;
 }
@@ -112,6 +112,20 @@ static inline uint64_t kzn_slice_pitch(const KznImageDesc* im) {
     if (im->tiling == KZN_TILING_TILED)
         return (uint64_t)kzn_tiles(im->width) * kzn_tiles(im->height) * KZN_TILE_DIM * KZN_TILE_DIM * ts;
     return ts * im->width * im->height;
+}
+// false when the image's byte size does not fit 2^62: the reference computes it with checked_mul().unwrap()
+// (image.rs:74-82) and panics; here the image is rejected before any address arithmetic can wrap around
+static inline bool kzn_image_size_fits(const KznImageDesc* im) {
+    unsigned long long w = im->width, h = im->height;
+    if (im->tiling == KZN_TILING_TILED) {
+        w = (unsigned long long)kzn_tiles(im->width) * KZN_TILE_DIM;
+        h = (unsigned long long)kzn_tiles(im->height) * KZN_TILE_DIM;
+    }
+    unsigned long long n = 0;
+    if (__builtin_mul_overflow(w, h, &n) || __builtin_mul_overflow(n, (unsigned long long)im->depth, &n) ||
+        __builtin_mul_overflow(n, (unsigned long long)im->array_layers, &n) || __builtin_mul_overflow(n, 4ull, &n))
+        return false;
+    return n < (1ull << 62);
 }
 KznResult kzn_check_image(const KznImageDesc* im, const char* what);
 

@@ -64,8 +64,8 @@ static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint64_t slice_pitch(const KznImageDesc* im) {
     uint64_t ts = kzo_texel_size(im->format);
     if (im->tiling == KZN_TILING_TILED) {
-        uint64_t tx = (im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
-        uint64_t ty = (im->height + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
+        uint64_t tx = ((uint64_t)im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
+        uint64_t ty = ((uint64_t)im->height + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
         return tx * ty * KZN_TILE_DIM * KZN_TILE_DIM * ts;
     }
     return ts * im->width * im->height;
@@ -75,7 +75,7 @@ uint64_t kzo_texel_offset(const KznImageDesc* im, uint32_t x, uint32_t y, uint32
     uint64_t ts = kzo_texel_size(im->format);
     uint64_t slice = (uint64_t)z + (uint64_t)im->depth * layer;
     if (im->tiling == KZN_TILING_TILED) {
-        uint64_t tiles_x = (im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
+        uint64_t tiles_x = ((uint64_t)im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM;
         uint64_t tile = (uint64_t)(y / KZN_TILE_DIM) * tiles_x + x / KZN_TILE_DIM;
         uint64_t within = (uint64_t)(y % KZN_TILE_DIM) * KZN_TILE_DIM + x % KZN_TILE_DIM;
         return slice * slice_pitch(im) + (tile * KZN_TILE_DIM * KZN_TILE_DIM + within) * ts;
@@ -90,6 +90,17 @@ static KznResult check_image(const KznImageDesc* im) {
     if (im->mip_levels != 1) return KZN_ERROR_FEATURE_NOT_PRESENT; /* image.rs:65 */
     if (im->tiling > KZN_TILING_TILED) return KZN_ERROR_VALIDATION_FAILED;
     if (!im->width || !im->height || !im->depth || !im->array_layers) return KZN_ERROR_VALIDATION_FAILED;
+    { /* the reference computes the size with checked_mul().unwrap() (image.rs:74-82): an overflowing size is a panic */
+        unsigned long long w = im->width, h = im->height, n = 0;
+        if (im->tiling == KZN_TILING_TILED) {
+            w = (unsigned long long)(((uint64_t)im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM) * KZN_TILE_DIM;
+            h = (unsigned long long)(((uint64_t)im->height + KZN_TILE_DIM - 1) / KZN_TILE_DIM) * KZN_TILE_DIM;
+        }
+        if (__builtin_mul_overflow(w, h, &n) || __builtin_mul_overflow(n, (unsigned long long)im->depth, &n) ||
+            __builtin_mul_overflow(n, (unsigned long long)im->array_layers, &n) || __builtin_mul_overflow(n, 4ull, &n) ||
+            n >= (1ull << 62))
+            return KZN_ERROR_VALIDATION_FAILED;
+    }
     return KZN_SUCCESS;
 }
 

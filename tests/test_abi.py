@@ -134,3 +134,14 @@ def test_image_memory_requirements_follow_image_rs():
     with pytest.raises(host.KazanError) as e:
         host.Image(0, 4, 4, mip_levels=2).memory_requirements()
     assert e.value.code == abi.ERROR_FEATURE_NOT_PRESENT
+
+
+def test_image_memory_requirements_reject_sizes_that_overflow():
+    """No GPU needed: kzn_image_memory_requirements is host arithmetic (image.rs:58-88 + checked_mul :74-82)."""
+    from kazan_b200 import host
+    for w, h, d, layers, tiling in [(2**32 - 1, 2**32 - 1, 1, 1, 0), (2**31, 2**31, 4, 4, 0), (2**32 - 1, 2**32 - 1, 1, 1, 1)]:
+        with __import__("pytest").raises(host.KazanError) as e:
+            host.Image(0x1000, w, h, d, layers, abi.FORMAT_R8G8B8A8_UNORM, tiling).memory_requirements()
+        assert e.value.code == abi.ERROR_VALIDATION_FAILED
+    assert host.Image(0x1000, 1024, 1024).memory_requirements() == (1024 * 1024 * 4, 64)
+    assert host.Image(0x1000, 50, 37, tiling=abi.TILING_TILED).memory_requirements() == (4 * 3 * 1024, 64)

@@ -186,3 +186,16 @@ def test_threads_do_not_change_results(oracle):
     b = runners.oracle_buffer_to_image(spec, regions, nbytes)
     oracle.kzo_set_threads(1)
     assert a == b
+
+
+def test_image_sizes_that_overflow_are_rejected(oracle):
+    """The reference computes an image's byte size with checked_mul().unwrap() (image.rs:74-82): a size that does not fit is a
+    panic there, an error here — in the oracle and (tests/test_abi.py) in the library alike, LINEAR and TILED."""
+    for w, h, d, layers, tiling in [(2**32 - 1, 2**32 - 1, 1, 1, 0), (2**31, 2**31, 4, 4, 0), (2**32 - 1, 2**32 - 1, 1, 1, 1),
+                                    (2**32 - 1, 2**28, 1, 1, 1)]:
+        desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, tiling, w, h, d, layers, 1, 0)
+        size, align = C.c_uint64(), C.c_uint64()
+        assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == abi.ERROR_VALIDATION_FAILED
+    desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, 0, 65536, 65536, 256, 256, 1, 0)  # 2^50 bytes: large but representable
+    size, align = C.c_uint64(), C.c_uint64()
+    assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == 0 and size.value == 1 << 50
