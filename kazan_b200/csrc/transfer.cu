@@ -732,9 +732,11 @@ KznResult check_buffer_image_region(const KznImageDesc* im, uint64_t buffer_size
     if (w && h && slices) {
         uint64_t row_len = c->bufferRowLength ? c->bufferRowLength : w;
         uint64_t img_h = c->bufferImageHeight ? c->bufferImageHeight : h;
-        uint64_t end = c->bufferOffset + ((((slices - 1) * img_h) + (h - 1)) * row_len + w) * ts;
-        KZN_VALID(end <= buffer_size, "%s: region needs %llu bytes, buffer has %llu (VUID 00171)", what,
-                  (unsigned long long)end, (unsigned long long)buffer_size);
+        // 128-bit: bufferRowLength and bufferImageHeight are free 32-bit values, the product may pass 2^64
+        const unsigned __int128 end = (unsigned __int128)c->bufferOffset +
+                                      ((((unsigned __int128)(slices - 1) * img_h) + (h - 1)) * row_len + w) * ts;
+        KZN_VALID(end <= buffer_size, "%s: region needs more bytes than the buffer has (%llu) (VUID 00171)", what,
+                  (unsigned long long)buffer_size);
     }
     return KZN_SUCCESS;
 }

@@ -241,7 +241,9 @@ static KznResult check_buffer_image_region(const KznImageDesc* im, uint64_t buff
     if (w && h && slices) {
         uint64_t row_len = c->bufferRowLength ? c->bufferRowLength : w;
         uint64_t img_h = c->bufferImageHeight ? c->bufferImageHeight : h;
-        uint64_t end = c->bufferOffset + ((((slices - 1) * img_h) + (h - 1)) * row_len + w) * ts;
+        /* 128-bit: bufferRowLength and bufferImageHeight are free 32-bit values, the product may pass 2^64 */
+        unsigned __int128 end = (unsigned __int128)c->bufferOffset +
+                                ((((unsigned __int128)(slices - 1) * img_h) + (h - 1)) * row_len + w) * ts;
         if (end > buffer_size) return KZN_ERROR_VALIDATION_FAILED; /* 00171 */
     }
     return KZN_SUCCESS;

@@ -130,6 +130,11 @@ def test_invalid_usage_returns_the_oracles_error_codes(gpu):
     assert code(lambda: q.cmd_clear_color_image(dimg, (0, 0, 0, 0))) == abi.ERROR_FORMAT_NOT_SUPPORTED
     assert code(lambda: q.cmd_fill_buffer(buf.address, buf.nbytes, 6, 8, 0)) == V
     assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img, [])) == V
+    # bufferRowLength x bufferImageHeight x slices past 2^64 must not wrap around and look small
+    img2 = host.Image(mem.address, 16, 16, array_layers=2)
+    huge = bic(16, 16, row_length=2**32 - 1, image_height=2**32 - 1, layer_count=2)
+    assert code(lambda: q.cmd_copy_buffer_to_image(buf.address, buf.nbytes, img2, [huge])) == V
+    assert code(lambda: q.cmd_copy_image_to_buffer(img2, buf.address, buf.nbytes, [huge])) == V
     gpu.release()
 
 

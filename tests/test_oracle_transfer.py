@@ -146,6 +146,11 @@ def test_invalid_usage_is_rejected(oracle):
     assert b2i(bic(64, 64), size=64 * 64 * 4 - 4) == V     # VUID 00171
     assert b2i(bic(64, 64, aspect=abi.ASPECT_DEPTH)) == V  # VUID 00212
     assert b2i(bic(64, 64, base_layer=1)) == V
+    # bufferRowLength x bufferImageHeight x slices past 2^64: the needed size must not wrap around and look small
+    mem2 = ob.aligned_empty(16 * 16 * 4 * 2)
+    d2 = abi.ImageDesc(ob.ptr(mem2), 37, 0, 16, 16, 1, 2, 1, 0)
+    a, n = ob.array_of(abi.BufferImageCopy, [bic(16, 16, row_length=2**32 - 1, image_height=2**32 - 1, layer_count=2)])
+    assert oracle.kzo_copy_buffer_to_image(C.c_void_p(ob.ptr(buf)), buf.nbytes, C.byref(d2), n, a) == V
     c = abi.ClearColorValue()
     a, n = ob.array_of(abi.ImageSubresourceRange, [abi.ImageSubresourceRange(abi.ASPECT_DEPTH, 0, 1, 0, 1)])
     assert oracle.kzo_clear_color_image(C.byref(d), C.byref(c), n, a) == V  # VUID 02498
