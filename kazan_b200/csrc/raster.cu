@@ -1577,6 +1577,8 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
     KZN_VALID(vi->stride % 4 == 0 && vi->position_offset % 4 == 0 && (vi->color_offset == ~0u || vi->color_offset % 4 == 0),
               "draw: vertex layout must be 4-byte aligned");
     KZN_VALID(vi->buffer_address && vi->buffer_address % 4 == 0, "draw: bad vertex buffer address");
+    // index (< 2^32 + |vertexOffset|) x stride must stay far from 2^64: the robust-fetch bounds test works on that product
+    KZN_VALID(vi->stride < (1u << 28), "draw: vertex stride of 2^28 bytes or more");
     return KZN_SUCCESS;
 }
 

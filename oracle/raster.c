@@ -300,6 +300,7 @@ static KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebu
     if (vi->stride % 4 || vi->position_offset % 4 || (vi->color_offset != ~0u && vi->color_offset % 4))
         return KZN_ERROR_VALIDATION_FAILED;
     if (!vi->buffer_address || vi->buffer_address % 4) return KZN_ERROR_VALIDATION_FAILED;
+    if (vi->stride >= (1u << 28)) return KZN_ERROR_VALIDATION_FAILED; /* index x stride stays far from 2^64 */
     return KZN_SUCCESS;
 }
 

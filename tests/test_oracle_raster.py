@@ -195,6 +195,9 @@ def test_invalid_draw_state_is_rejected():
     vi = abi.VertexInput(sc.vertices.ctypes.data, sc.vertices.nbytes, 28, 0, 3, 12)
     args = lambda st, vp: lib.kzo_draw(C.byref(st), C.byref(fb), C.byref(vp), C.byref(sc.scissor), C.byref(vi), 3, 1, 0, 0, None)
     assert args(sc.state, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
+    wide = abi.VertexInput(sc.vertices.ctypes.data, sc.vertices.nbytes, 1 << 28, 0, 3, 12)
+    assert lib.kzo_draw(C.byref(pipeline_state()), C.byref(fb), C.byref(sc.viewport), C.byref(sc.scissor), C.byref(wide), 3, 1, 0, 0,
+                        None) == abi.ERROR_VALIDATION_FAILED  # index x stride must stay far from 2^64
     lines = pipeline_state(topology=1)
     assert args(lines, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
     bad = pipeline_state()
