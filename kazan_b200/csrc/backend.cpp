@@ -480,9 +480,10 @@ KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const uint32_
         if (base_group) KZN_VALID((uint64_t)base_group[i] + group_count[i] <= 0xffffffffull, "baseGroup + groupCount overflows in dimension %d", i);
         total *= group_count[i];
         total *= pipeline->local_size[i];
+        // checked per dimension: six 32-bit factors can pass 2^128 and wrap around to something small
+        KZN_VALID(total <= (unsigned __int128)1 << 62, "dispatch of more than 2^62 invocations");
     }
     if (total == 0) return KZN_SUCCESS;  // a zero-sized dispatch is valid and does nothing
-    KZN_VALID(total <= (unsigned __int128)1 << 62, "dispatch of more than 2^62 invocations");
     uint64_t count = (uint64_t)total;
     KZN_VALID(pipeline->inputs_size == 0 || user_inputs_address, "pipeline reads user_inputs_block but no address was bound");
     KZN_VALID(pipeline->outputs_size == 0 || user_outputs_address, "pipeline writes user_outputs_block but no address was bound");
