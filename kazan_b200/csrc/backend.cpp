@@ -476,6 +476,8 @@ KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const uint32_
     // invocation count = groups * LocalSize; the base group only renumbers WorkgroupId (api_impl.rs:5079-5089), which
     // the IR cannot observe (interface.rs:61-67 has no compute built-ins), so it does not move the interface slots
     unsigned __int128 total = 1;
+    for (int i = 0; i < 3; ++i)
+        if (group_count[i] == 0 || pipeline->local_size[i] == 0) return KZN_SUCCESS;  // a zero-sized dispatch is valid and does nothing
     for (int i = 0; i < 3; ++i) {
         if (base_group) KZN_VALID((uint64_t)base_group[i] + group_count[i] <= 0xffffffffull, "baseGroup + groupCount overflows in dimension %d", i);
         total *= group_count[i];
@@ -483,7 +485,6 @@ KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const uint32_
         // checked per dimension: six 32-bit factors can pass 2^128 and wrap around to something small
         KZN_VALID(total <= (unsigned __int128)1 << 62, "dispatch of more than 2^62 invocations");
     }
-    if (total == 0) return KZN_SUCCESS;  // a zero-sized dispatch is valid and does nothing
     uint64_t count = (uint64_t)total;
     KZN_VALID(pipeline->inputs_size == 0 || user_inputs_address, "pipeline reads user_inputs_block but no address was bound");
     KZN_VALID(pipeline->outputs_size == 0 || user_outputs_address, "pipeline writes user_outputs_block but no address was bound");
