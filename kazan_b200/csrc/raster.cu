@@ -1572,6 +1572,10 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
     KZN_VALID(!fb->band_y1 || (fb->band_y0 < fb->band_y1 && fb->band_y1 <= *H), "draw: bad band");
     KZN_VALID(sc->offset.x >= 0 && sc->offset.y >= 0, "draw: negative scissor offset (VUID 00598)");
     KZN_VALID(vp->width > 0.0f && vp->height != 0.0f && finite_host(vp->height), "draw: bad viewport size");
+    // viewportBoundsRange: everything below converts these to integers, which is undefined for NaN / infinity / huge values
+    KZN_VALID(finite_host(vp->x) && finite_host(vp->y) && finite_host(vp->width) && fabsf(vp->x) <= 1048576.0f &&
+                  fabsf(vp->y) <= 1048576.0f && vp->width <= 1048576.0f && fabsf(vp->height) <= 1048576.0f,
+              "draw: viewport outside the +-2^20 bounds range");
     KZN_VALID(vp->minDepth >= 0.0f && vp->minDepth <= 1.0f && vp->maxDepth >= 0.0f && vp->maxDepth <= 1.0f, "draw: bad viewport depth range");
     KZN_VALID(vi->position_components == 3 || vi->position_components == 4, "draw: position must have 3 or 4 components");
     KZN_VALID(vi->stride % 4 == 0 && vi->position_offset % 4 == 0 && (vi->color_offset == ~0u || vi->color_offset % 4 == 0),

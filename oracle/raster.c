@@ -294,6 +294,10 @@ static KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebu
     if (fb->band_y1 && (fb->band_y0 >= fb->band_y1 || fb->band_y1 > *H)) return KZN_ERROR_VALIDATION_FAILED;
     if (sc->offset.x < 0 || sc->offset.y < 0) return KZN_ERROR_VALIDATION_FAILED; /* VUID 00598/00599 */
     if (!(vp->width > 0.0f) || vp->height == 0.0f || !is_finite(vp->height)) return KZN_ERROR_VALIDATION_FAILED;
+    /* viewportBoundsRange: the clip rectangle converts these to integers (undefined for NaN / infinity / huge values) */
+    if (!is_finite(vp->x) || !is_finite(vp->y) || !is_finite(vp->width) || fabsf(vp->x) > 1048576.0f ||
+        fabsf(vp->y) > 1048576.0f || vp->width > 1048576.0f || fabsf(vp->height) > 1048576.0f)
+        return KZN_ERROR_VALIDATION_FAILED;
     if (!(vp->minDepth >= 0.0f && vp->minDepth <= 1.0f && vp->maxDepth >= 0.0f && vp->maxDepth <= 1.0f))
         return KZN_ERROR_VALIDATION_FAILED;
     if (vi->position_components != 3 && vi->position_components != 4) return KZN_ERROR_VALIDATION_FAILED;

@@ -205,3 +205,6 @@ def test_invalid_draw_state_is_rejected():
     assert args(bad, sc.viewport) == abi.ERROR_VALIDATION_FAILED
     assert args(pipeline_state(), abi.Viewport(0, 0, 0, 8, 0, 1)) == abi.ERROR_VALIDATION_FAILED
     assert args(pipeline_state(), abi.Viewport(0, 0, 8, 8, 0, 2)) == abi.ERROR_VALIDATION_FAILED
+    for bad_vp in (abi.Viewport(float("nan"), 0, 8, 8, 0, 1), abi.Viewport(0, float("inf"), 8, 8, 0, 1),
+                   abi.Viewport(0, 0, float("inf"), 8, 0, 1), abi.Viewport(3e9, 0, 8, 8, 0, 1), abi.Viewport(0, 0, 8, -3e9, 0, 1)):
+        assert args(pipeline_state(), bad_vp) == abi.ERROR_VALIDATION_FAILED  # outside viewportBoundsRange
