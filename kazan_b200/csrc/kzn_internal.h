@@ -116,6 +116,9 @@ static inline uint64_t kzn_slice_pitch(const KznImageDesc* im) {
 // false when the image's byte size does not fit 2^62: the reference computes it with checked_mul().unwrap()
 // (image.rs:74-82) and panics; here the image is rejected before any address arithmetic can wrap around
 static inline bool kzn_image_size_fits(const KznImageDesc* im) {
+    // VkOffset3D is signed 32-bit: an extent past 2^31 - 1 could not be addressed by any region, and the kernels keep
+    // coordinates in int32
+    if (im->width > 0x7fffffffu || im->height > 0x7fffffffu || im->depth > 0x7fffffffu || im->array_layers > 0x7fffffffu) return false;
     unsigned long long w = im->width, h = im->height;
     if (im->tiling == KZN_TILING_TILED) {
         w = (unsigned long long)kzn_tiles(im->width) * KZN_TILE_DIM;

@@ -92,6 +92,9 @@ static KznResult check_image(const KznImageDesc* im) {
     if (!im->width || !im->height || !im->depth || !im->array_layers) return KZN_ERROR_VALIDATION_FAILED;
     { /* the reference computes the size with checked_mul().unwrap() (image.rs:74-82): an overflowing size is a panic */
         unsigned long long w = im->width, h = im->height, n = 0;
+        /* VkOffset3D is signed 32-bit: larger extents could not be addressed by any region */
+        if (im->width > 0x7fffffffu || im->height > 0x7fffffffu || im->depth > 0x7fffffffu || im->array_layers > 0x7fffffffu)
+            return KZN_ERROR_VALIDATION_FAILED;
         if (im->tiling == KZN_TILING_TILED) {
             w = (unsigned long long)(((uint64_t)im->width + KZN_TILE_DIM - 1) / KZN_TILE_DIM) * KZN_TILE_DIM;
             h = (unsigned long long)(((uint64_t)im->height + KZN_TILE_DIM - 1) / KZN_TILE_DIM) * KZN_TILE_DIM;

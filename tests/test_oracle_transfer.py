@@ -201,6 +201,9 @@ def test_image_sizes_that_overflow_are_rejected(oracle):
         desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, tiling, w, h, d, layers, 1, 0)
         size, align = C.c_uint64(), C.c_uint64()
         assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == abi.ERROR_VALIDATION_FAILED
+    desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, 0, 2**31, 1, 1, 1, 1, 0)  # small, but wider than any VkOffset3D
+    size, align = C.c_uint64(), C.c_uint64()
+    assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == abi.ERROR_VALIDATION_FAILED
     desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, 0, 65536, 65536, 256, 256, 1, 0)  # 2^50 bytes: large but representable
     size, align = C.c_uint64(), C.c_uint64()
     assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == 0 and size.value == 1 << 50
