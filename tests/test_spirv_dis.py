@@ -112,3 +112,19 @@ def test_subgroup_instructions_of_vulkan_1_1():
     assert "%6 = OpGroupNonUniformIAdd %1 %2 ClusteredReduce %7 %8 ;" in text
     assert "%9 = OpGroupNonUniformQuadSwap %1 %2 %7 %10 ;" in text
     assert "%11 = OpGroupNonUniformBallotBitCount %1 %2 Reduce %12 ;" in text
+
+
+def test_the_translators_fixture_disassembles_consistently_with_its_translation():
+    """trivial_test.spv (the SPIR-V -> IR golden of shader-compiler-translate-spirv-to-ir): what the reader prints and what
+    the translator produces describe the same module — entry point, LocalSize, the OpLine location, the source string."""
+    ir = json.loads((Path(__file__).parent / "golden" / "ir_goldens.json").read_text())["spirv_to_ir"][0]
+    words = _words(bytes.fromhex(ir["spv_hex"]))
+    text = backend.disassemble_spirv(words)
+    assert 'OpEntryPoint GLCompute %5 "main" ;' in text and "OpExecutionMode %5 LocalSize 1 1 1 ;" in text
+    assert '%1 = OpString "stdin" ;' in text and "OpLine %1 4 0 ;" in text
+    assert '\\n#version 450\\n\\nvoid main() {\\n    return;\\n}"' in text  # the source literal, Rust-debug escaped
+    module, local_size = backend.translate_spirv_to_ir(words, "main", backend.EXECUTION_MODEL_GLCOMPUTE)
+    assert local_size == (1, 1, 1)
+    translated = module.to_text()
+    module.destroy()
+    assert translated == ir["expected_ir"] and '"stdin":4:0' in translated  # the OpLine the reader printed, attached in the IR
