@@ -63,7 +63,7 @@ constexpr int kDstNone = 0;       // no blending, all channels written: the dest
 constexpr int kDstGeneric = 1;    // any blend state / write mask, resolved per fragment
 constexpr int kDstAlphaOver = 2;  // SRC_ALPHA, ONE_MINUS_SRC_ALPHA, ADD for colour and alpha, write mask RGBA
 
-struct __align__(16) TriRec {
+struct __align__(16) TriRec {  // expanded record: what the direct kernel and the wide-span path rasterise from
     int32_t minx, maxx, miny, maxy;  // inclusive, scissored; minx > maxx => produces no fragments
     int32_t a[3], b[3];
     uint32_t bias_bits;
@@ -73,6 +73,31 @@ struct __align__(16) TriRec {
     float col[3][4];  // colour * iw
 };
 static_assert(sizeof(TriRec) == 144, "TriRec layout");
+
+// Compact record of a binned draw (96 bytes, six 16-byte vectors): the snapped window coordinates and the per-vertex
+// interpolants.  Everything else a fragment needs — edge equations, top-left bias, 1/2A, the pixel box — is integer
+// arithmetic on X, Y and is re-derived per (triangle, row) by the row warp that rasterises it (derive in raster_chunk,
+// expand_record for the wide path): 50-odd instructions per triangle-row against 48 bytes per record that setup would
+// write and every row warp would read again.
+struct __align__(16) TriRecC {
+    int32_t X[3], Y[3];  // window coordinates in 1/16 pixel (R2)
+    float z[3], iw[3];
+    float col[3][4];  // colour * iw
+};
+static_assert(sizeof(TriRecC) == 96, "TriRecC layout");
+
+// What lane j of a row warp derives for triangle j of its chunk: the three edge functions at the first pixel of the
+// triangle's span in this row, biased so that "covered" is a sign test, and their step per pixel.  32-bit arithmetic is
+// exact here because only triangles whose snapped extent is below 2^14 subpixels (1024 pixels) in x and y take this path:
+// |a|,|b| < 2^14 and every sample of the pixel box is within the extent, so |E_i| < 2^29 (larger triangles go through
+// expand_record and the 64-bit quad path).
+struct __align__(16) RowEdge {
+    int32_t f[3];   // F_i = E_i + bias_i - 1 at the first pixel: the pixel is covered iff all three are >= 0 (R5)
+    uint32_t xw;    // first pixel's x within the tile | (1 - bias_i) << (8 + i) | depth-clip-cannot-reject << 11
+    int32_t s[3];   // 16 * a_i
+    float inv2a;
+};
+static_assert(sizeof(RowEdge) == 32, "RowEdge layout");
 
 struct DrawParams {
     // geometry
@@ -93,7 +118,7 @@ struct DrawParams {
     uint32_t fb_w, fb_h, color_tiled, color_tiles_x;
     float inv_fb_w, inv_fb_h;
     // scratch
-    TriRec* tris;
+    TriRec* tris;            // direct draws: expanded records; binned draws: the same memory holds TriRecC records
     uint2* boxes;            // [total_tris] minx | maxx << 16, miny | maxy << 16 (the records' pixel boxes, packed: the row filter reads only these)
     uint32_t* tile_counts;   // [tiles]  (bin_count)
     uint32_t* tile_offsets;  // [tiles+1] (bin_scan)
@@ -110,35 +135,32 @@ struct DrawParams {
 
 // ---- setup ------------------------------------------------------------------------------------------------
 
-struct VsOut {
-    float x, y, z, w;
-    float rgba[4];
-};
-
-__device__ __forceinline__ void fetch_vertex(const DrawParams& p, long long vidx, VsOut& o) {
-    o.x = o.y = o.z = 0.0f;
-    o.w = 1.0f;
-    o.rgba[0] = o.rgba[1] = o.rgba[2] = o.rgba[3] = 1.0f;
-    bool neg = vidx < 0;
-    unsigned long long off = (unsigned long long)vidx * p.stride;
-    if (!neg && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size) {
+// robust fetch of one vertex's position (x, y, z, w; w = 1 for three components; out of range reads 0, 0, 0, 1)
+__device__ __forceinline__ float4 fetch_position(const DrawParams& p, long long vidx) {
+    float4 o = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    const unsigned long long off = (unsigned long long)vidx * p.stride;
+    if (vidx >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size) {
         const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off);
         o.x = __ldg(s);
         o.y = __ldg(s + 1);
         o.z = __ldg(s + 2);
         if (p.pos_comps == 4) o.w = __ldg(s + 3);
     }
+    return o;
+}
+// ... and of its colour (1, 1, 1, 1 without a colour attribute; out of range reads 0, 0, 0, 1)
+__device__ __forceinline__ float4 fetch_color(const DrawParams& p, long long vidx) {
+    float4 o = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     if (p.col_off != ~0u) {
-        if (!neg && off + p.col_off + 16ull <= p.vertex_size) {
+        const unsigned long long off = (unsigned long long)vidx * p.stride;
+        if (vidx >= 0 && off + p.col_off + 16ull <= p.vertex_size) {
             const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.col_off);
-            o.rgba[0] = __ldg(s);
-            o.rgba[1] = __ldg(s + 1);
-            o.rgba[2] = __ldg(s + 2);
-            o.rgba[3] = __ldg(s + 3);
+            o = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
         } else {
-            o.rgba[0] = o.rgba[1] = o.rgba[2] = 0.0f;
+            o.x = o.y = o.z = 0.0f;
         }
     }
+    return o;
 }
 
 __device__ __forceinline__ bool finite_f(float f) { return (f - f) == 0.0f; }
@@ -202,15 +224,25 @@ __device__ __forceinline__ void bin_emit(const DrawParams& p, bool valid, uint32
     }
 }
 
-// Triangle t of an instance -> its record (R1-R5: fetch, passthrough VS, viewport, snap, cull, edge equations, pixel box).
-// false: the triangle produces no fragments (its box is left empty).
-__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r) {
-    r.minx = 1;
-    r.maxx = 0;
-    r.miny = 1;
-    r.maxy = 0;
+// bit 3 of TriRec::bias_bits / bit 11 of RowEdge::xw: the interpolated depth of every covered fragment is certainly
+// inside the depth-clip range, so the per-fragment z clip (R3) can be skipped.  Inside the triangle the barycentrics are in
+// [0,1] and the R6 expression is within a few ulp of a convex combination of the vertex depths: either all three are
+// exactly 0 (then every product and sum is exactly 0), or they keep a margin of 2^-16 from both ends.
+__device__ __forceinline__ bool depth_clip_cannot_reject(const DrawParams& p, float z0, float z1, float z2) {
+    const float zlo = fminf(z0, fminf(z1, z2)), zhi = fmaxf(z0, fmaxf(z1, z2));
+    const float margin = 1.52587890625e-05f;
+    const bool all_zero = zlo == 0.0f && zhi == 0.0f && p.zclip_lo <= 0.0f && p.zclip_hi >= 0.0f;
+    const bool inside = zlo >= p.zclip_lo + margin && zhi <= p.zclip_hi - margin && fabsf(zlo) <= 1.0f && fabsf(zhi) <= 1.0f;
+    return all_zero || inside;
+}
+
+// Triangle t of an instance -> its compact record (R1-R4: index + position fetch, passthrough VS, viewport, snap, cull)
+// and its scissored pixel box.  false: the triangle produces no fragments (box left empty; the record's colours are
+// not fetched — on a band of a split frame that is most of the scene).
+__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
+    box = make_int4(1, 0, 1, 0);  // minx maxx miny maxy
     bool ok = true;
-    int32_t X[3], Y[3];
+    long long vidx[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
@@ -218,17 +250,15 @@ __device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, Tri
         if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
         if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
         unsigned long long i = (unsigned long long)p.first + rel;
-        long long vidx;
         if (p.index_base) {
             unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
                                          ? (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(p.index_base) + i)
                                          : (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(p.index_base) + i);
-            vidx = (long long)raw + p.vertex_offset;
+            vidx[k] = (long long)raw + p.vertex_offset;
         } else {
-            vidx = (long long)i;
+            vidx[k] = (long long)i;
         }
-        VsOut v;
-        fetch_vertex(p, vidx, v);
+        const float4 v = fetch_position(p, vidx[k]);
         if (!(v.w > 0.0f)) ok = false;  // R3
         float iw = 1.0f / v.w;
         float xf = fmaf(p.hw, v.x * iw, p.ox);
@@ -236,98 +266,153 @@ __device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, Tri
         float zf = fmaf(p.dz, v.z * iw, p.zmin_vp);
         if (!finite_f(xf) || !finite_f(yf) || !finite_f(zf) || !finite_f(iw)) ok = false;
         if (fabsf(xf) > kGuardBand || fabsf(yf) > kGuardBand) ok = false;
-        X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
-        Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;
+        r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+        r.Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;
         r.z[k] = zf;
         r.iw[k] = iw;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) r.col[k][ch] = v.rgba[ch] * iw;
     }
-    long long two_a = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);  // R4
+    const long long two_a = (long long)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) - (long long)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);  // R4
     if (two_a == 0) ok = false;
-    bool front = p.st.front_face == 0 ? (two_a < 0) : (two_a > 0);
+    const bool front = p.st.front_face == 0 ? (two_a < 0) : (two_a > 0);
     if ((front && (p.st.cull_mode & 1u)) || (!front && (p.st.cull_mode & 2u))) ok = false;
-    long long s = two_a < 0 ? -1 : 1;
-    r.bias_bits = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {  // R5
-        int ia = (i + 1) % 3, ib = (i + 2) % 3;
-        long long dx = X[ib] - X[ia], dy = Y[ib] - Y[ia];
-        long long a = -dy * s, b = dx * s;
-        r.a[i] = (int32_t)a;
-        r.b[i] = (int32_t)b;
-        r.c[i] = s * (dy * X[ia] - dx * Y[ia]);
-        if (a > 0 || (a == 0 && b > 0)) r.bias_bits |= 1u << i;
-    }
-    r.inv2a = 1.0f / (float)(two_a * s);
-    {
-        // bit 3: the interpolated depth of every covered fragment is certainly inside the depth-clip range, so the
-        // raster kernel may skip the per-fragment z clip (R3).  Inside the triangle the barycentrics are in [0,1] and
-        // the R6 expression is within a few ulp of a convex combination of the vertex depths: either all three are
-        // exactly 0 (then every product and sum is exactly 0), or they keep a margin of 2^-16 from both ends.
-        const float zlo = fminf(r.z[0], fminf(r.z[1], r.z[2])), zhi = fmaxf(r.z[0], fmaxf(r.z[1], r.z[2]));
-        const float margin = 1.52587890625e-05f;
-        const bool all_zero = zlo == 0.0f && zhi == 0.0f && p.zclip_lo <= 0.0f && p.zclip_hi >= 0.0f;
-        const bool inside = zlo >= p.zclip_lo + margin && zhi <= p.zclip_hi - margin && fabsf(zlo) <= 1.0f && fabsf(zhi) <= 1.0f;
-        if (all_zero || inside) r.bias_bits |= 8u;
-    }
     if (ok) {
-        int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
-        int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
-        r.minx = max((minX - 8 + 15) >> 4, p.cx0);
-        r.maxx = min((maxX - 8) >> 4, p.cx1);
-        r.miny = max((minY - 8 + 15) >> 4, p.cy0);
-        r.maxy = min((maxY - 8) >> 4, p.cy1);
-        if (r.minx > r.maxx || r.miny > r.maxy) {
-            r.minx = 1; r.maxx = 0; r.miny = 1; r.maxy = 0;
+        const int32_t minX = min(r.X[0], min(r.X[1], r.X[2])), maxX = max(r.X[0], max(r.X[1], r.X[2]));
+        const int32_t minY = min(r.Y[0], min(r.Y[1], r.Y[2])), maxY = max(r.Y[0], max(r.Y[1], r.Y[2]));
+        // pixels whose sample 16p + 8 lies in [min, max]; the arithmetic shift is a floor division
+        box.x = max((minX - 8 + 15) >> 4, p.cx0);
+        box.y = min((maxX - 8) >> 4, p.cx1);
+        box.z = max((minY - 8 + 15) >> 4, p.cy0);
+        box.w = min((maxY - 8) >> 4, p.cy1);
+        if (box.x > box.y || box.z > box.w) {
+            box = make_int4(1, 0, 1, 0);
             ok = false;
         }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 c = ok ? fetch_color(p, vidx[k]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        r.col[k][0] = c.x * r.iw[k];
+        r.col[k][1] = c.y * r.iw[k];
+        r.col[k][2] = c.z * r.iw[k];
+        r.col[k][3] = c.w * r.iw[k];
     }
     return ok;
 }
 
+// compact -> expanded record (R5: sign-normalised integer edge equations, top-left bias, 1/2A); `c` must be the record of a
+// triangle that produces fragments (2A != 0) and `box` its scissored pixel box
+__device__ __forceinline__ void expand_record(const DrawParams& p, const TriRecC& c, const int4 box, TriRec& r) {
+    r.minx = box.x;
+    r.maxx = box.y;
+    r.miny = box.z;
+    r.maxy = box.w;
+    const long long two_a = (long long)(c.X[1] - c.X[0]) * (c.Y[2] - c.Y[0]) - (long long)(c.X[2] - c.X[0]) * (c.Y[1] - c.Y[0]);
+    const long long s = two_a < 0 ? -1 : 1;
+    r.bias_bits = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int ia = (i + 1) % 3, ib = (i + 2) % 3;
+        const long long dx = c.X[ib] - c.X[ia], dy = c.Y[ib] - c.Y[ia];
+        const long long a = -dy * s, b = dx * s;
+        r.a[i] = (int32_t)a;
+        r.b[i] = (int32_t)b;
+        r.c[i] = s * (dy * c.X[ia] - dx * c.Y[ia]);
+        if (a > 0 || (a == 0 && b > 0)) r.bias_bits |= 1u << i;
+    }
+    r.inv2a = 1.0f / (float)(two_a * s);
+    if (depth_clip_cannot_reject(p, c.z[0], c.z[1], c.z[2])) r.bias_bits |= 8u;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.z[k] = c.z[k];
+        r.iw[k] = c.iw[k];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) r.col[k][ch] = c.col[k][ch];
+    }
+}
+// the scissored pixel box of a compact record (what make_compact returned with it)
+__device__ __forceinline__ int4 record_box(const DrawParams& p, const TriRecC& c) {
+    const int32_t minX = min(c.X[0], min(c.X[1], c.X[2])), maxX = max(c.X[0], max(c.X[1], c.X[2]));
+    const int32_t minY = min(c.Y[0], min(c.Y[1], c.Y[2])), maxY = max(c.Y[0], max(c.Y[1], c.Y[2]));
+    return make_int4(max((minX - 8 + 15) >> 4, p.cx0), min((maxX - 8) >> 4, p.cx1), max((minY - 8 + 15) >> 4, p.cy0),
+                     min((maxY - 8) >> 4, p.cy1));
+}
+
+// Triangle t of an instance -> its expanded record; false: it produces no fragments (its box is left empty).
+__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r) {
+    TriRecC c;
+    int4 box;
+    const bool ok = make_compact(p, t, c, box);
+    if (ok) {
+        expand_record(p, c, box, r);
+    } else {
+        memset(&r, 0, sizeof r);
+        r.minx = 1;
+        r.miny = 1;
+    }
+    return ok;
+}
+
+// BINNED: compact records (6 x 16 bytes) for the triangles that produce fragments + the first binning pass;
+// otherwise (direct draws of at most kDirectMax triangles) expanded records for all of them.
+template <bool BINNED>
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
+    constexpr int kQuads = BINNED ? (int)(sizeof(TriRecC) / 16) : (int)(sizeof(TriRec) / 16);
     const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
-    if (t_raw == 0 && !p.binned) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
+    if (!BINNED && t_raw == 0) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
     const bool in_range = t_raw < p.tris_per_instance;
     const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
-    TriRec r;
-    const bool ok = make_record(p, t, r);
-    // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
-    const uint32_t n_inst = p.total_tris / p.tris_per_instance;
-    // The CTA's 256 records are contiguous in memory (36 KiB): they are transposed through shared memory and written
-    // with coalesced 16-byte stores (a thread writing its own 144 bytes makes 9 store instructions of 32 scattered
+    // The CTA's 256 records are contiguous in memory: they are transposed through shared memory and written with
+    // coalesced 16-byte stores (a thread writing its own record makes kQuads store instructions of 32 scattered
     // sectors each: the LSU queue was the top stall of this kernel).
-    __shared__ uint4 stage[256 * 9];
+    __shared__ uint4 stage[256 * kQuads];
     __shared__ uint8_t keep[256];
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(&r);
+    TriRecC c;
+    int4 box;
+    const bool ok = make_compact(p, t, c, box);
+    if (BINNED) {
+        const uint4* src = reinterpret_cast<const uint4*>(&c);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) stage[threadIdx.x * 9 + q] = src[q];
+        for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
         // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
         // degenerate, outside the clip rectangle or this GPU's band) needs no record
-        keep[threadIdx.x] = in_range && (ok || !p.binned);
+        keep[threadIdx.x] = in_range && ok;
+    } else {
+        TriRec r;
+        if (ok) {
+            expand_record(p, c, box, r);
+        } else {
+            memset(&r, 0, sizeof r);
+            r.minx = 1;
+            r.miny = 1;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
+        keep[threadIdx.x] = in_range;
     }
     __syncthreads();
+    // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
+    const uint32_t n_inst = p.total_tris / p.tris_per_instance;
     const uint32_t block_first = blockIdx.x * 256u;
     for (uint32_t inst = 0; inst < n_inst; ++inst) {
-        uint4* dst = reinterpret_cast<uint4*>(&p.tris[(size_t)inst * p.tris_per_instance + block_first]);
-        for (uint32_t i = threadIdx.x; i < 256u * 9u; i += 256u)
-            if (keep[i / 9u]) dst[i] = stage[i];
+        const size_t first_rec = (size_t)inst * p.tris_per_instance + block_first;
+        uint4* dst = BINNED ? reinterpret_cast<uint4*>(reinterpret_cast<TriRecC*>(p.tris) + first_rec) : reinterpret_cast<uint4*>(p.tris + first_rec);
+        for (uint32_t i = threadIdx.x; i < 256u * kQuads; i += 256u)
+            if (keep[i / kQuads]) dst[i] = stage[i];
     }
     if (in_range) {
         for (uint32_t inst = 0; inst < n_inst; ++inst)
             p.boxes[(size_t)inst * p.tris_per_instance + t] =
-                make_uint2((uint32_t)r.minx | ((uint32_t)r.maxx << 16), (uint32_t)r.miny | ((uint32_t)r.maxy << 16));
+                make_uint2((uint32_t)box.x | ((uint32_t)box.y << 16), (uint32_t)box.z | ((uint32_t)box.w << 16));
         if (p.stats) {
             atomicAdd(&p.stats[0], (unsigned long long)n_inst);
             if (!ok) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
         }
     }
-    if (p.binned) {  // first binning pass fused here: count the tiles each triangle overlaps
+    if (BINNED) {  // first binning pass fused here: count the tiles each triangle overlaps
         int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-        bool valid = in_range && tile_range(p, make_int4(r.minx, r.maxx, r.miny, r.maxy), tx0, tx1, ty0, ty1);
+        bool valid = in_range && tile_range(p, box, tx0, tx1, ty0, ty1);
         bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
@@ -463,14 +548,9 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 __device__ __forceinline__ uint32_t bits_to_bytes(uint32_t m) { return (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21); }
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); }
 
-struct FragQueue {  // covered fragments of one row waiting for a full 32-lane shading batch, in primitive order
-    uint32_t key[64];  // slot of the triangle in the row's chunk << 8 | x within the tile
-    float z[64], l0[64], l1[64], l2[64];
-};
-
 struct TileState {  // live from the tile prologue to the epilogue
-    TriRec recs[kTileH][32];  // per row: the records of the chunk being rasterised (private to the row's warp)
-    FragQueue queue[kTileH];
+    TriRecC recs[kTileH][32];   // per row: the records of the chunk being rasterised (private to the row's warp)
+    RowEdge edges[kTileH][32];  // per row: what lane j derived for triangle j of the chunk
     uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
     uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
     float depth[kTileH][kTileW];
@@ -664,63 +744,64 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
     return out;
 }
 
-// Depth test, fragment program and blend for the first `n` (<= 32) queued fragments of a warp's row, one fragment per lane.
-// Fragments of the batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
-// Not inlined: it is called from four places of raster_kernel and the copies pushed the kernel out of the instruction cache.
+// perspective-correct vertex colour (R6): one reciprocal per fragment, one multiply per channel
+__device__ __forceinline__ void interpolate_color(const float iw[3], const float col[3][4], float l0, float l1, float l2, float src[4]) {
+    const float den = fmaf(l2, iw[2], fmaf(l1, iw[1], l0 * iw[0]));
+    const float rden = __frcp_rn(den);  // IEEE 1.0f / den
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) src[ch] = __fmul_rn(fmaf(l2, col[2][ch], fmaf(l1, col[1][ch], l0 * col[0][ch])), rden);
+}
+
+// Depth test, fragment program and blend for one batch of covered fragments of a warp's row, one fragment per lane
+// (`have`): pixel kx of the row, triangle `slot` of the row's chunk, depth z and barycentrics l0..l2.  Fragments of the
+// batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.  Returns 1 on the
+// lanes whose fragment passed the depth test.
 template <uint32_t FS, int NEED_DST>
-__device__ __noinline__ uint32_t shade_fragments(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n,
-                                                 int tile_px0, int py, bool depth_test, bool depth_write, bool has_color) {
+__device__ __forceinline__ uint32_t shade_batch(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, bool have,
+                                                uint32_t kx_in, uint32_t slot, float z, float l0, float l1, float l2, int tile_px0,
+                                                int py, bool depth_test, bool depth_write, bool has_color) {
     uint32_t n_passed = 0;
-    const FragQueue& fq = sh.tile.queue[warp];
-    const bool have = lane < n;
-    uint32_t kx = 0x80000000u | lane;  // unique key for idle lanes
-    uint32_t slot = 0;
-    float z = 0.0f, l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
-    if (have) {
-        const uint32_t key = fq.key[lane];
-        kx = key & 255u;
-        slot = key >> 8;
-        z = fq.z[lane];
-        l0 = fq.l0[lane];
-        l1 = fq.l1[lane];
-        l2 = fq.l2[lane];
-    }
+    const uint32_t kx = have ? kx_in : (0x80000000u | lane);  // unique key for idle lanes
     const uint32_t peers = __match_any_sync(0xffffffffu, kx);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     const uint32_t max_rank = __reduce_max_sync(0xffffffffu, have ? rank : 0u);
-    const TriRec& t = sh.tile.recs[warp][slot];
+    const TriRecC& t = sh.tile.recs[warp][slot];
     float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (have && has_color && (max_rank > 0 || !depth_test)) {
-        // several fragments per pixel in this batch (or no depth test): shade up front, all lanes together
-        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-            fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
-        } else {
-            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) src[ch] = __fdiv_rn(fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch])), den);
+    if (max_rank == 0) {  // warp-uniform, the usual case: every fragment of the batch has its pixel to itself
+        bool pass = have;
+        if (depth_test && have) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][kx]);  // R7: early-Z
+        if (pass) {
+            n_passed = 1;
+            if (depth_write) {
+                sh.tile.depth[warp][kx] = z;
+                sh.tile.depth_dirty[warp][kx] = 1;
+            }
+            if (has_color) {
+                if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+                else interpolate_color(t.iw, t.col, l0, l1, l2, src);
+                const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
+                sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                sh.tile.color_dirty[warp][kx] = 1;
+            }
         }
+        __syncwarp();
+        return n_passed;
+    }
+    if (have && has_color) {  // several fragments per pixel in this batch: shade up front, all lanes together
+        if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+        else interpolate_color(t.iw, t.col, l0, l1, l2, src);
     }
     for (uint32_t rk = 0; rk <= max_rank; ++rk) {
         if (have && rank == rk) {
             bool pass = true;
             if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][kx]);  // R7: early-Z
             if (pass) {
-                ++n_passed;
+                n_passed = 1;
                 if (depth_write) {
                     sh.tile.depth[warp][kx] = z;
                     sh.tile.depth_dirty[warp][kx] = 1;
                 }
                 if (has_color) {
-                    if (max_rank == 0 && depth_test) {  // one fragment per pixel: shade only what passed the depth test
-                        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
-                            fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
-                        } else {
-                            float den = fmaf(l2, t.iw[2], fmaf(l1, t.iw[1], l0 * t.iw[0]));
-#pragma unroll
-                            for (int ch = 0; ch < 4; ++ch)
-                                src[ch] = __fdiv_rn(fmaf(l2, t.col[2][ch], fmaf(l1, t.col[1][ch], l0 * t.col[0][ch])), den);
-                        }
-                    }
                     const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
                     sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
                     sh.tile.color_dirty[warp][kx] = 1;
@@ -889,12 +970,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             else fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
         } else {
 #pragma unroll
-            for (int k = 0; k < PX; ++k) {
-                float den = fmaf(l2[k], t.iw[2], fmaf(l1[k], t.iw[1], l0[k] * t.iw[0]));
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    src[k][ch] = __fdiv_rn(fmaf(l2[k], t.col[2][ch], fmaf(l1[k], t.col[1][ch], l0[k] * t.col[0][ch])), den);
-            }
+            for (int k = 0; k < PX; ++k) interpolate_color(t.iw, t.col, l0[k], l1[k], l2[k], src[k]);
         }
 #pragma unroll
         for (int k = 0; k < PX; ++k) {  // branch-free: pixels not live keep their value
@@ -904,13 +980,19 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     }
 }
 
-// A triangle whose span covers at least half of the warp's row inside the streaming kernel: lane l handles the 4 pixels
-// 4l..4l+3 of the row directly (16-byte shared-memory accesses, no fragment queue).
+// A triangle of the chunk whose span in the warp's row is at least kWideSpan pixels, or whose extent is too large for the
+// 32-bit row arithmetic: lane l handles the 4 pixels 4l..4l+3 of the row directly from the expanded record (64-bit edge
+// functions, 16-byte shared-memory accesses).  Every lane expands the same record (warp-uniform); not inlined, so that the
+// registers of the expansion stay out of the streaming loop.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
-                                           int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
-                                           uint32_t& n_covered, uint32_t& n_passed) {
-    const TriRec& t = sh.tile.recs[warp][slot];
+__device__ __noinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
+                                        int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
+                                        uint32_t& n_covered, uint32_t& n_passed) {
+    TriRec t;
+    {
+        const TriRecC& c = sh.tile.recs[warp][slot];
+        expand_record(p, c, record_box(p, c), t);
+    }
     const int px0 = tile_px0 + (int)lane * kPx;
     const int xa = max(t.minx, tile_px0), xb = min(t.maxx, tile_px0 + kTileW - 1);
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1164,145 +1246,148 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
     }
 }
 
-// One CTA per 128x8-pixel screen tile; warp w owns row w of the tile.  A warp streams the CANDIDATE pixels of its row —
-// for every staged triangle, in primitive order, the pixels of the triangle's bounding box that lie in the row — 32 at a
-// time, one candidate per lane, whatever triangle it belongs to.  So small triangles fill the lanes as well as large ones.
-// Fragments of one batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.
-// One chunk of a row's work: lane j holds (have, my_slot) = the j-th triangle of the chunk (its record is in the
-// row's private sh.tile.recs[warp][my_slot]); every triangle's bounding box contains row py; slots are in primitive order.  Candidate pixels of all 32 spans are streamed 32 per step whatever triangle they
-// belong to; covered fragments go to the warp's queue and are shaded in full batches of 32.
+// One chunk of a row's work: the first n (<= 32) slots of sh.tile.recs[warp] hold the compact records of triangles whose
+// pixel box contains row py, in primitive order.
+//  1. Lane j derives triangle j for this row (RowEdge): pixel span, the three biased edge functions at its first pixel and
+//     their steps, 1/2A — exact 32-bit integer arithmetic for triangles of less than 1024 pixels extent.  Spans of up to
+//     kExactSpan pixels are cut down to the pixels that are really covered by stepping the edge functions along the span
+//     (the covered pixels of a row are an interval: three half-planes), so for small triangles every candidate is a fragment.
+//  2. The candidate pixels of all spans are streamed 32 per step, one per lane, whatever triangle they belong to (owner
+//     found by binary search over the prefix sums of the widths): coverage is a sign test of F_i + k * s_i, then
+//     barycentrics, depth (R6) and shade_batch.  Small triangles fill the lanes as well as large ones.
+//  3. Spans of kWideSpan pixels or more, and triangles too large for 32-bit arithmetic, go through shade_wide; they split
+//     the chunk into segments so that primitive order is kept.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, bool have,
-                                             uint32_t my_slot, int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write,
-                                             bool has_color, uint32_t& q_n, uint32_t& n_covered, uint32_t& n_passed) {
-    // lane j looks at the j-th of them: which pixels of my row can it cover?
-    int xa = 0;
+__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int tile_px0,
+                                             int py, int32_t sy, bool depth_test, bool depth_write, bool has_color, uint32_t& n_covered,
+                                             uint32_t& n_passed) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    const bool have = lane < n;
     uint32_t width = 0;
-    if (have) {
-        const int2 xx = *reinterpret_cast<const int2*>(&sh.tile.recs[warp][my_slot]);  // minx maxx
-        xa = max(xx.x, tile_px0);
-        const int xb = min(xx.y, tile_px0 + kTileW - 1);
-        width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
-    }
-    if (p.exact_spans) {
-        // Narrow spans are cut down to the pixels that are really covered: the covered pixels of a row are
-        // an interval (three half-planes), found by stepping the biased integer edge functions (R5) along
-        // the span, one triangle per lane.  F_i = e_i + bias_i - 1 >= 0  <=>  e_i + bias_i > 0.
-        const bool narrow = width != 0 && width <= (uint32_t)kExactSpan;
-        const uint32_t steps = __reduce_max_sync(0xffffffffu, narrow ? width : 0u);
-        if (steps) {
-            const TriRec& t = sh.tile.recs[warp][my_slot];
-            const int32_t sx = 16 * xa + 8;
-            const uint32_t bias = t.bias_bits;
-            long long f0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]) + (long long)(bias & 1u) - 1;
-            long long f1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]) + (long long)((bias >> 1) & 1u) - 1;
-            long long f2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]) + (long long)((bias >> 2) & 1u) - 1;
-            const long long d0 = 16ll * t.a[0], d1 = 16ll * t.a[1], d2 = 16ll * t.a[2];
-            uint32_t m = 0;
-            for (uint32_t k = 0; k < steps; ++k) {
-                if ((f0 | f1 | f2) >= 0) m |= 1u << k;
-                f0 += d0;
-                f1 += d1;
-                f2 += d2;
-            }
-            if (narrow) {
-                m &= (1u << width) - 1u;
-                xa += m ? __ffs(m) - 1 : 0;
-                width = __popc(m);
+    bool wide = false;
+    {
+        int xa = 0;
+        int32_t f0 = 0, f1 = 0, f2 = 0, s0 = 0, s1 = 0, s2 = 0;
+        uint32_t flags = 0;
+        float inv2a = 0.0f;
+        if (have) {
+            const TriRecC& r = sh.tile.recs[warp][lane];
+            const int4 q0 = *reinterpret_cast<const int4*>(&r.X[0]);  // X0 X1 X2 Y0
+            const int2 q1 = *reinterpret_cast<const int2*>(&r.Y[1]);  // Y1 Y2
+            const int32_t X0 = q0.x, X1 = q0.y, X2 = q0.z, Y0 = q0.w, Y1 = q1.x, Y2 = q1.y;
+            const int32_t minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
+            const int32_t minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+            // the triangle's scissored pixel box in x (its rows were tested by the filter), cut to the tile
+            xa = max(max((minX - 8 + 15) >> 4, p.cx0), tile_px0);
+            const int xb = min(min((maxX - 8) >> 4, p.cx1), tile_px0 + kTileW - 1);
+            width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+            const bool fits32 = maxX - minX < 16384 && maxY - minY < 16384;
+            wide = width != 0 && (!fits32 || width >= (uint32_t)kWideSpan);
+            if (width != 0 && !wide) {
+                const int32_t two_a = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);  // R4; |.| < 2^29
+                const int32_t sg = two_a < 0 ? -1 : 1;
+                const int32_t sx = 16 * xa + 8;
+                // edge i is opposite vertex i: from vertex (i+1)%3 to vertex (i+2)%3 (R5);  E_i(S) = a_i (Sx - X_ia) + b_i (Sy - Y_ia)
+                const int32_t a0 = -(Y2 - Y1) * sg, b0 = (X2 - X1) * sg;
+                const int32_t a1 = -(Y0 - Y2) * sg, b1 = (X0 - X2) * sg;
+                const int32_t a2 = -(Y1 - Y0) * sg, b2 = (X1 - X0) * sg;
+                const int32_t t0 = (a0 > 0 || (a0 == 0 && b0 > 0)) ? 1 : 0;
+                const int32_t t1 = (a1 > 0 || (a1 == 0 && b1 > 0)) ? 1 : 0;
+                const int32_t t2 = (a2 > 0 || (a2 == 0 && b2 > 0)) ? 1 : 0;
+                f0 = a0 * (sx - X1) + b0 * (sy - Y1) + t0 - 1;
+                f1 = a1 * (sx - X2) + b1 * (sy - Y2) + t1 - 1;
+                f2 = a2 * (sx - X0) + b2 * (sy - Y0) + t2 - 1;
+                s0 = 16 * a0;
+                s1 = 16 * a1;
+                s2 = 16 * a2;
+                flags = (uint32_t)(1 - t0) | (uint32_t)(1 - t1) << 1 | (uint32_t)(1 - t2) << 2;
+                inv2a = 1.0f / (float)(two_a * sg);
+                if (depth_clip_cannot_reject(p, r.z[0], r.z[1], r.z[2])) flags |= 8u;
             }
         }
+        if (p.exact_spans) {
+            const bool narrow = width != 0 && !wide && width <= (uint32_t)kExactSpan;
+            const uint32_t steps = __reduce_max_sync(kFull, narrow ? width : 0u);
+            if (steps) {
+                int32_t g0 = f0, g1 = f1, g2 = f2;
+                uint32_t m = 0;
+                for (uint32_t k = 0; k < steps; ++k) {
+                    if ((g0 | g1 | g2) >= 0) m |= 1u << k;
+                    g0 += s0;
+                    g1 += s1;
+                    g2 += s2;
+                }
+                if (narrow) {
+                    m &= (1u << width) - 1u;
+                    const int first = m ? __ffs(m) - 1 : 0;
+                    xa += first;
+                    f0 += first * s0;
+                    f1 += first * s1;
+                    f2 += first * s2;
+                    width = __popc(m);
+                }
+            }
+        }
+        if (have) {
+            RowEdge& e = sh.tile.edges[warp][lane];
+            *reinterpret_cast<int4*>(&e.f[0]) = make_int4(f0, f1, f2, (int)((uint32_t)(xa - tile_px0) | flags << 8));
+            *reinterpret_cast<int4*>(&e.s[0]) = make_int4(s0, s1, s2, __float_as_int(inv2a));
+        }
     }
-    // spans covering at least half the row go through the quad path (4 pixels per lane, no queue);
-    // they split the chunk into segments of ordinary candidates so that primitive order is kept
-    uint32_t wide_mask = __ballot_sync(0xffffffffu, width >= (uint32_t)kWideSpan);
-    if (width >= (uint32_t)kWideSpan) width = 0;
+    __syncwarp();
+    uint32_t wide_mask = __ballot_sync(kFull, wide);
+    if (wide) width = 0;
     uint32_t incl = width;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        uint32_t y = __shfl_up_sync(kFull, incl, d);
         if ((int)lane >= d) incl += y;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
     const uint32_t excl = incl - width;
     uint32_t seg_begin = 0;
     for (;;) {
         const int wide_lane = wide_mask ? __ffs(wide_mask) - 1 : -1;
-        const uint32_t seg_end = wide_lane >= 0 ? __shfl_sync(0xffffffffu, excl, wide_lane) : total;
-    for (uint32_t c0 = seg_begin; c0 < seg_end; c0 += 32) {
-        const uint32_t c = c0 + lane;
-        const bool active = c < seg_end;
-        // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
-        uint32_t pos = 0;
+        const uint32_t seg_end = wide_lane >= 0 ? __shfl_sync(kFull, excl, wide_lane) : total;
+        for (uint32_t c0 = seg_begin; c0 < seg_end; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool active = c < seg_end;
+            // owner = the last lane whose exclusive prefix is <= c (binary search over the 32 prefixes)
+            uint32_t pos = 0;
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            uint32_t e = __shfl_sync(0xffffffffu, excl, (pos + step) & 31u);
-            if (e <= c) pos += step;
-        }
-        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, pos);
-        const int o_xa = __shfl_sync(0xffffffffu, xa, pos);
-        const int px = o_xa + (int)(c - o_excl);
-        const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, pos);
-        const TriRec& t = sh.tile.recs[warp][slot];
-        bool cov = false;
-        float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
-        if (active) {
-            const int32_t sx = 16 * px + 8;
-            long long e0 = (long long)t.a[0] * sx + ((long long)t.b[0] * sy + t.c[0]);  // R5, exact
-            long long e1 = (long long)t.a[1] * sx + ((long long)t.b[1] * sy + t.c[1]);
-            long long e2 = (long long)t.a[2] * sx + ((long long)t.b[2] * sy + t.c[2]);
-            const uint32_t bias = t.bias_bits;
-            cov = e0 + (long long)(bias & 1u) > 0 && e1 + (long long)((bias >> 1) & 1u) > 0 &&
-                  e2 + (long long)((bias >> 2) & 1u) > 0;
-            if (cov) {
-                const float inv2a = t.inv2a;
-                l0 = (float)e0 * inv2a;  // R6
-                l1 = (float)e1 * inv2a;
-                l2 = (float)e2 * inv2a;
-                z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
-                cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
+            for (int step = 16; step > 0; step >>= 1) {
+                uint32_t e = __shfl_sync(kFull, excl, (pos + step) & 31u);
+                if (e <= c) pos += step;
             }
+            const int32_t k = (int32_t)(c - __shfl_sync(kFull, excl, pos));
+            const RowEdge& e = sh.tile.edges[warp][pos];
+            const int4 ef = *reinterpret_cast<const int4*>(&e.f[0]);
+            const int4 es = *reinterpret_cast<const int4*>(&e.s[0]);
+            const int32_t F0 = ef.x + k * es.x, F1 = ef.y + k * es.y, F2 = ef.z + k * es.z;  // R5, exact
+            const uint32_t xw = (uint32_t)ef.w;
+            bool cov = active && (F0 | F1 | F2) >= 0;
+            const uint32_t kx = (xw & 255u) + (uint32_t)k;
+            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
+            if (cov) {
+                const float inv2a = __int_as_float(es.w);
+                l0 = (float)(F0 + (int32_t)(xw >> 8 & 1u)) * inv2a;  // R6: E_i = F_i + 1 - bias_i
+                l1 = (float)(F1 + (int32_t)(xw >> 9 & 1u)) * inv2a;
+                l2 = (float)(F2 + (int32_t)(xw >> 10 & 1u)) * inv2a;
+                const TriRecC& t = sh.tile.recs[warp][pos];
+                z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+                if (!(xw >> 11 & 1u)) cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
+            }
+            if (!__any_sync(kFull, cov)) continue;
+            if (cov) ++n_covered;
+            n_passed += shade_batch<FS, NEED_DST>(p, sh, warp, lane, cov, kx, pos, z, l0, l1, l2, tile_px0, py, depth_test, depth_write, has_color);
         }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, cov);
-        if (!ballot) continue;
-        if (cov) {  // append to my warp's fragment queue, keeping primitive order
-            ++n_covered;
-            FragQueue& fq = sh.tile.queue[warp];
-            const uint32_t at = q_n + __popc(ballot & ((1u << lane) - 1u));
-            fq.key[at] = (slot << 8) | (uint32_t)(px - tile_px0);
-            fq.z[at] = z;
-            fq.l0[at] = l0;
-            fq.l1[at] = l1;
-            fq.l2[at] = l2;
-        }
-        q_n += __popc(ballot);
-        __syncwarp();
-        if (q_n >= 32) {
-            n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, 32u, tile_px0, py, depth_test, depth_write, has_color);
-            // move the remainder (< 32 entries) to the front
-            FragQueue& fq = sh.tile.queue[warp];
-            const bool mv = lane < q_n - 32u;
-            uint32_t k = 0;
-            float fz = 0, f0 = 0, f1 = 0, f2 = 0;
-            if (mv) { k = fq.key[32 + lane]; fz = fq.z[32 + lane]; f0 = fq.l0[32 + lane]; f1 = fq.l1[32 + lane]; f2 = fq.l2[32 + lane]; }
-            __syncwarp();
-            if (mv) { fq.key[lane] = k; fq.z[lane] = fz; fq.l0[lane] = f0; fq.l1[lane] = f1; fq.l2[lane] = f2; }
-            q_n -= 32u;
-            __syncwarp();
-        }
-    }
         if (wide_lane < 0) break;
-        // a wide span: everything queued so far comes first, then the span itself, 4 pixels per lane
-        if (q_n) {
-            n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
-            q_n = 0;
-        }
-        shade_wide<FS, NEED_DST>(p, sh, warp, lane, __shfl_sync(0xffffffffu, my_slot, wide_lane), tile_px0, py, sy, depth_test, depth_write,
-                                 has_color, n_covered, n_passed);
+        // a wide span: everything before it has been applied; then the span itself, 4 pixels per lane
+        shade_wide<FS, NEED_DST>(p, sh, warp, lane, (uint32_t)wide_lane, tile_px0, py, sy, depth_test, depth_write, has_color, n_covered, n_passed);
         wide_mask &= wide_mask - 1;
         seg_begin = seg_end;
     }
 }
-
 
 template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
@@ -1380,19 +1465,19 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
 
     const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
     uint32_t n_covered = 0, n_passed = 0;
-    uint32_t q_n = 0;  // fragments waiting in my warp's queue (warp-uniform)
 
     // ---- my row: every row warp streams the tile's whole triangle list on its own; there is no CTA-wide barrier from
     // here on.  Mesh order and screen position go together, so at any list position only a few rows of a tile have work:
     // lock-stepped rounds of staged records left most warps waiting (37 % of all stall samples at the round barrier).
-    // Lanes test 4 x 32 packed pixel boxes per step (8 bytes per triangle, coalesced for mesh-ordered ids; the next
-    // step's ids are in flight meanwhile); the ids that touch my row collect in a pending list and are rasterised 32 at
-    // a time, so chunks are full whatever the density.  A chunk's 32 records are copied to the warp's private slots in
-    // shared memory first (one L2 round trip per chunk, 9 x 16 bytes per lane).
+    // Lanes test 32 packed pixel boxes per step (8 bytes per triangle, coalesced for mesh-ordered ids; the next
+    // steps' ids and boxes are in flight meanwhile); the ids that touch my row collect in a pending list and are
+    // rasterised 32 at a time, so chunks are full whatever the density.  A chunk's 32 compact records are copied to the
+    // warp's private slots in shared memory first (one L2 round trip per chunk, 6 x 16 bytes per lane).
     if (row_in) {
         uint32_t* pend = sh.tile.pend[warp];
         uint32_t pend_n = 0;
         const uint32_t* ids = p.bin_entries + beg;
+        const TriRecC* recs_g = reinterpret_cast<const TriRecC*>(p.tris);
         auto load_id = [&](uint32_t i) { return i < n_source ? (direct ? i : ids[i]) : 0xffffffffu; };
         auto load_box = [&](uint32_t id) { return id != 0xffffffffu ? __ldg(&p.boxes[id]) : make_uint2(1u, 1u); };  // 1 > 0: empty
         const uint32_t n_steps = (n_source + 31u) / 32u;
@@ -1401,6 +1486,7 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
         uint2 box0 = load_box(id0), box1 = load_box(id1);
         uint32_t step = 0;
         const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
+        constexpr uint32_t kQ = sizeof(TriRecC) / 16;  // 16-byte vectors per record
         for (;;) {
             while (pend_n < 32u && step < n_steps) {
                 const int minx = (int)(box0.x & 0xffffu), maxx = (int)(box0.x >> 16);
@@ -1418,24 +1504,19 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             }
             if (pend_n == 0) break;
             const uint32_t n = min(pend_n, 32u);
-            if (q_n) {  // fragments still queued refer to the records that are about to be replaced: shade them first
-                n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
-                q_n = 0;
-            }
             __syncwarp();
-            // the chunk's records: global -> my warp's slots, 9 x 16 bytes per lane, asynchronous copies (LDGSTS, no registers)
+            // the chunk's records: global -> my warp's slots, asynchronous copies (LDGSTS, no registers)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                const uint32_t q = lane + 32u * i, r = q / 9u;
+            for (uint32_t i = 0; i < kQ; ++i) {
+                const uint32_t q = lane + 32u * i, r = q / kQ;
                 if (r < n) {
-                    const uint4* src = reinterpret_cast<const uint4*>(&p.tris[pend[r]]) + (q - 9u * r);
+                    const uint4* src = reinterpret_cast<const uint4*>(&recs_g[pend[r]]) + (q - kQ * r);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, lane < n, lane, tile_px0, py, sy, depth_test, depth_write, has_color, q_n,
-                                       n_covered, n_passed);
+            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, n, tile_px0, py, sy, depth_test, depth_write, has_color, n_covered, n_passed);
             const bool mv = lane + 32u < pend_n;
             const uint32_t v = mv ? pend[32u + lane] : 0u;
             __syncwarp();
@@ -1443,7 +1524,6 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             pend_n -= n;
             __syncwarp();
         }
-        if (q_n) n_passed += shade_fragments<FS, NEED_DST>(p, sh, warp, lane, q_n, tile_px0, py, depth_test, depth_write, has_color);
     }
 
     // ---- tile epilogue: each lane writes back its 4 pixels of the row where they changed ----
@@ -1742,7 +1822,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
     p.fused_setup = !p.binned && total <= 32u;
     if (!p.fused_setup) {
-        launch_draw_kernel(setup_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
+        if (p.binned) launch_draw_kernel(setup_kernel<true>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
+        else launch_draw_kernel(setup_kernel<false>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "setup_kernel"))) return r;
     }
     if (p.binned) {

@@ -53,7 +53,10 @@ _PROTOS = {
 
 
 def build(force: bool = False) -> Path:
-    if force or not _PATH.exists():
+    # make decides whether the sources are newer than the library; on a machine without gcc (never the case in this
+    # image) the prebuilt library is used as it is
+    import shutil
+    if force or not _PATH.exists() or shutil.which("make"):
         subprocess.run(["make", "-C", str(_DIR), "-s"] + (["-B"] if force else []), check=True)
     return _PATH
 

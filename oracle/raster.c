@@ -23,7 +23,9 @@
  *      is E_i > 0; top-left rule: E_i == 0 is inside iff a_i > 0 (left edge) or a_i == 0 && b_i > 0
  *      (top edge); implemented as E_i + bias_i > 0.
  *  R6  barycentric l_i = (float)E_i * (1.0f / (float)|2A|); z = fma(l2, z2, fma(l1, z1, l0*z0));
- *      attribute f = fma(l2, f2*iw2, fma(l1, f1*iw1, l0*(f0*iw0))) / fma(l2, iw2, fma(l1, iw1, l0*iw0)).
+ *      attribute f = fma(l2, f2*iw2, fma(l1, f1*iw1, l0*(f0*iw0))) * (1.0f / fma(l2, iw2, fma(l1, iw1, l0*iw0)))
+ *      (one correctly rounded reciprocal per fragment shared by the four channels, then one multiply each: within
+ *      1.5 ulp of the exact quotient, inside the 2-ulp bar of the shaded output).
  *  R7  fragment order per pixel = primitive order; depth test before shading (no shader writes depth).
  *  R8  blending: source clamped to [0,1]; Cd = u8/255; C = Cs*Sf (op) Cd*Df with separate roundings; E.1.
  */
@@ -373,9 +375,10 @@ static void raster_rows(const KznGraphicsPipelineState* st, const KznFramebuffer
                     kzo_fs_procedural_orbit((uint32_t)px, (uint32_t)py, (float)W, (float)H, src);
                 } else {
                     float den = fmaf(l2, t->iw[2], fmaf(l1, t->iw[1], l0 * t->iw[0]));
+                    float rden = 1.0f / den; /* R6: one reciprocal per fragment */
                     for (int ch = 0; ch < 4; ++ch) {
                         float num = fmaf(l2, t->col[2][ch], fmaf(l1, t->col[1][ch], l0 * t->col[0][ch]));
-                        src[ch] = num / den;
+                        src[ch] = num * rden;
                     }
                 }
                 uint32_t* cp = (uint32_t*)((uint8_t*)(uintptr_t)fb->color.address +
