@@ -37,9 +37,11 @@
 
 namespace {
 
-constexpr int kPx = 4;                   // horizontally adjacent pixels per thread: one 16-byte colour vector
-constexpr int kTileW = 32 * kPx, kTileH = 8;  // pixels per raster tile: one warp per row -> 512 B row stores
-constexpr int kRasterThreads = 32 * kTileH;
+constexpr int kBrick = 16;                     // raster_kernel: a warp owns one 16 x 16 pixel brick of its CTA's tile
+constexpr int kTileW = 4 * kBrick, kTileH = 2 * kBrick;  // pixels per raster tile (= binning granularity): 4 x 2 bricks
+constexpr int kRasterWarps = 8;                // one per brick
+constexpr int kRasterThreads = 32 * kRasterWarps;
+constexpr int kBrickPx = 8;                    // prologue / epilogue / wide path: lane l = row l >> 1, pixels 8 (l & 1) .. + 7 of the brick
 constexpr int kDirectPx = 8;                   // raster_direct_kernel: pixels per lane (two 16-byte vectors)
 constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels wide ...
 #ifndef KZN_DIRECT_ROWS
@@ -50,12 +52,10 @@ constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels w
 #endif
 constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows high
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
-constexpr int kWideSpan = 64;            // spans of at least this many pixels in a row take the 4-pixels-per-lane path
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
 #ifndef KZN_RASTER_CTAS
 #define KZN_RASTER_CTAS 3
 #endif
-constexpr int kExactSpan = 12;           // spans up to this many pixels are cut down to their covered interval first
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
@@ -86,18 +86,20 @@ struct __align__(16) TriRecC {
 };
 static_assert(sizeof(TriRecC) == 96, "TriRecC layout");
 
-// What lane j of a row warp derives for triangle j of its chunk: the three edge functions at the first pixel of the
-// triangle's span in this row, biased so that "covered" is a sign test, and their step per pixel.  32-bit arithmetic is
-// exact here because only triangles whose snapped extent is below 2^14 subpixels (1024 pixels) in x and y take this path:
-// |a|,|b| < 2^14 and every sample of the pixel box is within the extent, so |E_i| < 2^29 (larger triangles go through
-// expand_record and the 64-bit quad path).
-struct __align__(16) RowEdge {
-    int32_t f[3];   // F_i = E_i + bias_i - 1 at the first pixel: the pixel is covered iff all three are >= 0 (R5)
-    uint32_t xw;    // first pixel's x within the tile | (1 - bias_i) << (8 + i) | depth-clip-cannot-reject << 11
-    int32_t s[3];   // 16 * a_i
+// What lane j of a brick's warp derives for triangle j of its chunk: the three edge functions at the first pixel of the
+// triangle's pixel box inside the brick, biased so that "covered" is a sign test, and their steps per pixel in x and y.
+// 32-bit arithmetic is exact here because only triangles whose snapped extent is below 2^14 subpixels (1024 pixels) in
+// x and y take this path: |a|,|b| < 2^14 and every sample of the pixel box is within the extent, so |E_i| < 2^29
+// (larger triangles go through expand_record and the 64-bit path).
+struct __align__(16) BrickEdge {
+    int32_t f[3];   // F_i = E_i + bias_i - 1 at the box's first pixel: a pixel is covered iff all three are >= 0 (R5)
+    uint32_t xw;    // x0 | y0 << 4 (first pixel within the brick) | box width << 8 | (1 - bias_i) << (13 + i) | depth-clip-cannot-reject << 16
+    int32_t s[3];   // 16 * a_i: step per pixel in x
     float inv2a;
+    int32_t u[3];   // 16 * b_i: step per pixel in y
+    uint32_t magic; // ceil(2^16 / width): candidate k of the box is (k % width, k / width), k / width == k * magic >> 16 for k < 256
 };
-static_assert(sizeof(RowEdge) == 32, "RowEdge layout");
+static_assert(sizeof(BrickEdge) == 48, "BrickEdge layout");
 
 struct DrawParams {
     // geometry
@@ -545,22 +547,22 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 // ---- raster ------------------------------------------------------------------------------------------------------------
 
 // 4 flag bits <-> 4 flag bytes (0 / 1) of a lane's pixel quad
-__device__ __forceinline__ uint32_t bits_to_bytes(uint32_t m) { return (m & 1u) | ((m & 2u) << 7) | ((m & 4u) << 14) | ((m & 8u) << 21); }
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); }
 
-struct TileState {  // live from the tile prologue to the epilogue
-    TriRecC recs[kTileH][32];   // per row: the records of the chunk being rasterised (private to the row's warp)
-    RowEdge edges[kTileH][32];  // per row: what lane j derived for triangle j of the chunk
-    uint32_t pend[kTileH][64];        // per row: ids of the triangles whose bounding box contains the row, waiting for a full chunk
-    uint32_t color[kTileH][kTileW];   // the tile's colour and depth live here for the whole triangle list
-    float depth[kTileH][kTileW];
-    uint8_t color_dirty[kTileH][kTileW];  // one byte per pixel (plain stores: a row belongs to one warp), 4 per lane
-    uint8_t depth_dirty[kTileH][kTileW];
+struct TileState {  // live from the tile prologue to the epilogue; [warp] = the warp's brick
+    TriRecC recs[kRasterWarps][32];     // the records of the chunk being rasterised (private to the warp)
+    BrickEdge edges[kRasterWarps][32];  // what lane j derived for triangle j of the chunk
+    uint32_t pend[kRasterWarps][64];    // ids of the triangles whose pixel box meets the brick, waiting for a full chunk
+    uint32_t queue[kRasterWarps][64];   // covered fragments waiting for a full shading batch: chunk slot << 8 | y << 4 | x
+    uint32_t color[kRasterWarps][kBrick * kBrick];  // the brick's colour and depth live here for the whole triangle list
+    float depth[kRasterWarps][kBrick * kBrick];
+    uint8_t color_dirty[kRasterWarps][kBrick * kBrick];  // one byte per pixel (plain stores: a brick belongs to one warp)
+    uint8_t depth_dirty[kRasterWarps][kBrick * kBrick];
 };
 struct SortScratch {  // live only while the tile's id list is sorted (before the prologue); the result goes back to global memory
     uint32_t list[kSortCap];
     uint32_t second[kSortCap];
-    uint32_t table[256 * kTileH];  // [digit][warp]
+    uint32_t table[256 * kRasterWarps];  // [digit][warp]
 };
 
 struct RasterShared {
@@ -568,8 +570,9 @@ struct RasterShared {
         TileState tile;
         SortScratch sort;
     };
+    uint8_t brick_mask[kSortCap];  // per entry of the sorted list: the bricks of the tile its pixel box meets
     float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
-    uint32_t warp_counts[kTileH];
+    uint32_t warp_counts[kRasterWarps];
 };
 
 // Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.sort.list, by the whole CTA.  The binning
@@ -583,7 +586,7 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t* a = sh.sort.list;
     uint32_t* b = sh.sort.second;
-    uint32_t* table = sh.sort.table;  // [256 digits][kTileH warps]
+    uint32_t* table = sh.sort.table;  // [256 digits][kRasterWarps warps]
     // range of the ids
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (uint32_t i = tid; i < n; i += kRasterThreads) {
@@ -599,7 +602,7 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kTileH; ++w) {
+    for (int w = 0; w < kRasterWarps; ++w) {
         lo = min(lo, sh.warp_counts[w]);
         hi = max(hi, table[w]);
     }
@@ -609,7 +612,7 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
     const uint32_t per = ((n + kRasterThreads - 1) / kRasterThreads) * 32u;  // ids per warp, whole batches
     const uint32_t w_beg = min(warp * per, n), w_end = min(w_beg + per, n);
     for (uint32_t shift = 0; shift < bits; shift += 8) {
-        for (uint32_t i = tid; i < 256u * kTileH; i += kRasterThreads) table[i] = 0;
+        for (uint32_t i = tid; i < 256u * kRasterWarps; i += kRasterThreads) table[i] = 0;
         __syncthreads();
         // digit counts per warp
         for (uint32_t base = w_beg; base < w_end; base += 32) {
@@ -617,17 +620,17 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             const bool valid = i < w_end;
             const uint32_t d = valid ? ((a[i] - lo) >> shift) & 255u : 256u + lane;
             const uint32_t peers = __match_any_sync(kFull, d);
-            if (valid && (int)lane == __ffs(peers) - 1) table[d * kTileH + warp] += __popc(peers);
+            if (valid && (int)lane == __ffs(peers) - 1) table[d * kRasterWarps + warp] += __popc(peers);
             __syncwarp();
         }
         __syncthreads();
         // exclusive scan in (digit, warp) order: thread t owns digit t
         {
-            uint32_t v[kTileH], total = 0;
+            uint32_t v[kRasterWarps], total = 0;
 #pragma unroll
-            for (int k = 0; k < kTileH; ++k) {
+            for (int k = 0; k < kRasterWarps; ++k) {
                 v[k] = total;
-                total += table[tid * kTileH + k];
+                total += table[tid * kRasterWarps + k];
             }
             uint32_t incl = total;
 #pragma unroll
@@ -639,10 +642,10 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             __syncthreads();
             uint32_t before = incl - total;
 #pragma unroll
-            for (int w = 0; w < kTileH; ++w)
+            for (int w = 0; w < kRasterWarps; ++w)
                 if ((uint32_t)w < warp) before += sh.warp_counts[w];
 #pragma unroll
-            for (int k = 0; k < kTileH; ++k) table[tid * kTileH + k] = before + v[k];
+            for (int k = 0; k < kRasterWarps; ++k) table[tid * kRasterWarps + k] = before + v[k];
         }
         __syncthreads();
         // stable scatter
@@ -655,8 +658,8 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             const int leader = __ffs(peers) - 1;
             uint32_t start = 0;
             if (valid && (int)lane == leader) {
-                start = table[d * kTileH + warp];
-                table[d * kTileH + warp] = start + __popc(peers);
+                start = table[d * kRasterWarps + warp];
+                table[d * kRasterWarps + warp] = start + __popc(peers);
             }
             start = __shfl_sync(kFull, start, leader);
             if (valid) b[start + __popc(peers & ((1u << lane) - 1u))] = v;
@@ -752,59 +755,75 @@ __device__ __forceinline__ void interpolate_color(const float iw[3], const float
     for (int ch = 0; ch < 4; ++ch) src[ch] = __fmul_rn(fmaf(l2, col[2][ch], fmaf(l1, col[1][ch], l0 * col[0][ch])), rden);
 }
 
-// Depth test, fragment program and blend for one batch of covered fragments of a warp's row, one fragment per lane
-// (`have`): pixel kx of the row, triangle `slot` of the row's chunk, depth z and barycentrics l0..l2.  Fragments of the
-// batch that hit the same pixel are applied in lane order (= primitive order, R7) using match.any.  Returns 1 on the
-// lanes whose fragment passed the depth test.
+// Depth test, fragment program and blend for the first n (<= 32) fragments queued for a warp's brick, one per lane.  A
+// queue entry names the chunk slot of its triangle and the pixel; the edge functions at the pixel are rebuilt from the
+// triangle's BrickEdge (exact 32-bit integers), then barycentrics and depth (R6).  Fragments of the batch that hit the same
+// pixel are applied in lane order (= primitive order, R7) using match.any.  Returns 1 on the lanes whose fragment passed
+// the depth test.  Not inlined: it has three call sites in the chunk loop.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ uint32_t shade_batch(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, bool have,
-                                                uint32_t kx_in, uint32_t slot, float z, float l0, float l1, float l2, int tile_px0,
-                                                int py, bool depth_test, bool depth_write, bool has_color) {
+__device__ __noinline__ uint32_t shade_queue(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int brick_px0,
+                                             int brick_py0, bool depth_test, bool depth_write, bool has_color) {
     uint32_t n_passed = 0;
-    const uint32_t kx = have ? kx_in : (0x80000000u | lane);  // unique key for idle lanes
+    const bool have = lane < n;
+    const uint32_t key = have ? sh.tile.queue[warp][lane] : 0u;
+    const uint32_t slot = key >> 8, pix = key & 255u;
+    const BrickEdge& e = sh.tile.edges[warp][slot];
+    const int4 ef = *reinterpret_cast<const int4*>(&e.f[0]);
+    const int4 es = *reinterpret_cast<const int4*>(&e.s[0]);
+    const int4 eu = *reinterpret_cast<const int4*>(&e.u[0]);
+    const uint32_t xw = (uint32_t)ef.w;
+    const int32_t dx = (int32_t)(pix & 15u) - (int32_t)(xw & 15u), dy = (int32_t)(pix >> 4) - (int32_t)(xw >> 4 & 15u);
+    const int32_t F0 = ef.x + dx * es.x + dy * eu.x, F1 = ef.y + dx * es.y + dy * eu.y, F2 = ef.z + dx * es.z + dy * eu.z;
+    const float inv2a = __int_as_float(es.w);
+    const float l0 = (float)(F0 + (int32_t)(xw >> 13 & 1u)) * inv2a;  // R6: E_i = F_i + 1 - bias_i
+    const float l1 = (float)(F1 + (int32_t)(xw >> 14 & 1u)) * inv2a;
+    const float l2 = (float)(F2 + (int32_t)(xw >> 15 & 1u)) * inv2a;
+    const TriRecC& t = sh.tile.recs[warp][slot];
+    const float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+    const int px = brick_px0 + (int)(pix & 15u), py = brick_py0 + (int)(pix >> 4);
+    const uint32_t kx = have ? pix : (0x80000000u | lane);  // unique key for idle lanes
     const uint32_t peers = __match_any_sync(0xffffffffu, kx);
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     const uint32_t max_rank = __reduce_max_sync(0xffffffffu, have ? rank : 0u);
-    const TriRecC& t = sh.tile.recs[warp][slot];
     float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (max_rank == 0) {  // warp-uniform, the usual case: every fragment of the batch has its pixel to itself
         bool pass = have;
-        if (depth_test && have) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][kx]);  // R7: early-Z
+        if (depth_test && have) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][pix]);  // R7: early-Z
         if (pass) {
             n_passed = 1;
             if (depth_write) {
-                sh.tile.depth[warp][kx] = z;
-                sh.tile.depth_dirty[warp][kx] = 1;
+                sh.tile.depth[warp][pix] = z;
+                sh.tile.depth_dirty[warp][pix] = 1;
             }
             if (has_color) {
-                if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+                if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
                 else interpolate_color(t.iw, t.col, l0, l1, l2, src);
-                const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
-                sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                sh.tile.color_dirty[warp][kx] = 1;
+                const uint32_t dst = NEED_DST ? sh.tile.color[warp][pix] : 0u;
+                sh.tile.color[warp][pix] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                sh.tile.color_dirty[warp][pix] = 1;
             }
         }
         __syncwarp();
         return n_passed;
     }
     if (have && has_color) {  // several fragments per pixel in this batch: shade up front, all lanes together
-        if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(tile_px0 + (int)kx, py, p.inv_fb_w, p.inv_fb_h, src);
+        if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
         else interpolate_color(t.iw, t.col, l0, l1, l2, src);
     }
     for (uint32_t rk = 0; rk <= max_rank; ++rk) {
         if (have && rank == rk) {
             bool pass = true;
-            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][kx]);  // R7: early-Z
+            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][pix]);  // R7: early-Z
             if (pass) {
                 n_passed = 1;
                 if (depth_write) {
-                    sh.tile.depth[warp][kx] = z;
-                    sh.tile.depth_dirty[warp][kx] = 1;
+                    sh.tile.depth[warp][pix] = z;
+                    sh.tile.depth_dirty[warp][pix] = 1;
                 }
                 if (has_color) {
-                    const uint32_t dst = NEED_DST ? sh.tile.color[warp][kx] : 0u;
-                    sh.tile.color[warp][kx] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                    sh.tile.color_dirty[warp][kx] = 1;
+                    const uint32_t dst = NEED_DST ? sh.tile.color[warp][pix] : 0u;
+                    sh.tile.color[warp][pix] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
+                    sh.tile.color_dirty[warp][pix] = 1;
                 }
             }
         }
@@ -905,9 +924,10 @@ __device__ __forceinline__ uint32_t quad_mask(int px0, int xa, int xb) {
 // One triangle against the PX adjacent pixels px0..px0+PX-1 of row py that a lane owns, destination values in registers:
 // edge functions evaluated once and stepped by +16a per pixel (exact, R5), barycentric depth (R6), z clip (R3), early-Z
 // (R7), fragment program, output merge (R8).  `live` / `zwrite` return which of the PX pixels got a new colour / depth.
-// [xa, xb] is the triangle's pixel span in this row (bbox, already scissored) clipped to the 128-pixel tile row; it is
-// warp-uniform, and so is the trivial-accept branch.
-template <uint32_t FS, int NEED_DST, int PX>
+// [xa, xb] is the triangle's pixel span in this row (bbox, already scissored) clipped to the warp's block; with UNIFORM_ROW
+// all lanes of the warp work on the same row and span, and so the trivial-accept branch is warp-uniform (it is compiled out
+// when every lane has its own row: raster_kernel's bricks).
+template <uint32_t FS, int NEED_DST, int PX, bool UNIFORM_ROW = true>
 __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, const float* lut, int px0, int py, int32_t sy, int xa, int xb,
                                           bool depth_test, bool depth_write, bool has_color, uint32_t col[PX], float depth[PX],
                                           uint32_t& live, uint32_t& zwrite, uint32_t& n_covered, uint32_t& n_passed,
@@ -916,7 +936,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     live = 0;
     zwrite = 0;
     bool trivial = false;
-    if (FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test && (bias & 8u)) {
+    if (UNIFORM_ROW && FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test && (bias & 8u)) {
         // Trivial accept of the whole span: the covered pixels of a row are an interval (each biased edge test is a
         // half-plane), so if both end pixels of the span are covered, every pixel between them is; the depth clip cannot
         // reject (bit 3, set at setup) and this fragment program reads no interpolant — no per-pixel coverage work at all.
@@ -980,37 +1000,50 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     }
 }
 
-// A triangle of the chunk whose span in the warp's row is at least kWideSpan pixels, or whose extent is too large for the
-// 32-bit row arithmetic: lane l handles the 4 pixels 4l..4l+3 of the row directly from the expanded record (64-bit edge
-// functions, 16-byte shared-memory accesses).  Every lane expands the same record (warp-uniform); not inlined, so that the
-// registers of the expansion stay out of the streaming loop.
+// A triangle of the chunk too large for the 32-bit brick arithmetic (1024 pixels or more across): lane l handles the 8
+// pixels 8 (l & 1) .. + 7 of row l >> 1 of the brick directly from the expanded record (64-bit edge functions, 16-byte
+// shared-memory accesses).  Every lane expands the same record (warp-uniform); not inlined, so that the registers of the
+// expansion stay out of the streaming loop.
 template <uint32_t FS, int NEED_DST>
 __device__ __noinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
-                                        int tile_px0, int py, int32_t sy, bool depth_test, bool depth_write, bool has_color,
+                                        int brick_px0, int brick_py0, bool depth_test, bool depth_write, bool has_color,
                                         uint32_t& n_covered, uint32_t& n_passed) {
     TriRec t;
     {
         const TriRecC& c = sh.tile.recs[warp][slot];
         expand_record(p, c, record_box(p, c), t);
     }
-    const int px0 = tile_px0 + (int)lane * kPx;
-    const int xa = max(t.minx, tile_px0), xb = min(t.maxx, tile_px0 + kTileW - 1);
-    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][lane * kPx]);
-    float depth[kPx] = {dq.x, dq.y, dq.z, dq.w};
-    uint4 cq = make_uint4(0u, 0u, 0u, 0u);
-    if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][lane * kPx]);
-    uint32_t col[kPx] = {cq.x, cq.y, cq.z, cq.w};
-    uint32_t live, zwrite;
-    span_quad<FS, NEED_DST, kPx>(p, t, sh.unorm_lut, px0, py, sy, xa, xb, depth_test, depth_write, has_color, col, depth, live, zwrite, n_covered,
-                            n_passed);
-    if (zwrite) {
-        *reinterpret_cast<float4*>(&sh.tile.depth[warp][lane * kPx]) = make_float4(depth[0], depth[1], depth[2], depth[3]);
-        reinterpret_cast<uint32_t*>(sh.tile.depth_dirty[warp])[lane] |= bits_to_bytes(zwrite);
+    const uint32_t at = lane * kBrickPx;  // (lane >> 1) * 16 + (lane & 1) * 8
+    const int px0 = brick_px0 + (int)(lane & 1u) * kBrickPx, py = brick_py0 + (int)(lane >> 1);
+    int xa = max(t.minx, brick_px0), xb = min(t.maxx, brick_px0 + kBrick - 1);
+    if (py < t.miny || py > t.maxy) {  // my row is outside the pixel box: an empty span
+        xa = 1;
+        xb = 0;
     }
-    if (live) {
-        *reinterpret_cast<uint4*>(&sh.tile.color[warp][lane * kPx]) = make_uint4(col[0], col[1], col[2], col[3]);
-        reinterpret_cast<uint32_t*>(sh.tile.color_dirty[warp])[lane] |= bits_to_bytes(live);
+    float depth[kBrickPx];
+    uint32_t col[kBrickPx];
+#pragma unroll
+    for (int h = 0; h < kBrickPx / 4; ++h) {
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][at + 4 * h]);
+        depth[4 * h] = dq.x; depth[4 * h + 1] = dq.y; depth[4 * h + 2] = dq.z; depth[4 * h + 3] = dq.w;
+        uint4 cq = make_uint4(0u, 0u, 0u, 0u);
+        if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][at + 4 * h]);
+        col[4 * h] = cq.x; col[4 * h + 1] = cq.y; col[4 * h + 2] = cq.z; col[4 * h + 3] = cq.w;
+    }
+    uint32_t live, zwrite;
+    span_quad<FS, NEED_DST, kBrickPx, false>(p, t, sh.unorm_lut, px0, py, 16 * py + 8, xa, xb, depth_test, depth_write, has_color, col, depth,
+                                             live, zwrite, n_covered, n_passed);
+#pragma unroll
+    for (int k = 0; k < kBrickPx; ++k) {
+        if (zwrite >> k & 1u) {
+            sh.tile.depth[warp][at + k] = depth[k];
+            sh.tile.depth_dirty[warp][at + k] = 1;
+        }
+        if (live >> k & 1u) {
+            sh.tile.color[warp][at + k] = col[k];
+            sh.tile.color_dirty[warp][at + k] = 1;
+        }
     }
     __syncwarp();
 }
@@ -1246,47 +1279,47 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
     }
 }
 
-// One chunk of a row's work: the first n (<= 32) slots of sh.tile.recs[warp] hold the compact records of triangles whose
-// pixel box contains row py, in primitive order.
-//  1. Lane j derives triangle j for this row (RowEdge): pixel span, the three biased edge functions at its first pixel and
-//     their steps, 1/2A — exact 32-bit integer arithmetic for triangles of less than 1024 pixels extent.  Spans of up to
-//     kExactSpan pixels are cut down to the pixels that are really covered by stepping the edge functions along the span
-//     (the covered pixels of a row are an interval: three half-planes), so for small triangles every candidate is a fragment.
-//  2. The candidate pixels of all spans are streamed 32 per step, one per lane, whatever triangle they belong to (owner
-//     found by binary search over the prefix sums of the widths): coverage is a sign test of F_i + k * s_i, then
-//     barycentrics, depth (R6) and shade_batch.  Small triangles fill the lanes as well as large ones.
-//  3. Spans of kWideSpan pixels or more, and triangles too large for 32-bit arithmetic, go through shade_wide; they split
-//     the chunk into segments so that primitive order is kept.
+__constant__ uint32_t kWidthMagic[17] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,
+                                         7282,  6554,  5958,  5462,  5042,  4682,  4370, 4096};  // ceil(2^16 / w)
+
+// One chunk of a brick's work: the first n (<= 32) slots of sh.tile.recs[warp] hold the compact records of triangles whose
+// pixel box meets the brick, in primitive order.
+//  1. Lane j derives triangle j for this brick (BrickEdge): its pixel box inside the brick, the three biased edge
+//     functions at the box's first pixel and their steps in x and y, 1/2A — exact 32-bit integer arithmetic for triangles
+//     of less than 1024 pixels extent.
+//  2. The candidate pixels of all boxes are streamed 32 per step, one per lane, whatever triangle they belong to (owner
+//     found by binary search over the prefix sums of the box sizes): coverage is a sign test of F_i + dx s_i + dy u_i.
+//     Covered fragments are appended to the warp's queue in candidate order (= primitive order) and shaded in full batches
+//     of 32 (shade_queue), so small triangles fill the lanes as well as large ones in both stages.
+//  3. Triangles too large for 32-bit arithmetic go through shade_wide; they split the chunk into segments so that primitive
+//     order is kept.  The queue is drained before the chunk's records are replaced.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int tile_px0,
-                                             int py, int32_t sy, bool depth_test, bool depth_write, bool has_color, uint32_t& n_covered,
+__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int brick_px0,
+                                             int brick_py0, bool depth_test, bool depth_write, bool has_color, uint32_t& n_covered,
                                              uint32_t& n_passed) {
     constexpr uint32_t kFull = 0xffffffffu;
     const bool have = lane < n;
-    uint32_t width = 0;
+    uint32_t count = 0;
     bool wide = false;
-    {
-        int xa = 0;
-        int32_t f0 = 0, f1 = 0, f2 = 0, s0 = 0, s1 = 0, s2 = 0;
-        uint32_t flags = 0;
-        float inv2a = 0.0f;
-        if (have) {
-            const TriRecC& r = sh.tile.recs[warp][lane];
-            const int4 q0 = *reinterpret_cast<const int4*>(&r.X[0]);  // X0 X1 X2 Y0
-            const int2 q1 = *reinterpret_cast<const int2*>(&r.Y[1]);  // Y1 Y2
-            const int32_t X0 = q0.x, X1 = q0.y, X2 = q0.z, Y0 = q0.w, Y1 = q1.x, Y2 = q1.y;
-            const int32_t minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
-            const int32_t minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
-            // the triangle's scissored pixel box in x (its rows were tested by the filter), cut to the tile
-            xa = max(max((minX - 8 + 15) >> 4, p.cx0), tile_px0);
-            const int xb = min(min((maxX - 8) >> 4, p.cx1), tile_px0 + kTileW - 1);
-            width = xb >= xa ? (uint32_t)(xb - xa + 1) : 0u;
+    if (have) {
+        const TriRecC& r = sh.tile.recs[warp][lane];
+        const int4 q0 = *reinterpret_cast<const int4*>(&r.X[0]);  // X0 X1 X2 Y0
+        const int2 q1 = *reinterpret_cast<const int2*>(&r.Y[1]);  // Y1 Y2
+        const int32_t X0 = q0.x, X1 = q0.y, X2 = q0.z, Y0 = q0.w, Y1 = q1.x, Y2 = q1.y;
+        const int32_t minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
+        const int32_t minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+        // the triangle's scissored pixel box, cut to the brick
+        const int x0 = max(max((minX - 8 + 15) >> 4, p.cx0), brick_px0), x1 = min(min((maxX - 8) >> 4, p.cx1), brick_px0 + kBrick - 1);
+        const int y0 = max(max((minY - 8 + 15) >> 4, p.cy0), brick_py0), y1 = min(min((maxY - 8) >> 4, p.cy1), brick_py0 + kBrick - 1);
+        const int w = x1 - x0 + 1, h = y1 - y0 + 1;
+        if (w > 0 && h > 0) {
             const bool fits32 = maxX - minX < 16384 && maxY - minY < 16384;
-            wide = width != 0 && (!fits32 || width >= (uint32_t)kWideSpan);
-            if (width != 0 && !wide) {
+            wide = !fits32;
+            if (fits32) {
+                count = (uint32_t)(w * h);
                 const int32_t two_a = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);  // R4; |.| < 2^29
                 const int32_t sg = two_a < 0 ? -1 : 1;
-                const int32_t sx = 16 * xa + 8;
+                const int32_t sx = 16 * x0 + 8, sy = 16 * y0 + 8;  // fixed-point sample position (R2)
                 // edge i is opposite vertex i: from vertex (i+1)%3 to vertex (i+2)%3 (R5);  E_i(S) = a_i (Sx - X_ia) + b_i (Sy - Y_ia)
                 const int32_t a0 = -(Y2 - Y1) * sg, b0 = (X2 - X1) * sg;
                 const int32_t a1 = -(Y0 - Y2) * sg, b1 = (X0 - X2) * sg;
@@ -1294,57 +1327,31 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
                 const int32_t t0 = (a0 > 0 || (a0 == 0 && b0 > 0)) ? 1 : 0;
                 const int32_t t1 = (a1 > 0 || (a1 == 0 && b1 > 0)) ? 1 : 0;
                 const int32_t t2 = (a2 > 0 || (a2 == 0 && b2 > 0)) ? 1 : 0;
-                f0 = a0 * (sx - X1) + b0 * (sy - Y1) + t0 - 1;
-                f1 = a1 * (sx - X2) + b1 * (sy - Y2) + t1 - 1;
-                f2 = a2 * (sx - X0) + b2 * (sy - Y0) + t2 - 1;
-                s0 = 16 * a0;
-                s1 = 16 * a1;
-                s2 = 16 * a2;
-                flags = (uint32_t)(1 - t0) | (uint32_t)(1 - t1) << 1 | (uint32_t)(1 - t2) << 2;
-                inv2a = 1.0f / (float)(two_a * sg);
-                if (depth_clip_cannot_reject(p, r.z[0], r.z[1], r.z[2])) flags |= 8u;
+                const int32_t f0 = a0 * (sx - X1) + b0 * (sy - Y1) + t0 - 1;
+                const int32_t f1 = a1 * (sx - X2) + b1 * (sy - Y2) + t1 - 1;
+                const int32_t f2 = a2 * (sx - X0) + b2 * (sy - Y0) + t2 - 1;
+                uint32_t xw = (uint32_t)(x0 - brick_px0) | (uint32_t)(y0 - brick_py0) << 4 | (uint32_t)w << 8 | (uint32_t)(1 - t0) << 13 |
+                              (uint32_t)(1 - t1) << 14 | (uint32_t)(1 - t2) << 15;
+                if (depth_clip_cannot_reject(p, r.z[0], r.z[1], r.z[2])) xw |= 1u << 16;
+                BrickEdge& e = sh.tile.edges[warp][lane];
+                *reinterpret_cast<int4*>(&e.f[0]) = make_int4(f0, f1, f2, (int)xw);
+                *reinterpret_cast<int4*>(&e.s[0]) = make_int4(16 * a0, 16 * a1, 16 * a2, __float_as_int(1.0f / (float)(two_a * sg)));
+                *reinterpret_cast<int4*>(&e.u[0]) = make_int4(16 * b0, 16 * b1, 16 * b2, (int)kWidthMagic[w]);
             }
-        }
-        if (p.exact_spans) {
-            const bool narrow = width != 0 && !wide && width <= (uint32_t)kExactSpan;
-            const uint32_t steps = __reduce_max_sync(kFull, narrow ? width : 0u);
-            if (steps) {
-                int32_t g0 = f0, g1 = f1, g2 = f2;
-                uint32_t m = 0;
-                for (uint32_t k = 0; k < steps; ++k) {
-                    if ((g0 | g1 | g2) >= 0) m |= 1u << k;
-                    g0 += s0;
-                    g1 += s1;
-                    g2 += s2;
-                }
-                if (narrow) {
-                    m &= (1u << width) - 1u;
-                    const int first = m ? __ffs(m) - 1 : 0;
-                    xa += first;
-                    f0 += first * s0;
-                    f1 += first * s1;
-                    f2 += first * s2;
-                    width = __popc(m);
-                }
-            }
-        }
-        if (have) {
-            RowEdge& e = sh.tile.edges[warp][lane];
-            *reinterpret_cast<int4*>(&e.f[0]) = make_int4(f0, f1, f2, (int)((uint32_t)(xa - tile_px0) | flags << 8));
-            *reinterpret_cast<int4*>(&e.s[0]) = make_int4(s0, s1, s2, __float_as_int(inv2a));
         }
     }
     __syncwarp();
     uint32_t wide_mask = __ballot_sync(kFull, wide);
-    if (wide) width = 0;
-    uint32_t incl = width;
+    uint32_t incl = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t y = __shfl_up_sync(kFull, incl, d);
         if ((int)lane >= d) incl += y;
     }
     const uint32_t total = __shfl_sync(kFull, incl, 31);
-    const uint32_t excl = incl - width;
+    const uint32_t excl = incl - count;
+    uint32_t* queue = sh.tile.queue[warp];
+    uint32_t q_n = 0;  // fragments waiting in the queue (warp-uniform)
     uint32_t seg_begin = 0;
     for (;;) {
         const int wide_lane = wide_mask ? __ffs(wide_mask) - 1 : -1;
@@ -1359,36 +1366,70 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
                 uint32_t e = __shfl_sync(kFull, excl, (pos + step) & 31u);
                 if (e <= c) pos += step;
             }
-            const int32_t k = (int32_t)(c - __shfl_sync(kFull, excl, pos));
-            const RowEdge& e = sh.tile.edges[warp][pos];
+            const uint32_t k = c - __shfl_sync(kFull, excl, pos);
+            const BrickEdge& e = sh.tile.edges[warp][pos];
             const int4 ef = *reinterpret_cast<const int4*>(&e.f[0]);
             const int4 es = *reinterpret_cast<const int4*>(&e.s[0]);
-            const int32_t F0 = ef.x + k * es.x, F1 = ef.y + k * es.y, F2 = ef.z + k * es.z;  // R5, exact
+            const int4 eu = *reinterpret_cast<const int4*>(&e.u[0]);
             const uint32_t xw = (uint32_t)ef.w;
+            const uint32_t dy = (k * (uint32_t)eu.w) >> 16, dx = k - dy * (xw >> 8 & 31u);
+            const int32_t F0 = ef.x + (int32_t)dx * es.x + (int32_t)dy * eu.x;  // R5, exact
+            const int32_t F1 = ef.y + (int32_t)dx * es.y + (int32_t)dy * eu.y;
+            const int32_t F2 = ef.z + (int32_t)dx * es.z + (int32_t)dy * eu.z;
             bool cov = active && (F0 | F1 | F2) >= 0;
-            const uint32_t kx = (xw & 255u) + (uint32_t)k;
-            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, z = 0.0f;
-            if (cov) {
+            if (cov && !(xw >> 16 & 1u)) {  // the depth clip may reject (R3): evaluate the depth here as shade_queue will
                 const float inv2a = __int_as_float(es.w);
-                l0 = (float)(F0 + (int32_t)(xw >> 8 & 1u)) * inv2a;  // R6: E_i = F_i + 1 - bias_i
-                l1 = (float)(F1 + (int32_t)(xw >> 9 & 1u)) * inv2a;
-                l2 = (float)(F2 + (int32_t)(xw >> 10 & 1u)) * inv2a;
+                const float l0 = (float)(F0 + (int32_t)(xw >> 13 & 1u)) * inv2a;
+                const float l1 = (float)(F1 + (int32_t)(xw >> 14 & 1u)) * inv2a;
+                const float l2 = (float)(F2 + (int32_t)(xw >> 15 & 1u)) * inv2a;
                 const TriRecC& t = sh.tile.recs[warp][pos];
-                z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
-                if (!(xw >> 11 & 1u)) cov = z >= p.zclip_lo && z <= p.zclip_hi;  // R3 (false for NaN)
+                const float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
+                cov = z >= p.zclip_lo && z <= p.zclip_hi;  // false for NaN
             }
-            if (!__any_sync(kFull, cov)) continue;
-            if (cov) ++n_covered;
-            n_passed += shade_batch<FS, NEED_DST>(p, sh, warp, lane, cov, kx, pos, z, l0, l1, l2, tile_px0, py, depth_test, depth_write, has_color);
+            const uint32_t ballot = __ballot_sync(kFull, cov);
+            if (!ballot) continue;
+            if (cov) {
+                ++n_covered;
+                queue[q_n + __popc(ballot & ((1u << lane) - 1u))] = pos << 8 | ((xw >> 4 & 15u) + dy) << 4 | ((xw & 15u) + dx);
+            }
+            q_n += __popc(ballot);
+            __syncwarp();
+            if (q_n >= 32u) {
+                n_passed += shade_queue<FS, NEED_DST>(p, sh, warp, lane, 32u, brick_px0, brick_py0, depth_test, depth_write, has_color);
+                const uint32_t rest = lane < q_n - 32u ? queue[32u + lane] : 0u;  // move the remainder (< 32 entries) to the front
+                __syncwarp();
+                if (lane < q_n - 32u) queue[lane] = rest;
+                q_n -= 32u;
+                __syncwarp();
+            }
+        }
+        if (q_n) {  // before a wide triangle, and before the chunk's records are replaced
+            n_passed += shade_queue<FS, NEED_DST>(p, sh, warp, lane, q_n, brick_px0, brick_py0, depth_test, depth_write, has_color);
+            q_n = 0;
         }
         if (wide_lane < 0) break;
-        // a wide span: everything before it has been applied; then the span itself, 4 pixels per lane
-        shade_wide<FS, NEED_DST>(p, sh, warp, lane, (uint32_t)wide_lane, tile_px0, py, sy, depth_test, depth_write, has_color, n_covered, n_passed);
+        shade_wide<FS, NEED_DST>(p, sh, warp, lane, (uint32_t)wide_lane, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
         wide_mask &= wide_mask - 1;
         seg_begin = seg_end;
     }
 }
 
+// The bricks of the tile at (tile_px0, tile_py0) that a packed pixel box meets: bit 4 by + bx.
+__device__ __forceinline__ uint32_t brick_mask_of(uint2 box, int tile_px0, int tile_py0) {
+    const int minx = (int)(box.x & 0xffffu), maxx = (int)(box.x >> 16), miny = (int)(box.y & 0xffffu), maxy = (int)(box.y >> 16);
+    if (minx > maxx) return 0u;
+    const int bx0 = max(minx - tile_px0, 0) >> 4, bx1 = min(maxx - tile_px0, kTileW - 1) >> 4;
+    const int by0 = max(miny - tile_py0, 0) >> 4, by1 = min(maxy - tile_py0, kTileH - 1) >> 4;
+    if (bx0 > bx1 || by0 > by1) return 0u;
+    const uint32_t xm = (2u << bx1) - (1u << bx0);
+    return (by0 == 0 ? xm : 0u) | (by1 >= 1 ? xm << 4 : 0u);
+}
+
+// One CTA per 64 x 32-pixel screen tile; warp w owns the 16 x 16 brick (w & 3, w >> 2) of the tile: its colour and depth
+// live in shared memory for the whole triangle list (each framebuffer byte read at most once, written at most once), and
+// all its fragments are applied by this warp alone, in primitive order — nothing is shared between the warps after the
+// in-tile sort.  Bricks rather than rows: a small triangle meets one or two bricks but three or four rows, and everything
+// that is done per (triangle, warp) — record copy, edge derivation, prefix sums — is paid that many times.
 template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
@@ -1397,18 +1438,20 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
     const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
-    const int py = tile_py0 + (int)warp;
-    const bool row_in = py >= p.cy0 && py <= p.cy1;
+    const int brick_px0 = tile_px0 + (int)(warp & 3u) * kBrick, brick_py0 = tile_py0 + (int)(warp >> 2) * kBrick;
+    const bool brick_in = brick_px0 <= p.cx1 && brick_px0 + kBrick - 1 >= p.cx0 && brick_py0 <= p.cy1 && brick_py0 + kBrick - 1 >= p.cy0;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
-    // a lane's 4 pixels of the row (final load/store) are one aligned 16-byte vector when the row pitch allows it
-    const int qx0 = tile_px0 + (int)lane * kPx;
-    const bool vec_ok = (p.fb_w & 3u) == 0 && qx0 + kPx <= (int)p.fb_w;
+    // prologue / epilogue: lane l moves the 8 pixels 8 (l & 1) .. + 7 of row l >> 1 of the brick, two 16-byte vectors when
+    // the row pitch allows it
+    const int qx0 = brick_px0 + (int)(lane & 1u) * kBrickPx, qy = brick_py0 + (int)(lane >> 1);
+    const uint32_t qat = lane * kBrickPx;
+    const bool vec_ok = (p.fb_w & 3u) == 0 && qx0 + kBrickPx <= (int)p.fb_w;
     uint32_t quad_clip = 0;
 #pragma unroll
-    for (int k = 0; k < kPx; ++k)
-        if (row_in && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
+    for (int k = 0; k < kBrickPx; ++k)
+        if (qy >= p.cy0 && qy <= p.cy1 && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
 
     // triangle source
     uint32_t list_len = 0, beg = 0;
@@ -1425,8 +1468,13 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             __syncthreads();
             const uint32_t* sorted = sort_tile_list(sh, list_len);
             // the tile's segment of the bins is private to this CTA: the sorted list goes back in place and is streamed
-            // from there, which frees the sort's shared memory for the tile state
-            for (uint32_t i = tid; i < list_len; i += kRasterThreads) p.bin_entries[beg + i] = sorted[i];
+            // from there, which frees the sort's shared memory for the tile state; each entry's pixel box is looked at
+            // once, here, for all eight bricks (the warps then filter the list by one byte per entry)
+            for (uint32_t i = tid; i < list_len; i += kRasterThreads) {
+                const uint32_t id = sorted[i];
+                p.bin_entries[beg + i] = id;
+                sh.brick_mask[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
+            }
             __syncthreads();
         } else if (p.stats && tid == 0) {
             atomicAdd(&p.stats[7], 1ull);
@@ -1434,73 +1482,72 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
     }
     const uint32_t n_source = direct ? p.total_tris : list_len;
 
-    // ---- tile prologue: destination values the result depends on, dirty masks, the UNORM8 -> float table ----
+    // ---- brick prologue: destination values the result depends on, dirty masks, the UNORM8 -> float table ----
     unsigned long long caddr = 0, daddr = 0;
     if (quad_clip) {
-        if (has_color) caddr = color_addr(p, qx0, py);
-        if (has_depth) daddr = p.depth_base + ((unsigned long long)py * p.fb_w + qx0) * 4ull;
+        if (has_color) caddr = color_addr(p, qx0, qy);
+        if (has_depth) daddr = p.depth_base + ((unsigned long long)qy * p.fb_w + qx0) * 4ull;
     }
+    const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
     if (NEED_DST && quad_clip && has_color) {
-        if (vec_ok && (p.color_base & 15ull) == 0) {
-            *reinterpret_cast<uint4*>(&sh.tile.color[warp][lane * kPx]) = *reinterpret_cast<const uint4*>(caddr);
-        } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (quad_clip >> k & 1u) sh.tile.color[warp][lane * kPx + k] = *reinterpret_cast<const uint32_t*>(caddr + 4 * k);
+        for (int h = 0; h < kBrickPx / 4; ++h) {
+            const uint32_t m4 = quad_clip >> (4 * h) & 15u;
+            if (m4 == 15u && cvec) {
+                *reinterpret_cast<uint4*>(&sh.tile.color[warp][qat + 4 * h]) = *reinterpret_cast<const uint4*>(caddr + 16 * h);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (m4 >> k & 1u) sh.tile.color[warp][qat + 4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
+            }
         }
     }
     if (depth_test && quad_clip) {
-        if (vec_ok && (p.depth_base & 15ull) == 0) {
-            *reinterpret_cast<float4*>(&sh.tile.depth[warp][lane * kPx]) = *reinterpret_cast<const float4*>(daddr);
-        } else {
 #pragma unroll
-            for (int k = 0; k < kPx; ++k)
-                if (quad_clip >> k & 1u) sh.tile.depth[warp][lane * kPx + k] = *reinterpret_cast<const float*>(daddr + 4 * k);
+        for (int h = 0; h < kBrickPx / 4; ++h) {
+            const uint32_t m4 = quad_clip >> (4 * h) & 15u;
+            if (m4 == 15u && dvec) {
+                *reinterpret_cast<float4*>(&sh.tile.depth[warp][qat + 4 * h]) = *reinterpret_cast<const float4*>(daddr + 16 * h);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (m4 >> k & 1u) sh.tile.depth[warp][qat + 4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
+            }
         }
     }
-    reinterpret_cast<uint32_t*>(sh.tile.color_dirty[warp])[lane] = 0;  // my 4 pixels' flags
-    reinterpret_cast<uint32_t*>(sh.tile.depth_dirty[warp])[lane] = 0;
+    *reinterpret_cast<uint2*>(&sh.tile.color_dirty[warp][qat]) = make_uint2(0u, 0u);  // my 8 pixels' flags
+    *reinterpret_cast<uint2*>(&sh.tile.depth_dirty[warp][qat]) = make_uint2(0u, 0u);
     if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
     __syncthreads();
 
-    const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
     uint32_t n_covered = 0, n_passed = 0;
 
-    // ---- my row: every row warp streams the tile's whole triangle list on its own; there is no CTA-wide barrier from
-    // here on.  Mesh order and screen position go together, so at any list position only a few rows of a tile have work:
-    // lock-stepped rounds of staged records left most warps waiting (37 % of all stall samples at the round barrier).
-    // Lanes test 32 packed pixel boxes per step (8 bytes per triangle, coalesced for mesh-ordered ids; the next
-    // steps' ids and boxes are in flight meanwhile); the ids that touch my row collect in a pending list and are
-    // rasterised 32 at a time, so chunks are full whatever the density.  A chunk's 32 compact records are copied to the
-    // warp's private slots in shared memory first (one L2 round trip per chunk, 6 x 16 bytes per lane).
-    if (row_in) {
+    // ---- my brick: every warp streams the tile's whole triangle list on its own; there is no CTA-wide barrier from here
+    // on.  Lanes test 32 list entries per step (one byte each; without a sorted list — an overflowed tile walks every
+    // triangle of the draw — the packed pixel boxes themselves); the ids that meet my brick collect in a pending list and
+    // are rasterised 32 at a time, so chunks are full whatever the density.  A chunk's 32 compact records are copied to
+    // the warp's private slots in shared memory first (one L2 round trip per chunk, 6 x 16 bytes per lane).
+    if (brick_in) {
         uint32_t* pend = sh.tile.pend[warp];
         uint32_t pend_n = 0;
         const uint32_t* ids = p.bin_entries + beg;
         const TriRecC* recs_g = reinterpret_cast<const TriRecC*>(p.tris);
-        auto load_id = [&](uint32_t i) { return i < n_source ? (direct ? i : ids[i]) : 0xffffffffu; };
-        auto load_box = [&](uint32_t id) { return id != 0xffffffffu ? __ldg(&p.boxes[id]) : make_uint2(1u, 1u); };  // 1 > 0: empty
         const uint32_t n_steps = (n_source + 31u) / 32u;
-        // software pipeline of the filter: ids three steps ahead, boxes two steps ahead
-        uint32_t id0 = load_id(lane), id1 = load_id(32u + lane), id2 = load_id(64u + lane);
-        uint2 box0 = load_box(id0), box1 = load_box(id1);
         uint32_t step = 0;
         const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
         constexpr uint32_t kQ = sizeof(TriRecC) / 16;  // 16-byte vectors per record
         for (;;) {
             while (pend_n < 32u && step < n_steps) {
-                const int minx = (int)(box0.x & 0xffffu), maxx = (int)(box0.x >> 16);
-                const int miny = (int)(box0.y & 0xffffu), maxy = (int)(box0.y >> 16);
-                const bool hit = minx <= maxx && py >= miny && py <= maxy && minx <= tile_px0 + kTileW - 1 && maxx >= tile_px0;
+                const uint32_t i = step * 32u + lane;
+                bool hit = false;
+                if (i < n_source) {
+                    if (!direct) hit = sh.brick_mask[i] >> warp & 1u;
+                    else hit = brick_mask_of(__ldg(&p.boxes[i]), tile_px0, tile_py0) >> warp & 1u;
+                }
                 const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = id0;
+                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = direct ? i : ids[i];
                 pend_n += __popc(b);
-                id0 = id1;
-                box0 = box1;
-                id1 = id2;
-                box1 = load_box(id1);
                 ++step;
-                id2 = load_id((step + 2u) * 32u + lane);
             }
             if (pend_n == 0) break;
             const uint32_t n = min(pend_n, 32u);
@@ -1516,7 +1563,7 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, n, tile_px0, py, sy, depth_test, depth_write, has_color, n_covered, n_passed);
+            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, n, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
             const bool mv = lane + 32u < pend_n;
             const uint32_t v = mv ? pend[32u + lane] : 0u;
             __syncwarp();
@@ -1526,27 +1573,29 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
         }
     }
 
-    // ---- tile epilogue: each lane writes back its 4 pixels of the row where they changed ----
+    // ---- brick epilogue: each lane writes back its 8 pixels where they changed ----
     __syncwarp();
     if (quad_clip) {
-        const uint32_t cd = bytes_to_bits(reinterpret_cast<const uint32_t*>(sh.tile.color_dirty[warp])[lane]) & quad_clip;
-        const uint32_t dd = bytes_to_bits(reinterpret_cast<const uint32_t*>(sh.tile.depth_dirty[warp])[lane]) & quad_clip;
-        if (cd) {
-            if (cd == 15u && vec_ok && (p.color_base & 15ull) == 0) {
-                *reinterpret_cast<uint4*>(caddr) = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][lane * kPx]);
-            } else {
+        const uint2 cdb = *reinterpret_cast<const uint2*>(&sh.tile.color_dirty[warp][qat]);
+        const uint2 ddb = *reinterpret_cast<const uint2*>(&sh.tile.depth_dirty[warp][qat]);
+        const uint32_t cd = (bytes_to_bits(cdb.x) | bytes_to_bits(cdb.y) << 4) & quad_clip;
+        const uint32_t dd = (bytes_to_bits(ddb.x) | bytes_to_bits(ddb.y) << 4) & quad_clip;
 #pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    if (cd >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 4 * k) = sh.tile.color[warp][lane * kPx + k];
+        for (int h = 0; h < kBrickPx / 4; ++h) {
+            const uint32_t c4 = cd >> (4 * h) & 15u, d4 = dd >> (4 * h) & 15u;
+            if (c4 == 15u && cvec) {
+                *reinterpret_cast<uint4*>(caddr + 16 * h) = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][qat + 4 * h]);
+            } else if (c4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = sh.tile.color[warp][qat + 4 * h + k];
             }
-        }
-        if (dd) {
-            if (dd == 15u && vec_ok && (p.depth_base & 15ull) == 0) {
-                *reinterpret_cast<float4*>(daddr) = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][lane * kPx]);
-            } else {
+            if (d4 == 15u && dvec) {
+                *reinterpret_cast<float4*>(daddr + 16 * h) = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][qat + 4 * h]);
+            } else if (d4) {
 #pragma unroll
-                for (int k = 0; k < kPx; ++k)
-                    if (dd >> k & 1u) *reinterpret_cast<float*>(daddr + 4 * k) = sh.tile.depth[warp][lane * kPx + k];
+                for (int k = 0; k < 4; ++k)
+                    if (d4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = sh.tile.depth[warp][qat + 4 * h + k];
             }
         }
     }
