@@ -39,8 +39,14 @@ namespace {
 
 constexpr int kBrick = 16;                     // raster_kernel: a warp owns one 16 x 16 pixel brick of its CTA's tile
 constexpr int kTileW = 4 * kBrick, kTileH = 2 * kBrick;  // pixels per raster tile (= binning granularity): 4 x 2 bricks
-constexpr int kRasterWarps = 8;                // one per brick
+constexpr int kTileBricks = 8;                 // bricks per tile
+constexpr int kSortThreads = 256;              // tile_sort_kernel: one CTA per tile
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRasterWarps = 4;                // raster_kernel: independent warps per CTA, each takes bricks from a work counter
 constexpr int kRasterThreads = 32 * kRasterWarps;
+#ifndef KZN_RASTER_CTAS
+#define KZN_RASTER_CTAS 6
+#endif
 constexpr int kBrickPx = 8;                    // prologue / epilogue / wide path: lane l = row l >> 1, pixels 8 (l & 1) .. + 7 of the brick
 constexpr int kDirectPx = 8;                   // raster_direct_kernel: pixels per lane (two 16-byte vectors)
 constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels wide ...
@@ -53,9 +59,6 @@ constexpr int kDirectTileW = 32 * kDirectPx;   // a warp's block is 256 pixels w
 constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows high
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
-#ifndef KZN_RASTER_CTAS
-#define KZN_RASTER_CTAS 3
-#endif
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
@@ -126,6 +129,8 @@ struct DrawParams {
     uint32_t* tile_offsets;  // [tiles+1] (bin_scan)
     uint32_t* tile_cursor;   // [tiles]  (bin_fill)
     uint32_t* bin_entries;   // [bin_capacity]
+    uint32_t* bin_entries_alt;  // [bin_capacity] second buffer of the in-tile sort
+    uint8_t* bin_masks;      // [bin_capacity] per sorted entry: the bricks of its tile that the triangle's pixel box meets (tile_sort_kernel)
     uint32_t bin_capacity;
     uint32_t tiles_x, tiles_y, tile_x0, tile_y0;  // tile grid covering the clip rectangle
     uint32_t binned;                               // 0 => every tile walks all triangles
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     kzn_pdl_wait();
     constexpr int kQuads = BINNED ? (int)(sizeof(TriRecC) / 16) : (int)(sizeof(TriRec) / 16);
     const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
-    if (!BINNED && t_raw == 0) *p.work_counter = 0u;  // raster_direct_kernel's block dispenser
+    if (t_raw == 0) p.work_counter[BINNED ? 2 : 0] = 0u;  // the work dispenser of raster_kernel / raster_direct_kernel
     const bool in_range = t_raw < p.tris_per_instance;
     const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
     // The CTA's 256 records are contiguous in memory: they are transposed through shared memory and written with
@@ -549,47 +554,41 @@ __device__ __forceinline__ unsigned long long color_addr(const DrawParams& p, in
 // 4 flag bits <-> 4 flag bytes (0 / 1) of a lane's pixel quad
 __device__ __forceinline__ uint32_t bytes_to_bits(uint32_t w) { return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); }
 
-struct TileState {  // live from the tile prologue to the epilogue; [warp] = the warp's brick
-    TriRecC recs[kRasterWarps][32];     // the records of the chunk being rasterised (private to the warp)
-    BrickEdge edges[kRasterWarps][32];  // what lane j derived for triangle j of the chunk
-    uint32_t pend[kRasterWarps][64];    // ids of the triangles whose pixel box meets the brick, waiting for a full chunk
-    uint32_t queue[kRasterWarps][64];   // covered fragments waiting for a full shading batch: chunk slot << 8 | y << 4 | x
-    uint32_t color[kRasterWarps][kBrick * kBrick];  // the brick's colour and depth live here for the whole triangle list
-    float depth[kRasterWarps][kBrick * kBrick];
-    uint8_t color_dirty[kRasterWarps][kBrick * kBrick];  // one byte per pixel (plain stores: a brick belongs to one warp)
-    uint8_t depth_dirty[kRasterWarps][kBrick * kBrick];
+struct BrickState {  // private to one warp of raster_kernel: the brick it is working on
+    TriRecC recs[32];     // the records of the chunk being rasterised
+    BrickEdge edges[32];  // what lane j derived for triangle j of the chunk
+    uint32_t pend[160];   // ids of the triangles whose pixel box meets the brick, waiting for a full chunk (32 + one filter step of 128)
+    uint32_t queue[64];   // covered fragments waiting for a full shading batch: chunk slot << 8 | y << 4 | x
+    uint32_t color[kBrick * kBrick];  // the brick's colour and depth live here for the whole triangle list
+    float depth[kBrick * kBrick];
+    uint8_t color_dirty[kBrick * kBrick];  // one byte per pixel (plain stores: a brick belongs to one warp)
+    uint8_t depth_dirty[kBrick * kBrick];
 };
-struct SortScratch {  // live only while the tile's id list is sorted (before the prologue); the result goes back to global memory
+struct RasterShared {
+    BrickState brick[kRasterWarps];
+    float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
+};
+struct SortShared {  // tile_sort_cta_kernel
     uint32_t list[kSortCap];
     uint32_t second[kSortCap];
-    uint32_t table[256 * kRasterWarps];  // [digit][warp]
+    uint32_t table[256 * kSortWarps];  // [digit][warp]
+    uint32_t warp_counts[kSortWarps];
 };
 
-struct RasterShared {
-    union {
-        TileState tile;
-        SortScratch sort;
-    };
-    uint8_t brick_mask[kSortCap];  // per entry of the sorted list: the bricks of the tile its pixel box meets
-    float unorm_lut[256];  // u8 / 255.0f, the exact quotients (E.1), so blending needs no division per fragment
-    uint32_t warp_counts[kRasterWarps];
-};
-
-// Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.sort.list, by the whole CTA.  The binning
+// Stable LSD radix sort (8-bit digits) of the n <= kSortCap triangle ids in sh.list, by the whole CTA.  The binning
 // atomics deliver each tile's list in arbitrary order; primitive order (R7) is restored here.  Only the bits in which the
 // ids of this tile differ are sorted (ids of one tile come from a narrow range of a mesh: typically 2 passes).
 // Warp w owns a contiguous slice of the list and walks it 32 ids at a time; match.any ranks equal digits inside a batch
 // in lane order, a [digit][warp] table of running offsets orders batches and warps, so every pass is stable.
-// Scratch (second id buffer, offset table) shares memory with the tile state, which is not live yet.
-__device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint32_t n) {
+__device__ __forceinline__ const uint32_t* sort_tile_list(SortShared& sh, uint32_t n) {
     constexpr uint32_t kFull = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t* a = sh.sort.list;
-    uint32_t* b = sh.sort.second;
-    uint32_t* table = sh.sort.table;  // [256 digits][kRasterWarps warps]
+    uint32_t* a = sh.list;
+    uint32_t* b = sh.second;
+    uint32_t* table = sh.table;  // [256 digits][kSortWarps warps]
     // range of the ids
     uint32_t lo = 0xffffffffu, hi = 0u;
-    for (uint32_t i = tid; i < n; i += kRasterThreads) {
+    for (uint32_t i = tid; i < n; i += kSortThreads) {
         const uint32_t v = a[i];
         lo = min(lo, v);
         hi = max(hi, v);
@@ -602,17 +601,17 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kRasterWarps; ++w) {
+    for (int w = 0; w < kSortWarps; ++w) {
         lo = min(lo, sh.warp_counts[w]);
         hi = max(hi, table[w]);
     }
     __syncthreads();
     const uint32_t span = hi - lo;
     const uint32_t bits = span ? 32u - (uint32_t)__clz(span) : 0u;
-    const uint32_t per = ((n + kRasterThreads - 1) / kRasterThreads) * 32u;  // ids per warp, whole batches
+    const uint32_t per = ((n + kSortThreads - 1) / kSortThreads) * 32u;  // ids per warp, whole batches
     const uint32_t w_beg = min(warp * per, n), w_end = min(w_beg + per, n);
     for (uint32_t shift = 0; shift < bits; shift += 8) {
-        for (uint32_t i = tid; i < 256u * kRasterWarps; i += kRasterThreads) table[i] = 0;
+        for (uint32_t i = tid; i < 256u * kSortWarps; i += kSortThreads) table[i] = 0;
         __syncthreads();
         // digit counts per warp
         for (uint32_t base = w_beg; base < w_end; base += 32) {
@@ -620,17 +619,17 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             const bool valid = i < w_end;
             const uint32_t d = valid ? ((a[i] - lo) >> shift) & 255u : 256u + lane;
             const uint32_t peers = __match_any_sync(kFull, d);
-            if (valid && (int)lane == __ffs(peers) - 1) table[d * kRasterWarps + warp] += __popc(peers);
+            if (valid && (int)lane == __ffs(peers) - 1) table[d * kSortWarps + warp] += __popc(peers);
             __syncwarp();
         }
         __syncthreads();
         // exclusive scan in (digit, warp) order: thread t owns digit t
         {
-            uint32_t v[kRasterWarps], total = 0;
+            uint32_t v[kSortWarps], total = 0;
 #pragma unroll
-            for (int k = 0; k < kRasterWarps; ++k) {
+            for (int k = 0; k < kSortWarps; ++k) {
                 v[k] = total;
-                total += table[tid * kRasterWarps + k];
+                total += table[tid * kSortWarps + k];
             }
             uint32_t incl = total;
 #pragma unroll
@@ -642,10 +641,10 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             __syncthreads();
             uint32_t before = incl - total;
 #pragma unroll
-            for (int w = 0; w < kRasterWarps; ++w)
+            for (int w = 0; w < kSortWarps; ++w)
                 if ((uint32_t)w < warp) before += sh.warp_counts[w];
 #pragma unroll
-            for (int k = 0; k < kRasterWarps; ++k) table[tid * kRasterWarps + k] = before + v[k];
+            for (int k = 0; k < kSortWarps; ++k) table[tid * kSortWarps + k] = before + v[k];
         }
         __syncthreads();
         // stable scatter
@@ -658,8 +657,8 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(RasterShared& sh, uint
             const int leader = __ffs(peers) - 1;
             uint32_t start = 0;
             if (valid && (int)lane == leader) {
-                start = table[d * kRasterWarps + warp];
-                table[d * kRasterWarps + warp] = start + __popc(peers);
+                start = table[d * kSortWarps + warp];
+                table[d * kSortWarps + warp] = start + __popc(peers);
             }
             start = __shfl_sync(kFull, start, leader);
             if (valid) b[start + __popc(peers & ((1u << lane) - 1u))] = v;
@@ -761,13 +760,13 @@ __device__ __forceinline__ void interpolate_color(const float iw[3], const float
 // pixel are applied in lane order (= primitive order, R7) using match.any.  Returns 1 on the lanes whose fragment passed
 // the depth test.  Not inlined: it has three call sites in the chunk loop.
 template <uint32_t FS, int NEED_DST>
-__device__ __noinline__ uint32_t shade_queue(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int brick_px0,
+__device__ __noinline__ uint32_t shade_queue(const DrawParams& p, BrickState& bs, const float* lut, uint32_t lane, uint32_t n, int brick_px0,
                                              int brick_py0, bool depth_test, bool depth_write, bool has_color) {
     uint32_t n_passed = 0;
     const bool have = lane < n;
-    const uint32_t key = have ? sh.tile.queue[warp][lane] : 0u;
+    const uint32_t key = have ? bs.queue[lane] : 0u;
     const uint32_t slot = key >> 8, pix = key & 255u;
-    const BrickEdge& e = sh.tile.edges[warp][slot];
+    const BrickEdge& e = bs.edges[slot];
     const int4 ef = *reinterpret_cast<const int4*>(&e.f[0]);
     const int4 es = *reinterpret_cast<const int4*>(&e.s[0]);
     const int4 eu = *reinterpret_cast<const int4*>(&e.u[0]);
@@ -778,7 +777,7 @@ __device__ __noinline__ uint32_t shade_queue(const DrawParams& p, RasterShared& 
     const float l0 = (float)(F0 + (int32_t)(xw >> 13 & 1u)) * inv2a;  // R6: E_i = F_i + 1 - bias_i
     const float l1 = (float)(F1 + (int32_t)(xw >> 14 & 1u)) * inv2a;
     const float l2 = (float)(F2 + (int32_t)(xw >> 15 & 1u)) * inv2a;
-    const TriRecC& t = sh.tile.recs[warp][slot];
+    const TriRecC& t = bs.recs[slot];
     const float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
     const int px = brick_px0 + (int)(pix & 15u), py = brick_py0 + (int)(pix >> 4);
     const uint32_t kx = have ? pix : (0x80000000u | lane);  // unique key for idle lanes
@@ -788,19 +787,19 @@ __device__ __noinline__ uint32_t shade_queue(const DrawParams& p, RasterShared& 
     float src[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (max_rank == 0) {  // warp-uniform, the usual case: every fragment of the batch has its pixel to itself
         bool pass = have;
-        if (depth_test && have) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][pix]);  // R7: early-Z
+        if (depth_test && have) pass = depth_compare(p.st.depth_compare_op, z, bs.depth[pix]);  // R7: early-Z
         if (pass) {
             n_passed = 1;
             if (depth_write) {
-                sh.tile.depth[warp][pix] = z;
-                sh.tile.depth_dirty[warp][pix] = 1;
+                bs.depth[pix] = z;
+                bs.depth_dirty[pix] = 1;
             }
             if (has_color) {
                 if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
                 else interpolate_color(t.iw, t.col, l0, l1, l2, src);
-                const uint32_t dst = NEED_DST ? sh.tile.color[warp][pix] : 0u;
-                sh.tile.color[warp][pix] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                sh.tile.color_dirty[warp][pix] = 1;
+                const uint32_t dst = NEED_DST ? bs.color[pix] : 0u;
+                bs.color[pix] = output_merge_lut<NEED_DST>(p.st, lut, src, dst);
+                bs.color_dirty[pix] = 1;
             }
         }
         __syncwarp();
@@ -813,17 +812,17 @@ __device__ __noinline__ uint32_t shade_queue(const DrawParams& p, RasterShared& 
     for (uint32_t rk = 0; rk <= max_rank; ++rk) {
         if (have && rank == rk) {
             bool pass = true;
-            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, sh.tile.depth[warp][pix]);  // R7: early-Z
+            if (depth_test) pass = depth_compare(p.st.depth_compare_op, z, bs.depth[pix]);  // R7: early-Z
             if (pass) {
                 n_passed = 1;
                 if (depth_write) {
-                    sh.tile.depth[warp][pix] = z;
-                    sh.tile.depth_dirty[warp][pix] = 1;
+                    bs.depth[pix] = z;
+                    bs.depth_dirty[pix] = 1;
                 }
                 if (has_color) {
-                    const uint32_t dst = NEED_DST ? sh.tile.color[warp][pix] : 0u;
-                    sh.tile.color[warp][pix] = output_merge_lut<NEED_DST>(p.st, sh.unorm_lut, src, dst);
-                    sh.tile.color_dirty[warp][pix] = 1;
+                    const uint32_t dst = NEED_DST ? bs.color[pix] : 0u;
+                    bs.color[pix] = output_merge_lut<NEED_DST>(p.st, lut, src, dst);
+                    bs.color_dirty[pix] = 1;
                 }
             }
         }
@@ -1005,12 +1004,12 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
 // shared-memory accesses).  Every lane expands the same record (warp-uniform); not inlined, so that the registers of the
 // expansion stay out of the streaming loop.
 template <uint32_t FS, int NEED_DST>
-__device__ __noinline__ void shade_wide(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t slot,
+__device__ __noinline__ void shade_wide(const DrawParams& p, BrickState& bs, const float* lut, uint32_t lane, uint32_t slot,
                                         int brick_px0, int brick_py0, bool depth_test, bool depth_write, bool has_color,
                                         uint32_t& n_covered, uint32_t& n_passed) {
     TriRec t;
     {
-        const TriRecC& c = sh.tile.recs[warp][slot];
+        const TriRecC& c = bs.recs[slot];
         expand_record(p, c, record_box(p, c), t);
     }
     const uint32_t at = lane * kBrickPx;  // (lane >> 1) * 16 + (lane & 1) * 8
@@ -1025,24 +1024,24 @@ __device__ __noinline__ void shade_wide(const DrawParams& p, RasterShared& sh, u
 #pragma unroll
     for (int h = 0; h < kBrickPx / 4; ++h) {
         float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (depth_test) dq = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][at + 4 * h]);
+        if (depth_test) dq = *reinterpret_cast<const float4*>(&bs.depth[at + 4 * h]);
         depth[4 * h] = dq.x; depth[4 * h + 1] = dq.y; depth[4 * h + 2] = dq.z; depth[4 * h + 3] = dq.w;
         uint4 cq = make_uint4(0u, 0u, 0u, 0u);
-        if (has_color) cq = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][at + 4 * h]);
+        if (has_color) cq = *reinterpret_cast<const uint4*>(&bs.color[at + 4 * h]);
         col[4 * h] = cq.x; col[4 * h + 1] = cq.y; col[4 * h + 2] = cq.z; col[4 * h + 3] = cq.w;
     }
     uint32_t live, zwrite;
-    span_quad<FS, NEED_DST, kBrickPx, false>(p, t, sh.unorm_lut, px0, py, 16 * py + 8, xa, xb, depth_test, depth_write, has_color, col, depth,
+    span_quad<FS, NEED_DST, kBrickPx, false>(p, t, lut, px0, py, 16 * py + 8, xa, xb, depth_test, depth_write, has_color, col, depth,
                                              live, zwrite, n_covered, n_passed);
 #pragma unroll
     for (int k = 0; k < kBrickPx; ++k) {
         if (zwrite >> k & 1u) {
-            sh.tile.depth[warp][at + k] = depth[k];
-            sh.tile.depth_dirty[warp][at + k] = 1;
+            bs.depth[at + k] = depth[k];
+            bs.depth_dirty[at + k] = 1;
         }
         if (live >> k & 1u) {
-            sh.tile.color[warp][at + k] = col[k];
-            sh.tile.color_dirty[warp][at + k] = 1;
+            bs.color[at + k] = col[k];
+            bs.color_dirty[at + k] = 1;
         }
     }
     __syncwarp();
@@ -1282,7 +1281,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
 __constant__ uint32_t kWidthMagic[17] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,
                                          7282,  6554,  5958,  5462,  5042,  4682,  4370, 4096};  // ceil(2^16 / w)
 
-// One chunk of a brick's work: the first n (<= 32) slots of sh.tile.recs[warp] hold the compact records of triangles whose
+// One chunk of a brick's work: the first n (<= 32) slots of bs.recs hold the compact records of triangles whose
 // pixel box meets the brick, in primitive order.
 //  1. Lane j derives triangle j for this brick (BrickEdge): its pixel box inside the brick, the three biased edge
 //     functions at the box's first pixel and their steps in x and y, 1/2A — exact 32-bit integer arithmetic for triangles
@@ -1294,7 +1293,7 @@ __constant__ uint32_t kWidthMagic[17] = {0,     65536, 32768, 21846, 16384, 1310
 //  3. Triangles too large for 32-bit arithmetic go through shade_wide; they split the chunk into segments so that primitive
 //     order is kept.  The queue is drained before the chunk's records are replaced.
 template <uint32_t FS, int NEED_DST>
-__device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& sh, uint32_t warp, uint32_t lane, uint32_t n, int brick_px0,
+__device__ __forceinline__ void raster_chunk(const DrawParams& p, BrickState& bs, const float* lut, uint32_t lane, uint32_t n, int brick_px0,
                                              int brick_py0, bool depth_test, bool depth_write, bool has_color, uint32_t& n_covered,
                                              uint32_t& n_passed) {
     constexpr uint32_t kFull = 0xffffffffu;
@@ -1302,7 +1301,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
     uint32_t count = 0;
     bool wide = false;
     if (have) {
-        const TriRecC& r = sh.tile.recs[warp][lane];
+        const TriRecC& r = bs.recs[lane];
         const int4 q0 = *reinterpret_cast<const int4*>(&r.X[0]);  // X0 X1 X2 Y0
         const int2 q1 = *reinterpret_cast<const int2*>(&r.Y[1]);  // Y1 Y2
         const int32_t X0 = q0.x, X1 = q0.y, X2 = q0.z, Y0 = q0.w, Y1 = q1.x, Y2 = q1.y;
@@ -1333,7 +1332,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
                 uint32_t xw = (uint32_t)(x0 - brick_px0) | (uint32_t)(y0 - brick_py0) << 4 | (uint32_t)w << 8 | (uint32_t)(1 - t0) << 13 |
                               (uint32_t)(1 - t1) << 14 | (uint32_t)(1 - t2) << 15;
                 if (depth_clip_cannot_reject(p, r.z[0], r.z[1], r.z[2])) xw |= 1u << 16;
-                BrickEdge& e = sh.tile.edges[warp][lane];
+                BrickEdge& e = bs.edges[lane];
                 *reinterpret_cast<int4*>(&e.f[0]) = make_int4(f0, f1, f2, (int)xw);
                 *reinterpret_cast<int4*>(&e.s[0]) = make_int4(16 * a0, 16 * a1, 16 * a2, __float_as_int(1.0f / (float)(two_a * sg)));
                 *reinterpret_cast<int4*>(&e.u[0]) = make_int4(16 * b0, 16 * b1, 16 * b2, (int)kWidthMagic[w]);
@@ -1350,7 +1349,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
     }
     const uint32_t total = __shfl_sync(kFull, incl, 31);
     const uint32_t excl = incl - count;
-    uint32_t* queue = sh.tile.queue[warp];
+    uint32_t* queue = bs.queue;
     uint32_t q_n = 0;  // fragments waiting in the queue (warp-uniform)
     uint32_t seg_begin = 0;
     for (;;) {
@@ -1367,7 +1366,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
                 if (e <= c) pos += step;
             }
             const uint32_t k = c - __shfl_sync(kFull, excl, pos);
-            const BrickEdge& e = sh.tile.edges[warp][pos];
+            const BrickEdge& e = bs.edges[pos];
             const int4 ef = *reinterpret_cast<const int4*>(&e.f[0]);
             const int4 es = *reinterpret_cast<const int4*>(&e.s[0]);
             const int4 eu = *reinterpret_cast<const int4*>(&e.u[0]);
@@ -1382,7 +1381,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
                 const float l0 = (float)(F0 + (int32_t)(xw >> 13 & 1u)) * inv2a;
                 const float l1 = (float)(F1 + (int32_t)(xw >> 14 & 1u)) * inv2a;
                 const float l2 = (float)(F2 + (int32_t)(xw >> 15 & 1u)) * inv2a;
-                const TriRecC& t = sh.tile.recs[warp][pos];
+                const TriRecC& t = bs.recs[pos];
                 const float z = fmaf(l2, t.z[2], fmaf(l1, t.z[1], l0 * t.z[0]));
                 cov = z >= p.zclip_lo && z <= p.zclip_hi;  // false for NaN
             }
@@ -1395,7 +1394,7 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
             q_n += __popc(ballot);
             __syncwarp();
             if (q_n >= 32u) {
-                n_passed += shade_queue<FS, NEED_DST>(p, sh, warp, lane, 32u, brick_px0, brick_py0, depth_test, depth_write, has_color);
+                n_passed += shade_queue<FS, NEED_DST>(p, bs, lut, lane, 32u, brick_px0, brick_py0, depth_test, depth_write, has_color);
                 const uint32_t rest = lane < q_n - 32u ? queue[32u + lane] : 0u;  // move the remainder (< 32 entries) to the front
                 __syncwarp();
                 if (lane < q_n - 32u) queue[lane] = rest;
@@ -1404,11 +1403,11 @@ __device__ __forceinline__ void raster_chunk(const DrawParams& p, RasterShared& 
             }
         }
         if (q_n) {  // before a wide triangle, and before the chunk's records are replaced
-            n_passed += shade_queue<FS, NEED_DST>(p, sh, warp, lane, q_n, brick_px0, brick_py0, depth_test, depth_write, has_color);
+            n_passed += shade_queue<FS, NEED_DST>(p, bs, lut, lane, q_n, brick_px0, brick_py0, depth_test, depth_write, has_color);
             q_n = 0;
         }
         if (wide_lane < 0) break;
-        shade_wide<FS, NEED_DST>(p, sh, warp, lane, (uint32_t)wide_lane, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
+        shade_wide<FS, NEED_DST>(p, bs, lut, lane, (uint32_t)wide_lane, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
         wide_mask &= wide_mask - 1;
         seg_begin = seg_end;
     }
@@ -1425,179 +1424,348 @@ __device__ __forceinline__ uint32_t brick_mask_of(uint2 box, int tile_px0, int t
     return (by0 == 0 ? xm : 0u) | (by1 >= 1 ? xm << 4 : 0u);
 }
 
-// One CTA per 64 x 32-pixel screen tile; warp w owns the 16 x 16 brick (w & 3, w >> 2) of the tile: its colour and depth
-// live in shared memory for the whole triangle list (each framebuffer byte read at most once, written at most once), and
-// all its fragments are applied by this warp alone, in primitive order — nothing is shared between the warps after the
-// in-tile sort.  Bricks rather than rows: a small triangle meets one or two bricks but three or four rows, and everything
-// that is done per (triangle, warp) — record copy, edge derivation, prefix sums — is paid that many times.
+// where the brick masks of a tile's list live: 4-byte aligned so that a lane can fetch four entries at once (the gap of
+// 4 bytes per tile keeps consecutive tiles' regions apart after rounding up)
+__device__ __forceinline__ uint8_t* tile_masks(const DrawParams& p, uint32_t tile, uint32_t beg) {
+    return p.bin_masks + (((size_t)beg + 3u) & ~(size_t)3u) + 4u * (size_t)tile;
+}
+
+// (tile_sort_warp_kernel: frames of many tiles with short lists; tile_sort_cta_kernel below: fewer tiles with long lists.)
+// One warp per 64 x 32-pixel screen tile: the binning atomics deliver the tile's triangle ids in arbitrary order; they are
+// sorted here (ascending = primitive order, R7) and each entry's pixel box is looked at once, for all eight bricks of the
+// tile: one byte per entry that raster_kernel's warps filter the list by.
+// Stable LSD radix sort, 8-bit digits, only over the bits in which the ids of this tile differ (ids of one tile come from a
+// narrow range of a mesh: typically 2 passes).  The warp walks the list 32 ids at a time: match.any ranks equal digits
+// inside a batch in lane order, a 256-entry table of running offsets in shared memory orders the batches.  The lists
+// themselves stay in global memory (the tile's segment of the bins and of a second buffer of the same size, ping-pong;
+// a few KiB that live in L2), so a warp needs 1 KiB of shared memory and no CTA barrier — 64 sorting warps per SM, where a
+// CTA per tile with the lists in shared memory spent its time in barriers (9 us per tile whatever its length).
+__global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    constexpr uint32_t kFull = 0xffffffffu;
+    __shared__ uint32_t tables[kSortWarps][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * kSortWarps + warp;
+    if (tile >= p.tiles_x * p.tiles_y) return;
+    const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+    const int tile_px0 = (int)(p.tile_x0 + tile_x) * kTileW, tile_py0 = (int)(p.tile_y0 + tile_y) * kTileH;
+    const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], n = end - beg;
+    if (n == 0) return;
+    if (p.stats && lane == 0) atomicAdd(&p.stats[6], 1ull);
+    if (n > (uint32_t)kSortCap || end > p.bin_capacity) {  // raster_kernel walks every triangle of the draw for this tile
+        if (p.stats && lane == 0) atomicAdd(&p.stats[7], 1ull);
+        return;
+    }
+    uint32_t* table = tables[warp];
+    uint32_t* a = p.bin_entries + beg;
+    uint32_t* b = p.bin_entries_alt + beg;
+    // range of the ids
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = lane; i < n; i += 32u) {
+        const uint32_t v = a[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    const uint32_t span = hi - lo;
+    const uint32_t bits = span ? 32u - (uint32_t)__clz(span) : 0u;
+    for (uint32_t shift = 0; shift < bits; shift += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) table[lane + 32 * k] = 0;
+        __syncwarp();
+        // digit counts (four batches of 32 ids in flight: the lists live in L2, a batch per round trip was the whole kernel)
+        for (uint32_t base = 0; base < n; base += 128u) {
+            uint32_t v[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) v[k] = base + 32u * k + lane < n ? __ldcg(a + base + 32u * k + lane) : 0u;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                if (base + 32u * k >= n) break;
+                const bool valid = base + 32u * k + lane < n;
+                const uint32_t d = valid ? ((v[k] - lo) >> shift) & 255u : 256u + lane;
+                const uint32_t peers = __match_any_sync(kFull, d);
+                if (valid && (int)lane == __ffs(peers) - 1) table[d] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        // exclusive scan of the 256 counts: lane l owns digits 8l .. 8l + 7
+        {
+            uint32_t v[8], total = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = total;
+                total += table[lane * 8 + k];
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            const uint32_t before = incl - total;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) table[lane * 8 + k] = before + v[k];
+        }
+        __syncwarp();
+        // stable scatter
+        for (uint32_t base = 0; base < n; base += 128u) {
+            uint32_t vv[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) vv[k] = base + 32u * k + lane < n ? __ldcg(a + base + 32u * k + lane) : 0u;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                if (base + 32u * k >= n) break;
+                const bool valid = base + 32u * k + lane < n;
+                const uint32_t v = vv[k];
+                const uint32_t d = valid ? ((v - lo) >> shift) & 255u : 256u + lane;
+                const uint32_t peers = __match_any_sync(kFull, d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t start = 0;
+                if (valid && (int)lane == leader) {
+                    start = table[d];
+                    table[d] = start + __popc(peers);
+                }
+                start = __shfl_sync(kFull, start, leader);
+                if (valid) __stcg(b + start + __popc(peers & ((1u << lane) - 1u)), v);
+                __syncwarp();
+            }
+        }
+        __threadfence_block();  // the next pass (other lanes of this warp) reads what this one wrote
+        __syncwarp();
+        uint32_t* t = a;
+        a = b;
+        b = t;
+    }
+    // the sorted list goes to the tile's segment of the bins (if the last pass left it in the other buffer) with its masks
+    uint32_t* out = p.bin_entries + beg;
+    uint8_t* masks = tile_masks(p, tile, beg);
+    for (uint32_t i = lane; i < n; i += 32u) {
+        const uint32_t id = __ldcg(a + i);
+        if (a != out) out[i] = id;
+        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
+    }
+}
+
+// The same with one CTA per tile and the lists in shared memory (per-warp slices, a [digit][warp] table orders batches and
+// warps, so every pass is stable): the better form when tiles are few and their lists long (a warp alone walks a list of a
+// thousand ids in 35 dependent steps per phase).
+__global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortShared& sh = *reinterpret_cast<SortShared*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
+    const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], list_len = end - beg;
+    if (list_len == 0) return;
+    if (p.stats && tid == 0) atomicAdd(&p.stats[6], 1ull);
+    if (list_len > (uint32_t)kSortCap || end > p.bin_capacity) {  // raster_kernel walks every triangle of the draw for this tile
+        if (p.stats && tid == 0) atomicAdd(&p.stats[7], 1ull);
+        return;
+    }
+    for (uint32_t i = tid; i < list_len; i += kSortThreads) sh.list[i] = p.bin_entries[beg + i];
+    __syncthreads();
+    const uint32_t* sorted = sort_tile_list(sh, list_len);
+    uint8_t* masks = tile_masks(p, tile, beg);
+    for (uint32_t i = tid; i < list_len; i += kSortThreads) {
+        const uint32_t id = sorted[i];
+        p.bin_entries[beg + i] = id;
+        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
+    }
+}
+
+// Persistent, independent warps (kRasterWarps per CTA share nothing but the UNORM8 table): a warp takes one 16 x 16 brick
+// at a time from a global work counter — unit u = brick u % 8 of tile u / 8 — until none are left, so no warp waits for
+// the slowest brick of its tile and the last wave of a frame is bricks, not tiles.  The brick's colour and depth live in
+// the warp's shared memory for the whole triangle list (each framebuffer byte read at most once, written at most once),
+// and all its fragments are applied by this warp alone, in primitive order.  Bricks rather than rows: a small triangle
+// meets one or two bricks but three or four rows, and everything that is done per (triangle, warp) — record copy, edge
+// derivation, prefix sums — is paid that many times.
 template <uint32_t FS, int NEED_DST>
 __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
-    const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
-    const int brick_px0 = tile_px0 + (int)(warp & 3u) * kBrick, brick_py0 = tile_py0 + (int)(warp >> 2) * kBrick;
-    const bool brick_in = brick_px0 <= p.cx1 && brick_px0 + kBrick - 1 >= p.cx0 && brick_py0 <= p.cy1 && brick_py0 + kBrick - 1 >= p.cy0;
+    BrickState& bs = sh.brick[warp];
+    const float* lut = sh.unorm_lut;
     const bool has_color = p.color_base != 0, has_depth = p.depth_base != 0;
     const bool depth_test = has_depth && p.st.depth_test_enable;
     const bool depth_write = depth_test && p.st.depth_write_enable;
-    // prologue / epilogue: lane l moves the 8 pixels 8 (l & 1) .. + 7 of row l >> 1 of the brick, two 16-byte vectors when
-    // the row pitch allows it
-    const int qx0 = brick_px0 + (int)(lane & 1u) * kBrickPx, qy = brick_py0 + (int)(lane >> 1);
-    const uint32_t qat = lane * kBrickPx;
-    const bool vec_ok = (p.fb_w & 3u) == 0 && qx0 + kBrickPx <= (int)p.fb_w;
-    uint32_t quad_clip = 0;
-#pragma unroll
-    for (int k = 0; k < kBrickPx; ++k)
-        if (qy >= p.cy0 && qy <= p.cy1 && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
-
-    // triangle source
-    uint32_t list_len = 0, beg = 0;
-    bool direct = true;
-    if (p.binned) {
-        beg = p.tile_offsets[tile];
-        const uint32_t end = p.tile_offsets[tile + 1];
-        list_len = end - beg;
-        if (list_len == 0) return;
-        if (list_len <= (uint32_t)kSortCap && end <= p.bin_capacity) {
-            direct = false;
-            // load and sort the tile's triangle ids (ascending = primitive order)
-            for (uint32_t i = tid; i < list_len; i += kRasterThreads) sh.sort.list[i] = p.bin_entries[beg + i];
-            __syncthreads();
-            const uint32_t* sorted = sort_tile_list(sh, list_len);
-            // the tile's segment of the bins is private to this CTA: the sorted list goes back in place and is streamed
-            // from there, which frees the sort's shared memory for the tile state; each entry's pixel box is looked at
-            // once, here, for all eight bricks (the warps then filter the list by one byte per entry)
-            for (uint32_t i = tid; i < list_len; i += kRasterThreads) {
-                const uint32_t id = sorted[i];
-                p.bin_entries[beg + i] = id;
-                sh.brick_mask[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
-            }
-            __syncthreads();
-        } else if (p.stats && tid == 0) {
-            atomicAdd(&p.stats[7], 1ull);
-        }
+    if (NEED_DST) {
+        for (uint32_t i = tid; i < 256u; i += kRasterThreads) sh.unorm_lut[i] = unorm8_to_float(i);
+        __syncthreads();
     }
-    const uint32_t n_source = direct ? p.total_tris : list_len;
-
-    // ---- brick prologue: destination values the result depends on, dirty masks, the UNORM8 -> float table ----
-    unsigned long long caddr = 0, daddr = 0;
-    if (quad_clip) {
-        if (has_color) caddr = color_addr(p, qx0, qy);
-        if (has_depth) daddr = p.depth_base + ((unsigned long long)qy * p.fb_w + qx0) * 4ull;
-    }
-    const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
-    if (NEED_DST && quad_clip && has_color) {
-#pragma unroll
-        for (int h = 0; h < kBrickPx / 4; ++h) {
-            const uint32_t m4 = quad_clip >> (4 * h) & 15u;
-            if (m4 == 15u && cvec) {
-                *reinterpret_cast<uint4*>(&sh.tile.color[warp][qat + 4 * h]) = *reinterpret_cast<const uint4*>(caddr + 16 * h);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (m4 >> k & 1u) sh.tile.color[warp][qat + 4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
-            }
-        }
-    }
-    if (depth_test && quad_clip) {
-#pragma unroll
-        for (int h = 0; h < kBrickPx / 4; ++h) {
-            const uint32_t m4 = quad_clip >> (4 * h) & 15u;
-            if (m4 == 15u && dvec) {
-                *reinterpret_cast<float4*>(&sh.tile.depth[warp][qat + 4 * h]) = *reinterpret_cast<const float4*>(daddr + 16 * h);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (m4 >> k & 1u) sh.tile.depth[warp][qat + 4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
-            }
-        }
-    }
-    *reinterpret_cast<uint2*>(&sh.tile.color_dirty[warp][qat]) = make_uint2(0u, 0u);  // my 8 pixels' flags
-    *reinterpret_cast<uint2*>(&sh.tile.depth_dirty[warp][qat]) = make_uint2(0u, 0u);
-    if (NEED_DST) sh.unorm_lut[tid] = unorm8_to_float(tid);
-    __syncthreads();
-
+    const uint32_t n_units = p.tiles_x * p.tiles_y * (uint32_t)kTileBricks;
+    const TriRecC* recs_g = reinterpret_cast<const TriRecC*>(p.tris);
+    const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(bs.recs);
+    constexpr uint32_t kQ = sizeof(TriRecC) / 16;  // 16-byte vectors per record
     uint32_t n_covered = 0, n_passed = 0;
 
-    // ---- my brick: every warp streams the tile's whole triangle list on its own; there is no CTA-wide barrier from here
-    // on.  Lanes test 32 list entries per step (one byte each; without a sorted list — an overflowed tile walks every
-    // triangle of the draw — the packed pixel boxes themselves); the ids that meet my brick collect in a pending list and
-    // are rasterised 32 at a time, so chunks are full whatever the density.  A chunk's 32 compact records are copied to
-    // the warp's private slots in shared memory first (one L2 round trip per chunk, 6 x 16 bytes per lane).
-    if (brick_in) {
-        uint32_t* pend = sh.tile.pend[warp];
-        uint32_t pend_n = 0;
-        const uint32_t* ids = p.bin_entries + beg;
-        const TriRecC* recs_g = reinterpret_cast<const TriRecC*>(p.tris);
-        const uint32_t n_steps = (n_source + 31u) / 32u;
-        uint32_t step = 0;
-        const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(sh.tile.recs[warp]);
-        constexpr uint32_t kQ = sizeof(TriRecC) / 16;  // 16-byte vectors per record
-        for (;;) {
-            while (pend_n < 32u && step < n_steps) {
-                const uint32_t i = step * 32u + lane;
-                bool hit = false;
-                if (i < n_source) {
-                    if (!direct) hit = sh.brick_mask[i] >> warp & 1u;
-                    else hit = brick_mask_of(__ldg(&p.boxes[i]), tile_px0, tile_py0) >> warp & 1u;
-                }
-                const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                if (hit) pend[pend_n + __popc(b & ((1u << lane) - 1u))] = direct ? i : ids[i];
-                pend_n += __popc(b);
-                ++step;
-            }
-            if (pend_n == 0) break;
-            const uint32_t n = min(pend_n, 32u);
-            __syncwarp();
-            // the chunk's records: global -> my warp's slots, asynchronous copies (LDGSTS, no registers)
-#pragma unroll
-            for (uint32_t i = 0; i < kQ; ++i) {
-                const uint32_t q = lane + 32u * i, r = q / kQ;
-                if (r < n) {
-                    const uint4* src = reinterpret_cast<const uint4*>(&recs_g[pend[r]]) + (q - kQ * r);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
-                }
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();
-            raster_chunk<FS, NEED_DST>(p, sh, warp, lane, n, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
-            const bool mv = lane + 32u < pend_n;
-            const uint32_t v = mv ? pend[32u + lane] : 0u;
-            __syncwarp();
-            if (mv) pend[lane] = v;
-            pend_n -= n;
-            __syncwarp();
-        }
-    }
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(p.work_counter + 2, 1u);  // slot 2: zeroed by setup_kernel<true> (slots 0, 1 belong to the direct kernel)
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const uint32_t tile = unit / kTileBricks, brick = unit % kTileBricks;
+        const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+        const int tile_px0 = (int)(p.tile_x0 + tile_x) * kTileW, tile_py0 = (int)(p.tile_y0 + tile_y) * kTileH;
+        const int brick_px0 = tile_px0 + (int)(brick & 3u) * kBrick, brick_py0 = tile_py0 + (int)(brick >> 2) * kBrick;
+        if (!(brick_px0 <= p.cx1 && brick_px0 + kBrick - 1 >= p.cx0 && brick_py0 <= p.cy1 && brick_py0 + kBrick - 1 >= p.cy0)) continue;
+        // triangle source: the tile's sorted id list, or — a tile whose list did not fit — every triangle of the draw
+        const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
+        if (end == beg) continue;
+        const bool direct = end - beg > (uint32_t)kSortCap || end > p.bin_capacity;
+        const uint32_t n_source = direct ? p.total_tris : end - beg;
 
-    // ---- brick epilogue: each lane writes back its 8 pixels where they changed ----
-    __syncwarp();
-    if (quad_clip) {
-        const uint2 cdb = *reinterpret_cast<const uint2*>(&sh.tile.color_dirty[warp][qat]);
-        const uint2 ddb = *reinterpret_cast<const uint2*>(&sh.tile.depth_dirty[warp][qat]);
-        const uint32_t cd = (bytes_to_bits(cdb.x) | bytes_to_bits(cdb.y) << 4) & quad_clip;
-        const uint32_t dd = (bytes_to_bits(ddb.x) | bytes_to_bits(ddb.y) << 4) & quad_clip;
+        // ---- brick prologue: lane l moves the 8 pixels 8 (l & 1) .. + 7 of row l >> 1, two 16-byte vectors when the row
+        // pitch allows it: destination values the result depends on, dirty flags ----
+        const int qx0 = brick_px0 + (int)(lane & 1u) * kBrickPx, qy = brick_py0 + (int)(lane >> 1);
+        const uint32_t qat = lane * kBrickPx;
+        const bool vec_ok = (p.fb_w & 3u) == 0 && qx0 + kBrickPx <= (int)p.fb_w;
+        const bool cvec = vec_ok && (p.color_base & 15ull) == 0, dvec = vec_ok && (p.depth_base & 15ull) == 0;
+        uint32_t quad_clip = 0;
 #pragma unroll
-        for (int h = 0; h < kBrickPx / 4; ++h) {
-            const uint32_t c4 = cd >> (4 * h) & 15u, d4 = dd >> (4 * h) & 15u;
-            if (c4 == 15u && cvec) {
-                *reinterpret_cast<uint4*>(caddr + 16 * h) = *reinterpret_cast<const uint4*>(&sh.tile.color[warp][qat + 4 * h]);
-            } else if (c4) {
+        for (int k = 0; k < kBrickPx; ++k)
+            if (qy >= p.cy0 && qy <= p.cy1 && qx0 + k >= p.cx0 && qx0 + k <= p.cx1) quad_clip |= 1u << k;
+        unsigned long long caddr = 0, daddr = 0;
+        if (quad_clip) {
+            if (has_color) caddr = color_addr(p, qx0, qy);
+            if (has_depth) daddr = p.depth_base + ((unsigned long long)qy * p.fb_w + qx0) * 4ull;
+        }
+        if (NEED_DST && quad_clip && has_color) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = sh.tile.color[warp][qat + 4 * h + k];
-            }
-            if (d4 == 15u && dvec) {
-                *reinterpret_cast<float4*>(daddr + 16 * h) = *reinterpret_cast<const float4*>(&sh.tile.depth[warp][qat + 4 * h]);
-            } else if (d4) {
+            for (int h = 0; h < kBrickPx / 4; ++h) {
+                const uint32_t m4 = quad_clip >> (4 * h) & 15u;
+                if (m4 == 15u && cvec) {
+                    *reinterpret_cast<uint4*>(&bs.color[qat + 4 * h]) = *reinterpret_cast<const uint4*>(caddr + 16 * h);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (d4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = sh.tile.depth[warp][qat + 4 * h + k];
+                    for (int k = 0; k < 4; ++k)
+                        if (m4 >> k & 1u) bs.color[qat + 4 * h + k] = *reinterpret_cast<const uint32_t*>(caddr + 16 * h + 4 * k);
+                }
             }
         }
+        if (depth_test && quad_clip) {
+#pragma unroll
+            for (int h = 0; h < kBrickPx / 4; ++h) {
+                const uint32_t m4 = quad_clip >> (4 * h) & 15u;
+                if (m4 == 15u && dvec) {
+                    *reinterpret_cast<float4*>(&bs.depth[qat + 4 * h]) = *reinterpret_cast<const float4*>(daddr + 16 * h);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (m4 >> k & 1u) bs.depth[qat + 4 * h + k] = *reinterpret_cast<const float*>(daddr + 16 * h + 4 * k);
+                }
+            }
+        }
+        *reinterpret_cast<uint2*>(&bs.color_dirty[qat]) = make_uint2(0u, 0u);  // my 8 pixels' flags
+        *reinterpret_cast<uint2*>(&bs.depth_dirty[qat]) = make_uint2(0u, 0u);
+        __syncwarp();
+
+        // ---- the triangle list: lanes test 4 x 32 list entries per step (one byte each; without a sorted list the packed
+        // pixel boxes themselves); the ids that meet my brick collect in a pending list, in list order, and are rasterised
+        // 32 at a time, so chunks are full whatever the density.  A chunk's 32 compact records are copied to the warp's
+        // slots in shared memory first (one L2 round trip per chunk, 6 x 16 bytes per lane).
+        {
+            uint32_t* pend = bs.pend;
+            uint32_t pend_n = 0;
+            const uint32_t* ids = p.bin_entries + beg;
+            const uint8_t* masks = tile_masks(p, tile, beg);
+            const uint32_t n_steps = (n_source + 127u) / 128u;
+            uint32_t step = 0;
+            for (;;) {
+                while (pend_n < 32u && step < n_steps) {
+                    const uint32_t i0 = step * 128u + lane * 4u;  // my four entries: i0 .. i0 + 3
+                    uint32_t hits = 0;
+                    if (!direct) {
+                        uint32_t m4 = 0;
+                        if (i0 + 3u < n_source) {
+                            m4 = *reinterpret_cast<const uint32_t*>(masks + i0);
+                        } else {
+#pragma unroll
+                            for (uint32_t k = 0; k < 4u; ++k)
+                                if (i0 + k < n_source) m4 |= (uint32_t)masks[i0 + k] << (8u * k);
+                        }
+                        m4 >>= brick;
+                        hits = (m4 & 1u) | (m4 >> 7 & 2u) | (m4 >> 14 & 4u) | (m4 >> 21 & 8u);
+                    } else {
+#pragma unroll
+                        for (uint32_t k = 0; k < 4u; ++k)
+                            if (i0 + k < n_source && (brick_mask_of(__ldg(&p.boxes[i0 + k]), tile_px0, tile_py0) >> brick & 1u)) hits |= 1u << k;
+                    }
+                    // ordered append: entry (lane, k) goes after all hits of lower lanes and my own lower k
+                    uint32_t incl = __popc(hits);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((int)lane >= d) incl += y;
+                    }
+                    uint32_t at = pend_n + incl - __popc(hits);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4u; ++k)
+                        if (hits >> k & 1u) pend[at++] = direct ? i0 + k : ids[i0 + k];
+                    pend_n += __shfl_sync(0xffffffffu, incl, 31);
+                    ++step;
+                }
+                if (pend_n == 0) break;
+                const uint32_t n = min(pend_n, 32u);
+                __syncwarp();
+                // the chunk's records: global -> my warp's slots, asynchronous copies (LDGSTS, no registers)
+#pragma unroll
+                for (uint32_t i = 0; i < kQ; ++i) {
+                    const uint32_t q = lane + 32u * i, r = q / kQ;
+                    if (r < n) {
+                        const uint4* src = reinterpret_cast<const uint4*>(&recs_g[pend[r]]) + (q - kQ * r);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(recs_s + q * 16u), "l"(src) : "memory");
+                    }
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                raster_chunk<FS, NEED_DST>(p, bs, lut, lane, n, brick_px0, brick_py0, depth_test, depth_write, has_color, n_covered, n_passed);
+                // move the remainder (< 128 + 32 entries) to the front
+                const uint32_t rest = pend_n - n;
+                uint32_t v[5];
+#pragma unroll
+                for (uint32_t k = 0; k < 5u; ++k) v[k] = lane + 32u * k < rest ? pend[n + lane + 32u * k] : 0u;
+                __syncwarp();
+#pragma unroll
+                for (uint32_t k = 0; k < 5u; ++k)
+                    if (lane + 32u * k < rest) pend[lane + 32u * k] = v[k];
+                pend_n = rest;
+                __syncwarp();
+            }
+        }
+
+        // ---- brick epilogue: each lane writes back its 8 pixels where they changed ----
+        __syncwarp();
+        if (quad_clip) {
+            const uint2 cdb = *reinterpret_cast<const uint2*>(&bs.color_dirty[qat]);
+            const uint2 ddb = *reinterpret_cast<const uint2*>(&bs.depth_dirty[qat]);
+            const uint32_t cd = (bytes_to_bits(cdb.x) | bytes_to_bits(cdb.y) << 4) & quad_clip;
+            const uint32_t dd = (bytes_to_bits(ddb.x) | bytes_to_bits(ddb.y) << 4) & quad_clip;
+#pragma unroll
+            for (int h = 0; h < kBrickPx / 4; ++h) {
+                const uint32_t c4 = cd >> (4 * h) & 15u, d4 = dd >> (4 * h) & 15u;
+                if (c4 == 15u && cvec) {
+                    *reinterpret_cast<uint4*>(caddr + 16 * h) = *reinterpret_cast<const uint4*>(&bs.color[qat + 4 * h]);
+                } else if (c4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c4 >> k & 1u) *reinterpret_cast<uint32_t*>(caddr + 16 * h + 4 * k) = bs.color[qat + 4 * h + k];
+                }
+                if (d4 == 15u && dvec) {
+                    *reinterpret_cast<float4*>(daddr + 16 * h) = *reinterpret_cast<const float4*>(&bs.depth[qat + 4 * h]);
+                } else if (d4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (d4 >> k & 1u) *reinterpret_cast<float*>(daddr + 16 * h + 4 * k) = bs.depth[qat + 4 * h + k];
+                }
+            }
+        }
+        __syncwarp();
     }
     if (p.stats) {
         // warp-reduce then one atomic per warp
@@ -1608,7 +1776,6 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
         if (lane == 0) {
             if (n_covered) atomicAdd(&p.stats[4], (unsigned long long)n_covered);
             if (n_passed) atomicAdd(&p.stats[5], (unsigned long long)n_passed);
-            if (warp == 0) atomicAdd(&p.stats[6], 1ull);
         }
     }
 }
@@ -1626,6 +1793,10 @@ struct KznRasterScratch {
     size_t tile_capacity = 0;
     uint32_t* bin_entries = nullptr;
     size_t bin_capacity = 0;
+    uint8_t* bin_masks = nullptr;
+    size_t mask_capacity = 0;
+    uint32_t* bin_entries_alt = nullptr;
+    size_t alt_capacity = 0;
     uint32_t* counters = nullptr;  // [4]: work counter of the direct kernel
     size_t counter_capacity = 0;
     bool attrs_set = false;
@@ -1637,6 +1808,8 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->boxes);
     cudaFree(s->tile_words);
     cudaFree(s->bin_entries);
+    cudaFree(s->bin_masks);
+    cudaFree(s->bin_entries_alt);
     cudaFree(s->counters);
     delete s;
 }
@@ -1749,7 +1922,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
     if ((r = grow(q, &s->boxes, &s->box_capacity, total))) return r;
     if (!s->counters) {  // [0] block dispenser of the direct kernel, [1] warps that have left it (fused setup): start at zero
         if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
-        KZN_CUDA(cudaMemset(s->counters, 0, s->counter_capacity * sizeof(uint32_t)));
+        KZN_CUDA(cudaMemsetAsync(s->counters, 0, s->counter_capacity * sizeof(uint32_t), q->stream));  // ordered before the first draw kernel of this queue
     }
     if (binned) {
         if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
@@ -1758,6 +1931,8 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
         size_t want = total * 8 + tiles;
         if (want > 0xfffffff0ull) want = 0xfffffff0ull;
         if ((r = grow(q, &s->bin_entries, &s->bin_capacity, want))) return r;
+        if ((r = grow(q, &s->bin_masks, &s->mask_capacity, s->bin_capacity + 4 * tiles + 8))) return r;
+        if ((r = grow(q, &s->bin_entries_alt, &s->alt_capacity, s->bin_capacity))) return r;
     }
     if (!s->attrs_set) {
         const int bytes = (int)sizeof(RasterShared);
@@ -1767,6 +1942,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
         KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         KZN_CUDA(cudaFuncSetAttribute(raster_kernel<KZN_FS_PROCEDURAL_ORBIT, kDstAlphaOver>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        KZN_CUDA(cudaFuncSetAttribute(tile_sort_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortShared)));
         s->attrs_set = true;
     }
     return KZN_SUCCESS;
@@ -1865,6 +2041,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         p.tile_cursor = s->tile_words + tiles;
         p.tile_offsets = s->tile_words + 2 * tiles;
         p.bin_entries = s->bin_entries;
+        p.bin_masks = s->bin_masks;
+        p.bin_entries_alt = s->bin_entries_alt;
         p.bin_capacity = (uint32_t)(s->bin_capacity > 0xfffffff0ull ? 0xfffffff0ull : s->bin_capacity);
     }
 
@@ -1880,6 +2058,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
         launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
+        // few tiles with long lists: a CTA per tile; many tiles with short lists: a warp per tile (see the kernels)
+        if (total / tiles >= 512) launch_draw_kernel(tile_sort_cta_kernel, dim3(p.tiles_x, p.tiles_y), dim3(kSortThreads), sizeof(SortShared), q->stream, p);
+        else launch_draw_kernel(tile_sort_warp_kernel, dim3((uint32_t)((tiles + kSortWarps - 1) / kSortWarps)), dim3(kSortThreads), 0, q->stream, p);
+        if ((r = kzn_launched(q, "tile_sort_kernel"))) return r;
     }
     dim3 grid(p.tiles_x, p.tiles_y);
     // the destination colour is only read when the result depends on it
@@ -1913,6 +2095,12 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         grid = dim3((uint32_t)(blocks < resident ? blocks : resident));
         KZN_RASTER_LAUNCH(raster_direct_kernel, 32, 0);
         return kzn_launched(q, "raster_direct_kernel");
+    }
+    {   // persistent warps over a brick counter: as many CTAs as fit on the device, or fewer when the frame is small
+        const uint64_t units = (uint64_t)tiles * kTileBricks, resident = (uint64_t)q->device->sm_count * KZN_RASTER_CTAS;
+        KZN_REQUIRE(units <= 0xffffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer too large");
+        const uint64_t ctas = (units + kRasterWarps - 1) / kRasterWarps;
+        grid = dim3((uint32_t)(ctas < resident ? ctas : resident));
     }
     KZN_RASTER_LAUNCH(raster_kernel, kRasterThreads, smem);
 #undef KZN_RASTER_LAUNCH
