@@ -301,7 +301,8 @@ def mesh_state(abi):
     return st
 
 
-def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1080), seed=4, check_oracle=True):
+def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1080), seed=4, check_oracle=True, hbm_peak=None,
+               traffic_key="mesh_1M_1080p"):
     """BASELINE configs[3]: 1M-triangle indexed mesh, D32 LESS + alpha blend, 1920x1080.  One frame = clear colour +
     clear depth + vkCmdDrawIndexed."""
     W, H = size
@@ -336,6 +337,15 @@ def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1
            "Gpix_shaded_per_s": int(s[5]) / ms / 1e6, "fragments_covered": int(s[4]), "fragments_depth_passed": int(s[5]),
            "triangles_culled": int(s[1]), "bin_entries": int(s[3]), "bin_overflow_tiles": int(s[7]),
            "depth_complexity": int(s[4]) / (W * H)}
+    # algorithmic bytes of the frame = indices + vertices + per shaded fragment (4 R + 4 W colour, 4 R + 4 W
+    # depth) + per depth-failed fragment 4 R; against the measured HBM peak.  The draw is issue-bound, not bandwidth-bound:
+    # the fraction says how far the frame is from the bandwidth floor, `traffic` (ncu, all kernels of the draw) how much of
+    # the DRAM traffic is not algorithmic (triangle records, bins).
+    alg = idx.nbytes + verts.nbytes + int(s[5]) * 16 + (int(s[4]) - int(s[5])) * 4
+    if hbm_peak:
+        out["roofline"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": alg / ms / 1e6 / hbm_peak, "traffic": roofline_traffic(traffic_key),
+                           "note": "frame time includes the two clears; setup + binning + sort + raster kernels"}
     if check_oracle:
         from oracle import binding as ob
         lib = ob.load()
@@ -470,7 +480,7 @@ class FrameTargets:
             self.tensors = []
 
 
-def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, mode):
+def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, mode, hbm_peak=None):
     """BASELINE configs[4]: 7680x4320 frame of a 4M-triangle mesh (D32 LESS + alpha blend), sort-first split into `world`
     bands, composited to rank 0.  Strong scaling: the frame is fixed, every rank sees all geometry and culls to its band."""
     from kazan_b200.split_frame import SplitFrame
@@ -536,6 +546,14 @@ def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, b
         same = code == 0 and bool(np.array_equal(h.numpy().view(np.uint8), ocolor[:W * H * 4]))
         out["parity"] = (f"bit-exact colour vs oracle at full size ({world} band(s) composited)" if same else "MISMATCH vs oracle")
         out["cpu_baseline"] = {"ms_per_frame": dt * 1e3, "cores": int(lib.kzo_hardware_threads()), "kind": "port"}
+        # SURVEY.md §8(d) bytes of the whole frame (fragment counts from the oracle's run of the same scene) against the HBM
+        # peak of the GPUs that render it; geometry is replicated on every band rank, so with N bands the indices and
+        # vertices are read N times (counted once here: algorithmic)
+        alg = idx.nbytes + verts.nbytes + int(ostats.fragments_depth_passed) * 16 + int(ostats.fragments_covered - ostats.fragments_depth_passed) * 4
+        if hbm_peak:
+            out["roofline"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / ms / 1e6, "peak": hbm_peak * world, "unit": "GB/s",
+                               "frac": alg / ms / 1e6 / (hbm_peak * world), "traffic": roofline_traffic("split_frame_8k") if world == 1 else None,
+                               "note": "issue-bound draw: the fraction is the distance from the bandwidth floor"}
     ft.close()
     return out
 
@@ -813,13 +831,13 @@ def run_ours(args):
             line["extra"] = {"transfer": transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak),
                              "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src,
                              "dispatch_2p24": dispatch_extra(torch, queue, stream),
-                             "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream)}
+                             "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream, hbm_peak=hbm_peak)}
     if not args.profile:
         with torch.cuda.stream(stream):
             ft.close()
             del fbs
             torch.cuda.empty_cache()
-            sfx = split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, args.composite)
+            sfx = split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, barrier, args.composite, hbm_peak)
         if rank == 0:
             line.setdefault("extra", {})["split_frame_8k_4Mtri"] = sfx
     if rank == 0:

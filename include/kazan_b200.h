@@ -356,6 +356,13 @@ KZN_API KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* sr
 #define KZN_FS_VERTEX_COLOR 0u     /* out = perspective-correct interpolated vertex rgba */
 #define KZN_FS_PROCEDURAL_ORBIT 1u /* the fill-rate shader of BASELINE.json configs[2] (fp32 fma orbit, K=32) */
 #define KZN_FS_ORBIT_ITERATIONS 32u
+/* The fragment program bound with kzn_cmd_bind_fragment_program (kazan_b200_backend.h): a shader-compiler-ir module compiled
+ * by the PTX back end into the raster kernels, which is how a GraphicsPipeline's fragment stage runs once the pipeline
+ * exists (GraphicsPipeline::create, pipeline.rs:167-183); the two built-in programs above remain as the oracle-defined
+ * fixed programs.  Its push constants and descriptor set are the GRAPHICS bind point's (kzn_cmd_push_constants,
+ * kzn_cmd_bind_descriptor_set). */
+#define KZN_FS_COMPILED 2u
+#define KZN_MAX_PUSH_CONSTANTS_SIZE 128u /* maxPushConstantsSize */
 
 typedef struct KznGraphicsPipelineState {
     uint32_t vertex_program;   /* KZN_VS_* */

@@ -15,7 +15,8 @@
  *
  * Invocation ABI of a compiled entry point (defined by this back end; the reference never got that far):
  *   one invocation == one thread, 256 invocations per CTA whatever the SPIR-V LocalSize;
- *   kernel parameters (user_inputs_base, user_outputs_base, invocation_count, first_invocation);
+ *   kernel parameters (user_inputs_base, user_outputs_base, invocation_count, first_invocation, global_size_x,
+ *   global_size_y, descriptor_table, global_base[16], push_constants[128]);
  *   invocation g (0 <= g < invocation_count) sees  user_inputs_block  = user_inputs_base  + (first+g) * inputs.size
  *                                                  user_outputs_block = user_outputs_base + (first+g) * outputs.size;
  *   the values the entry point returns (`break <body>[v...]`) are stored to user_outputs_block at the offsets of the
@@ -33,6 +34,23 @@ extern "C" {
 /* ---- shader-compiler-ir text (text.rs:1392 FromText, :1987 ToText) ------------------------------------------------ */
 typedef struct KznIrModule KznIrModule;
 KZN_API KznResult kzn_ir_parse(const char* text, size_t length, KznIrModule** module);
+/* Version 1 is the reference's instruction set to the letter (instructions_impl.rs:395-433: add, load, break, branch,
+ * continue, block, loop).  Version 2 adds, in the C++ mirror only, what a shader with a body needs:
+ * instructions spelled like the SPIR-V instruction they translate, in the reference's `name [args] -> [results]` syntax —
+ *   i_sub i_mul bitwise_and bitwise_or bitwise_xor shift_left_logical shift_right_logical shift_right_arithmetic s_negate not
+ *   f_add f_sub f_mul f_div f_min f_max f_negate f_abs fma
+ *   i_equal i_not_equal u_less_than s_less_than u_less_than_equal s_less_than_equal u_greater_than s_greater_than
+ *   u_greater_than_equal s_greater_than_equal f_ord_equal f_ord_less_than f_ord_less_than_equal f_ord_greater_than
+ *   f_ord_greater_than_equal f_unord_not_equal logical_and logical_or logical_not select
+ *   convert_f_to_u convert_f_to_s convert_s_to_f convert_u_to_f u_convert s_convert f_convert bitcast
+ *   store [pointer, value], align: A -> []      ptr_add [pointer, offset: i64] -> [q: data_ptr]
+ *   group_non_uniform_elect / _all / _any / _ballot / _broadcast_first / _shuffle / _shuffle_xor / _i_add
+ *     (subgroup = 32 consecutive invocations = one warp: vote.sync / shfl.sync / redux.sync; subgroup-uniform control flow)
+ * and the built-in kinds global_invocation_id <3 x i32>, subgroup_local_invocation_id i32, subgroup_size i32,
+ * frag_coord <4 x f32>, push_constants data_ptr, descriptor_table data_ptr.  Semantics: csrc/ir.h; checker: oracle/ir_simt.py. */
+#define KZN_IR_VERSION_1 1u
+#define KZN_IR_VERSION_2 2u
+KZN_API KznResult kzn_ir_parse_ex(const char* text, size_t length, uint32_t version, KznIrModule** module);
 KZN_API void kzn_ir_module_destroy(KznIrModule* module);
 /* canonical text; *text is malloc()ed, release with kzn_free */
 KZN_API KznResult kzn_ir_to_text(const KznIrModule* module, char** text, size_t* length);
@@ -75,6 +93,54 @@ KZN_API KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const
                                    uint64_t user_outputs_address, uint64_t first_invocation);
 KZN_API uint64_t kzn_pipeline_inputs_size(const KznPipeline* pipeline);  /* bytes per invocation */
 KZN_API uint64_t kzn_pipeline_outputs_size(const KznPipeline* pipeline);
+
+/* ---- descriptor sets and push constants -------------------------------------------------------------- */
+/* vulkan-driver/src/descriptor_set.rs: DescriptorLayout :12-49, Descriptor :230-267, Descriptor::write :460-527;
+ * vkAllocateDescriptorSets api_impl.rs:4218, vkUpdateDescriptorSets :4339, vkCmdBindDescriptorSets :4597,
+ * vkCmdPushConstants :4932 (the two commands are unimplemented!() upstream); PipelineLayout shader-compiler/src/lib.rs:706-730.
+ * Kernel-argument ABI: a bound set reaches the shader as ONE pointer (built-in kind `descriptor_table`) to a table of
+ * 16-byte slots {uint64 address, uint64 range}, one per descriptor, bindings in layout order, array elements consecutive
+ * (kzn_descriptor_set_slot gives a binding's first slot); the push constant block (128 bytes, maxPushConstantsSize) travels
+ * in the launch's parameter space and reaches the shader through the built-in kind `push_constants`. */
+#define KZN_DESCRIPTOR_TYPE_UNIFORM_BUFFER 6u /* VkDescriptorType */
+#define KZN_DESCRIPTOR_TYPE_STORAGE_BUFFER 7u
+#define KZN_PIPELINE_BIND_POINT_GRAPHICS 0u /* VkPipelineBindPoint */
+#define KZN_PIPELINE_BIND_POINT_COMPUTE 1u
+typedef struct KznDescriptorSet KznDescriptorSet; /* descriptor_set.rs `DescriptorSet` + its layout */
+typedef struct KznDescriptorSetLayoutBinding {   /* VkDescriptorSetLayoutBinding without samplers and stage flags */
+    uint32_t binding, descriptor_type, descriptor_count;
+} KznDescriptorSetLayoutBinding;
+typedef struct KznDescriptorBufferInfo { /* VkDescriptorBufferInfo with the buffer's device address for the handle */
+    uint64_t address, offset, range;
+} KznDescriptorBufferInfo;
+KZN_API KznResult kzn_descriptor_set_create(KznDevice* device, uint32_t binding_count, const KznDescriptorSetLayoutBinding* bindings,
+                                            KznDescriptorSet** set);
+KZN_API void kzn_descriptor_set_destroy(KznDescriptorSet* set);
+/* vkUpdateDescriptorSets with pBufferInfo: elements first_element .. first_element + count - 1 of `binding` */
+KZN_API KznResult kzn_descriptor_set_write_buffers(KznDescriptorSet* set, uint32_t binding, uint32_t first_element, uint32_t count,
+                                                   const KznDescriptorBufferInfo* buffers);
+KZN_API uint64_t kzn_descriptor_set_table_address(const KznDescriptorSet* set);
+KZN_API int64_t kzn_descriptor_set_slot(const KznDescriptorSet* set, uint32_t binding); /* -1: not in the layout */
+/* state of the queue's command stream, consumed by the next kzn_cmd_dispatch (COMPUTE) / kzn_cmd_draw* (GRAPHICS) */
+KZN_API KznResult kzn_cmd_bind_descriptor_set(KznQueue* queue, uint32_t pipeline_bind_point, const KznDescriptorSet* set);
+KZN_API KznResult kzn_cmd_push_constants(KznQueue* queue, uint32_t offset, uint32_t size, const void* values);
+
+/* ---- fragment programs: the fragment stage of a graphics pipeline ------------------------------------------------------------ */
+/* vkCreateGraphicsPipelines api_impl.rs:4018-4032 -> GraphicsPipeline::create pipeline.rs:167-183 (unimplemented!() upstream),
+ * vkCmdBindPipeline :4506.  The module is a fragment shader in shader-compiler-ir: user_inputs_block = up to four f32
+ * interpolated inputs (the passthrough vertex stage's colour, perspective correct), user_outputs_block = four f32 (the
+ * colour of attachment 0), built-in inputs frag_coord / push_constants / descriptor_table.  Creation generates the shader's
+ * PTX and builds it INTO the raster kernels (their PTX is part of this library; every call of the fragment program is
+ * replaced by the shader's code), so a compiled program costs what a built-in one costs.  A draw whose state says
+ * fragment_program == KZN_FS_COMPILED runs the program bound to the queue. */
+typedef struct KznFragmentProgram KznFragmentProgram;
+KZN_API KznResult kzn_fragment_program_create(KznDevice* device, const KznIrModule* module, KznFragmentProgram** program);
+KZN_API void kzn_fragment_program_destroy(KznFragmentProgram* program);
+KZN_API KznResult kzn_cmd_bind_fragment_program(KznQueue* queue, KznFragmentProgram* program);
+/* the PTX of the fragment shader alone as it is placed at one call site (malloc()ed; needs no GPU) */
+KZN_API KznResult kzn_fragment_program_ptx(const KznIrModule* module, char** ptx, size_t* length);
+/* ... and of the whole module kzn_fragment_program_create loads: the raster kernels with the shader at every call site */
+KZN_API KznResult kzn_fragment_program_module_ptx(const KznIrModule* module, char** ptx, size_t* length);
 
 /* ---- the backend trait surface (shader-compiler-backend/src/lib.rs) ------------------------------------------------------ */
 typedef struct KznBackendContext KznBackendContext;   /* trait Context  lib.rs:162-189 */

@@ -59,6 +59,7 @@ MEMORY_TYPE_DEVICE_LOCAL = 1
 VS_PASSTHROUGH = 0
 FS_VERTEX_COLOR = 0
 FS_PROCEDURAL_ORBIT = 1
+FS_COMPILED = 2
 # VkCompareOp
 COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_OR_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, \
     COMPARE_GREATER_OR_EQUAL, COMPARE_ALWAYS = range(8)
@@ -252,10 +253,37 @@ class Callable(C.Structure):  # kazan_b200_backend.h KznCallable
 
 sz = C.c_size_t
 cp = C.c_char_p
+i64 = C.c_int64
+
+
+class DescriptorSetLayoutBinding(C.Structure):  # kazan_b200_backend.h KznDescriptorSetLayoutBinding
+    _fields_ = [("binding", u32), ("descriptor_type", u32), ("descriptor_count", u32)]
+
+
+class DescriptorBufferInfo(C.Structure):  # kazan_b200_backend.h KznDescriptorBufferInfo
+    _fields_ = [("address", u64), ("offset", u64), ("range", u64)]
+
+
+DESCRIPTOR_TYPE_UNIFORM_BUFFER, DESCRIPTOR_TYPE_STORAGE_BUFFER = 6, 7
+PIPELINE_BIND_POINT_GRAPHICS, PIPELINE_BIND_POINT_COMPUTE = 0, 1
+IR_VERSION_1, IR_VERSION_2 = 1, 2
 # include/kazan_b200_backend.h
 BACKEND_PROTOTYPES = {
     "kzn_ir_parse": (i32, [cp, sz, P(vp)]),
+    "kzn_ir_parse_ex": (i32, [cp, sz, u32, P(vp)]),
     "kzn_ir_module_destroy": (None, [vp]),
+    "kzn_descriptor_set_create": (i32, [vp, u32, P(DescriptorSetLayoutBinding), P(vp)]),
+    "kzn_descriptor_set_destroy": (None, [vp]),
+    "kzn_descriptor_set_write_buffers": (i32, [vp, u32, u32, u32, P(DescriptorBufferInfo)]),
+    "kzn_descriptor_set_table_address": (u64, [vp]),
+    "kzn_descriptor_set_slot": (i64, [vp, u32]),
+    "kzn_cmd_bind_descriptor_set": (i32, [vp, u32, vp]),
+    "kzn_cmd_push_constants": (i32, [vp, u32, u32, vp]),
+    "kzn_fragment_program_create": (i32, [vp, vp, P(vp)]),
+    "kzn_fragment_program_destroy": (None, [vp]),
+    "kzn_cmd_bind_fragment_program": (i32, [vp, vp]),
+    "kzn_fragment_program_ptx": (i32, [vp, P(vp), P(sz)]),
+    "kzn_fragment_program_module_ptx": (i32, [vp, P(vp), P(sz)]),
     "kzn_ir_to_text": (i32, [vp, P(vp), P(sz)]),
     "kzn_ir_round_trip": (i32, [cp, cp, sz, P(vp), P(sz)]),
     "kzn_free": (None, [vp]),

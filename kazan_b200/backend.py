@@ -41,10 +41,14 @@ class IrModule:
         self.handle, self._lib = handle, load_library()
 
     @classmethod
-    def parse(cls, text: str) -> "IrModule":
+    def parse(cls, text: str, version: int = 1) -> "IrModule":
+        """version 1: the reference's seven instructions; version 2: the C++ mirror's additions (kazan_b200_backend.h)."""
         h = C.c_void_p()
         b = text.encode()
-        _check(load_library().kzn_ir_parse(b, len(b), C.byref(h)))
+        if version == 1:
+            _check(load_library().kzn_ir_parse(b, len(b), C.byref(h)))
+        else:
+            _check(load_library().kzn_ir_parse_ex(b, len(b), version, C.byref(h)))
         return cls(h)
 
     def to_text(self) -> str:
@@ -111,6 +115,83 @@ def cmd_dispatch(queue: Queue, pipeline: ComputePipeline, group_count, user_inpu
 
 
 Queue.cmd_dispatch = cmd_dispatch  # same spelling as the other vkCmd* mirrors
+
+
+class DescriptorSet:
+    """vulkan-driver/src/descriptor_set.rs DescriptorSet + its layout: bindings = [(binding, descriptor_type, count), ...]."""
+
+    def __init__(self, device: Device, bindings):
+        self._lib = load_library()
+        arr = (abi.DescriptorSetLayoutBinding * max(len(bindings), 1))(*[abi.DescriptorSetLayoutBinding(*b) for b in bindings])
+        h = C.c_void_p()
+        _check(self._lib.kzn_descriptor_set_create(device.handle, len(bindings), arr, C.byref(h)))
+        self.handle = h
+
+    def write_buffers(self, binding: int, buffers, first_element: int = 0):
+        """vkUpdateDescriptorSets with pBufferInfo; buffers = [(address, offset, range), ...]"""
+        arr = (abi.DescriptorBufferInfo * max(len(buffers), 1))(*[abi.DescriptorBufferInfo(*b) for b in buffers])
+        _check(self._lib.kzn_descriptor_set_write_buffers(self.handle, binding, first_element, len(buffers), arr))
+
+    @property
+    def table_address(self) -> int:
+        return self._lib.kzn_descriptor_set_table_address(self.handle)
+
+    def slot(self, binding: int) -> int:
+        return self._lib.kzn_descriptor_set_slot(self.handle, binding)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_descriptor_set_destroy(self.handle)
+            self.handle = None
+
+
+def cmd_bind_descriptor_set(queue: Queue, bind_point: int, descriptor_set: "DescriptorSet | None"):
+    """vkCmdBindDescriptorSets (api_impl.rs:4597)"""
+    _check(load_library().kzn_cmd_bind_descriptor_set(queue.handle, bind_point, descriptor_set.handle if descriptor_set else None))
+
+
+def cmd_push_constants(queue: Queue, data: bytes, offset: int = 0):
+    """vkCmdPushConstants (api_impl.rs:4932)"""
+    buf = C.create_string_buffer(bytes(data), len(data))
+    _check(load_library().kzn_cmd_push_constants(queue.handle, offset, len(data), buf))
+
+
+class FragmentProgram:
+    """The fragment stage of a graphics pipeline (GraphicsPipeline::create, pipeline.rs:167-183): a shader-compiler-ir module
+    compiled into the raster kernels."""
+
+    def __init__(self, device: Device, module: IrModule):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.kzn_fragment_program_create(device.handle, module.handle, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def call_site_ptx(module: IrModule) -> str:
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(load_library().kzn_fragment_program_ptx(module.handle, C.byref(out), C.byref(n)))
+        return _take_text(out, n)
+
+    @staticmethod
+    def module_ptx(module: IrModule) -> str:
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(load_library().kzn_fragment_program_module_ptx(module.handle, C.byref(out), C.byref(n)))
+        return _take_text(out, n)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_fragment_program_destroy(self.handle)
+            self.handle = None
+
+
+def cmd_bind_fragment_program(queue: Queue, program: "FragmentProgram | None"):
+    """vkCmdBindPipeline (api_impl.rs:4506) for the fragment stage"""
+    _check(load_library().kzn_cmd_bind_fragment_program(queue.handle, program.handle if program else None))
+
+
+Queue.cmd_bind_fragment_program = cmd_bind_fragment_program
+Queue.cmd_bind_descriptor_set = cmd_bind_descriptor_set
+Queue.cmd_push_constants = cmd_push_constants
 
 
 # ---- the backend trait surface -------------------------------------------------------------------------------------------

@@ -42,6 +42,8 @@ struct DriverApi {
     CUresult_ (*cuModuleGetFunction)(CUfunction_*, CUmodule_, const char*) = nullptr;
     CUresult_ (*cuModuleUnload)(CUmodule_) = nullptr;
     CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+    CUresult_ (*cuLaunchKernelEx)(const void* config, CUfunction_, void**, void**) = nullptr;  // optional: programmatic dependent launch
+    CUresult_ (*cuFuncSetAttribute)(CUfunction_, int, int) = nullptr;
     CUresult_ (*cuGetErrorString)(CUresult_, const char**) = nullptr;
     std::string error;
 };
@@ -69,7 +71,9 @@ DriverApi* driver() {
         api.cuModuleGetFunction = (decltype(api.cuModuleGetFunction))sym("cuModuleGetFunction");
         api.cuModuleUnload = (decltype(api.cuModuleUnload))sym("cuModuleUnload");
         api.cuLaunchKernel = (decltype(api.cuLaunchKernel))sym("cuLaunchKernel");
+        api.cuFuncSetAttribute = (decltype(api.cuFuncSetAttribute))sym("cuFuncSetAttribute");
         api.cuGetErrorString = (decltype(api.cuGetErrorString))sym("cuGetErrorString");
+        api.cuLaunchKernelEx = (decltype(api.cuLaunchKernelEx))dlsym(api.handle, "cuLaunchKernelEx");
     });
     return &api;
 }
@@ -93,7 +97,8 @@ KznResult load_ptx(KznDevice* device, const std::string& ptx, CUmodule_* module)
     CUresult_ r = d->cuCtxGetCurrent(&ctx);
     if (r != 0) return driver_failed(r, "cuCtxGetCurrent");
     KZN_REQUIRE(ctx, KZN_ERROR_INITIALIZATION_FAILED, "no current CUDA context");
-    char info[4096] = "", err[4096] = "";
+    static char info[8192], err[8192];  // (one compile at a time: pipeline creation is externally synchronised)
+    info[0] = err[0] = 0;
     int opts[4] = {CU_JIT_INFO_LOG_BUFFER_, CU_JIT_INFO_LOG_BUFFER_SIZE_BYTES_, CU_JIT_ERROR_LOG_BUFFER_, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES_};
     void* vals[4] = {info, (void*)(uintptr_t)sizeof info, err, (void*)(uintptr_t)sizeof err};
     r = d->cuModuleLoadDataEx(module, ptx.c_str(), 4, opts, vals);
@@ -140,6 +145,15 @@ struct KznIrModule {
     std::unique_ptr<kir::Module> module;
 };
 
+// A fragment shader built into the raster kernels (include/kazan_b200_backend.h).
+struct KznFragmentProgram {
+    KznDevice* device = nullptr;
+    CUmodule_ module = nullptr;
+    CUfunction_ kernel[2][3] = {};  // [raster_direct, raster][destination mode]
+    uint32_t flags = 0;
+    int call_sites = 0;
+};
+
 struct KznPipeline {
     KznDevice* device = nullptr;
     CUmodule_ module = nullptr;
@@ -147,6 +161,19 @@ struct KznPipeline {
     uint32_t local_size[3] = {1, 1, 1};
     uint64_t inputs_size = 0, outputs_size = 0;
     std::string ptx;
+};
+
+// vulkan-driver/src/descriptor_set.rs:230-267 `Descriptor` for the two kinds a kernel can read through a pointer
+// (UniformBuffer / StorageBuffer hold BufferSlices, :460-527 `write`); the device-side form is a flat table of
+// {address, size} pairs in binding order that the shader indexes (include/kazan_b200_backend.h)
+struct KznDescriptorSet {
+    KznDevice* device = nullptr;
+    struct Binding {
+        uint32_t binding, type, count, first_slot;
+    };
+    std::vector<Binding> bindings;
+    std::vector<uint64_t> host;  // 2 words per slot
+    void* table = nullptr;       // device copy
 };
 
 // ---- backend trait objects ----------------------------------------------------------------------------------------------
@@ -358,15 +385,17 @@ extern "C" {
 
 // ---- IR text ------------------------------------------------------------------------------------------------------------
 
-KznResult kzn_ir_parse(const char* text, size_t length, KznIrModule** module) {
+KznResult kzn_ir_parse_ex(const char* text, size_t length, uint32_t version, KznIrModule** module) {
     KZN_VALID(text && module, "kzn_ir_parse: null argument");
     *module = nullptr;
+    KZN_VALID(version == KZN_IR_VERSION_1 || version == KZN_IR_VERSION_2, "kzn_ir_parse_ex: unknown IR version %u", version);
     return guarded([&] {
-        auto m = kir::parse_module(std::string(text, length));
+        auto m = kir::parse_module(std::string(text, length), (int)version);
         *module = new KznIrModule{std::move(m)};
         return KZN_SUCCESS;
     });
 }
+KznResult kzn_ir_parse(const char* text, size_t length, KznIrModule** module) { return kzn_ir_parse_ex(text, length, KZN_IR_VERSION_1, module); }
 
 void kzn_ir_module_destroy(KznIrModule* module) { delete module; }
 
@@ -497,10 +526,328 @@ KznResult kzn_cmd_dispatch(KznQueue* queue, KznPipeline* pipeline, const uint32_
         gy = (ctas + gx - 1) / gx;
         KZN_VALID(gy <= 65535, "dispatch too large for one launch");
     }
-    void* args[4] = {&user_inputs_address, &user_outputs_address, &count, &first_invocation};
+    // version 2 parameters: the global size (global_invocation_id is cut from the linear index, x fastest), the first
+    // workgroup of vkCmdDispatchBase, and what vkCmdBindDescriptorSets / vkCmdPushConstants left on the queue
+    uint64_t size_x = (uint64_t)group_count[0] * pipeline->local_size[0], size_y = (uint64_t)group_count[1] * pipeline->local_size[1];
+    struct alignas(16) { uint32_t v[4]; } base = {{0, 0, 0, 0}};
+    for (int i = 0; i < 3; ++i) base.v[i] = base_group ? base_group[i] * pipeline->local_size[i] : 0u;
+    uint64_t table = queue->descriptor_table[KZN_PIPELINE_BIND_POINT_COMPUTE];
+    void* args[9] = {&user_inputs_address, &user_outputs_address, &count, &first_invocation, &size_x, &size_y, &table, &base, queue->push_constants};
     CUresult_ cr = driver()->cuLaunchKernel(pipeline->function, (unsigned)gx, (unsigned)gy, 1, threads, 1, 1, 0, (void*)queue->stream, args, nullptr);
     if (cr != 0) return driver_failed(cr, "cuLaunchKernel");
     queue->launches++;
+    return KZN_SUCCESS;
+}
+
+// ---- fragment programs --------------------------------------------------------------------------------------------------------------
+
+namespace {
+
+// The raster kernels' PTX (raster.cu compiled with KZN_FS_TEMPLATE, a string constant of this library) calls the fragment
+// program as an external function.  nvcc writes every call as one delimited sequence
+//     { // callseq N, 0   .param ...; st.param.f32 [param0], %f2; ... call.uni (retval0), kzn_fs_main, (...);
+//       ld.param.v4.f32 {%f7, %f8, %f9, %f10}, [retval0];   } // callseq N
+// which is replaced, call by call, by the shader's own PTX reading the stored operands and writing the loaded registers
+// (kir::emit_fragment_inline): after that the fragment program is ordinary code of the kernel — registers allocated and
+// instructions scheduled across it, unused inputs and outputs eliminated with the code that made them.
+std::string build_fragment_module(const kir::Module& m, int* call_sites) {
+    const std::string text = kzn_raster_template_ptx;
+    std::string out;
+    out.reserve(text.size() + (1u << 20));
+    // the external declaration goes: no reference to it is left
+    size_t pos = 0;
+    {
+        const size_t d = text.find(".extern .func");
+        const size_t name = d == std::string::npos ? d : text.find("kzn_fs_main", d);
+        const size_t end = name == std::string::npos ? name : text.find(';', name);
+        if (d == std::string::npos || end == std::string::npos || text.find(".extern", d + 1) < name)
+            throw kir::Error("internal: the raster template does not declare kzn_fs_main the way this library expects");
+        out.append(text, 0, d);
+        pos = end + 1;
+    }
+    int sites = 0;
+    for (;;) {
+        const size_t b = text.find("{ // callseq ", pos);
+        if (b == std::string::npos) break;
+        // inside which definition?  A kernel entry keeps the push constants in its parameter space (DrawParams is its
+        // only parameter); a helper function of the template sees them through a pointer
+        std::string entry;
+        {
+            const size_t ent = text.rfind(".entry ", b), fn = text.rfind("\n.func", b);
+            if (ent != std::string::npos && (fn == std::string::npos || fn < ent)) {
+                const size_t n0 = ent + 7, n1 = text.find('(', n0);
+                entry = text.substr(n0, n1 - n0);
+            }
+        }
+        const size_t e0 = text.find("} // callseq ", b);
+        if (e0 == std::string::npos) throw kir::Error("internal: unterminated call sequence in the raster template");
+        const size_t e = text.find('\n', e0);
+        const std::string seq = text.substr(b, e0 - b);
+        if (seq.find("kzn_fs_main") == std::string::npos) {  // a call of another function of the template
+            out.append(text, pos, e - pos);
+            pos = e;
+            continue;
+        }
+        kir::FragmentSite site;
+        site.id = sites++;
+        site.in.assign(10, "0");
+        site.out.assign(4, "");
+        if (!entry.empty()) site.push_constants_param = entry + "_param_0+" + std::to_string(kzn_draw_params_push_constants_offset);
+        size_t at = 0;
+        while (at < seq.size()) {
+            size_t nl = seq.find('\n', at);
+            if (nl == std::string::npos) nl = seq.size();
+            std::string ln = seq.substr(at, nl - at);
+            at = nl + 1;
+            const size_t first = ln.find_first_not_of(" \t");
+            if (first == std::string::npos) continue;
+            ln = ln.substr(first);
+            if (ln.rfind("st.param", 0) == 0) {
+                const size_t pb = ln.find("[param"), pe = ln.find(']', pb), semi = ln.rfind(';');
+                if (pb == std::string::npos || pe == std::string::npos || semi == std::string::npos) throw kir::Error("internal: unexpected st.param in a fragment call");
+                const int k = atoi(ln.c_str() + pb + 6);
+                size_t v = ln.find(',', pe);
+                std::string operand = ln.substr(v + 1, semi - v - 1);
+                operand.erase(0, operand.find_first_not_of(" \t"));
+                if (k < 0 || k >= 10) throw kir::Error("internal: fragment call with more than 10 parameters");
+                site.in[k] = operand;
+            } else if (ln.rfind("ld.param", 0) == 0) {
+                const size_t rb = ln.find("[retval0");
+                if (rb == std::string::npos) throw kir::Error("internal: unexpected ld.param in a fragment call");
+                int component = 0;
+                if (ln[rb + 8] == '+') component = atoi(ln.c_str() + rb + 9) / 4;
+                const size_t comma = ln.rfind(',', rb);
+                std::string dst = ln.substr(ln.find_first_of(" \t"), comma - ln.find_first_of(" \t"));
+                std::string regs;
+                for (char ch : dst)
+                    if (ch != '{' && ch != '}' && ch != ' ' && ch != '\t') regs += ch;
+                size_t r0 = 0;
+                while (r0 <= regs.size() && component < 4) {
+                    size_t r1 = regs.find(',', r0);
+                    if (r1 == std::string::npos) r1 = regs.size();
+                    if (r1 > r0) site.out[component++] = regs.substr(r0, r1 - r0);
+                    r0 = r1 + 1;
+                }
+            }
+        }
+        out.append(text, pos, b - pos);
+        out += "// fragment program, call site " + std::to_string(site.id) + "\n";
+        out += kir::emit_fragment_inline(m, site, nullptr);
+        pos = e;
+    }
+    out.append(text, pos, std::string::npos);
+    if (sites == 0) throw kir::Error("internal: the raster template holds no call of the fragment program");
+    if (call_sites) *call_sites = sites;
+    return out;
+}
+
+struct LaunchAttribute_ {  // CUlaunchAttribute (cuda.h): id, 4 bytes of padding, 64-byte value
+    int id;
+    char pad[4];
+    union {
+        char bytes[64];
+        int programmatic_stream_serialization_allowed;
+    } value;
+};
+struct LaunchConfig_ {  // CUlaunchConfig
+    unsigned grid_x, grid_y, grid_z, block_x, block_y, block_z, shared_bytes;
+    void* stream;
+    LaunchAttribute_* attrs;
+    unsigned num_attrs;
+};
+
+}  // namespace
+
+KznResult kzn_fragment_program_ptx(const KznIrModule* module, char** ptx, size_t* length) {
+    KZN_VALID(module && ptx, "kzn_fragment_program_ptx: null argument");
+    *ptx = nullptr;
+    return guarded([&] {
+        kir::fragment_interface(*module->module);
+        kir::FragmentSite site;
+        site.id = 0;
+        site.in = {"%fx", "%fy", "%fz", "%fw", "%in0", "%in1", "%in2", "%in3", "%push_constants", "%descriptor_table"};
+        site.out = {"%out0", "%out1", "%out2", "%out3"};
+        *ptx = dup_text(kir::emit_fragment_inline(*module->module, site, nullptr), length);
+        KZN_REQUIRE(*ptx, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
+KznResult kzn_fragment_program_module_ptx(const KznIrModule* module, char** ptx, size_t* length) {
+    KZN_VALID(module && ptx, "kzn_fragment_program_module_ptx: null argument");
+    *ptx = nullptr;
+    return guarded([&] {
+        kir::fragment_interface(*module->module);
+        *ptx = dup_text(build_fragment_module(*module->module, nullptr), length);
+        KZN_REQUIRE(*ptx, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+        return KZN_SUCCESS;
+    });
+}
+
+KznResult kzn_fragment_program_create(KznDevice* device, const KznIrModule* module, KznFragmentProgram** program) {
+    KZN_VALID(device && module && program, "kzn_fragment_program_create: null argument");
+    *program = nullptr;
+    auto p = std::make_unique<KznFragmentProgram>();
+    p->device = device;
+    std::string ptx;
+    KznResult r = guarded([&] {
+        const kir::FragmentInterface fi = kir::fragment_interface(*module->module);
+        p->flags = (fi.reads_inputs || fi.reads_frag_coord_zw) ? 1u : 0u;
+        ptx = build_fragment_module(*module->module, &p->call_sites);
+        return KZN_SUCCESS;
+    });
+    if (r != KZN_SUCCESS) return r;
+    if (const char* dump = getenv("KZN_DUMP_FRAGMENT_PTX")) {
+        if (FILE* f = fopen(dump, "w")) {
+            fwrite(ptx.data(), 1, ptx.size(), f);
+            fclose(f);
+        }
+    }
+    r = load_ptx(device, ptx, &p->module);
+    if (r != KZN_SUCCESS) return r;
+    static const char* const names[2][3] = {{"kzn_fs_raster_direct_0", "kzn_fs_raster_direct_1", "kzn_fs_raster_direct_2"},
+                                            {"kzn_fs_raster_0", "kzn_fs_raster_1", "kzn_fs_raster_2"}};
+    for (int k = 0; k < 2; ++k)
+        for (int mode = 0; mode < 3; ++mode) {
+            CUresult_ cr = driver()->cuModuleGetFunction(&p->kernel[k][mode], p->module, names[k][mode]);
+            if (cr != 0) {
+                driver()->cuModuleUnload(p->module);
+                return driver_failed(cr, "cuModuleGetFunction");
+            }
+        }
+    *program = p.release();
+    return KZN_SUCCESS;
+}
+
+void kzn_fragment_program_destroy(KznFragmentProgram* program) {
+    if (!program) return;
+    if (program->module) {
+        cudaSetDevice(program->device->ordinal);
+        driver()->cuModuleUnload(program->module);
+    }
+    delete program;
+}
+
+KznResult kzn_cmd_bind_fragment_program(KznQueue* queue, KznFragmentProgram* program) {
+    KZN_VALID(queue, "vkCmdBindPipeline: null queue");
+    KZN_VALID(!program || program->device->ordinal == queue->device->ordinal, "fragment program was created for another device");
+    queue->fragment_program = program;
+    return KZN_SUCCESS;
+}
+
+}  // extern "C"
+
+// internal (kzn_internal.h): used by raster.cu
+uint32_t kzn_fragment_program_flags(const KznFragmentProgram* program) { return program ? program->flags : 0u; }
+
+KznResult kzn_fragment_program_launch(KznFragmentProgram* program, int kernel, int mode, unsigned grid_x, unsigned threads, size_t dynamic_smem,
+                                      cudaStream_t stream, const void* params, size_t) {
+    KZN_VALID(program && kernel >= 0 && kernel < 2 && mode >= 0 && mode < 3, "internal: bad fragment program launch");
+    DriverApi* d = driver();
+    CUfunction_ fn = program->kernel[kernel][mode];
+    if (dynamic_smem > 48 * 1024) {
+        CUresult_ cr = d->cuFuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)dynamic_smem);
+        if (cr != 0) return driver_failed(cr, "cuFuncSetAttribute");
+    }
+    void* args[1] = {const_cast<void*>(params)};
+    CUresult_ cr;
+    if (d->cuLaunchKernelEx && kzn_pdl_enabled()) {
+        // programmatic dependent launch, as the built-in kernels are launched (kzn_internal.h kzn_launch_pdl)
+        LaunchAttribute_ attr;
+        memset(&attr, 0, sizeof attr);
+        attr.id = 6;  // CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION
+        attr.value.programmatic_stream_serialization_allowed = 1;
+        LaunchConfig_ cfg = {grid_x, 1, 1, threads, 1, 1, (unsigned)dynamic_smem, (void*)stream, &attr, 1};
+        cr = d->cuLaunchKernelEx(&cfg, fn, args, nullptr);
+    } else {
+        cr = d->cuLaunchKernel(fn, grid_x, 1, 1, threads, 1, 1, (unsigned)dynamic_smem, (void*)stream, args, nullptr);
+    }
+    if (cr != 0) return driver_failed(cr, "cuLaunchKernel (fragment program)");
+    return KZN_SUCCESS;
+}
+
+extern "C" {
+
+// ---- descriptor sets and push constants -----------------------------------------------------------------------
+// vkCreateDescriptorSetLayout / vkAllocateDescriptorSets api_impl.rs:4218, vkUpdateDescriptorSets :4339,
+// vkCmdBindDescriptorSets :4597, vkCmdPushConstants :4932; vulkan-driver/src/descriptor_set.rs
+
+KznResult kzn_descriptor_set_create(KznDevice* device, uint32_t binding_count, const KznDescriptorSetLayoutBinding* bindings, KznDescriptorSet** set) {
+    KZN_VALID(device && set && (bindings || binding_count == 0), "kzn_descriptor_set_create: null argument");
+    *set = nullptr;
+    auto s = std::make_unique<KznDescriptorSet>();
+    s->device = device;
+    uint64_t slots = 0;
+    for (uint32_t i = 0; i < binding_count; ++i) {
+        const KznDescriptorSetLayoutBinding& b = bindings[i];
+        // the kinds descriptor_set.rs can write (:460-527): buffers are what a kernel reads through a pointer; images and
+        // samplers need a sampling path this back end does not have; texel and dynamic buffers are unimplemented!() upstream
+        KZN_REQUIRE(b.descriptor_type == KZN_DESCRIPTOR_TYPE_UNIFORM_BUFFER || b.descriptor_type == KZN_DESCRIPTOR_TYPE_STORAGE_BUFFER,
+                    KZN_ERROR_FEATURE_NOT_PRESENT, "descriptor type %u: only UNIFORM_BUFFER and STORAGE_BUFFER descriptors are supported", b.descriptor_type);
+        for (auto& o : s->bindings) KZN_VALID(o.binding != b.binding, "binding %u appears twice in the layout", b.binding);
+        KZN_VALID(slots + b.descriptor_count <= (1u << 20), "descriptor set with more than 2^20 descriptors");
+        s->bindings.push_back({b.binding, b.descriptor_type, b.descriptor_count, (uint32_t)slots});
+        slots += b.descriptor_count;
+    }
+    s->host.assign(2 * (slots ? slots : 1), 0);
+    KZN_CUDA(cudaSetDevice(device->ordinal));
+    KZN_CUDA(cudaMalloc(&s->table, s->host.size() * sizeof(uint64_t)));
+    KZN_CUDA(cudaMemset(s->table, 0, s->host.size() * sizeof(uint64_t)));
+    *set = s.release();
+    return KZN_SUCCESS;
+}
+
+void kzn_descriptor_set_destroy(KznDescriptorSet* set) {
+    if (!set) return;
+    cudaSetDevice(set->device->ordinal);
+    cudaFree(set->table);
+    delete set;
+}
+
+KznResult kzn_descriptor_set_write_buffers(KznDescriptorSet* set, uint32_t binding, uint32_t first_element, uint32_t count,
+                                           const KznDescriptorBufferInfo* buffers) {
+    KZN_VALID(set && (buffers || count == 0), "kzn_descriptor_set_write_buffers: null argument");
+    for (auto& b : set->bindings) {
+        if (b.binding != binding) continue;
+        KZN_VALID((uint64_t)first_element + count <= b.count, "descriptor write past the end of binding %u", binding);
+        for (uint32_t i = 0; i < count; ++i) {
+            set->host[2 * (size_t)(b.first_slot + first_element + i)] = buffers[i].address + buffers[i].offset;
+            set->host[2 * (size_t)(b.first_slot + first_element + i) + 1] = buffers[i].range;
+        }
+        if (count) {
+            // vkUpdateDescriptorSets is a host operation that is complete when it returns
+            KZN_CUDA(cudaSetDevice(set->device->ordinal));
+            KZN_CUDA(cudaMemcpy((uint64_t*)set->table + 2 * (size_t)(b.first_slot + first_element), &set->host[2 * (size_t)(b.first_slot + first_element)],
+                                (size_t)count * 16, cudaMemcpyHostToDevice));
+        }
+        return KZN_SUCCESS;
+    }
+    kzn_set_error("binding %u is not in the set's layout", binding);
+    return KZN_ERROR_VALIDATION_FAILED;
+}
+
+uint64_t kzn_descriptor_set_table_address(const KznDescriptorSet* set) { return set ? (uint64_t)(uintptr_t)set->table : 0; }
+
+int64_t kzn_descriptor_set_slot(const KznDescriptorSet* set, uint32_t binding) {
+    if (set)
+        for (auto& b : set->bindings)
+            if (b.binding == binding) return b.first_slot;
+    return -1;
+}
+
+KznResult kzn_cmd_bind_descriptor_set(KznQueue* queue, uint32_t pipeline_bind_point, const KznDescriptorSet* set) {
+    KZN_VALID(queue, "vkCmdBindDescriptorSets: null queue");
+    KZN_VALID(pipeline_bind_point <= KZN_PIPELINE_BIND_POINT_COMPUTE, "vkCmdBindDescriptorSets: bad pipeline bind point %u", pipeline_bind_point);
+    KZN_VALID(!set || set->device->ordinal == queue->device->ordinal, "descriptor set belongs to another device");
+    queue->descriptor_table[pipeline_bind_point] = set ? (uint64_t)(uintptr_t)set->table : 0;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_push_constants(KznQueue* queue, uint32_t offset, uint32_t size, const void* values) {
+    KZN_VALID(queue && values, "vkCmdPushConstants: null argument");
+    KZN_VALID(size > 0 && offset % 4 == 0 && size % 4 == 0, "vkCmdPushConstants: offset and size must be multiples of 4 and size non-zero");
+    KZN_VALID((uint64_t)offset + size <= KZN_MAX_PUSH_CONSTANTS_SIZE, "vkCmdPushConstants: range past maxPushConstantsSize (%u)", KZN_MAX_PUSH_CONSTANTS_SIZE);
+    memcpy(queue->push_constants + offset, values, size);
     return KZN_SUCCESS;
 }
 

@@ -95,7 +95,54 @@ struct Loop {
     int id = 0;
 };
 
-enum class Op { Add, Load, Break, Continue, Branch, BlockI, LoopI };
+enum class Op { Add, Load, Break, Continue, Branch, BlockI, LoopI, Ext };
+
+// ---- version 2 of the instruction set ----------------------------------------------------------------
+// The reference's IR has seven instructions (instructions_impl.rs:395-433) and its translator stops at the first SPIR-V
+// instruction with a body (473 `todo!()`s, parse/unimplemented_instructions.rs).  What a shader needs beyond them lives here,
+// in the C++ mirror, behind a version flag: a reader accepts these instructions only when it is asked for version 2
+// (parse_module(text, 2) / kzn_ir_parse_ex(..., KZN_IR_VERSION_2)); version 1 is the reference's grammar to the letter.
+// Each instruction is spelled like the SPIR-V instruction it translates (OpFMul -> `f_mul`, OpConvertFToU ->
+// `convert_f_to_u`, OpGroupNonUniformBallot -> `group_non_uniform_ballot`) in the reference's instruction syntax
+// `name [arguments] -> [results]`, and means what the SPIR-V specification says for scalar operands, with the
+// implementation-defined corners fixed (oracle/ir_simt.py is the checker):
+//   floating point: IEEE round-to-nearest-even, no contraction (`fma` is the only fused form), denormals kept;
+//   f_min / f_max return the other operand when one is NaN; float -> integer conversions round toward zero and saturate
+//   (NaN -> 0); shifts by the operand width or more give 0 (logical) or the sign (arithmetic);
+//   `store [pointer, value], align: A -> []` and `ptr_add [pointer, offset: i64] -> [q: data_ptr]` (the byte-offset form of
+//   OpAccessChain once the layout is known) complete `load`;
+//   group_non_uniform_*: subgroup = 32 consecutive invocations (one warp), defined in subgroup-uniform control flow only;
+//   ballot returns the low word of the SPIR-V uvec4; i_add is the Reduce group operation.
+enum class ExtKind {
+    IntBinary,     // [a, b] -> [r], one integer type
+    IntUnary,      // [a] -> [r]
+    FloatBinary,   // [a, b] -> [r], one float type
+    FloatUnary,
+    FloatTernary,  // fma
+    IntCompare,    // [a, b: iN] -> [r: bool]
+    FloatCompare,  // [a, b: fN] -> [r: bool]
+    BoolBinary,    // [a, b: bool] -> [r: bool]
+    BoolUnary,
+    Select,        // [c: bool, a, b] -> [r]
+    Convert,       // [a] -> [r], kinds checked per instruction
+    Store,         // [p: data_ptr, v], align: A -> []
+    PtrAdd,        // [p: data_ptr, off: i64] -> [q: data_ptr]
+    SubgroupElect,      // [] -> [bool]
+    SubgroupVote,       // [bool] -> [bool]
+    SubgroupBallot,     // [bool] -> [i32]
+    SubgroupBroadcast,  // [x] -> [x]
+    SubgroupShuffle,    // [x, i32] -> [x]
+    SubgroupReduce,     // [i32] -> [i32]
+};
+struct ExtOp {
+    const char* name;
+    ExtKind kind;
+    const char* ptx;  // mnemonic stem used by ptx_emit.cpp
+};
+extern const ExtOp kExtOps[];
+extern const int kExtOpCount;
+int ext_op_index(const std::string& name);  // -1 when `name` is not a version 2 instruction
+bool is_v2_built_in(const std::string& kind);
 
 struct BranchCase {
     Const value;
@@ -113,7 +160,8 @@ struct Instr {
     Op op;
     std::vector<Value*> args;
     std::vector<Value*> results;
-    uint64_t align = 0;          // Load
+    uint64_t align = 0;          // Load, Ext store
+    int ext = -1;                // Ext: index into kExtOps
     Block* block = nullptr;      // Break target / BlockI body
     Loop* loop = nullptr;        // Continue target / LoopI body
     std::vector<BranchCase> cases;
@@ -153,6 +201,7 @@ struct Module {
     std::vector<std::unique_ptr<Loop>> loops;
     std::vector<std::unique_ptr<Instr>> instrs;
     std::vector<std::unique_ptr<Function>> function_arena;
+    int version = 1;  // 2: the module may hold Ext instructions and version 2 built-in kinds
 
     const Type* intern(Type t);
     const Type* int_type(IntKind k);
@@ -167,7 +216,7 @@ struct Module {
 };
 
 // text.rs FromText / ToText
-std::unique_ptr<Module> parse_module(const std::string& text);
+std::unique_ptr<Module> parse_module(const std::string& text, int version = 1);
 std::string module_to_text(const Module& m);
 // parse `text` as one syntactic category and print it canonically — what the reference's test_from_to_text /
 // test_type / test_const macros check.  kind: type const target_properties block function

@@ -14,6 +14,83 @@
 
 namespace kir {
 
+const ExtOp kExtOps[] = {
+    {"i_sub", ExtKind::IntBinary, "sub"},
+    {"i_mul", ExtKind::IntBinary, "mul.lo"},
+    {"bitwise_and", ExtKind::IntBinary, "and"},
+    {"bitwise_or", ExtKind::IntBinary, "or"},
+    {"bitwise_xor", ExtKind::IntBinary, "xor"},
+    {"shift_left_logical", ExtKind::IntBinary, "shl"},
+    {"shift_right_logical", ExtKind::IntBinary, "shr.u"},
+    {"shift_right_arithmetic", ExtKind::IntBinary, "shr.s"},
+    {"s_negate", ExtKind::IntUnary, "neg"},
+    {"not", ExtKind::IntUnary, "not"},
+    {"f_add", ExtKind::FloatBinary, "add.rn"},
+    {"f_sub", ExtKind::FloatBinary, "sub.rn"},
+    {"f_mul", ExtKind::FloatBinary, "mul.rn"},
+    {"f_div", ExtKind::FloatBinary, "div.rn"},
+    {"f_min", ExtKind::FloatBinary, "min"},
+    {"f_max", ExtKind::FloatBinary, "max"},
+    {"f_negate", ExtKind::FloatUnary, "neg"},
+    {"f_abs", ExtKind::FloatUnary, "abs"},
+    {"fma", ExtKind::FloatTernary, "fma.rn"},
+    {"i_equal", ExtKind::IntCompare, "eq"},
+    {"i_not_equal", ExtKind::IntCompare, "ne"},
+    {"u_less_than", ExtKind::IntCompare, "lt.u"},
+    {"s_less_than", ExtKind::IntCompare, "lt.s"},
+    {"u_less_than_equal", ExtKind::IntCompare, "le.u"},
+    {"s_less_than_equal", ExtKind::IntCompare, "le.s"},
+    {"u_greater_than", ExtKind::IntCompare, "gt.u"},
+    {"s_greater_than", ExtKind::IntCompare, "gt.s"},
+    {"u_greater_than_equal", ExtKind::IntCompare, "ge.u"},
+    {"s_greater_than_equal", ExtKind::IntCompare, "ge.s"},
+    {"f_ord_equal", ExtKind::FloatCompare, "eq"},
+    {"f_ord_less_than", ExtKind::FloatCompare, "lt"},
+    {"f_ord_less_than_equal", ExtKind::FloatCompare, "le"},
+    {"f_ord_greater_than", ExtKind::FloatCompare, "gt"},
+    {"f_ord_greater_than_equal", ExtKind::FloatCompare, "ge"},
+    {"f_unord_not_equal", ExtKind::FloatCompare, "neu"},
+    {"logical_and", ExtKind::BoolBinary, "and"},
+    {"logical_or", ExtKind::BoolBinary, "or"},
+    {"logical_not", ExtKind::BoolUnary, "not"},
+    {"select", ExtKind::Select, "selp"},
+    {"convert_f_to_u", ExtKind::Convert, "f2u"},
+    {"convert_f_to_s", ExtKind::Convert, "f2s"},
+    {"convert_s_to_f", ExtKind::Convert, "s2f"},
+    {"convert_u_to_f", ExtKind::Convert, "u2f"},
+    {"u_convert", ExtKind::Convert, "u2u"},
+    {"s_convert", ExtKind::Convert, "s2s"},
+    {"f_convert", ExtKind::Convert, "f2f"},
+    {"bitcast", ExtKind::Convert, "bits"},
+    {"store", ExtKind::Store, "st"},
+    {"ptr_add", ExtKind::PtrAdd, "add"},
+    {"group_non_uniform_elect", ExtKind::SubgroupElect, "elect"},
+    {"group_non_uniform_all", ExtKind::SubgroupVote, "all"},
+    {"group_non_uniform_any", ExtKind::SubgroupVote, "any"},
+    {"group_non_uniform_ballot", ExtKind::SubgroupBallot, "ballot"},
+    {"group_non_uniform_broadcast_first", ExtKind::SubgroupBroadcast, "first"},
+    {"group_non_uniform_shuffle", ExtKind::SubgroupShuffle, "idx"},
+    {"group_non_uniform_shuffle_xor", ExtKind::SubgroupShuffle, "bfly"},
+    {"group_non_uniform_i_add", ExtKind::SubgroupReduce, "add"},
+};
+const int kExtOpCount = (int)(sizeof(kExtOps) / sizeof(kExtOps[0]));
+// Built-in kinds of version 2 (the reference has `vertex_position` only, interface.rs:61-67), spelled like the SPIR-V
+// BuiltIn they carry: inputs global_invocation_id <3 x i32>, subgroup_local_invocation_id i32, subgroup_size i32,
+// frag_coord <4 x f32>; push_constants / descriptor_table: a data_ptr to the bound block (vkCmdPushConstants,
+// vkCmdBindDescriptorSets).
+bool is_v2_built_in(const std::string& kind) {
+    static const char* const kinds[] = {"global_invocation_id", "subgroup_local_invocation_id", "subgroup_size", "frag_coord",
+                                        "push_constants", "descriptor_table"};
+    for (auto* k : kinds)
+        if (kind == k) return true;
+    return false;
+}
+int ext_op_index(const std::string& name) {
+    for (int i = 0; i < kExtOpCount; ++i)
+        if (name == kExtOps[i].name) return i;
+    return -1;
+}
+
 int int_bits(IntKind k) {
     switch (k) {
     case IntKind::I8: return 8;
@@ -325,8 +402,9 @@ struct Parser {
     std::vector<std::map<Key, Block*>> blocks{1};
     std::vector<std::map<Key, Loop*>> loops{1};
     std::map<Key, Function*> functions;
+    int version = 1;  // 2: version 2 instructions and built-in kinds are accepted (ir.h)
 
-    Parser(Module& mod, const std::string& text) : m(mod), toks(lex(text)) {}
+    Parser(Module& mod, const std::string& text, int ver = 1) : m(mod), toks(lex(text)), version(ver) {}
 
     const Token& t() const { return toks[i]; }
     Token next() { return toks[i++]; }
@@ -628,6 +706,116 @@ struct Parser {
         return ins;
     }
 
+    // argument / result counts and types of a version 2 instruction
+    static void check_ext(const Instr* ins) {
+        const ExtOp& op = kExtOps[ins->ext];
+        auto bad = [&](const char* what) { throw Error(std::string(op.name) + ": " + what); };
+        auto counts = [&](size_t a, size_t r) {
+            if (ins->args.size() != a || ins->results.size() != r)
+                bad(("takes " + std::to_string(a) + " argument(s) and " + std::to_string(r) + " result(s)").c_str());
+        };
+        auto is = [](const Value* v, TypeKind k) { return v->type->kind == k; };
+        auto int32 = [](const Value* v) { return v->type->kind == TypeKind::Int && int_bits(v->type->int_kind) == 32; };
+        auto scalar = [](const Value* v) {
+            TypeKind k = v->type->kind;
+            return k == TypeKind::Int || k == TypeKind::Float || k == TypeKind::Bool || k == TypeKind::DataPtr;
+        };
+        switch (op.kind) {
+        case ExtKind::IntBinary:
+            counts(2, 1);
+            if (!is(ins->results[0], TypeKind::Int) || ins->args[0]->type != ins->results[0]->type || ins->args[1]->type != ins->results[0]->type)
+                bad("operands and result must have one integer type");
+            break;
+        case ExtKind::IntUnary:
+            counts(1, 1);
+            if (!is(ins->results[0], TypeKind::Int) || ins->args[0]->type != ins->results[0]->type) bad("operand and result must have one integer type");
+            break;
+        case ExtKind::FloatBinary:
+        case ExtKind::FloatUnary:
+        case ExtKind::FloatTernary: {
+            const size_t n = op.kind == ExtKind::FloatBinary ? 2 : op.kind == ExtKind::FloatUnary ? 1 : 3;
+            counts(n, 1);
+            if (!is(ins->results[0], TypeKind::Float) || float_bits(ins->results[0]->type->float_kind) == 16) bad("the result must be f32 or f64");
+            for (auto* a : ins->args)
+                if (a->type != ins->results[0]->type) bad("operands and result must have one float type");
+            break;
+        }
+        case ExtKind::IntCompare:
+        case ExtKind::FloatCompare:
+            counts(2, 1);
+            if (!is(ins->results[0], TypeKind::Bool)) bad("the result must be bool");
+            if (ins->args[0]->type != ins->args[1]->type) bad("operands must have one type");
+            if (op.kind == ExtKind::IntCompare ? !(is(ins->args[0], TypeKind::Int) || is(ins->args[0], TypeKind::DataPtr))
+                                               : !(is(ins->args[0], TypeKind::Float) && float_bits(ins->args[0]->type->float_kind) != 16))
+                bad(op.kind == ExtKind::IntCompare ? "operands must be integers" : "operands must be f32 or f64");
+            break;
+        case ExtKind::BoolBinary:
+        case ExtKind::BoolUnary:
+            counts(op.kind == ExtKind::BoolBinary ? 2 : 1, 1);
+            if (!is(ins->results[0], TypeKind::Bool)) bad("the result must be bool");
+            for (auto* a : ins->args)
+                if (!is(a, TypeKind::Bool)) bad("operands must be bool");
+            break;
+        case ExtKind::Select:
+            counts(3, 1);
+            if (!is(ins->args[0], TypeKind::Bool)) bad("the condition must be bool");
+            if (!scalar(ins->results[0]) || ins->args[1]->type != ins->results[0]->type || ins->args[2]->type != ins->results[0]->type)
+                bad("both values and the result must have one scalar type");
+            break;
+        case ExtKind::Convert: {
+            counts(1, 1);
+            const Value *a = ins->args[0], *r = ins->results[0];
+            const std::string n = op.name;
+            auto flt = [&](const Value* v) { return is(v, TypeKind::Float) && float_bits(v->type->float_kind) != 16; };
+            bool ok = true;
+            if (n == "convert_f_to_u" || n == "convert_f_to_s") ok = flt(a) && is(r, TypeKind::Int);
+            else if (n == "convert_s_to_f" || n == "convert_u_to_f") ok = is(a, TypeKind::Int) && flt(r);
+            else if (n == "u_convert" || n == "s_convert") ok = is(a, TypeKind::Int) && is(r, TypeKind::Int);
+            else if (n == "f_convert") ok = flt(a) && flt(r);
+            else ok = scalar(a) && scalar(r) && !is(a, TypeKind::Bool) && !is(r, TypeKind::Bool) && type_size(a->type) == type_size(r->type);
+            if (!ok) bad("operand / result types do not fit the conversion");
+            break;
+        }
+        case ExtKind::Store:
+            counts(2, 0);
+            if (!is(ins->args[0], TypeKind::DataPtr)) bad("the first argument must be a data_ptr");
+            if (!scalar(ins->args[1])) bad("only scalar values are stored");
+            break;
+        case ExtKind::PtrAdd:
+            counts(2, 1);
+            if (!is(ins->args[0], TypeKind::DataPtr) || !is(ins->results[0], TypeKind::DataPtr)) bad("pointer and result must be data_ptr");
+            if (!is(ins->args[1], TypeKind::Int) || int_bits(ins->args[1]->type->int_kind) != 64) bad("the offset must be i64");
+            break;
+        case ExtKind::SubgroupElect:
+            counts(0, 1);
+            if (!is(ins->results[0], TypeKind::Bool)) bad("the result must be bool");
+            break;
+        case ExtKind::SubgroupVote:
+            counts(1, 1);
+            if (!is(ins->args[0], TypeKind::Bool) || !is(ins->results[0], TypeKind::Bool)) bad("operand and result must be bool");
+            break;
+        case ExtKind::SubgroupBallot:
+            counts(1, 1);
+            if (!is(ins->args[0], TypeKind::Bool) || !int32(ins->results[0])) bad("takes a bool, returns an i32");
+            break;
+        case ExtKind::SubgroupBroadcast:
+            counts(1, 1);
+            if (ins->args[0]->type != ins->results[0]->type || !(int32(ins->args[0]) || (is(ins->args[0], TypeKind::Float) && float_bits(ins->args[0]->type->float_kind) == 32)))
+                bad("operand and result must be one 32-bit type");
+            break;
+        case ExtKind::SubgroupShuffle:
+            counts(2, 1);
+            if (ins->args[0]->type != ins->results[0]->type || !(int32(ins->args[0]) || (is(ins->args[0], TypeKind::Float) && float_bits(ins->args[0]->type->float_kind) == 32)))
+                bad("value and result must be one 32-bit type");
+            if (!int32(ins->args[1])) bad("the lane selector must be i32");
+            break;
+        case ExtKind::SubgroupReduce:
+            counts(1, 1);
+            if (!int32(ins->args[0]) || ins->args[0]->type != ins->results[0]->type) bad("operand and result must be i32");
+            break;
+        }
+    }
+
     Instr* instruction() {
         Token k = next();
         if (k.kind != Tk::Id) fail("expected an instruction, found '" + k.text + "'", k.pos);
@@ -685,6 +873,18 @@ struct Parser {
         } else if (k.text == "loop") {
             ins = m.new_instr(Op::LoopI);
             ins->loop = loop_instruction();
+        } else if (version >= 2 && ext_op_index(k.text) >= 0) {
+            ins = m.new_instr(Op::Ext);
+            ins->ext = ext_op_index(k.text);
+            expect("[");
+            ins->args = uses();
+            if (kExtOps[ins->ext].kind == ExtKind::Store) {
+                expect(",");
+                ins->align = alignment();
+            }
+            expect("->");
+            ins->results = defs();
+            check_ext(ins);
         } else {
             fail("unknown instruction '" + k.text + "'", k.pos);
         }
@@ -862,7 +1062,8 @@ struct Parser {
             expect("kind");
             expect(":");
             v.built_in_kind = word();
-            if (v.built_in_kind != "vertex_position") throw Error("unknown built-in kind " + v.built_in_kind);  // interface.rs:61-67
+            if (v.built_in_kind != "vertex_position" && !(version >= 2 && is_v2_built_in(v.built_in_kind)))
+                throw Error("unknown built-in kind " + v.built_in_kind);  // interface.rs:61-67
             expect("}");
             expect(";");
             out.push_back(v);
@@ -1107,6 +1308,14 @@ struct Printer {
             w("], align: " + hex(ins->align) + " -> ");
             def_list(ins->results);
             break;
+        case Op::Ext:
+            w(std::string(kExtOps[ins->ext].name) + " [");
+            use_list(ins->args);
+            w("]");
+            if (kExtOps[ins->ext].kind == ExtKind::Store) w(", align: " + hex(ins->align));
+            w(" -> ");
+            def_list(ins->results);
+            break;
         case Op::Break: brk(ins->block, ins->args); break;
         case Op::Continue:
             w("continue " + lname(ins->loop) + "[");
@@ -1282,9 +1491,10 @@ struct Printer {
 
 }  // namespace
 
-std::unique_ptr<Module> parse_module(const std::string& text) {
+std::unique_ptr<Module> parse_module(const std::string& text, int version) {
     auto m = std::make_unique<Module>();
-    Parser p(*m, text);
+    m->version = version;
+    Parser p(*m, text, version);
     p.module();
     p.finish();
     return m;

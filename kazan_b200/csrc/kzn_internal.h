@@ -40,7 +40,23 @@ struct KznQueue {
     KznPendingTransfer pending[KZN_MAX_MERGED];  // recorded, not yet captured (only while recording)
     uint32_t n_pending;
     uint64_t merged_commands;  // commands that went into a merged launch (statistics)
+    // vkCmdBindDescriptorSets / vkCmdPushConstants state, read by the next dispatch or draw (its values go into that
+    // launch's kernel parameters, so a recorded command keeps what was bound when it was recorded)
+    uint64_t descriptor_table[2];  // [VkPipelineBindPoint]: device address of the bound set's table, 0 = none
+    alignas(16) unsigned char push_constants[128];
+    struct KznFragmentProgram* fragment_program;  // kzn_cmd_bind_fragment_program
 };
+
+// backend.cpp: launch one of the raster kernels built around a compiled fragment program.  kernel: 0 = raster_direct,
+// 1 = raster (binned); mode: kDstNone / kDstGeneric / kDstAlphaOver; `params` is the kernel's single by-value parameter.
+KznResult kzn_fragment_program_launch(struct KznFragmentProgram* program, int kernel, int mode, unsigned grid_x, unsigned threads,
+                                      size_t dynamic_smem, cudaStream_t stream, const void* params, size_t params_size);
+// what the program reads: bit 0 = interpolated inputs or frag_coord z / w
+uint32_t kzn_fragment_program_flags(const struct KznFragmentProgram* program);
+// byte offset of the push constant block inside the raster kernels' parameter (raster.cu DrawParams)
+extern "C" const uint32_t kzn_draw_params_push_constants_offset;
+// the raster kernels' PTX with the fragment program as an external call (generated at build time from raster.cu)
+extern "C" const char kzn_raster_template_ptx[];
 
 struct KznMemory {
     KznDevice* device;

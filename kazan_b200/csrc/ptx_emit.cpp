@@ -2,20 +2,31 @@
 //
 // Replaces, for the B200, what shader-compiler-backend-llvm-7/src/backend.rs:553-690 (`LLVM7Compiler::run`) is for the
 // host CPU.  Input is the structured SSA of shader-compiler-ir (instructions_impl.rs:395-433: add, load, break, branch,
-// continue, block, loop); output is one `.visible .entry` per module, one invocation per thread (BASELINE north_star).
+// continue, block, loop) plus, for modules read as version 2, the instructions of ir.h (`ExtOp`: float arithmetic,
+// compares, select, conversions, store, ptr_add, subgroup operations).  Two forms of output:
+//   emit_ptx             one `.visible .entry` per module, one invocation per thread (BASELINE north_star): compute
+//                        dispatch.  Subgroup operations map to warp votes and shuffles (a subgroup is a warp).
+//   emit_fragment_inline the entry point of a fragment shader as a PTX scope that reads its inputs from, and leaves its
+//                        outputs in, registers of the surrounding code: fragment_jit.cpp puts one copy at every place the
+//                        raster kernels (raster.cu, compiled to PTX at build time) call the fragment program.
 //
-// Invocation ABI (include/kazan_b200_backend.h): parameters (user_inputs_base, user_outputs_base, invocation_count,
-// first_invocation).  Thread g of the grid (2-D folded) runs invocation first+g; its interface blocks
-// (interface.rs:199-252) are base + (first+g) * block.size.  The values the entry point's body block is left with
-// (`break <body>[v...]`, block.rs:16-23) are stored to the members of user_outputs_block, in order.
+// Invocation ABI of a kernel (include/kazan_b200_backend.h): parameters (user_inputs_base, user_outputs_base,
+// invocation_count, first_invocation, global_size_x, global_size_y, descriptor_table, global_base[16], push_constants[128]).  Thread g of the
+// grid (2-D folded) runs invocation first+g; its interface blocks (interface.rs:199-252) are base + (first+g) * block.size.
+// The values the entry point's body block is left with (`break <body>[v...]`, block.rs:16-23) are stored to the members of
+// user_outputs_block, in order.
 //
 // Lowering:
 //   value                    -> one virtual register of its class (.pred bool, .b16 i8/i16/f16, .b32, .b64)
 //   block name -> [r..] {..} -> fall-through region closed by a label; `break` = moves into r.. + bra to the label
 //   loop                     -> moves arguments into the parameters, head label, body block; `continue` = parallel move + bra
 //   branch                   -> setp.eq chain, each case a predicated skip around (moves + bra)
-//   load, align A            -> one ld of natural width when A >= size, otherwise A-sized pieces combined with shl/or
-//   variables (function.rs:155-193, module.rs:145-147, interface.rs:61-67) -> .local arrays, address through cvta.local
+//   load / store, align A    -> one access of natural width when A >= size, otherwise A-sized pieces
+//   variables (function.rs:155-193, module.rs:145-147, interface.rs:61-67): a variable whose pointer is only ever used as
+//   `pointer + constant` in loads and stores of disjoint scalar slots lives in registers, one per slot (built-in inputs
+//   arrive that way: global_invocation_id is three registers, not memory); any other use of the pointer gives it a
+//   .local array (address through cvta.local).
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <set>
@@ -27,9 +38,29 @@ namespace kir {
 namespace {
 
 enum class RC { Pred, B16, B32, B64 };
+enum class Mode { Kernel, Inline };
+
+// what a data_ptr value is known to point at: `base` + a constant
+struct Base {
+    enum Kind { UserIn, UserOut, Var, PushConstants } kind = Var;
+    const Variable* var = nullptr;
+    std::string built_in;  // kind of a built-in variable
+    uint64_t size = 0;
+    bool scalarized = true;  // lives in registers: one per accessed slot
+    bool conflicted = false;
+    std::map<uint64_t, unsigned> slots;      // offset -> bytes, from the analysis
+    std::map<uint64_t, std::string> cells;   // offset -> register
+    std::string address;                     // register (or symbol expression) of the base when it is memory
+};
+struct Prov {
+    int base;
+    int64_t offset;
+};
 
 struct Emitter {
     const Module& m;
+    Mode mode;
+    std::string tag;  // suffix that makes labels and symbols of one inline copy unique
     std::ostringstream body;
     std::map<const Value*, std::string> reg;
     std::map<const Block*, const std::vector<Value*>*> dests;  // where `break block[...]` writes
@@ -37,8 +68,14 @@ struct Emitter {
     std::map<const Loop*, std::string> head_label;
     int n_pred = 0, n16 = 0, n32 = 0, n64 = 0, n_label = 0, n_var = 0;
     std::ostringstream locals;
+    std::vector<Base> bases;
+    std::map<const Value*, Prov> prov;
+    std::string submask;      // kernel: member mask of the in-range threads of the warp (subgroup operations)
+    bool uses_subgroup = false;
+    std::string pc_param;     // symbol (+ offset) of the push constant block in parameter space, when it is there
+    bool reads_user_inputs = false, reads_frag_coord = false, reads_frag_coord_zw = false;
 
-    explicit Emitter(const Module& mod) : m(mod) {}
+    Emitter(const Module& mod, Mode md, const std::string& suffix = "") : m(mod), mode(md), tag(suffix) {}
 
     [[noreturn]] static void unsupported(const std::string& what) { throw Unsupported("PTX back end: " + what); }
 
@@ -62,24 +99,34 @@ struct Emitter {
             default: unsupported("vector / struct typed SSA values (only scalar values are lowered)");
         }
     }
+    static RC class_of_bytes(int n) { return n <= 2 ? RC::B16 : n == 4 ? RC::B32 : RC::B64; }
     std::string fresh(RC c) {
-        char b[32];
+        char b[48];
+        const char* t = tag.c_str();
         switch (c) {
-            case RC::Pred: snprintf(b, sizeof b, "%%p%d", n_pred++); break;
-            case RC::B16: snprintf(b, sizeof b, "%%h%d", n16++); break;
-            case RC::B32: snprintf(b, sizeof b, "%%r%d", n32++); break;
-            case RC::B64: snprintf(b, sizeof b, "%%rd%d", n64++); break;
+            case RC::Pred: snprintf(b, sizeof b, "%%p%s%d", t, n_pred++); break;
+            case RC::B16: snprintf(b, sizeof b, "%%h%s%d", t, n16++); break;
+            case RC::B32: snprintf(b, sizeof b, "%%r%s%d", t, n32++); break;
+            case RC::B64: snprintf(b, sizeof b, "%%rd%s%d", t, n64++); break;
         }
         return b;
     }
     static const char* mov_type(RC c) { return c == RC::Pred ? "pred" : c == RC::B16 ? "b16" : c == RC::B32 ? "b32" : "b64"; }
     std::string label(const char* stem) {
-        char b[48];
-        snprintf(b, sizeof b, "$%s_%d", stem, n_label++);
+        char b[96];
+        snprintf(b, sizeof b, "$%s%s_%d", stem, tag.c_str(), n_label++);
         return b;
     }
     void line(const std::string& s) { body << "    " << s << "\n"; }
     void put_label(const std::string& l) { body << l << ":\n"; }
+    static bool is_immediate(const std::string& s) { return s.rfind("0x", 0) == 0 || s == "0" || s.rfind("0f", 0) == 0 || s.rfind("0d", 0) == 0; }
+    // an operand that must be a register: immediates are moved into one
+    std::string in_register(const std::string& operand, RC c) {
+        if (!is_immediate(operand)) return operand;
+        std::string r = fresh(c);
+        line(std::string("mov.") + mov_type(c) + " " + r + ", " + operand + ";");
+        return r;
+    }
 
     // register that holds a definition
     const std::string& def(const Value* v) {
@@ -87,10 +134,23 @@ struct Emitter {
         if (it != reg.end()) return it->second;
         return reg.emplace(v, fresh(reg_class(v->type))).first->second;
     }
+    // the register holding `base + offset` of a pointer the analysis knows (memory-backed bases only)
+    std::string materialize(const Prov& p) {
+        Base& b = bases[p.base];
+        if (b.scalarized) throw Error("internal: the address of a register-resident variable was asked for");
+        if (p.offset == 0) return b.address;
+        std::string r = fresh(RC::B64);
+        line("add.s64 " + r + ", " + b.address + ", " + std::to_string(p.offset) + ";");
+        return r;
+    }
     // operand text for a use: registers for definitions, immediates for inline constants (values.rs:168-200)
     std::string use(const Value* v) {
         if (!v->has_const) {
             auto it = reg.find(v);
+            auto pr = prov.find(v);
+            // a known place used as a value: base + constant, made where it is used (a register made inside one block
+            // would not be defined on the paths around it)
+            if (pr != prov.end() && it == reg.end()) return materialize(pr->second);
             if (it == reg.end()) throw Error("value '" + v->name + "' is used before it is defined");
             return it->second;
         }
@@ -133,6 +193,14 @@ struct Emitter {
         }
         unsupported("constant kind");
     }
+    // a use that an arithmetic instruction reads as a typed operand: float constants become typed immediates
+    // (an untyped 0x.. literal is read as an integer by floating-point instructions)
+    std::string use_float(const Value* v) {
+        std::string s = use(v);
+        if (!is_immediate(s)) return s;
+        return in_register(s, reg_class(v->type));
+    }
+    std::string use_reg(const Value* v) { return in_register(use(v), reg_class(v->type)); }
     void move(const Value* dst, const std::string& src) {
         RC c = reg_class(dst->type);
         line(std::string("mov.") + mov_type(c) + " " + def(dst) + ", " + src + ";");
@@ -155,9 +223,112 @@ struct Emitter {
         for (size_t i = 0; i < dsts.size(); ++i) move(dsts[i], ops[i]);
     }
 
+    // ---- pointer analysis -----------------------------------------------------------------------------------------
+    int add_base(Base b) {
+        bases.push_back(std::move(b));
+        return (int)bases.size() - 1;
+    }
+    void pointer_escapes(const Value* v) {
+        auto it = prov.find(v);
+        if (it != prov.end()) bases[it->second.base].scalarized = false;
+    }
+    void note_access(const Value* pointer, int bytes) {
+        auto it = prov.find(pointer);
+        if (it == prov.end()) return;
+        Base& b = bases[it->second.base];
+        if (b.kind == Base::UserIn) reads_user_inputs = true;
+        if (b.built_in == "frag_coord") reads_frag_coord = true;
+        const int64_t off = it->second.offset;
+        if (b.built_in == "frag_coord" && off + bytes > 8) reads_frag_coord_zw = true;
+        if (off < 0 || (uint64_t)off + (uint64_t)bytes > b.size) {
+            b.conflicted = true;  // outside the object: only real memory gives that a meaning
+            return;
+        }
+        auto s = b.slots.find((uint64_t)off);
+        if (s != b.slots.end() && s->second != (unsigned)bytes) b.conflicted = true;
+        b.slots[(uint64_t)off] = (unsigned)bytes;
+    }
+    void analyze_values(const std::vector<Value*>& vs) {
+        for (const Value* v : vs) pointer_escapes(v);
+    }
+    void analyze(const Block* b) {
+        for (const Instr* ins : b->body) {
+            switch (ins->op) {
+                case Op::Load:
+                    if (ins->args.size() == 1 && ins->results.size() == 1) {
+                        note_access(ins->args[0], scalar_bytes(ins->results[0]->type));
+                        // the pointer a push_constants variable holds is itself a known place
+                        auto it = prov.find(ins->args[0]);
+                        if (it != prov.end() && bases[it->second.base].built_in == "push_constants" && it->second.offset == 0 &&
+                            ins->results[0]->type->kind == TypeKind::DataPtr)
+                            prov[ins->results[0]] = Prov{push_constants_base(), 0};
+                    }
+                    break;
+                case Op::Ext: {
+                    const ExtKind k = kExtOps[ins->ext].kind;
+                    if (k == ExtKind::PtrAdd && ins->args.size() == 2 && ins->results.size() == 1) {
+                        auto it = prov.find(ins->args[0]);
+                        if (it != prov.end()) {
+                            const Value* off = ins->args[1];
+                            if (off->has_const && off->constant.kind == ConstKind::Int) prov[ins->results[0]] = Prov{it->second.base, it->second.offset + (int64_t)off->constant.bits};
+                            else bases[it->second.base].scalarized = false;
+                        }
+                    } else if (k == ExtKind::Store && ins->args.size() == 2) {
+                        note_access(ins->args[0], scalar_bytes(ins->args[1]->type));
+                        pointer_escapes(ins->args[1]);
+                    } else {
+                        analyze_values(ins->args);
+                    }
+                    break;
+                }
+                case Op::Add: analyze_values(ins->args); break;
+                case Op::Break:
+                case Op::Continue: analyze_values(ins->args); break;
+                case Op::Branch:
+                    analyze_values(ins->args);
+                    for (auto& c : ins->cases) analyze_values(c.results);
+                    break;
+                case Op::BlockI: analyze(ins->block); break;
+                case Op::LoopI:
+                    analyze_values(ins->loop->arguments);
+                    analyze(ins->loop->body);
+                    break;
+            }
+        }
+    }
+    int pc_base = -1;
+    int push_constants_base() {
+        if (pc_base < 0) {
+            Base b;
+            b.kind = Base::PushConstants;
+            b.size = 128;
+            b.scalarized = false;
+            pc_base = add_base(std::move(b));
+        }
+        return pc_base;
+    }
+    void finish_analysis() {
+        for (Base& b : bases) {
+            if (b.conflicted) b.scalarized = false;
+            if (!b.scalarized) continue;
+            uint64_t end = 0;
+            for (auto& s : b.slots) {  // ordered by offset: slots must not overlap
+                if (s.first < end) b.scalarized = false;
+                end = s.first + s.second;
+            }
+        }
+    }
+
     // ---- memory -------------------------------------------------------------------------------------------------
-    // dst register <- size bytes at [addr], the access split into `piece`-byte naturally aligned loads
-    void load_scalar(const Value* result, const std::string& addr, uint64_t align) {
+    // text of `[register + constant]`
+    static std::string address(const std::string& r, int64_t off) {
+        const size_t plus = r.find('+');  // "symbol+constant": the constants add up
+        if (plus != std::string::npos) return r.substr(0, plus) + "+" + std::to_string(std::stoll(r.substr(plus + 1)) + off);
+        if (off == 0) return r;
+        return r + (off > 0 ? "+" : "") + std::to_string(off);
+    }
+    // dst register <- size bytes at [addr + off], the access split into `piece`-byte naturally aligned loads
+    void load_scalar(const Value* result, const std::string& addr, int64_t off, uint64_t align, const char* space = "") {
         const Type* t = result->type;
         int size = scalar_bytes(t);
         RC rc = reg_class(t);
@@ -165,17 +336,18 @@ struct Emitter {
         uint64_t piece = 1;
         while (piece * 2 <= align && piece * 2 <= (uint64_t)size) piece *= 2;
         std::string value;
+        const std::string ld = std::string("ld") + space;
         if (piece == (uint64_t)size) {
             value = rc == RC::Pred ? fresh(RC::B16) : def(result);
-            line("ld.u" + std::to_string(size * 8) + " " + value + ", [" + addr + "];");
+            line(ld + ".u" + std::to_string(size * 8) + " " + value + ", [" + address(addr, off) + "];");
         } else {
             // little-endian assembly in a 64-bit temporary
             std::string acc = fresh(RC::B64), part = fresh(RC::B64);
-            for (int off = 0; off < size; off += (int)piece) {
-                std::string dstp = off == 0 ? acc : part;
-                line("ld.u" + std::to_string(piece * 8) + " " + dstp + ", [" + addr + "+" + std::to_string(off) + "];");
-                if (off) {
-                    line("shl.b64 " + part + ", " + part + ", " + std::to_string(off * 8) + ";");
+            for (int o = 0; o < size; o += (int)piece) {
+                std::string dstp = o == 0 ? acc : part;
+                line(ld + ".u" + std::to_string(piece * 8) + " " + dstp + ", [" + address(addr, off + o) + "];");
+                if (o) {
+                    line("shl.b64 " + part + ", " + part + ", " + std::to_string(o * 8) + ";");
                     line("or.b64 " + acc + ", " + acc + ", " + part + ";");
                 }
             }
@@ -192,7 +364,7 @@ struct Emitter {
         }
         if (rc == RC::Pred) line("setp.ne.u16 " + def(result) + ", " + value + ", 0;");
     }
-    void store_scalar(const Type* t, const std::string& src_operand, const std::string& addr, uint64_t offset, uint64_t align) {
+    void store_scalar(const Type* t, const std::string& src_operand, const std::string& addr, int64_t offset, uint64_t align, const char* space = "") {
         int size = scalar_bytes(t);
         RC rc = reg_class(t);
         std::string src = src_operand;
@@ -200,34 +372,74 @@ struct Emitter {
             std::string h = fresh(RC::B16);
             line("selp.u16 " + h + ", 1, 0, " + src + ";");
             src = h;
-        } else if (src.rfind("0x", 0) == 0 || src == "0") {  // immediates cannot be store sources
-            std::string r = fresh(rc);
-            line(std::string("mov.") + mov_type(rc) + " " + r + ", " + src + ";");
-            src = r;
+        } else {
+            src = in_register(src, rc);  // immediates cannot be store sources
         }
         if (align == 0) align = 1;
         uint64_t piece = 1;
         while (piece * 2 <= align && piece * 2 <= (uint64_t)size) piece *= 2;
+        const std::string st = std::string("st") + space;
         if (piece == (uint64_t)size) {
-            line("st.u" + std::to_string(size * 8) + " [" + addr + "+" + std::to_string(offset) + "], " + src + ";");
+            line(st + ".u" + std::to_string(size * 8) + " [" + address(addr, offset) + "], " + src + ";");
             return;
         }
         std::string wide = fresh(RC::B64), part = fresh(RC::B64);
         line(std::string("cvt.u64.u") + (rc == RC::B64 ? "64 " : rc == RC::B32 ? "32 " : "16 ") + wide + ", " + src + ";");
         for (int off = 0; off < size; off += (int)piece) {
             line("shr.u64 " + part + ", " + wide + ", " + std::to_string(off * 8) + ";");
-            line("st.u" + std::to_string(piece * 8) + " [" + addr + "+" + std::to_string(offset + off) + "], " + part + ";");
+            line(st + ".u" + std::to_string(piece * 8) + " [" + address(addr, offset + off) + "], " + part + ";");
         }
     }
-    void variable(const Variable& v) {
+    // the register of slot `off` of a register-resident base (created on first use, holding 0)
+    const std::string& cell(Base& b, uint64_t off) {
+        auto it = b.cells.find(off);
+        if (it != b.cells.end()) return it->second;
+        auto s = b.slots.find(off);
+        if (s == b.slots.end()) throw Error("internal: access to a slot the analysis did not see");
+        RC c = class_of_bytes((int)s->second);
+        std::string r = fresh(c);
+        prologue << "    mov." << mov_type(c) << " " << r << ", 0;\n";
+        return b.cells.emplace(off, r).first->second;
+    }
+    std::ostringstream prologue;  // register cells are zeroed ahead of the body
+
+    // a variable: registers (nothing to emit: cells appear on demand) or a .local array
+    void variable(const Variable& v, int base_index) {
         if (!v.pointer) return;
+        Base& b = bases[base_index];
+        if (b.scalarized) return;
         uint64_t size = type_size(v.type), align = v.align ? v.align : 1;
         if (align & (align - 1)) throw Error("variable alignment is not a power of two");
-        std::string sym = "__kzn_var" + std::to_string(n_var++);
+        std::string sym = "__kzn_var" + tag + std::to_string(n_var++);
         locals << "    .local .align " << align << " .b8 " << sym << "[" << (size ? size : 1) << "];\n";
-        const std::string& r = def(v.pointer);
+        std::string r = fresh(RC::B64);
         line("mov.u64 " + r + ", " + sym + ";");
         line("cvta.local.u64 " + r + ", " + r + ";");
+        b.address = r;
+    }
+    int declare_variable(const Variable& v) {
+        Base b;
+        b.kind = Base::Var;
+        b.var = &v;
+        b.built_in = v.built_in_kind;
+        b.size = type_size(v.type);
+        int i = add_base(std::move(b));
+        if (v.pointer) prov[v.pointer] = Prov{i, 0};
+        return i;
+    }
+    // give slot `off` (bytes) of a built-in input its value: a register cell or a store into the variable's memory
+    void set_built_in(Base& b, uint64_t off, int bytes, const std::string& value) {
+        RC c = class_of_bytes(bytes);
+        if (b.scalarized) {
+            if (!b.slots.count(off)) return;  // never read
+            if (b.slots[off] != (unsigned)bytes) unsupported("built-in '" + b.built_in + "' is read with another width than it has");
+            std::string r = fresh(c);
+            line(std::string("mov.") + mov_type(c) + " " + r + ", " + value + ";");
+            b.cells[off] = r;
+        } else {
+            std::string v = in_register(value, c);
+            line("st.u" + std::to_string(bytes * 8) + " [" + address(b.address, (int64_t)off) + "], " + v + ";");
+        }
     }
 
     // ---- instructions -------------------------------------------------------------------------------------------
@@ -239,33 +451,224 @@ struct Emitter {
             line("// @ \"" + f + "\":" + std::to_string(ins->location.line) + ":" + std::to_string(ins->location.column));
         }
     }
+    static const char* int_suffix(int w) { return w <= 16 ? "16" : w == 32 ? "32" : "64"; }
     void add(const Instr* ins) {
         if (ins->args.size() != 2 || ins->results.size() != 1) throw Error("add takes two arguments and one result");
         const Type* t = ins->results[0]->type;
-        if (t->kind != TypeKind::Int) unsupported("add on non-integer types (the reference defines no float semantics, SURVEY.md §8 a12)");
+        if (t->kind != TypeKind::Int) unsupported("add on non-integer types (the reference defines no float semantics, SURVEY.md §8 a12; version 2 has f_add)");
         if (ins->args[0]->type != t || ins->args[1]->type != t) throw Error("add: operand types differ from the result type");
-        std::string a = use(ins->args[0]), b = use(ins->args[1]);
-        if (a.rfind("0x", 0) == 0) {  // first source operand of add must be a register
-            RC c = reg_class(t);
-            std::string r = fresh(c);
-            line(std::string("mov.") + mov_type(c) + " " + r + ", " + a + ";");
-            a = r;
-        }
+        std::string a = use_reg(ins->args[0]), b = use(ins->args[1]);  // first source operand of add must be a register
         const std::string& d = def(ins->results[0]);
         int w = int_bits(t->int_kind);
-        line(std::string("add.s") + (w <= 16 ? "16 " : w == 32 ? "32 " : "64 ") + d + ", " + a + ", " + b + ";");
+        line(std::string("add.s") + int_suffix(w) + " " + d + ", " + a + ", " + b + ";");
         if (w == 8) line("and.b16 " + d + ", " + d + ", 0xff;");  // i8 lives zero-extended in a 16-bit register
     }
     void load(const Instr* ins) {
         if (ins->args.size() != 1 || ins->results.size() != 1) throw Error("load takes one pointer and one result");
         if (ins->args[0]->type->kind != TypeKind::DataPtr) throw Error("load: the argument is not a data_ptr");
-        std::string addr = use(ins->args[0]);
-        if (addr.rfind("0x", 0) == 0 || addr == "0") {
-            std::string r = fresh(RC::B64);
-            line("mov.b64 " + r + ", " + addr + ";");
-            addr = r;
+        const Value* res = ins->results[0];
+        auto it = prov.find(ins->args[0]);
+        if (it != prov.end()) {
+            Base& b = bases[it->second.base];
+            if (b.scalarized) {  // a register cell
+                const std::string& c = cell(b, (uint64_t)it->second.offset);
+                if (reg_class(res->type) == RC::Pred) line("setp.ne.u16 " + def(res) + ", " + c + ", 0;");
+                else move(res, c);
+                return;
+            }
+            if (b.kind == Base::PushConstants && !pc_param.empty()) {
+                load_scalar(res, pc_param, it->second.offset, ins->align, ".param");
+                return;
+            }
+            load_scalar(res, b.address, it->second.offset, ins->align);
+            return;
         }
-        load_scalar(ins->results[0], addr, ins->align);
+        load_scalar(res, in_register(use(ins->args[0]), RC::B64), 0, ins->align);
+    }
+    void store(const Instr* ins) {
+        const Value *p = ins->args[0], *v = ins->args[1];
+        auto it = prov.find(p);
+        if (it != prov.end()) {
+            Base& b = bases[it->second.base];
+            if (b.kind == Base::PushConstants) unsupported("stores to the push constant block");
+            if (b.scalarized) {
+                const std::string& c = cell(b, (uint64_t)it->second.offset);
+                RC rc = reg_class(v->type);
+                if (rc == RC::Pred) line("selp.u16 " + c + ", 1, 0, " + use(v) + ";");
+                else line(std::string("mov.") + mov_type(rc) + " " + c + ", " + use(v) + ";");
+                return;
+            }
+            store_scalar(v->type, use(v), b.address, it->second.offset, ins->align);
+            return;
+        }
+        store_scalar(v->type, use(v), in_register(use(p), RC::B64), 0, ins->align);
+    }
+    // i8 values live zero-extended in 16-bit registers: a signed reading needs the sign first
+    std::string signed16(const std::string& r8) {
+        std::string t = fresh(RC::B16);
+        line("cvt.s16.s8 " + t + ", " + r8 + ";");
+        return t;
+    }
+    void ext(const Instr* ins) {
+        const ExtOp& op = kExtOps[ins->ext];
+        const std::string name = op.name, ptx = op.ptx;
+        auto res = [&]() -> const std::string& { return def(ins->results[0]); };
+        switch (op.kind) {
+        case ExtKind::IntBinary: {
+            const Type* t = ins->results[0]->type;
+            const int w = int_bits(t->int_kind);
+            const std::string sfx = int_suffix(w);
+            std::string a = use_reg(ins->args[0]), b = use_reg(ins->args[1]);
+            const bool shift = ptx.rfind("sh", 0) == 0;
+            if (shift) {
+                // PTX takes a 32-bit amount and clamps amounts past the width, which is this IR's meaning of an over-wide shift
+                std::string amt = fresh(RC::B32);
+                if (w == 64) {
+                    std::string c = fresh(RC::B64);
+                    line("min.u64 " + c + ", " + b + ", 64;");
+                    line("cvt.u32.u64 " + amt + ", " + c + ";");
+                } else if (w == 32) {
+                    line("mov.b32 " + amt + ", " + b + ";");
+                } else {
+                    line("cvt.u32.u16 " + amt + ", " + b + ";");
+                }
+                if (ptx == "shr.s" && w == 8) a = signed16(a);
+                std::string mn = ptx == "shl" ? "shl.b" + sfx : ptx + sfx;
+                line(mn + " " + res() + ", " + a + ", " + amt + ";");
+            } else if (ptx == "sub" || ptx == "mul.lo") {
+                line(ptx + ".s" + sfx + " " + res() + ", " + a + ", " + b + ";");
+            } else {
+                line(ptx + ".b" + sfx + " " + res() + ", " + a + ", " + b + ";");
+            }
+            if (w == 8) line("and.b16 " + res() + ", " + res() + ", 0xff;");
+            break;
+        }
+        case ExtKind::IntUnary: {
+            const int w = int_bits(ins->results[0]->type->int_kind);
+            std::string a = use_reg(ins->args[0]);
+            line(ptx + (ptx == "neg" ? ".s" : ".b") + int_suffix(w) + " " + res() + ", " + a + ";");
+            if (w == 8) line("and.b16 " + res() + ", " + res() + ", 0xff;");
+            break;
+        }
+        case ExtKind::FloatBinary: {
+            const std::string ft = float_bits(ins->results[0]->type->float_kind) == 64 ? ".f64" : ".f32";
+            line(ptx + ft + " " + res() + ", " + use_float(ins->args[0]) + ", " + use_float(ins->args[1]) + ";");
+            break;
+        }
+        case ExtKind::FloatUnary: {  // neg / abs: the sign bit only (ptxas folds them into operand modifiers); a NaN stays a NaN
+            const std::string ft = float_bits(ins->results[0]->type->float_kind) == 64 ? ".f64" : ".f32";
+            line(ptx + ft + " " + res() + ", " + use_float(ins->args[0]) + ";");
+            break;
+        }
+        case ExtKind::FloatTernary: {
+            const std::string ft = float_bits(ins->results[0]->type->float_kind) == 64 ? ".f64" : ".f32";
+            line(ptx + ft + " " + res() + ", " + use_float(ins->args[0]) + ", " + use_float(ins->args[1]) + ", " + use_float(ins->args[2]) + ";");
+            break;
+        }
+        case ExtKind::IntCompare: {
+            const Type* t = ins->args[0]->type;
+            const int w = t->kind == TypeKind::DataPtr ? 64 : int_bits(t->int_kind);
+            std::string a = use_reg(ins->args[0]), b = use_reg(ins->args[1]);
+            std::string cmp = ptx;  // "eq" "ne" or "lt.u" ...
+            if (cmp == "eq" || cmp == "ne") cmp += ".b";
+            else if (w == 8 && cmp.back() == 's') {
+                a = signed16(a);
+                b = signed16(b);
+            }
+            line("setp." + cmp + int_suffix(w) + " " + res() + ", " + a + ", " + b + ";");
+            break;
+        }
+        case ExtKind::FloatCompare: {
+            const std::string ft = float_bits(ins->args[0]->type->float_kind) == 64 ? ".f64" : ".f32";
+            line("setp." + ptx + ft + " " + res() + ", " + use_float(ins->args[0]) + ", " + use_float(ins->args[1]) + ";");
+            break;
+        }
+        case ExtKind::BoolBinary: line(ptx + ".pred " + res() + ", " + use(ins->args[0]) + ", " + use(ins->args[1]) + ";"); break;
+        case ExtKind::BoolUnary: line("not.pred " + res() + ", " + use(ins->args[0]) + ";"); break;
+        case ExtKind::Select: {
+            const RC rc = reg_class(ins->results[0]->type);
+            const std::string c = use(ins->args[0]);
+            if (rc == RC::Pred) {
+                std::string a = use(ins->args[1]), b = use(ins->args[2]), t1 = fresh(RC::Pred), t2 = fresh(RC::Pred), nc = fresh(RC::Pred);
+                line("and.pred " + t1 + ", " + c + ", " + a + ";");
+                line("not.pred " + nc + ", " + c + ";");
+                line("and.pred " + t2 + ", " + nc + ", " + b + ";");
+                line("or.pred " + res() + ", " + t1 + ", " + t2 + ";");
+            } else {
+                pointer_value_check(ins);
+                line(std::string("selp.") + mov_type(rc) + " " + res() + ", " + use(ins->args[1]) + ", " + use(ins->args[2]) + ", " + c + ";");
+            }
+            break;
+        }
+        case ExtKind::Convert: convert(ins); break;
+        case ExtKind::Store: store(ins); break;
+        case ExtKind::PtrAdd: {
+            if (prov.count(ins->results[0])) break;  // known place: no code until it is used as a value
+            std::string p = in_register(use(ins->args[0]), RC::B64);
+            line("add.s64 " + res() + ", " + p + ", " + use(ins->args[1]) + ";");
+            break;
+        }
+        case ExtKind::SubgroupElect:
+        case ExtKind::SubgroupVote:
+        case ExtKind::SubgroupBallot:
+        case ExtKind::SubgroupBroadcast:
+        case ExtKind::SubgroupShuffle:
+        case ExtKind::SubgroupReduce: subgroup(ins); break;
+        }
+    }
+    void pointer_value_check(const Instr*) {}
+    void convert(const Instr* ins) {
+        const std::string n = kExtOps[ins->ext].name;
+        const Value *a = ins->args[0], *r = ins->results[0];
+        const std::string src = use_reg(a);
+        const std::string& d = def(r);
+        auto ibits = [](const Value* v) { return int_bits(v->type->int_kind); };
+        auto fty = [](const Value* v) { return float_bits(v->type->float_kind) == 64 ? std::string("f64") : std::string("f32"); };
+        if (n == "convert_f_to_u" || n == "convert_f_to_s") {
+            const int w = ibits(r);
+            const char s = n.back();  // 'u' or 's'
+            // round toward zero; PTX saturates out-of-range values and turns NaN into 0, which is this IR's definition
+            line(std::string("cvt.rzi.") + s + std::to_string(w) + "." + fty(a) + " " + d + ", " + src + ";");
+            if (w == 8) line("and.b16 " + d + ", " + d + ", 0xff;");
+        } else if (n == "convert_s_to_f" || n == "convert_u_to_f") {
+            const char s = n[8];  // convert_S_to_f / convert_U_to_f
+            line(std::string("cvt.rn.") + fty(r) + "." + s + std::to_string(ibits(a)) + " " + d + ", " + src + ";");
+        } else if (n == "u_convert" || n == "s_convert") {
+            const char s = n[0];
+            const int wa = ibits(a), wr = ibits(r);
+            if (wa == wr) line(std::string("mov.b") + int_suffix(wr) + " " + d + ", " + src + ";");
+            else line(std::string("cvt.") + s + std::to_string(wr) + "." + s + std::to_string(wa) + " " + d + ", " + src + ";");
+            if (wr == 8) line("and.b16 " + d + ", " + d + ", 0xff;");
+        } else if (n == "f_convert") {
+            if (fty(a) == fty(r)) line("mov.b" + std::string(fty(r) == "f64" ? "64 " : "32 ") + d + ", " + src + ";");
+            else if (fty(r) == "f64") line("cvt.f64.f32 " + d + ", " + src + ";");
+            else line("cvt.rn.f32.f64 " + d + ", " + src + ";");
+        } else {  // bitcast: same size, same register class
+            if (reg_class(a->type) != reg_class(r->type)) throw Error("bitcast between values of different sizes");
+            line(std::string("mov.") + mov_type(reg_class(r->type)) + " " + d + ", " + src + ";");
+        }
+    }
+    void subgroup(const Instr* ins) {
+        if (mode != Mode::Kernel) unsupported("subgroup operations outside compute shaders (fragment invocations are not laid out in subgroups by the rasteriser)");
+        uses_subgroup = true;
+        const ExtOp& op = kExtOps[ins->ext];
+        const std::string ptx = op.ptx;
+        const std::string& d = def(ins->results[0]);
+        const std::string mask = "%kzn_submask";
+        switch (op.kind) {
+        case ExtKind::SubgroupElect: {  // the in-range lanes of a warp start at lane 0
+            std::string l = fresh(RC::B32);
+            line("mov.u32 " + l + ", %laneid;");
+            line("setp.eq.u32 " + d + ", " + l + ", 0;");
+            break;
+        }
+        case ExtKind::SubgroupVote: line("vote.sync." + ptx + ".pred " + d + ", " + use(ins->args[0]) + ", " + mask + ";"); break;
+        case ExtKind::SubgroupBallot: line("vote.sync.ballot.b32 " + d + ", " + use(ins->args[0]) + ", " + mask + ";"); break;
+        case ExtKind::SubgroupBroadcast: line("shfl.sync.idx.b32 " + d + ", " + use_reg(ins->args[0]) + ", 0, 31, " + mask + ";"); break;
+        case ExtKind::SubgroupShuffle: line("shfl.sync." + ptx + ".b32 " + d + ", " + use_reg(ins->args[0]) + ", " + use(ins->args[1]) + ", 31, " + mask + ";"); break;
+        case ExtKind::SubgroupReduce: line("redux.sync.add.s32 " + d + ", " + use_reg(ins->args[0]) + ", " + mask + ";"); break;
+        default: break;
+        }
     }
     void do_break(const Instr* ins) {
         auto it = dests.find(ins->block);
@@ -295,16 +698,11 @@ struct Emitter {
                 int w = int_bits(t->int_kind);
                 uint64_t bits = c.value.bits;
                 if (w < 64) bits &= (1ull << w) - 1;
-                std::string xr = x;
-                if (xr.rfind("0x", 0) == 0) {
-                    RC rc = reg_class(t);
-                    xr = fresh(rc);
-                    line(std::string("mov.") + mov_type(rc) + " " + xr + ", " + x + ";");
-                }
+                std::string xr = in_register(x, reg_class(t));
                 std::string p = fresh(RC::Pred);
                 char imm[32];
                 snprintf(imm, sizeof imm, "0x%llx", (unsigned long long)bits);
-                line(std::string("setp.ne.b") + (w <= 16 ? "16 " : w == 32 ? "32 " : "64 ") + p + ", " + xr + ", " + imm + ";");
+                line(std::string("setp.ne.b") + int_suffix(w) + " " + p + ", " + xr + ", " + imm + ";");
                 line("@" + p + " bra " + skip + ";");
             } else {
                 unsupported("branch on a selector that is neither an integer nor a bool");
@@ -325,6 +723,7 @@ struct Emitter {
                 case Op::Branch: branch(ins); break;
                 case Op::BlockI: nested_block(ins->block, &ins->block->results); break;
                 case Op::LoopI: loop(ins->loop); break;
+                case Op::Ext: ext(ins); break;
             }
         }
         // a block is left only through `break` (block.rs:16-23); control reaching here is what the interpreter rejects
@@ -354,9 +753,33 @@ struct Emitter {
     static std::string sanitize(const std::string& s) {
         std::string o;
         for (char ch : s) o += (isalnum((unsigned char)ch) || ch == '_') ? ch : '_';
+        if (o.size() > 40) o.resize(40);
         return o.empty() ? "anon" : o;
     }
+
+    std::string register_declarations() const {
+        std::ostringstream o;
+        const char* t = tag.c_str();
+        if (n_pred) o << "    .reg .pred %p" << t << "<" << n_pred << ">;\n";
+        if (n16) o << "    .reg .b16 %h" << t << "<" << n16 << ">;\n";
+        if (n32) o << "    .reg .b32 %r" << t << "<" << n32 << ">;\n";
+        if (n64) o << "    .reg .b64 %rd" << t << "<" << n64 << ">;\n";
+        return o.str();
+    }
 };
+
+void check_entry(const Module& m) {
+    const Function* f = m.entry_point;
+    if (!f) throw Error("module has no entry point");
+    if (!f->body) throw Error("entry point has no body");
+    if (!f->params.empty()) Emitter::unsupported("entry points with parameters");
+    if (m.user_inputs.size_variable || m.user_outputs.size_variable) Emitter::unsupported("variable-size interface blocks");
+    const auto& outs = m.user_outputs.members;
+    const auto& rets = f->body->results;
+    if (!rets.empty() && rets.size() != outs.size())
+        throw Error("entry point leaves " + std::to_string(rets.size()) + " values but user_outputs_block has " +
+                    std::to_string(outs.size()) + " members");
+}
 
 }  // namespace
 
@@ -376,21 +799,35 @@ std::string ptx_mangle(const std::string& name) {
 }
 
 std::string emit_ptx(const Module& m, EntryInfo* info) {
+    check_entry(m);
     const Function* f = m.entry_point;
-    if (!f) throw Error("module has no entry point");
-    if (!f->body) throw Error("entry point has no body");
-    if (!f->params.empty()) Emitter::unsupported("entry points with parameters");
-    if (m.user_inputs.size_variable || m.user_outputs.size_variable) Emitter::unsupported("variable-size interface blocks");
     const auto& outs = m.user_outputs.members;
     const auto& rets = f->body->results;
-    if (!rets.empty() && rets.size() != outs.size())
-        throw Error("entry point leaves " + std::to_string(rets.size()) + " values but user_outputs_block has " +
-                    std::to_string(outs.size()) + " members");
 
-    Emitter e(m);
+    Emitter e(m, Mode::Kernel);
     std::string entry = ptx_mangle(f->name);
-    // prologue: linear invocation index over a 2-D folded grid
-    std::string gid = e.fresh(RC::B64), t64 = e.fresh(RC::B64), count = e.fresh(RC::B64), first = e.fresh(RC::B64);
+    // ---- what every pointer is: interface blocks are memory, variables are registers unless their address is needed ----
+    int in_base, out_base;
+    {
+        Base b;
+        b.kind = Base::UserIn;
+        b.size = m.user_inputs.size;
+        b.scalarized = false;
+        in_base = e.add_base(b);
+        b.kind = Base::UserOut;
+        b.size = m.user_outputs.size;
+        out_base = e.add_base(b);
+    }
+    if (m.user_inputs.pointer) e.prov[m.user_inputs.pointer] = Prov{in_base, 0};
+    if (m.user_outputs.pointer) e.prov[m.user_outputs.pointer] = Prov{out_base, 0};
+    std::vector<std::pair<const Variable*, int>> vars;
+    for (auto* list : {&m.built_in_inputs, &m.built_in_outputs, &m.globals, &f->locals})
+        for (auto& v : *list) vars.emplace_back(&v, e.declare_variable(v));
+    e.analyze(f->body);
+    e.finish_analysis();
+
+    // ---- prologue: linear invocation index over a 2-D folded grid ----
+    std::string gid = e.fresh(RC::B64), t64 = e.fresh(RC::B64), count = e.fresh(RC::B64), first = e.fresh(RC::B64), local = e.fresh(RC::B64);
     std::string cx = e.fresh(RC::B32), cy = e.fresh(RC::B32), ncx = e.fresh(RC::B32), nt = e.fresh(RC::B32), tx = e.fresh(RC::B32);
     std::string oob = e.fresh(RC::Pred);
     e.line("mov.u32 " + cx + ", %ctaid.x;");
@@ -408,25 +845,74 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
     e.line("ld.param.u64 " + count + ", [kzn_invocation_count];");
     e.line("setp.ge.u64 " + oob + ", " + gid + ", " + count + ";");
     e.line("@" + oob + " ret;");
+    e.line("mov.b64 " + local + ", " + gid + ";");  // index within this launch (subgroups are cut from it)
     e.line("ld.param.u64 " + first + ", [kzn_first_invocation];");
     e.line("add.u64 " + gid + ", " + gid + ", " + first + ";");
     // interface block pointers of this invocation
-    auto bind_block = [&](const InterfaceBlock& b, const char* param) -> std::string {
-        std::string r = b.pointer ? e.def(b.pointer) : e.fresh(RC::B64);
+    auto bind_block = [&](const InterfaceBlock& b, const char* param, int base) -> std::string {
+        std::string r = e.fresh(RC::B64);
         e.line(std::string("ld.param.u64 ") + r + ", [" + param + "];");
         if (b.size) {
             std::string o = e.fresh(RC::B64);
             e.line("mul.lo.u64 " + o + ", " + gid + ", " + std::to_string(b.size) + ";");
             e.line("add.u64 " + r + ", " + r + ", " + o + ";");
         }
+        e.bases[base].address = r;
         return r;
     };
-    bind_block(m.user_inputs, "kzn_user_inputs_base");
-    std::string out_ptr = bind_block(m.user_outputs, "kzn_user_outputs_base");
-    for (auto& v : m.built_in_inputs) e.variable(v);
-    for (auto& v : m.built_in_outputs) e.variable(v);
-    for (auto& v : m.globals) e.variable(v);
-    for (auto& v : f->locals) e.variable(v);
+    bind_block(m.user_inputs, "kzn_user_inputs_base", in_base);
+    std::string out_ptr = bind_block(m.user_outputs, "kzn_user_outputs_base", out_base);
+    e.pc_param = "kzn_push_constants";
+    if (e.pc_base >= 0) e.bases[e.pc_base].address = "kzn_push_constants";
+    for (auto& v : vars) e.variable(*v.first, v.second);
+    // built-in inputs (version 2)
+    for (auto& v : vars) {
+        Base& b = e.bases[v.second];
+        if (b.built_in.empty() || b.built_in == "vertex_position") continue;
+        if (b.built_in == "global_invocation_id") {
+            // x fastest: id = (g % sx, (g / sx) % sy, g / (sx * sy)) with sx, sy the global size of the dispatch in x and y
+            std::string sx = e.fresh(RC::B64), sy = e.fresh(RC::B64), q = e.fresh(RC::B64), x = e.fresh(RC::B64), y = e.fresh(RC::B64), z = e.fresh(RC::B64);
+            std::string x32 = e.fresh(RC::B32), y32 = e.fresh(RC::B32), z32 = e.fresh(RC::B32);
+            e.line("ld.param.u64 " + sx + ", [kzn_global_size_x];");
+            e.line("ld.param.u64 " + sy + ", [kzn_global_size_y];");
+            e.line("rem.u64 " + x + ", " + gid + ", " + sx + ";");
+            e.line("div.u64 " + q + ", " + gid + ", " + sx + ";");
+            e.line("rem.u64 " + y + ", " + q + ", " + sy + ";");
+            e.line("div.u64 " + z + ", " + q + ", " + sy + ";");
+            e.line("cvt.u32.u64 " + x32 + ", " + x + ";");
+            e.line("cvt.u32.u64 " + y32 + ", " + y + ";");
+            e.line("cvt.u32.u64 " + z32 + ", " + z + ";");
+            // vkCmdDispatchBase: the first workgroup's id times LocalSize
+            std::string bx = e.fresh(RC::B32), by = e.fresh(RC::B32), bz = e.fresh(RC::B32);
+            e.line("ld.param.u32 " + bx + ", [kzn_global_base];");
+            e.line("ld.param.u32 " + by + ", [kzn_global_base+4];");
+            e.line("ld.param.u32 " + bz + ", [kzn_global_base+8];");
+            e.line("add.u32 " + x32 + ", " + x32 + ", " + bx + ";");
+            e.line("add.u32 " + y32 + ", " + y32 + ", " + by + ";");
+            e.line("add.u32 " + z32 + ", " + z32 + ", " + bz + ";");
+            e.set_built_in(b, 0, 4, x32);
+            e.set_built_in(b, 4, 4, y32);
+            e.set_built_in(b, 8, 4, z32);
+        } else if (b.built_in == "subgroup_local_invocation_id") {
+            std::string l = e.fresh(RC::B32);
+            e.line("mov.u32 " + l + ", %laneid;");
+            e.set_built_in(b, 0, 4, l);
+        } else if (b.built_in == "subgroup_size") {
+            e.set_built_in(b, 0, 4, "32");
+        } else if (b.built_in == "descriptor_table") {
+            std::string r = e.fresh(RC::B64);
+            e.line("ld.param.u64 " + r + ", [kzn_descriptor_table];");
+            e.set_built_in(b, 0, 8, r);
+        } else if (b.built_in == "push_constants") {
+            if (!b.scalarized) Emitter::unsupported("the push_constants variable may only be loaded from");
+            for (auto& s : b.slots)
+                if (s.first != 0 || s.second != 8) Emitter::unsupported("the push_constants variable holds one data_ptr");
+        } else if (b.built_in == "frag_coord") {
+            Emitter::unsupported("frag_coord in a compute entry point");
+        }
+    }
+    std::string body_prologue = e.body.str();
+    e.body.str("");
 
     e.nested_block(f->body, &f->body->results);
     // epilogue: the body's results are the invocation's outputs
@@ -438,26 +924,141 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
         uint64_t low = outs[i].offset ? (outs[i].offset & (~outs[i].offset + 1)) : align;
         uint64_t eff = low < align ? low : align;
         if (m.user_outputs.size % align) eff = 1;
-        e.store_scalar(t, e.def(rets[i]), out_ptr, outs[i].offset, eff);
+        e.store_scalar(t, e.def(rets[i]), out_ptr, (int64_t)outs[i].offset, eff);
     }
     e.line("ret;");
+
+    std::ostringstream sub;
+    if (e.uses_subgroup) {
+        // member mask of the subgroup operations: the lanes of this warp that are inside the launch (lanes 0 .. n-1)
+        std::string l = e.fresh(RC::B32), l64 = e.fresh(RC::B64), base = e.fresh(RC::B64), left = e.fresh(RC::B64), n = e.fresh(RC::B32), full = e.fresh(RC::Pred);
+        sub << "    mov.u32 " << l << ", %laneid;\n    cvt.u64.u32 " << l64 << ", " << l << ";\n    sub.u64 " << base << ", " << local << ", " << l64 << ";\n"
+            << "    sub.u64 " << left << ", " << count << ", " << base << ";\n    min.u64 " << left << ", " << left << ", 32;\n    cvt.u32.u64 " << n << ", " << left << ";\n"
+            << "    setp.ge.u32 " << full << ", " << n << ", 32;\n    shl.b32 %kzn_submask, 1, " << n << ";\n    sub.u32 %kzn_submask, %kzn_submask, 1;\n"
+            << "    @" << full << " mov.b32 %kzn_submask, 0xffffffff;\n";
+    }
 
     std::ostringstream o;
     o << "//\n// Generated by kazan_b200 shader-compiler-backend-ptx from shader-compiler-ir\n//\n";
     o << ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
     o << ".visible .entry " << entry
       << "(\n    .param .u64 kzn_user_inputs_base,\n    .param .u64 kzn_user_outputs_base,\n"
-         "    .param .u64 kzn_invocation_count,\n    .param .u64 kzn_first_invocation\n)\n{\n";
-    if (e.n_pred) o << "    .reg .pred %p<" << e.n_pred << ">;\n";
-    if (e.n16) o << "    .reg .b16 %h<" << e.n16 << ">;\n";
-    if (e.n32) o << "    .reg .b32 %r<" << e.n32 << ">;\n";
-    if (e.n64) o << "    .reg .b64 %rd<" << e.n64 << ">;\n";
-    o << e.locals.str() << "\n" << e.body.str() << "}\n";
+         "    .param .u64 kzn_invocation_count,\n    .param .u64 kzn_first_invocation,\n"
+         "    .param .u64 kzn_global_size_x,\n    .param .u64 kzn_global_size_y,\n    .param .u64 kzn_descriptor_table,\n"
+         "    .param .align 16 .b8 kzn_global_base[16],\n    .param .align 16 .b8 kzn_push_constants[128]\n)\n{\n";
+    o << e.register_declarations();
+    if (e.uses_subgroup) o << "    .reg .b32 %kzn_submask;\n";
+    o << e.locals.str() << "\n" << body_prologue << sub.str() << e.prologue.str() << e.body.str() << "}\n";
     if (info) {
         info->entry_name = entry;
         info->inputs_size = m.user_inputs.size;
         info->outputs_size = m.user_outputs.size;
+        info->uses_global_invocation_id = false;
+        for (auto& v : vars)
+            if (e.bases[v.second].built_in == "global_invocation_id") info->uses_global_invocation_id = true;
     }
+    return o.str();
+}
+
+// ---- fragment shaders ------------------------------------------------------------------------------------------------
+
+FragmentInterface fragment_interface(const Module& m) {
+    check_entry(m);
+    FragmentInterface fi;
+    if (m.user_inputs.size > 16) Emitter::unsupported("fragment shaders with more than four 32-bit interpolated inputs (the rasteriser interpolates one vec4)");
+    for (auto& mem : m.user_inputs.members)
+        if (mem.type->kind != TypeKind::Float || float_bits(mem.type->float_kind) != 32 || mem.offset % 4)
+            Emitter::unsupported("interpolated fragment inputs other than f32 at 4-byte offsets");
+    if (m.user_outputs.size != 16 || m.user_outputs.members.size() != 4) Emitter::unsupported("fragment shaders must write one vec4 colour (four f32 members of user_outputs_block)");
+    for (size_t i = 0; i < 4; ++i)
+        if (m.user_outputs.members[i].type->kind != TypeKind::Float || float_bits(m.user_outputs.members[i].type->float_kind) != 32 || m.user_outputs.members[i].offset != 4 * i)
+            Emitter::unsupported("fragment output members must be f32 at offsets 0, 4, 8, 12");
+    // one dry run tells what the shader reads
+    FragmentSite site;
+    site.id = 0;
+    site.in.assign(10, "0");
+    site.out = {"%o0", "%o1", "%o2", "%o3"};
+    FragmentInterface probe;
+    emit_fragment_inline(m, site, &probe);
+    fi = probe;
+    return fi;
+}
+
+std::string emit_fragment_inline(const Module& m, const FragmentSite& site, FragmentInterface* info) {
+    check_entry(m);
+    const Function* f = m.entry_point;
+    if (site.in.size() != 10 || site.out.size() != 4) throw Error("internal: a fragment call site has 10 inputs and 4 outputs");
+    Emitter e(m, Mode::Inline, "_fs" + std::to_string(site.id) + "_");
+    int in_base, out_base;
+    {
+        Base b;
+        b.kind = Base::UserIn;
+        b.size = 16;
+        in_base = e.add_base(b);
+        b.kind = Base::UserOut;
+        b.size = 16;
+        out_base = e.add_base(b);
+    }
+    if (m.user_inputs.pointer) e.prov[m.user_inputs.pointer] = Prov{in_base, 0};
+    if (m.user_outputs.pointer) e.prov[m.user_outputs.pointer] = Prov{out_base, 0};
+    std::vector<std::pair<const Variable*, int>> vars;
+    for (auto* list : {&m.built_in_inputs, &m.built_in_outputs, &m.globals, &f->locals})
+        for (auto& v : *list) vars.emplace_back(&v, e.declare_variable(v));
+    e.analyze(f->body);
+    e.finish_analysis();
+    if (!e.bases[in_base].scalarized || !e.bases[out_base].scalarized)
+        Emitter::unsupported("fragment shaders must access their interface blocks as pointer + constant (the blocks live in registers)");
+    for (auto& s : e.bases[in_base].slots)
+        if (s.second != 4 || s.first % 4) Emitter::unsupported("interpolated inputs are read as 32-bit values");
+    for (auto& s : e.bases[out_base].slots)
+        if (s.second != 4 || s.first % 4) Emitter::unsupported("fragment outputs are written as 32-bit values");
+
+    // inputs: site.in = frag_coord x y z w, the four interpolated inputs, push constant pointer, descriptor table pointer
+    for (auto& s : e.bases[in_base].slots) {
+        std::string r = e.fresh(RC::B32);
+        e.line("mov.b32 " + r + ", " + site.in[4 + s.first / 4] + ";");
+        e.bases[in_base].cells[s.first] = r;
+    }
+    e.pc_param = site.push_constants_param;
+    if (e.pc_base >= 0 && e.pc_param.empty()) e.bases[e.pc_base].address = e.in_register(site.in[8], RC::B64);
+    for (auto& v : vars) e.variable(*v.first, v.second);
+    for (auto& v : vars) {
+        Base& b = e.bases[v.second];
+        if (b.built_in.empty() || b.built_in == "vertex_position") continue;
+        if (b.built_in == "frag_coord") {
+            for (int k = 0; k < 4; ++k) e.set_built_in(b, 4 * k, 4, site.in[k]);
+        } else if (b.built_in == "descriptor_table") {
+            e.set_built_in(b, 0, 8, site.in[9]);
+        } else if (b.built_in == "push_constants") {
+            if (!b.scalarized) Emitter::unsupported("the push_constants variable may only be loaded from");
+        } else {
+            Emitter::unsupported("built-in '" + b.built_in + "' in a fragment shader");
+        }
+    }
+    std::string body_prologue = e.body.str();
+    e.body.str("");
+    e.nested_block(f->body, &f->body->results);
+    // outputs: the cells of user_outputs_block, overridden by the body's results when it returns values
+    const auto& rets = f->body->results;
+    for (int k = 0; k < 4; ++k) {
+        if (site.out[k].empty()) continue;
+        if (k < (int)rets.size()) {
+            if (Emitter::reg_class(rets[k]->type) != RC::B32) throw Error("fragment shader result is not a 32-bit value");
+            e.line("mov.b32 " + site.out[k] + ", " + e.def(rets[k]) + ";");
+        } else {
+            auto c = e.bases[out_base].cells.find(4 * k);
+            e.line("mov.b32 " + site.out[k] + ", " + (c != e.bases[out_base].cells.end() ? c->second : std::string("0")) + ";");
+        }
+    }
+    if (info) {
+        info->reads_inputs = e.reads_user_inputs;
+        info->reads_frag_coord = e.reads_frag_coord;
+        info->reads_frag_coord_zw = e.reads_frag_coord_zw;
+        for (auto& b : e.bases)  // a frag_coord whose address is taken is read in ways the analysis cannot see
+            if (b.built_in == "frag_coord" && !b.scalarized) info->reads_frag_coord_zw = true;
+    }
+    std::ostringstream o;
+    o << "    {\n" << e.register_declarations() << e.locals.str() << e.prologue.str() << body_prologue << e.body.str() << "    }\n";
     return o.str();
 }
 

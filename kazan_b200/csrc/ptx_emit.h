@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "ir.h"
 
@@ -17,12 +18,33 @@ struct Unsupported : Error {
 struct EntryInfo {
     std::string entry_name;  // PTX symbol of the kernel
     uint64_t inputs_size = 0, outputs_size = 0;
+    bool uses_global_invocation_id = false;
+};
+
+// One place where the raster kernels call the fragment program: operands of the surrounding PTX code.
+struct FragmentSite {
+    int id = 0;                    // makes the copy's registers and labels unique
+    std::vector<std::string> in;   // 10: frag_coord x y z w, interpolated inputs 0..3, push constant pointer, descriptor table pointer
+    std::vector<std::string> out;  // 4 registers that receive the colour ("" = unused)
+    // when the call is inside a kernel entry: "<entry>_param_0+<offset>" of the push constant block in the kernel's
+    // parameter space, so that the shader's push constant loads are ld.param (constant bank operands); otherwise the block
+    // is read through the generic pointer in[8]
+    std::string push_constants_param;
+};
+struct FragmentInterface {
+    bool reads_inputs = false;      // the shader loads from user_inputs_block (the rasteriser must interpolate)
+    bool reads_frag_coord = false;
+    bool reads_frag_coord_zw = false;  // depth or 1/w: the rasteriser must evaluate the fragment's barycentrics
 };
 
 // PTX symbol for an IR / backend function name (backend.rs:444-459 allows '.', '-', '$' which PTX does not)
 std::string ptx_mangle(const std::string& name);
 // the module's entry point as one `.visible .entry`; ABI in include/kazan_b200_backend.h
 std::string emit_ptx(const Module& m, EntryInfo* info);
+// a fragment shader's entry point as one PTX scope for `site` (see ptx_emit.cpp); fragment_interface checks that the module
+// has the shape of a fragment shader (<= 4 f32 inputs, one vec4 colour output) and tells what it reads
+std::string emit_fragment_inline(const Module& m, const FragmentSite& site, FragmentInterface* info);
+FragmentInterface fragment_interface(const Module& m);
 
 // shader-compiler-translate-spirv-to-ir/src/lib.rs:190-215 for the shaders that crate translates
 // (control-flow-free entry points); throws Unsupported for what the reference leaves todo!()

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cstddef>
 #include <new>
 
 #include "kzn_internal.h"
@@ -138,6 +139,11 @@ struct DrawParams {
     uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
     uint32_t fused_setup;                          // direct draws of <= 32 triangles: raster_direct_kernel makes the records itself
+    // compiled fragment programs (KZN_FS_COMPILED): what vkCmdBindDescriptorSets / vkCmdPushConstants left on the queue, and
+    // what the program reads (bit 0: it needs interpolated inputs or the z / w of frag_coord, so no coverage shortcut applies)
+    uint32_t fs_flags;
+    unsigned long long descriptor_table;
+    unsigned char push_constants[KZN_MAX_PUSH_CONSTANTS_SIZE];
 };
 
 // ---- setup ------------------------------------------------------------------------------------------------
@@ -426,6 +432,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 
 // ---- binning --------------------------------------------------------------------------------------------------
 
+#ifndef KZN_FS_TEMPLATE
 // second binning pass: one thread per triangle record writes its id into every tile segment it overlaps
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
@@ -480,6 +487,8 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
         if (p.stats) atomicAdd(&p.stats[3], (unsigned long long)carry);
     }
 }
+
+#endif  // !KZN_FS_TEMPLATE
 
 // ---- per-fragment helpers ------------------------------------------------------------------------------------------
 
@@ -754,6 +763,50 @@ __device__ __forceinline__ void interpolate_color(const float iw[3], const float
     for (int ch = 0; ch < 4; ++ch) src[ch] = __fmul_rn(fmaf(l2, col[2][ch], fmaf(l1, col[1][ch], l0 * col[0][ch])), rden);
 }
 
+#ifdef KZN_FS_TEMPLATE
+// The compiled fragment program: this translation unit is also compiled to PTX with KZN_FS_TEMPLATE (build.py), where the
+// fragment program is a call to this external function; at vkCreateGraphicsPipelines time (kzn_fragment_program_create,
+// backend.cpp) every call is replaced by the shader's own PTX, generated from its shader-compiler-ir module by ptx_emit.cpp,
+// and the result is loaded with cuModuleLoadDataEx.  Arguments: frag_coord (x, y = pixel centre, z = depth, w = 1/w), the
+// four interpolated inputs, the push constant block, the descriptor table.
+extern "C" __device__ float4 kzn_fs_main(float x, float y, float z, float w, float in0, float in1, float in2, float in3, const void* push_constants,
+                                         const void* descriptor_table);
+#endif
+
+// does fragment program FS read anything that needs the fragment's barycentrics (interpolated inputs, depth, 1/w)?  When it
+// does not, fully covered spans and blocks need no per-pixel coverage arithmetic at all.
+template <uint32_t FS>
+__device__ __forceinline__ bool fs_needs_interpolants(const DrawParams& p) {
+    return FS == KZN_FS_VERTEX_COLOR ? true : FS == KZN_FS_PROCEDURAL_ORBIT ? false : (p.fs_flags & 1u) != 0;
+}
+
+// one invocation of fragment program FS: pixel (px, py), depth z, barycentrics l0..l2 over the triangle's per-vertex 1/w and
+// colour/w (R6)
+template <uint32_t FS>
+__device__ __forceinline__ void run_fragment_program(const DrawParams& p, int px, int py, float z, const float iw[3], const float col[3][4],
+                                                     float l0, float l1, float l2, float src[4]) {
+    if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+        fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
+    } else if (FS == KZN_FS_VERTEX_COLOR) {
+        interpolate_color(iw, col, l0, l1, l2, src);
+    } else {
+#ifdef KZN_FS_TEMPLATE
+        float in[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float w = 1.0f;
+        if (fs_needs_interpolants<FS>(p)) {
+            interpolate_color(iw, col, l0, l1, l2, in);
+            w = fmaf(l2, iw[2], fmaf(l1, iw[1], l0 * iw[0]));
+        }
+        const float4 c = kzn_fs_main((float)px + 0.5f, (float)py + 0.5f, z, w, in[0], in[1], in[2], in[3], p.push_constants,
+                                     reinterpret_cast<const void*>(p.descriptor_table));
+        src[0] = c.x;
+        src[1] = c.y;
+        src[2] = c.z;
+        src[3] = c.w;
+#endif
+    }
+}
+
 // Depth test, fragment program and blend for the first n (<= 32) fragments queued for a warp's brick, one per lane.  A
 // queue entry names the chunk slot of its triangle and the pixel; the edge functions at the pixel are rebuilt from the
 // triangle's BrickEdge (exact 32-bit integers), then barycentrics and depth (R6).  Fragments of the batch that hit the same
@@ -795,8 +848,7 @@ __device__ __noinline__ uint32_t shade_queue(const DrawParams& p, BrickState& bs
                 bs.depth_dirty[pix] = 1;
             }
             if (has_color) {
-                if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
-                else interpolate_color(t.iw, t.col, l0, l1, l2, src);
+                run_fragment_program<FS>(p, px, py, z, t.iw, t.col, l0, l1, l2, src);
                 const uint32_t dst = NEED_DST ? bs.color[pix] : 0u;
                 bs.color[pix] = output_merge_lut<NEED_DST>(p.st, lut, src, dst);
                 bs.color_dirty[pix] = 1;
@@ -806,8 +858,7 @@ __device__ __noinline__ uint32_t shade_queue(const DrawParams& p, BrickState& bs
         return n_passed;
     }
     if (have && has_color) {  // several fragments per pixel in this batch: shade up front, all lanes together
-        if (FS == KZN_FS_PROCEDURAL_ORBIT) fs_procedural_orbit(px, py, p.inv_fb_w, p.inv_fb_h, src);
-        else interpolate_color(t.iw, t.col, l0, l1, l2, src);
+        run_fragment_program<FS>(p, px, py, z, t.iw, t.col, l0, l1, l2, src);
     }
     for (uint32_t rk = 0; rk <= max_rank; ++rk) {
         if (have && rank == rk) {
@@ -935,7 +986,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
     live = 0;
     zwrite = 0;
     bool trivial = false;
-    if (UNIFORM_ROW && FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test && (bias & 8u)) {
+    if (UNIFORM_ROW && !fs_needs_interpolants<FS>(p) && !depth_test && (bias & 8u)) {
         // Trivial accept of the whole span: the covered pixels of a row are an interval (each biased edge test is a
         // half-plane), so if both end pixels of the span are covered, every pixel between them is; the depth clip cannot
         // reject (bit 3, set at setup) and this fragment program reads no interpolant — no per-pixel coverage work at all.
@@ -951,7 +1002,9 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             n_passed += __popc(live);
         }
     }
-    float l0[PX], l1[PX], l2[PX];
+    float l0[PX], l1[PX], l2[PX], zf[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) l0[k] = l1[k] = l2[k] = zf[k] = 0.0f;  // a trivially accepted span has no barycentrics (and its program reads none)
     if (!trivial) {
         const long long b0 = bias & 1u, b1 = (bias >> 1) & 1u, b2 = (bias >> 2) & 1u;
         const long long r0 = (long long)t.b[0] * sy + t.c[0], r1 = (long long)t.b[1] * sy + t.c[1], r2 = (long long)t.b[2] * sy + t.c[2];
@@ -967,6 +1020,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             l1[k] = (float)f1 * inv2a;
             l2[k] = (float)f2 * inv2a;
             const float z = fmaf(l2[k], t.z[2], fmaf(l1[k], t.z[1], l0[k] * t.z[0]));
+            zf[k] = z;
             cov = cov && z >= p.zclip_lo && z <= p.zclip_hi;  // R3
             if (cov) {
                 ++n_covered;
@@ -989,7 +1043,7 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             else fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
         } else {
 #pragma unroll
-            for (int k = 0; k < PX; ++k) interpolate_color(t.iw, t.col, l0[k], l1[k], l2[k], src[k]);
+            for (int k = 0; k < PX; ++k) run_fragment_program<FS>(p, px0 + k, py, zf[k], t.iw, t.col, l0[k], l1[k], l2[k], src[k]);
         }
 #pragma unroll
         for (int k = 0; k < PX; ++k) {  // branch-free: pixels not live keep their value
@@ -1059,7 +1113,7 @@ __device__ __noinline__ void shade_wide(const DrawParams& p, BrickState& bs, con
 // *Block-level trivial accept*: lane i tests triangle i (the first 32) at the corner of the block where each edge function
 // is smallest; if all three are positive the whole block is inside the triangle and its rows skip coverage entirely.
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(const __grid_constant__ DrawParams p) {
+__device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
     kzn_pdl_wait();
     __shared__ float unorm_lut[NEED_DST ? 256 : 1];
     const uint32_t lane = threadIdx.x;
@@ -1125,7 +1179,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
         }
         const int row0 = (int)(p.tile_y0 + (uint32_t)brow) * kDirectRows;
         uint32_t full = 0;  // bit i: triangle i covers every pixel centre of this block (and needs no per-fragment work)
-        if (FS == KZN_FS_PROCEDURAL_ORBIT && !depth_test) {
+        if (!fs_needs_interpolants<FS>(p) && !depth_test) {
             bool ok = false;
             if (lane < p.total_tris) {
                 const TriRec& t = recs[lane];
@@ -1144,7 +1198,7 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
             full = __ballot_sync(0xffffffffu, ok);
         }
         const int r_lo = max(row0, p.cy0), r_hi = min(row0 + kDirectRows - 1, p.cy1);
-        if (FS == KZN_FS_PROCEDURAL_ORBIT && NEED_DST == kDstNone) {
+        if (FS != KZN_FS_VERTEX_COLOR && NEED_DST == kDstNone) {
             // The block is nothing but shader work when the LAST triangle of the draw covers it completely and opaquely
             // (whatever earlier triangles produced is overwritten; statistics still need their fragments, so with
             // statistics on this is limited to single-triangle draws) and the block lies inside the clip rectangle:
@@ -1156,7 +1210,16 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
 #pragma unroll 1
                 for (int r = 0; r < kDirectRows; ++r, a += pitch) {
                     uint32_t out[kDirectPx];
-                    fs_procedural_orbit_rgba8<kDirectPx>(cxp, row0 + r, p.inv_fb_h, out);
+                    if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                        fs_procedural_orbit_rgba8<kDirectPx>(cxp, row0 + r, p.inv_fb_h, out);
+                    } else {  // a compiled program that reads no interpolant (full is zero otherwise): its colour, converted (E.1)
+#pragma unroll
+                        for (int k = 0; k < kDirectPx; ++k) {
+                            float src[4];
+                            run_fragment_program<FS>(p, px0 + k, row0 + r, 0.0f, nullptr, nullptr, 0.0f, 0.0f, 0.0f, src);
+                            out[k] = output_merge_lut<kDstNone>(p.st, unorm_lut, src, 0u);
+                        }
+                    }
 #pragma unroll
                     for (int h = 0; h < kDirectPx / 4; ++h)
                         *reinterpret_cast<uint4*>(a + 16 * h) = make_uint4(out[4 * h], out[4 * h + 1], out[4 * h + 2], out[4 * h + 3]);
@@ -1206,13 +1269,19 @@ __global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(co
             const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
             uint32_t cdirty = 0, zdirty = 0;
             for (uint32_t i = 0; i < p.total_tris; ++i) {
-                if (FS == KZN_FS_PROCEDURAL_ORBIT && i < 32u && (full >> i & 1u)) {  // warp-uniform
+                if (FS != KZN_FS_VERTEX_COLOR && i < 32u && (full >> i & 1u)) {  // warp-uniform
                     // block-level trivial accept: every pixel of the row inside the clip rectangle is covered and passes
                     n_covered += __popc(quad_clip);
                     n_passed += __popc(quad_clip);
                     if (has_color && quad_clip) {
                         float src[kDirectPx][4];
-                        fs_procedural_orbit_n<kDirectPx>(cxp, py, p.inv_fb_h, src);
+                        if (FS == KZN_FS_PROCEDURAL_ORBIT) {
+                            fs_procedural_orbit_n<kDirectPx>(cxp, py, p.inv_fb_h, src);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kDirectPx; ++k)
+                                run_fragment_program<FS>(p, px0 + k, py, 0.0f, nullptr, nullptr, 0.0f, 0.0f, 0.0f, src[k]);
+                        }
 #pragma unroll
                         for (int k = 0; k < kDirectPx; ++k) {
                             const uint32_t merged = output_merge_lut<NEED_DST>(p.st, unorm_lut, src[k], col[k]);
@@ -1430,6 +1499,7 @@ __device__ __forceinline__ uint8_t* tile_masks(const DrawParams& p, uint32_t til
     return p.bin_masks + (((size_t)beg + 3u) & ~(size_t)3u) + 4u * (size_t)tile;
 }
 
+#ifndef KZN_FS_TEMPLATE
 // (tile_sort_warp_kernel: frames of many tiles with short lists; tile_sort_cta_kernel below: fewer tiles with long lists.)
 // One warp per 64 x 32-pixel screen tile: the binning atomics deliver the tile's triangle ids in arbitrary order; they are
 // sorted here (ascending = primitive order, R7) and each entry's pixel box is looked at once, for all eight bricks of the
@@ -1576,6 +1646,8 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
     }
 }
 
+#endif  // !KZN_FS_TEMPLATE
+
 // Persistent, independent warps (kRasterWarps per CTA share nothing but the UNORM8 table): a warp takes one 16 x 16 brick
 // at a time from a global work counter — unit u = brick u % 8 of tile u / 8 — until none are left, so no warp waits for
 // the slowest brick of its tile and the last wave of a frame is bricks, not tiles.  The brick's colour and depth live in
@@ -1584,7 +1656,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
 // meets one or two bricks but three or four rows, and everything that is done per (triangle, warp) — record copy, edge
 // derivation, prefix sums — is paid that many times.
 template <uint32_t FS, int NEED_DST>
-__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
+__device__ __forceinline__ void raster_body(const DrawParams& p) {
     kzn_pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterShared& sh = *reinterpret_cast<RasterShared*>(smem_raw);
@@ -1780,7 +1852,35 @@ __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel
     }
 }
 
+#ifndef KZN_FS_TEMPLATE
+template <uint32_t FS, int NEED_DST>
+__global__ void __launch_bounds__(32, kDirectWarpsPerSM) raster_direct_kernel(const __grid_constant__ DrawParams p) {
+    raster_direct_body<FS, NEED_DST>(p);
+}
+template <uint32_t FS, int NEED_DST>
+__global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) raster_kernel(const __grid_constant__ DrawParams p) {
+    raster_body<FS, NEED_DST>(p);
+}
+#endif
+
 }  // namespace
+
+#ifdef KZN_FS_TEMPLATE
+// The PTX templates of the two raster kernels for compiled fragment programs, one per destination mode (see
+// run_fragment_program): extern "C" names, so that backend.cpp finds them in the module it builds.
+#define KZN_FS_TEMPLATE_KERNELS(MODE)                                                                                              \
+    extern "C" __global__ void __launch_bounds__(32, kDirectWarpsPerSM) kzn_fs_raster_direct_##MODE(const __grid_constant__ DrawParams p) { \
+        raster_direct_body<KZN_FS_COMPILED, MODE>(p);                                                                              \
+    }                                                                                                                              \
+    extern "C" __global__ void __launch_bounds__(kRasterThreads, KZN_RASTER_CTAS) kzn_fs_raster_##MODE(const __grid_constant__ DrawParams p) { \
+        raster_body<KZN_FS_COMPILED, MODE>(p);                                                                                     \
+    }
+KZN_FS_TEMPLATE_KERNELS(0)
+KZN_FS_TEMPLATE_KERNELS(1)
+KZN_FS_TEMPLATE_KERNELS(2)
+#else  // everything below is host code and the kernels with built-in fragment programs
+
+extern "C" const uint32_t kzn_draw_params_push_constants_offset = (uint32_t)offsetof(DrawParams, push_constants);
 
 // ---- scratch --------------------------------------------------------------------------------------------------------------
 
@@ -1838,7 +1938,7 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
                      const KznVertexInput* vi, uint32_t* W, uint32_t* H) {
     KZN_VALID(st && fb && vp && sc && vi, "draw: null argument");
     KZN_REQUIRE(st->vertex_program == KZN_VS_PASSTHROUGH, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown vertex program %u", st->vertex_program);
-    KZN_REQUIRE(st->fragment_program <= KZN_FS_PROCEDURAL_ORBIT, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown fragment program %u",
+    KZN_REQUIRE(st->fragment_program <= KZN_FS_COMPILED, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown fragment program %u",
                 st->fragment_program);
     KZN_VALID(st->cull_mode <= 3 && st->front_face <= 1 && st->depth_compare_op <= 7, "draw: bad rasterization / depth state");
     KZN_REQUIRE(st->src_color_blend_factor <= 9 && st->dst_color_blend_factor <= 9 && st->src_alpha_blend_factor <= 9 &&
@@ -2021,6 +2121,12 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     p.tiles_y = (uint32_t)p.cy1 / kTileH - p.tile_y0 + 1;
     KZN_REQUIRE(p.tiles_y <= 65535u, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer taller than 524280 rows");
     p.stats = reinterpret_cast<unsigned long long*>(q->stats_address);
+    if (st->fragment_program == KZN_FS_COMPILED) {
+        KZN_VALID(q->fragment_program, "draw: fragment_program is KZN_FS_COMPILED but no program is bound (kzn_cmd_bind_fragment_program)");
+        p.fs_flags = kzn_fragment_program_flags(q->fragment_program);
+        p.descriptor_table = q->descriptor_table[0];  // VK_PIPELINE_BIND_POINT_GRAPHICS
+        memcpy(p.push_constants, q->push_constants, sizeof p.push_constants);
+    }
 
     size_t tiles = (size_t)p.tiles_x * p.tiles_y;
     p.binned = total > kDirectMax;
@@ -2093,7 +2199,11 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         const uint64_t blocks = (uint64_t)p.tiles_x * p.tiles_y, resident = (uint64_t)q->device->sm_count * kDirectWarpsPerSM;
         KZN_REQUIRE(blocks <= 0xffffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer too large");
         grid = dim3((uint32_t)(blocks < resident ? blocks : resident));
-        KZN_RASTER_LAUNCH(raster_direct_kernel, 32, 0);
+        if (st->fragment_program == KZN_FS_COMPILED) {
+            if ((r = kzn_fragment_program_launch(q->fragment_program, 0, mode, grid.x, 32, 0, q->stream, &p, sizeof p))) return r;
+        } else {
+            KZN_RASTER_LAUNCH(raster_direct_kernel, 32, 0);
+        }
         return kzn_launched(q, "raster_direct_kernel");
     }
     {   // persistent warps over a brick counter: as many CTAs as fit on the device, or fewer when the frame is small
@@ -2102,7 +2212,11 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         const uint64_t ctas = (units + kRasterWarps - 1) / kRasterWarps;
         grid = dim3((uint32_t)(ctas < resident ? ctas : resident));
     }
-    KZN_RASTER_LAUNCH(raster_kernel, kRasterThreads, smem);
+    if (st->fragment_program == KZN_FS_COMPILED) {
+        if ((r = kzn_fragment_program_launch(q->fragment_program, 1, mode, grid.x, kRasterThreads, smem, q->stream, &p, sizeof p))) return r;
+    } else {
+        KZN_RASTER_LAUNCH(raster_kernel, kRasterThreads, smem);
+    }
 #undef KZN_RASTER_LAUNCH
     return kzn_launched(q, "raster_kernel");
 }
@@ -2141,3 +2255,5 @@ KznResult kzn_cmd_draw_indexed(KznQueue* queue, const KznGraphicsPipelineState* 
 }
 
 }  // extern "C"
+
+#endif  // !KZN_FS_TEMPLATE

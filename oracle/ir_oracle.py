@@ -30,6 +30,25 @@ class IrError(ValueError):
     pass
 
 
+# Version 2 of the instruction set (kazan_b200/csrc/ir.h `kExtOps`): name -> (argument count, result count).  The reference
+# has none of these (instructions_impl.rs:395-433); the C++ mirror reads them only when asked for version 2, and so does
+# this parser.  Execution: oracle/ir_simt.py.
+V2_OPS = {
+    **{n: (2, 1) for n in ("i_sub i_mul bitwise_and bitwise_or bitwise_xor shift_left_logical shift_right_logical "
+                           "shift_right_arithmetic f_add f_sub f_mul f_div f_min f_max i_equal i_not_equal u_less_than s_less_than "
+                           "u_less_than_equal s_less_than_equal u_greater_than s_greater_than u_greater_than_equal "
+                           "s_greater_than_equal f_ord_equal f_ord_less_than f_ord_less_than_equal f_ord_greater_than "
+                           "f_ord_greater_than_equal f_unord_not_equal logical_and logical_or ptr_add group_non_uniform_shuffle "
+                           "group_non_uniform_shuffle_xor").split()},
+    **{n: (1, 1) for n in ("s_negate not f_negate f_abs logical_not convert_f_to_u convert_f_to_s convert_s_to_f convert_u_to_f "
+                           "u_convert s_convert f_convert bitcast group_non_uniform_all group_non_uniform_any "
+                           "group_non_uniform_ballot group_non_uniform_broadcast_first group_non_uniform_i_add").split()},
+    "fma": (3, 1), "select": (3, 1), "store": (2, 0), "group_non_uniform_elect": (0, 1),
+}
+V2_BUILT_INS = ("global_invocation_id", "subgroup_local_invocation_id", "subgroup_size", "frag_coord", "push_constants",
+                "descriptor_table")
+
+
 # ---- lexer (text.rs:1133-1326) ----------------------------------------------------------------------------------
 
 _TOKEN = re.compile(r"""
@@ -223,7 +242,8 @@ class Module:
 # ---- parser ---------------------------------------------------------------------------------------------------------
 
 class Parser:
-    def __init__(self, text: str):
+    def __init__(self, text: str, version: int = 1):
+        self.version = version
         self.toks, self.i = lex(text), 0
         self.structs: dict[int, Type] = {}
         self.values: list[dict] = [{}]     # scope stack: (name, suffix) -> Value
@@ -503,6 +523,15 @@ class Parser:
             ins = Instr("block", target=self.block_instruction())
         elif t.text == "loop":
             ins = Instr("loop", target=self.loop_instruction())
+        elif self.version >= 2 and t.text in V2_OPS:
+            self.expect("["); a = self.uses()
+            al = 0
+            if t.text == "store":
+                self.expect(","); al = self.alignment()
+            self.expect("->"); r = self.defs()
+            if (len(a), len(r)) != V2_OPS[t.text]:
+                raise IrError(f"{t.text} takes {V2_OPS[t.text][0]} argument(s) and {V2_OPS[t.text][1]} result(s)")
+            ins = Instr(t.text, args=a, results=r, align=al)
         else:
             raise IrError(f"unknown instruction {t.text!r} at offset {t.pos}")
         ins.location = self.location()
@@ -622,7 +651,7 @@ class Parser:
         while not self.at("}"):
             v = self.variable(); self.expect(":"); self.expect("{"); self.expect("kind"); self.expect(":")
             v.kind = self.next().text
-            if v.kind != "vertex_position":  # interface.rs:61-67: the only built-in kind
+            if v.kind != "vertex_position" and not (self.version >= 2 and v.kind in V2_BUILT_INS):  # interface.rs:61-67: the only built-in kind
                 raise IrError(f"unknown built-in kind {v.kind}")
             self.expect("}"); self.expect(";")
             out.append(v)
@@ -773,6 +802,11 @@ class Printer:
         elif ins.op == "block":
             b = ins.target
             self.w("block " + self.name("block", b) + " -> "); self.results(b.results); self.w(" "); self.body(b)
+        elif ins.op in V2_OPS:
+            self.w(ins.op + " ["); self.comma(ins.args, self.value_use); self.w("]")
+            if ins.op == "store":
+                self.w(f", align: {ins.align:#X}".replace("0X", "0x"))
+            self.w(" -> "); self.results(ins.results)
         elif ins.op == "loop":
             lp = ins.target
             self.w("loop " + self.name("loop", lp) + "["); self.comma(lp.arguments, self.value_use); self.w("] -> ")
@@ -851,8 +885,8 @@ class Printer:
 
 # ---- entry points used by the tests --------------------------------------------------------------------------------------
 
-def parse_module(text: str) -> Module:
-    p = Parser(text); m = p.module(); p.finish(); return m
+def parse_module(text: str, version: int = 1) -> Module:
+    p = Parser(text, version); m = p.module(); p.finish(); return m
 
 
 def module_to_text(m: Module) -> str:

@@ -1,0 +1,177 @@
+"""GPU: version 2 of the IR through the PTX back end (north_star (1) and (2)).
+
+Compute: programs using float arithmetic, compares, select, conversions, store, ptr_add, the built-in inputs, a bound
+descriptor set and push constants, and the subgroup operations (warp votes / shuffles / redux) are dispatched through the C
+ABI and compared bit for bit with the SIMT interpreter (oracle/ir_simt.py); the buffer-to-buffer shader also at 2^24
+invocations against its closed form.
+Draw: every parity scene of tests/cases.py is drawn again with its fragment program COMPILED from shader-compiler-ir
+(tests/ir_programs_v2/fs_*.kazan-ir) into the raster kernels; the frames must be the oracle's, bit for bit, like the frames
+of the built-in programs."""
+import numpy as np
+import pytest
+
+from kazan_b200 import abi, backend
+from tests import cases
+from tests import ir_v2_cases as v2
+from tests.test_gpu_raster import GOLDEN, SCENES, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _dispatch(gpu, name, inputs, group_count, local_size=(1, 1, 1)):
+    dt_in, dt_out = v2.CASES[name]
+    module = backend.IrModule.parse(v2.program_text(name), 2)
+    pipe = backend.ComputePipeline(gpu.device, module, local_size)
+    assert pipe.inputs_size == dt_in.itemsize and pipe.outputs_size == dt_out.itemsize
+    n = len(inputs)
+    ibuf = gpu.buffer(inputs.nbytes, inputs)
+    obuf = gpu.buffer(n * dt_out.itemsize, np.full(n * dt_out.itemsize, 0xEE, dtype=np.uint8))
+    gpu.queue.cmd_dispatch(pipe, group_count, ibuf.address, obuf.address)
+    gpu.queue.wait_idle()
+    raw = obuf.download()[:n * dt_out.itemsize]
+    pipe.destroy()
+    module.destroy()
+    return raw.view(dt_out)
+
+
+def test_integer_program_matches_interpreter(gpu):
+    inputs = v2.make_inputs("int_ops", 333, seed=21)
+    got, want = _dispatch(gpu, "int_ops", inputs, (333, 1, 1)), v2.interpret("int_ops", inputs)
+    for f in want.dtype.names:
+        if f != "r14":  # r14 is a pointer difference: layout, checked below
+            assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["r14"], want["r14"]), "select on pointers / pointer difference"
+    gpu.release()
+
+
+def test_float_program_matches_interpreter(gpu):
+    inputs = v2.make_inputs("float_ops", 333, seed=22)
+    got, want = _dispatch(gpu, "float_ops", inputs, (333, 1, 1)), v2.interpret("float_ops", inputs)
+    for f in want.dtype.names:
+        if f in ("r0", "r1", "r2", "r3", "r4", "r5", "r9", "r10"):
+            assert v2.same_floats(got[f], want[f]), f  # IEEE results: bit patterns, NaN == NaN
+        else:
+            assert np.array_equal(got[f], want[f]), f
+    gpu.release()
+
+
+@pytest.mark.parametrize("n", [96, 256 + 32 + 7])
+def test_subgroup_operations_match_interpreter(gpu, n):
+    """warp votes, shuffles and redux: full subgroups, an all-odd and a none-odd one, and (second size) a last subgroup of 7
+    invocations whose member mask is cut from the launch size"""
+    inputs = v2.make_inputs("subgroup_ops", n, seed=23)
+    got, want = _dispatch(gpu, "subgroup_ops", inputs, (n, 1, 1)), v2.interpret("subgroup_ops", inputs)
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f]), f
+    v = inputs["v"]
+    assert got["r0"][0] == sum(int(v[i] & 1) << i for i in range(32))  # ballot, closed form
+    assert got["r1"][32] == 3 and got["r1"][64] == 0  # all | any
+    assert np.array_equal(got["r6"][:32], np.full(32, np.uint32(v[:32].astype(np.uint64).sum() & 0xFFFFFFFF)))
+    gpu.release()
+
+
+def _saxpy(gpu, W, H, local, check_interpreter):
+    rng = np.random.default_rng(24)
+    x = rng.integers(-1000, 1000, W * H).astype(np.float32)
+    y = rng.integers(-1000, 1000, W * H).astype(np.float32)
+    alpha = np.float32(1.5)
+    xb, yb = gpu.buffer(x.nbytes, x), gpu.buffer(y.nbytes, y)
+    ds = backend.DescriptorSet(gpu.device, [(0, abi.DESCRIPTOR_TYPE_STORAGE_BUFFER, 1), (3, abi.DESCRIPTOR_TYPE_STORAGE_BUFFER, 1)])
+    ds.write_buffers(0, [(xb.address, 0, x.nbytes)])
+    ds.write_buffers(3, [(yb.address, 0, y.nbytes)])
+    assert (ds.slot(0), ds.slot(3), ds.slot(1)) == (0, 1, -1)
+    module = backend.IrModule.parse(v2.program_text("saxpy_buffers"), 2)
+    pipe = backend.ComputePipeline(gpu.device, module, local)
+    q = gpu.queue
+    q.cmd_bind_descriptor_set(abi.PIPELINE_BIND_POINT_COMPUTE, ds)
+    q.cmd_push_constants(alpha.tobytes() + np.uint32(W).tobytes())
+    q.cmd_dispatch(pipe, (W // local[0], H // local[1], 1))
+    q.wait_idle()
+    got = yb.download().view(np.float32)[:W * H]
+    assert np.array_equal(got, alpha * x + y), "closed form (every value is exactly representable)"
+    if check_interpreter:
+        from oracle import ir_oracle as iro
+        from oracle import ir_simt as sim
+        table = np.array([0x3000_0000, x.nbytes, 0x4000_0000, y.nbytes], dtype=np.uint64)
+        ybuf = bytearray(y.tobytes())
+        mem = sim.Memory({0x3000_0000: bytearray(x.tobytes()), 0x4000_0000: ybuf, 0x5000_0000: bytearray(table.tobytes())})
+        sim.run_dispatch(iro.parse_module(v2.program_text("saxpy_buffers"), 2), W * H, mem, global_size=(W, H, 1),
+                         push_constants=alpha.tobytes() + np.uint32(W).tobytes(), descriptor_table=0x5000_0000)
+        assert np.array_equal(got, np.frombuffer(bytes(ybuf), dtype=np.float32))
+    q.cmd_bind_descriptor_set(abi.PIPELINE_BIND_POINT_COMPUTE, None)
+    pipe.destroy()
+    module.destroy()
+    ds.destroy()
+    gpu.release()
+
+
+def test_buffer_to_buffer_shader_through_a_descriptor_set_matches_interpreter(gpu):
+    """f1: y = alpha * x + y over two STORAGE_BUFFER descriptors, alpha and the row length in push constants, the element
+    index from global_invocation_id (16 x 12 invocations, LocalSize 8 x 4)"""
+    _saxpy(gpu, 16, 12, (8, 4, 1), True)
+
+
+def test_buffer_to_buffer_shader_over_2_pow_24_invocations(gpu):
+    """the configs[1] size: 4096 x 4096 invocations, closed form"""
+    _saxpy(gpu, 4096, 4096, (16, 16, 1), False)
+
+
+def test_descriptor_set_validation(gpu):
+    from kazan_b200.host import KazanError
+    with pytest.raises(KazanError) as e:
+        backend.DescriptorSet(gpu.device, [(0, 1, 1)])  # VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER
+    assert e.value.code == -8
+    ds = backend.DescriptorSet(gpu.device, [(0, abi.DESCRIPTOR_TYPE_UNIFORM_BUFFER, 2)])
+    with pytest.raises(KazanError):
+        ds.write_buffers(0, [(0x1000, 0, 16)] * 3)
+    with pytest.raises(KazanError):
+        ds.write_buffers(7, [(0x1000, 0, 16)])
+    with pytest.raises(KazanError):
+        gpu.queue.cmd_push_constants(b"\0" * 132)
+    ds.destroy()
+
+
+@pytest.fixture(scope="module")
+def compiled(gpu):
+    """the two built-in fragment programs, compiled from their shader-compiler-ir form into the raster kernels"""
+    progs = {}
+    for enum, name in ((abi.FS_VERTEX_COLOR, "fs_vertex_color"), (abi.FS_PROCEDURAL_ORBIT, "fs_orbit")):
+        m = backend.IrModule.parse(v2.program_text(name), 2)
+        progs[enum] = backend.FragmentProgram(gpu.device, m)
+        m.destroy()
+    yield progs
+    for p in progs.values():
+        p.destroy()
+
+
+@pytest.mark.parametrize("scene", SCENES, ids=lambda s: s.name)
+def test_draw_with_compiled_fragment_program_matches_oracle(gpu, compiled, scene):
+    oc, od, os_ = scene.run_oracle()
+    gc, gd, gs = scene.run_gpu(gpu, compiled=compiled)
+    assert (gs.triangles_in, gs.triangles_culled) == (os_.triangles_in, os_.triangles_culled)
+    assert (gs.fragments_covered, gs.fragments_depth_passed) == (os_.fragments_covered, os_.fragments_depth_passed)
+    assert gd.tobytes() == od.tobytes(), "depth buffer differs (must be bit exact)"
+    if gc.tobytes() != oc.tobytes():
+        diff = np.abs(gc.astype(np.int16) - oc.astype(np.int16))
+        pytest.fail(f"colour differs: max {diff.max()} LSB on {(diff > 0).sum()} bytes")
+    assert sha(gc.tobytes()) == GOLDEN[f"draw/{scene.name}/color"]
+
+
+def test_draw_without_a_bound_program_is_refused(gpu):
+    from kazan_b200.host import KazanError
+    sc = next(s for s in SCENES if s.name == "fill_orbit_256x144")
+    with pytest.raises(KazanError):
+        sc.run_gpu(gpu, compiled={abi.FS_PROCEDURAL_ORBIT: None})
+    gpu.release()
+
+
+def test_full_size_fill_4k_with_the_compiled_orbit_shader(gpu, compiled):
+    """BASELINE configs[2] at full size with the fragment shader coming from .kazan-ir: the frame of the built-in program,
+    bit for bit"""
+    from tests import util
+    W, H = 3840, 2160
+    sc = util.Scene("fill4k", W, H, util.FULLSCREEN_TRIANGLE, state=util.pipeline_state(fs=abi.FS_PROCEDURAL_ORBIT))
+    a, _, st_a = sc.run_gpu(gpu)
+    b, _, st_b = sc.run_gpu(gpu, compiled=compiled)
+    assert st_b.fragments_covered == W * H == st_a.fragments_covered
+    assert a.tobytes() == b.tobytes()

@@ -196,7 +196,10 @@ class Scene:
         check(code)
         return color, depth, stats
 
-    def run_gpu(self, ctx: GpuContext):
+    def run_gpu(self, ctx: GpuContext, compiled=None):
+        """compiled: {fragment program enum: backend.FragmentProgram} — the draw then runs the compiled form of the scene's
+        built-in fragment program (state.fragment_program = KZN_FS_COMPILED, the program bound to the queue, the frame's
+        1/width and 1/height as push constants, which is what fs_orbit.kazan-ir reads)."""
         color0, depth0 = self._initial()
         cbuf = ctx.buffer(color0.nbytes, color0)
         dbuf = ctx.buffer(depth0.nbytes, depth0)
@@ -205,14 +208,23 @@ class Scene:
         fb = self._framebuffer(cbuf.address, dbuf.address)
         vi = abi.VertexInput(vbuf.address, self.vertices.nbytes, self.stride, 0, self.pos_comps, self.color_offset)
         q = ctx.queue
+        state = self.state
+        if compiled is not None:
+            state = abi.GraphicsPipelineState.from_buffer_copy(bytes(self.state))
+            state.fragment_program = abi.FS_COMPILED
+            q.cmd_bind_fragment_program(compiled[self.state.fragment_program])
+            q.cmd_push_constants(np.array([np.float32(1.0) / np.float32(self.width), np.float32(1.0) / np.float32(self.height)],
+                                          dtype=np.float32).tobytes())
         q.set_draw_statistics(sbuf.address)
         if self.indices is not None:
             ibuf = ctx.buffer(self.indices.nbytes, self.indices)
-            q.cmd_draw_indexed(self.state, fb, self.viewport, self.scissor, vi, ibuf.address, self.indices.nbytes,
+            q.cmd_draw_indexed(state, fb, self.viewport, self.scissor, vi, ibuf.address, self.indices.nbytes,
                                self.index_type, self.count, self.instances, self.first, self.vertex_offset, 0)
         else:
-            q.cmd_draw(self.state, fb, self.viewport, self.scissor, vi, self.count, self.instances, self.first, 0)
+            q.cmd_draw(state, fb, self.viewport, self.scissor, vi, self.count, self.instances, self.first, 0)
         q.set_draw_statistics(0)
+        if compiled is not None:
+            q.cmd_bind_fragment_program(None)
         color, depth = cbuf.download(), dbuf.download()
         stats = abi.DrawStatistics.from_buffer_copy(sbuf.download().tobytes())
         ctx.release()
