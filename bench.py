@@ -662,6 +662,18 @@ def run_ours(args):
     frame_bytes = W * total_h * 4
     n_targets = 8  # each rank writes 8 x 33 MB of distinct lines in rotation (265 MB > 126 MiB L2): never L2 resident
     st = fill_state(abi)
+    fs_program = None
+    if args.fs == "compiled":
+        # north_star (1)+(2): the fragment shader is a shader-compiler-ir module (the oracle's procedural shader written in
+        # the IR, tests/ir_programs_v2/fs_orbit.kazan-ir) lowered to PTX by the back end and built into the raster kernels
+        from kazan_b200 import backend
+        ir = backend.IrModule.parse((ROOT / "tests" / "ir_programs_v2" / "fs_orbit.kazan-ir").read_text(), 2)
+        fs_program = backend.FragmentProgram(dev, ir)
+        ir.destroy()
+        st.fragment_program = abi.FS_COMPILED
+        queue.cmd_bind_fragment_program(fs_program)
+        # what the shader reads: 1 / frame width, 1 / frame height (the values the built-in program derives from the framebuffer)
+        queue.cmd_push_constants(np.array([np.float32(1.0) / np.float32(W), np.float32(1.0) / np.float32(H * world)], dtype=np.float32).tobytes())
     vp = abi.Viewport(0, 0, W, total_h, 0, 1)
     sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, total_h))
     verts = torch.from_numpy(FULLSCREEN_TRIANGLE.copy()).cuda()
@@ -696,7 +708,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": "fullscreen-triangle procedural fragment shader at 3840x2160 R8G8B8A8_UNORM (configs[2])"
                                + ("" if world == 1 else f"; {world} bands of 3840x2160, NCCL composite to rank 0"),
-                   "frame": [W, total_h], "fragment_program": "procedural orbit, 32 fp32 fma iterations",
+                   "frame": [W, total_h],
+                   "fragment_program": ("procedural orbit, 32 fp32 fma iterations; " +
+                                        ("compiled from shader-compiler-ir (fs_orbit.kazan-ir) by the PTX back end into the raster kernel"
+                                         if fs_program else "built-in CUDA form (--fs builtin)")),
                    "l2": f"rotating {n_targets} render targets ({n_targets * W * H * 4 >> 20} MiB written per rank > 126 MiB L2)"},
         "gpu_launches": int(launches),
     }
@@ -801,7 +816,8 @@ def run_ours(args):
         nominal_issue = dev.sm_count * 128 * sm_mhz * 1e6 / 1e12  # T fp32 lane-instructions/s at the sampled clock
         issue = W * H * FP32_INSTR_PER_PIXEL / sec / 1e12
         line["roofline"] = {"bound": "fp32_issue", "achieved": issue, "peak": measured_issue, "unit": "Tinstr/s", "frac": issue / measured_issue,
-                            "traffic": roofline_traffic("raster_direct_kernel"), "kernel": "raster_direct_kernel<ORBIT,0>",
+                            "traffic": roofline_traffic("raster_direct_kernel"),
+                            "kernel": "kzn_fs_raster_direct_0 (raster_direct_kernel with the compiled shader)" if fs_program else "raster_direct_kernel<ORBIT,0>",
                             "kernel_ms": k_ms, "kernel_ms_event_pair": k_ms_events,
                             "kernel_ms_source": ("event pair around the kernel" if k_ms_events <= ms_per_step else
                                                  "step time: upper bound of the kernel's duration (the event pair also brackets the launch latency that programmatic dependent launch hides)"),
@@ -825,6 +841,15 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": W * H / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "one full 3840x2160 frame, oracle/raster.c, all host threads"}
         line["parity"] = "bit-exact vs oracle on the full 4K frame" if same else "MISMATCH vs oracle"
+
+        # ---- the same frames with the built-in CUDA form of the shader (what the compiled form is measured against) ----
+        if fs_program:
+            with torch.cuda.stream(stream):
+                st_b = fill_state(abi)
+                n_b = max(50, min(args.steps, 500))
+                ms_b = time_region(torch, stream, lambda k: queue.cmd_draw(st_b, fbs[k % n_targets], vp, sc, vi, 3), n_b, 5)
+            line["builtin_fragment_program"] = {"value": pixels_per_step * n_b / ms_b / 1e6, "unit": UNIT, "steps": n_b,
+                                                "compiled_over_builtin": value / (pixels_per_step * n_b / ms_b / 1e6)}
 
         # ---- the rest of BASELINE's metric: clear / copy GB/s vs HBM peak, compute dispatch, 1M-triangle mesh ----
         with torch.cuda.stream(stream):
@@ -876,6 +901,8 @@ def main():
     ap.add_argument("--composite", default="push", choices=["push", "store", "nccl"],
                     help="N > 1: how bands reach rank 0 (see FrameTargets)")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e, CPU baseline or transfer sweep")
+    ap.add_argument("--fs", default="compiled", choices=["compiled", "builtin"],
+                    help="the fill-rate fragment shader: compiled from its shader-compiler-ir module by the PTX back end (default), or the built-in CUDA form")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

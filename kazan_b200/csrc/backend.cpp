@@ -554,17 +554,19 @@ std::string build_fragment_module(const kir::Module& m, int* call_sites) {
     const std::string text = kzn_raster_template_ptx;
     std::string out;
     out.reserve(text.size() + (1u << 20));
-    // the external declaration goes: no reference to it is left
+    // the external declarations of the two entry points of the fragment program go: no reference to them is left
     size_t pos = 0;
-    {
-        const size_t d = text.find(".extern .func");
-        const size_t name = d == std::string::npos ? d : text.find("kzn_fs_main", d);
-        const size_t end = name == std::string::npos ? name : text.find(';', name);
-        if (d == std::string::npos || end == std::string::npos || text.find(".extern", d + 1) < name)
-            throw kir::Error("internal: the raster template does not declare kzn_fs_main the way this library expects");
-        out.append(text, 0, d);
+    int declarations = 0;
+    for (size_t d = text.find(".extern .func"); d != std::string::npos; d = text.find(".extern .func", d + 1)) {
+        const size_t paren = text.find("\n(", d), end = text.find(';', d);
+        if (paren == std::string::npos || end == std::string::npos) break;
+        const std::string head = text.substr(d, paren - d);
+        if (head.find(" kzn_fs_main") == std::string::npos) continue;
+        out.append(text, pos, d - pos);
         pos = end + 1;
+        ++declarations;
     }
+    if (declarations != 2) throw kir::Error("internal: the raster template does not declare the fragment program the way this library expects");
     int sites = 0;
     for (;;) {
         const size_t b = text.find("{ // callseq ", pos);
@@ -590,8 +592,9 @@ std::string build_fragment_module(const kir::Module& m, int* call_sites) {
         }
         kir::FragmentSite site;
         site.id = sites++;
-        site.in.assign(10, "0");
-        site.out.assign(4, "");
+        site.fragments = seq.find("kzn_fs_main2") != std::string::npos ? 2 : 1;
+        site.in.assign(8 * site.fragments + 2, "0");
+        site.out.assign(4 * site.fragments, "");
         if (!entry.empty()) site.push_constants_param = entry + "_param_0+" + std::to_string(kzn_draw_params_push_constants_offset);
         size_t at = 0;
         while (at < seq.size()) {
@@ -609,7 +612,7 @@ std::string build_fragment_module(const kir::Module& m, int* call_sites) {
                 size_t v = ln.find(',', pe);
                 std::string operand = ln.substr(v + 1, semi - v - 1);
                 operand.erase(0, operand.find_first_not_of(" \t"));
-                if (k < 0 || k >= 10) throw kir::Error("internal: fragment call with more than 10 parameters");
+                if (k < 0 || k >= (int)site.in.size()) throw kir::Error("internal: fragment call with more parameters than its callee has");
                 site.in[k] = operand;
             } else if (ln.rfind("ld.param", 0) == 0) {
                 const size_t rb = ln.find("[retval0");
@@ -622,7 +625,7 @@ std::string build_fragment_module(const kir::Module& m, int* call_sites) {
                 for (char ch : dst)
                     if (ch != '{' && ch != '}' && ch != ' ' && ch != '\t') regs += ch;
                 size_t r0 = 0;
-                while (r0 <= regs.size() && component < 4) {
+                while (r0 <= regs.size() && component < (int)site.out.size()) {
                     size_t r1 = regs.find(',', r0);
                     if (r1 == std::string::npos) r1 = regs.size();
                     if (r1 > r0) site.out[component++] = regs.substr(r0, r1 - r0);

@@ -50,6 +50,7 @@ struct Base {
     bool conflicted = false;
     std::map<uint64_t, unsigned> slots;      // offset -> bytes, from the analysis
     std::map<uint64_t, std::string> cells;   // offset -> register
+    std::map<uint64_t, std::string> cells_b; // pair mode: the registers of the second fragment while the first one's are in `cells`
     std::string address;                     // register (or symbol expression) of the base when it is memory
 };
 struct Prov {
@@ -72,6 +73,18 @@ struct Emitter {
     std::map<const Value*, Prov> prov;
     std::string submask;      // kernel: member mask of the in-range threads of the warp (subgroup operations)
     bool uses_subgroup = false;
+    // ---- pair mode (fragment shaders): ONE copy of the code shades TWO fragments.  Values that differ between the two
+    // ("varying": everything computed from frag_coord or the interpolated inputs) exist twice; an f32 one lives packed in a
+    // 64-bit register and its add / sub / mul / fma are the packed fma.rn.f32x2 forms (FFMA2: two IEEE operations per issue
+    // slot, each identical to the scalar instruction), every other varying instruction is emitted once per fragment.
+    // Values that do not depend on the fragment (push constants, loop counters) and all control flow stay single.
+    bool pair = false;
+    std::set<const Value*> varying;
+    std::set<std::pair<int, uint64_t>> varying_cells;
+    struct PairReg {
+        std::string packed, s0, s1;
+    };
+    std::map<const Value*, PairReg> preg;
     std::string pc_param;     // symbol (+ offset) of the push constant block in parameter space, when it is there
     bool reads_user_inputs = false, reads_frag_coord = false, reads_frag_coord_zw = false;
 
@@ -209,6 +222,31 @@ struct Emitter {
     void parallel_move(const std::vector<Value*>& dsts, const std::vector<Value*>& srcs, const char* what) {
         if (dsts.size() != srcs.size()) throw Error(std::string(what) + ": value count does not match the target's definition count");
         std::vector<std::string> ops;
+        if (pair) {
+            bool any = false;
+            for (const Value* d : dsts) any = any || is_varying(d);
+            if (any) {
+                // sources first (a destination may be among them), then the assignments
+                std::vector<std::pair<std::string, std::string>> vals;
+                for (size_t i = 0; i < srcs.size(); ++i) {
+                    if (reg_class(dsts[i]->type) != reg_class(srcs[i]->type)) throw Error(std::string(what) + ": type mismatch");
+                    auto v = scalars_of(srcs[i]);
+                    if (!srcs[i]->has_const) {
+                        const RC c = reg_class(srcs[i]->type);
+                        std::string t0 = fresh(c), t1 = fresh(c);
+                        line(std::string("mov.") + mov_type(c) + " " + t0 + ", " + v.first + ";");
+                        line(std::string("mov.") + mov_type(c) + " " + t1 + ", " + v.second + ";");
+                        v = {t0, t1};
+                    }
+                    vals.push_back(v);
+                }
+                for (size_t i = 0; i < dsts.size(); ++i) {
+                    if (is_varying(dsts[i])) pair_assign(dsts[i], vals[i].first, vals[i].second);
+                    else move(dsts[i], vals[i].first);
+                }
+                return;
+            }
+        }
         for (size_t i = 0; i < srcs.size(); ++i) {
             if (reg_class(dsts[i]->type) != reg_class(srcs[i]->type)) throw Error(std::string(what) + ": type mismatch");
             std::string s = use(srcs[i]);
@@ -319,6 +357,205 @@ struct Emitter {
         }
     }
 
+    // ---- pair mode: which values differ between the two fragments ---------------------------------------------------------
+    bool is_varying(const Value* v) const { return pair && !v->has_const && varying.count(v) != 0; }
+    static bool is_f32(const Type* t) { return t->kind == TypeKind::Float && float_bits(t->float_kind) == 32; }
+    bool taint_values(const std::vector<Value*>& dsts, const std::vector<Value*>& srcs) {
+        bool changed = false;
+        for (size_t i = 0; i < dsts.size() && i < srcs.size(); ++i)
+            if (!srcs[i]->has_const && varying.count(srcs[i]) && varying.insert(dsts[i]).second) changed = true;
+        return changed;
+    }
+    // one sweep; returns true when something became varying.  `eligible` is cleared when the code cannot be shared by two
+    // fragments: control flow that depends on the fragment, or memory that both would write.
+    bool taint(const Block* b, bool* eligible) {
+        bool changed = false;
+        auto var = [&](const Value* v) { return !v->has_const && varying.count(v) != 0; };
+        auto mark = [&](const Value* v) {
+            if (varying.insert(v).second) changed = true;
+        };
+        for (const Instr* ins : b->body) {
+            switch (ins->op) {
+                case Op::Load: {
+                    const Value* pv = ins->args[0];
+                    auto it = prov.find(pv);
+                    bool v = var(pv);
+                    if (it != prov.end()) {
+                        const Base& bs = bases[it->second.base];
+                        if (bs.scalarized && varying_cells.count({it->second.base, (uint64_t)it->second.offset})) v = true;
+                    }
+                    if (v) mark(ins->results[0]);
+                    break;
+                }
+                case Op::Ext:
+                    if (kExtOps[ins->ext].kind == ExtKind::Store) {
+                        auto it = prov.find(ins->args[0]);
+                        if (it != prov.end() && bases[it->second.base].scalarized) {
+                            if (var(ins->args[1]) && varying_cells.insert({it->second.base, (uint64_t)it->second.offset}).second) changed = true;
+                        } else {
+                            *eligible = false;  // a store to real memory would be done once for two fragments
+                        }
+                        break;
+                    }
+                    [[fallthrough]];
+                case Op::Add: {
+                    bool v = false;
+                    for (const Value* a : ins->args) v = v || var(a);
+                    if (v)
+                        for (const Value* r : ins->results) mark(r);
+                    break;
+                }
+                case Op::Break: {
+                    auto it = dests_all.find(ins->block);
+                    if (it != dests_all.end() && taint_values(*it->second, ins->args)) changed = true;
+                    break;
+                }
+                case Op::Continue:
+                    if (taint_values(ins->loop->params, ins->args)) changed = true;
+                    break;
+                case Op::Branch:
+                    if (var(ins->args[0])) *eligible = false;
+                    for (auto& c : ins->cases) {
+                        auto it = dests_all.find(c.target);
+                        if (it != dests_all.end() && taint_values(*it->second, c.results)) changed = true;
+                    }
+                    break;
+                case Op::BlockI:
+                    dests_all[ins->block] = &ins->block->results;
+                    if (taint(ins->block, eligible)) changed = true;
+                    break;
+                case Op::LoopI:
+                    dests_all[ins->loop->body] = &ins->loop->results;
+                    if (taint_values(ins->loop->params, ins->loop->arguments)) changed = true;
+                    if (taint(ins->loop->body, eligible)) changed = true;
+                    break;
+            }
+        }
+        return changed;
+    }
+    std::map<const Block*, const std::vector<Value*>*> dests_all;
+    // can one copy of the entry point's code shade two fragments?  (fills `varying` / `varying_cells`)
+    bool analyze_pair(const Function* f, int in_base, int frag_coord_base) {
+        bool eligible = true;
+        for (const Base& b : bases)
+            if (b.kind == Base::Var && !b.scalarized) eligible = false;  // a .local variable would be shared by the two
+        for (auto& s : bases[in_base].slots) varying_cells.insert({in_base, s.first});
+        if (frag_coord_base >= 0)
+            for (auto& s : bases[frag_coord_base].slots) varying_cells.insert({frag_coord_base, s.first});
+        dests_all[f->body] = &f->body->results;
+        while (taint(f->body, &eligible)) {
+        }
+        return eligible;
+    }
+    // a varying value's registers: f32 values are kept packed, everything else as two scalars
+    PairReg& pair_def(const Value* v) {
+        auto it = preg.find(v);
+        if (it != preg.end()) return it->second;
+        PairReg r;
+        if (is_f32(v->type)) {
+            r.packed = fresh(RC::B64);
+        } else {
+            r.s0 = fresh(reg_class(v->type));
+            r.s1 = fresh(reg_class(v->type));
+        }
+        return preg.emplace(v, r).first->second;
+    }
+    // the packed form of an f32 value (a value that is the same for both fragments is duplicated)
+    std::string packed_of(const Value* v) {
+        if (is_varying(v)) {
+            auto it = preg.find(v);
+            if (it == preg.end()) throw Error("value '" + v->name + "' is used before it is defined");
+            return it->second.packed;
+        }
+        const std::string u = in_register(use(v), RC::B32);
+        std::string r = fresh(RC::B64);
+        line("mov.b64 " + r + ", {" + u + ", " + u + "};");
+        return r;
+    }
+    // the two scalar forms of a value
+    std::pair<std::string, std::string> scalars_of(const Value* v) {
+        if (!is_varying(v)) {
+            const std::string u = use(v);
+            return {u, u};
+        }
+        auto it = preg.find(v);
+        if (it == preg.end()) throw Error("value '" + v->name + "' is used before it is defined");
+        if (!it->second.packed.empty()) {
+            std::string a = fresh(RC::B32), b = fresh(RC::B32);
+            line("mov.b64 {" + a + ", " + b + "}, " + it->second.packed + ";");
+            return {a, b};
+        }
+        return {it->second.s0, it->second.s1};
+    }
+    void pair_assign(const Value* dst, const std::string& v0, const std::string& v1) {
+        PairReg& d = pair_def(dst);
+        if (!d.packed.empty()) {
+            line("mov.b64 " + d.packed + ", {" + in_register(v0, RC::B32) + ", " + in_register(v1, RC::B32) + "};");
+        } else {
+            const RC c = reg_class(dst->type);
+            line(std::string("mov.") + mov_type(c) + " " + d.s0 + ", " + v0 + ";");
+            line(std::string("mov.") + mov_type(c) + " " + d.s1 + ", " + v1 + ";");
+        }
+    }
+    bool instruction_is_varying(const Instr* ins) {
+        for (const Value* r : ins->results)
+            if (is_varying(r)) return true;
+        if (ins->op == Op::Ext && kExtOps[ins->ext].kind == ExtKind::Store) {
+            auto it = prov.find(ins->args[0]);
+            if (it != prov.end() && varying_cells.count({it->second.base, (uint64_t)it->second.offset})) return true;
+        }
+        return false;
+    }
+    void scalar_instruction(const Instr* ins) {
+        switch (ins->op) {
+            case Op::Add: add(ins); break;
+            case Op::Load: load(ins); break;
+            case Op::Ext: ext(ins); break;
+            default: throw Error("internal: not a value instruction");
+        }
+    }
+    // one varying instruction for both fragments
+    void pair_instruction(const Instr* ins) {
+        if (ins->op == Op::Ext && ins->results.size() == 1 && is_f32(ins->results[0]->type)) {
+            const ExtOp& op = kExtOps[ins->ext];
+            const std::string ptx = op.ptx;
+            if ((op.kind == ExtKind::FloatBinary && (ptx == "add.rn" || ptx == "sub.rn" || ptx == "mul.rn")) || op.kind == ExtKind::FloatTernary) {
+                std::string ops;
+                for (const Value* a : ins->args) ops += ", " + packed_of(a);
+                line(ptx + ".f32x2 " + pair_def(ins->results[0]).packed + ops + ";");
+                return;
+            }
+        }
+        // any other instruction: once per fragment, on that fragment's registers and cells
+        std::vector<std::pair<std::string, std::string>> args;
+        for (const Value* a : ins->args) args.push_back(is_varying(a) ? scalars_of(a) : std::pair<std::string, std::string>());
+        std::string result[2];
+        for (int frag = 0; frag < 2; ++frag) {
+            std::map<const Value*, std::string> saved;
+            for (size_t i = 0; i < ins->args.size(); ++i)
+                if (is_varying(ins->args[i])) {
+                    auto it = reg.find(ins->args[i]);
+                    if (it != reg.end()) saved[ins->args[i]] = it->second;
+                    reg[ins->args[i]] = frag ? args[i].second : args[i].first;
+                }
+            for (const Value* r : ins->results) reg.erase(r);
+            if (frag)
+                for (Base& b : bases) std::swap(b.cells, b.cells_b);
+            scalar_instruction(ins);
+            if (frag)
+                for (Base& b : bases) std::swap(b.cells, b.cells_b);
+            if (!ins->results.empty()) result[frag] = reg.at(ins->results[0]);
+            for (const Value* r : ins->results) reg.erase(r);
+            for (size_t i = 0; i < ins->args.size(); ++i)
+                if (is_varying(ins->args[i])) {
+                    reg.erase(ins->args[i]);
+                    auto it = saved.find(ins->args[i]);
+                    if (it != saved.end()) reg[ins->args[i]] = it->second;
+                }
+        }
+        if (!ins->results.empty()) pair_assign(ins->results[0], result[0], result[1]);
+    }
+
     // ---- memory -------------------------------------------------------------------------------------------------
     // text of `[register + constant]`
     static std::string address(const std::string& r, int64_t off) {
@@ -396,9 +633,15 @@ struct Emitter {
         if (it != b.cells.end()) return it->second;
         auto s = b.slots.find(off);
         if (s == b.slots.end()) throw Error("internal: access to a slot the analysis did not see");
+        const int bi = (int)(&b - &bases[0]);
+        if (pair && !varying_cells.count({bi, off})) {  // one register for both fragments
+            auto o = b.cells_b.find(off);
+            if (o != b.cells_b.end()) return b.cells.emplace(off, o->second).first->second;
+        }
         RC c = class_of_bytes((int)s->second);
         std::string r = fresh(c);
         prologue << "    mov." << mov_type(c) << " " << r << ", 0;\n";
+        if (pair && !varying_cells.count({bi, off})) b.cells_b.emplace(off, r);
         return b.cells.emplace(off, r).first->second;
     }
     std::ostringstream prologue;  // register cells are zeroed ahead of the body
@@ -715,6 +958,10 @@ struct Emitter {
     void block_body(const Block* b) {
         for (const Instr* ins : b->body) {
             comment_location(ins);
+            if (pair && (ins->op == Op::Add || ins->op == Op::Load || ins->op == Op::Ext) && instruction_is_varying(ins)) {
+                pair_instruction(ins);
+                continue;
+            }
             switch (ins->op) {
                 case Op::Add: add(ins); break;
                 case Op::Load: load(ins); break;
@@ -729,8 +976,12 @@ struct Emitter {
         // a block is left only through `break` (block.rs:16-23); control reaching here is what the interpreter rejects
         line("trap;");
     }
+    void define(const Value* v) {
+        if (is_varying(v)) pair_def(v);
+        else def(v);
+    }
     void nested_block(const Block* b, const std::vector<Value*>* result_defs) {
-        for (Value* r : *result_defs) def(r);
+        for (Value* r : *result_defs) define(r);
         std::string end = label(("end_" + sanitize(b->name)).c_str());
         end_label[b] = end;
         dests[b] = result_defs;
@@ -741,7 +992,7 @@ struct Emitter {
     }
     void loop(const Loop* l) {
         if (l->arguments.size() != l->params.size()) throw Error("loop: argument count differs from parameter count");
-        for (Value* p : l->params) def(p);
+        for (Value* p : l->params) define(p);
         parallel_move(l->params, l->arguments, "loop entry");
         std::string head = label(("head_" + sanitize(l->name)).c_str());
         head_label[l] = head;
@@ -984,12 +1235,15 @@ FragmentInterface fragment_interface(const Module& m) {
     return fi;
 }
 
-std::string emit_fragment_inline(const Module& m, const FragmentSite& site, FragmentInterface* info) {
-    check_entry(m);
+namespace {
+
+// one copy of the entry point for `site` (site.fragments fragments); returns false — nothing emitted — when two fragments
+// were asked for and the code cannot be shared
+bool fragment_copy(const Module& m, const FragmentSite& site, const std::string& tag, FragmentInterface* info, std::string* text) {
     const Function* f = m.entry_point;
-    if (site.in.size() != 10 || site.out.size() != 4) throw Error("internal: a fragment call site has 10 inputs and 4 outputs");
-    Emitter e(m, Mode::Inline, "_fs" + std::to_string(site.id) + "_");
-    int in_base, out_base;
+    const int nf = site.fragments;
+    Emitter e(m, Mode::Inline, tag);
+    int in_base, out_base, frag_coord_base = -1;
     {
         Base b;
         b.kind = Base::UserIn;
@@ -1004,6 +1258,8 @@ std::string emit_fragment_inline(const Module& m, const FragmentSite& site, Frag
     std::vector<std::pair<const Variable*, int>> vars;
     for (auto* list : {&m.built_in_inputs, &m.built_in_outputs, &m.globals, &f->locals})
         for (auto& v : *list) vars.emplace_back(&v, e.declare_variable(v));
+    for (auto& v : vars)
+        if (e.bases[v.second].built_in == "frag_coord") frag_coord_base = v.second;
     e.analyze(f->body);
     e.finish_analysis();
     if (!e.bases[in_base].scalarized || !e.bases[out_base].scalarized)
@@ -1012,23 +1268,42 @@ std::string emit_fragment_inline(const Module& m, const FragmentSite& site, Frag
         if (s.second != 4 || s.first % 4) Emitter::unsupported("interpolated inputs are read as 32-bit values");
     for (auto& s : e.bases[out_base].slots)
         if (s.second != 4 || s.first % 4) Emitter::unsupported("fragment outputs are written as 32-bit values");
-
-    // inputs: site.in = frag_coord x y z w, the four interpolated inputs, push constant pointer, descriptor table pointer
-    for (auto& s : e.bases[in_base].slots) {
-        std::string r = e.fresh(RC::B32);
-        e.line("mov.b32 " + r + ", " + site.in[4 + s.first / 4] + ";");
-        e.bases[in_base].cells[s.first] = r;
+    if (frag_coord_base >= 0 && !e.bases[frag_coord_base].scalarized && nf == 2) return false;
+    if (nf == 2) {
+        e.pair = true;
+        if (!e.analyze_pair(f, in_base, frag_coord_base)) return false;
     }
+    if (info) {
+        info->reads_inputs = e.reads_user_inputs;
+        info->reads_frag_coord = e.reads_frag_coord;
+        info->reads_frag_coord_zw = e.reads_frag_coord_zw;
+        for (auto& b : e.bases)  // a frag_coord whose address is taken is read in ways the analysis cannot see
+            if (b.built_in == "frag_coord" && !b.scalarized) info->reads_frag_coord_zw = true;
+    }
+
+    // inputs of fragment k: site.in[8k .. 8k+7] = frag_coord x y z w, the four interpolated inputs
+    for (int k = 0; k < nf; ++k)
+        for (auto& s : e.bases[in_base].slots) {
+            std::string r = e.fresh(RC::B32);
+            e.line("mov.b32 " + r + ", " + site.in[8 * k + 4 + s.first / 4] + ";");
+            (k ? e.bases[in_base].cells_b : e.bases[in_base].cells)[s.first] = r;
+        }
     e.pc_param = site.push_constants_param;
-    if (e.pc_base >= 0 && e.pc_param.empty()) e.bases[e.pc_base].address = e.in_register(site.in[8], RC::B64);
+    if (e.pc_base >= 0 && e.pc_param.empty()) e.bases[e.pc_base].address = e.in_register(site.in[8 * nf], RC::B64);
     for (auto& v : vars) e.variable(*v.first, v.second);
     for (auto& v : vars) {
         Base& b = e.bases[v.second];
         if (b.built_in.empty() || b.built_in == "vertex_position") continue;
         if (b.built_in == "frag_coord") {
-            for (int k = 0; k < 4; ++k) e.set_built_in(b, 4 * k, 4, site.in[k]);
+            for (int c = 0; c < 4; ++c) e.set_built_in(b, 4 * c, 4, site.in[c]);
+            if (nf == 2) {
+                std::swap(b.cells, b.cells_b);
+                for (int c = 0; c < 4; ++c) e.set_built_in(b, 4 * c, 4, site.in[8 + c]);
+                std::swap(b.cells, b.cells_b);
+            }
         } else if (b.built_in == "descriptor_table") {
-            e.set_built_in(b, 0, 8, site.in[9]);
+            e.set_built_in(b, 0, 8, site.in[8 * nf + 1]);
+            if (nf == 2 && b.scalarized && b.cells.count(0)) b.cells_b[0] = b.cells[0];
         } else if (b.built_in == "push_constants") {
             if (!b.scalarized) Emitter::unsupported("the push_constants variable may only be loaded from");
         } else {
@@ -1040,26 +1315,62 @@ std::string emit_fragment_inline(const Module& m, const FragmentSite& site, Frag
     e.nested_block(f->body, &f->body->results);
     // outputs: the cells of user_outputs_block, overridden by the body's results when it returns values
     const auto& rets = f->body->results;
-    for (int k = 0; k < 4; ++k) {
-        if (site.out[k].empty()) continue;
-        if (k < (int)rets.size()) {
-            if (Emitter::reg_class(rets[k]->type) != RC::B32) throw Error("fragment shader result is not a 32-bit value");
-            e.line("mov.b32 " + site.out[k] + ", " + e.def(rets[k]) + ";");
+    for (int c = 0; c < 4; ++c) {
+        if (c < (int)rets.size()) {
+            if (Emitter::reg_class(rets[c]->type) != RC::B32) throw Error("fragment shader result is not a 32-bit value");
+            if (nf == 2) {
+                auto v = e.scalars_of(rets[c]);
+                if (!site.out[c].empty()) e.line("mov.b32 " + site.out[c] + ", " + v.first + ";");
+                if (!site.out[4 + c].empty()) e.line("mov.b32 " + site.out[4 + c] + ", " + v.second + ";");
+            } else if (!site.out[c].empty()) {
+                e.line("mov.b32 " + site.out[c] + ", " + e.def(rets[c]) + ";");
+            }
         } else {
-            auto c = e.bases[out_base].cells.find(4 * k);
-            e.line("mov.b32 " + site.out[k] + ", " + (c != e.bases[out_base].cells.end() ? c->second : std::string("0")) + ";");
+            Base& ob = e.bases[out_base];
+            for (int k = 0; k < nf; ++k) {
+                if (site.out[4 * k + c].empty()) continue;
+                auto& cells = k ? ob.cells_b : ob.cells;
+                auto it = cells.find(4 * c);
+                e.line("mov.b32 " + site.out[4 * k + c] + ", " + (it != cells.end() ? it->second : std::string("0")) + ";");
+            }
         }
-    }
-    if (info) {
-        info->reads_inputs = e.reads_user_inputs;
-        info->reads_frag_coord = e.reads_frag_coord;
-        info->reads_frag_coord_zw = e.reads_frag_coord_zw;
-        for (auto& b : e.bases)  // a frag_coord whose address is taken is read in ways the analysis cannot see
-            if (b.built_in == "frag_coord" && !b.scalarized) info->reads_frag_coord_zw = true;
     }
     std::ostringstream o;
     o << "    {\n" << e.register_declarations() << e.locals.str() << e.prologue.str() << body_prologue << e.body.str() << "    }\n";
-    return o.str();
+    *text = o.str();
+    return true;
+}
+
+}  // namespace
+
+std::string emit_fragment_inline(const Module& m, const FragmentSite& site, FragmentInterface* info) {
+    check_entry(m);
+    const int nf = site.fragments;
+    if ((nf != 1 && nf != 2) || (int)site.in.size() != 8 * nf + 2 || (int)site.out.size() != 4 * nf)
+        throw Error("internal: a fragment call site has 8 inputs and 4 outputs per fragment, and two pointers");
+    const std::string tag = "_fs" + std::to_string(site.id) + "_";
+    std::string text;
+    if (fragment_copy(m, site, tag, info, &text)) {
+        if (info) info->pairs_share_code = nf == 2;
+        return text;
+    }
+    // two fragments whose code cannot be shared: one copy each
+    std::string both;
+    for (int k = 0; k < 2; ++k) {
+        FragmentSite one;
+        one.id = site.id;
+        one.fragments = 1;
+        one.in.assign(site.in.begin() + 8 * k, site.in.begin() + 8 * k + 8);
+        one.in.push_back(site.in[16]);
+        one.in.push_back(site.in[17]);
+        one.out.assign(site.out.begin() + 4 * k, site.out.begin() + 4 * k + 4);
+        one.push_constants_param = site.push_constants_param;
+        std::string t;
+        fragment_copy(m, one, tag + (k ? "b_" : "a_"), k == 0 ? info : nullptr, &t);
+        both += t;
+    }
+    if (info) info->pairs_share_code = false;
+    return both;
 }
 
 }  // namespace kir

@@ -24,8 +24,11 @@ struct EntryInfo {
 // One place where the raster kernels call the fragment program: operands of the surrounding PTX code.
 struct FragmentSite {
     int id = 0;                    // makes the copy's registers and labels unique
-    std::vector<std::string> in;   // 10: frag_coord x y z w, interpolated inputs 0..3, push constant pointer, descriptor table pointer
-    std::vector<std::string> out;  // 4 registers that receive the colour ("" = unused)
+    int fragments = 1;             // 1, or 2: a call that shades two fragments at once (packed f32x2 arithmetic where the shader allows)
+    // per fragment 8 operands: frag_coord x y z w, interpolated inputs 0..3; then the push constant pointer and the
+    // descriptor table pointer: 8 * fragments + 2
+    std::vector<std::string> in;
+    std::vector<std::string> out;  // 4 * fragments registers that receive the colours ("" = unused)
     // when the call is inside a kernel entry: "<entry>_param_0+<offset>" of the push constant block in the kernel's
     // parameter space, so that the shader's push constant loads are ld.param (constant bank operands); otherwise the block
     // is read through the generic pointer in[8]
@@ -35,6 +38,7 @@ struct FragmentInterface {
     bool reads_inputs = false;      // the shader loads from user_inputs_block (the rasteriser must interpolate)
     bool reads_frag_coord = false;
     bool reads_frag_coord_zw = false;  // depth or 1/w: the rasteriser must evaluate the fragment's barycentrics
+    bool pairs_share_code = false;     // two fragments run as one copy of the code (no fragment-dependent control flow, no memory writes)
 };
 
 // PTX symbol for an IR / backend function name (backend.rs:444-459 allows '.', '-', '$' which PTX does not)

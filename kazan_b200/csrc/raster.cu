@@ -494,7 +494,12 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 
 __device__ __forceinline__ float clamp01(float f) { return __saturatef(f); }  // NaN -> 0
 __device__ __forceinline__ float unorm8_to_float(uint32_t u) { return __fdiv_rn((float)u, 255.0f); }
-__device__ __forceinline__ uint32_t float_to_unorm8(float f) { return __float2uint_rn(clamp01(f) * 255.0f); }
+// E.1: clamp to [0, 1], one multiply by 255, round to nearest even.  The rounding is an fp32 add of 1.5 * 2^23: every fp32 in
+// [2^23, 2^24) is an integer, so for t in [0, 255] the sum is 1.5 * 2^23 + rint(t), exactly what cvt.rni gives, and the integer
+// is the low byte of the sum's bit pattern (an FADD on the fp32 pipe where F2I goes through the conversion unit).
+// float_to_unorm8_bits leaves the other bytes of the word as they come (0x4B40 00 xx).
+__device__ __forceinline__ uint32_t float_to_unorm8_bits(float f) { return __float_as_uint(__fadd_rn(__fmul_rn(clamp01(f), 255.0f), 12582912.0f)); }
+__device__ __forceinline__ uint32_t float_to_unorm8(float f) { return float_to_unorm8_bits(f) & 0xffu; }
 
 // VkCompareOp 0..7 = {NEVER, LESS, EQUAL, LESS_OR_EQUAL, GREATER, NOT_EQUAL, GREATER_OR_EQUAL, ALWAYS}: bit 0 = "less passes",
 // bit 1 = "equal passes", bit 2 = "greater passes"; an unordered pair (NaN in the depth buffer) passes NOT_EQUAL and ALWAYS
@@ -711,7 +716,10 @@ __device__ __forceinline__ uint32_t output_merge_lut(const KznGraphicsPipelineSt
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) s[ch] = clamp01(src[ch]);
     if (!NEED_DST) {  // no blending, all channels written
-        return float_to_unorm8(s[0]) | (float_to_unorm8(s[1]) << 8) | (float_to_unorm8(s[2]) << 16) | (float_to_unorm8(s[3]) << 24);
+        // four low bytes -> one word: two byte permutes for the pairs, one for the word
+        const uint32_t rg = __byte_perm(float_to_unorm8_bits(s[0]), float_to_unorm8_bits(s[1]), 0x4440);
+        const uint32_t ba = __byte_perm(float_to_unorm8_bits(s[2]), float_to_unorm8_bits(s[3]), 0x4440);
+        return __byte_perm(rg, ba, 0x5410);
     }
     if (NEED_DST == kDstAlphaOver) {
         // SRC_ALPHA / ONE_MINUS_SRC_ALPHA / ADD on colour and alpha, all channels written (the usual "over" blend):
@@ -771,6 +779,13 @@ __device__ __forceinline__ void interpolate_color(const float iw[3], const float
 // four interpolated inputs, the push constant block, the descriptor table.
 extern "C" __device__ float4 kzn_fs_main(float x, float y, float z, float w, float in0, float in1, float in2, float in3, const void* push_constants,
                                          const void* descriptor_table);
+// ... and for two fragments at once (horizontally adjacent pixels of one triangle): where the shader's control flow does not
+// depend on the fragment, the back end emits ONE copy of its code for both, with packed f32x2 arithmetic
+struct FsPair {
+    float c[8];
+};
+extern "C" __device__ FsPair kzn_fs_main2(float x0, float y0, float z0, float w0, float a0, float a1, float a2, float a3, float x1, float y1, float z1,
+                                          float w1, float b0, float b1, float b2, float b3, const void* push_constants, const void* descriptor_table);
 #endif
 
 // does fragment program FS read anything that needs the fragment's barycentrics (interpolated inputs, depth, 1/w)?  When it
@@ -803,6 +818,35 @@ __device__ __forceinline__ void run_fragment_program(const DrawParams& p, int px
         src[1] = c.y;
         src[2] = c.z;
         src[3] = c.w;
+#endif
+    }
+}
+
+// two invocations: pixels (px, py) and (px + 1, py) of one triangle
+template <uint32_t FS>
+__device__ __forceinline__ void run_fragment_program2(const DrawParams& p, int px, int py, float z0, float z1, const float iw[3], const float col[3][4],
+                                                      const float la[3], const float lb[3], float src0[4], float src1[4]) {
+    if (FS != KZN_FS_COMPILED) {
+        run_fragment_program<FS>(p, px, py, z0, iw, col, la[0], la[1], la[2], src0);
+        run_fragment_program<FS>(p, px + 1, py, z1, iw, col, lb[0], lb[1], lb[2], src1);
+    } else {
+#ifdef KZN_FS_TEMPLATE
+        float a[4] = {0.0f, 0.0f, 0.0f, 0.0f}, b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float w0 = 1.0f, w1 = 1.0f;
+        if (fs_needs_interpolants<FS>(p)) {
+            interpolate_color(iw, col, la[0], la[1], la[2], a);
+            interpolate_color(iw, col, lb[0], lb[1], lb[2], b);
+            w0 = fmaf(la[2], iw[2], fmaf(la[1], iw[1], la[0] * iw[0]));
+            w1 = fmaf(lb[2], iw[2], fmaf(lb[1], iw[1], lb[0] * iw[0]));
+        }
+        const float y = (float)py + 0.5f;
+        const FsPair c = kzn_fs_main2((float)px + 0.5f, y, z0, w0, a[0], a[1], a[2], a[3], (float)(px + 1) + 0.5f, y, z1, w1, b[0], b[1], b[2], b[3],
+                                      p.push_constants, reinterpret_cast<const void*>(p.descriptor_table));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            src0[k] = c.c[k];
+            src1[k] = c.c[4 + k];
+        }
 #endif
     }
 }
@@ -1043,7 +1087,10 @@ __device__ __forceinline__ void span_quad(const DrawParams& p, const TriRec& t, 
             else fs_procedural_orbit_n<PX>(px0, py, p.inv_fb_w, p.inv_fb_h, src);
         } else {
 #pragma unroll
-            for (int k = 0; k < PX; ++k) run_fragment_program<FS>(p, px0 + k, py, zf[k], t.iw, t.col, l0[k], l1[k], l2[k], src[k]);
+            for (int k = 0; k < PX; k += 2) {
+                const float la[3] = {l0[k], l1[k], l2[k]}, lb[3] = {l0[k + 1], l1[k + 1], l2[k + 1]};
+                run_fragment_program2<FS>(p, px0 + k, py, zf[k], zf[k + 1], t.iw, t.col, la, lb, src[k], src[k + 1]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < PX; ++k) {  // branch-free: pixels not live keep their value
@@ -1213,11 +1260,13 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
                     if (FS == KZN_FS_PROCEDURAL_ORBIT) {
                         fs_procedural_orbit_rgba8<kDirectPx>(cxp, row0 + r, p.inv_fb_h, out);
                     } else {  // a compiled program that reads no interpolant (full is zero otherwise): its colour, converted (E.1)
+                        const float none[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-                        for (int k = 0; k < kDirectPx; ++k) {
-                            float src[4];
-                            run_fragment_program<FS>(p, px0 + k, row0 + r, 0.0f, nullptr, nullptr, 0.0f, 0.0f, 0.0f, src);
-                            out[k] = output_merge_lut<kDstNone>(p.st, unorm_lut, src, 0u);
+                        for (int k = 0; k < kDirectPx; k += 2) {
+                            float src0[4], src1[4];
+                            run_fragment_program2<FS>(p, px0 + k, row0 + r, 0.0f, 0.0f, nullptr, nullptr, none, none, src0, src1);
+                            out[k] = output_merge_lut<kDstNone>(p.st, unorm_lut, src0, 0u);
+                            out[k + 1] = output_merge_lut<kDstNone>(p.st, unorm_lut, src1, 0u);
                         }
                     }
 #pragma unroll
@@ -1278,9 +1327,10 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
                         if (FS == KZN_FS_PROCEDURAL_ORBIT) {
                             fs_procedural_orbit_n<kDirectPx>(cxp, py, p.inv_fb_h, src);
                         } else {
+                            const float none[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-                            for (int k = 0; k < kDirectPx; ++k)
-                                run_fragment_program<FS>(p, px0 + k, py, 0.0f, nullptr, nullptr, 0.0f, 0.0f, 0.0f, src[k]);
+                            for (int k = 0; k < kDirectPx; k += 2)
+                                run_fragment_program2<FS>(p, px0 + k, py, 0.0f, 0.0f, nullptr, nullptr, none, none, src[k], src[k + 1]);
                         }
 #pragma unroll
                         for (int k = 0; k < kDirectPx; ++k) {
