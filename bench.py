@@ -203,6 +203,36 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
                       "bytes": nbytes, "rotating_images": n_img, "reps": reps}
         if variants:
             out[label]["copy_b2i_variants_submit"] = variants
+        if label in ("3840x2160", "7680x4320"):
+            # the other two transfer commands north_star names: vkCmdBlitImage (algorithmic bytes: 4 written per destination
+            # texel + 4 read per source texel of the blit region) and the tiled <-> linear layout swizzle (8 per texel)
+            def blit_region(sw, sh, dw, dh):
+                b = abi.ImageBlit()
+                b.srcSubresource = b.dstSubresource = abi.ImageSubresourceLayers(abi.ASPECT_COLOR, 0, 0, 1)
+                b.srcOffsets[0], b.srcOffsets[1] = abi.Offset3D(0, 0, 0), abi.Offset3D(sw, sh, 1)
+                b.dstOffsets[0], b.dstOffsets[1] = abi.Offset3D(0, 0, 0), abi.Offset3D(dw, dh, 1)
+                return [b]
+            rows = {}
+            half = [host.Image(t.data_ptr(), w // 2, h // 2) for t in buffers]  # a half-size source in the same memory
+            for name, srcs, region, moved, filt in (
+                    ("blit_nearest_1to1", [host.Image(t.data_ptr(), w, h) for t in buffers], blit_region(w, h, w, h), 2 * nbytes, abi.FILTER_NEAREST),
+                    ("blit_linear_1to1", [host.Image(t.data_ptr(), w, h) for t in buffers], blit_region(w, h, w, h), 2 * nbytes, abi.FILTER_LINEAR),
+                    ("blit_nearest_2x", half, blit_region(w // 2, h // 2, w, h), nbytes + nbytes // 4, abi.FILTER_NEAREST),
+                    ("blit_linear_2x", half, blit_region(w // 2, h // 2, w, h), nbytes + nbytes // 4, abi.FILTER_LINEAR)):
+                r = max(8, reps // 4)
+                ms = time_region(torch, stream, lambda k: queue.cmd_blit_image(srcs[k % n_img], imgs[(k + 1) % n_img], region, filt), r, 3)
+                rows[name] = {"GBps": round(moved * r / ms / 1e6, 1), "frac_hbm": round(moved * r / ms / 1e6 / hbm_peak, 3)}
+            tw, th = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+            tiled_mem = [torch.empty(tw * th * 4, dtype=torch.uint8, device="cuda") for _ in range(n_img)]
+            tiled = [host.Image(t.data_ptr(), w, h, tiling=abi.TILING_TILED) for t in tiled_mem]
+            lin = [host.Image(t.data_ptr(), w, h) for t in buffers]
+            r = max(8, reps // 2)
+            ms = time_region(torch, stream, lambda k: queue.cmd_convert_tiling(lin[k % n_img], tiled[(k + 1) % n_img]), r, 3)
+            rows["linear_to_tiled"] = {"GBps": round(2 * nbytes * r / ms / 1e6, 1), "frac_hbm": round(2 * nbytes * r / ms / 1e6 / hbm_peak, 3)}
+            ms = time_region(torch, stream, lambda k: queue.cmd_convert_tiling(tiled[k % n_img], imgs[(k + 1) % n_img]), r, 3)
+            rows["tiled_to_linear"] = {"GBps": round(2 * nbytes * r / ms / 1e6, 1), "frac_hbm": round(2 * nbytes * r / ms / 1e6 / hbm_peak, 3)}
+            out[label]["blit_and_swizzle"] = rows
+            del tiled_mem
         del images, buffers
         torch.cuda.empty_cache()
     return out

@@ -27,7 +27,14 @@ struct KznCommandBuffer {
     uint64_t launches = 0;            // kernels per replay
     uint64_t launches_at_begin = 0;
     std::vector<void*> host_copies;   // vkCmdUpdateBuffer data, captured at record time
+    KznRasterScratch* raster_scratch = nullptr;  // pinned: a recorded draw names its buffers
 };
+
+void kzn_command_buffer_uses_raster_scratch(KznCommandBuffer* cb, KznRasterScratch* scratch) {
+    if (!cb || !scratch || cb->raster_scratch) return;
+    cb->raster_scratch = scratch;
+    kzn_raster_scratch_pin(scratch);
+}
 
 void kzn_raster_scratch_destroy(KznRasterScratch* s);  // raster.cu
 
@@ -553,7 +560,12 @@ KznResult kzn_queue_submit(KznQueue* queue, uint32_t count, KznCommandBuffer* co
         KznCommandBuffer* cb = command_buffers[i];
         KZN_VALID(cb && cb->exec && !cb->recording, "command buffer %u is not in the executable state", i);
         KZN_VALID(cb->queue->device == queue->device, "command buffer %u was recorded for another device", i);
+        // a recorded draw works in the recording queue's raster scratch and work counters: replayed on another queue it
+        // would race with that queue's own draws
+        KZN_VALID(!cb->raster_scratch || cb->queue == queue, "command buffer %u records a draw: it can only be submitted to the queue it was recorded on", i);
     }
+    // the whole submission is validated before any of it is enqueued
+    if (fence) KZN_VALID(!fence->pending && !fence->signaled_without_work, "fence must be unsignaled when submitted");
     for (uint32_t i = 0; i < count; ++i) {
         KZN_CUDA(cudaGraphLaunch(command_buffers[i]->exec, queue->stream));
         queue->launches += command_buffers[i]->launches;
@@ -578,6 +590,10 @@ void kzn_command_buffer_destroy(KznCommandBuffer* cb) {
     }
     if (cb->exec) cudaGraphExecDestroy(cb->exec);
     if (cb->graph) cudaGraphDestroy(cb->graph);
+    if (cb->raster_scratch) {
+        cudaStreamSynchronize(cb->queue->stream);  // a replay may still be running in the retired buffers
+        kzn_raster_scratch_unpin(cb->raster_scratch);
+    }
     for (void* p : cb->host_copies) free(p);
     delete cb;
 }

@@ -80,6 +80,12 @@ struct KznSemaphore {
     bool signaled;  // a signal has been enqueued and not yet consumed by a wait
 };
 
+// A recorded draw names the queue's raster scratch buffers in its CUDA graph: the command buffer pins them (raster.cu) until
+// it is destroyed, and may only be submitted to the queue it was recorded on (whose scratch and work counters it uses).
+void kzn_command_buffer_uses_raster_scratch(KznCommandBuffer* cb, KznRasterScratch* scratch);
+void kzn_raster_scratch_pin(KznRasterScratch* s);
+void kzn_raster_scratch_unpin(KznRasterScratch* s);
+
 // error plumbing -----------------------------------------------------------------------------
 void kzn_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
 KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int line);

@@ -85,6 +85,10 @@ struct Emitter {
         std::string packed, s0, s1;
     };
     std::map<const Value*, PairReg> preg;
+    // f32 values made by a packed multiply (or a sign change of one).  ptxas contracts add.rn.f32x2 / sub.rn.f32x2 of a
+    // mul.rn.f32x2 result into one FFMA2 although all of them carry .rn (it does not do that to the scalar forms): a sum with
+    // such an operand is therefore emitted per fragment, as two scalar instructions.
+    std::set<const Value*> packed_products;
     std::string pc_param;     // symbol (+ offset) of the push constant block in parameter space, when it is there
     bool reads_user_inputs = false, reads_frag_coord = false, reads_frag_coord_zw = false;
 
@@ -445,7 +449,52 @@ struct Emitter {
         dests_all[f->body] = &f->body->results;
         while (taint(f->body, &eligible)) {
         }
+        while (mark_products(f->body)) {
+        }
         return eligible;
+    }
+    // packed_products to a fixed point: results of f_mul on varying f32 values, sign changes of those, and the block
+    // results / loop parameters they are passed to
+    bool mark_products(const Block* b) {
+        bool changed = false;
+        auto pass = [&](const std::vector<Value*>& dsts, const std::vector<Value*>& srcs) {
+            for (size_t i = 0; i < dsts.size() && i < srcs.size(); ++i)
+                if (packed_products.count(srcs[i]) && packed_products.insert(dsts[i]).second) changed = true;
+        };
+        for (const Instr* ins : b->body) {
+            switch (ins->op) {
+                case Op::Ext: {
+                    const ExtOp& op = kExtOps[ins->ext];
+                    if (ins->results.size() != 1 || !is_f32(ins->results[0]->type) || !varying.count(ins->results[0])) break;
+                    const bool mul = op.kind == ExtKind::FloatBinary && std::string(op.ptx) == "mul.rn";
+                    const bool sign = op.kind == ExtKind::FloatUnary && packed_products.count(ins->args[0]);
+                    const bool sel = op.kind == ExtKind::Select && (packed_products.count(ins->args[1]) || packed_products.count(ins->args[2]));
+                    if ((mul || sign || sel) && packed_products.insert(ins->results[0]).second) changed = true;
+                    break;
+                }
+                case Op::Break: {
+                    auto it = dests_all.find(ins->block);
+                    if (it != dests_all.end()) pass(*it->second, ins->args);
+                    break;
+                }
+                case Op::Continue: pass(ins->loop->params, ins->args); break;
+                case Op::Branch:
+                    for (auto& c : ins->cases) {
+                        auto it = dests_all.find(c.target);
+                        if (it != dests_all.end()) pass(*it->second, c.results);
+                    }
+                    break;
+                case Op::BlockI:
+                    if (mark_products(ins->block)) changed = true;
+                    break;
+                case Op::LoopI:
+                    pass(ins->loop->params, ins->loop->arguments);
+                    if (mark_products(ins->loop->body)) changed = true;
+                    break;
+                default: break;
+            }
+        }
+        return changed;
     }
     // a varying value's registers: f32 values are kept packed, everything else as two scalars
     PairReg& pair_def(const Value* v) {
@@ -519,7 +568,11 @@ struct Emitter {
         if (ins->op == Op::Ext && ins->results.size() == 1 && is_f32(ins->results[0]->type)) {
             const ExtOp& op = kExtOps[ins->ext];
             const std::string ptx = op.ptx;
-            if ((op.kind == ExtKind::FloatBinary && (ptx == "add.rn" || ptx == "sub.rn" || ptx == "mul.rn")) || op.kind == ExtKind::FloatTernary) {
+            bool sum_of_product = false;
+            if (op.kind == ExtKind::FloatBinary && (ptx == "add.rn" || ptx == "sub.rn"))
+                for (const Value* a : ins->args) sum_of_product = sum_of_product || packed_products.count(a) != 0;
+            if (!sum_of_product &&
+                ((op.kind == ExtKind::FloatBinary && (ptx == "add.rn" || ptx == "sub.rn" || ptx == "mul.rn")) || op.kind == ExtKind::FloatTernary)) {
                 std::string ops;
                 for (const Value* a : ins->args) ops += ", " + packed_of(a);
                 line(ptx + ".f32x2 " + pair_def(ins->results[0]).packed + ops + ";");

@@ -33,6 +33,7 @@
 
 #include <cstddef>
 #include <new>
+#include <vector>
 
 #include "kzn_internal.h"
 
@@ -1950,10 +1951,25 @@ struct KznRasterScratch {
     uint32_t* counters = nullptr;  // [4]: work counter of the direct kernel
     size_t counter_capacity = 0;
     bool attrs_set = false;
+    // Executable command buffers that recorded a draw hold the buffer addresses of that time in their CUDA graphs: while any
+    // such command buffer exists (pins > 0) a buffer that is outgrown is retired instead of freed, and freed when the last
+    // of them is destroyed.
+    int pins = 0;
+    std::vector<void*> retired;
 };
+
+void kzn_raster_scratch_pin(KznRasterScratch* s) {
+    if (s) ++s->pins;
+}
+void kzn_raster_scratch_unpin(KznRasterScratch* s) {
+    if (!s || --s->pins > 0) return;
+    for (void* p : s->retired) cudaFree(p);
+    s->retired.clear();
+}
 
 void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     if (!s) return;
+    for (void* p : s->retired) cudaFree(p);
     cudaFree(s->tris);
     cudaFree(s->boxes);
     cudaFree(s->tile_words);
@@ -1967,7 +1983,8 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
 namespace {
 
 // Scratch grows monotonically; growth happens before any kernel of this draw is enqueued and the old buffer
-// is freed with cudaFree, which synchronises with work still using it.
+// is freed with cudaFree, which synchronises with work still using it — unless an executable command buffer still names
+// it (KznRasterScratch::pins): then it is retired and outlives that command buffer.
 template <typename T>
 KznResult grow(const KznQueue* q, T** ptr, size_t* cap, size_t need) {
     if (need <= *cap) return KZN_SUCCESS;
@@ -1976,7 +1993,10 @@ KznResult grow(const KznQueue* q, T** ptr, size_t* cap, size_t need) {
     size_t n = need + need / 2;
     T* fresh = nullptr;
     KZN_CUDA(cudaMalloc(&fresh, n * sizeof(T)));
-    if (*ptr) cudaFree(*ptr);
+    if (*ptr) {
+        if (q->raster && q->raster->pins > 0) q->raster->retired.push_back(*ptr);
+        else cudaFree(*ptr);
+    }
     *ptr = fresh;
     *cap = n;
     return KZN_SUCCESS;
@@ -2181,6 +2201,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     size_t tiles = (size_t)p.tiles_x * p.tiles_y;
     p.binned = total > kDirectMax;
     if ((r = ensure_scratch(q, (size_t)total, tiles, p.binned != 0))) return r;
+    if (q->recording) kzn_command_buffer_uses_raster_scratch(q->recording, q->raster);  // its graph will name these buffers
     KznRasterScratch* s = q->raster;
     p.tris = s->tris;
     p.boxes = s->boxes;

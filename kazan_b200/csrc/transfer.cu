@@ -21,6 +21,7 @@
 //   merged_transfer_kernel  up to 96 recorded contiguous fills / copies with disjoint ranges as one launch
 // Except for the two bulk (TMA) kernels, launches use programmatic dependent launch (kzn_internal.h).
 // All of them are bandwidth bound; algorithmic bytes per texel are 4 (fill) or 8 (copy).
+#include <cuda.h>  // CUtensorMap and its enumerations (the encode function is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <string.h>
 
@@ -186,6 +187,77 @@ __global__ void __launch_bounds__(32) copy_bulk_kernel(uint8_t* __restrict__ dst
             uint32_t n2 = chunk_len(off2);
             mbar_expect_tx(&full[sj], n2);
             bulk_g2s(smem + sj * kCopyChunk, src + off2, n2, &full[sj]);
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ---- tiled <-> linear layout swizzle through TMA tensor copies ------------------------------------------------------------
+
+// The TILED layout is 16 x 16-texel tiles of 1 KiB, row-major inside and across (oracle/transfer.c).  The LINEAR image is
+// described to the TMA unit as a 4-D tensor (texel in tile row: 16 x 4 B | row in tile: 16, stride = row pitch | tile
+// column: stride 64 B | tile row: stride 16 row pitches), so a box of {16, 16, kSwzTiles, 1} lands in shared memory as
+// kSwzTiles whole tiles in exactly the TILED byte order: the other side of the copy is ONE contiguous bulk copy of
+// kSwzTiles KiB.  No thread computes an address or touches a texel (SASS: UTMALDG / UTMASTG for the tensor side, UBLKCP for the
+// contiguous side); thread 0 of each CTA drives a ring of stages as in copy_bulk_kernel.
+// Measured on B200 (profiles/r02l, bench.py extra.transfer): 4K 0.71 / 0.81 of the HBM peak (to TILED / to LINEAR), 8K 0.82 /
+// 0.86 — box_kernel<4> with per-thread addresses does 0.77 / 0.81 and 0.93 / 0.96 (the tensor box has 64-byte rows, 128 row
+// segments per 8 KiB operation).  So the default path is box_kernel; this one runs with KZN_TRANSFER_PATH=tma.
+constexpr int kSwzTiles = 8;                       // tiles per stage: 8 KiB
+constexpr int kSwzStages = 6;
+constexpr uint32_t kSwzBytes = kSwzTiles * 1024u;
+
+__device__ __forceinline__ void tensor_g2s_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_s2g_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
+// groups of kSwzTiles consecutive tiles of a tile row; `groups_x` per tile row (the last one of a row may be partial: the
+// tensor side clips it, the contiguous side is cut to the tiles that exist)
+template <bool TO_TILED>
+__global__ void __launch_bounds__(32) swizzle_tma_kernel(const __grid_constant__ CUtensorMap linear_map, uint8_t* __restrict__ tiled,
+                                                         uint32_t tiles_x, uint32_t groups_x, uint64_t groups) {
+    kzn_pdl_wait();
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[kSwzStages];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSwzStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const uint64_t n_mine = groups > blockIdx.x ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto load = [&](uint64_t k) {  // group k of this CTA -> its stage
+        const uint64_t g = blockIdx.x + k * (uint64_t)gridDim.x;
+        const uint32_t ty = (uint32_t)(g / groups_x), tx0 = (uint32_t)(g % groups_x) * kSwzTiles;
+        const uint32_t nt = min((uint32_t)kSwzTiles, tiles_x - tx0);
+        const int st = (int)(k % kSwzStages);
+        // the tensor box is always kSwzTiles wide: tiles past the image edge are zero-filled in shared memory (and counted)
+        mbar_expect_tx(&full[st], TO_TILED ? kSwzBytes : nt * 1024u);
+        if (TO_TILED) tensor_g2s_4d(smem + st * kSwzBytes, &linear_map, 0, 0, (int)tx0, (int)ty, &full[st]);
+        else bulk_g2s(smem + st * kSwzBytes, tiled + ((uint64_t)ty * tiles_x + tx0) * 1024u, nt * 1024u, &full[st]);
+    };
+    for (uint64_t j = 0; j < n_mine && j < kSwzStages; ++j) load(j);
+    for (uint64_t k = 0; k < n_mine; ++k) {
+        const int st = (int)(k % kSwzStages);
+        mbar_wait(&full[st], (uint32_t)((k / kSwzStages) & 1));
+        const uint64_t g = blockIdx.x + k * (uint64_t)gridDim.x;
+        const uint32_t ty = (uint32_t)(g / groups_x), tx0 = (uint32_t)(g % groups_x) * kSwzTiles;
+        const uint32_t nt = min((uint32_t)kSwzTiles, tiles_x - tx0);
+        if (TO_TILED) bulk_s2g(tiled + ((uint64_t)ty * tiles_x + tx0) * 1024u, smem + st * kSwzBytes, nt * 1024u);
+        else tensor_s2g_4d(&linear_map, 0, 0, (int)tx0, (int)ty, smem + st * kSwzBytes);  // clipped to the tensor's extent
+        bulk_commit();
+        const uint64_t j = k + kSwzStages - 1;
+        if (k >= 1 && j < n_mine) {
+            bulk_wait_read<1>();
+            load(j);
         }
     }
     bulk_wait_read<0>();
@@ -388,6 +460,7 @@ struct BlitParams {
     int32_t x_lo, y_lo;          // min corner of the destination box
     uint32_t w, h;               // destination box size
     uint32_t filter;
+    float scale_x, scale_y;      // (s1 - s0) / (d1 - d0) per axis: one IEEE division each, done on the host
 };
 
 __device__ __forceinline__ float blit_coord(int32_t i, int32_t d0, int32_t d1, int32_t s0, int32_t s1) {
@@ -404,42 +477,130 @@ __device__ __forceinline__ uint32_t float_to_unorm8(float f) {
     return __float2uint_rn(__fmul_rn(__saturatef(f), 255.0f));
 }
 
+// One thread makes 4 horizontally adjacent destination texels (one 16-byte store where the row allows it); a warp covers
+// 128 texels of a row, the CTA's 8 warps 8 rows.  The per-axis scale is computed once on the host (the same IEEE division
+// blit_coord would repeat per texel), UNORM8 -> float is the division-free exact form unorm8_exact (16 IEEE divisions per
+// LINEAR texel before), source texels are read through the read-only path (neighbouring
+// threads share them in L1).  Same operations in the same order as oracle/transfer.c: results are unchanged.
+__device__ __forceinline__ float blit_coord_scaled(int32_t i, int32_t d0, float scale, int32_t s0) {
+    return __fmaf_rn(__fsub_rn(__fadd_rn((float)i, 0.5f), (float)d0), scale, (float)s0);
+}
+__device__ __forceinline__ uint32_t ld_texel(unsigned long long a) { return __ldg(reinterpret_cast<const uint32_t*>(a)); }
+
+// u / 255.0f, correctly rounded, without a division: q0 = u * fl(1/255), one fused correction step (the remainder
+// u - 255 q0 is exact in an fma).  Equal to __fdiv_rn(u, 255.0f) for all 256 values of u (tests/test_oracle_transfer.py
+// checks the sequence in exact arithmetic): the 256-entry table this replaces cost 16 shared-memory lookups with bank
+// conflicts per LINEAR texel, which was the kernel's bound.
+// byte `ch` of a texel as a float: the byte is placed under the exponent of 2^23 with one byte permute (0x4B0000uu = 2^23 + u)
+// and 2^23 subtracted — exact, and on the ALU / fp32 pipes where the compiler's I2F.U8 goes through the conversion unit (16
+// lanes per clock: 16 conversions per LINEAR texel were the kernel's bound after the table was gone)
+template <int CH>
+__device__ __forceinline__ float texel_byte(uint32_t t) {
+    return __fsub_rn(__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7540u | CH)), 8388608.0f);
+}
+// packed fp32 pairs (FMUL2 / FADD2): two IEEE operations per instruction.  NOTE: ptxas 12.9 contracts add.rn.f32x2 of a
+// mul.rn.f32x2 result into FFMA2 even though both carry .rn (it leaves mul.rn.f32 / add.rn.f32 alone): keep packed products
+// away from packed adds.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b);
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    return *reinterpret_cast<float2*>(&r);
+}
+// ... bytes CH and CH + 1 as a pair
+template <int CH>
+__device__ __forceinline__ float2 texel_bytes(uint32_t t) {
+    const float2 b = make_float2(__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7540u | CH)), __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7540u | (CH + 1))));
+    return add2(b, make_float2(-8388608.0f, -8388608.0f));
+}
+__device__ __forceinline__ float2 unorm8_exact2(float2 x) {
+    const float2 r = make_float2(0.003921568859368563f, 0.003921568859368563f), k = make_float2(255.0f, 255.0f);
+    const float2 q0 = mul2(x, r);
+    return __ffma2_rn(__ffma2_rn(make_float2(-q0.x, -q0.y), k, x), r, q0);
+}
+__device__ __forceinline__ float unorm8_exact(float x) {
+    const float r = 0.003921568859368563f;  // fl(1 / 255)
+    const float q0 = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), r, q0);
+}
+
+template <bool SRC_TILED, bool DST_TILED, bool LINEAR_FILTER>
 __global__ void __launch_bounds__(kThreads) blit_kernel(const __grid_constant__ BlitParams p) {
     kzn_pdl_wait();
-    uint32_t i = blockIdx.x * 32u + (threadIdx.x & 31u);
-    uint32_t j = blockIdx.y * (kThreads / 32) + (threadIdx.x >> 5);
-    if (i >= p.w || j >= p.h) return;
-    int32_t dx = p.x_lo + (int32_t)i, dy = p.y_lo + (int32_t)j;
-    float u = blit_coord(dx, p.dx0, p.dx1, p.sx0, p.sx1);
-    float v = blit_coord(dy, p.dy0, p.dy1, p.sy0, p.sy1);
-    uint32_t out;
-    if (p.filter == KZN_FILTER_NEAREST) {
-        int32_t sx = clampi((int32_t)floorf(u), 0, p.src_w - 1);
-        int32_t sy = clampi((int32_t)floorf(v), 0, p.src_h - 1);
-        out = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, sx, sy);
-    } else {
-        float uu = __fsub_rn(u, 0.5f), vv = __fsub_rn(v, 0.5f);
-        float fu = floorf(uu), fv = floorf(vv);
-        float a = __fsub_rn(uu, fu), b = __fsub_rn(vv, fv);
-        int32_t x0 = clampi((int32_t)fu, 0, p.src_w - 1), x1 = clampi((int32_t)fu + 1, 0, p.src_w - 1);
-        int32_t y0 = clampi((int32_t)fv, 0, p.src_h - 1), y1 = clampi((int32_t)fv + 1, 0, p.src_h - 1);
-        uint32_t t00 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x0, y0);
-        uint32_t t10 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x1, y0);
-        uint32_t t01 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x0, y1);
-        uint32_t t11 = *(const uint32_t*)surf_addr_rt(p.src, p.src_tiled, x1, y1);
-        float na = __fsub_rn(1.0f, a), nb = __fsub_rn(1.0f, b);
-        float w00 = __fmul_rn(na, nb), w10 = __fmul_rn(a, nb), w01 = __fmul_rn(na, b), w11 = __fmul_rn(a, b);
-        out = 0;
+    const uint32_t i0 = (blockIdx.x * 32u + (threadIdx.x & 31u)) * 4u;
+    const uint32_t j = blockIdx.y * (kThreads / 32) + (threadIdx.x >> 5);
+    if (i0 >= p.w || j >= p.h) return;
+    const int32_t dy = p.y_lo + (int32_t)j;
+    const float v = blit_coord_scaled(dy, p.dy0, p.scale_y, p.sy0);
+    uint32_t out[4];
+    if (!LINEAR_FILTER) {
+        const int32_t sy = clampi((int32_t)floorf(v), 0, p.src_h - 1);
+        const unsigned long long row = SRC_TILED ? 0ull : surf_addr<false>(p.src, 0, sy, 0);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            float acc = __fmul_rn(w00, unorm8_to_float((t00 >> (8 * ch)) & 255u));
-            acc = __fadd_rn(acc, __fmul_rn(w10, unorm8_to_float((t10 >> (8 * ch)) & 255u)));
-            acc = __fadd_rn(acc, __fmul_rn(w01, unorm8_to_float((t01 >> (8 * ch)) & 255u)));
-            acc = __fadd_rn(acc, __fmul_rn(w11, unorm8_to_float((t11 >> (8 * ch)) & 255u)));
-            out |= float_to_unorm8(acc) << (8 * ch);
+        for (int k = 0; k < 4; ++k) {
+            const float u = blit_coord_scaled(p.x_lo + (int32_t)(i0 + k), p.dx0, p.scale_x, p.sx0);
+            const int32_t sx = clampi((int32_t)floorf(u), 0, p.src_w - 1);
+            out[k] = ld_texel(SRC_TILED ? surf_addr<true>(p.src, sx, sy, 0) : row + 4ull * (uint32_t)sx);
+        }
+    } else {
+        const float vv = __fsub_rn(v, 0.5f), fv = floorf(vv), b = __fsub_rn(vv, fv), nb = __fsub_rn(1.0f, b);
+        const int32_t y0 = clampi((int32_t)fv, 0, p.src_h - 1), y1 = clampi((int32_t)fv + 1, 0, p.src_h - 1);
+        const unsigned long long row0 = SRC_TILED ? 0ull : surf_addr<false>(p.src, 0, y0, 0), row1 = SRC_TILED ? 0ull : surf_addr<false>(p.src, 0, y1, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float u = blit_coord_scaled(p.x_lo + (int32_t)(i0 + k), p.dx0, p.scale_x, p.sx0);
+            const float uu = __fsub_rn(u, 0.5f), fu = floorf(uu), a = __fsub_rn(uu, fu), na = __fsub_rn(1.0f, a);
+            const int32_t x0 = clampi((int32_t)fu, 0, p.src_w - 1), x1 = clampi((int32_t)fu + 1, 0, p.src_w - 1);
+            const uint32_t t00 = ld_texel(SRC_TILED ? surf_addr<true>(p.src, x0, y0, 0) : row0 + 4ull * (uint32_t)x0);
+            const uint32_t t10 = ld_texel(SRC_TILED ? surf_addr<true>(p.src, x1, y0, 0) : row0 + 4ull * (uint32_t)x1);
+            const uint32_t t01 = ld_texel(SRC_TILED ? surf_addr<true>(p.src, x0, y1, 0) : row1 + 4ull * (uint32_t)x0);
+            const uint32_t t11 = ld_texel(SRC_TILED ? surf_addr<true>(p.src, x1, y1, 0) : row1 + 4ull * (uint32_t)x1);
+            const float w00 = __fmul_rn(na, nb), w10 = __fmul_rn(a, nb), w01 = __fmul_rn(na, b), w11 = __fmul_rn(a, b);
+            // two channels per instruction: packed fmul / fadd / fma (.f32x2: FMUL2, FADD2, FFMA2) do two IEEE operations
+            // with the results of the scalar instructions — the same sequence per channel as oracle/transfer.c
+            uint32_t bits[4];
+            auto channels = [&](float2 c00, float2 c10, float2 c01, float2 c11, uint32_t& lo, uint32_t& hi) {
+                // products packed, sums scalar: ptxas contracts an add.rn.f32x2 of a mul.rn.f32x2 into one FFMA2 (one rounding
+                // where the oracle has two) although it leaves the scalar forms alone, so a packed product never meets a
+                // packed add here
+                const float2 p00 = mul2(make_float2(w00, w00), unorm8_exact2(c00)), p10 = mul2(make_float2(w10, w10), unorm8_exact2(c10));
+                const float2 p01 = mul2(make_float2(w01, w01), unorm8_exact2(c01)), p11 = mul2(make_float2(w11, w11), unorm8_exact2(c11));
+                const float ax = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p10.x), p01.x), p11.x);
+                const float ay = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p10.y), p01.y), p11.y);
+                // E.1 with the rounding done by an fp32 add of 1.5 * 2^23 (exactly cvt.rni for [0, 255]): the byte is the low
+                // byte of the sum
+                const float2 m = mul2(make_float2(__saturatef(ax), __saturatef(ay)), make_float2(255.0f, 255.0f));
+                lo = __float_as_uint(__fadd_rn(m.x, 12582912.0f));
+                hi = __float_as_uint(__fadd_rn(m.y, 12582912.0f));
+            };
+            channels(texel_bytes<0>(t00), texel_bytes<0>(t10), texel_bytes<0>(t01), texel_bytes<0>(t11), bits[0], bits[1]);
+            channels(texel_bytes<2>(t00), texel_bytes<2>(t10), texel_bytes<2>(t01), texel_bytes<2>(t11), bits[2], bits[3]);
+            out[k] = __byte_perm(__byte_perm(bits[0], bits[1], 0x4440), __byte_perm(bits[2], bits[3], 0x4440), 0x5410);
         }
     }
-    *(uint32_t*)surf_addr_rt(p.dst, p.dst_tiled, dx, dy) = out;
+    const int32_t dx = p.x_lo + (int32_t)i0;
+    const unsigned long long da = surf_addr<DST_TILED>(p.dst, dx, dy, 0);
+    // the 4 texels are contiguous in memory when the row is LINEAR, or TILED and they do not cross a tile (dx % 4 == 0)
+    const bool contiguous = !DST_TILED || (dx & 3) == 0;
+    if (i0 + 4u <= p.w && contiguous && (da & 15ull) == 0) {
+        st_stream16((void*)da, make_uint4(out[0], out[1], out[2], out[3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < p.w) *(uint32_t*)surf_addr<DST_TILED>(p.dst, dx + k, dy, 0) = out[k];
+    }
+}
+
+typedef void (*BlitKernel)(BlitParams);
+BlitKernel blit_kernel_for(bool src_tiled, bool dst_tiled, bool linear) {
+    static const BlitKernel table[8] = {blit_kernel<false, false, false>, blit_kernel<false, false, true>, blit_kernel<false, true, false>,
+                                        blit_kernel<false, true, true>,   blit_kernel<true, false, false>, blit_kernel<true, false, true>,
+                                        blit_kernel<true, true, false>,   blit_kernel<true, true, true>};
+    return table[(src_tiled ? 4 : 0) | (dst_tiled ? 2 : 0) | (linear ? 1 : 0)];
 }
 
 // ---- host-side launch logic ------------------------------------------------------------------------------
@@ -457,7 +618,15 @@ Path transfer_path() {
 
 int grid_for(const KznQueue* q, unsigned long long items) {
     unsigned long long blocks = (items + (unsigned long long)kThreads * kUnroll - 1) / ((unsigned long long)kThreads * kUnroll);
-    unsigned long long cap = (unsigned long long)q->device->sm_count * 8;  // multiple of the SM count
+    // A multiple of the SM count.  The cap is what balances a medium-sized command: with 8 CTAs per SM a 4K image (2025
+    // blocks of work) ran as 1.7 grid-stride sweeps — every CTA waits for the ones that do two — and lost 15 %; with the
+    // blocks handed out by the hardware one by one the last wave is a fraction of a sweep.  (KZN_GRID_PER_SM overrides.)
+    static const unsigned long long per_sm = [] {
+        const char* e = getenv("KZN_GRID_PER_SM");
+        const long v = e ? atol(e) : 0;
+        return (unsigned long long)(v > 0 ? v : 64);
+    }();
+    unsigned long long cap = (unsigned long long)q->device->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     return blocks ? (int)blocks : 1;
 }
@@ -1002,6 +1171,8 @@ KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const Kzn
         p.w = (uint32_t)(d0->x < d1->x ? d1->x - d0->x : d0->x - d1->x);
         p.h = (uint32_t)(d0->y < d1->y ? d1->y - d0->y : d0->y - d1->y);
         p.filter = filter;
+        p.scale_x = (float)(p.sx1 - p.sx0) / (float)(p.dx1 - p.dx0);
+        p.scale_y = (float)(p.sy1 - p.sy0) / (float)(p.dy1 - p.dy0);
         int32_t z_lo = d0->z < d1->z ? d0->z : d1->z, z_hi = d0->z < d1->z ? d1->z : d0->z;
         for (uint32_t l = 0; l < b->srcSubresource.layerCount; ++l)
             for (int32_t k = z_lo; k < z_hi; ++k) {
@@ -1011,14 +1182,70 @@ KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const Kzn
                 sz = sz < 0 ? 0 : (sz > (int32_t)src->depth - 1 ? (int32_t)src->depth - 1 : sz);
                 p.src = lower(image_box(src, 0, 0, sz, b->srcSubresource.baseArrayLayer + l));
                 p.dst = lower(image_box(dst, 0, 0, k, b->dstSubresource.baseArrayLayer + l));
-                dim3 grid((p.w + 31) / 32, (p.h + kThreads / 32 - 1) / (kThreads / 32));
+                dim3 grid((p.w + 127) / 128, (p.h + kThreads / 32 - 1) / (kThreads / 32));
                 kzn_timing_begin(queue);
-                kzn_launch_pdl(blit_kernel, grid, dim3(kThreads), 0, queue->stream, p);
+                kzn_launch_pdl(blit_kernel_for(p.src_tiled != 0, p.dst_tiled != 0, filter != KZN_FILTER_NEAREST), grid, dim3(kThreads), 0, queue->stream, p);
                 if ((r = kzn_launched(queue, "blit_kernel"))) return r;
             }
     }
     return KZN_SUCCESS;
 }
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// LINEAR <-> TILED copy of one whole slice through the TMA unit; false: not applicable (the caller uses box_kernel)
+bool swizzle_tma(KznQueue* q, const KznImageDesc* linear, uint64_t linear_base, uint64_t tiled_base, bool to_tiled, KznResult* result) {
+    *result = KZN_SUCCESS;
+    const uint32_t w = linear->width, h = linear->height;
+    // whole tiles only: a partial tile would have its padding written by the tensor copy (zero fill), which box_kernel never
+    // touches; the tensor map needs 16-byte aligned bases and pitches
+    if (transfer_path() != Path::Tma || w % 16 || h % 16 || linear_base % 16 || tiled_base % 16 || (uint64_t)w * h < (1u << 16)) return false;
+    EncodeTiledFn encode = encode_tiled();
+    if (!encode) return false;
+    const uint32_t tiles_x = w / 16, tiles_y = h / 16;
+    const uint64_t pitch = (uint64_t)w * 4;
+    alignas(64) CUtensorMap map;
+    const cuuint64_t dims[4] = {16, 16, tiles_x, tiles_y};
+    const cuuint64_t strides[3] = {pitch, 64, 16 * pitch};  // bytes, of dimensions 1..3
+    const cuuint32_t box[4] = {16, 16, (cuuint32_t)(tiles_x < (uint32_t)kSwzTiles ? tiles_x : kSwzTiles), 1};
+    const cuuint32_t elem[4] = {1, 1, 1, 1};
+    if (pitch >= (1ull << 40) / 16) return false;
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)(uintptr_t)linear_base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (tiles_x < (uint32_t)kSwzTiles) return false;  // (the kernel's stages are kSwzTiles wide)
+    if ((*result = kzn_flush_transfers(q))) return true;
+    static bool attr_set = false;
+    const int smem = kSwzStages * (int)kSwzBytes;
+    if (!attr_set) {
+        cudaFuncSetAttribute(swizzle_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(swizzle_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const uint32_t groups_x = (tiles_x + kSwzTiles - 1) / kSwzTiles;
+    const uint64_t groups = (uint64_t)groups_x * tiles_y;
+    const uint64_t cap = (uint64_t)q->device->sm_count * 4;  // 4 rings of 48 KiB per SM
+    const int grid = (int)(groups < cap ? groups : cap);
+    kzn_timing_begin(q);
+    if (to_tiled) swizzle_tma_kernel<true><<<grid, 32, smem, q->stream>>>(map, (uint8_t*)(uintptr_t)tiled_base, tiles_x, groups_x, groups);
+    else swizzle_tma_kernel<false><<<grid, 32, smem, q->stream>>>(map, (uint8_t*)(uintptr_t)tiled_base, tiles_x, groups_x, groups);
+    *result = kzn_launched(q, "swizzle_tma_kernel");
+    return true;
+}
+
+}  // namespace
 
 KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* src, const KznImageDesc* dst) {
     KznResult r = kzn_queue_enter_transfer(queue);
@@ -1027,6 +1254,20 @@ KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* src, const
     KZN_VALID(src->format == dst->format && src->width == dst->width && src->height == dst->height && src->depth == dst->depth &&
                   src->array_layers == dst->array_layers,
               "convert_tiling: images differ in more than tiling");
+    if (src->tiling != dst->tiling) {
+        // every slice is one LINEAR <-> TILED copy of whole tiles: the TMA unit does the swizzle
+        const KznImageDesc* lin = src->tiling == KZN_TILING_LINEAR ? src : dst;
+        const KznImageDesc* til = src->tiling == KZN_TILING_LINEAR ? dst : src;
+        const uint64_t slices = (uint64_t)src->depth * src->array_layers;
+        bool all = true;
+        for (uint64_t sl = 0; sl < slices && all; ++sl) {
+            KznResult tr;
+            all = swizzle_tma(queue, lin, lin->address + sl * kzn_slice_pitch(lin), til->address + sl * kzn_slice_pitch(til), dst->tiling == KZN_TILING_TILED, &tr);
+            if (all && tr) return tr;
+            if (!all && sl != 0) return KZN_ERROR_DEVICE_LOST;  // (applicability does not depend on the slice)
+        }
+        if (all) return KZN_SUCCESS;
+    }
     Box sb = image_box(src, 0, 0, 0, 0), db = image_box(dst, 0, 0, 0, 0);
     return launch_box(queue, &sb, db, src->width, src->height, src->depth * src->array_layers, false, 0);
 }

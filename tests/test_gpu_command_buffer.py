@@ -219,3 +219,70 @@ def test_merged_batch_is_flushed_by_a_draw_and_by_odd_sizes(gpu):
     assert odd.download().tolist() == [0] * 4 + [255] * 8 + [0] * 52
     cb.destroy()
     gpu.release()
+
+
+def test_recorded_draw_survives_scratch_growth_and_stays_on_its_queue(gpu):
+    """A recorded draw names the queue's raster scratch in its graph.  A later, larger immediate draw outgrows that scratch:
+    the old buffers must stay alive for the command buffer (retired, not freed), so its replay still renders the oracle's
+    frame; and the command buffer is refused by any queue other than the one it was recorded on."""
+    scene = next(s for s in cases.draw_scenes() if s.name == "mesh_40x20_depth_blend")
+    big = next(s for s in cases.draw_scenes() if s.name == "mesh_200x100_depth_blend")
+    want_c, want_d, _ = scene.run_oracle()
+    color0, depth0 = scene._initial()
+    dev = host.Device(0)
+    q, other = dev.create_queue(), dev.create_queue()
+    mem = [dev.allocate(a.nbytes) for a in (color0, depth0, scene.vertices, scene.indices)]
+
+    def reset():
+        for m, a in zip(mem, (color0, depth0, scene.vertices, scene.indices)):
+            a = np.ascontiguousarray(a)
+            q.upload(m.address, a.ctypes.data, a.nbytes)
+        q.wait_idle()
+
+    reset()
+    fb = scene._framebuffer(mem[0].address, mem[1].address)
+    vi = abi.VertexInput(mem[2].address, scene.vertices.nbytes, scene.stride, 0, scene.pos_comps, scene.color_offset)
+    q.reserve_draw(scene.count // 3, scene.width, scene.height)
+    with q.record() as cb:
+        q.cmd_draw_indexed(scene.state, fb, scene.viewport, scene.scissor, vi, mem[3].address, scene.indices.nbytes, scene.index_type,
+                           scene.count, scene.instances, scene.first, scene.vertex_offset, 0)
+    # an immediate draw 25 times the size on the same queue: every scratch buffer is reallocated
+    bc, bd = big._initial()
+    bmem = [dev.allocate(a.nbytes) for a in (bc, bd, big.vertices, big.indices)]
+    for m, a in zip(bmem, (bc, bd, big.vertices, big.indices)):
+        a = np.ascontiguousarray(a)
+        q.upload(m.address, a.ctypes.data, a.nbytes)
+    bfb = big._framebuffer(bmem[0].address, bmem[1].address)
+    bvi = abi.VertexInput(bmem[2].address, big.vertices.nbytes, big.stride, 0, big.pos_comps, big.color_offset)
+    q.cmd_draw_indexed(big.state, bfb, big.viewport, big.scissor, bvi, bmem[3].address, big.indices.nbytes, big.index_type, big.count,
+                       big.instances, big.first, big.vertex_offset, 0)
+    q.wait_idle()
+    # fresh allocations of the sizes just released would land in freed scratch, were it freed
+    junk = [dev.allocate(1 << 20) for _ in range(8)]
+    for j in junk:
+        q.cmd_fill_buffer(j.address, 1 << 20, 0, 1 << 20, 0xDEADBEEF)
+    q.wait_idle()
+    for round_ in range(2):
+        reset()
+        q.submit([cb])
+        q.wait_idle()
+        got_c, got_d = np.empty_like(color0), np.empty_like(depth0)
+        q.download(got_c.ctypes.data, mem[0].address, got_c.nbytes)
+        q.download(got_d.ctypes.data, mem[1].address, got_d.nbytes)
+        q.wait_idle()
+        assert got_d.tobytes() == want_d.tobytes() and got_c.tobytes() == want_c.tobytes(), round_
+    with pytest.raises(host.KazanError) as e:
+        other.submit([cb])
+    assert e.value.code == abi.ERROR_VALIDATION_FAILED and "recorded on" in str(e.value)
+    # a fence that is already pending is refused before anything is enqueued
+    fence = dev.create_fence()
+    q.submit([cb], fence)
+    before = q.launch_count
+    with pytest.raises(host.KazanError):
+        q.submit([cb], fence)
+    assert q.launch_count == before
+    fence.wait()
+    cb.destroy(); fence.destroy()
+    for m in mem + bmem + junk:
+        m.free()
+    other.destroy(); q.destroy(); dev.destroy()

@@ -175,3 +175,27 @@ def test_full_size_fill_4k_with_the_compiled_orbit_shader(gpu, compiled):
     b, _, st_b = sc.run_gpu(gpu, compiled=compiled)
     assert st_b.fragments_covered == W * H == st_a.fragments_covered
     assert a.tobytes() == b.tobytes()
+
+
+def test_compiled_shader_keeps_products_and_sums_apart(gpu):
+    """No contraction: f_mul followed by f_add / f_sub are two roundings (ir.h), also when two fragments share one copy of the
+    code with packed f32x2 arithmetic — ptxas contracts add.rn.f32x2 of a mul.rn.f32x2 result into FFMA2, which the emitter
+    avoids.  fs_mul_add.kazan-ir turns the difference between (a * b + c) and fma(a, b, c) into the colour, so a contracted
+    product would show as a frame of constant grey.  Checked against the SIMT interpreter on every pixel."""
+    from oracle import ir_oracle as iro
+    from oracle import ir_simt as sim
+    from tests import util
+    W, H = 64, 36
+    text = v2.program_text("fs_mul_add")
+    m = backend.IrModule.parse(text, 2)
+    prog = backend.FragmentProgram(gpu.device, m)
+    sc = util.Scene("mul_add", W, H, util.FULLSCREEN_TRIANGLE, state=util.pipeline_state(fs=abi.FS_PROCEDURAL_ORBIT))
+    got, _, st = sc.run_gpu(gpu, compiled={abi.FS_PROCEDURAL_ORBIT: prog})
+    assert st.fragments_covered == W * H
+    coords = [(x + 0.5, y + 0.5, 0.0, 1.0) for y in range(H) for x in range(W)]
+    out = np.array(sim.run_fragments(iro.parse_module(text, 2), coords, [(0, 0, 0, 0)] * len(coords)), dtype=np.uint32).view(np.float32)
+    want = np.rint(np.clip(out, np.float32(0), np.float32(1)) * np.float32(255.0)).astype(np.uint8).reshape(H, W, 4)
+    frame = got[:W * H * 4].reshape(H, W, 4)
+    assert len(np.unique(want[..., :3])) > 2, "the shader must expose the two roundings"
+    assert np.array_equal(frame, want)
+    prog.destroy(); m.destroy()

@@ -207,3 +207,28 @@ def test_image_sizes_that_overflow_are_rejected(oracle):
     desc = abi.ImageDesc(0x1000, abi.FORMAT_R8G8B8A8_UNORM, 0, 65536, 65536, 256, 256, 1, 0)  # 2^50 bytes: large but representable
     size, align = C.c_uint64(), C.c_uint64()
     assert oracle.kzo_image_memory_requirements(C.byref(desc), C.byref(size), C.byref(align)) == 0 and size.value == 1 << 50
+
+
+def test_division_free_unorm8_to_float_is_exact():
+    """transfer.cu `unorm8_exact`: q0 = u * fl(1/255); q = fma(fma(-q0, 255, u), fl(1/255), q0) equals the correctly rounded
+    u / 255.0f (E.1) for every byte — checked here in exact rational arithmetic with explicit roundings to fp32."""
+    from fractions import Fraction
+    f = np.float32
+
+    def rnd(fr):
+        x = f(float(fr))
+        cands = [np.nextafter(x, f(-np.inf)), x, np.nextafter(x, f(np.inf))]
+        best = min(cands, key=lambda t: abs(Fraction(float(t)) - fr))
+        ties = [t for t in cands if abs(Fraction(float(t)) - fr) == abs(Fraction(float(best)) - fr)]
+        if len(ties) > 1:  # halfway: to the even significand
+            best = next(t for t in ties if (int(np.float32(t).view(np.uint32)) & 1) == 0)
+        return best
+
+    rcp = f(1.0) / f(255.0)
+    assert float(rcp) == 0.003921568859368563
+    for u in range(256):
+        q0 = rnd(Fraction(u) * Fraction(float(rcp)))
+        rem = rnd(Fraction(u) - Fraction(float(q0)) * 255)
+        assert Fraction(float(rem)) == Fraction(u) - Fraction(float(q0)) * 255, "the remainder is exact"
+        q = rnd(Fraction(float(q0)) + Fraction(float(rem)) * Fraction(float(rcp)))
+        assert q == f(u) / f(255.0), u
