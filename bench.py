@@ -737,7 +737,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "fullscreen-triangle procedural fragment shader at 3840x2160 R8G8B8A8_UNORM (configs[2])"
-                               + ("" if world == 1 else f"; {world} bands of 3840x2160, NCCL composite to rank 0"),
+                               + ("" if world == 1 else f"; {world} bands of 3840x2160, composite to rank 0 over NVLink peer memory ("
+                                  + {"push": "copy-engine push of each band", "store": "raster kernels store into rank 0's image",
+                                     "nccl": "grouped NCCL send/recv"}[args.composite] + ")"),
                    "frame": [W, total_h],
                    "fragment_program": ("procedural orbit, 32 fp32 fma iterations; " +
                                         ("compiled from shader-compiler-ir (fs_orbit.kazan-ir) by the PTX back end into the raster kernel"
@@ -753,8 +755,11 @@ def run_ours(args):
             "nccl": "grouped NCCL send/recv of the bands to rank 0 after the draw"}[ft.mode]
         # the presenter ingests (world-1) bands per frame over its NVLink port: measured peer-copy bandwidth 770 GB/s per direction
         ingest_gbps = sf.composite_bytes() / (ms_per_step * 1e-3) / 1e9
-        line["nvlink"] = {"presenter_ingest_GBps": ingest_gbps, "peak": 770.0, "frac": ingest_gbps / 770.0,
-                          "peak_source": "B200_PROFILING.md measured peer copy, per direction"}
+        line["nvlink"] = {"bound": "presenter_ingest", "presenter_ingest_GBps": ingest_gbps, "peak": 770.0, "frac": ingest_gbps / 770.0,
+                          "peak_source": "B200_PROFILING.md measured peer copy, per direction",
+                          "note": "weak-scaled fill is link-bound by construction: one GPU shades 4 B/pixel x ~200 Gpixel/s = 800 GB/s of pixels, more than "
+                                  "one NVLink port takes (770 GB/s measured), so composite-to-one-GPU cannot scale past one band's worth of ingest; "
+                                  "extra.split_frame_8k_4Mtri (strong scaling of a geometry-bound frame) is the scaling curve to track"}
 
     # ---- e2e: the same frame through the same calls with HOST buffers: vertex upload, draw, composite, frame read-back.
     # Every step uploads its vertices from pinned memory and delivers its finished frame to pinned host memory; the

@@ -238,6 +238,10 @@ KZN_API KznResult kzn_queue_last_kernel_ms(KznQueue* queue, float* ms);
  * (0 = none) instead of hanging the GPU. */
 KZN_API KznResult kzn_cmd_signal_flag(KznQueue* queue, uint64_t flag_address, uint64_t add);
 KZN_API KznResult kzn_cmd_wait_flag(KznQueue* queue, uint64_t flag_address, uint64_t expected, uint64_t status_address);
+/* ... until EVERY one of flag_count consecutive 64-bit flags is >= expected (one flag per band rank: an aggregated counter
+ * cannot tell two frames of a fast rank from one frame each of two ranks) */
+KZN_API KznResult kzn_cmd_wait_flags(KznQueue* queue, uint64_t first_flag_address, uint32_t flag_count, uint64_t expected,
+                                     uint64_t status_address);
 
 /* device-to-device copy on the copy engines (no SM time): local or imported peer addresses; used to push a rendered band
  * to the presenting GPU while the SMs already render the next frame */
@@ -431,6 +435,28 @@ KZN_API KznResult kzn_cmd_draw_indexed(KznQueue* queue, const KznGraphicsPipelin
                                        uint32_t index_type, uint32_t index_count,
                                        uint32_t instance_count, uint32_t first_index,
                                        int32_t vertex_offset, uint32_t first_instance);
+/* ------------------------------------------------------------------------------------------ */
+/* split frames: one frame over the GPUs of a box, in one process                */
+/* The reference exposes one physical device (api_impl.rs:5092-5119): the split is internal to the driver.  A
+ * KznSplitFrame opens the given devices, gives each a render queue, a whole-frame colour (and depth) image in its own HBM
+ * and a band of rows (starts on multiples of 16, the raster brick height); rank 0 presents.  The host records the SAME draws on
+ * every rank's queue with that rank's framebuffer (kzn_split_frame_framebuffer sets band_y0 / band_y1; geometry is
+ * replicated: vertex and index buffers live on every device).  kzn_split_frame_composite is the one exchange step of the
+ * frame: every band is pushed into the presenter's image by the copy engines over NVLink peer memory, ordered after the
+ * band's rendering, and the presenter's queue is ordered after the pushes — all stream work, no host round trip. */
+typedef struct KznSplitFrame KznSplitFrame;
+KZN_API KznResult kzn_split_frame_create(uint32_t device_count, const int32_t* device_ordinals, uint32_t width, uint32_t height,
+                                         uint32_t with_depth, KznSplitFrame** split_frame);
+KZN_API void kzn_split_frame_destroy(KznSplitFrame* split_frame);
+KZN_API uint32_t kzn_split_frame_device_count(const KznSplitFrame* split_frame);
+KZN_API KznDevice* kzn_split_frame_device(const KznSplitFrame* split_frame, uint32_t rank);
+KZN_API KznQueue* kzn_split_frame_queue(const KznSplitFrame* split_frame, uint32_t rank);
+KZN_API KznResult kzn_split_frame_framebuffer(const KznSplitFrame* split_frame, uint32_t rank, KznFramebuffer* framebuffer);
+KZN_API KznResult kzn_split_frame_composite(KznSplitFrame* split_frame);
+KZN_API uint64_t kzn_split_frame_present_address(const KznSplitFrame* split_frame); /* the assembled image, on rank 0's device */
+KZN_API KznQueue* kzn_split_frame_present_queue(const KznSplitFrame* split_frame);  /* ordered after every composite */
+KZN_API KznResult kzn_split_frame_wait_idle(KznSplitFrame* split_frame);
+
 /* where (device address of a KznDrawStatistics, zeroed by the caller) the next draws accumulate
  * counters; 0 disables */
 KZN_API KznResult kzn_queue_set_draw_statistics(KznQueue* queue, uint64_t stats_address);

@@ -212,6 +212,7 @@ PROTOTYPES = {
     "kzn_queue_signal_semaphore": (i32, [vp, vp]),
     "kzn_queue_wait_semaphore": (i32, [vp, vp]),
     "kzn_queue_copy_dma": (i32, [vp, u64, u64, u64]),
+    "kzn_cmd_wait_flags": (i32, [vp, u64, u32, u64, u64]),
     "kzn_calibrate_fp32_issue": (i32, [vp, P(f32)]),
     "kzn_cmd_pipeline_barrier": (i32, [vp]),
     "kzn_fence_create": (i32, [vp, i32, P(vp)]),
@@ -237,6 +238,16 @@ PROTOTYPES = {
     "kzn_cmd_draw_indexed": (i32, [vp, P(GraphicsPipelineState), P(Framebuffer), P(Viewport), P(Rect2D),
                                    P(VertexInput), u64, u64, u32, u32, u32, u32, i32, u32]),
     "kzn_queue_set_draw_statistics": (i32, [vp, u64]),
+    "kzn_split_frame_create": (i32, [u32, P(i32), u32, u32, u32, P(vp)]),
+    "kzn_split_frame_destroy": (None, [vp]),
+    "kzn_split_frame_device_count": (u32, [vp]),
+    "kzn_split_frame_device": (vp, [vp, u32]),
+    "kzn_split_frame_queue": (vp, [vp, u32]),
+    "kzn_split_frame_framebuffer": (i32, [vp, u32, P(Framebuffer)]),
+    "kzn_split_frame_composite": (i32, [vp]),
+    "kzn_split_frame_present_address": (u64, [vp]),
+    "kzn_split_frame_present_queue": (vp, [vp]),
+    "kzn_split_frame_wait_idle": (i32, [vp]),
 }
 
 

@@ -40,6 +40,22 @@ __global__ void wait_flag_kernel(const unsigned long long* flag, unsigned long l
     }
 }
 
+// the same for `count` consecutive flags, one thread each: returns when every one of them is >= expected
+__global__ void wait_flags_kernel(const unsigned long long* flags, unsigned long long expected, uint32_t* status) {
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long* flag = flags + threadIdx.x;
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= expected) return;
+        if (globaltimer_ns() - t0 > kWaitTimeoutNs) {
+            if (status) atomicExch_system(status, 1u);
+            return;
+        }
+        __nanosleep(200);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -100,6 +116,16 @@ KznResult kzn_cmd_wait_flag(KznQueue* queue, uint64_t flag_address, uint64_t exp
     KZN_VALID(status_address % 4 == 0, "status address must be 4-byte aligned");
     wait_flag_kernel<<<1, 1, 0, queue->stream>>>((const unsigned long long*)(uintptr_t)flag_address, expected, (uint32_t*)(uintptr_t)status_address);
     return kzn_launched(queue, "wait_flag_kernel");
+}
+
+KznResult kzn_cmd_wait_flags(KznQueue* queue, uint64_t first_flag_address, uint32_t flag_count, uint64_t expected, uint64_t status_address) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(first_flag_address && first_flag_address % 8 == 0, "flag address must be 8-byte aligned");
+    KZN_VALID(flag_count >= 1 && flag_count <= 1024, "kzn_cmd_wait_flags: 1 .. 1024 flags");
+    KZN_VALID(status_address % 4 == 0, "status address must be 4-byte aligned");
+    wait_flags_kernel<<<1, flag_count, 0, queue->stream>>>((const unsigned long long*)(uintptr_t)first_flag_address, expected, (uint32_t*)(uintptr_t)status_address);
+    return kzn_launched(queue, "wait_flags_kernel");
 }
 
 }  // extern "C"

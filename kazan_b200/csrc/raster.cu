@@ -143,26 +143,14 @@ struct DrawParams {
     // compiled fragment programs (KZN_FS_COMPILED): what vkCmdBindDescriptorSets / vkCmdPushConstants left on the queue, and
     // what the program reads (bit 0: it needs interpolated inputs or the z / w of frag_coord, so no coverage shortcut applies)
     uint32_t fs_flags;
+    uint32_t rows_first;  // setup: decide on y before x, z and the colours are fetched (the clip rectangle keeps under half of the viewport's rows)
     unsigned long long descriptor_table;
     unsigned char push_constants[KZN_MAX_PUSH_CONSTANTS_SIZE];
 };
 
 // ---- setup ------------------------------------------------------------------------------------------------
 
-// robust fetch of one vertex's position (x, y, z, w; w = 1 for three components; out of range reads 0, 0, 0, 1)
-__device__ __forceinline__ float4 fetch_position(const DrawParams& p, long long vidx) {
-    float4 o = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-    const unsigned long long off = (unsigned long long)vidx * p.stride;
-    if (vidx >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size) {
-        const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off);
-        o.x = __ldg(s);
-        o.y = __ldg(s + 1);
-        o.z = __ldg(s + 2);
-        if (p.pos_comps == 4) o.w = __ldg(s + 3);
-    }
-    return o;
-}
-// ... and of its colour (1, 1, 1, 1 without a colour attribute; out of range reads 0, 0, 0, 1)
+// robust fetch of one vertex's colour (1, 1, 1, 1 without a colour attribute; out of range reads 0, 0, 0, 1)
 __device__ __forceinline__ float4 fetch_color(const DrawParams& p, long long vidx) {
     float4 o = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     if (p.col_off != ~0u) {
@@ -253,10 +241,15 @@ __device__ __forceinline__ bool depth_clip_cannot_reject(const DrawParams& p, fl
 // Triangle t of an instance -> its compact record (R1-R4: index + position fetch, passthrough VS, viewport, snap, cull)
 // and its scissored pixel box.  false: the triangle produces no fragments (box left empty; the record's colours are
 // not fetched — on a band of a split frame that is most of the scene).
-__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
+// ROWS_FIRST: y and w of the three vertices decide first whether the triangle can touch the clip rectangle's rows at all; on a
+// band of a split frame most of the scene ends there, before x, z and the colours are fetched.  (Same tests, same
+// arithmetic, another order; a draw whose clip rectangle keeps most rows takes the single pass, which is shorter.)
+template <bool ROWS_FIRST>
+__device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
     box = make_int4(1, 0, 1, 0);  // minx maxx miny maxy
     bool ok = true;
     long long vidx[3];
+    const float* pos[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
@@ -272,18 +265,57 @@ __device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, Tr
         } else {
             vidx[k] = (long long)i;
         }
-        const float4 v = fetch_position(p, vidx[k]);
-        if (!(v.w > 0.0f)) ok = false;  // R3
-        float iw = 1.0f / v.w;
-        float xf = fmaf(p.hw, v.x * iw, p.ox);
-        float yf = fmaf(p.hh, v.y * iw, p.oy);
-        float zf = fmaf(p.dz, v.z * iw, p.zmin_vp);
-        if (!finite_f(xf) || !finite_f(yf) || !finite_f(zf) || !finite_f(iw)) ok = false;
-        if (fabsf(xf) > kGuardBand || fabsf(yf) > kGuardBand) ok = false;
-        r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
-        r.Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;
-        r.z[k] = zf;
+        // robust fetch: out of range reads (0, 0, 0, 1)
+        const unsigned long long off = (unsigned long long)vidx[k] * p.stride;
+        pos[k] = vidx[k] >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size ? reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off) : nullptr;
+        float x = 0.0f, y = 0.0f, z = 0.0f, w = 1.0f;
+        if (pos[k]) {
+            if (!ROWS_FIRST) {
+                x = __ldg(pos[k]);
+                z = __ldg(pos[k] + 2);
+            }
+            y = __ldg(pos[k] + 1);
+            if (p.pos_comps == 4) w = __ldg(pos[k] + 3);
+        }
+        if (!(w > 0.0f)) ok = false;  // R3
+        const float iw = 1.0f / w;
+        const float yf = fmaf(p.hh, y * iw, p.oy);
+        if (!finite_f(yf) || !finite_f(iw) || fabsf(yf) > kGuardBand) ok = false;
+        if (!ROWS_FIRST) {
+            const float xf = fmaf(p.hw, x * iw, p.ox);
+            const float zf = fmaf(p.dz, z * iw, p.zmin_vp);
+            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) ok = false;
+            r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+            r.z[k] = zf;
+        }
+        r.Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;  // R2
         r.iw[k] = iw;
+    }
+    if (ok) {
+        const int32_t minY = min(r.Y[0], min(r.Y[1], r.Y[2])), maxY = max(r.Y[0], max(r.Y[1], r.Y[2]));
+        // pixels whose sample 16p + 8 lies in [min, max]; the arithmetic shift is a floor division
+        box.z = max((minY - 8 + 15) >> 4, p.cy0);
+        box.w = min((maxY - 8) >> 4, p.cy1);
+        if (box.z > box.w) ok = false;
+    }
+    if (ROWS_FIRST) {
+        if (!ok) {
+            box = make_int4(1, 0, 1, 0);
+            return false;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float x = 0.0f, z = 0.0f;
+            if (pos[k]) {
+                x = __ldg(pos[k]);
+                z = __ldg(pos[k] + 2);
+            }
+            const float xf = fmaf(p.hw, x * r.iw[k], p.ox);
+            const float zf = fmaf(p.dz, z * r.iw[k], p.zmin_vp);
+            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) ok = false;
+            r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+            r.z[k] = zf;
+        }
     }
     const long long two_a = (long long)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) - (long long)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);  // R4
     if (two_a == 0) ok = false;
@@ -291,26 +323,26 @@ __device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, Tr
     if ((front && (p.st.cull_mode & 1u)) || (!front && (p.st.cull_mode & 2u))) ok = false;
     if (ok) {
         const int32_t minX = min(r.X[0], min(r.X[1], r.X[2])), maxX = max(r.X[0], max(r.X[1], r.X[2]));
-        const int32_t minY = min(r.Y[0], min(r.Y[1], r.Y[2])), maxY = max(r.Y[0], max(r.Y[1], r.Y[2]));
-        // pixels whose sample 16p + 8 lies in [min, max]; the arithmetic shift is a floor division
         box.x = max((minX - 8 + 15) >> 4, p.cx0);
         box.y = min((maxX - 8) >> 4, p.cx1);
-        box.z = max((minY - 8 + 15) >> 4, p.cy0);
-        box.w = min((maxY - 8) >> 4, p.cy1);
-        if (box.x > box.y || box.z > box.w) {
-            box = make_int4(1, 0, 1, 0);
-            ok = false;
-        }
+        if (box.x > box.y) ok = false;
+    }
+    if (!ok) {
+        box = make_int4(1, 0, 1, 0);
+        return false;
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float4 c = ok ? fetch_color(p, vidx[k]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float4 c = fetch_color(p, vidx[k]);
         r.col[k][0] = c.x * r.iw[k];
         r.col[k][1] = c.y * r.iw[k];
         r.col[k][2] = c.z * r.iw[k];
         r.col[k][3] = c.w * r.iw[k];
     }
-    return ok;
+    return true;
+}
+__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
+    return p.rows_first ? make_compact_t<true>(p, t, r, box) : make_compact_t<false>(p, t, r, box);
 }
 
 // compact -> expanded record (R5: sign-normalised integer edge equations, top-left bias, 1/2A); `c` must be the record of a
@@ -384,36 +416,38 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     TriRecC c;
     int4 box;
     const bool ok = make_compact(p, t, c, box);
-    if (BINNED) {
-        const uint4* src = reinterpret_cast<const uint4*>(&c);
+    // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
+    // degenerate, outside the clip rectangle or this GPU's band) needs no record — and a CTA none of whose triangles
+    // does (most of them, on a band of a split frame) has nothing to stage
+    const bool keep_mine = BINNED ? (in_range && ok) : in_range;
+    const uint32_t n_inst = p.total_tris / p.tris_per_instance;  // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
+    if (__syncthreads_or(keep_mine)) {
+        if (BINNED) {
+            const uint4* src = reinterpret_cast<const uint4*>(&c);
 #pragma unroll
-        for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
-        // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
-        // degenerate, outside the clip rectangle or this GPU's band) needs no record
-        keep[threadIdx.x] = in_range && ok;
-    } else {
-        TriRec r;
-        if (ok) {
-            expand_record(p, c, box, r);
+            for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
         } else {
-            memset(&r, 0, sizeof r);
-            r.minx = 1;
-            r.miny = 1;
-        }
-        const uint4* src = reinterpret_cast<const uint4*>(&r);
+            TriRec r;
+            if (ok) {
+                expand_record(p, c, box, r);
+            } else {
+                memset(&r, 0, sizeof r);
+                r.minx = 1;
+                r.miny = 1;
+            }
+            const uint4* src = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
-        for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
-        keep[threadIdx.x] = in_range;
-    }
-    __syncthreads();
-    // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
-    const uint32_t n_inst = p.total_tris / p.tris_per_instance;
-    const uint32_t block_first = blockIdx.x * 256u;
-    for (uint32_t inst = 0; inst < n_inst; ++inst) {
-        const size_t first_rec = (size_t)inst * p.tris_per_instance + block_first;
-        uint4* dst = BINNED ? reinterpret_cast<uint4*>(reinterpret_cast<TriRecC*>(p.tris) + first_rec) : reinterpret_cast<uint4*>(p.tris + first_rec);
-        for (uint32_t i = threadIdx.x; i < 256u * kQuads; i += 256u)
-            if (keep[i / kQuads]) dst[i] = stage[i];
+            for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
+        }
+        keep[threadIdx.x] = keep_mine;
+        __syncthreads();
+        const uint32_t block_first = blockIdx.x * 256u;
+        for (uint32_t inst = 0; inst < n_inst; ++inst) {
+            const size_t first_rec = (size_t)inst * p.tris_per_instance + block_first;
+            uint4* dst = BINNED ? reinterpret_cast<uint4*>(reinterpret_cast<TriRecC*>(p.tris) + first_rec) : reinterpret_cast<uint4*>(p.tris + first_rec);
+            for (uint32_t i = threadIdx.x; i < 256u * kQuads; i += 256u)
+                if (keep[i / kQuads]) dst[i] = stage[i];
+        }
     }
     if (in_range) {
         for (uint32_t inst = 0; inst < n_inst; ++inst)
@@ -2191,6 +2225,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     p.tiles_y = (uint32_t)p.cy1 / kTileH - p.tile_y0 + 1;
     KZN_REQUIRE(p.tiles_y <= 65535u, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: framebuffer taller than 524280 rows");
     p.stats = reinterpret_cast<unsigned long long*>(q->stats_address);
+    {
+        const double view_rows = fabs((double)vp->height);
+        p.rows_first = (double)(p.cy1 - p.cy0 + 1) < 0.5 * view_rows;
+    }
     if (st->fragment_program == KZN_FS_COMPILED) {
         KZN_VALID(q->fragment_program, "draw: fragment_program is KZN_FS_COMPILED but no program is bound (kzn_cmd_bind_fragment_program)");
         p.fs_flags = kzn_fragment_program_flags(q->fragment_program);
@@ -2235,8 +2273,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
         launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
-        // few tiles with long lists: a CTA per tile; many tiles with short lists: a warp per tile (see the kernels)
-        if (total / tiles >= 512) launch_draw_kernel(tile_sort_cta_kernel, dim3(p.tiles_x, p.tiles_y), dim3(kSortThreads), sizeof(SortShared), q->stream, p);
+        // few tiles with long lists: a CTA per tile; many tiles with short lists: a warp per tile (see the kernels).  The
+        // length is estimated from the viewport (a band of a split frame sees 1 / N of the triangles in 1 / N of the tiles)
+        const double viewport_tiles = ceil(fabs((double)vp->width) / kTileW) * ceil(fabs((double)vp->height) / kTileH);
+        if ((double)total / (viewport_tiles > 1.0 ? viewport_tiles : 1.0) >= 512.0) launch_draw_kernel(tile_sort_cta_kernel, dim3(p.tiles_x, p.tiles_y), dim3(kSortThreads), sizeof(SortShared), q->stream, p);
         else launch_draw_kernel(tile_sort_warp_kernel, dim3((uint32_t)((tiles + kSortWarps - 1) / kSortWarps)), dim3(kSortThreads), 0, q->stream, p);
         if ((r = kzn_launched(q, "tile_sort_kernel"))) return r;
     }

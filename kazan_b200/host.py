@@ -293,6 +293,9 @@ class Queue:
     def cmd_wait_flag(self, flag_address: int, expected: int, status_address: int = 0):
         _check(self._lib.kzn_cmd_wait_flag(self.handle, flag_address, expected, status_address))
 
+    def cmd_wait_flags(self, first_flag_address: int, flag_count: int, expected: int, status_address: int = 0):
+        _check(self._lib.kzn_cmd_wait_flags(self.handle, first_flag_address, flag_count, expected, status_address))
+
     def signal_fence(self, fence: Fence):
         _check(self._lib.kzn_queue_signal_fence(self.handle, fence.handle))
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-TILE_ROWS = 8  # raster tile height (kazan_b200/csrc/raster.cu kTileH): bands start on tile rows so no tile is shared
+TILE_ROWS = 16  # height of a raster brick (kazan_b200/csrc/raster.cu kBrick): bands start on brick rows, so no warp's pixel block is shared between ranks
 
 
 def band_rows(height: int, world: int, rank: int, align: int = TILE_ROWS) -> tuple[int, int]:
@@ -91,8 +91,11 @@ class PeerSplitFrame:
               the band directly into the presenter's HBM (no copy at all).  Best at 2 GPUs; with more writers the remote
               stores back-pressure the raster kernels (measured: profiles/).
     Per frame:
-        band rank : [wait credit] -> draw band -> (push) -> signal `arrived` (+1, after a system-scope fence)
-        presenter : draw own band -> wait `arrived` >= (world-1) * frames -> frame complete -> signal each rank's `credit`
+        band rank : [wait credit] -> draw band -> (push) -> signal ITS `arrived` flag (+1, after a system-scope fence)
+        presenter : draw own band -> wait until EVERY band rank's `arrived` flag >= frames -> frame complete -> signal each
+                    rank's `credit`
+    (One arrival flag per band rank: with one aggregated counter a rank running a frame ahead would be counted for a rank
+    that is a frame behind, and the presenter would declare a frame complete with a band missing.)
     `credit` bounds how far a band rank may run ahead of the presenter (the number of rotating targets), so a target is
     never overwritten before the presenter has seen the frame that used it.  No collective is on the data path;
     torch.distributed only carries the 64-byte handles once at start-up.
@@ -113,7 +116,7 @@ class PeerSplitFrame:
         self.frames = 0
         self._owned, self._imported = [], []
         is_presenter = rank == presenter
-        # my own flag block: presenter -> {arrived @0, status @64}; band rank -> {credit @0, status @64}
+        # my own flag block: presenter -> {arrived[band rank] @ 8 * index, status @192}; band rank -> {credit @0, status @192}
         self.flags = device.allocate(self.FLAG_BYTES)
         self._owned.append(self.flags)
         queue.cmd_fill_buffer(self.flags.address, self.FLAG_BYTES, 0, self.FLAG_BYTES, 0)
@@ -154,10 +157,14 @@ class PeerSplitFrame:
                 self.target_addresses.append(m.address)
             m = device.import_memory(everyone[presenter]["flags"], self.FLAG_BYTES)
             self._imported.append(m)
-            self.arrived_address = m.address
-        self.status_address = self.flags.address + 64
+            self.arrived_address = m.address + 8 * self.band_index(rank)  # this rank's own arrival flag
+        self.status_address = self.flags.address + 192
         if world > 1:
             dist.barrier()
+
+    def band_index(self, rank: int) -> int:
+        """position of `rank` among the band ranks (everyone but the presenter): the index of its arrival flag"""
+        return rank if rank < self.presenter else rank - 1
 
     @property
     def pushes(self) -> bool:
@@ -191,7 +198,7 @@ class PeerSplitFrame:
         if self.world == 1:
             return
         if self.rank == self.presenter:
-            self.queue.cmd_wait_flag(self.arrived_address, (self.world - 1) * self.frames, self.status_address)
+            self.queue.cmd_wait_flags(self.arrived_address, self.world - 1, self.frames, self.status_address)
             for addr in self.credit_addresses.values():
                 self.queue.cmd_signal_flag(addr, 1)
         elif self.pushes:

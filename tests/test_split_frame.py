@@ -17,9 +17,9 @@ def test_bands_partition_the_frame(height, world):
     assert bands[0][0] == 0 and bands[-1][1] == height
     for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
         assert a1 == b0 and a0 <= a1
-    assert all(y0 % 8 == 0 for y0, _ in bands)  # no raster tile is shared between ranks
+    assert all(y0 % 16 == 0 for y0, _ in bands)  # no raster brick is shared between ranks
     heights = [b - a for a, b in bands if b > a]
-    assert max(heights) - min(heights) <= 8 or len(heights) < world
+    assert max(heights) - min(heights) <= 16 or len(heights) < world
 
 
 @pytest.mark.parametrize("total,world", [(1 << 24, 8), (1000, 3), (255, 2), (0, 4), (257, 2)])
