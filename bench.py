@@ -312,8 +312,18 @@ def dispatch_extra(torch, queue, stream):
     ms = time_region(torch, stream, lambda k: queue.cmd_dispatch(pipe, (65536, 256, 1), x.data_ptr(), y.data_ptr()), 20, 3) / 20
     torch.cuda.synchronize()
     ok = bool(torch.equal(y, x * 256))  # int32 wrap-around, the loop's closed form
-    # 256 iterations x (2 adds + compare/branch) per invocation: integer issue rate
-    out["sum_loop_256"] = {"invocations": n, "ms": ms, "Ginvocations_per_s": n / ms / 1e6, "Tint_adds_per_s": n * 512 / ms / 1e9,
+    # The IR loop is 256 iterations of two adds and a compare; ptxas folds the counter away and unrolls the accumulation into
+    # 129 IADD3 (three-input adds) per invocation — profiles/sass_summary.txt, `kzn_main of sum_loop.kazan-ir` — so the rate
+    # that means something is EXECUTED IADD3 per second against the integer ALU issue rate: 64 lanes per SM per clock
+    # (B300_MICROARCH.md: alu pipe, one warp instruction per 2 cycles per SM sub-partition).
+    iadd3 = 129
+    sm_count = queue.device.sm_count
+    peak = sm_count * 64 * 1.965e9 / 1e12
+    rate = n * iadd3 / ms / 1e9
+    out["sum_loop_256"] = {"invocations": n, "ms": ms, "Ginvocations_per_s": n / ms / 1e6,
+                           "executed_iadd3_per_invocation": iadd3, "Tiadd3_per_s": rate,
+                           "roofline": {"bound": "int_alu_issue", "achieved": rate, "peak": peak, "unit": "Tinstr/s", "frac": rate / peak,
+                                        "peak_source": "nominal: SMs x 64 lanes x 1.965 GHz"},
                            "bytes_per_invocation": 8, "GBps": n * 8 / ms / 1e6, "parity": "closed form x*256 (mod 2^32) holds" if ok else "MISMATCH"}
     pipe.destroy()
     return out
@@ -850,14 +860,16 @@ def run_ours(args):
         sm_mhz = clk["sm_mhz"] or 1965.0
         nominal_issue = dev.sm_count * 128 * sm_mhz * 1e6 / 1e12  # T fp32 lane-instructions/s at the sampled clock
         issue = W * H * FP32_INSTR_PER_PIXEL / sec / 1e12
-        line["roofline"] = {"bound": "fp32_issue", "achieved": issue, "peak": measured_issue, "unit": "Tinstr/s", "frac": issue / measured_issue,
+        line["roofline"] = {"bound": "fp32_issue", "achieved": issue, "peak": nominal_issue, "unit": "Tinstr/s", "frac": issue / nominal_issue,
+                            "calibrated_peak": measured_issue, "frac_of_calibrated": issue / measured_issue,
                             "traffic": roofline_traffic("raster_direct_kernel"),
                             "kernel": "kzn_fs_raster_direct_0 (raster_direct_kernel with the compiled shader)" if fs_program else "raster_direct_kernel<ORBIT,0>",
                             "kernel_ms": k_ms, "kernel_ms_event_pair": k_ms_events,
                             "kernel_ms_source": ("event pair around the kernel" if k_ms_events <= ms_per_step else
                                                  "step time: upper bound of the kernel's duration (the event pair also brackets the launch latency that programmatic dependent launch hides)"),
                             "kernel_share_of_step": k_ms / ms_per_step,
-                            "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL, "peak_source": "measured in this run: kzn_calibrate_fp32_issue (FFMA2 chains)",
+                            "fp32_instr_per_pixel": FP32_INSTR_PER_PIXEL,
+                            "peak_source": "nominal: SMs x 128 fp32 lanes x the SM clock sampled during the timed region; calibrated_peak = kzn_calibrate_fp32_issue (FFMA2 chains) in this run",
                             "nominal_peak": nominal_issue, "frac_of_nominal": issue / nominal_issue, "sm_mhz": sm_mhz,
                             "note": "north_star: 'FP32 issue rate for shader-bound work'; the HBM side of the same kernel is `roofline_hbm`"}
         achieved = W * H * 4 / sec / 1e9
