@@ -68,6 +68,15 @@ KZN_API void kzn_free(void* ptr);
  * local_size receives the LocalSize execution mode (1,1,1 when absent). */
 KZN_API KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, const char* entry_point,
                                             uint32_t execution_model, KznIrModule** module, uint32_t local_size[3]);
+/* version KZN_IR_VERSION_2: shaders with a body — what the reference leaves todo!() (OpLoad / OpStore / OpAccessChain,
+ * composites, conversions, arithmetic, compares, OpSelect, selection constructs with OpSwitch / OpBranchConditional, OpPhi at
+ * their merge blocks) translated into the version 2 instructions of the IR (csrc/spirv_to_ir_v2.cpp), values scalarised.
+ * Input / Output variables are laid out by Location (16 bytes each, io_layout.rs:5-13) in the two interface blocks, a
+ * `BuiltIn Position` output is the `vertex_position` built-in variable.  The reference's own second test shader
+ * (test_data/simple_test.spv, src/lib.rs:260-287: #[ignore], golden "not yet entered") translates. */
+KZN_API KznResult kzn_translate_spirv_to_ir_ex(const uint32_t* words, size_t word_count, const char* entry_point,
+                                               uint32_t execution_model, uint32_t version, KznIrModule** module,
+                                               uint32_t local_size[3]);
 
 /* ---- SPIR-V reader (spirv-parser crate: Parser::start / iteration / Display, spirv-parser/src/lib.rs:26-44) --------- */
 /* Parses a SPIR-V module and writes its disassembly in the reference's text format: "; SPIR-V / ; Version / ; Generator

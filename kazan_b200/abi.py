@@ -299,6 +299,7 @@ BACKEND_PROTOTYPES = {
     "kzn_ir_round_trip": (i32, [cp, cp, sz, P(vp), P(sz)]),
     "kzn_free": (None, [vp]),
     "kzn_translate_spirv_to_ir": (i32, [P(u32), sz, cp, u32, P(vp), P(u32)]),
+    "kzn_translate_spirv_to_ir_ex": (i32, [P(u32), sz, cp, u32, u32, P(vp), P(u32)]),
     "kzn_spirv_disassemble": (i32, [P(u32), sz, P(vp), P(sz)]),
     "kzn_ptx_from_ir": (i32, [vp, P(vp), P(sz)]),
     "kzn_compute_pipeline_create": (i32, [vp, vp, P(u32), P(vp)]),

@@ -67,11 +67,16 @@ class IrModule:
             self.handle = None
 
 
-def translate_spirv_to_ir(words: Sequence[int], entry_point: str, execution_model: int) -> tuple[IrModule, tuple[int, int, int]]:
+def translate_spirv_to_ir(words: Sequence[int], entry_point: str, execution_model: int, version: int = 1) -> tuple[IrModule, tuple[int, int, int]]:
+    """version 1: what the reference translates (control-flow-free entry points); version 2: shaders with a body, into the
+    version 2 instructions of the IR (kazan_b200/csrc/spirv_to_ir_v2.cpp)."""
     arr = (abi.u32 * len(words))(*words)
     h = C.c_void_p()
     ls = (abi.u32 * 3)()
-    _check(load_library().kzn_translate_spirv_to_ir(arr, len(words), entry_point.encode(), execution_model, C.byref(h), ls))
+    if version == 1:
+        _check(load_library().kzn_translate_spirv_to_ir(arr, len(words), entry_point.encode(), execution_model, C.byref(h), ls))
+    else:
+        _check(load_library().kzn_translate_spirv_to_ir_ex(arr, len(words), entry_point.encode(), execution_model, version, C.byref(h), ls))
     return IrModule(h), tuple(ls)
 
 

@@ -423,15 +423,21 @@ void kzn_free(void* ptr) { free(ptr); }
 
 // ---- SPIR-V -> IR -> PTX ---------------------------------------------------------------------------------------------------
 
-KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, const char* entry_point, uint32_t execution_model,
-                                    KznIrModule** module, uint32_t local_size[3]) {
+KznResult kzn_translate_spirv_to_ir_ex(const uint32_t* words, size_t word_count, const char* entry_point, uint32_t execution_model,
+                                       uint32_t version, KznIrModule** module, uint32_t local_size[3]) {
     KZN_VALID(words && entry_point && module, "kzn_translate_spirv_to_ir: null argument");
     *module = nullptr;
+    KZN_VALID(version == KZN_IR_VERSION_1 || version == KZN_IR_VERSION_2, "kzn_translate_spirv_to_ir_ex: unknown IR version %u", version);
     return guarded([&] {
-        auto m = kir::translate_spirv(words, word_count, entry_point, execution_model, local_size);
+        auto m = version == KZN_IR_VERSION_2 ? kir::translate_spirv_v2(words, word_count, entry_point, execution_model, local_size)
+                                             : kir::translate_spirv(words, word_count, entry_point, execution_model, local_size);
         *module = new KznIrModule{std::move(m)};
         return KZN_SUCCESS;
     });
+}
+KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_count, const char* entry_point, uint32_t execution_model,
+                                    KznIrModule** module, uint32_t local_size[3]) {
+    return kzn_translate_spirv_to_ir_ex(words, word_count, entry_point, execution_model, KZN_IR_VERSION_1, module, local_size);
 }
 
 KznResult kzn_spirv_disassemble(const uint32_t* words, size_t word_count, char** text, size_t* length) {

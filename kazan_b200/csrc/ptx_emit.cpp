@@ -1128,6 +1128,23 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
     for (auto* list : {&m.built_in_inputs, &m.built_in_outputs, &m.globals, &f->locals})
         for (auto& v : *list) vars.emplace_back(&v, e.declare_variable(v));
     e.analyze(f->body);
+    // Built-in OUTPUT variables (vertex_position) leave the invocation after its user outputs: the output slot of an
+    // invocation is [user_outputs_block | built-in outputs in declaration order, each at a multiple of 16 bytes], every
+    // component written (0 where the shader wrote nothing).
+    uint64_t out_slot_size = m.user_outputs.size;
+    std::vector<std::pair<int, uint64_t>> built_in_outs;  // (base, offset in the slot)
+    for (auto& v : vars) {
+        Base& b = e.bases[v.second];
+        bool is_out = false;
+        for (auto& o : m.built_in_outputs) is_out = is_out || &o == v.first;
+        if (!is_out) continue;
+        if (v.first->type->kind != TypeKind::Vector || type_size(v.first->type->element) != 4) Emitter::unsupported("built-in outputs other than vectors of 32-bit components");
+        out_slot_size = (out_slot_size + 15) / 16 * 16;
+        built_in_outs.push_back({v.second, out_slot_size});
+        for (uint64_t c = 0; c < v.first->type->length; ++c)
+            if (!b.slots.count(4 * c)) b.slots[4 * c] = 4;
+        out_slot_size += (type_size(v.first->type) + 15) / 16 * 16;
+    }
     e.finish_analysis();
 
     // ---- prologue: linear invocation index over a 2-D folded grid ----
@@ -1153,19 +1170,19 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
     e.line("ld.param.u64 " + first + ", [kzn_first_invocation];");
     e.line("add.u64 " + gid + ", " + gid + ", " + first + ";");
     // interface block pointers of this invocation
-    auto bind_block = [&](const InterfaceBlock& b, const char* param, int base) -> std::string {
+    auto bind_block = [&](uint64_t size, const char* param, int base) -> std::string {
         std::string r = e.fresh(RC::B64);
         e.line(std::string("ld.param.u64 ") + r + ", [" + param + "];");
-        if (b.size) {
+        if (size) {
             std::string o = e.fresh(RC::B64);
-            e.line("mul.lo.u64 " + o + ", " + gid + ", " + std::to_string(b.size) + ";");
+            e.line("mul.lo.u64 " + o + ", " + gid + ", " + std::to_string(size) + ";");
             e.line("add.u64 " + r + ", " + r + ", " + o + ";");
         }
         e.bases[base].address = r;
         return r;
     };
-    bind_block(m.user_inputs, "kzn_user_inputs_base", in_base);
-    std::string out_ptr = bind_block(m.user_outputs, "kzn_user_outputs_base", out_base);
+    bind_block(m.user_inputs.size, "kzn_user_inputs_base", in_base);
+    std::string out_ptr = bind_block(out_slot_size, "kzn_user_outputs_base", out_base);
     e.pc_param = "kzn_push_constants";
     if (e.pc_base >= 0) e.bases[e.pc_base].address = "kzn_push_constants";
     for (auto& v : vars) e.variable(*v.first, v.second);
@@ -1230,6 +1247,19 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
         if (m.user_outputs.size % align) eff = 1;
         e.store_scalar(t, e.def(rets[i]), out_ptr, (int64_t)outs[i].offset, eff);
     }
+    for (auto& bo : built_in_outs) {
+        Base& b = e.bases[bo.first];
+        for (uint64_t c = 0; c * 4 < b.size; ++c) {
+            std::string v;
+            if (b.scalarized) {
+                v = e.cell(b, 4 * c);
+            } else {
+                v = e.fresh(RC::B32);
+                e.line("ld.u32 " + v + ", [" + Emitter::address(b.address, (int64_t)(4 * c)) + "];");
+            }
+            e.line("st.u32 [" + Emitter::address(out_ptr, (int64_t)(bo.second + 4 * c)) + "], " + v + ";");
+        }
+    }
     e.line("ret;");
 
     std::ostringstream sub;
@@ -1256,7 +1286,7 @@ std::string emit_ptx(const Module& m, EntryInfo* info) {
     if (info) {
         info->entry_name = entry;
         info->inputs_size = m.user_inputs.size;
-        info->outputs_size = m.user_outputs.size;
+        info->outputs_size = out_slot_size;
         info->uses_global_invocation_id = false;
         for (auto& v : vars)
             if (e.bases[v.second].built_in == "global_invocation_id") info->uses_global_invocation_id = true;

@@ -55,6 +55,11 @@ FragmentInterface fragment_interface(const Module& m);
 std::unique_ptr<Module> translate_spirv(const uint32_t* words, size_t count, const std::string& entry_point,
                                         uint32_t execution_model, uint32_t local_size[3]);
 
+// ... and, into version 2 of the IR, shaders with a body (spirv_to_ir_v2.cpp): loads, stores, access chains, composites,
+// conversions, arithmetic, selection constructs (OpSwitch / OpBranchConditional)
+std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, const std::string& entry_point,
+                                           uint32_t execution_model, uint32_t local_size[3]);
+
 // spirv-parser's parse-and-dump (spirv-parser/src/lib.rs:26-44): header block + one line per instruction with its byte
 // offset, in the reference's exact text format; throws Error with the reference's messages for malformed modules
 std::string disassemble_spirv(const uint32_t* words, size_t count);

@@ -385,6 +385,7 @@ class Simt:
     # ---- entry points ----
     def _variables(self, lane_slot: int, built_ins: dict):
         """allocate the invocation's variables in its private memory; returns {id(pointer value): address}"""
+        self.var_address = getattr(self, "var_address", {})
         m, f = self.m, self.m.entry_point
         base = LOCAL_BASE + lane_slot * LANE_STRIDE
         region = bytearray(LANE_STRIDE)
@@ -394,6 +395,7 @@ class Simt:
             al = max(v.align, 1)
             at = (at + al - 1) // al * al
             ptrs[id(v.pointer)] = base + at
+            self.var_address[(lane_slot, id(v.pointer))] = base + at
             if v.kind in built_ins:
                 data = built_ins[v.kind]
                 region[at:at + len(data)] = data
@@ -414,6 +416,15 @@ class Simt:
         return {l: [self.env[l][id(d)] for d in (body.results or [])] for l in lanes}
 
 
+def output_slot_size(module) -> int:
+    """bytes of one invocation's output slot: user_outputs_block, then the built-in output variables (vertex_position), each at
+    a multiple of 16 bytes (kazan_b200/csrc/ptx_emit.cpp emit_ptx)"""
+    size = module.user_outputs.size
+    for v in module.built_in_outputs:
+        size = (size + 15) // 16 * 16 + (_type_bytes(v.type) + 15) // 16 * 16
+    return size
+
+
 def run_dispatch(module, count: int, memory: Memory, user_inputs: int = 0, user_outputs: int = 0, first_invocation: int = 0,
                  global_size=(None, 1, 1), global_base=(0, 0, 0), push_constants: bytes = b"", descriptor_table: int = 0) -> None:
     """The dispatch of kzn_cmd_dispatch: invocation g (0 <= g < count) runs with index first_invocation + g; its interface
@@ -421,6 +432,7 @@ def run_dispatch(module, count: int, memory: Memory, user_inputs: int = 0, user_
     sim = Simt(module, memory)
     sx = global_size[0] if global_size[0] else max(count, 1)
     sy = global_size[1] or 1
+    out_stride = output_slot_size(module)
     pc_addr = 0x6FFF_0000_0000
     memory.regions[pc_addr] = bytearray(push_constants.ljust(128, b"\0"))
     for g0 in range(0, count, SUBGROUP):
@@ -436,13 +448,20 @@ def run_dispatch(module, count: int, memory: Memory, user_inputs: int = 0, user_
                      "descriptor_table": struct.pack("<Q", descriptor_table)}
             e = sim._variables(g - g0, built)
             e[id(module.user_inputs.pointer)] = user_inputs + idx * module.user_inputs.size
-            e[id(module.user_outputs.pointer)] = user_outputs + idx * module.user_outputs.size
+            e[id(module.user_outputs.pointer)] = user_outputs + idx * out_stride
             env[g] = e
         res = sim.run_group(lanes, env)
         for g in lanes:
-            base = user_outputs + (first_invocation + g) * module.user_outputs.size
+            base = user_outputs + (first_invocation + g) * out_stride
             for (off, ty), v in zip(module.user_outputs.members, res[g]):
                 memory.write(base + off, iro.type_size(ty), int(v))
+            at = module.user_outputs.size
+            for v in module.built_in_outputs:  # the built-in output variables follow the user outputs
+                at = (at + 15) // 16 * 16
+                n = _type_bytes(v.type)
+                src = sim.var_address[(g - g0, id(v.pointer))]
+                memory.write(base + at, n, memory.read(src, n))
+                at += (n + 15) // 16 * 16
     for k in [k for k in memory.regions if k >= LOCAL_BASE or k == pc_addr]:
         del memory.regions[k]
 

@@ -143,3 +143,58 @@ def test_interpreter_corner_cases():
     fi = v2.make_inputs("float_ops", 64, seed=3)
     t7 = fi["a"] * np.float32(1000.0)
     assert np.all(fo["r7"][t7 < 0] == 0) and np.all(fo["r13"][t7 > 255] == 255) and np.all(fo["r14"][t7 > 127] == 127)
+
+
+def _simple_test_words():
+    """the reference's second translator test shader: test_data/simple_test.spv == spirv-parser/test_inputs/test.spv
+    (a vertex shader: gl_Position = vec4(in, 1), float -> u64 -> u32 -> i32 conversions into a Function variable, an OpSwitch
+    on the 64-bit value whose default stores 0 to gl_Position.x)"""
+    import base64
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "spirv_goldens.json").read_text())
+    case = next(c for c in g["cases"] if c["file"].endswith("test.spv"))
+    return np.frombuffer(base64.b64decode(case["spv_base64"]), dtype="<u4").tolist()
+
+
+def test_simple_test_spv_translates_to_version_2_ir():
+    """the shader the reference's translator cannot translate (src/lib.rs:260-287 is #[ignore], its golden
+    "not yet entered"): OpLoad / OpStore / OpAccessChain / OpCompositeExtract / OpCompositeConstruct / OpConvertFToU / OpUConvert
+    / OpBitcast / OpSelectionMerge + OpSwitch.  Version 1 of the translator still refuses it, like the reference."""
+    from oracle import ir_oracle as iro
+    words = _simple_test_words()
+    with pytest.raises(host.KazanError) as e:
+        backend.translate_spirv_to_ir(words, "main", backend.EXECUTION_MODEL_VERTEX)
+    assert e.value.code == -8
+    module, _ = backend.translate_spirv_to_ir(words, "main", backend.EXECUTION_MODEL_VERTEX, 2)
+    text = module.to_text()
+    for needle in ("kind: vertex_position", "convert_f_to_u [id_30] -> [id_32: i64]", "u_convert [id_32] -> [id_33: i32]", "bitcast [id_33] -> [id_34: i32]",
+                   "block id_38 -> [] {", "0x8i64 -> break id_36[];", "store [id_10, c3: f32 0x0], align: 0x4 -> [];"):
+        assert needle in text, needle
+    assert backend.IrModule.parse(text, 2).to_text() == text and iro.module_to_text(iro.parse_module(text, 2)) == text
+    if os.path.exists(PTXAS):
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            (open(f"{d}/k.ptx", "w")).write(module.to_ptx())
+            r = subprocess.run([PTXAS, "-arch=sm_100a", "-o", "/dev/null", f"{d}/k.ptx"], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+
+
+def test_translated_simple_test_runs_in_the_interpreter():
+    """what the shader means, per vertex: position = (x, y, z, 1), and x = 0 unless trunc(z) is 1, 2 or 8"""
+    from oracle import ir_oracle as iro
+    from oracle import ir_simt as sim
+    module, _ = backend.translate_spirv_to_ir(_simple_test_words(), "main", backend.EXECUTION_MODEL_VERTEX, 2)
+    m = iro.parse_module(module.to_text(), 2)
+    zs = [0.5, 1.0, 1.9, 2.2, 3.0, 8.5, 9.0, -4.0, 1e30, float("nan")]
+    inp = np.zeros((len(zs), 4), dtype=np.float32)
+    inp[:, 0], inp[:, 1], inp[:, 2] = 7.0, -3.0, zs
+    out = bytearray(16 * len(zs))
+    assert sim.output_slot_size(m) == 16
+    mem = sim.Memory({0x1000: bytearray(inp.tobytes()), 0x9000: out})
+    sim.run_dispatch(m, len(zs), mem, 0x1000, 0x9000)
+    pos = np.frombuffer(bytes(out), dtype=np.float32).reshape(-1, 4)
+    for z, p in zip(zs, pos):
+        keeps_x = z == z and int(min(max(z, 0.0), 2.0**64)) in (1, 2, 8)
+        assert p[0] == (7.0 if keeps_x else 0.0) and p[1] == -3.0 and p[3] == 1.0, (z, p)
+        assert (p[2] == np.float32(z)) or (z != z and p[2] != p[2])
