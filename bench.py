@@ -351,7 +351,7 @@ def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1
     d_verts, d_idx = torch.from_numpy(verts).cuda(), torch.from_numpy(idx.view(np.int32)).cuda()
     color = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
     depth = torch.empty(W * H, dtype=torch.float32, device="cuda")
-    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(12, dtype=torch.int64, device="cuda")
     cimg = host.Image(color.data_ptr(), W, H)
     dimg = host.Image(depth.data_ptr(), W, H, format=abi.FORMAT_D32_SFLOAT)
     fb = abi.Framebuffer()

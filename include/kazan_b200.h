@@ -418,11 +418,25 @@ typedef struct KznFramebuffer { /* vkCreateFramebuffer api_impl.rs:4383-4390 + r
     uint32_t band_y0, band_y1;
 } KznFramebuffer;
 
-typedef struct KznDrawStatistics { /* optional, device-written counters (8 x u64) */
+typedef struct KznDrawStatistics { /* optional, device-written counters (12 x u64) */
     uint64_t triangles_in, triangles_culled, triangles_binned, bin_entries, fragments_covered,
         fragments_depth_passed, tiles_launched, bin_overflow_tiles;
+    /* primitive clipping (see "Clipping" above kzn_cmd_draw): triangles that crossed the w = 2^-20 plane or the guard band and
+     * were clipped; the triangles the clipper made of them; triangles DISCARDED because a clip coordinate was NaN or infinite;
+     * clipped triangles whose extra triangles did not fit the queue's reserve (always 0 unless a draw of more than 65536
+     * triangles has more than one extra triangle per primitive on average: those lose the extra triangles) */
+    uint64_t triangles_clipped, clip_triangles, triangles_discarded, clip_overflow;
 } KznDrawStatistics;
 
+/* Clipping (Vulkan 1.1 "Primitive Clipping"; rule R3 of oracle/raster.c).  The view volume cuts in x / y by scissoring to
+ * the viewport rectangle and in z by a per-fragment test against [minDepth, maxDepth] (depthClamp is FALSE,
+ * api_impl.rs:875-930) — neither changes a triangle.  A triangle with a vertex at w <= 0, or farther than 2^19 pixels from the
+ * origin of the window, is clipped in homogeneous coordinates against w >= 2^-20 and a guard band of +-2^18 pixels and the
+ * polygon (at most 8 vertices, colours interpolated with the positions) is drawn as a fan at the primitive's place in
+ * primitive order; KznDrawStatistics counts them.  Only a triangle with a NaN or infinite clip coordinate is discarded
+ * (triangles_discarded).  first_instance: there are no instance-rate vertex inputs and no built-in that reads the instance
+ * index (the vertex stage is KZN_VS_PASSTHROUGH), so instances repeat the same triangles and first_instance has nothing to
+ * offset; it is accepted for the signature's sake. */
 KZN_API KznResult kzn_cmd_draw(KznQueue* queue, const KznGraphicsPipelineState* state,
                                const KznFramebuffer* framebuffer, const KznViewport* viewport,
                                const KznRect2D* scissor, const KznVertexInput* vertices,

@@ -163,7 +163,8 @@ class Framebuffer(C.Structure):
 class DrawStatistics(C.Structure):
     _fields_ = [(n, u64) for n in (
         "triangles_in", "triangles_culled", "triangles_binned", "bin_entries", "fragments_covered",
-        "fragments_depth_passed", "tiles_launched", "bin_overflow_tiles")]
+        "fragments_depth_passed", "tiles_launched", "bin_overflow_tiles", "triangles_clipped", "clip_triangles", "triangles_discarded",
+        "clip_overflow")]
 
 
 P = C.POINTER

@@ -62,6 +62,12 @@ constexpr int kDirectRows = KZN_DIRECT_ROWS;          // ... and this many rows 
 constexpr int kDirectWarpsPerSM = KZN_DIRECT_WARPS;   // persistent one-warp CTAs per SM (bounds the registers per thread)
 constexpr int kSortCap = 4096;           // largest binned list sorted in shared memory
 constexpr float kGuardBand = 524288.0f;  // 2^19 pixels (R3)
+constexpr float kClipGuard = 262144.0f;  // 2^18 pixels: where clipped polygons end (R3)
+constexpr float kClipW = 9.5367431640625e-07f;  // 2^-20 (R3)
+constexpr uint32_t kFusedMax = 5;        // direct draws of at most this many triangles make their records in the raster kernel (5 x 6 clipped triangles fit 32 slots)
+// work_counter slots: 0, 1 block dispenser of the direct kernel and its leavers; 2 brick dispenser of raster_kernel; 3 records
+// of a direct draw; 4 extra records allocated by this draw's clip_kernel (zeroed again by its sort kernel); 5 their count for
+// raster_kernel; 6 primitives setup_kernel left to clip_kernel (zeroed by the sort kernel)
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
 constexpr int kDstNone = 0;       // no blending, all channels written: the destination is never read
@@ -139,11 +145,18 @@ struct DrawParams {
     unsigned long long* stats;                     // KznDrawStatistics or null
     uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
-    uint32_t fused_setup;                          // direct draws of <= 32 triangles: raster_direct_kernel makes the records itself
+    uint32_t fused_setup;                          // direct draws of <= kFusedMax triangles: raster_direct_kernel makes the records itself
     // compiled fragment programs (KZN_FS_COMPILED): what vkCmdBindDescriptorSets / vkCmdPushConstants left on the queue, and
     // what the program reads (bit 0: it needs interpolated inputs or the z / w of frag_coord, so no coverage shortcut applies)
     uint32_t fs_flags;
     uint32_t rows_first;  // setup: decide on y before x, z and the colours are fetched (the clip rectangle keeps under half of the viewport's rows)
+    // clipped primitives of binned draws (R3): the first triangle of the clipped polygon takes the primitive's own record, the
+    // others ("extra" records, shared by all instances) follow the draw's records at tris / boxes [total_tris + k]
+    uint32_t* clip_bits;    // [tris_per_instance / 32] bit t: primitive t has extra records (zeroed with the tile counters)
+    uint32_t* clip_link;    // [tris_per_instance] first extra record k | number of extras << 29; valid where the primitive's bit is set
+    uint32_t* clip_parent;  // [clip_capacity] primitive << 3 | fan index j (1..5) of each extra record; ~0u: unused
+    uint32_t* clip_list;    // [tris_per_instance] the primitives setup_kernel left to clip_kernel (work_counter[6] of them)
+    uint32_t clip_capacity;
     unsigned long long descriptor_table;
     unsigned char push_constants[KZN_MAX_PUSH_CONSTANTS_SIZE];
 };
@@ -244,30 +257,40 @@ __device__ __forceinline__ bool depth_clip_cannot_reject(const DrawParams& p, fl
 // ROWS_FIRST: y and w of the three vertices decide first whether the triangle can touch the clip rectangle's rows at all; on a
 // band of a split frame most of the scene ends there, before x, z and the colours are fetched.  (Same tests, same
 // arithmetic, another order; a draw whose clip rectangle keeps most rows takes the single pass, which is shorter.)
+// vertex k of triangle t of an instance: its index into the vertex buffer (negative or huge: out of range)
+__device__ __forceinline__ long long triangle_vertex(const DrawParams& p, uint32_t t, int k) {
+    // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
+    unsigned long long rel = 3ull * t + k;
+    if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
+    if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
+    unsigned long long i = (unsigned long long)p.first + rel;
+    if (p.index_base) {
+        unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
+                                     ? (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(p.index_base) + i)
+                                     : (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(p.index_base) + i);
+        return (long long)raw + p.vertex_offset;
+    }
+    return (long long)i;
+}
+// where its position is, or null: the robust fetch reads (0, 0, 0, 1) out of range
+__device__ __forceinline__ const float* vertex_position(const DrawParams& p, long long vidx) {
+    const unsigned long long off = (unsigned long long)vidx * p.stride;
+    return vidx >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size ? reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off) : nullptr;
+}
+
+// `slow`: the triangle has a vertex behind w = 0 or outside the guard band (or a coordinate that is not finite): it is
+// clipped (clip_primitive) or discarded, R3 — false is returned and nothing else is decided here.
 template <bool ROWS_FIRST>
-__device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
+__device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow) {
     box = make_int4(1, 0, 1, 0);  // minx maxx miny maxy
-    bool ok = true;
+    slow = false;
+    bool y_ok = true, x_ok = true;
     long long vidx[3];
     const float* pos[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
-        unsigned long long rel = 3ull * t + k;
-        if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
-        if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
-        unsigned long long i = (unsigned long long)p.first + rel;
-        if (p.index_base) {
-            unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
-                                         ? (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(p.index_base) + i)
-                                         : (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(p.index_base) + i);
-            vidx[k] = (long long)raw + p.vertex_offset;
-        } else {
-            vidx[k] = (long long)i;
-        }
-        // robust fetch: out of range reads (0, 0, 0, 1)
-        const unsigned long long off = (unsigned long long)vidx[k] * p.stride;
-        pos[k] = vidx[k] >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size ? reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off) : nullptr;
+        vidx[k] = triangle_vertex(p, t, k);
+        pos[k] = vertex_position(p, vidx[k]);
         float x = 0.0f, y = 0.0f, z = 0.0f, w = 1.0f;
         if (pos[k]) {
             if (!ROWS_FIRST) {
@@ -277,21 +300,22 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
             y = __ldg(pos[k] + 1);
             if (p.pos_comps == 4) w = __ldg(pos[k] + 3);
         }
-        if (!(w > 0.0f)) ok = false;  // R3
+        if (!(w > 0.0f)) y_ok = false;  // R3
         const float iw = 1.0f / w;
         const float yf = fmaf(p.hh, y * iw, p.oy);
-        if (!finite_f(yf) || !finite_f(iw) || fabsf(yf) > kGuardBand) ok = false;
+        if (!finite_f(yf) || !finite_f(iw) || fabsf(yf) > kGuardBand) y_ok = false;
         if (!ROWS_FIRST) {
             const float xf = fmaf(p.hw, x * iw, p.ox);
             const float zf = fmaf(p.dz, z * iw, p.zmin_vp);
-            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) ok = false;
-            r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) x_ok = false;
+            r.X[k] = y_ok && x_ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
             r.z[k] = zf;
         }
-        r.Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;  // R2
+        r.Y[k] = y_ok ? __float2int_rn(yf * 16.0f) : 0;  // R2
         r.iw[k] = iw;
     }
-    if (ok) {
+    bool ok = true;
+    if (y_ok) {  // (R3: rows that miss the clip rectangle end the triangle before anything else is looked at)
         const int32_t minY = min(r.Y[0], min(r.Y[1], r.Y[2])), maxY = max(r.Y[0], max(r.Y[1], r.Y[2]));
         // pixels whose sample 16p + 8 lies in [min, max]; the arithmetic shift is a floor division
         box.z = max((minY - 8 + 15) >> 4, p.cy0);
@@ -299,8 +323,9 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
         if (box.z > box.w) ok = false;
     }
     if (ROWS_FIRST) {
-        if (!ok) {
+        if (!ok || !y_ok) {
             box = make_int4(1, 0, 1, 0);
+            slow = ok && !y_ok;
             return false;
         }
 #pragma unroll
@@ -312,10 +337,14 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
             }
             const float xf = fmaf(p.hw, x * r.iw[k], p.ox);
             const float zf = fmaf(p.dz, z * r.iw[k], p.zmin_vp);
-            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) ok = false;
-            r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
+            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) x_ok = false;
+            r.X[k] = x_ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
             r.z[k] = zf;
         }
+    }
+    if (ok && !(y_ok && x_ok)) {
+        slow = true;
+        ok = false;
     }
     const long long two_a = (long long)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) - (long long)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);  // R4
     if (two_a == 0) ok = false;
@@ -341,8 +370,126 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
     }
     return true;
 }
-__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box) {
-    return p.rows_first ? make_compact_t<true>(p, t, r, box) : make_compact_t<false>(p, t, r, box);
+__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow) {
+    return p.rows_first ? make_compact_t<true>(p, t, r, box, slow) : make_compact_t<false>(p, t, r, box, slow);
+}
+
+// ---- clipping (R3, oracle/raster.c clip_triangle): the rare triangles make_compact calls `slow` ----------------------------
+
+__device__ __forceinline__ int4 record_box(const DrawParams& p, const TriRecC& c);
+
+__device__ __forceinline__ float clip_distance(const DrawParams& p, const float* c, int plane) {
+    if (plane == 0) return c[3] - kClipW;
+    const float gw = kClipGuard * c[3];
+    if (plane <= 2) {
+        const float wx = fmaf(p.hw, c[0], p.ox * c[3]);
+        return plane == 1 ? gw - wx : gw + wx;
+    }
+    const float wy = fmaf(p.hh, c[1], p.oy * c[3]);
+    return plane == 3 ? gw - wy : gw + wy;
+}
+
+// Triangle t of an instance, clipped: `poly` receives the polygon's vertices (x y z w r g b a each), the result is their
+// number (0, 3..8) or -1 when a clip coordinate is not finite (the triangle is discarded).
+__device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, float (*poly)[8]) {
+    float other[8][8];
+    float(*src)[8] = other;
+    float(*dst)[8] = poly;  // five planes: other -> poly -> other -> poly -> other -> poly
+    for (int k = 0; k < 3; ++k) {
+        const long long vidx = triangle_vertex(p, t, k);
+        const float* pos = vertex_position(p, vidx);
+        float x = 0.0f, y = 0.0f, z = 0.0f, w = 1.0f;
+        if (pos) {
+            x = __ldg(pos);
+            y = __ldg(pos + 1);
+            z = __ldg(pos + 2);
+            if (p.pos_comps == 4) w = __ldg(pos + 3);
+        }
+        if (!finite_f(x) || !finite_f(y) || !finite_f(z) || !finite_f(w)) return -1;
+        const float4 c = fetch_color(p, vidx);
+        src[k][0] = x; src[k][1] = y; src[k][2] = z; src[k][3] = w;
+        src[k][4] = c.x; src[k][5] = c.y; src[k][6] = c.z; src[k][7] = c.w;
+    }
+    int n = 3;
+    for (int plane = 0; plane < 5; ++plane) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const float* cur = src[i];
+            const float* nxt = src[i + 1 == n ? 0 : i + 1];
+            const float dc = clip_distance(p, cur, plane), dn = clip_distance(p, nxt, plane);
+            const bool in_c = dc >= 0.0f, in_n = dn >= 0.0f;
+            if (in_c) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dst[m][k] = cur[k];
+                ++m;
+            }
+            if (in_c != in_n) {  // the edge is cut from its inside end to its outside end, whichever way the polygon runs
+                const float* I = in_c ? cur : nxt;
+                const float* O = in_c ? nxt : cur;
+                const float di = in_c ? dc : dn, d_o = in_c ? dn : dc;
+                const float tt = __fdiv_rn(di, di - d_o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dst[m][k] = __fmaf_rn(tt, O[k] - I[k], I[k]);
+                if (plane == 0) dst[m][3] = kClipW;
+                ++m;
+            }
+        }
+        float(*tmp)[8] = src;
+        src = dst;
+        dst = tmp;
+        n = m;
+        if (n < 3) return 0;
+    }
+    return n;  // five swaps: the result is in `poly`
+}
+
+// One triangle of a clipped polygon -> its compact record and scissored pixel box, by the rules of make_compact_t (R1, R2,
+// R4; oracle/raster.c setup_triangle); false: it produces no fragments.
+__device__ __forceinline__ bool make_compact_from(const DrawParams& p, const float* v0, const float* v1, const float* v2, TriRecC& r, int4& box) {
+    box = make_int4(1, 0, 1, 0);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* v = k == 0 ? v0 : k == 1 ? v1 : v2;
+        if (!(v[3] > 0.0f)) ok = false;
+        const float iw = 1.0f / v[3];
+        const float xf = fmaf(p.hw, v[0] * iw, p.ox);
+        const float yf = fmaf(p.hh, v[1] * iw, p.oy);
+        const float zf = fmaf(p.dz, v[2] * iw, p.zmin_vp);
+        if (!finite_f(xf) || !finite_f(yf) || !finite_f(zf) || !finite_f(iw) || fabsf(xf) > kGuardBand || fabsf(yf) > kGuardBand) ok = false;
+        r.X[k] = ok ? __float2int_rn(xf * 16.0f) : 0;
+        r.Y[k] = ok ? __float2int_rn(yf * 16.0f) : 0;
+        r.z[k] = zf;
+        r.iw[k] = iw;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) r.col[k][ch] = v[4 + ch] * iw;
+    }
+    if (!ok) return false;
+    const long long two_a = (long long)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) - (long long)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);  // R4
+    if (two_a == 0) return false;
+    const bool front = p.st.front_face == 0 ? (two_a < 0) : (two_a > 0);
+    if ((front && (p.st.cull_mode & 1u)) || (!front && (p.st.cull_mode & 2u))) return false;
+    const int4 b = record_box(p, r);
+    if (b.x > b.y || b.z > b.w) return false;
+    box = b;
+    return true;
+}
+
+__device__ __forceinline__ uint2 pack_box(const int4 box) {
+    return make_uint2((uint32_t)box.x | ((uint32_t)box.y << 16), (uint32_t)box.z | ((uint32_t)box.w << 16));
+}
+__device__ __forceinline__ int4 unpack_box(const uint2 b) {  // minx maxx miny maxy
+    return make_int4((int)(b.x & 0xffffu), (int)(b.x >> 16), (int)(b.y & 0xffffu), (int)(b.y >> 16));
+}
+
+__device__ __forceinline__ void clip_statistics(const DrawParams& p, int m, unsigned long long n_inst) {
+    if (!p.stats) return;
+    if (m < 0) {
+        atomicAdd(&p.stats[10], n_inst);
+    } else {
+        atomicAdd(&p.stats[8], n_inst);
+        if (m >= 3) atomicAdd(&p.stats[9], (unsigned long long)(m - 2) * n_inst);
+    }
 }
 
 // compact -> expanded record (R5: sign-normalised integer edge equations, top-left bias, 1/2A); `c` must be the record of a
@@ -384,22 +531,82 @@ __device__ __forceinline__ int4 record_box(const DrawParams& p, const TriRecC& c
 }
 
 // Triangle t of an instance -> its expanded record; false: it produces no fragments (its box is left empty).
-__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r) {
+__device__ __forceinline__ void empty_record(TriRec& r) {
+    memset(&r, 0, sizeof r);
+    r.minx = 1;
+    r.miny = 1;
+}
+__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r, bool& slow) {
     TriRecC c;
     int4 box;
-    const bool ok = make_compact(p, t, c, box);
-    if (ok) {
-        expand_record(p, c, box, r);
-    } else {
-        memset(&r, 0, sizeof r);
-        r.minx = 1;
-        r.miny = 1;
-    }
+    const bool ok = make_compact(p, t, c, box, slow);
+    if (ok) expand_record(p, c, box, r);
+    else empty_record(r);
+    return ok;
+}
+// triangle j of a clipped polygon -> expanded record (direct draws)
+__device__ __forceinline__ bool make_record_from(const DrawParams& p, const float (*poly)[8], int j, TriRec& r) {
+    TriRecC c;
+    int4 box;
+    const bool ok = make_compact_from(p, poly[0], poly[j + 1], poly[j + 2], c, box);
+    if (ok) expand_record(p, c, box, r);
+    else empty_record(r);
     return ok;
 }
 
-// BINNED: compact records (6 x 16 bytes) for the triangles that produce fragments + the first binning pass;
-// otherwise (direct draws of at most kDirectMax triangles) expanded records for all of them.
+// A clipped primitive of a binned draw (clip_kernel): the first triangle of its polygon takes the primitive's own record, the
+// others get extra records after the draw's (allocated from work_counter[4]); the tiles they overlap are counted here
+// (setup_kernel counted nothing for the primitive), bin_fill_kernel files them.
+__device__ __forceinline__ void count_tiles(const DrawParams& p, const int4 box, uint32_t n_inst) {
+    int tx0, tx1, ty0, ty1;
+    if (!tile_range(p, box, tx0, tx1, ty0, ty1)) return;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&p.tile_counts[(uint32_t)ty * p.tiles_x + (uint32_t)tx], n_inst);
+}
+__device__ __forceinline__ void clip_binned(const DrawParams& p, uint32_t t, uint32_t n_inst) {
+    float poly[8][8];
+    const int m = clip_primitive(p, t, poly);
+    clip_statistics(p, m, n_inst);
+    bool any_fragments = false;
+    if (m >= 3) {
+        TriRecC c;
+        int4 box;
+        if (make_compact_from(p, poly[0], poly[1], poly[2], c, box)) {
+            any_fragments = true;
+            for (uint32_t inst = 0; inst < n_inst; ++inst) {
+                reinterpret_cast<TriRecC*>(p.tris)[(size_t)inst * p.tris_per_instance + t] = c;
+                p.boxes[(size_t)inst * p.tris_per_instance + t] = pack_box(box);
+            }
+            count_tiles(p, box, n_inst);
+        }
+        const uint32_t n_extra = (uint32_t)m - 3u;
+        if (n_extra) {
+            const uint32_t k = atomicAdd(p.work_counter + 4, n_extra);
+            if (k + n_extra > p.clip_capacity) {  // no room (KznDrawStatistics::clip_overflow): the slots that exist stay unused
+                for (uint32_t i = k; i < p.clip_capacity && i < k + n_extra; ++i) p.clip_parent[i] = 0xffffffffu;
+                if (p.stats) atomicAdd(&p.stats[11], (unsigned long long)n_inst);
+                any_fragments = true;  // (not "culled": lost)
+            } else {
+                p.clip_link[t] = k | n_extra << 29;
+                atomicOr(&p.clip_bits[t >> 5], 1u << (t & 31u));
+                TriRecC* recs = reinterpret_cast<TriRecC*>(p.tris) + p.total_tris + k;
+                for (uint32_t j = 1; j <= n_extra; ++j) {
+                    TriRecC e;
+                    int4 eb;
+                    if (make_compact_from(p, poly[0], poly[j + 1], poly[j + 2], e, eb)) {
+                        any_fragments = true;
+                        recs[j - 1] = e;
+                        count_tiles(p, eb, n_inst);
+                    }
+                    p.boxes[p.total_tris + k + j - 1u] = pack_box(eb);
+                    p.clip_parent[k + j - 1u] = t << 3 | j;
+                }
+            }
+        }
+    }
+    if (!any_fragments && p.stats) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
+}
+
 template <bool BINNED>
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
@@ -415,12 +622,68 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     __shared__ uint8_t keep[256];
     TriRecC c;
     int4 box;
-    const bool ok = make_compact(p, t, c, box);
+    bool slow;
+    const bool ok = make_compact(p, t, c, box, slow);
+    slow = slow && in_range;
+    const uint32_t n_inst = p.total_tris / p.tris_per_instance;  // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
+    bool any_fragments = ok;  // some triangle of the (clipped) primitive produces fragments
+    if (BINNED && slow) p.clip_list[atomicAdd(p.work_counter + 6, 1u)] = t;  // R3: clip_kernel does this one (nothing is counted for it here)
+    if (!BINNED) {
+        // direct draws (one CTA): a clipped primitive takes as many consecutive records as its polygon has triangles, so the
+        // records are placed by a prefix sum over the CTA whenever any primitive was clipped
+        __shared__ uint32_t warp_sums[8];
+        if (__syncthreads_or(slow)) {
+            float poly[8][8];
+            int m = 0;
+            if (slow) {
+                m = clip_primitive(p, t, poly);
+                clip_statistics(p, m, n_inst);
+            }
+            const uint32_t cnt = !in_range ? 0u : (slow && m > 3) ? (uint32_t)m - 2u : 1u;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)(threadIdx.x & 31u) >= d) incl += y;
+            }
+            if ((threadIdx.x & 31u) == 31u) warp_sums[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            uint32_t before = 0, per_inst = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < 8u; ++w) {
+                if (w < (threadIdx.x >> 5)) before += warp_sums[w];
+                per_inst += warp_sums[w];
+            }
+            const uint32_t at = before + incl - cnt;
+            if (threadIdx.x == 0) p.work_counter[3] = per_inst * n_inst;
+            if (in_range) {
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    TriRec r;
+                    bool okj = ok;
+                    if (slow) {
+                        okj = m >= 3 && make_record_from(p, poly, (int)j, r);
+                        if (m < 3) empty_record(r);
+                    } else if (ok) {
+                        expand_record(p, c, box, r);
+                    } else {
+                        empty_record(r);
+                    }
+                    any_fragments = any_fragments || okj;
+                    for (uint32_t inst = 0; inst < n_inst; ++inst) p.tris[(size_t)inst * per_inst + at + j] = r;
+                }
+                if (p.stats) {
+                    atomicAdd(&p.stats[0], (unsigned long long)n_inst);
+                    if (!any_fragments) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
+                }
+            }
+            return;
+        }
+        if (threadIdx.x == 0) p.work_counter[3] = p.total_tris;
+    }
     // binned draws find their triangles through the packed boxes: a triangle that produces no fragments (culled,
     // degenerate, outside the clip rectangle or this GPU's band) needs no record — and a CTA none of whose triangles
     // does (most of them, on a band of a split frame) has nothing to stage
     const bool keep_mine = BINNED ? (in_range && ok) : in_range;
-    const uint32_t n_inst = p.total_tris / p.tris_per_instance;  // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
     if (__syncthreads_or(keep_mine)) {
         if (BINNED) {
             const uint4* src = reinterpret_cast<const uint4*>(&c);
@@ -428,13 +691,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
             for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
         } else {
             TriRec r;
-            if (ok) {
-                expand_record(p, c, box, r);
-            } else {
-                memset(&r, 0, sizeof r);
-                r.minx = 1;
-                r.miny = 1;
-            }
+            if (ok) expand_record(p, c, box, r);
+            else empty_record(r);
             const uint4* src = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
             for (int q = 0; q < kQuads; ++q) stage[threadIdx.x * kQuads + q] = src[q];
@@ -450,12 +708,10 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         }
     }
     if (in_range) {
-        for (uint32_t inst = 0; inst < n_inst; ++inst)
-            p.boxes[(size_t)inst * p.tris_per_instance + t] =
-                make_uint2((uint32_t)box.x | ((uint32_t)box.y << 16), (uint32_t)box.z | ((uint32_t)box.w << 16));
+        for (uint32_t inst = 0; inst < n_inst; ++inst) p.boxes[(size_t)inst * p.tris_per_instance + t] = pack_box(box);
         if (p.stats) {
             atomicAdd(&p.stats[0], (unsigned long long)n_inst);
-            if (!ok) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
+            if (!any_fragments && !(BINNED && slow)) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
         }
     }
     if (BINNED) {  // first binning pass fused here: count the tiles each triangle overlaps
@@ -464,6 +720,16 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
+
+#ifndef KZN_FS_TEMPLATE
+// The primitives setup_kernel<true> found crossing the eye plane or the guard band (work_counter[6] of them, usually none):
+// one thread each.
+__global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    const uint32_t n = p.work_counter[6], n_inst = p.total_tris / p.tris_per_instance;
+    for (uint32_t i = blockIdx.x * 128u + threadIdx.x; i < n; i += gridDim.x * 128u) clip_binned(p, p.clip_list[i], n_inst);
+}
+#endif
 
 // ---- binning --------------------------------------------------------------------------------------------------
 
@@ -474,12 +740,25 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
     bool valid = false;
-    if (t < p.total_tris) {
-        const uint2 box = __ldg(&p.boxes[t]);  // minx | maxx << 16, miny | maxy << 16
-        valid = tile_range(p, make_int4((int)(box.x & 0xffffu), (int)(box.x >> 16), (int)(box.y & 0xffffu), (int)(box.y >> 16)), tx0, tx1,
-                           ty0, ty1);
+    if (t < p.total_tris) valid = tile_range(p, unpack_box(__ldg(&p.boxes[t])), tx0, tx1, ty0, ty1);
+    bin_emit<true>(p, valid, t << 3, 1u, tx0, tx1, ty0, ty1);  // list entries: record << 3 | fan index (0: the primitive's own record)
+    // the extra triangles of clipped primitives (R3; rare): entry (instance's record of the primitive) << 3 | fan index, so
+    // that sorting the entries puts them at the primitive's place
+    const uint32_t n_extra = min(p.work_counter[4], p.clip_capacity);
+    for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < n_extra; k += gridDim.x * 256u) {
+        const uint32_t parent = p.clip_parent[k];
+        if (parent == 0xffffffffu) continue;
+        if (!tile_range(p, unpack_box(p.boxes[p.total_tris + k]), tx0, tx1, ty0, ty1)) continue;
+        const uint32_t n_inst = p.total_tris / p.tris_per_instance;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const uint32_t tile = (uint32_t)ty * p.tiles_x + (uint32_t)tx;
+                for (uint32_t inst = 0; inst < n_inst; ++inst) {
+                    const uint32_t pos = p.tile_offsets[tile] + atomicAdd(&p.tile_cursor[tile], 1u);
+                    if (pos < p.bin_capacity) p.bin_entries[pos] = ((inst * p.tris_per_instance + (parent >> 3)) << 3) | (parent & 7u);
+                }
+            }
     }
-    bin_emit<true>(p, valid, t, 1u, tx0, tx1, ty0, ty1);
 }
 
 // exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
@@ -654,12 +933,13 @@ __device__ __forceinline__ const uint32_t* sort_tile_list(SortShared& sh, uint32
         lo = min(lo, sh.warp_counts[w]);
         hi = max(hi, table[w]);
     }
+    lo &= ~7u;  // entries are record << 3 | fan index: sorted by record (the triangles of one primitive do not overlap)
     __syncthreads();
     const uint32_t span = hi - lo;
     const uint32_t bits = span ? 32u - (uint32_t)__clz(span) : 0u;
     const uint32_t per = ((n + kSortThreads - 1) / kSortThreads) * 32u;  // ids per warp, whole batches
     const uint32_t w_beg = min(warp * per, n), w_end = min(w_beg + per, n);
-    for (uint32_t shift = 0; shift < bits; shift += 8) {
+    for (uint32_t shift = 3; shift < bits; shift += 8) {
         for (uint32_t i = tid; i < 256u * kSortWarps; i += kSortThreads) table[i] = 0;
         __syncthreads();
         // digit counts per warp
@@ -1194,6 +1474,47 @@ __device__ __noinline__ void shade_wide(const DrawParams& p, BrickState& bs, con
 // the primitive order by construction and nothing is shared between warps but the UNORM8 table.
 // *Block-level trivial accept*: lane i tests triangle i (the first 32) at the corner of the block where each edge function
 // is smallest; if all three are positive the whole block is inside the triangle and its rows skip coverage entirely.
+// Direct draws of at most kFusedMax triangles, one of them clipped (R3; rare): the calling warp makes the draw's records
+// again, lane i = triangle i, a clipped one taking as many of the 32 slots of `recs` as its polygon has triangles; returns
+// their number.  Kept out of line: nothing of it (the clipper's polygons least of all) should cost the raster loop a register.
+__device__ __noinline__ uint32_t fused_clip_records(const DrawParams& p, uint32_t lane, TriRec* recs) {
+    TriRec r;
+    bool ok = false, slow = false;
+    const bool mine = lane < p.total_tris;
+    if (mine) ok = make_record(p, lane % p.tris_per_instance, r, slow);
+    uint32_t n_recs = p.total_tris;
+    __syncwarp();
+    {  // records placed by a prefix sum over the polygon sizes
+        float poly[8][8];
+        int m = 0;
+        if (slow) {
+            m = clip_primitive(p, lane % p.tris_per_instance, poly);
+            if (blockIdx.x == 0) clip_statistics(p, m, 1ull);
+        }
+        const uint32_t cnt = !mine ? 0u : (slow && m > 3) ? (uint32_t)m - 2u : 1u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += y;
+        }
+        n_recs = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t at = incl - cnt;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            if (slow) {
+                if (m >= 3) ok = make_record_from(p, poly, (int)j, r) || ok;
+                else empty_record(r);
+            }
+            recs[at + j] = r;
+        }
+    }
+    if (mine && p.stats && blockIdx.x == 0) {
+        atomicAdd(&p.stats[0], 1ull);
+        if (!ok) atomicAdd(&p.stats[1], 1ull);
+    }
+    return n_recs;
+}
+
 template <uint32_t FS, int NEED_DST>
 __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
     kzn_pdl_wait();
@@ -1207,22 +1528,31 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
         for (int i = 0; i < 8; ++i) unorm_lut[lane + 32 * i] = unorm8_to_float(lane + 32 * i);
         __syncwarp();
     }
-    // Draws of at most 32 triangles (fullscreen passes, quads) have no setup_kernel launch: every warp makes the records
+    // Draws of at most kFusedMax triangles (fullscreen passes, quads) have no setup_kernel launch: every warp makes the records
     // itself, lane i = triangle i, into its own shared memory — a few hundred instructions per warp against a dependent
     // kernel launch per draw.  The work counter is then handed back by the last warp to leave (see the end of the kernel).
     __shared__ TriRec own_recs[32];
+    __shared__ uint32_t n_recs_s;  // records of the draw: its triangles, a clipped one counting as many as its polygon has triangles (R3)
+    uint32_t n_recs = p.total_tris;
     if (p.fused_setup) {
+        bool ok = false, slow = false;
         if (lane < p.total_tris) {
             TriRec r;
-            const bool ok = make_record(p, lane % p.tris_per_instance, r);
+            ok = make_record(p, lane % p.tris_per_instance, r, slow);
             own_recs[lane] = r;
-            if (p.stats && blockIdx.x == 0) {
-                atomicAdd(&p.stats[0], 1ull);
-                if (!ok) atomicAdd(&p.stats[1], 1ull);
-            }
         }
-        __syncwarp();
+        if (__builtin_expect(__any_sync(0xffffffffu, slow), 0)) {
+            n_recs = fused_clip_records(p, lane, own_recs);
+        } else if (lane < p.total_tris && p.stats && blockIdx.x == 0) {
+            atomicAdd(&p.stats[0], 1ull);
+            if (!ok) atomicAdd(&p.stats[1], 1ull);
+        }
+    } else {
+        n_recs = p.work_counter[3];  // setup_kernel<false>
     }
+    if (lane == 0) n_recs_s = n_recs;  // (read from shared memory where it is needed: a register for the whole kernel costs the row loop a spill)
+    __syncwarp();
+#define n_recs (*(volatile uint32_t*)&n_recs_s)
     const TriRec* recs = p.fused_setup ? own_recs : p.tris;
     const uint32_t n_blocks = p.tiles_x * p.tiles_y;
     const unsigned long long pitch = (unsigned long long)p.fb_w * 4ull;
@@ -1263,7 +1593,7 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
         uint32_t full = 0;  // bit i: triangle i covers every pixel centre of this block (and needs no per-fragment work)
         if (!fs_needs_interpolants<FS>(p) && !depth_test) {
             bool ok = false;
-            if (lane < p.total_tris) {
+            if (lane < n_recs) {
                 const TriRec& t = recs[lane];
                 const uint32_t bias = t.bias_bits;
                 ok = t.minx <= t.maxx && (bias & 8u);  // produces fragments; the depth clip cannot reject (setup)
@@ -1285,7 +1615,7 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
             // (whatever earlier triangles produced is overwritten; statistics still need their fragments, so with
             // statistics on this is limited to single-triangle draws) and the block lies inside the clip rectangle:
             // four rows of orbit + packed conversion + two 16-byte stores per lane, no per-row bookkeeping.
-            const uint32_t last = p.total_tris - 1u;
+            const uint32_t last = n_recs - 1u;
             if (last < 32u && (full >> last & 1u) && (last == 0u || !p.stats) && has_color && !p.color_tiled && col_whole &&
                 r_lo == row0 && r_hi == row0 + kDirectRows - 1) {
                 unsigned long long a = p.color_base + ((unsigned long long)row0 * p.fb_w + px0) * 4ull;
@@ -1352,7 +1682,7 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
             }
             const int32_t sy = 16 * py + 8;  // fixed-point sample row (R2)
             uint32_t cdirty = 0, zdirty = 0;
-            for (uint32_t i = 0; i < p.total_tris; ++i) {
+            for (uint32_t i = 0; i < n_recs; ++i) {
                 if (FS != KZN_FS_VERTEX_COLOR && i < 32u && (full >> i & 1u)) {  // warp-uniform
                     // block-level trivial accept: every pixel of the row inside the clip rectangle is covered and passes
                     n_covered += __popc(quad_clip);
@@ -1431,6 +1761,8 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
         }
     }
 }
+
+#undef n_recs
 
 __constant__ uint32_t kWidthMagic[17] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,
                                          7282,  6554,  5958,  5462,  5042,  4682,  4370, 4096};  // ceil(2^16 / w)
@@ -1580,6 +1912,13 @@ __device__ __forceinline__ uint32_t brick_mask_of(uint2 box, int tile_px0, int t
 
 // where the brick masks of a tile's list live: 4-byte aligned so that a lane can fetch four entries at once (the gap of
 // 4 bytes per tile keeps consecutive tiles' regions apart after rounding up)
+// the record (and box) a list entry names: record << 3 | fan index j; j > 0: extra record j - 1 of the clipped primitive
+__device__ __forceinline__ uint32_t entry_record(const DrawParams& p, uint32_t e) {
+    const uint32_t rec = e >> 3, j = e & 7u;
+    if (j == 0u) return rec;
+    return p.total_tris + (p.clip_link[rec % p.tris_per_instance] & 0x1fffffffu) + j - 1u;
+}
+
 __device__ __forceinline__ uint8_t* tile_masks(const DrawParams& p, uint32_t tile, uint32_t beg) {
     return p.bin_masks + (((size_t)beg + 3u) & ~(size_t)3u) + 4u * (size_t)tile;
 }
@@ -1600,6 +1939,11 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __gr
     constexpr uint32_t kFull = 0xffffffffu;
     __shared__ uint32_t tables[kSortWarps][256];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // bin_fill_kernel was the last to need the allocator of extra records: zero for the next draw
+        p.work_counter[5] = p.work_counter[4];
+        p.work_counter[4] = 0u;
+        p.work_counter[6] = 0u;
+    }
     const uint32_t tile = blockIdx.x * kSortWarps + warp;
     if (tile >= p.tiles_x * p.tiles_y) return;
     const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
@@ -1621,11 +1965,11 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __gr
         lo = min(lo, v);
         hi = max(hi, v);
     }
-    lo = __reduce_min_sync(kFull, lo);
+    lo = __reduce_min_sync(kFull, lo) & ~7u;  // entries are record << 3 | fan index: the triangles of one primitive do not overlap, their order is free
     hi = __reduce_max_sync(kFull, hi);
     const uint32_t span = hi - lo;
     const uint32_t bits = span ? 32u - (uint32_t)__clz(span) : 0u;
-    for (uint32_t shift = 0; shift < bits; shift += 8) {
+    for (uint32_t shift = 3; shift < bits; shift += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) table[lane + 32 * k] = 0;
         __syncwarp();
@@ -1699,7 +2043,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __gr
     for (uint32_t i = lane; i < n; i += 32u) {
         const uint32_t id = __ldcg(a + i);
         if (a != out) out[i] = id;
-        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
+        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[entry_record(p, id)]), tile_px0, tile_py0);
     }
 }
 
@@ -1712,6 +2056,11 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
     SortShared& sh = *reinterpret_cast<SortShared*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    if (tile == 0 && tid == 0) {  // (as in tile_sort_warp_kernel)
+        p.work_counter[5] = p.work_counter[4];
+        p.work_counter[4] = 0u;
+        p.work_counter[6] = 0u;
+    }
     const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
     const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], list_len = end - beg;
     if (list_len == 0) return;
@@ -1727,7 +2076,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
     for (uint32_t i = tid; i < list_len; i += kSortThreads) {
         const uint32_t id = sorted[i];
         p.bin_entries[beg + i] = id;
-        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[id]), tile_px0, tile_py0);
+        masks[i] = (uint8_t)brick_mask_of(__ldg(&p.boxes[entry_record(p, id)]), tile_px0, tile_py0);
     }
 }
 
@@ -1775,7 +2124,10 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
         const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
         if (end == beg) continue;
         const bool direct = end - beg > (uint32_t)kSortCap || end > p.bin_capacity;
-        const uint32_t n_source = direct ? p.total_tris : end - beg;
+        // (walking all triangles: with clipped primitives in the draw every primitive stands for eight list entries, its own
+        // record and up to five extra ones, so that the extra triangles come at the primitive's place)
+        const uint32_t walk_shift = direct && p.work_counter[5] ? 3u : 0u;
+        const uint32_t n_source = direct ? p.total_tris << walk_shift : end - beg;
 
         // ---- brick prologue: lane l moves the 8 pixels 8 (l & 1) .. + 7 of row l >> 1, two 16-byte vectors when the row
         // pitch allows it: destination values the result depends on, dirty flags ----
@@ -1850,8 +2202,20 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
                         hits = (m4 & 1u) | (m4 >> 7 & 2u) | (m4 >> 14 & 4u) | (m4 >> 21 & 8u);
                     } else {
 #pragma unroll
-                        for (uint32_t k = 0; k < 4u; ++k)
-                            if (i0 + k < n_source && (brick_mask_of(__ldg(&p.boxes[i0 + k]), tile_px0, tile_py0) >> brick & 1u)) hits |= 1u << k;
+                        for (uint32_t k = 0; k < 4u; ++k) {
+                            if (i0 + k >= n_source) break;
+                            const uint32_t rec = (i0 + k) >> walk_shift, j = (i0 + k) & ((1u << walk_shift) - 1u);
+                            uint2 b;
+                            if (j) {  // extra record j - 1 of a clipped primitive, if it has that many
+                                const uint32_t prim = rec % p.tris_per_instance;
+                                const uint32_t link = p.clip_bits[prim >> 5] >> (prim & 31u) & 1u ? p.clip_link[prim] : 0u;
+                                if (j > link >> 29) continue;
+                                b = __ldg(&p.boxes[p.total_tris + (link & 0x1fffffffu) + j - 1u]);
+                            } else {
+                                b = __ldg(&p.boxes[rec]);
+                            }
+                            if (brick_mask_of(b, tile_px0, tile_py0) >> brick & 1u) hits |= 1u << k;
+                        }
                     }
                     // ordered append: entry (lane, k) goes after all hits of lower lanes and my own lower k
                     uint32_t incl = __popc(hits);
@@ -1863,7 +2227,7 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
                     uint32_t at = pend_n + incl - __popc(hits);
 #pragma unroll
                     for (uint32_t k = 0; k < 4u; ++k)
-                        if (hits >> k & 1u) pend[at++] = direct ? i0 + k : ids[i0 + k];
+                        if (hits >> k & 1u) pend[at++] = entry_record(p, direct ? (i0 + k) << (3u - walk_shift) : ids[i0 + k]);
                     pend_n += __shfl_sync(0xffffffffu, incl, 31);
                     ++step;
                 }
@@ -1982,8 +2346,14 @@ struct KznRasterScratch {
     size_t mask_capacity = 0;
     uint32_t* bin_entries_alt = nullptr;
     size_t alt_capacity = 0;
-    uint32_t* counters = nullptr;  // [4]: work counter of the direct kernel
+    uint32_t* counters = nullptr;  // [8]: the work_counter slots (see kFusedMax)
     size_t counter_capacity = 0;
+    uint32_t* clip_link = nullptr;  // clipped primitives of binned draws: see DrawParams
+    size_t link_capacity = 0;
+    uint32_t* clip_parent = nullptr;
+    size_t parent_capacity = 0;
+    uint32_t* clip_list = nullptr;
+    size_t list_capacity = 0;
     bool attrs_set = false;
     // Executable command buffers that recorded a draw hold the buffer addresses of that time in their CUDA graphs: while any
     // such command buffer exists (pins > 0) a buffer that is outgrown is retired instead of freed, and freed when the last
@@ -2011,6 +2381,9 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->bin_masks);
     cudaFree(s->bin_entries_alt);
     cudaFree(s->counters);
+    cudaFree(s->clip_link);
+    cudaFree(s->clip_parent);
+    cudaFree(s->clip_list);
     delete s;
 }
 
@@ -2114,22 +2487,35 @@ void make_clip(const KznFramebuffer* fb, const KznViewport* vp, const KznRect2D*
     p->zclip_hi = vp->minDepth < vp->maxDepth ? vp->maxDepth : vp->minDepth;
 }
 
-// the queue's raster scratch, grown to hold `total` triangle records and (binned draws) the tile tables
-KznResult ensure_scratch(KznQueue* q, size_t total, size_t tiles, bool binned) {
+// extra records a binned draw of `per_instance` triangles can give its clipped primitives (R3): five each (the most a
+// polygon needs) up to 16384 primitives, one each on average beyond that (KznDrawStatistics::clip_overflow counts the rest)
+size_t clip_reserve(size_t per_instance) { return per_instance * 5 < per_instance + 65536 ? per_instance * 5 : per_instance + 65536; }
+
+// the queue's raster scratch, grown to hold the records of `total` triangles (`per_instance` of them distinct) and (binned
+// draws) the tile tables
+KznResult ensure_scratch(KznQueue* q, size_t total, size_t per_instance, size_t tiles, bool binned) {
     KznResult r;
     if (!q->raster) {
         q->raster = new (std::nothrow) KznRasterScratch();
         KZN_REQUIRE(q->raster, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
     }
     KznRasterScratch* s = q->raster;
-    if ((r = grow(q, &s->tris, &s->tri_capacity, total))) return r;
-    if ((r = grow(q, &s->boxes, &s->box_capacity, total))) return r;
-    if (!s->counters) {  // [0] block dispenser of the direct kernel, [1] warps that have left it (fused setup): start at zero
-        if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)4))) return r;
+    // direct draws: expanded records, up to six per primitive; binned draws: compact records, the extra ones after the draw's
+    const size_t extras = binned ? clip_reserve(per_instance) : 0;
+    const size_t tri_slots = binned ? ((total + extras) * sizeof(TriRecC) + sizeof(TriRec) - 1) / sizeof(TriRec) : total * 6;
+    if ((r = grow(q, &s->tris, &s->tri_capacity, tri_slots))) return r;
+    if ((r = grow(q, &s->boxes, &s->box_capacity, total + extras))) return r;
+    if (binned) {
+        if ((r = grow(q, &s->clip_link, &s->link_capacity, per_instance))) return r;
+        if ((r = grow(q, &s->clip_parent, &s->parent_capacity, extras))) return r;
+        if ((r = grow(q, &s->clip_list, &s->list_capacity, per_instance))) return r;
+    }
+    if (!s->counters) {  // the dispensers and the allocator of extra records start at zero and are handed back at zero by their users
+        if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)8))) return r;
         KZN_CUDA(cudaMemsetAsync(s->counters, 0, s->counter_capacity * sizeof(uint32_t), q->stream));  // ordered before the first draw kernel of this queue
     }
     if (binned) {
-        if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1))) return r;
+        if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1 + (per_instance + 31) / 32))) return r;
         // capacity for the (tile, triangle) pairs: the exact total is only known on the device; tiles whose
         // segment does not fit fall back to walking the whole triangle list (still exact, only slower)
         size_t want = total * 8 + tiles;
@@ -2187,7 +2573,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
     KZN_REQUIRE(p.cx1 <= 65535 && p.cy1 <= 65535, KZN_ERROR_FEATURE_NOT_PRESENT,
                 "draw: render area reaches beyond pixel 65535 (pixel boxes are packed into 16 bits per coordinate)");
-    KZN_REQUIRE(total <= 0x7fffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: more than 2^31 triangles in one draw");
+    KZN_REQUIRE(total <= 0x1fffffffull, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: more than 2^29 triangles in one draw");
 
     p.vertex_base = vi->buffer_address;
     p.vertex_size = vi->buffer_size;
@@ -2238,7 +2624,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
 
     size_t tiles = (size_t)p.tiles_x * p.tiles_y;
     p.binned = total > kDirectMax;
-    if ((r = ensure_scratch(q, (size_t)total, tiles, p.binned != 0))) return r;
+    if ((r = ensure_scratch(q, (size_t)total, (size_t)ntri, tiles, p.binned != 0))) return r;
     if (q->recording) kzn_command_buffer_uses_raster_scratch(q->recording, q->raster);  // its graph will name these buffers
     KznRasterScratch* s = q->raster;
     p.tris = s->tris;
@@ -2252,23 +2638,33 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         p.exact_spans = exact;
     }
     if (p.binned) {
-        p.tile_counts = s->tile_words;
+        p.tile_counts = s->tile_words;  // counts | cursor | clip_bits: zeroed together below
         p.tile_cursor = s->tile_words + tiles;
-        p.tile_offsets = s->tile_words + 2 * tiles;
+        p.clip_bits = s->tile_words + 2 * tiles;
+        p.tile_offsets = p.clip_bits + (ntri + 31) / 32;
         p.bin_entries = s->bin_entries;
         p.bin_masks = s->bin_masks;
         p.bin_entries_alt = s->bin_entries_alt;
         p.bin_capacity = (uint32_t)(s->bin_capacity > 0xfffffff0ull ? 0xfffffff0ull : s->bin_capacity);
+        p.clip_link = s->clip_link;
+        p.clip_parent = s->clip_parent;
+        p.clip_list = s->clip_list;
+        p.clip_capacity = (uint32_t)clip_reserve((size_t)ntri);
     }
 
-    if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, 2 * tiles * sizeof(uint32_t), q->stream));
-    p.fused_setup = !p.binned && total <= 32u;
+    if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, (2 * tiles + (ntri + 31) / 32) * sizeof(uint32_t), q->stream));
+    p.fused_setup = !p.binned && total <= kFusedMax;
     if (!p.fused_setup) {
         if (p.binned) launch_draw_kernel(setup_kernel<true>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         else launch_draw_kernel(setup_kernel<false>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "setup_kernel"))) return r;
     }
     if (p.binned) {
+        {   // R3: the primitives setup left to the clipper (usually none: the kernel reads one counter)
+            const uint64_t blocks = (ntri + 127) / 128, cap = (uint64_t)q->device->sm_count * 8;
+            launch_draw_kernel(clip_kernel, dim3((uint32_t)(blocks < cap ? blocks : cap)), dim3(128), 0, q->stream, p);
+            if ((r = kzn_launched(q, "clip_kernel"))) return r;
+        }
         launch_draw_kernel(bin_scan_kernel, dim3(1), dim3(1024), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
         launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
@@ -2340,9 +2736,9 @@ KznResult kzn_queue_reserve_draw(KznQueue* queue, uint64_t max_triangles, uint32
     KznResult r = kzn_queue_enter(queue);
     if (r) return r;
     KZN_VALID(!queue->recording, "kzn_queue_reserve_draw allocates: call it before vkBeginCommandBuffer");
-    KZN_VALID(max_triangles > 0 && max_triangles <= 0x7fffffffull && width && height, "kzn_queue_reserve_draw: bad argument");
+    KZN_VALID(max_triangles > 0 && max_triangles <= 0x1fffffffull && width && height, "kzn_queue_reserve_draw: bad argument");
     size_t tiles = (size_t)((width + kTileW - 1) / kTileW) * ((height + kTileH - 1) / kTileH);
-    return ensure_scratch(queue, (size_t)max_triangles, tiles, max_triangles > kDirectMax);
+    return ensure_scratch(queue, (size_t)max_triangles, (size_t)max_triangles, tiles, max_triangles > kDirectMax);
 }
 
 KznResult kzn_cmd_draw(KznQueue* queue, const KznGraphicsPipelineState* state, const KznFramebuffer* framebuffer,

@@ -14,9 +14,21 @@
  *  R1  clip->window: iw = 1/w; xd = x*iw; xf = fma(W/2, xd, X + W/2) (same for y, z with
  *      fma(maxDepth-minDepth, zd, minDepth)).
  *  R2  snapping: Xfix = (int32) rint(xf * 16) (RNE), sample of pixel p = 16p + 8.
- *  R3  a triangle is DISCARDED (not clipped) when any vertex has w <= 0, a non-finite window
- *      coordinate, or |xf|,|yf| > 2^19 (guard band).  Clipping to the view volume in x/y is done by
- *      scissoring to the viewport rectangle, in z by a per-fragment test against [minDepth,maxDepth].
+ *  R3  clipping.  In x/y the view volume is cut by scissoring to the viewport rectangle, in z by a per-fragment
+ *      test against [minDepth,maxDepth]; neither changes a triangle.  A triangle whose vertices all have
+ *      w > 0 and finite window coordinates with |xf|,|yf| <= 2^19 (guard band) is rasterised as it is.  Any
+ *      other triangle with finite clip coordinates is CLIPPED (Sutherland-Hodgman, homogeneous
+ *      coordinates, colours interpolated with the positions) against five planes, in this order:
+ *          w >= 2^-20,   G*w - wx >= 0,   G*w + wx >= 0,   G*w - wy >= 0,   G*w + wy >= 0
+ *      with G = 2^18 pixels, wx = fma(W/2, x, (X + W/2)*w), wy likewise (window coordinate times w).  A
+ *      crossing edge is cut from its inside end I to its outside end O at t = dI / (dI - dO), every
+ *      component c = fma(t, cO - cI, cI) (both triangles sharing an edge compute the same point); on the
+ *      w plane the new vertex gets w = 2^-20 exactly.  The polygon (<= 8 vertices) is drawn as the fan
+ *      (P0, Pj+1, Pj+2), j = 0.. (<= 6 triangles, at the primitive's place in primitive order), each set
+ *      up by R1-R5 like any triangle.  A triangle with a NaN / infinite clip coordinate is discarded.
+ *      One exception keeps bands of a split frame cheap: when all three w > 0 and all three yf pass the
+ *      tests and the snapped rows miss the clip rectangle, the triangle produces nothing (it is not
+ *      looked at further, whatever its x).
  *  R4  2A = (X1-X0)(Y2-Y0) - (X2-X0)(Y1-Y0) in int64; 2A == 0 -> no fragments; with
  *      FRONT_FACE_COUNTER_CLOCKWISE a triangle is front facing iff 2A < 0 (Vulkan's area a = -A).
  *  R5  edge i is opposite vertex i, E_i(S) = a_i*Sx + b_i*Sy + c_i, sign-normalised so the interior
@@ -36,6 +48,9 @@
 #include <string.h>
 
 #define GUARD_BAND 524288.0f /* 2^19 pixels */
+#define CLIP_GUARD 262144.0f /* 2^18 pixels: where clipped polygons end (R3) */
+#define CLIP_W 9.5367431640625e-07f /* 2^-20 */
+#define MAX_SUB 6 /* triangles a clipped triangle can become: 3 + 5 planes = 8 vertices */
 
 typedef struct {
     int32_t minx, maxx, miny, maxy; /* inclusive pixel bbox, already scissored; empty when minx > maxx */
@@ -134,6 +149,99 @@ static int setup_triangle(const VsOut v[3], const KznGraphicsPipelineState* st, 
     if (t->miny < clip->y0) t->miny = clip->y0;
     if (t->maxy > clip->y1) t->maxy = clip->y1;
     return t->minx <= t->maxx && t->miny <= t->maxy;
+}
+
+/* ---- clipping (R3) ---------------------------------------------------------------------------------------- */
+
+typedef struct {
+    float hw, hh, ox, oy;
+} WindowScale;
+
+static WindowScale window_scale(const KznViewport* vp) {
+    WindowScale s;
+    s.hw = vp->width * 0.5f;
+    s.hh = vp->height * 0.5f;
+    s.ox = vp->x + s.hw;
+    s.oy = vp->y + s.hh;
+    return s;
+}
+
+/* 0: rasterise as it is; 1: clip (or discard); 2: produces nothing (rows) */
+static int classify_triangle(const VsOut v[3], const KznViewport* vp, const ClipRect* clip) {
+    WindowScale s = window_scale(vp);
+    float dz = vp->maxDepth - vp->minDepth;
+    int y_ok = 1, x_ok = 1;
+    int32_t Y[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) {
+        float iw = 1.0f / v[i].w;
+        float yf = fmaf(s.hh, v[i].y * iw, s.oy);
+        if (!(v[i].w > 0.0f) || !is_finite(yf) || !is_finite(iw) || fabsf(yf) > GUARD_BAND) y_ok = 0;
+        float xf = fmaf(s.hw, v[i].x * iw, s.ox);
+        float zf = fmaf(dz, v[i].z * iw, vp->minDepth);
+        if (!is_finite(xf) || !is_finite(zf) || fabsf(xf) > GUARD_BAND) x_ok = 0;
+        if (y_ok) Y[i] = (int32_t)nearbyintf(yf * 16.0f);
+    }
+    if (y_ok) {
+        int32_t minY = Y[0], maxY = Y[0];
+        for (int i = 1; i < 3; ++i) {
+            if (Y[i] < minY) minY = Y[i];
+            if (Y[i] > maxY) maxY = Y[i];
+        }
+        int32_t r0 = (minY - 8 + 15) >> 4, r1 = (maxY - 8) >> 4;
+        if (r0 < clip->y0) r0 = clip->y0;
+        if (r1 > clip->y1) r1 = clip->y1;
+        if (r0 > r1) return 2;
+    }
+    return y_ok && x_ok ? 0 : 1;
+}
+
+static float clip_distance(const float c[8], int plane, const WindowScale* s) {
+    if (plane == 0) return c[3] - CLIP_W;
+    float gw = CLIP_GUARD * c[3];
+    if (plane <= 2) {
+        float wx = fmaf(s->hw, c[0], s->ox * c[3]);
+        return plane == 1 ? gw - wx : gw + wx;
+    }
+    float wy = fmaf(s->hh, c[1], s->oy * c[3]);
+    return plane == 3 ? gw - wy : gw + wy;
+}
+
+/* poly: in = the triangle (x y z w r g b a per vertex), out = the clipped polygon; returns its vertex count (0, 3..8),
+ * or -1 when a clip coordinate is not finite */
+static int clip_triangle(const VsOut v[3], const KznViewport* vp, float poly[8][8]) {
+    WindowScale s = window_scale(vp);
+    float a[8][8], b[8][8];
+    for (int i = 0; i < 3; ++i) {
+        if (!is_finite(v[i].x) || !is_finite(v[i].y) || !is_finite(v[i].z) || !is_finite(v[i].w)) return -1;
+        a[i][0] = v[i].x; a[i][1] = v[i].y; a[i][2] = v[i].z; a[i][3] = v[i].w;
+        for (int ch = 0; ch < 4; ++ch) a[i][4 + ch] = v[i].rgba[ch];
+    }
+    int n = 3;
+    float (*src)[8] = a, (*dst)[8] = b;
+    for (int plane = 0; plane < 5; ++plane) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const float* cur = src[i];
+            const float* nxt = src[i + 1 == n ? 0 : i + 1];
+            float dc = clip_distance(cur, plane, &s), dn = clip_distance(nxt, plane, &s);
+            int in_c = dc >= 0.0f, in_n = dn >= 0.0f;
+            if (in_c) memcpy(dst[m++], cur, sizeof(float) * 8);
+            if (in_c != in_n) {
+                const float* I = in_c ? cur : nxt;
+                const float* O = in_c ? nxt : cur;
+                float di = in_c ? dc : dn, dO = in_c ? dn : dc;
+                float t = di / (di - dO);
+                for (int k = 0; k < 8; ++k) dst[m][k] = fmaf(t, O[k] - I[k], I[k]);
+                if (plane == 0) dst[m][3] = CLIP_W;
+                ++m;
+            }
+        }
+        float (*tmp)[8] = src; src = dst; dst = tmp;
+        n = m;
+        if (n < 3) return 0;
+    }
+    memcpy(poly, src, sizeof(float) * 8 * (size_t)n);
+    return n;
 }
 
 /* ---- fragment programs ------------------------------------------------------------------------------ */
@@ -402,9 +510,12 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
     uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0);
     uint64_t total = ntri * instance_count;
     if (total == 0) return KZN_SUCCESS;
-    TriSetup* tris = (TriSetup*)malloc(total * sizeof(TriSetup));
-    uint8_t* valid = (uint8_t*)malloc(total);
-    if (!tris || !valid) { free(tris); free(valid); return KZN_ERROR_OUT_OF_HOST_MEMORY; }
+    /* MAX_SUB record slots per primitive: slot 0 of an unclipped one, slots 0 .. n-1 of one clipped into n triangles */
+    TriSetup* tris = (TriSetup*)malloc(total * MAX_SUB * sizeof(TriSetup));
+    uint8_t* valid = (uint8_t*)calloc(total * MAX_SUB, 1);
+    uint8_t* fate = (uint8_t*)calloc(ntri, 1); /* 1: clipped, 2: discarded (not finite) */
+    uint8_t* nsub = (uint8_t*)calloc(ntri, 1);
+    if (!tris || !valid || !fate || !nsub) { free(tris); free(valid); free(fate); free(nsub); return KZN_ERROR_OUT_OF_HOST_MEMORY; }
     int threads = kzo_get_threads();
 #pragma omp parallel for num_threads(threads) schedule(static)
     for (int64_t t = 0; t < (int64_t)ntri; ++t) {
@@ -425,14 +536,39 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
             if (vidx < 0) vidx = (int64_t)1 << 40; /* out of range -> robust fetch */
             fetch_vertex(vi, (uint64_t)vidx, &v[k]);
         }
-        valid[t] = (uint8_t)setup_triangle(v, st, vp, &clip, &tris[t]);
+        int cls = classify_triangle(v, vp, &clip);
+        if (cls == 0) {
+            valid[t * MAX_SUB] = (uint8_t)setup_triangle(v, st, vp, &clip, &tris[t * MAX_SUB]);
+        } else if (cls == 1) { /* R3 */
+            float poly[8][8];
+            int m = clip_triangle(v, vp, poly);
+            fate[t] = m < 0 ? 2 : 1;
+            for (int j = 0; j + 2 < m; ++j) {
+                VsOut s3[3];
+                const int src[3] = {0, j + 1, j + 2};
+                for (int k = 0; k < 3; ++k) {
+                    const float* c = poly[src[k]];
+                    s3[k].x = c[0]; s3[k].y = c[1]; s3[k].z = c[2]; s3[k].w = c[3];
+                    memcpy(s3[k].rgba, c + 4, 16);
+                }
+                valid[t * MAX_SUB + j] = (uint8_t)setup_triangle(s3, st, vp, &clip, &tris[t * MAX_SUB + j]);
+                nsub[t]++;
+            }
+        }
     }
     for (uint32_t inst = 1; inst < instance_count; ++inst) { /* no per-instance inputs: instances repeat */
-        memcpy(tris + (uint64_t)inst * ntri, tris, ntri * sizeof(TriSetup));
-        memcpy(valid + (uint64_t)inst * ntri, valid, ntri);
+        memcpy(tris + (uint64_t)inst * ntri * MAX_SUB, tris, ntri * MAX_SUB * sizeof(TriSetup));
+        memcpy(valid + (uint64_t)inst * ntri * MAX_SUB, valid, ntri * MAX_SUB);
     }
-    uint64_t culled = 0;
-    for (uint64_t t = 0; t < total; ++t) culled += !valid[t];
+    uint64_t culled = 0, clipped = 0, clip_out = 0, discarded = 0;
+    for (uint64_t t = 0; t < ntri; ++t) {
+        int any = 0;
+        for (int j = 0; j < MAX_SUB; ++j) any |= valid[t * MAX_SUB + j];
+        culled += (uint64_t)!any * instance_count;
+        clipped += (uint64_t)(fate[t] == 1) * instance_count;
+        discarded += (uint64_t)(fate[t] == 2) * instance_count;
+        clip_out += (uint64_t)nsub[t] * instance_count;
+    }
     /* bands of rows are independent (disjoint pixels); every band walks all triangles in order */
     int32_t band = 8;
     int32_t nb = clip.y1 >= clip.y0 ? (clip.y1 - clip.y0 + band) / band : 0;
@@ -442,7 +578,7 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
         FragCounts fc = {0, 0};
         int32_t r0 = clip.y0 + bnd * band, r1 = r0 + band - 1;
         if (r1 > clip.y1) r1 = clip.y1;
-        raster_rows(st, fb, &clip, tris, valid, total, r0, r1, W, H, &fc);
+        raster_rows(st, fb, &clip, tris, valid, total * MAX_SUB, r0, r1, W, H, &fc);
         covered += fc.covered;
         passed += fc.depth_passed;
     }
@@ -451,9 +587,14 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
         stats->triangles_culled += culled;
         stats->fragments_covered += covered;
         stats->fragments_depth_passed += passed;
+        stats->triangles_clipped += clipped;
+        stats->clip_triangles += clip_out;
+        stats->triangles_discarded += discarded;
     }
     free(tris);
     free(valid);
+    free(fate);
+    free(nsub);
     return KZN_SUCCESS;
 }
 

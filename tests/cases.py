@@ -264,4 +264,84 @@ def draw_scenes() -> list[Scene]:
                         state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND), use_depth=True))
     scenes.append(Scene("mixed_sizes_additive_tiled", 300, 170, np.array(mx[:600], dtype=np.float32) * np.array([1, 1, 1, 0.1, 0.1, 0.1, 0.1], dtype=np.float32),
                         state=pipeline_state(blend=util.ADDITIVE_BLEND), color_tiling=T))
+    scenes += clip_scenes(rng)
+    return scenes
+
+
+def _ground_plane(rng, nx, nz, x_half, z_far, z_behind, height=-1.0):
+    """a jittered grid in the plane y = height of eye space, from z_far in front of the eye to z_behind BEHIND it, in clip
+    coordinates of a perspective projection (w = distance in front of the eye, negative behind it): the rows of quads around
+    z = 0 cross the eye plane.  Returns vertices (x y z w r g b a) and uint32 indices."""
+    near, far = 0.1, 100.0
+    a, b = far / (far - near), -far * near / (far - near)
+    verts = []
+    for j in range(nz + 1):
+        for i in range(nx + 1):
+            X = -x_half + 2 * x_half * i / nx + rng.uniform(-0.2, 0.2) * x_half / nx
+            dist = z_far + (z_behind - z_far) * j / nz + rng.uniform(-0.2, 0.2) * (z_far - z_behind) / nz  # in front of the eye > 0
+            verts.append([1.2 * X, -1.6 * height, a * dist + b, dist, *rng.uniform(0.05, 1.0, 4)])
+    idx = []
+    for j in range(nz):
+        for i in range(nx):
+            v00 = j * (nx + 1) + i
+            idx += [v00, v00 + 1, v00 + nx + 2, v00, v00 + nx + 2, v00 + nx + 1]
+    return np.array(verts, dtype=np.float32), np.array(idx, dtype=np.uint32)
+
+
+def clip_scenes(rng) -> list[Scene]:
+    """R3: triangles that cross the eye plane (w = 0) or leave the guard band are clipped, not dropped."""
+    scenes: list[Scene] = []
+    # a floor under the eye, two triangles (fused direct path), both crossing the eye plane
+    fv, fi = _ground_plane(rng, 1, 1, 4.0, 30.0, -14.0)
+    scenes.append(Scene("clip_floor_quad_eye_plane", 160, 100, fv, fi, pos_comps=4, color_offset=16,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS, 1)), use_depth=True))
+    # the same floor finer: 8 x 12 quads = 192 triangles (direct path with setup_kernel), additive blending shows every
+    # pixel covered twice or not at all along the edges the clipper made
+    fv, fi = _ground_plane(rng, 8, 12, 6.0, 40.0, -8.0)
+    fv[:, 4:] *= 0.25
+    scenes.append(Scene("clip_floor_192_additive", 200, 120, fv, fi, pos_comps=4, color_offset=16,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # 40 x 30 quads = 2400 triangles (binned path), depth + alpha blending, then two instances of it, then one band of it
+    fv, fi = _ground_plane(rng, 40, 30, 8.0, 60.0, -6.0)
+    scenes.append(Scene("clip_floor_2400_depth_blend", 320, 200, fv, fi, pos_comps=4, color_offset=16,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    fa = fv.copy()
+    fa[:, 4:] *= 0.2
+    scenes.append(Scene("clip_floor_2400_instances2_additive_tiled", 320, 200, fa, fi, pos_comps=4, color_offset=16, instances=2,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND), color_tiling=T))
+    scenes.append(Scene("clip_floor_2400_band_96_144", 320, 200, fv, fi, pos_comps=4, color_offset=16, band=(96, 144),
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    # triangles far larger than the guard band (vertices millions of pixels away) around and over the frame: every plane of
+    # the clipper, polygons of up to seven vertices; few triangles (direct) and, padded with a small mesh, many (binned)
+    huge = []
+    for k in range(40):
+        c = rng.uniform(-1.5, 1.5, 2)
+        r = 10.0 ** rng.uniform(3.5, 6.0)
+        ang = rng.uniform(0, 2 * np.pi) + np.array([0.0, 2.1, 4.2]) + rng.uniform(-0.4, 0.4, 3)
+        col = rng.uniform(0.0, 0.2, 4)
+        zz = rng.uniform(0, 1)
+        w = rng.uniform(0.5, 2.0, 3)
+        for j in range(3):
+            x, y = c[0] + r * np.cos(ang[j]) * (1.0 if j else 1e-4), c[1] + r * np.sin(ang[j]) * (1.0 if j else 1e-4)
+            huge.append([x * w[j], y * w[j], zz * w[j], w[j], *col])
+    huge = np.array(huge, dtype=np.float32)
+    scenes.append(Scene("clip_guard_band_huge_40", 192, 128, huge, pos_comps=4, color_offset=16,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    gv, gi = util.grid_mesh(16, 12, 11)
+    g4 = np.concatenate([gv[:, :3], np.ones((len(gv), 1), dtype=np.float32), gv[:, 3:]], axis=1)
+    mixed_v = np.concatenate([g4, huge])
+    mixed_i = np.concatenate([gi[:600], np.arange(len(huge), dtype=np.uint32) + len(g4), gi[600:]])
+    scenes.append(Scene("clip_guard_band_mixed_binned", 192, 128, mixed_v, mixed_i, pos_comps=4, color_offset=16,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND), use_depth=True))
+    # one tile with more triangles than its sorted list holds (every triangle of the draw is walked), clipped ones among them
+    many = []
+    for k in range(4400):
+        x0, y0 = rng.uniform(-1.0, 0.2, 2)
+        col = [0.01, 0.02, 0.03, 0.004]
+        if k % 97 == 5:  # through the eye plane
+            many += [[x0, y0, 0.5, 1.0, *col], [x0 + 0.9, y0 + 0.1, 0.5, 1.0, *col], [-(x0 + 0.2) * 0.5, -(y0 + 0.8) * 0.5, -0.25, -0.5, *col]]
+        else:
+            many += [[x0, y0, 0.5, 1.0, *col], [x0 + 0.9, y0 + 0.1, 0.5, 1.0, *col], [x0 + 0.2, y0 + 0.8, 0.5, 1.0, *col]]
+    scenes.append(Scene("clip_overflow_4400_tris_one_tile", 40, 24, np.array(many, dtype=np.float32), pos_comps=4, color_offset=16,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
     return scenes

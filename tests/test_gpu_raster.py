@@ -28,6 +28,8 @@ def test_draw_matches_oracle(gpu, scene):
     oc, od, os_ = scene.run_oracle()
     gc, gd, gs = scene.run_gpu(gpu)
     assert (gs.triangles_in, gs.triangles_culled) == (os_.triangles_in, os_.triangles_culled)
+    assert (gs.triangles_clipped, gs.clip_triangles, gs.triangles_discarded, gs.clip_overflow) == \
+        (os_.triangles_clipped, os_.clip_triangles, os_.triangles_discarded, 0), "R3: clipped / discarded primitives differ"
     assert (gs.fragments_covered, gs.fragments_depth_passed) == (os_.fragments_covered, os_.fragments_depth_passed), \
         "coverage / depth-test outcome differs (integer path must be bit exact)"
     assert gd.tobytes() == od.tobytes(), "depth buffer differs (must be bit exact)"
@@ -46,6 +48,17 @@ def test_binned_and_overflow_paths_were_exercised(gpu):
     sc = next(s for s in SCENES if s.name == "mesh_200x100_depth_blend")
     _, _, st = sc.run_gpu(gpu)
     assert st.bin_entries > 0 and st.bin_overflow_tiles == 0
+
+
+def test_clipped_primitives_took_every_path(gpu):
+    """R3 on the GPU: the fused direct path (2 triangles), the direct path behind setup_kernel, the binned path with extra
+    records (also under instancing and on a band), and the walk of all triangles for a tile whose list overflowed"""
+    by_name = {s.name: s for s in SCENES}
+    for name in ("clip_floor_quad_eye_plane", "clip_floor_192_additive", "clip_floor_2400_depth_blend", "clip_guard_band_mixed_binned"):
+        _, _, st = by_name[name].run_gpu(gpu)
+        assert st.triangles_clipped > 0 and st.clip_triangles > st.triangles_clipped // 4 and st.clip_overflow == 0, name
+    _, _, st = by_name["clip_overflow_4400_tris_one_tile"].run_gpu(gpu)
+    assert st.bin_overflow_tiles > 0 and st.clip_triangles > 0
 
 
 def test_full_size_fill_4k_properties(gpu):

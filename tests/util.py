@@ -204,7 +204,7 @@ class Scene:
         cbuf = ctx.buffer(color0.nbytes, color0)
         dbuf = ctx.buffer(depth0.nbytes, depth0)
         vbuf = ctx.buffer(self.vertices.nbytes, self.vertices)
-        sbuf = ctx.buffer(64, np.zeros(8, dtype=np.uint64))
+        sbuf = ctx.buffer(C.sizeof(abi.DrawStatistics), np.zeros(C.sizeof(abi.DrawStatistics) // 8, dtype=np.uint64))
         fb = self._framebuffer(cbuf.address, dbuf.address)
         vi = abi.VertexInput(vbuf.address, self.vertices.nbytes, self.stride, 0, self.pos_comps, self.color_offset)
         q = ctx.queue
