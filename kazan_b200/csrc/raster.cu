@@ -66,8 +66,9 @@ constexpr float kClipGuard = 262144.0f;  // 2^18 pixels: where clipped polygons 
 constexpr float kClipW = 9.5367431640625e-07f;  // 2^-20 (R3)
 constexpr uint32_t kFusedMax = 5;        // direct draws of at most this many triangles make their records in the raster kernel (5 x 6 clipped triangles fit 32 slots)
 // work_counter slots: 0, 1 block dispenser of the direct kernel and its leavers; 2 brick dispenser of raster_kernel; 3 records
-// of a direct draw; 4 extra records allocated by this draw's clip_kernel (zeroed again by its sort kernel); 5 their count for
-// raster_kernel; 6 primitives setup_kernel left to clip_kernel (zeroed by the sort kernel)
+// of a direct draw; 4 extra records allocated by this draw's clipper (zeroed again by its sort kernel); 5 their count for
+// raster_kernel; 6 primitives setup_kernel left to the clipper in bin_scan_kernel (zeroed by the sort kernel); 7 CTAs of
+// bin_scan_kernel that are done
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
 constexpr int kDstNone = 0;       // no blending, all channels written: the destination is never read
@@ -121,6 +122,8 @@ struct DrawParams {
     uint32_t first;  // firstIndex / firstVertex
     int32_t vertex_offset;
     uint32_t tris_per_instance, total_tris;
+    uint32_t instances;                         // total_tris / tris_per_instance
+    unsigned long long pos_vertices, col_vertices;  // vertices 0 .. n-1 have their position / colour wholly inside the vertex buffer (robust fetch: the others read zeros)
     // state
     KznGraphicsPipelineState st;
     float hw, hh, ox, oy, dz, zmin_vp;  // viewport transform (R1)
@@ -155,7 +158,7 @@ struct DrawParams {
     uint32_t* clip_bits;    // [tris_per_instance / 32] bit t: primitive t has extra records (zeroed with the tile counters)
     uint32_t* clip_link;    // [tris_per_instance] first extra record k | number of extras << 29; valid where the primitive's bit is set
     uint32_t* clip_parent;  // [clip_capacity] primitive << 3 | fan index j (1..5) of each extra record; ~0u: unused
-    uint32_t* clip_list;    // [tris_per_instance] the primitives setup_kernel left to clip_kernel (work_counter[6] of them)
+    uint32_t* clip_list;    // [tris_per_instance] the primitives setup_kernel left to the clipper (work_counter[6] of them)
     uint32_t clip_capacity;
     unsigned long long descriptor_table;
     unsigned char push_constants[KZN_MAX_PUSH_CONSTANTS_SIZE];
@@ -167,9 +170,8 @@ struct DrawParams {
 __device__ __forceinline__ float4 fetch_color(const DrawParams& p, long long vidx) {
     float4 o = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     if (p.col_off != ~0u) {
-        const unsigned long long off = (unsigned long long)vidx * p.stride;
-        if (vidx >= 0 && off + p.col_off + 16ull <= p.vertex_size) {
-            const float* s = reinterpret_cast<const float*>(p.vertex_base + off + p.col_off);
+        if ((unsigned long long)vidx < p.col_vertices) {
+            const float* s = reinterpret_cast<const float*>(p.vertex_base + (unsigned long long)vidx * p.stride + p.col_off);
             o = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
         } else {
             o.x = o.y = o.z = 0.0f;
@@ -260,9 +262,10 @@ __device__ __forceinline__ bool depth_clip_cannot_reject(const DrawParams& p, fl
 // vertex k of triangle t of an instance: its index into the vertex buffer (negative or huge: out of range)
 __device__ __forceinline__ long long triangle_vertex(const DrawParams& p, uint32_t t, int k) {
     // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
-    unsigned long long rel = 3ull * t + k;
+    unsigned long long rel;
     if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
-    if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
+    else if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
+    else rel = 3ull * t + k;
     unsigned long long i = (unsigned long long)p.first + rel;
     if (p.index_base) {
         unsigned long long raw = p.index_type == KZN_INDEX_TYPE_UINT16
@@ -274,8 +277,7 @@ __device__ __forceinline__ long long triangle_vertex(const DrawParams& p, uint32
 }
 // where its position is, or null: the robust fetch reads (0, 0, 0, 1) out of range
 __device__ __forceinline__ const float* vertex_position(const DrawParams& p, long long vidx) {
-    const unsigned long long off = (unsigned long long)vidx * p.stride;
-    return vidx >= 0 && off + p.pos_off + p.pos_comps * 4ull <= p.vertex_size ? reinterpret_cast<const float*>(p.vertex_base + off + p.pos_off) : nullptr;
+    return (unsigned long long)vidx < p.pos_vertices ? reinterpret_cast<const float*>(p.vertex_base + (unsigned long long)vidx * p.stride + p.pos_off) : nullptr;
 }
 
 // `slow`: the triangle has a vertex behind w = 0 or outside the guard band (or a coordinate that is not finite): it is
@@ -300,8 +302,11 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
             y = __ldg(pos[k] + 1);
             if (p.pos_comps == 4) w = __ldg(pos[k] + 3);
         }
-        if (!(w > 0.0f)) y_ok = false;  // R3
-        const float iw = 1.0f / w;
+        float iw = 1.0f;  // positions without a w component: w = 1, and 1.0f / 1.0f needs no division
+        if (p.pos_comps == 4) {
+            if (!(w > 0.0f)) y_ok = false;  // R3
+            iw = 1.0f / w;
+        }
         const float yf = fmaf(p.hh, y * iw, p.oy);
         if (!finite_f(yf) || !finite_f(iw) || fabsf(yf) > kGuardBand) y_ok = false;
         if (!ROWS_FIRST) {
@@ -554,7 +559,7 @@ __device__ __forceinline__ bool make_record_from(const DrawParams& p, const floa
     return ok;
 }
 
-// A clipped primitive of a binned draw (clip_kernel): the first triangle of its polygon takes the primitive's own record, the
+// A clipped primitive of a binned draw (bin_scan_kernel): the first triangle of its polygon takes the primitive's own record, the
 // others get extra records after the draw's (allocated from work_counter[4]); the tiles they overlap are counted here
 // (setup_kernel counted nothing for the primitive), bin_fill_kernel files them.
 __device__ __forceinline__ void count_tiles(const DrawParams& p, const int4 box, uint32_t n_inst) {
@@ -625,9 +630,9 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     bool slow;
     const bool ok = make_compact(p, t, c, box, slow);
     slow = slow && in_range;
-    const uint32_t n_inst = p.total_tris / p.tris_per_instance;  // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
+    const uint32_t n_inst = p.instances;  // instances repeat the same triangles (no per-instance inputs): record i*tris_per_instance + t
     bool any_fragments = ok;  // some triangle of the (clipped) primitive produces fragments
-    if (BINNED && slow) p.clip_list[atomicAdd(p.work_counter + 6, 1u)] = t;  // R3: clip_kernel does this one (nothing is counted for it here)
+    if (BINNED && slow) p.clip_list[atomicAdd(p.work_counter + 6, 1u)] = t;  // R3: bin_scan_kernel clips this one (nothing is counted for it here)
     if (!BINNED) {
         // direct draws (one CTA): a clipped primitive takes as many consecutive records as its polygon has triangles, so the
         // records are placed by a prefix sum over the CTA whenever any primitive was clipped
@@ -708,7 +713,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         }
     }
     if (in_range) {
-        for (uint32_t inst = 0; inst < n_inst; ++inst) p.boxes[(size_t)inst * p.tris_per_instance + t] = pack_box(box);
+        p.boxes[t] = pack_box(box);
+        for (uint32_t inst = 1; inst < n_inst; ++inst) p.boxes[(size_t)inst * p.tris_per_instance + t] = pack_box(box);
         if (p.stats) {
             atomicAdd(&p.stats[0], (unsigned long long)n_inst);
             if (!any_fragments && !(BINNED && slow)) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
@@ -720,16 +726,6 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
-
-#ifndef KZN_FS_TEMPLATE
-// The primitives setup_kernel<true> found crossing the eye plane or the guard band (work_counter[6] of them, usually none):
-// one thread each.
-__global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ DrawParams p) {
-    kzn_pdl_wait();
-    const uint32_t n = p.work_counter[6], n_inst = p.total_tris / p.tris_per_instance;
-    for (uint32_t i = blockIdx.x * 128u + threadIdx.x; i < n; i += gridDim.x * 128u) clip_binned(p, p.clip_list[i], n_inst);
-}
-#endif
 
 // ---- binning --------------------------------------------------------------------------------------------------
 
@@ -749,7 +745,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
         const uint32_t parent = p.clip_parent[k];
         if (parent == 0xffffffffu) continue;
         if (!tile_range(p, unpack_box(p.boxes[p.total_tris + k]), tx0, tx1, ty0, ty1)) continue;
-        const uint32_t n_inst = p.total_tris / p.tris_per_instance;
+        const uint32_t n_inst = p.instances;
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const uint32_t tile = (uint32_t)ty * p.tiles_x + (uint32_t)tx;
@@ -761,17 +757,33 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
     }
 }
 
-// exclusive scan of tile_counts -> tile_offsets[0..tiles], single CTA (tiles <= a few hundred thousand)
+// Between the two binning passes: (1) the primitives setup_kernel<true> found crossing the eye plane or the guard band
+// (work_counter[6] of them, usually none) are clipped, one thread each over the whole grid; (2) the last CTA to finish that
+// makes the exclusive scan of tile_counts -> tile_offsets[0..tiles] (tiles <= a few hundred thousand).
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
+    __shared__ uint32_t last_cta;
+    const uint32_t n_slow = p.work_counter[6];
+    for (uint32_t i = blockIdx.x * 1024u + threadIdx.x; i < n_slow; i += gridDim.x * 1024u) clip_binned(p, p.clip_list[i], p.instances);
+    if (gridDim.x > 1) {
+        __threadfence();  // my counts and records before my ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            last_cta = atomicAdd(p.work_counter + 7, 1u) == gridDim.x - 1u;
+            if (last_cta) p.work_counter[7] = 0u;  // for the next draw
+        }
+        __syncthreads();
+        if (!last_cta) return;
+        __threadfence();
+    }
     uint32_t tiles = p.tiles_x * p.tiles_y;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (uint32_t base = 0; base < tiles; base += 1024) {
         uint32_t i = base + threadIdx.x;
-        uint32_t v = i < tiles ? p.tile_counts[i] : 0;
+        uint32_t v = i < tiles ? __ldcg(&p.tile_counts[i]) : 0;
         uint32_t x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -2587,6 +2599,15 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     p.vertex_offset = vertex_offset;
     p.tris_per_instance = (uint32_t)ntri;
     p.total_tris = (uint32_t)total;
+    p.instances = instance_count;
+    {   // robust fetch as one comparison: vertex v is fetched iff v * stride + offset + bytes <= size
+        auto whole = [&](uint64_t offset, uint64_t bytes) -> unsigned long long {
+            if (offset + bytes > vi->buffer_size) return 0ull;
+            return vi->stride ? (vi->buffer_size - offset - bytes) / vi->stride + 1ull : 1ull << 63;  // (a negative index, as unsigned, is never below it)
+        };
+        p.pos_vertices = whole(vi->position_offset, vi->position_components * 4ull);
+        p.col_vertices = vi->color_offset != ~0u ? whole(vi->color_offset, 16ull) : 0ull;
+    }
     p.st = *st;
     p.hw = vp->width * 0.5f;
     p.hh = vp->height * 0.5f;
@@ -2660,12 +2681,10 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         if ((r = kzn_launched(q, "setup_kernel"))) return r;
     }
     if (p.binned) {
-        {   // R3: the primitives setup left to the clipper (usually none: the kernel reads one counter)
-            const uint64_t blocks = (ntri + 127) / 128, cap = (uint64_t)q->device->sm_count * 8;
-            launch_draw_kernel(clip_kernel, dim3((uint32_t)(blocks < cap ? blocks : cap)), dim3(128), 0, q->stream, p);
-            if ((r = kzn_launched(q, "clip_kernel"))) return r;
+        {   // (as many CTAs as could have work if every primitive needed clipping; usually none does and the last one scans)
+            const uint64_t blocks = (ntri + 1023) / 1024, cap = (uint64_t)q->device->sm_count;
+            launch_draw_kernel(bin_scan_kernel, dim3((uint32_t)(blocks < cap ? blocks : cap)), dim3(1024), 0, q->stream, p);
         }
-        launch_draw_kernel(bin_scan_kernel, dim3(1), dim3(1024), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
         launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
