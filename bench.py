@@ -238,6 +238,38 @@ def transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak):
     return out
 
 
+def present_extra(torch, abi, host, dev, queue, stream):
+    """vkQueuePresentKHR at 4K: a rendered image into its X11 shared memory segment, for windows of
+    either byte order.  The bound is the PCIe link (what e2e's frame download also rides on), not HBM."""
+    W, H = 3840, 2160
+    out = {"frame": [W, H], "bound": "pcie", "note": "image in HBM -> SysV segment registered with CUDA; R8G8B8A8 windows: copy engine, B8G8R8A8 windows: "
+           "byte-swapping kernel storing into the mapped segment; timed from the present call to the segment holding the frame"}
+    frame = torch.randint(0, 2**31 - 1, (W * H,), dtype=torch.int32, device="cuda")
+    for name, order in (("b8g8r8a8_window", abi.WINDOW_B8G8R8A8), ("r8g8b8a8_window", abi.WINDOW_R8G8B8A8)):
+        sc = host.Swapchain(dev, W, H, image_count=3, window_byte_order=order)
+        images = [sc.image(i) for i in range(3)]
+        for im in images:
+            queue.cmd_copy_buffer(frame.data_ptr(), frame.numel() * 4, im.address, frame.numel() * 4, [abi.BufferCopy(0, 0, frame.numel() * 4)])
+        queue.wait_idle()
+        best = None
+        for rep in range(6):
+            idx = sc.acquire_next_image()
+            t0 = time.perf_counter()
+            queue.present(sc, idx)
+            sc.wait_presented(idx)
+            dt = time.perf_counter() - t0
+            if rep >= 2:
+                best = dt if best is None else min(best, dt)
+        seg = sc.segment(idx)
+        got = np.ctypeslib.as_array((C.c_uint32 * (W * H)).from_address(seg.mapped))
+        want = frame.cpu().numpy().view(np.uint32)
+        if order == abi.WINDOW_B8G8R8A8:
+            want = (want & 0xFF00FF00) | ((want & 0xFF) << 16) | ((want >> 16) & 0xFF)
+        out[name] = {"ms": best * 1e3, "GBps": W * H * 4 / best / 1e9, "frame_matches": bool(np.array_equal(got, want))}
+        sc.destroy()
+    return out
+
+
 def grid_mesh(quads_x, quads_y, seed):
     """Jittered grid mesh of SURVEY.md §8d config #4 (same numbers as oracle/raster.c kzo_make_grid_mesh, restated in
     numpy so that the bench does not call the oracle for its inputs): vertex = x,y,z,r,g,b,a f32; u32 indices."""
@@ -903,7 +935,8 @@ def run_ours(args):
             line["extra"] = {"transfer": transfer_extra(torch, abi, host, dev, queue, stream, hbm_peak),
                              "hbm_peak_GBps": hbm_peak, "hbm_peak_source": peak_src,
                              "dispatch_2p24": dispatch_extra(torch, queue, stream),
-                             "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream, hbm_peak=hbm_peak)}
+                             "mesh_1M_1080p": mesh_extra(torch, abi, host, queue, stream, hbm_peak=hbm_peak),
+                             "present_4k": present_extra(torch, abi, host, dev, queue, stream)}
     if not args.profile:
         with torch.cuda.stream(stream):
             ft.close()

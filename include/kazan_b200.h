@@ -471,6 +471,44 @@ KZN_API uint64_t kzn_split_frame_present_address(const KznSplitFrame* split_fram
 KZN_API KznQueue* kzn_split_frame_present_queue(const KznSplitFrame* split_frame);  /* ordered after every composite */
 KZN_API KznResult kzn_split_frame_wait_idle(KznSplitFrame* split_frame);
 
+/* ------------------------------------------------------------------------------------------ */
+/* WSI presentation, data path                                            */
+/* The reference prepares swapchains over X11 MIT-SHM (vulkan-driver/src/xcb_swapchain.rs:117-136,258-340: 32-bit pixmaps in
+ * R8G8B8A8 or B8G8R8A8 byte order, scanline_pad, 2..16 images; SysV segments shm.rs:22-58) and leaves XcbSwapchain::new,
+ * vkGetSwapchainImagesKHR, vkAcquireNextImageKHR and vkQueuePresentKHR unimplemented (xcb_swapchain.rs:342-349,
+ * api_impl.rs:5656-5682).  A KznSwapchain is their GPU side: `image_count` presentable images (LINEAR R8G8B8A8_UNORM, in HBM:
+ * colour attachments / transfer destinations like any image) and one SysV shared memory segment per image, created as
+ * shm.rs does (shmget IPC_PRIVATE, IPC_CREAT | IPC_EXCL | 0666) and registered with CUDA.  kzn_queue_present, ordered after
+ * the queue's earlier work, writes the image into its segment in the window's byte order with the window's scanline pitch
+ * (copy engine when the orders agree, a byte-swapping kernel storing straight into the segment otherwise);
+ * kzn_swapchain_wait_presented returns when the segment holds the frame — the point at which the host calls
+ * xcb_shm_put_image(shmseg of that segment).  Images are acquired in order; an image whose previous present is still being
+ * written is waited for (or VK_NOT_READY with timeout 0).  The xcb calls stay in the host. */
+typedef struct KznSwapchain KznSwapchain;
+#define KZN_MAX_SWAPCHAIN_IMAGES 16u /* xcb_swapchain.rs:136 MAX_SWAPCHAIN_IMAGE_COUNT */
+#define KZN_WINDOW_R8G8B8A8 0u       /* SurfaceFormatGroup::R8G8B8A8 (xcb_swapchain.rs:117-118) */
+#define KZN_WINDOW_B8G8R8A8 1u       /* SurfaceFormatGroup::B8G8R8A8 */
+typedef struct KznSwapchainCreateInfo {
+    uint32_t width, height;      /* VkSwapchainCreateInfoKHR::imageExtent = the window's size (xcb_swapchain.rs:309-311) */
+    uint32_t image_count;        /* minImageCount, 2 .. KZN_MAX_SWAPCHAIN_IMAGES */
+    uint32_t window_byte_order;  /* KZN_WINDOW_* from the window's pixmap format */
+    uint32_t scanline_alignment; /* bytes: scanline_pad / 8 = 1, 2 or 4 (xcb_swapchain.rs:290-295) */
+    uint32_t reserved;
+} KznSwapchainCreateInfo;
+typedef struct KznSwapchainSegment {
+    int32_t shm_id;          /* SysV id: xcb_shm_attach(connection, shmseg, shm_id, read_only = 1) */
+    uint32_t bytes_per_line; /* width * 4 rounded up to scanline_alignment */
+    uint64_t size;           /* bytes_per_line * height */
+    void* mapped;            /* the segment attached in this process */
+} KznSwapchainSegment;
+KZN_API KznResult kzn_swapchain_create(KznDevice* device, const KznSwapchainCreateInfo* info, KznSwapchain** swapchain);
+KZN_API void kzn_swapchain_destroy(KznSwapchain* swapchain); /* waits for presents in flight; removes the segments */
+KZN_API KznResult kzn_swapchain_get_image(const KznSwapchain* swapchain, uint32_t index, KznImageDesc* image);         /* vkGetSwapchainImagesKHR */
+KZN_API KznResult kzn_swapchain_get_segment(const KznSwapchain* swapchain, uint32_t index, KznSwapchainSegment* segment);
+KZN_API KznResult kzn_swapchain_acquire_next_image(KznSwapchain* swapchain, uint64_t timeout_ns, uint32_t* index);      /* vkAcquireNextImageKHR */
+KZN_API KznResult kzn_queue_present(KznQueue* queue, KznSwapchain* swapchain, uint32_t index);                          /* vkQueuePresentKHR */
+KZN_API KznResult kzn_swapchain_wait_presented(KznSwapchain* swapchain, uint32_t index);
+
 /* where (device address of a KznDrawStatistics, zeroed by the caller) the next draws accumulate
  * counters; 0 disables */
 KZN_API KznResult kzn_queue_set_draw_statistics(KznQueue* queue, uint64_t stats_address);

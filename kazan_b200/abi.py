@@ -167,6 +167,18 @@ class DrawStatistics(C.Structure):
         "clip_overflow")]
 
 
+class SwapchainCreateInfo(C.Structure):  # KznSwapchainCreateInfo
+    _fields_ = [("width", u32), ("height", u32), ("image_count", u32), ("window_byte_order", u32), ("scanline_alignment", u32),
+                ("reserved", u32)]
+
+
+class SwapchainSegment(C.Structure):  # KznSwapchainSegment
+    _fields_ = [("shm_id", i32), ("bytes_per_line", u32), ("size", u64), ("mapped", C.c_void_p)]
+
+
+WINDOW_R8G8B8A8, WINDOW_B8G8R8A8 = 0, 1
+MAX_SWAPCHAIN_IMAGES = 16
+
 P = C.POINTER
 vp = C.c_void_p
 
@@ -249,6 +261,13 @@ PROTOTYPES = {
     "kzn_split_frame_present_address": (u64, [vp]),
     "kzn_split_frame_present_queue": (vp, [vp]),
     "kzn_split_frame_wait_idle": (i32, [vp]),
+    "kzn_swapchain_create": (i32, [vp, P(SwapchainCreateInfo), P(vp)]),
+    "kzn_swapchain_destroy": (None, [vp]),
+    "kzn_swapchain_get_image": (i32, [vp, u32, P(ImageDesc)]),
+    "kzn_swapchain_get_segment": (i32, [vp, u32, P(SwapchainSegment)]),
+    "kzn_swapchain_acquire_next_image": (i32, [vp, u64, P(u32)]),
+    "kzn_queue_present": (i32, [vp, vp, u32]),
+    "kzn_swapchain_wait_presented": (i32, [vp, u32]),
 }
 
 

@@ -229,6 +229,43 @@ class CommandBuffer:
             self.handle = C.c_void_p()
 
 
+class Swapchain:
+    """VkSwapchainKHR, GPU side (include/kazan_b200.h "WSI presentation"): presentable images in HBM, one SysV shared memory
+    segment per image for xcb_shm_put_image."""
+
+    def __init__(self, device: "Device", width: int, height: int, image_count: int = 2, window_byte_order: int = abi.WINDOW_B8G8R8A8,
+                 scanline_alignment: int = 4):
+        self.device, self._lib = device, device._lib
+        info = abi.SwapchainCreateInfo(width, height, image_count, window_byte_order, scanline_alignment, 0)
+        self.handle = C.c_void_p()
+        _check(self._lib.kzn_swapchain_create(device.handle, C.byref(info), C.byref(self.handle)))
+        self.width, self.height, self.image_count = width, height, image_count
+
+    def image(self, index: int) -> "Image":
+        d = abi.ImageDesc()
+        _check(self._lib.kzn_swapchain_get_image(self.handle, index, C.byref(d)))
+        return Image(d.address, d.width, d.height, d.depth, d.array_layers, d.format, d.tiling, d.mip_levels)
+
+    def segment(self, index: int) -> abi.SwapchainSegment:
+        s = abi.SwapchainSegment()
+        _check(self._lib.kzn_swapchain_get_segment(self.handle, index, C.byref(s)))
+        return s
+
+    def acquire_next_image(self, timeout_ns: int = 2**64 - 1) -> int:
+        """index of the acquired image; raises KazanError on errors, returns -1 for VK_NOT_READY / VK_TIMEOUT"""
+        idx = C.c_uint32()
+        code = _check(self._lib.kzn_swapchain_acquire_next_image(self.handle, timeout_ns, C.byref(idx)))
+        return idx.value if code == 0 else -1
+
+    def wait_presented(self, index: int):
+        _check(self._lib.kzn_swapchain_wait_presented(self.handle, index))
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_swapchain_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class Queue:
     """One VkQueue == one CUDA stream.  Method names follow the Vulkan commands they implement."""
 
@@ -254,6 +291,10 @@ class Queue:
     def submit(self, command_buffers, fence: "Fence | None" = None):
         arr = (C.c_void_p * max(len(command_buffers), 1))(*[cb.handle.value for cb in command_buffers])
         _check(self._lib.kzn_queue_submit(self.handle, len(command_buffers), arr, fence.handle if fence else None))
+
+    def present(self, swapchain: Swapchain, index: int):
+        """vkQueuePresentKHR: after the queue's earlier work, the image goes into its shared memory segment"""
+        _check(self._lib.kzn_queue_present(self.handle, swapchain.handle, index))
 
     def reserve_draw(self, max_triangles: int, width: int, height: int):
         _check(self._lib.kzn_queue_reserve_draw(self.handle, max_triangles, width, height))
