@@ -585,13 +585,27 @@ def split_frame_extra(torch, dist, abi, host, dev, queue, stream, world, rank, b
         queue.cmd_draw_indexed(st, fbs[i], vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
         ft.end()
 
-    reps = 10
-    ms = time_region(torch, stream, frame, reps, 3, barrier) / reps
+    reps = 20
+    ms = time_region(torch, stream, frame, reps, 4, barrier) / reps
+    per_rank = [ms]
     if world > 1:
         t = torch.tensor([ms], device="cuda")
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank = [float(e.item()) for e in every]
+        ms = max(per_rank)
+    # the band's draws alone on this rank (no composite, no other rank to wait for): what the frame would take if the exchange were free
+    def band_only(k):
+        queue.cmd_clear_attachment(cimgs[0], (0, 0, 0, 0), band)
+        queue.cmd_clear_attachment(dimg, (1.0, 0, 0, 0), band)
+        queue.cmd_draw_indexed(st, fbs[0], vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+    ft.wait_idle(queue)
+    ms_band = time_region(torch, stream, band_only, reps, 3, barrier) / reps
+    if world > 1:
+        t = torch.tensor([ms_band], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    out = {"frame": [W, H], "triangles": ntri, "bands": world, "ms_per_frame": ms, "Gpix_per_s": W * H / ms / 1e6, "Mtri_per_s": ntri / ms / 1e3,
+        ms_band = float(t.item())
+    out = {"frame": [W, H], "triangles": ntri, "bands": world, "ms_per_frame": ms, "ms_per_frame_by_rank": per_rank, "ms_band_draws_alone": ms_band, "Gpix_per_s": W * H / ms / 1e6, "Mtri_per_s": ntri / ms / 1e3,
             "composite_bytes": sf.composite_bytes(), "scaling": "strong", "composite": ft.mode}
     if rank == 0:  # checksum of the assembled frame (the same number whatever the band count)
         last = (ft.frames - 1) % ft.n

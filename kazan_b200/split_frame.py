@@ -92,8 +92,10 @@ class PeerSplitFrame:
               stores back-pressure the raster kernels (measured: profiles/).
     Per frame:
         band rank : [wait credit] -> draw band -> (push) -> signal ITS `arrived` flag (+1, after a system-scope fence)
-        presenter : draw own band -> wait until EVERY band rank's `arrived` flag >= frames -> frame complete -> signal each
-                    rank's `credit`
+        presenter : draw own band; on its PRESENT queue: wait for that draw and until EVERY band rank's `arrived` flag >= frames
+                    -> frame complete -> signal each rank's `credit`.  Its render queue goes on with the next frame meanwhile
+                    (another target) and only waits for "frame complete" of the frame that used the same target, so the
+                    presenter's SMs never idle while the other ranks' bands are on the wire.
     (One arrival flag per band rank: with one aggregated counter a rank running a frame ahead would be counted for a rank
     that is a frame behind, and the presenter would declare a frame complete with a band missing.)
     `credit` bounds how far a band rank may run ahead of the presenter (the number of rotating targets), so a target is
@@ -127,6 +129,11 @@ class PeerSplitFrame:
             for t in self.targets:
                 queue.cmd_fill_buffer(t.address, self.frame_bytes, 0, self.frame_bytes, 0)
         self.copy_queue, self.local, self.rendered, self.copied = None, [], [], []
+        self.present_queue, self.completed = None, []
+        if is_presenter and world > 1:
+            self.present_queue = device.create_queue()
+            self.rendered = [Semaphore(device) for _ in range(n_targets)]
+            self.completed = [Semaphore(device) for _ in range(n_targets)]
         if not is_presenter and mode == "push":
             self.copy_queue = device.create_queue()
             self.local = [device.allocate(self.frame_bytes) for _ in range(self.LOCAL_IMAGES)]
@@ -189,6 +196,8 @@ class PeerSplitFrame:
         if self.rank != self.presenter and f >= self.n_targets:
             # do not start frame f before the presenter has completed frame f - n_targets
             self.queue.cmd_wait_flag(self.flags.address, f - self.n_targets + 1, self.status_address)
+        if self.present_queue and f >= self.n_targets:
+            self.queue.wait_semaphore(self.completed[f % self.n_targets])  # the frame that used this target is complete
         return self.target(f)
 
     def end_frame(self):
@@ -198,9 +207,13 @@ class PeerSplitFrame:
         if self.world == 1:
             return
         if self.rank == self.presenter:
-            self.queue.cmd_wait_flags(self.arrived_address, self.world - 1, self.frames, self.status_address)
+            slot, pq = f % self.n_targets, self.present_queue
+            self.queue.signal_semaphore(self.rendered[slot])
+            pq.wait_semaphore(self.rendered[slot])
+            pq.cmd_wait_flags(self.arrived_address, self.world - 1, self.frames, self.status_address)
             for addr in self.credit_addresses.values():
-                self.queue.cmd_signal_flag(addr, 1)
+                pq.cmd_signal_flag(addr, 1)
+            pq.signal_semaphore(self.completed[slot])
         elif self.pushes:
             slot = f % self.LOCAL_IMAGES
             a, b = self.split.byte_range(self.rank)
@@ -219,6 +232,8 @@ class PeerSplitFrame:
         self.queue.wait_idle()
         if self.copy_queue:
             self.copy_queue.wait_idle()
+        if self.present_queue:
+            self.present_queue.wait_idle()
 
     def check(self):
         """Raise if any wait on this rank gave up (a peer stopped making progress)."""
@@ -240,8 +255,11 @@ class PeerSplitFrame:
             self.dist.barrier()
         for m in self._owned:
             m.free()
-        for sem in self.rendered + self.copied:
+        for sem in self.rendered + self.copied + self.completed:
             sem.destroy()
         if self.copy_queue:
             self.copy_queue.destroy()
+        if self.present_queue:
+            self.present_queue.destroy()
         self._imported, self._owned, self.rendered, self.copied, self.copy_queue = [], [], [], [], None
+        self.completed, self.present_queue = [], None
