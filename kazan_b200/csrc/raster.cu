@@ -124,6 +124,7 @@ struct DrawParams {
     uint32_t tris_per_instance, total_tris;
     uint32_t instances;                         // total_tris / tris_per_instance
     unsigned long long pos_vertices, col_vertices;  // vertices 0 .. n-1 have their position / colour wholly inside the vertex buffer (robust fetch: the others read zeros)
+    const float* null_vertex;                       // (0, 0, 0, 1) in device memory: what an out-of-range position reads
     // state
     KznGraphicsPipelineState st;
     float hw, hh, ox, oy, dz, zmin_vp;  // viewport transform (R1)
@@ -275,9 +276,10 @@ __device__ __forceinline__ long long triangle_vertex(const DrawParams& p, uint32
     }
     return (long long)i;
 }
-// where its position is, or null: the robust fetch reads (0, 0, 0, 1) out of range
+// where its position is: the robust fetch reads (0, 0, 0, 1) out of range, from a vertex of those values in the scratch
+// (p.null_vertex), so that fetching needs no branch
 __device__ __forceinline__ const float* vertex_position(const DrawParams& p, long long vidx) {
-    return (unsigned long long)vidx < p.pos_vertices ? reinterpret_cast<const float*>(p.vertex_base + (unsigned long long)vidx * p.stride + p.pos_off) : nullptr;
+    return (unsigned long long)vidx < p.pos_vertices ? reinterpret_cast<const float*>(p.vertex_base + (unsigned long long)vidx * p.stride + p.pos_off) : p.null_vertex;
 }
 
 // `slow`: the triangle has a vertex behind w = 0 or outside the guard band (or a coordinate that is not finite): it is
@@ -293,26 +295,24 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
     for (int k = 0; k < 3; ++k) {
         vidx[k] = triangle_vertex(p, t, k);
         pos[k] = vertex_position(p, vidx[k]);
-        float x = 0.0f, y = 0.0f, z = 0.0f, w = 1.0f;
-        if (pos[k]) {
-            if (!ROWS_FIRST) {
-                x = __ldg(pos[k]);
-                z = __ldg(pos[k] + 2);
-            }
-            y = __ldg(pos[k] + 1);
-            if (p.pos_comps == 4) w = __ldg(pos[k] + 3);
+        float x = 0.0f, z = 0.0f;
+        if (!ROWS_FIRST) {
+            x = __ldg(pos[k]);
+            z = __ldg(pos[k] + 2);
         }
+        const float y = __ldg(pos[k] + 1);
         float iw = 1.0f;  // positions without a w component: w = 1, and 1.0f / 1.0f needs no division
         if (p.pos_comps == 4) {
-            if (!(w > 0.0f)) y_ok = false;  // R3
+            const float w = __ldg(pos[k] + 3);
             iw = 1.0f / w;
+            if (!(w > 0.0f) || !finite_f(iw)) y_ok = false;  // R3
         }
         const float yf = fmaf(p.hh, y * iw, p.oy);
-        if (!finite_f(yf) || !finite_f(iw) || fabsf(yf) > kGuardBand) y_ok = false;
+        if (!(fabsf(yf) <= kGuardBand)) y_ok = false;  // (false for NaN and infinity too)
         if (!ROWS_FIRST) {
             const float xf = fmaf(p.hw, x * iw, p.ox);
             const float zf = fmaf(p.dz, z * iw, p.zmin_vp);
-            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) x_ok = false;
+            if (!(fabsf(xf) <= kGuardBand) || !finite_f(zf)) x_ok = false;
             r.X[k] = y_ok && x_ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
             r.z[k] = zf;
         }
@@ -335,14 +335,10 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            float x = 0.0f, z = 0.0f;
-            if (pos[k]) {
-                x = __ldg(pos[k]);
-                z = __ldg(pos[k] + 2);
-            }
+            const float x = __ldg(pos[k]), z = __ldg(pos[k] + 2);
             const float xf = fmaf(p.hw, x * r.iw[k], p.ox);
             const float zf = fmaf(p.dz, z * r.iw[k], p.zmin_vp);
-            if (!finite_f(xf) || !finite_f(zf) || fabsf(xf) > kGuardBand) x_ok = false;
+            if (!(fabsf(xf) <= kGuardBand) || !finite_f(zf)) x_ok = false;
             r.X[k] = x_ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
             r.z[k] = zf;
         }
@@ -403,13 +399,7 @@ __device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, f
     for (int k = 0; k < 3; ++k) {
         const long long vidx = triangle_vertex(p, t, k);
         const float* pos = vertex_position(p, vidx);
-        float x = 0.0f, y = 0.0f, z = 0.0f, w = 1.0f;
-        if (pos) {
-            x = __ldg(pos);
-            y = __ldg(pos + 1);
-            z = __ldg(pos + 2);
-            if (p.pos_comps == 4) w = __ldg(pos + 3);
-        }
+        const float x = __ldg(pos), y = __ldg(pos + 1), z = __ldg(pos + 2), w = p.pos_comps == 4 ? __ldg(pos + 3) : 1.0f;
         if (!finite_f(x) || !finite_f(y) || !finite_f(z) || !finite_f(w)) return -1;
         const float4 c = fetch_color(p, vidx);
         src[k][0] = x; src[k][1] = y; src[k][2] = z; src[k][3] = w;
@@ -723,7 +713,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     if (BINNED) {  // first binning pass fused here: count the tiles each triangle overlaps
         int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
         bool valid = in_range && tile_range(p, box, tx0, tx1, ty0, ty1);
-        bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
+        if (__any_sync(0xffffffffu, valid)) bin_emit<false>(p, valid, t, n_inst, tx0, tx1, ty0, ty1);
     }
 }
 
@@ -2523,8 +2513,10 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t per_instance, size_t 
         if ((r = grow(q, &s->clip_list, &s->list_capacity, per_instance))) return r;
     }
     if (!s->counters) {  // the dispensers and the allocator of extra records start at zero and are handed back at zero by their users
-        if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)8))) return r;
+        if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)32))) return r;
         KZN_CUDA(cudaMemsetAsync(s->counters, 0, s->counter_capacity * sizeof(uint32_t), q->stream));  // ordered before the first draw kernel of this queue
+        static const float one = 1.0f;  // words 16..19: the vertex (0, 0, 0, 1) out-of-range positions read
+        KZN_CUDA(cudaMemcpyAsync(s->counters + 19, &one, sizeof one, cudaMemcpyHostToDevice, q->stream));
     }
     if (binned) {
         if ((r = grow(q, &s->tile_words, &s->tile_capacity, 3 * tiles + 1 + (per_instance + 31) / 32))) return r;
@@ -2651,6 +2643,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     p.tris = s->tris;
     p.boxes = s->boxes;
     p.work_counter = s->counters;
+    p.null_vertex = reinterpret_cast<const float*>(s->counters + 16);
     {
         static const bool exact = [] {
             const char* e = getenv("KZN_RASTER_EXACT_SPANS");

@@ -18,7 +18,12 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rast
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_mesh.csv python tools/prof_mesh.py > $OUT/ncu_mesh.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|setup_kernel|bin_' -s 4 -c 4 -f -o $OUT/prof_mesh python tools/prof_mesh.py > $OUT/ncu_mesh_full.log 2>&1
 # transfer kernels: full capture
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fill_|copy_bulk|box_kernel|merged_transfer' -c 16 -f -o $OUT/prof_transfer python tools/prof_transfer.py > $OUT/ncu_transfer_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fill_|copy_bulk|copy_realign|box_kernel|blit_kernel|merged_transfer' -c 28 -f -o $OUT/prof_transfer python tools/prof_transfer.py > $OUT/ncu_transfer_full.log 2>&1
 # the 8K / 4M-triangle frame: launch list
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches_8k.csv python tools/prof_8k.py > $OUT/ncu_8k.log 2>&1
+# one band (1/8 of the rows) of the same frame: what each rank of an 8-GPU split frame runs
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches_8k_band.csv python tools/prof_8k_band.py > $OUT/ncu_8k_band.log 2>&1
+# DRAM traffic of every kernel of the two mesh frames (roofline.traffic of extra.mesh_1M_1080p / split_frame_8k)
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 14 --csv --log-file $OUT/traffic_mesh.csv python tools/prof_mesh.py > $OUT/ncu_traffic_mesh.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 14 --csv --log-file $OUT/traffic_8k.csv python tools/prof_8k.py > $OUT/ncu_traffic_8k.log 2>&1
 ls -la $OUT
