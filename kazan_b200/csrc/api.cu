@@ -98,6 +98,18 @@ KznResult kzn_device_create(int32_t ordinal, KznDevice** device) {
         delete d;
         return KZN_ERROR_INITIALIZATION_FAILED;
     }
+    {   // KZN_L2_PERSIST=1: L2 lines set aside for the triangle records of binned draws between setup and raster (raster.cu
+        // draw_common).  Off by default: measured on B200 it takes a third off the DRAM traffic of the 1M-triangle frame
+        // (270 -> 180 MB) without making it faster (the draw is issue-bound), and the set-aside costs every other kernel L2
+        // (the 4M-triangle frame: 2.10 -> 2.25 ms).
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ordinal);
+        cudaDeviceGetAttribute(&d->l2_window_bytes, cudaDevAttrMaxAccessPolicyWindowSize, ordinal);
+        const char* e = getenv("KZN_L2_PERSIST");
+        if (!(e && e[0] == '1')) max_persist = 0;
+        if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) d->l2_persist_bytes = max_persist;
+        cudaGetLastError();
+    }
     *device = d;
     return KZN_SUCCESS;
 }

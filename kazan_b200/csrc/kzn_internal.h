@@ -11,6 +11,8 @@ struct KznDevice {
     int sm_count;
     int l2_bytes;
     int cc_major, cc_minor;
+    int l2_persist_bytes;   // cudaLimitPersistingL2CacheSize as set at creation (0: no persisting lines)
+    int l2_window_bytes;    // cudaDevAttrMaxAccessPolicyWindowSize
 };
 
 struct KznRasterScratch;  // raster.cu
