@@ -357,6 +357,9 @@ KZN_API KznResult kzn_cmd_convert_tiling(KznQueue* queue, const KznImageDesc* sr
  * programmable stages are selected from built-in programs defined by the oracle (oracle/raster.c).  Compute entry
  * points go through the PTX back end (kazan_b200_backend.h). */
 #define KZN_VS_PASSTHROUGH 0u      /* gl_Position = vec4(pos.xyz, pos.w or 1); colour passed through */
+/* The vertex program bound with kzn_cmd_bind_vertex_program (kazan_b200_backend.h): a vertex shader in shader-compiler-ir
+ * (for instance the translation of a SPIR-V module) run by the PTX back end, one invocation per vertex, before setup. */
+#define KZN_VS_COMPILED 1u
 #define KZN_FS_VERTEX_COLOR 0u     /* out = perspective-correct interpolated vertex rgba */
 #define KZN_FS_PROCEDURAL_ORBIT 1u /* the fill-rate shader of BASELINE.json configs[2] (fp32 fma orbit, K=32) */
 #define KZN_FS_ORBIT_ITERATIONS 32u

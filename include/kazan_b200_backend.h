@@ -151,6 +151,24 @@ KZN_API KznResult kzn_fragment_program_ptx(const KznIrModule* module, char** ptx
 /* ... and of the whole module kzn_fragment_program_create loads: the raster kernels with the shader at every call site */
 KZN_API KznResult kzn_fragment_program_module_ptx(const KznIrModule* module, char** ptx, size_t* length);
 
+/* ---- vertex programs: the vertex stage of a graphics pipeline ---------------------------------------------------------------- */
+/* vkCreateGraphicsPipelines api_impl.rs:4018-4032 (vertex stage of GraphicsPipeline::create, pipeline.rs:167-183, unimplemented!()
+ * upstream).  The module is a vertex shader in version 2 of the IR — what kzn_translate_spirv_to_ir_ex makes of a SPIR-V
+ * vertex shader: user_inputs_block = the attributes of the vertex binding in the shader's Location layout (16 bytes per
+ * location; the binding's stride must equal the block's size), a built-in output of kind vertex_position (four f32), and
+ * optionally user output location 0 = four f32, the colour the fragment stage interpolates (white without it).  A draw whose
+ * state says vertex_program == KZN_VS_COMPILED runs the program bound to the queue as a dispatch of the PTX back end over the
+ * vertices the draw can name (vertices first_vertex .. + vertex_count of a non-indexed draw, every whole vertex of the
+ * binding for an indexed one) into the queue's vertex scratch, and rasterises from there; push constants and descriptor set
+ * are the GRAPHICS bind point's.  kzn_queue_reserve_vertex_outputs sizes that scratch ahead of a recorded draw. */
+typedef struct KznVertexProgram KznVertexProgram;
+KZN_API KznResult kzn_vertex_program_create(KznDevice* device, const KznIrModule* module, KznVertexProgram** program);
+KZN_API void kzn_vertex_program_destroy(KznVertexProgram* program);
+KZN_API KznResult kzn_cmd_bind_vertex_program(KznQueue* queue, KznVertexProgram* program);
+KZN_API uint64_t kzn_vertex_program_inputs_size(const KznVertexProgram* program);  /* = the vertex binding's stride */
+KZN_API uint64_t kzn_vertex_program_outputs_size(const KznVertexProgram* program); /* bytes per vertex in the scratch */
+KZN_API KznResult kzn_queue_reserve_vertex_outputs(KznQueue* queue, uint64_t max_vertices, const KznVertexProgram* program);
+
 /* ---- the backend trait surface (shader-compiler-backend/src/lib.rs) ------------------------------------------------------ */
 typedef struct KznBackendContext KznBackendContext;   /* trait Context  lib.rs:162-189 */
 typedef struct KznBackendModule KznBackendModule;     /* trait Module   lib.rs:132-145 */

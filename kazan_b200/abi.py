@@ -60,6 +60,7 @@ VS_PASSTHROUGH = 0
 FS_VERTEX_COLOR = 0
 FS_PROCEDURAL_ORBIT = 1
 FS_COMPILED = 2
+VS_PASSTHROUGH, VS_COMPILED = 0, 1
 # VkCompareOp
 COMPARE_NEVER, COMPARE_LESS, COMPARE_EQUAL, COMPARE_LESS_OR_EQUAL, COMPARE_GREATER, COMPARE_NOT_EQUAL, \
     COMPARE_GREATER_OR_EQUAL, COMPARE_ALWAYS = range(8)
@@ -313,6 +314,12 @@ BACKEND_PROTOTYPES = {
     "kzn_fragment_program_create": (i32, [vp, vp, P(vp)]),
     "kzn_fragment_program_destroy": (None, [vp]),
     "kzn_cmd_bind_fragment_program": (i32, [vp, vp]),
+    "kzn_vertex_program_create": (i32, [vp, vp, P(vp)]),
+    "kzn_vertex_program_destroy": (None, [vp]),
+    "kzn_cmd_bind_vertex_program": (i32, [vp, vp]),
+    "kzn_vertex_program_inputs_size": (u64, [vp]),
+    "kzn_vertex_program_outputs_size": (u64, [vp]),
+    "kzn_queue_reserve_vertex_outputs": (i32, [vp, u64, vp]),
     "kzn_fragment_program_ptx": (i32, [vp, P(vp), P(sz)]),
     "kzn_fragment_program_module_ptx": (i32, [vp, P(vp), P(sz)]),
     "kzn_ir_to_text": (i32, [vp, P(vp), P(sz)]),

@@ -189,12 +189,47 @@ class FragmentProgram:
             self.handle = None
 
 
+class VertexProgram:
+    """The vertex stage of a graphics pipeline: a vertex shader in version 2 of the IR, run by the PTX back end over the
+    vertices of a draw before setup (state.vertex_program = VS_COMPILED)."""
+
+    def __init__(self, device: Device, module: IrModule):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.kzn_vertex_program_create(device.handle, module.handle, C.byref(h)))
+        self.handle = h
+
+    @property
+    def inputs_size(self) -> int:
+        return self._lib.kzn_vertex_program_inputs_size(self.handle)
+
+    @property
+    def outputs_size(self) -> int:
+        return self._lib.kzn_vertex_program_outputs_size(self.handle)
+
+    def destroy(self):
+        if self.handle:
+            self._lib.kzn_vertex_program_destroy(self.handle)
+            self.handle = None
+
+
+def cmd_bind_vertex_program(queue: Queue, program: "VertexProgram | None"):
+    """vkCmdBindPipeline (api_impl.rs:4506) for the vertex stage"""
+    _check(load_library().kzn_cmd_bind_vertex_program(queue.handle, program.handle if program else None))
+
+
+def reserve_vertex_outputs(queue: Queue, max_vertices: int, program: VertexProgram):
+    _check(load_library().kzn_queue_reserve_vertex_outputs(queue.handle, max_vertices, program.handle))
+
+
 def cmd_bind_fragment_program(queue: Queue, program: "FragmentProgram | None"):
     """vkCmdBindPipeline (api_impl.rs:4506) for the fragment stage"""
     _check(load_library().kzn_cmd_bind_fragment_program(queue.handle, program.handle if program else None))
 
 
 Queue.cmd_bind_fragment_program = cmd_bind_fragment_program
+Queue.cmd_bind_vertex_program = cmd_bind_vertex_program
+Queue.reserve_vertex_outputs = reserve_vertex_outputs
 Queue.cmd_bind_descriptor_set = cmd_bind_descriptor_set
 Queue.cmd_push_constants = cmd_push_constants
 

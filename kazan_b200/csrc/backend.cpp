@@ -154,6 +154,11 @@ struct KznFragmentProgram {
     int call_sites = 0;
 };
 
+struct KznVertexProgram {
+    struct KznPipeline* pipeline = nullptr;  // the shader as a kernel of the PTX back end, one invocation per vertex
+    KznVertexLayout layout = {};
+};
+
 struct KznPipeline {
     KznDevice* device = nullptr;
     CUmodule_ module = nullptr;
@@ -744,9 +749,88 @@ KznResult kzn_cmd_bind_fragment_program(KznQueue* queue, KznFragmentProgram* pro
     return KZN_SUCCESS;
 }
 
+// ---- vertex programs ------------------------------------------------------------------------------------------------------------
+
+KznResult kzn_vertex_program_create(KznDevice* device, const KznIrModule* module, KznVertexProgram** program) {
+    KZN_VALID(device && module && program, "kzn_vertex_program_create: null argument");
+    *program = nullptr;
+    const kir::Module& m = *module->module;
+    KZN_REQUIRE(m.version >= 2, KZN_ERROR_FEATURE_NOT_PRESENT, "a vertex program needs version 2 of the IR (stores, the vertex_position built-in)");
+    // where the emitter puts the built-in outputs: after the user outputs, each at a multiple of 16 bytes (ptx_emit.cpp emit_ptx)
+    uint64_t at = m.user_outputs.size;
+    int64_t position = -1;
+    for (const auto& v : m.built_in_outputs) {
+        at = (at + 15) / 16 * 16;
+        const bool vec4 = v.type && v.type->kind == kir::TypeKind::Vector && v.type->length == 4 && v.type->element &&
+                          v.type->element->kind == kir::TypeKind::Float && v.type->element->float_kind == kir::FloatKind::F32;
+        if (v.built_in_kind == "vertex_position") {
+            KZN_VALID(vec4, "vertex program: vertex_position must be <4 x f32>");
+            position = (int64_t)at;
+        }
+        at += (kir::type_size(v.type) + 15) / 16 * 16;
+    }
+    KZN_VALID(position >= 0, "vertex program: the module has no built-in output of kind vertex_position");
+    KZN_VALID(m.user_inputs.size > 0 && m.user_inputs.size % 4 == 0 && m.user_inputs.size < (1u << 28), "vertex program: bad user_inputs_block size");
+    auto vp = std::make_unique<KznVertexProgram>();
+    const uint32_t one[3] = {1, 1, 1};
+    KznResult r = kzn_compute_pipeline_create(device, module, one, &vp->pipeline);
+    if (r != KZN_SUCCESS) return r;
+    vp->layout.inputs_size = vp->pipeline->inputs_size;
+    vp->layout.outputs_size = vp->pipeline->outputs_size;
+    vp->layout.position_offset = (uint32_t)position;
+    vp->layout.color_offset = m.user_outputs.size >= 16 ? 0u : ~0u;  // user output location 0
+    if (vp->layout.outputs_size != at || vp->layout.outputs_size >= (1u << 28)) {
+        kzn_pipeline_destroy(vp->pipeline);
+        kzn_set_error("internal: vertex program output slot of %llu bytes, expected %llu", (unsigned long long)vp->layout.outputs_size, (unsigned long long)at);
+        return KZN_ERROR_VALIDATION_FAILED;
+    }
+    *program = vp.release();
+    return KZN_SUCCESS;
+}
+
+void kzn_vertex_program_destroy(KznVertexProgram* program) {
+    if (!program) return;
+    kzn_pipeline_destroy(program->pipeline);
+    delete program;
+}
+
+KznResult kzn_cmd_bind_vertex_program(KznQueue* queue, KznVertexProgram* program) {
+    KZN_VALID(queue, "vkCmdBindPipeline: null queue");
+    KZN_VALID(!program || program->pipeline->device->ordinal == queue->device->ordinal, "vertex program was created for another device");
+    queue->vertex_program = program;
+    return KZN_SUCCESS;
+}
+
+uint64_t kzn_vertex_program_inputs_size(const KznVertexProgram* program) { return program ? program->layout.inputs_size : 0; }
+uint64_t kzn_vertex_program_outputs_size(const KznVertexProgram* program) { return program ? program->layout.outputs_size : 0; }
+
+KznResult kzn_queue_reserve_vertex_outputs(KznQueue* queue, uint64_t max_vertices, const KznVertexProgram* program) {
+    KznResult r = kzn_queue_enter(queue);
+    if (r) return r;
+    KZN_VALID(program && max_vertices > 0 && max_vertices <= 0xffffffffull, "kzn_queue_reserve_vertex_outputs: bad argument");
+    KZN_VALID(!queue->recording, "kzn_queue_reserve_vertex_outputs allocates: call it before vkBeginCommandBuffer");
+    uint64_t address = 0;
+    return kzn_raster_vertex_scratch(queue, max_vertices * program->layout.outputs_size, &address);
+}
+
 }  // extern "C"
 
 // internal (kzn_internal.h): used by raster.cu
+KznVertexLayout kzn_vertex_program_layout(const KznVertexProgram* program) { return program ? program->layout : KznVertexLayout{}; }
+
+KznResult kzn_vertex_program_run(KznQueue* queue, KznVertexProgram* program, uint64_t inputs, uint64_t outputs, uint64_t first, uint64_t count) {
+    KZN_VALID(program && count <= 0xffffffffull, "internal: bad vertex program run");
+    if (count == 0) return KZN_SUCCESS;
+    // one invocation per vertex: invocation i works on slot first + i of both buffers; the GRAPHICS bind point's descriptor
+    // set and the push constants go into the launch like a dispatch's
+    const uint64_t saved = queue->descriptor_table[KZN_PIPELINE_BIND_POINT_COMPUTE];
+    queue->descriptor_table[KZN_PIPELINE_BIND_POINT_COMPUTE] = queue->descriptor_table[KZN_PIPELINE_BIND_POINT_GRAPHICS];
+    const uint32_t groups[3] = {(uint32_t)count, 1, 1};
+    const KznResult r = kzn_cmd_dispatch(queue, program->pipeline, nullptr, groups, inputs, outputs, first);
+    queue->descriptor_table[KZN_PIPELINE_BIND_POINT_COMPUTE] = saved;
+    return r;
+}
+
 uint32_t kzn_fragment_program_flags(const KznFragmentProgram* program) { return program ? program->flags : 0u; }
 
 KznResult kzn_fragment_program_launch(KznFragmentProgram* program, int kernel, int mode, unsigned grid_x, unsigned threads, size_t dynamic_smem,

@@ -47,7 +47,20 @@ struct KznQueue {
     uint64_t descriptor_table[2];  // [VkPipelineBindPoint]: device address of the bound set's table, 0 = none
     alignas(16) unsigned char push_constants[128];
     struct KznFragmentProgram* fragment_program;  // kzn_cmd_bind_fragment_program
+    struct KznVertexProgram* vertex_program;      // kzn_cmd_bind_vertex_program
 };
+
+// backend.cpp: a draw with a compiled vertex stage.  layout: what one vertex occupies in the vertex scratch and where its
+// position (four f32) and colour (four f32; ~0u: none) are; run: shade `count` vertices starting at vertex `first` of the
+// binding at `inputs` (stride = the program's input block) into `outputs`, on the queue's stream.
+struct KznVertexLayout {
+    uint64_t inputs_size, outputs_size;
+    uint32_t position_offset, color_offset;
+};
+KznVertexLayout kzn_vertex_program_layout(const struct KznVertexProgram* program);
+KznResult kzn_vertex_program_run(KznQueue* queue, struct KznVertexProgram* program, uint64_t inputs, uint64_t outputs, uint64_t first, uint64_t count);
+// raster.cu: the queue's vertex scratch, grown to `bytes`
+KznResult kzn_raster_vertex_scratch(KznQueue* queue, uint64_t bytes, uint64_t* address);
 
 // backend.cpp: launch one of the raster kernels built around a compiled fragment program.  kernel: 0 = raster_direct,
 // 1 = raster (binned); mode: kDstNone / kDstGeneric / kDstAlphaOver; `params` is the kernel's single by-value parameter.

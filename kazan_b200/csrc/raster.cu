@@ -2356,6 +2356,8 @@ struct KznRasterScratch {
     size_t parent_capacity = 0;
     uint32_t* clip_list = nullptr;
     size_t list_capacity = 0;
+    unsigned char* vs_out = nullptr;  // what a compiled vertex stage writes and setup reads (KZN_VS_COMPILED)
+    size_t vs_capacity = 0;
     bool attrs_set = false;
     void* window_base = nullptr;  // the access policy window last set on the queue's stream (the records of binned draws)
     size_t window_bytes = 0;
@@ -2388,6 +2390,7 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->clip_link);
     cudaFree(s->clip_parent);
     cudaFree(s->clip_list);
+    cudaFree(s->vs_out);
     delete s;
 }
 
@@ -2418,7 +2421,7 @@ bool finite_host(float f) { return (f - f) == 0.0f; }
 KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp, const KznRect2D* sc,
                      const KznVertexInput* vi, uint32_t* W, uint32_t* H) {
     KZN_VALID(st && fb && vp && sc && vi, "draw: null argument");
-    KZN_REQUIRE(st->vertex_program == KZN_VS_PASSTHROUGH, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown vertex program %u", st->vertex_program);
+    KZN_REQUIRE(st->vertex_program <= KZN_VS_COMPILED, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown vertex program %u", st->vertex_program);
     KZN_REQUIRE(st->fragment_program <= KZN_FS_COMPILED, KZN_ERROR_FEATURE_NOT_PRESENT, "draw: unknown fragment program %u",
                 st->fragment_program);
     KZN_VALID(st->cull_mode <= 3 && st->front_face <= 1 && st->depth_compare_op <= 7, "draw: bad rasterization / depth state");
@@ -2563,6 +2566,32 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     if (r) return r;
     uint32_t W = 0, H = 0;
     if ((r = check_draw(st, fb, vp, sc, vi, &W, &H))) return r;
+    KznVertexInput shaded;
+    if (st->vertex_program == KZN_VS_COMPILED && count && instance_count) {
+        // The vertex stage as a dispatch of the PTX back end, one invocation per vertex, into the queue's vertex scratch; the
+        // fixed stages then read positions and colours from there (same vertex numbering, so indices and vertexOffset apply
+        // unchanged).  Setup waits for it like for any earlier kernel of the stream (griddepcontrol.wait).
+        KZN_VALID(q->vertex_program, "draw: vertex_program is KZN_VS_COMPILED but no program is bound (kzn_cmd_bind_vertex_program)");
+        const KznVertexLayout lay = kzn_vertex_program_layout(q->vertex_program);
+        KZN_VALID(vi->stride == lay.inputs_size, "draw: the vertex binding's stride (%u) is not the vertex program's input block size (%llu)", vi->stride,
+                  (unsigned long long)lay.inputs_size);
+        const uint64_t in_buffer = vi->buffer_size / vi->stride;  // whole vertices of the binding
+        uint64_t v0 = 0, n = in_buffer;
+        if (!index_base) {  // a non-indexed draw names vertices first .. first + count - 1
+            v0 = first < in_buffer ? first : in_buffer;
+            n = (uint64_t)first + count < in_buffer ? count : in_buffer - v0;
+        }
+        uint64_t out = 0;
+        if ((r = kzn_raster_vertex_scratch(q, (v0 + n) * lay.outputs_size, &out))) return r;
+        if ((r = kzn_vertex_program_run(q, q->vertex_program, vi->buffer_address, out, v0, n))) return r;
+        shaded.buffer_address = out;
+        shaded.buffer_size = (v0 + n) * lay.outputs_size;  // vertices beyond the binding read (0, 0, 0, 1) / black (robust fetch)
+        shaded.stride = (uint32_t)lay.outputs_size;
+        shaded.position_offset = lay.position_offset;
+        shaded.position_components = 4;
+        shaded.color_offset = lay.color_offset;
+        vi = &shaded;
+    }
     DrawParams p;
     memset(&p, 0, sizeof p);
     make_clip(fb, vp, sc, W, H, &p);
@@ -2766,6 +2795,19 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
 }
 
 }  // namespace
+
+KznResult kzn_raster_vertex_scratch(KznQueue* q, uint64_t bytes, uint64_t* address) {
+    if (!q->raster) {
+        q->raster = new (std::nothrow) KznRasterScratch();
+        KZN_REQUIRE(q->raster, KZN_ERROR_OUT_OF_HOST_MEMORY, "out of host memory");
+    }
+    KznRasterScratch* s = q->raster;
+    KznResult r = grow(q, &s->vs_out, &s->vs_capacity, (size_t)(bytes ? bytes : 16));
+    if (r) return r;
+    if (q->recording) kzn_command_buffer_uses_raster_scratch(q->recording, q->raster);
+    *address = (uint64_t)(uintptr_t)s->vs_out;
+    return KZN_SUCCESS;
+}
 
 extern "C" {
 

@@ -152,6 +152,7 @@ class Scene:
         self.color_tiling, self.index_type = color_tiling, index_type
         self.pos_comps, self.color_offset, self.instances, self.band = pos_comps, color_offset, instances, band
         self.first, self.vertex_offset = first, vertex_offset
+        self.position_offset = 0
         self.stride = self.vertices.shape[1] * 4 if self.vertices.ndim == 2 else 28
 
     @property
@@ -182,7 +183,7 @@ class Scene:
             lib.kzo_set_threads(threads)
         color, depth = self._initial()
         fb = self._framebuffer(ob.ptr(color), ob.ptr(depth))
-        vi = abi.VertexInput(ob.ptr(self.vertices), self.vertices.nbytes, self.stride, 0, self.pos_comps,
+        vi = abi.VertexInput(ob.ptr(self.vertices), self.vertices.nbytes, self.stride, self.position_offset, self.pos_comps,
                              self.color_offset)
         stats = abi.DrawStatistics()
         if self.indices is not None:
@@ -196,21 +197,29 @@ class Scene:
         check(code)
         return color, depth, stats
 
-    def run_gpu(self, ctx: GpuContext, compiled=None):
+    def run_gpu(self, ctx: GpuContext, compiled=None, vertex_program=None, push_constants: bytes = b""):
         """compiled: {fragment program enum: backend.FragmentProgram} — the draw then runs the compiled form of the scene's
         built-in fragment program (state.fragment_program = KZN_FS_COMPILED, the program bound to the queue, the frame's
-        1/width and 1/height as push constants, which is what fs_orbit.kazan-ir reads)."""
+        1/width and 1/height as push constants, which is what fs_orbit.kazan-ir reads).
+        vertex_program: a backend.VertexProgram — the draw runs it as its vertex stage (state.vertex_program = KZN_VS_COMPILED)
+        with `push_constants`; the scene's vertices are then the shader's input block, one per stride."""
         color0, depth0 = self._initial()
         cbuf = ctx.buffer(color0.nbytes, color0)
         dbuf = ctx.buffer(depth0.nbytes, depth0)
         vbuf = ctx.buffer(self.vertices.nbytes, self.vertices)
         sbuf = ctx.buffer(C.sizeof(abi.DrawStatistics), np.zeros(C.sizeof(abi.DrawStatistics) // 8, dtype=np.uint64))
         fb = self._framebuffer(cbuf.address, dbuf.address)
-        vi = abi.VertexInput(vbuf.address, self.vertices.nbytes, self.stride, 0, self.pos_comps, self.color_offset)
+        vi = abi.VertexInput(vbuf.address, self.vertices.nbytes, self.stride, self.position_offset, self.pos_comps, self.color_offset)
         q = ctx.queue
         state = self.state
-        if compiled is not None:
+        if compiled is not None or vertex_program is not None:
             state = abi.GraphicsPipelineState.from_buffer_copy(bytes(self.state))
+        if vertex_program is not None:
+            state.vertex_program = abi.VS_COMPILED
+            q.cmd_bind_vertex_program(vertex_program)
+            if push_constants:
+                q.cmd_push_constants(push_constants)
+        if compiled is not None:
             state.fragment_program = abi.FS_COMPILED
             q.cmd_bind_fragment_program(compiled[self.state.fragment_program])
             q.cmd_push_constants(np.array([np.float32(1.0) / np.float32(self.width), np.float32(1.0) / np.float32(self.height)],
@@ -225,6 +234,8 @@ class Scene:
         q.set_draw_statistics(0)
         if compiled is not None:
             q.cmd_bind_fragment_program(None)
+        if vertex_program is not None:
+            q.cmd_bind_vertex_program(None)
         color, depth = cbuf.download(), dbuf.download()
         stats = abi.DrawStatistics.from_buffer_copy(sbuf.download().tobytes())
         ctx.release()
