@@ -23,8 +23,12 @@ struct KznCommandBuffer;  // api.cu
 // that no barrier separates, and disjoint ranges make the merged result identical to in-order execution anyway.
 #define KZN_MAX_MERGED 96
 struct KznPendingTransfer {
-    uint64_t dst, src, bytes;  // src == 0: fill with `value`
+    uint64_t dst, src, bytes;  // src == 0: fill with `value`; bytes = payload (row_bytes x rows for a pitched box)
     uint32_t value;
+    // pitched boxes of LINEAR memory (padded bufferRowLength, sub-rectangles): rows of row_bytes at the two pitches;
+    // row_bytes == 0: one contiguous run.
+    uint32_t row_bytes, rows;
+    uint32_t dst_pitch, src_pitch;
 };
 
 struct KznQueue {

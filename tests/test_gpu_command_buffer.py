@@ -286,3 +286,87 @@ def test_recorded_draw_survives_scratch_growth_and_stays_on_its_queue(gpu):
     for m in mem + bmem + junk:
         m.free()
     other.destroy(); q.destroy(); dev.destroy()
+
+
+def test_pitched_sub_rect_and_realigned_copies_merge_and_match_the_oracle(gpu):
+    """Recorded buffer <-> image copies with a padded bufferRowLength, a sub-rectangle, an image -> buffer copy into padded
+    rows and a plain one, all on disjoint memory: ONE merged launch (pitched boxes inside merged_transfer_kernel), byte for
+    byte the oracle's result; a copy that reads what the batch wrote starts a new launch; copies from a bufferOffset of 4, 8,
+    12 mod 16 realign in a kernel of their own.  Odd sizes exercise partial units and rows that straddle units."""
+    lib = ob.load()
+    q = gpu.queue
+    w, h = 200, 67  # 13400 texels: 3350 vectors = 3 full units + a partial one
+    nbytes = w * h * 4
+    pitch = w + 12
+    variants = [
+        ("padded_pitch", buffer_image_copy(w, h, row_length=pitch), pitch * h * 4, True),
+        ("sub_rect", buffer_image_copy(w - 32, h - 16, row_length=w, offset=(16, 8, 0)), nbytes, True),
+        ("to_padded_buffer", buffer_image_copy(w - 8, h, row_length=pitch, offset=(8, 0, 0)), pitch * h * 4, False),
+        ("contiguous", buffer_image_copy(w, h), nbytes, True),
+        # sources 4, 8, 12 mod 16: copy_realign_kernel, one launch each (they do not join a merged launch)
+        ("offset_4", buffer_image_copy(w, h, buffer_offset=4), nbytes + 16, True),
+        ("offset_8", buffer_image_copy(w, h, buffer_offset=8), nbytes + 16, True),
+        ("offset_12_tall_pitch", buffer_image_copy(w, h, buffer_offset=12, image_height=h + 3), nbytes + 16, True),
+    ]
+    images, buffers, want_img, want_buf = [], [], [], []
+    for i, (name, region, buf_bytes, to_image) in enumerate(variants):
+        img0 = ob.random_bytes(nbytes, 7000 + i)
+        buf0 = ob.random_bytes(buf_bytes, 7100 + i)
+        wi, wb = ob.aligned_empty(nbytes), ob.aligned_empty(buf_bytes)
+        wi[:], wb[:] = img0, buf0
+        d = abi.ImageDesc(ob.ptr(wi), abi.FORMAT_R8G8B8A8_UNORM, 0, w, h, 1, 1, 1, 0)
+        reg, k = util.arr(abi.BufferImageCopy, [region])
+        if to_image:
+            check(lib.kzo_copy_buffer_to_image(C.c_void_p(ob.ptr(wb)), buf_bytes, C.byref(d), k, reg))
+        else:
+            check(lib.kzo_copy_image_to_buffer(C.byref(d), C.c_void_p(ob.ptr(wb)), buf_bytes, k, reg))
+        want_img.append(wi.copy()); want_buf.append(wb.copy())
+        images.append((gpu.buffer(nbytes, img0), img0)); buffers.append((gpu.buffer(buf_bytes, buf0), buf0))
+    readback = gpu.buffer(nbytes, np.zeros(nbytes, dtype=np.uint8))
+    def record_one(k):
+        (name, region, buf_bytes, to_image), (im, _), (bf, _) = variants[k], images[k], buffers[k]
+        img = host.Image(im.address, w, h)
+        if to_image:
+            q.cmd_copy_buffer_to_image(bf.address, buf_bytes, img, [region])
+        else:
+            q.cmd_copy_image_to_buffer(img, bf.address, buf_bytes, [region])
+
+    with q.record() as cb:
+        for k in range(4):
+            record_one(k)  # one merged launch
+        q.cmd_copy_image_to_buffer(host.Image(images[1][0].address, w, h), readback.address, nbytes, [buffer_image_copy(w, h)])  # reads the batch: its own launch
+        for k in range(4, 7):
+            record_one(k)
+    assert cb.launch_count == 5
+    for rep in range(2):
+        q.submit([cb])
+        q.wait_idle()
+        for i, (name, *_rest) in enumerate(variants):
+            assert np.array_equal(images[i][0].download(), want_img[i]), f"{name}: image, replay {rep}"
+            assert np.array_equal(buffers[i][0].download(), want_buf[i]), f"{name}: buffer, replay {rep}"
+        assert np.array_equal(readback.download(), want_img[1])
+        for (im, img0), (bf, buf0) in zip(images, buffers):
+            im.upload(img0); bf.upload(buf0)
+    cb.destroy()
+    # two pitched boxes interleaved in ONE buffer (rows of the one in the padding of the other): the conservative byte
+    # spans overlap, so they do not merge — and the result is still right
+    both = ob.random_bytes(2 * w * h * 4, 7300)
+    wb = ob.aligned_empty(both.nbytes); wb[:] = both
+    srcs = [ob.random_bytes(nbytes, 7301), ob.random_bytes(nbytes, 7302)]
+    regions = [buffer_image_copy(w, h, row_length=2 * w), buffer_image_copy(w, h, buffer_offset=w * 4, row_length=2 * w)]
+    for s, r in zip(srcs, regions):
+        si = ob.aligned_empty(nbytes); si[:] = s
+        d = abi.ImageDesc(ob.ptr(si), abi.FORMAT_R8G8B8A8_UNORM, 0, w, h, 1, 1, 1, 0)
+        reg, k = util.arr(abi.BufferImageCopy, [r])
+        check(lib.kzo_copy_image_to_buffer(C.byref(d), C.c_void_p(ob.ptr(wb)), both.nbytes, k, reg))
+    gb = gpu.buffer(both.nbytes, both)
+    gs = [gpu.buffer(nbytes, s) for s in srcs]
+    with q.record() as cb:
+        for g, r in zip(gs, regions):
+            q.cmd_copy_image_to_buffer(host.Image(g.address, w, h), gb.address, both.nbytes, [r])
+    assert cb.launch_count == 2
+    q.submit([cb])
+    q.wait_idle()
+    assert np.array_equal(gb.download(), wb)
+    cb.destroy()
+    gpu.release()
