@@ -421,6 +421,26 @@ typedef struct KznFramebuffer { /* vkCreateFramebuffer api_impl.rs:4383-4390 + r
     uint32_t band_y0, band_y1;
 } KznFramebuffer;
 
+/* vkCmdBeginRenderPass (api_impl.rs:4944-4958) / vkCmdEndRenderPass (:4961-4968) for one subpass with at most one colour
+ * and one depth attachment — the part of a render pass that is data-path work: VK_ATTACHMENT_LOAD_OP_CLEAR.  The clear of
+ * the render area (cut to the framebuffer's band) is not launched when the render pass begins: the first draw whose clip
+ * rectangle (scissor x viewport x framebuffer x band) IS that area, on the same attachments, and that is large enough to
+ * be binned, starts every 16 x 16 brick from the clear values instead of reading it and writes every pixel of the brick
+ * back — no clear kernel, no read of the framebuffer (what a tiling GPU does with LOAD_OP_CLEAR).  Any other command, a draw
+ * that does not qualify, or vkCmdEndRenderPass performs the clear with the transfer kernels first.  The result is the
+ * same, byte for byte, as vkCmdClearAttachments on the area followed by the draws. */
+#define KZN_ATTACHMENT_LOAD_OP_LOAD 0u
+#define KZN_ATTACHMENT_LOAD_OP_CLEAR 1u
+typedef struct KznRenderPassBegin {
+    KznFramebuffer framebuffer;
+    KznRect2D render_area;                 /* VkRenderPassBeginInfo::renderArea: inside the framebuffer */
+    uint32_t color_load_op, depth_load_op; /* VkAttachmentDescription::loadOp (DONT_CARE may be passed as LOAD) */
+    KznClearColorValue clear_color;        /* pClearValues of the two attachments */
+    KznClearDepthStencilValue clear_depth_stencil;
+} KznRenderPassBegin;
+KZN_API KznResult kzn_cmd_begin_render_pass(KznQueue* queue, const KznRenderPassBegin* begin);
+KZN_API KznResult kzn_cmd_end_render_pass(KznQueue* queue);
+
 typedef struct KznDrawStatistics { /* optional, device-written counters (12 x u64) */
     uint64_t triangles_in, triangles_culled, triangles_binned, bin_entries, fragments_covered,
         fragments_depth_passed, tiles_launched, bin_overflow_tiles;

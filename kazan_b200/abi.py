@@ -161,6 +161,14 @@ class Framebuffer(C.Structure):
                 ("band_y0", u32), ("band_y1", u32)]
 
 
+LOAD_OP_LOAD, LOAD_OP_CLEAR = 0, 1
+
+
+class RenderPassBegin(C.Structure):  # KznRenderPassBegin
+    _fields_ = [("framebuffer", Framebuffer), ("render_area", Rect2D), ("color_load_op", u32), ("depth_load_op", u32),
+                ("clear_color", ClearColorValue), ("clear_depth_stencil", ClearDepthStencilValue)]
+
+
 class DrawStatistics(C.Structure):
     _fields_ = [(n, u64) for n in (
         "triangles_in", "triangles_culled", "triangles_binned", "bin_entries", "fragments_covered",
@@ -239,6 +247,8 @@ PROTOTYPES = {
     "kzn_cmd_clear_depth_stencil_image": (i32, [vp, P(ImageDesc), P(ClearDepthStencilValue), u32,
                                                 P(ImageSubresourceRange)]),
     "kzn_cmd_clear_attachment": (i32, [vp, P(ImageDesc), P(ClearColorValue), u32, P(ClearRect)]),
+    "kzn_cmd_begin_render_pass": (i32, [vp, P(RenderPassBegin)]),
+    "kzn_cmd_end_render_pass": (i32, [vp]),
     "kzn_cmd_copy_buffer_to_image": (i32, [vp, u64, u64, P(ImageDesc), u32, P(BufferImageCopy)]),
     "kzn_cmd_copy_image_to_buffer": (i32, [vp, P(ImageDesc), u64, u64, u32, P(BufferImageCopy)]),
     "kzn_cmd_copy_buffer": (i32, [vp, u64, u64, u64, u64, u32, P(BufferCopy)]),

@@ -193,12 +193,18 @@ KznResult kzn_memory_map(KznMemory* memory, uint64_t offset, void** host_ptr) {
 KznResult kzn_queue_enter_transfer(KznQueue* q) {
     KZN_VALID(q && q->device, "null queue");
     KZN_CUDA(cudaSetDevice(q->device->ordinal));
-    return KZN_SUCCESS;
+    return q->pending_clear.active ? kzn_flush_render_pass_clear(q) : KZN_SUCCESS;  // LOAD_OP_CLEAR that no draw took over
 }
 
 KznResult kzn_queue_enter(KznQueue* q) {
     KznResult r = kzn_queue_enter_transfer(q);
     if (r) return r;
+    return q->n_pending ? kzn_flush_transfers(q) : KZN_SUCCESS;
+}
+
+KznResult kzn_queue_enter_draw(KznQueue* q) {
+    KZN_VALID(q && q->device, "null queue");
+    KZN_CUDA(cudaSetDevice(q->device->ordinal));
     return q->n_pending ? kzn_flush_transfers(q) : KZN_SUCCESS;
 }
 

@@ -31,6 +31,16 @@ struct KznPendingTransfer {
     uint32_t dst_pitch, src_pitch;
 };
 
+// vkCmdBeginRenderPass with LOAD_OP_CLEAR, not yet performed: the next qualifying draw starts its bricks from these values
+// (raster.cu), anything else performs the clear first (kzn_flush_render_pass_clear, transfer.cu).
+struct KznPendingClear {
+    bool active;
+    KznFramebuffer fb;
+    int32_t x0, y0, x1, y1;  // inclusive pixel rectangle: the render area cut to the framebuffer and its band
+    uint32_t load;           // bit 0: colour, bit 1: depth
+    uint32_t color_word, depth_bits;
+};
+
 struct KznQueue {
     KznDevice* device;
     cudaStream_t stream;
@@ -50,6 +60,8 @@ struct KznQueue {
     // launch's kernel parameters, so a recorded command keeps what was bound when it was recorded)
     uint64_t descriptor_table[2];  // [VkPipelineBindPoint]: device address of the bound set's table, 0 = none
     alignas(16) unsigned char push_constants[128];
+    KznPendingClear pending_clear;
+    bool in_render_pass;
     struct KznFragmentProgram* fragment_program;  // kzn_cmd_bind_fragment_program
     struct KznVertexProgram* vertex_program;      // kzn_cmd_bind_vertex_program
 };
@@ -127,6 +139,8 @@ KznResult kzn_cuda_failed(cudaError_t e, const char* what, const char* file, int
 
 // make the queue's device current and check the queue is usable; captures any pending merged transfers first
 KznResult kzn_queue_enter(KznQueue* q);
+KznResult kzn_queue_enter_draw(KznQueue* q);  // as kzn_queue_enter, but a pending render-pass clear stays pending (the draw decides)
+KznResult kzn_flush_render_pass_clear(KznQueue* q);  // transfer.cu
 // the same for the transfer commands themselves, which may join the pending batch instead of flushing it
 KznResult kzn_queue_enter_transfer(KznQueue* q);
 // capture the pending batch now (transfer.cu); no-op when nothing is pending

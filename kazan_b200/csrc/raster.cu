@@ -150,6 +150,10 @@ struct DrawParams {
     uint32_t* work_counter;                        // direct draws: next block to hand out (zeroed by setup_kernel)
     uint32_t exact_spans;                          // raster_kernel: narrow spans are reduced to the covered interval first
     uint32_t fused_setup;                          // direct draws of <= kFusedMax triangles: raster_direct_kernel makes the records itself
+    // vkCmdBeginRenderPass with LOAD_OP_CLEAR taken over by this (binned) draw: bit 0 — every brick's colour starts as
+    // clear_color and is written back whole, bit 1 — the same for depth (no clear kernel, no framebuffer read)
+    uint32_t load_clear, clear_color;
+    float clear_depth;
     // compiled fragment programs (KZN_FS_COMPILED): what vkCmdBindDescriptorSets / vkCmdPushConstants left on the queue, and
     // what the program reads (bit 0: it needs interpolated inputs or the z / w of frag_coord, so no coverage shortcut applies)
     uint32_t fs_flags;
@@ -2124,7 +2128,7 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
         if (!(brick_px0 <= p.cx1 && brick_px0 + kBrick - 1 >= p.cx0 && brick_py0 <= p.cy1 && brick_py0 + kBrick - 1 >= p.cy0)) continue;
         // triangle source: the tile's sorted id list, or — a tile whose list did not fit — every triangle of the draw
         const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
-        if (end == beg) continue;
+        if (end == beg && !p.load_clear) continue;  // (with LOAD_OP_CLEAR an empty brick is still written: the clear values)
         const bool direct = end - beg > (uint32_t)kSortCap || end > p.bin_capacity;
         // (walking all triangles: with clipped primitives in the draw every primitive stands for eight list entries, its own
         // record and up to five extra ones, so that the extra triangles come at the primitive's place)
@@ -2146,7 +2150,11 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
             if (has_color) caddr = color_addr(p, qx0, qy);
             if (has_depth) daddr = p.depth_base + ((unsigned long long)qy * p.fb_w + qx0) * 4ull;
         }
-        if (NEED_DST && quad_clip && has_color) {
+        if (p.load_clear & 1u) {
+            const uint32_t w = p.clear_color;
+            *reinterpret_cast<uint4*>(&bs.color[qat]) = make_uint4(w, w, w, w);
+            *reinterpret_cast<uint4*>(&bs.color[qat + 4]) = make_uint4(w, w, w, w);
+        } else if (NEED_DST && quad_clip && has_color) {
 #pragma unroll
             for (int h = 0; h < kBrickPx / 4; ++h) {
                 const uint32_t m4 = quad_clip >> (4 * h) & 15u;
@@ -2159,7 +2167,11 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
                 }
             }
         }
-        if (depth_test && quad_clip) {
+        if (p.load_clear & 2u) {
+            const float z = p.clear_depth;
+            *reinterpret_cast<float4*>(&bs.depth[qat]) = make_float4(z, z, z, z);
+            *reinterpret_cast<float4*>(&bs.depth[qat + 4]) = make_float4(z, z, z, z);
+        } else if (depth_test && quad_clip) {
 #pragma unroll
             for (int h = 0; h < kBrickPx / 4; ++h) {
                 const uint32_t m4 = quad_clip >> (4 * h) & 15u;
@@ -2267,8 +2279,9 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
         if (quad_clip) {
             const uint2 cdb = *reinterpret_cast<const uint2*>(&bs.color_dirty[qat]);
             const uint2 ddb = *reinterpret_cast<const uint2*>(&bs.depth_dirty[qat]);
-            const uint32_t cd = (bytes_to_bits(cdb.x) | bytes_to_bits(cdb.y) << 4) & quad_clip;
-            const uint32_t dd = (bytes_to_bits(ddb.x) | bytes_to_bits(ddb.y) << 4) & quad_clip;
+            // (LOAD_OP_CLEAR: every pixel of the brick inside the clip rectangle is written, changed or not)
+            const uint32_t cd = ((p.load_clear & 1u) ? 0xffu : bytes_to_bits(cdb.x) | bytes_to_bits(cdb.y) << 4) & quad_clip;
+            const uint32_t dd = ((p.load_clear & 2u) ? 0xffu : bytes_to_bits(ddb.x) | bytes_to_bits(ddb.y) << 4) & quad_clip;
 #pragma unroll
             for (int h = 0; h < kBrickPx / 4; ++h) {
                 const uint32_t c4 = cd >> (4 * h) & 15u, d4 = dd >> (4 * h) & 15u;
@@ -2562,11 +2575,12 @@ void launch_draw_kernel(void (*kernel)(DrawParams), dim3 grid, dim3 block, size_
 KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const KznFramebuffer* fb, const KznViewport* vp,
                       const KznRect2D* sc, const KznVertexInput* vi, uint64_t index_base, uint32_t index_type, uint32_t first,
                       uint32_t count, int32_t vertex_offset, uint32_t instance_count) {
-    KznResult r = kzn_queue_enter(q);
+    KznResult r = kzn_queue_enter_draw(q);  // (a pending LOAD_OP_CLEAR stays pending: this draw may take it over, below)
     if (r) return r;
     uint32_t W = 0, H = 0;
     if ((r = check_draw(st, fb, vp, sc, vi, &W, &H))) return r;
     KznVertexInput shaded;
+    if (st->vertex_program == KZN_VS_COMPILED && (r = kzn_flush_render_pass_clear(q))) return r;  // (the vertex stage is a dispatch of its own)
     if (st->vertex_program == KZN_VS_COMPILED && count && instance_count) {
         // The vertex stage as a dispatch of the PTX back end, one invocation per vertex, into the queue's vertex scratch; the
         // fixed stages then read positions and colours from there (same vertex numbering, so indices and vertexOffset apply
@@ -2597,8 +2611,9 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     make_clip(fb, vp, sc, W, H, &p);
     const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
     uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0), total = ntri * instance_count;
-    if (total == 0) return KZN_SUCCESS;
+    if (total == 0) return kzn_flush_render_pass_clear(q);
     if (p.cx1 < p.cx0 || p.cy1 < p.cy0) {  // empty clip rectangle (scissor, viewport, framebuffer and band do not meet)
+        if ((r = kzn_flush_render_pass_clear(q))) return r;
         if (q->stats_address) {
             kzn_launch_pdl(count_unrasterised_kernel, dim3(1), dim3(1), 0, q->stream, reinterpret_cast<unsigned long long*>(q->stats_address),
                            (unsigned long long)total);
@@ -2668,6 +2683,24 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
 
     size_t tiles = (size_t)p.tiles_x * p.tiles_y;
     p.binned = total > kDirectMax;
+    if (q->pending_clear.active) {
+        // LOAD_OP_CLEAR of the render pass this draw opens: a binned draw over exactly the cleared rectangle of the same
+        // attachments starts its bricks from the clear values (raster_body); anything else has the clear performed first
+        const KznPendingClear& c = q->pending_clear;
+        const bool same_color = !(c.load & 1u) || (has_color && fb->color.address == c.fb.color.address && fb->color_layer == c.fb.color_layer &&
+                                                   fb->color.tiling == c.fb.color.tiling && fb->color.width == c.fb.color.width);
+        const bool same_depth = !(c.load & 2u) || (has_depth && fb->depth.address == c.fb.depth.address && fb->depth_layer == c.fb.depth_layer &&
+                                                   fb->depth.width == c.fb.depth.width);
+        static const bool fuse_enabled = [] { const char* e = getenv("KZN_FUSE_LOAD_CLEAR"); return !(e && e[0] == '0'); }();
+        if (fuse_enabled && p.binned && same_color && same_depth && c.x0 == p.cx0 && c.y0 == p.cy0 && c.x1 == p.cx1 && c.y1 == p.cy1) {
+            p.load_clear = c.load;
+            p.clear_color = c.color_word;
+            memcpy(&p.clear_depth, &c.depth_bits, 4);
+            q->pending_clear.active = false;
+        } else if ((r = kzn_flush_render_pass_clear(q))) {
+            return r;
+        }
+    }
     if ((r = ensure_scratch(q, (size_t)total, (size_t)ntri, tiles, p.binned != 0))) return r;
     if (q->recording) kzn_command_buffer_uses_raster_scratch(q->recording, q->raster);  // its graph will name these buffers
     KznRasterScratch* s = q->raster;

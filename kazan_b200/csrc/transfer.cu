@@ -1056,6 +1056,26 @@ KznResult kzn_flush_transfers(KznQueue* q) {
     return kzn_launched(q, "merged_transfer_kernel");
 }
 
+// vkCmdBeginRenderPass left a LOAD_OP_CLEAR pending and no draw took it over: the clear as box fills (what
+// vkCmdClearAttachments on the same rectangle does).
+KznResult kzn_flush_render_pass_clear(KznQueue* q) {
+    if (!q->pending_clear.active) return KZN_SUCCESS;
+    const KznPendingClear c = q->pending_clear;
+    q->pending_clear.active = false;  // first: the launch helpers enter the queue again
+    if (c.x1 < c.x0 || c.y1 < c.y0) return KZN_SUCCESS;
+    const uint32_t w = (uint32_t)(c.x1 - c.x0 + 1), h = (uint32_t)(c.y1 - c.y0 + 1);
+    KznResult r;
+    if (c.load & 1u) {
+        Box b = image_box(&c.fb.color, c.x0, c.y0, 0, c.fb.color_layer);
+        if ((r = launch_box(q, nullptr, b, w, h, 1, true, c.color_word))) return r;
+    }
+    if (c.load & 2u) {
+        Box b = image_box(&c.fb.depth, c.x0, c.y0, 0, c.fb.depth_layer);
+        if ((r = launch_box(q, nullptr, b, w, h, 1, true, c.depth_bits))) return r;
+    }
+    return KZN_SUCCESS;
+}
+
 // ---- C ABI ----------------------------------------------------------------------------------------------------
 
 extern "C" {
@@ -1105,6 +1125,64 @@ KznResult kzn_cmd_clear_attachment(KznQueue* queue, const KznImageDesc* image, c
         Box b = image_box(image, c->rect.offset.x, c->rect.offset.y, 0, c->baseArrayLayer);
         if ((r = launch_box(queue, nullptr, b, c->rect.extent.width, c->rect.extent.height, c->layerCount, true, word))) return r;
     }
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_begin_render_pass(KznQueue* queue, const KznRenderPassBegin* begin) {
+    KznResult r = kzn_queue_enter_transfer(queue);
+    if (r) return r;
+    KZN_VALID(begin, "vkCmdBeginRenderPass: null argument");
+    KZN_VALID(!queue->in_render_pass, "vkCmdBeginRenderPass: a render pass is already active on this queue (VUID-vkCmdBeginRenderPass-renderpass)");
+    const KznFramebuffer* fb = &begin->framebuffer;
+    const bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
+    KZN_VALID(has_color || has_depth, "vkCmdBeginRenderPass: the framebuffer has no attachment");
+    KZN_VALID(begin->color_load_op <= KZN_ATTACHMENT_LOAD_OP_CLEAR && begin->depth_load_op <= KZN_ATTACHMENT_LOAD_OP_CLEAR, "vkCmdBeginRenderPass: bad loadOp");
+    uint32_t W = 0, H = 0;
+    if (has_color) {
+        if ((r = kzn_check_image(&fb->color, "vkCmdBeginRenderPass"))) return r;
+        KZN_REQUIRE(fb->color.format == KZN_FORMAT_R8G8B8A8_UNORM, KZN_ERROR_FORMAT_NOT_SUPPORTED, "vkCmdBeginRenderPass: colour attachment must be R8G8B8A8_UNORM");
+        KZN_VALID(fb->color.depth == 1 && fb->color_layer < fb->color.array_layers, "vkCmdBeginRenderPass: colour attachment must be a layer of a 2D image");
+        W = fb->color.width;
+        H = fb->color.height;
+    }
+    if (has_depth) {
+        if ((r = kzn_check_image(&fb->depth, "vkCmdBeginRenderPass"))) return r;
+        KZN_REQUIRE(fb->depth.format == KZN_FORMAT_D32_SFLOAT && fb->depth.tiling == KZN_TILING_LINEAR, KZN_ERROR_FORMAT_NOT_SUPPORTED,
+                    "vkCmdBeginRenderPass: depth attachment must be LINEAR D32_SFLOAT");
+        KZN_VALID(fb->depth.depth == 1 && fb->depth_layer < fb->depth.array_layers, "vkCmdBeginRenderPass: depth attachment must be a layer of a 2D image");
+        KZN_VALID(!has_color || (fb->depth.width == W && fb->depth.height == H), "vkCmdBeginRenderPass: attachments differ in size");
+        W = fb->depth.width;
+        H = fb->depth.height;
+    }
+    const KznRect2D* a = &begin->render_area;
+    KZN_VALID(a->offset.x >= 0 && a->offset.y >= 0 && (uint64_t)a->offset.x + a->extent.width <= W && (uint64_t)a->offset.y + a->extent.height <= H,
+              "vkCmdBeginRenderPass: renderArea outside the framebuffer (VUID-VkRenderPassBeginInfo-renderArea-02848)");
+    KZN_VALID(fb->band_y1 == 0 || (fb->band_y0 < fb->band_y1 && fb->band_y1 <= H), "vkCmdBeginRenderPass: bad band");
+    queue->in_render_pass = true;
+    KznPendingClear& c = queue->pending_clear;
+    c.load = (has_color && begin->color_load_op == KZN_ATTACHMENT_LOAD_OP_CLEAR ? 1u : 0u) |
+             (has_depth && begin->depth_load_op == KZN_ATTACHMENT_LOAD_OP_CLEAR ? 2u : 0u);
+    if (!c.load) return KZN_SUCCESS;
+    c.fb = *fb;
+    c.x0 = a->offset.x;
+    c.x1 = a->offset.x + (int32_t)a->extent.width - 1;
+    c.y0 = a->offset.y;
+    c.y1 = a->offset.y + (int32_t)a->extent.height - 1;
+    if (fb->band_y1) {  // a band of a split frame owns rows [band_y0, band_y1) only
+        if (c.y0 < (int32_t)fb->band_y0) c.y0 = (int32_t)fb->band_y0;
+        if ((int64_t)c.y1 > (int64_t)fb->band_y1 - 1) c.y1 = (int32_t)((int64_t)fb->band_y1 - 1);
+    }
+    c.color_word = kzn_pack_rgba8_host(begin->clear_color.float32);
+    memcpy(&c.depth_bits, &begin->clear_depth_stencil.depth, 4);
+    c.active = true;
+    return KZN_SUCCESS;
+}
+
+KznResult kzn_cmd_end_render_pass(KznQueue* queue) {
+    KznResult r = kzn_queue_enter_transfer(queue);  // (performs a clear that is still pending: a render pass without a qualifying draw)
+    if (r) return r;
+    KZN_VALID(queue->in_render_pass, "vkCmdEndRenderPass: no render pass is active (VUID-vkCmdEndRenderPass-renderpass)");
+    queue->in_render_pass = false;
     return KZN_SUCCESS;
 }
 

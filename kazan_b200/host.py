@@ -373,6 +373,25 @@ class Queue:
         arr, n = _array(abi.ClearRect, rects)
         _check(self._lib.kzn_cmd_clear_attachment(self.handle, C.byref(d), C.byref(c), n, arr))
 
+    def cmd_begin_render_pass(self, framebuffer: abi.Framebuffer, render_area: abi.Rect2D | None = None,
+                              clear_color: Sequence[float] | None = None, clear_depth: float | None = None):
+        """vkCmdBeginRenderPass: loadOp CLEAR for the attachments a clear value is given for, LOAD for the others."""
+        b = abi.RenderPassBegin()
+        b.framebuffer = framebuffer
+        w = framebuffer.color.width if framebuffer.color.format else framebuffer.depth.width
+        h = framebuffer.color.height if framebuffer.color.format else framebuffer.depth.height
+        b.render_area = render_area if render_area is not None else abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(w, h))
+        if clear_color is not None:
+            b.color_load_op = abi.LOAD_OP_CLEAR
+            b.clear_color.float32[:] = (list(clear_color) + [0.0] * 4)[:4]
+        if clear_depth is not None:
+            b.depth_load_op = abi.LOAD_OP_CLEAR
+            b.clear_depth_stencil = abi.ClearDepthStencilValue(clear_depth, 0)
+        _check(self._lib.kzn_cmd_begin_render_pass(self.handle, C.byref(b)))
+
+    def cmd_end_render_pass(self):
+        _check(self._lib.kzn_cmd_end_render_pass(self.handle))
+
     def cmd_copy_buffer_to_image(self, buffer_address: int, buffer_size: int, image: Image,
                                  regions: Iterable[abi.BufferImageCopy]):
         d = image.desc()

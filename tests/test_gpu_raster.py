@@ -41,6 +41,81 @@ def test_draw_matches_oracle(gpu, scene):
     assert sha(gd.tobytes()) == GOLDEN[f"draw/{scene.name}/depth"]
 
 
+@pytest.mark.parametrize("scene", SCENES, ids=lambda s: s.name)
+def test_draw_in_a_render_pass_with_load_op_clear_matches_oracle(gpu, scene):
+    """vkCmdBeginRenderPass(LOAD_OP_CLEAR) .. draw .. vkCmdEndRenderPass on attachments that hold a byte pattern, against
+    the oracle's vkCmdClearAttachments + draw: (a) render area = the draw's clip rectangle — a binned draw takes the clear
+    over (bricks start from the clear values, every pixel written once, no clear kernel: the launch count says so), a
+    direct draw has it performed first; (b) a render area one pixel larger where the framebuffer allows — never taken over."""
+    area = scene.render_area()
+    if area.extent.width == 0 or area.extent.height == 0:
+        pytest.skip("empty clip rectangle")
+    q = gpu.queue
+    n0 = q.launch_count
+    scene.run_gpu(gpu)
+    plain = q.launch_count - n0
+    oc, od, os_ = scene.run_oracle(render_pass=area)
+    n0 = q.launch_count
+    gc, gd, gs = scene.run_gpu(gpu, render_pass=area)
+    launches = q.launch_count - n0
+    assert (gs.fragments_covered, gs.fragments_depth_passed) == (os_.fragments_covered, os_.fragments_depth_passed)
+    assert gd.tobytes() == od.tobytes(), "depth differs"
+    assert gc.tobytes() == oc.tobytes(), "colour differs"
+    n_tri = scene.count // 3 if scene.state.topology in (0, 3) else max(0, scene.count - 2)
+    if n_tri * scene.instances > 256:  # binned: the draw took the clear over
+        assert launches == plain, f"the clear was not fused into the draw ({launches} launches against {plain})"
+    else:
+        assert launches == plain + (2 if scene.use_depth else 1)
+    big = abi.Rect2D(abi.Offset2D(max(0, area.offset.x - 1), area.offset.y),
+                     abi.Extent2D(min(scene.width - max(0, area.offset.x - 1), area.extent.width + 2), area.extent.height))
+    if big.extent.width != area.extent.width:
+        oc, od, _ = scene.run_oracle(render_pass=big)
+        n0 = q.launch_count
+        gc, gd, _ = scene.run_gpu(gpu, render_pass=big)
+        assert q.launch_count - n0 == plain + (2 if scene.use_depth else 1)
+        assert gd.tobytes() == od.tobytes() and gc.tobytes() == oc.tobytes(), "larger render area"
+
+
+def test_render_pass_rules(gpu):
+    """A render pass without a draw still clears (at vkCmdEndRenderPass, or before the next other command); begin inside a
+    render pass and end outside one are refused; LOAD leaves the attachments alone."""
+    from kazan_b200 import host
+    w, h = 96, 40
+    q = gpu.queue
+    img = gpu.buffer(w * h * 4, np.full(w * h * 4, 0xA5, dtype=np.uint8))
+    dep = gpu.buffer(w * h * 4, np.full(w * h * 4, 0x11, dtype=np.uint8))
+    fb = abi.Framebuffer()
+    fb.color = abi.ImageDesc(img.address, abi.FORMAT_R8G8B8A8_UNORM, 0, w, h, 1, 1, 1, 0)
+    fb.depth = abi.ImageDesc(dep.address, abi.FORMAT_D32_SFLOAT, 0, w, h, 1, 1, 1, 0)
+    area = abi.Rect2D(abi.Offset2D(8, 4), abi.Extent2D(50, 20))
+    q.cmd_begin_render_pass(fb, area, (0.25, 0.5, 0.75, 1.0), 0.5)
+    with pytest.raises(host.KazanError):
+        q.cmd_begin_render_pass(fb, area, (0, 0, 0, 0), None)
+    q.cmd_end_render_pass()
+    with pytest.raises(host.KazanError):
+        q.cmd_end_render_pass()
+    q.wait_idle()
+    c = img.download().view(np.uint32).reshape(h, w)
+    d = dep.download().view(np.float32).reshape(h, w)
+    inside = np.zeros((h, w), dtype=bool)
+    inside[4:24, 8:58] = True
+    assert np.all(c[inside] == 0xFFBF8040) and np.all(c[~inside] == 0xA5A5A5A5)
+    assert np.all(d[inside] == 0.5) and np.all(dep.download().view(np.uint32).reshape(h, w)[~inside] == 0x11111111)
+    # LOAD: nothing is written; a band cuts the cleared rows
+    q.cmd_begin_render_pass(fb, area, None, None)
+    q.cmd_end_render_pass()
+    fb.band_y0, fb.band_y1 = 16, 32
+    q.cmd_begin_render_pass(fb, area, (1.0, 1.0, 1.0, 1.0), None)
+    q.cmd_fill_buffer(dep.address, w * h * 4, 0, 16, 0)  # any other command performs the pending clear first
+    q.wait_idle()
+    c2 = img.download().view(np.uint32).reshape(h, w)
+    band = np.zeros((h, w), dtype=bool)
+    band[16:24, 8:58] = True
+    assert np.all(c2[band] == 0xFFFFFFFF) and np.array_equal(c2[~band], c[~band])
+    q.cmd_end_render_pass()
+    gpu.release()
+
+
 def test_binned_and_overflow_paths_were_exercised(gpu):
     sc = next(s for s in SCENES if s.name == "overflow_4500_tris_one_tile")
     _, _, st = sc.run_gpu(gpu)

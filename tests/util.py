@@ -177,11 +177,45 @@ class Scene:
         depth.view(np.float32)[:] = self.clear_depth
         return color, depth
 
-    def run_oracle(self, threads: int = 0):
+    def render_area(self):
+        """The draw's clip rectangle without the band (scissor x viewport x framebuffer), as a render area: what a render pass
+        around this one draw would name so that the draw can take its LOAD_OP_CLEAR over."""
+        f = np.float32
+        vx0, vx1 = f(self.viewport.x), f(self.viewport.x) + f(self.viewport.width)
+        vy0, vy1 = sorted((f(self.viewport.y), f(self.viewport.y) + f(self.viewport.height)))
+        x0 = max(0, self.scissor.offset.x, int(np.ceil(vx0 - f(0.5))))
+        y0 = max(0, self.scissor.offset.y, int(np.ceil(vy0 - f(0.5))))
+        x1 = min(self.width - 1, self.scissor.offset.x + self.scissor.extent.width - 1, int(np.floor(vx1 - f(0.5))))
+        y1 = min(self.height - 1, self.scissor.offset.y + self.scissor.extent.height - 1, int(np.floor(vy1 - f(0.5))))
+        return abi.Rect2D(abi.Offset2D(x0, y0), abi.Extent2D(max(0, x1 - x0 + 1), max(0, y1 - y0 + 1)))
+
+    def _initial_render_pass(self, area: abi.Rect2D):
+        """What the attachments hold after vkCmdBeginRenderPass with LOAD_OP_CLEAR on `area` (cut to the band) when they held
+        a byte pattern before: the oracle's vkCmdClearAttachments on that rectangle."""
+        lib = ob.load()
+        color, depth = self._initial()
+        color[:] = 0xA5
+        depth.view(np.uint32)[:] = 0x3E99999A  # 0.3
+        y0, y1 = area.offset.y, area.offset.y + area.extent.height
+        if self.band[1]:
+            y0, y1 = max(y0, self.band[0]), min(y1, self.band[1])
+        if area.extent.width and y1 > y0:
+            rect, n = arr(abi.ClearRect, [abi.ClearRect(abi.Rect2D(abi.Offset2D(area.offset.x, y0), abi.Extent2D(area.extent.width, y1 - y0)), 0, 1)])
+            fb = self._framebuffer(ob.ptr(color), ob.ptr(depth))
+            c = abi.ClearColorValue()
+            c.float32[:] = list(self.clear_color)
+            check(lib.kzo_clear_attachment(C.byref(fb.color), C.byref(c), n, rect))
+            if self.use_depth:
+                d = abi.ClearColorValue()
+                d.float32[0] = self.clear_depth
+                check(lib.kzo_clear_attachment(C.byref(fb.depth), C.byref(d), n, rect))
+        return color, depth
+
+    def run_oracle(self, threads: int = 0, render_pass: abi.Rect2D | None = None):
         lib = ob.load()
         if threads:
             lib.kzo_set_threads(threads)
-        color, depth = self._initial()
+        color, depth = self._initial() if render_pass is None else self._initial_render_pass(render_pass)
         fb = self._framebuffer(ob.ptr(color), ob.ptr(depth))
         vi = abi.VertexInput(ob.ptr(self.vertices), self.vertices.nbytes, self.stride, self.position_offset, self.pos_comps,
                              self.color_offset)
@@ -197,13 +231,18 @@ class Scene:
         check(code)
         return color, depth, stats
 
-    def run_gpu(self, ctx: GpuContext, compiled=None, vertex_program=None, push_constants: bytes = b""):
+    def run_gpu(self, ctx: GpuContext, compiled=None, vertex_program=None, push_constants: bytes = b"", render_pass: abi.Rect2D | None = None):
         """compiled: {fragment program enum: backend.FragmentProgram} — the draw then runs the compiled form of the scene's
         built-in fragment program (state.fragment_program = KZN_FS_COMPILED, the program bound to the queue, the frame's
         1/width and 1/height as push constants, which is what fs_orbit.kazan-ir reads).
         vertex_program: a backend.VertexProgram — the draw runs it as its vertex stage (state.vertex_program = KZN_VS_COMPILED)
-        with `push_constants`; the scene's vertices are then the shader's input block, one per stride."""
+        with `push_constants`; the scene's vertices are then the shader's input block, one per stride.
+        render_pass: the draw runs inside vkCmdBeginRenderPass(renderArea = render_pass, LOAD_OP_CLEAR) .. vkCmdEndRenderPass
+        on attachments that hold a byte pattern (compare with run_oracle(render_pass=...))."""
         color0, depth0 = self._initial()
+        if render_pass is not None:
+            color0[:] = 0xA5
+            depth0.view(np.uint32)[:] = 0x3E99999A
         cbuf = ctx.buffer(color0.nbytes, color0)
         dbuf = ctx.buffer(depth0.nbytes, depth0)
         vbuf = ctx.buffer(self.vertices.nbytes, self.vertices)
@@ -225,12 +264,16 @@ class Scene:
             q.cmd_push_constants(np.array([np.float32(1.0) / np.float32(self.width), np.float32(1.0) / np.float32(self.height)],
                                           dtype=np.float32).tobytes())
         q.set_draw_statistics(sbuf.address)
+        ibuf = ctx.buffer(self.indices.nbytes, self.indices) if self.indices is not None else None
+        if render_pass is not None:  # (after the uploads: any other command on the queue performs the pending clear)
+            q.cmd_begin_render_pass(fb, render_pass, self.clear_color, self.clear_depth if self.use_depth else None)
         if self.indices is not None:
-            ibuf = ctx.buffer(self.indices.nbytes, self.indices)
             q.cmd_draw_indexed(state, fb, self.viewport, self.scissor, vi, ibuf.address, self.indices.nbytes,
                                self.index_type, self.count, self.instances, self.first, self.vertex_offset, 0)
         else:
             q.cmd_draw(state, fb, self.viewport, self.scissor, vi, self.count, self.instances, self.first, 0)
+        if render_pass is not None:
+            q.cmd_end_render_pass()
         q.set_draw_statistics(0)
         if compiled is not None:
             q.cmd_bind_fragment_program(None)
