@@ -158,6 +158,11 @@ struct DrawParams {
     // what the program reads (bit 0: it needs interpolated inputs or the z / w of frag_coord, so no coverage shortcut applies)
     uint32_t fs_flags;
     uint32_t rows_first;  // setup: decide on y before x, z and the colours are fetched (the clip rectangle keeps under half of the viewport's rows)
+    // bands of split frames (rows_first, one instance, many triangles): band_prefilter_kernel looks at the rows of every
+    // triangle first — index and y / w fetches only, no shared memory, full occupancy — and leaves one byte per block of 256
+    // triangles: 0 = none of them can touch the band's rows.  setup_kernel and bin_fill_kernel skip those blocks (nothing is
+    // written for their triangles, not even the packed boxes); null: no prefilter ran.
+    const uint8_t* block_flags;
     // clipped primitives of binned draws (R3): the first triangle of the clipped polygon takes the primitive's own record, the
     // others ("extra" records, shared by all instances) follow the draw's records at tris / boxes [total_tris + k]
     uint32_t* clip_bits;    // [tris_per_instance / 32] bit t: primitive t has extra records (zeroed with the tile counters)
@@ -288,6 +293,35 @@ __device__ __forceinline__ const float* vertex_position(const DrawParams& p, lon
 
 // `slow`: the triangle has a vertex behind w = 0 or outside the guard band (or a coordinate that is not finite): it is
 // clipped (clip_primitive) or discarded, R3 — false is returned and nothing else is decided here.
+// the snapped window y of one vertex (R1, R2) and 1 / w; y_ok goes false for a vertex behind w = 0 or outside the guard band (R3)
+__device__ __forceinline__ int32_t vertex_row(const DrawParams& p, const float* pos, float& iw, bool& y_ok) {
+    const float y = __ldg(pos + 1);
+    iw = 1.0f;  // positions without a w component: w = 1, and 1.0f / 1.0f needs no division
+    if (p.pos_comps == 4) {
+        const float w = __ldg(pos + 3);
+        iw = 1.0f / w;
+        if (!(w > 0.0f) || !finite_f(iw)) y_ok = false;  // R3
+    }
+    const float yf = fmaf(p.hh, y * iw, p.oy);
+    if (!(fabsf(yf) <= kGuardBand)) y_ok = false;  // (false for NaN and infinity too)
+    return y_ok ? __float2int_rn(yf * 16.0f) : 0;  // R2
+}
+
+// true: triangle t certainly produces no fragments because its rows miss the clip rectangle — exactly the triangles
+// make_compact_t<true> ends at its first test (not `slow`, box empty); same arithmetic, nothing else fetched
+__device__ __forceinline__ bool rows_miss(const DrawParams& p, uint32_t t) {
+    bool y_ok = true;
+    int32_t Y[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float iw;
+        Y[k] = vertex_row(p, vertex_position(p, triangle_vertex(p, t, k)), iw, y_ok);
+    }
+    if (!y_ok) return false;
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    return max((minY - 8 + 15) >> 4, p.cy0) > min((maxY - 8) >> 4, p.cy1);
+}
+
 template <bool ROWS_FIRST>
 __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow) {
     box = make_int4(1, 0, 1, 0);  // minx maxx miny maxy
@@ -304,15 +338,8 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
             x = __ldg(pos[k]);
             z = __ldg(pos[k] + 2);
         }
-        const float y = __ldg(pos[k] + 1);
-        float iw = 1.0f;  // positions without a w component: w = 1, and 1.0f / 1.0f needs no division
-        if (p.pos_comps == 4) {
-            const float w = __ldg(pos[k] + 3);
-            iw = 1.0f / w;
-            if (!(w > 0.0f) || !finite_f(iw)) y_ok = false;  // R3
-        }
-        const float yf = fmaf(p.hh, y * iw, p.oy);
-        if (!(fabsf(yf) <= kGuardBand)) y_ok = false;  // (false for NaN and infinity too)
+        float iw;
+        const int32_t Yk = vertex_row(p, pos[k], iw, y_ok);
         if (!ROWS_FIRST) {
             const float xf = fmaf(p.hw, x * iw, p.ox);
             const float zf = fmaf(p.dz, z * iw, p.zmin_vp);
@@ -320,7 +347,7 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
             r.X[k] = y_ok && x_ok ? __float2int_rn(xf * 16.0f) : 0;  // R2
             r.z[k] = zf;
         }
-        r.Y[k] = y_ok ? __float2int_rn(yf * 16.0f) : 0;  // R2
+        r.Y[k] = Yk;
         r.iw[k] = iw;
     }
     bool ok = true;
@@ -606,13 +633,21 @@ __device__ __forceinline__ void clip_binned(const DrawParams& p, uint32_t t, uin
     if (!any_fragments && p.stats) atomicAdd(&p.stats[1], (unsigned long long)n_inst);
 }
 
+// setup of one block of 256 triangles (block `blk` of the draw) by one CTA
 template <bool BINNED>
-__global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
-    kzn_pdl_wait();
+__device__ __forceinline__ void setup_block(const DrawParams& p, const uint32_t blk) {
     constexpr int kQuads = BINNED ? (int)(sizeof(TriRecC) / 16) : (int)(sizeof(TriRec) / 16);
-    const uint32_t t_raw = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t t_raw = blk * 256u + threadIdx.x;
     if (t_raw == 0) p.work_counter[BINNED ? 2 : 0] = 0u;  // the work dispenser of raster_kernel / raster_direct_kernel
     const bool in_range = t_raw < p.tris_per_instance;
+    if (BINNED && p.block_flags && !p.block_flags[blk]) {  // band_prefilter_kernel: none of my 256 triangles touches the band's rows
+        if (p.stats && threadIdx.x == 0) {
+            const unsigned long long n = (unsigned long long)min(256u, p.tris_per_instance - blk * 256u) * p.instances;
+            atomicAdd(&p.stats[0], n);
+            atomicAdd(&p.stats[1], n);
+        }
+        return;
+    }
     const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
     // The CTA's 256 records are contiguous in memory: they are transposed through shared memory and written with
     // coalesced 16-byte stores (a thread writing its own record makes kQuads store instructions of 32 scattered
@@ -698,7 +733,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
         }
         keep[threadIdx.x] = keep_mine;
         __syncthreads();
-        const uint32_t block_first = blockIdx.x * 256u;
+        const uint32_t block_first = blk * 256u;
         for (uint32_t inst = 0; inst < n_inst; ++inst) {
             const size_t first_rec = (size_t)inst * p.tris_per_instance + block_first;
             uint4* dst = BINNED ? reinterpret_cast<uint4*>(reinterpret_cast<TriRecC*>(p.tris) + first_rec) : reinterpret_cast<uint4*>(p.tris + first_rec);
@@ -721,17 +756,25 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
     }
 }
 
+template <bool BINNED>
+__global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    setup_block<BINNED>(p, blockIdx.x);
+}
+
 // ---- binning --------------------------------------------------------------------------------------------------
 
 #ifndef KZN_FS_TEMPLATE
 // second binning pass: one thread per triangle record writes its id into every tile segment it overlaps
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
-    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-    bool valid = false;
-    if (t < p.total_tris) valid = tile_range(p, unpack_box(__ldg(&p.boxes[t])), tx0, tx1, ty0, ty1);
-    bin_emit<true>(p, valid, t << 3, 1u, tx0, tx1, ty0, ty1);  // list entries: record << 3 | fan index (0: the primitive's own record)
+    if (!p.block_flags || p.block_flags[blockIdx.x]) {  // (prefiltered draws have one instance: my block is setup's block)
+        const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+        bool valid = false;
+        if (t < p.total_tris) valid = tile_range(p, unpack_box(__ldg(&p.boxes[t])), tx0, tx1, ty0, ty1);
+        bin_emit<true>(p, valid, t << 3, 1u, tx0, tx1, ty0, ty1);  // list entries: record << 3 | fan index (0: the primitive's own record)
+    }
     // the extra triangles of clipped primitives (R3; rare): entry (instance's record of the primitive) << 3 | fan index, so
     // that sorting the entries puts them at the primitive's place
     const uint32_t n_extra = min(p.work_counter[4], p.clip_capacity);
@@ -748,6 +791,89 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ D
                     if (pos < p.bin_capacity) p.bin_entries[pos] = ((inst * p.tris_per_instance + (parent >> 3)) << 3) | (parent & 7u);
                 }
             }
+    }
+}
+
+// Before setup on a band of a split frame: which blocks of 256 triangles have a triangle whose rows can touch the band.
+// Two passes.  band_code_kernel, one thread per vertex of the vertex buffer (coalesced): bit 0 — the vertex lies above the
+// band's first sample row, bit 1 — below its last (0 for a vertex behind w = 0 or outside the guard band: nothing is known).
+// band_prefilter_kernel, one thread per triangle: three indices and three bytes of the code table; a triangle whose vertices
+// share a bit cannot touch the band (conservative: setup_kernel makes the exact test again for the blocks that stay).
+// Against fetching y at the vertex stride per triangle (every 32-byte sector of the vertex buffer through the L1 three times
+// over) the table is 1 byte per vertex and stays in the L1 / L2.
+__global__ void __launch_bounds__(256) band_code_kernel(const __grid_constant__ DrawParams p, uint8_t* __restrict__ codes, uint32_t n_codes) {
+    kzn_pdl_wait();
+    const uint32_t v = blockIdx.x * 256u + threadIdx.x;
+    if (v > n_codes) return;  // codes[n_codes]: the vertex an out-of-range index reads (robust fetch)
+    bool y_ok = true;
+    float iw;
+    const int32_t Y = vertex_row(p, vertex_position(p, v < n_codes ? (long long)v : -1ll), iw, y_ok);
+    uint32_t c = 0;
+    if (y_ok) c = (((Y - 8) >> 4) < p.cy0 ? 1u : 0u) | (((Y - 8 + 15) >> 4) > p.cy1 ? 2u : 0u);
+    codes[v] = (uint8_t)c;
+}
+
+__global__ void __launch_bounds__(256) band_prefilter_kernel(const __grid_constant__ DrawParams p, uint8_t* __restrict__ flags,
+                                                              const uint8_t* __restrict__ codes, uint32_t n_codes) {
+    kzn_pdl_wait();
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    bool live = false;
+    if (t < p.tris_per_instance) {
+        if (codes) {
+            uint32_t c = 3u;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned long long v = (unsigned long long)triangle_vertex(p, t, k);
+                c &= __ldg(codes + (v < n_codes ? v : (unsigned long long)n_codes));
+            }
+            live = c == 0u;
+        } else {
+            live = !rows_miss(p, t);
+        }
+    }
+    const int any = __syncthreads_or(live);
+    if (threadIdx.x == 0) flags[blockIdx.x] = (uint8_t)(any != 0);
+}
+
+// The same for the common case — TRIANGLE_LIST, 32-bit indices, the first index 16-byte aligned, a code table: a thread
+// takes four triangles (three 16-byte index loads, twelve code bytes in flight at once), a warp half a block, a CTA of 256
+// threads four blocks.  The one-triangle-per-thread form waits for one index -> code round trip at a time (25 us on a band
+// of the 4M-triangle frame, reading 50 MB).
+__global__ void __launch_bounds__(256) band_prefilter4_kernel(const __grid_constant__ DrawParams p, uint8_t* __restrict__ flags,
+                                                               const uint8_t* __restrict__ codes, uint32_t n_codes) {
+    kzn_pdl_wait();
+    __shared__ uint32_t warp_live[8];
+    const uint32_t q = blockIdx.x * 256u + threadIdx.x;  // triangles 4q .. 4q + 3
+    const uint32_t n = p.tris_per_instance;
+    bool live = false;
+    if (4u * q < n) {
+        const uint4* idx = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.index_base) + p.first) + 3ull * q;
+        uint32_t v[12];
+        if (4u * q + 3u < n) {
+            const uint4 a = __ldg(idx), b = __ldg(idx + 1), c = __ldg(idx + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+        } else {  // the draw's last triangles: index by index (nothing beyond the index range is read)
+            const uint32_t* i32 = reinterpret_cast<const uint32_t*>(idx);
+#pragma unroll
+            for (uint32_t k = 0; k < 12u; ++k) v[k] = 12u * q + k < 3u * n ? __ldg(i32 + k) : 0u;
+        }
+        uint32_t c[12];
+#pragma unroll
+        for (uint32_t k = 0; k < 12u; ++k) {
+            const unsigned long long vi = (unsigned long long)((long long)v[k] + p.vertex_offset);
+            c[k] = __ldg(codes + (vi < n_codes ? vi : (unsigned long long)n_codes));
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j)
+            if (4u * q + j < n && (c[3 * j] & c[3 * j + 1] & c[3 * j + 2]) == 0u) live = true;
+    }
+    // a warp holds 128 triangles = half a block: block j of this CTA = warps 2j and 2j + 1
+    const uint32_t ballot = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31u) == 0) warp_live[threadIdx.x >> 5] = ballot;
+    __syncthreads();
+    if (threadIdx.x < 4u) {
+        const uint32_t blk = blockIdx.x * 4u + threadIdx.x;
+        if (blk * 256u < n) flags[blk] = (uint8_t)((warp_live[2 * threadIdx.x] | warp_live[2 * threadIdx.x + 1]) != 0u);
     }
 }
 
@@ -2226,6 +2352,7 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
                                 if (j > link >> 29) continue;
                                 b = __ldg(&p.boxes[p.total_tris + (link & 0x1fffffffu) + j - 1u]);
                             } else {
+                                if (p.block_flags && !p.block_flags[rec >> 8]) continue;  // (prefiltered block: its boxes were never written)
                                 b = __ldg(&p.boxes[rec]);
                             }
                             if (brick_mask_of(b, tile_px0, tile_py0) >> brick & 1u) hits |= 1u << k;
@@ -2369,6 +2496,10 @@ struct KznRasterScratch {
     size_t parent_capacity = 0;
     uint32_t* clip_list = nullptr;
     size_t list_capacity = 0;
+    uint8_t* block_flags = nullptr;  // band_prefilter_kernel: one byte per block of 256 triangles
+    size_t flag_capacity = 0;
+    uint8_t* band_codes = nullptr;   // band_code_kernel: one byte per vertex (+ 1)
+    size_t code_capacity = 0;
     unsigned char* vs_out = nullptr;  // what a compiled vertex stage writes and setup reads (KZN_VS_COMPILED)
     size_t vs_capacity = 0;
     bool attrs_set = false;
@@ -2403,6 +2534,8 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->clip_link);
     cudaFree(s->clip_parent);
     cudaFree(s->clip_list);
+    cudaFree(s->block_flags);
+    cudaFree(s->band_codes);
     cudaFree(s->vs_out);
     delete s;
 }
@@ -2529,6 +2662,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t per_instance, size_t 
         if ((r = grow(q, &s->clip_link, &s->link_capacity, per_instance))) return r;
         if ((r = grow(q, &s->clip_parent, &s->parent_capacity, extras))) return r;
         if ((r = grow(q, &s->clip_list, &s->list_capacity, per_instance))) return r;
+        if ((r = grow(q, &s->block_flags, &s->flag_capacity, (per_instance + 255) / 256))) return r;
     }
     if (!s->counters) {  // the dispensers and the allocator of extra records start at zero and are handed back at zero by their users
         if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)32))) return r;
@@ -2755,6 +2889,30 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, (2 * tiles + (ntri + 31) / 32) * sizeof(uint32_t), q->stream));
     p.fused_setup = !p.binned && total <= kFusedMax;
+    {
+        static const long min_tris = [] { const char* e = getenv("KZN_BAND_PREFILTER_MIN"); return e ? atol(e) : 65536l; }();  // (negative: never)
+        static const bool use_codes = [] { const char* e = getenv("KZN_BAND_CODES"); return !(e && e[0] == '0'); }();
+        if (p.binned && p.rows_first && instance_count == 1 && min_tris >= 0 && (long)ntri >= min_tris) {
+            // the code table pays when the vertex buffer is not much larger than what the draw can name (an indexed mesh)
+            const bool codes = use_codes && index_base && p.pos_vertices <= 2ull * ntri && p.pos_vertices < 0xffffffffull && !q->recording;
+            uint32_t n_codes = 0;
+            if (codes) {
+                n_codes = (uint32_t)p.pos_vertices;
+                if ((r = grow(q, &s->band_codes, &s->code_capacity, (size_t)n_codes + 1))) return r;
+                kzn_launch_pdl(band_code_kernel, dim3(n_codes / 256u + 1u), dim3(256), 0, q->stream, p, s->band_codes, n_codes);
+                if ((r = kzn_launched(q, "band_code_kernel"))) return r;
+            }
+            static const bool four = [] { const char* e = getenv("KZN_BAND_PREFILTER4"); return !(e && e[0] == '0'); }();
+            if (four && codes && topo == KZN_TOPOLOGY_TRIANGLE_LIST && index_type == KZN_INDEX_TYPE_UINT32 && (index_base + 4ull * first) % 16 == 0)
+                kzn_launch_pdl(band_prefilter4_kernel, dim3((uint32_t)((ntri + 1023) / 1024)), dim3(256), 0, q->stream, p, s->block_flags,
+                               (const uint8_t*)s->band_codes, n_codes);
+            else
+                kzn_launch_pdl(band_prefilter_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p, s->block_flags,
+                               codes ? (const uint8_t*)s->band_codes : (const uint8_t*)nullptr, n_codes);
+            if ((r = kzn_launched(q, "band_prefilter_kernel"))) return r;
+            p.block_flags = s->block_flags;
+        }
+    }
     if (!p.fused_setup) {
         if (p.binned) launch_draw_kernel(setup_kernel<true>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         else launch_draw_kernel(setup_kernel<false>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);

@@ -344,4 +344,17 @@ def clip_scenes(rng) -> list[Scene]:
             many += [[x0, y0, 0.5, 1.0, *col], [x0 + 0.9, y0 + 0.1, 0.5, 1.0, *col], [x0 + 0.2, y0 + 0.8, 0.5, 1.0, *col]]
     scenes.append(Scene("clip_overflow_4400_tris_one_tile", 40, 24, np.array(many, dtype=np.float32), pos_comps=4, color_offset=16,
                         state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # bands of draws large enough for band_prefilter_kernel (>= 65536 triangles, the band under half of the viewport's rows):
+    # blocks of 256 triangles that miss the band are skipped by setup and binning.  A plain mesh; a floor through the eye plane
+    # (clipped primitives inside and outside the band); a frame so small that every tile's list overflows (the raster kernel
+    # then walks all triangles of the draw, skipped blocks included)
+    v, i = util.grid_mesh(256, 160, 9)
+    scenes.append(Scene("band_prefilter_mesh_81920", 512, 320, v, i, band=(112, 176), use_depth=True,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS, 1), blend=util.ALPHA_BLEND)))
+    fv, fi = _ground_plane(rng, 256, 140, 8.0, 60.0, -6.0)
+    scenes.append(Scene("band_prefilter_clip_floor_71680", 320, 200, fv, fi, pos_comps=4, color_offset=16, band=(128, 176), use_depth=True,
+                        state=pipeline_state(depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND)))
+    va = v.copy()
+    va[:, 3:] *= 0.05
+    scenes.append(Scene("band_prefilter_overflow_tiles", 128, 80, va, i, band=(32, 48), state=pipeline_state(blend=util.ADDITIVE_BLEND)))
     return scenes

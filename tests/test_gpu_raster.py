@@ -125,6 +125,22 @@ def test_binned_and_overflow_paths_were_exercised(gpu):
     assert st.bin_entries > 0 and st.bin_overflow_tiles == 0
 
 
+def test_band_prefilter_ran_on_the_large_band_scenes(gpu):
+    """band_code_kernel + band_prefilter_kernel: two more launches than a binned draw has otherwise (setup, scan, fill, sort,
+    raster), on draws of >= 65536 triangles whose band keeps under half of the viewport's rows — and only there."""
+    by_name = {s.name: s for s in SCENES}
+    q = gpu.queue
+    for name, want in (("band_prefilter_mesh_81920", 7), ("band_prefilter_clip_floor_71680", 7), ("band_prefilter_overflow_tiles", 7),
+                       ("clip_floor_2400_band_96_144", 5), ("mesh_200x100_depth_blend", 5)):
+        n0 = q.launch_count
+        _, _, st = by_name[name].run_gpu(gpu)
+        assert q.launch_count - n0 == want, name
+        if name == "band_prefilter_overflow_tiles":
+            assert st.bin_overflow_tiles > 0
+        if name == "band_prefilter_clip_floor_71680":
+            assert st.triangles_clipped > 0
+
+
 def test_clipped_primitives_took_every_path(gpu):
     """R3 on the GPU: the fused direct path (2 triangles), the direct path behind setup_kernel, the binned path with extra
     records (also under instancing and on a band), and the walk of all triangles for a tile whose list overflowed"""

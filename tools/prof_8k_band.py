@@ -13,6 +13,9 @@ with torch.cuda.stream(s):
     fb.band_y0, fb.band_y1 = band
     st = bench.mesh_state(abi); vp = abi.Viewport(0, 0, W, H, 0, 1); sc = abi.Rect2D(abi.Offset2D(0, 0), abi.Extent2D(W, H))
     vi = abi.VertexInput(d_verts.data_ptr(), verts.nbytes, 28, 0, 3, 12)
-    def frame(k): q.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+    def frame(k):  # the band's frame as bench.py's split_frame_extra issues it: a render pass that clears the band + the draw
+        q.cmd_begin_render_pass(fb, None, (0, 0, 0, 0), 1.0)
+        q.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
+        q.cmd_end_render_pass()
     ms = bench.time_region(torch, s, frame, 10, 3) / 10
 print("band", band, "ms per draw", ms)
