@@ -68,7 +68,8 @@ constexpr uint32_t kFusedMax = 5;        // direct draws of at most this many tr
 // work_counter slots: 0, 1 block dispenser of the direct kernel and its leavers; 2 brick dispenser of raster_kernel; 3 records
 // of a direct draw; 4 extra records allocated by this draw's clipper (zeroed again by its sort kernel); 5 their count for
 // raster_kernel; 6 primitives setup_kernel left to the clipper in bin_scan_kernel (zeroed by the sort kernel); 7 CTAs of
-// bin_scan_kernel that are done
+// bin_scan_kernel that are done; 8, 9 band_prefilter_kernel's blocks with work and their triangles (zeroed by the sort kernel);
+// 16 .. 19 the vertex (0, 0, 0, 1) that out-of-range indices read
 constexpr uint32_t kDirectMax = 256;     // draws with at most this many triangles skip binning
 // how a kernel instantiation treats the destination colour (template parameter NEED_DST)
 constexpr int kDstNone = 0;       // no blending, all channels written: the destination is never read
@@ -163,6 +164,10 @@ struct DrawParams {
     // triangles: 0 = none of them can touch the band's rows.  setup_kernel and bin_fill_kernel skip those blocks (nothing is
     // written for their triangles, not even the packed boxes); null: no prefilter ran.
     const uint8_t* block_flags;
+    // ... and the list of the blocks that stay (work_counter[8] of them, any order; work_counter[9] = their triangles): CTA i of
+    // setup_kernel / bin_fill_kernel takes block live_blocks[i], the CTAs beyond the list exit — after the ones with work were
+    // started, whatever part of the index range the band's triangles lie in
+    const uint32_t* live_blocks;
     // clipped primitives of binned draws (R3): the first triangle of the clipped polygon takes the primitive's own record, the
     // others ("extra" records, shared by all instances) follow the draw's records at tris / boxes [total_tris + k]
     uint32_t* clip_bits;    // [tris_per_instance / 32] bit t: primitive t has extra records (zeroed with the tile counters)
@@ -638,16 +643,7 @@ template <bool BINNED>
 __device__ __forceinline__ void setup_block(const DrawParams& p, const uint32_t blk) {
     constexpr int kQuads = BINNED ? (int)(sizeof(TriRecC) / 16) : (int)(sizeof(TriRec) / 16);
     const uint32_t t_raw = blk * 256u + threadIdx.x;
-    if (t_raw == 0) p.work_counter[BINNED ? 2 : 0] = 0u;  // the work dispenser of raster_kernel / raster_direct_kernel
     const bool in_range = t_raw < p.tris_per_instance;
-    if (BINNED && p.block_flags && !p.block_flags[blk]) {  // band_prefilter_kernel: none of my 256 triangles touches the band's rows
-        if (p.stats && threadIdx.x == 0) {
-            const unsigned long long n = (unsigned long long)min(256u, p.tris_per_instance - blk * 256u) * p.instances;
-            atomicAdd(&p.stats[0], n);
-            atomicAdd(&p.stats[1], n);
-        }
-        return;
-    }
     const uint32_t t = in_range ? t_raw : 0u;  // out-of-range lanes redo triangle 0 and write nothing (they stay for the warp-wide binning)
     // The CTA's 256 records are contiguous in memory: they are transposed through shared memory and written with
     // coalesced 16-byte stores (a thread writing its own record makes kQuads store instructions of 32 scattered
@@ -759,7 +755,19 @@ __device__ __forceinline__ void setup_block(const DrawParams& p, const uint32_t 
 template <bool BINNED>
 __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
-    setup_block<BINNED>(p, blockIdx.x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.work_counter[BINNED ? 2 : 0] = 0u;  // the work dispenser of raster_kernel / raster_direct_kernel
+    uint32_t blk = blockIdx.x;
+    if (BINNED && p.live_blocks) {  // band_prefilter_kernel ran: only the listed blocks have a triangle that can touch the band's rows
+        const uint32_t n_live = p.work_counter[8];
+        if (p.stats && blockIdx.x == 0 && threadIdx.x == 0) {  // the triangles of all other blocks: seen, no fragments
+            const unsigned long long n = (unsigned long long)(p.tris_per_instance - p.work_counter[9]) * p.instances;
+            atomicAdd(&p.stats[0], n);
+            atomicAdd(&p.stats[1], n);
+        }
+        if (blockIdx.x >= n_live) return;
+        blk = p.live_blocks[blockIdx.x];
+    }
+    setup_block<BINNED>(p, blk);
 }
 
 // ---- binning --------------------------------------------------------------------------------------------------
@@ -769,8 +777,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-    if (!p.block_flags || p.block_flags[blockIdx.x]) {  // (prefiltered draws have one instance: my block is setup's block)
-        const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (!p.live_blocks || blockIdx.x < p.work_counter[8]) {  // (prefiltered draws have one instance: my block is one of setup's)
+        const uint32_t t = (p.live_blocks ? p.live_blocks[blockIdx.x] : blockIdx.x) * 256u + threadIdx.x;
         bool valid = false;
         if (t < p.total_tris) valid = tile_range(p, unpack_box(__ldg(&p.boxes[t])), tx0, tx1, ty0, ty1);
         bin_emit<true>(p, valid, t << 3, 1u, tx0, tx1, ty0, ty1);  // list entries: record << 3 | fan index (0: the primitive's own record)
@@ -814,7 +822,7 @@ __global__ void __launch_bounds__(256) band_code_kernel(const __grid_constant__ 
 }
 
 __global__ void __launch_bounds__(256) band_prefilter_kernel(const __grid_constant__ DrawParams p, uint8_t* __restrict__ flags,
-                                                              const uint8_t* __restrict__ codes, uint32_t n_codes) {
+                                                              uint32_t* __restrict__ list, const uint8_t* __restrict__ codes, uint32_t n_codes) {
     kzn_pdl_wait();
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     bool live = false;
@@ -832,7 +840,13 @@ __global__ void __launch_bounds__(256) band_prefilter_kernel(const __grid_consta
         }
     }
     const int any = __syncthreads_or(live);
-    if (threadIdx.x == 0) flags[blockIdx.x] = (uint8_t)(any != 0);
+    if (threadIdx.x == 0) {
+        flags[blockIdx.x] = (uint8_t)(any != 0);
+        if (any) {
+            list[atomicAdd(p.work_counter + 8, 1u)] = blockIdx.x;
+            atomicAdd(p.work_counter + 9, min(256u, p.tris_per_instance - blockIdx.x * 256u));
+        }
+    }
 }
 
 // The same for the common case — TRIANGLE_LIST, 32-bit indices, the first index 16-byte aligned, a code table: a thread
@@ -840,7 +854,7 @@ __global__ void __launch_bounds__(256) band_prefilter_kernel(const __grid_consta
 // threads four blocks.  The one-triangle-per-thread form waits for one index -> code round trip at a time (25 us on a band
 // of the 4M-triangle frame, reading 50 MB).
 __global__ void __launch_bounds__(256) band_prefilter4_kernel(const __grid_constant__ DrawParams p, uint8_t* __restrict__ flags,
-                                                               const uint8_t* __restrict__ codes, uint32_t n_codes) {
+                                                               uint32_t* __restrict__ list, const uint8_t* __restrict__ codes, uint32_t n_codes) {
     kzn_pdl_wait();
     __shared__ uint32_t warp_live[8];
     const uint32_t q = blockIdx.x * 256u + threadIdx.x;  // triangles 4q .. 4q + 3
@@ -873,7 +887,14 @@ __global__ void __launch_bounds__(256) band_prefilter4_kernel(const __grid_const
     __syncthreads();
     if (threadIdx.x < 4u) {
         const uint32_t blk = blockIdx.x * 4u + threadIdx.x;
-        if (blk * 256u < n) flags[blk] = (uint8_t)((warp_live[2 * threadIdx.x] | warp_live[2 * threadIdx.x + 1]) != 0u);
+        if (blk * 256u < n) {
+            const bool any = (warp_live[2 * threadIdx.x] | warp_live[2 * threadIdx.x + 1]) != 0u;
+            flags[blk] = (uint8_t)any;
+            if (any) {
+                list[atomicAdd(p.work_counter + 8, 1u)] = blk;
+                atomicAdd(p.work_counter + 9, min(256u, n - blk * 256u));
+            }
+        }
     }
 }
 
@@ -2075,6 +2096,8 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __gr
         p.work_counter[5] = p.work_counter[4];
         p.work_counter[4] = 0u;
         p.work_counter[6] = 0u;
+        p.work_counter[8] = 0u;  // band_prefilter_kernel's list of blocks and their triangle count
+        p.work_counter[9] = 0u;
     }
     const uint32_t tile = blockIdx.x * kSortWarps + warp;
     if (tile >= p.tiles_x * p.tiles_y) return;
@@ -2192,6 +2215,8 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
         p.work_counter[5] = p.work_counter[4];
         p.work_counter[4] = 0u;
         p.work_counter[6] = 0u;
+        p.work_counter[8] = 0u;  // band_prefilter_kernel's list of blocks and their triangle count
+        p.work_counter[9] = 0u;
     }
     const int tile_px0 = (int)(p.tile_x0 + blockIdx.x) * kTileW, tile_py0 = (int)(p.tile_y0 + blockIdx.y) * kTileH;
     const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], list_len = end - beg;
@@ -2498,6 +2523,8 @@ struct KznRasterScratch {
     size_t list_capacity = 0;
     uint8_t* block_flags = nullptr;  // band_prefilter_kernel: one byte per block of 256 triangles
     size_t flag_capacity = 0;
+    uint32_t* live_blocks = nullptr;  // ... and the list of the blocks whose flag is set
+    size_t live_capacity = 0;
     uint8_t* band_codes = nullptr;   // band_code_kernel: one byte per vertex (+ 1)
     size_t code_capacity = 0;
     unsigned char* vs_out = nullptr;  // what a compiled vertex stage writes and setup reads (KZN_VS_COMPILED)
@@ -2536,6 +2563,7 @@ void kzn_raster_scratch_destroy(KznRasterScratch* s) {
     cudaFree(s->clip_list);
     cudaFree(s->block_flags);
     cudaFree(s->band_codes);
+    cudaFree(s->live_blocks);
     cudaFree(s->vs_out);
     delete s;
 }
@@ -2663,6 +2691,7 @@ KznResult ensure_scratch(KznQueue* q, size_t total, size_t per_instance, size_t 
         if ((r = grow(q, &s->clip_parent, &s->parent_capacity, extras))) return r;
         if ((r = grow(q, &s->clip_list, &s->list_capacity, per_instance))) return r;
         if ((r = grow(q, &s->block_flags, &s->flag_capacity, (per_instance + 255) / 256))) return r;
+        if ((r = grow(q, &s->live_blocks, &s->live_capacity, (per_instance + 255) / 256))) return r;
     }
     if (!s->counters) {  // the dispensers and the allocator of extra records start at zero and are handed back at zero by their users
         if ((r = grow(q, &s->counters, &s->counter_capacity, (size_t)32))) return r;
@@ -2905,12 +2934,13 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
             static const bool four = [] { const char* e = getenv("KZN_BAND_PREFILTER4"); return !(e && e[0] == '0'); }();
             if (four && codes && topo == KZN_TOPOLOGY_TRIANGLE_LIST && index_type == KZN_INDEX_TYPE_UINT32 && (index_base + 4ull * first) % 16 == 0)
                 kzn_launch_pdl(band_prefilter4_kernel, dim3((uint32_t)((ntri + 1023) / 1024)), dim3(256), 0, q->stream, p, s->block_flags,
-                               (const uint8_t*)s->band_codes, n_codes);
+                               s->live_blocks, (const uint8_t*)s->band_codes, n_codes);
             else
                 kzn_launch_pdl(band_prefilter_kernel, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p, s->block_flags,
-                               codes ? (const uint8_t*)s->band_codes : (const uint8_t*)nullptr, n_codes);
+                               s->live_blocks, codes ? (const uint8_t*)s->band_codes : (const uint8_t*)nullptr, n_codes);
             if ((r = kzn_launched(q, "band_prefilter_kernel"))) return r;
             p.block_flags = s->block_flags;
+            p.live_blocks = s->live_blocks;
         }
     }
     if (!p.fused_setup) {
