@@ -374,7 +374,7 @@ def mesh_state(abi):
 
 
 def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1080), seed=4, check_oracle=True, hbm_peak=None,
-               traffic_key="mesh_1M_1080p"):
+               traffic_key="mesh_1M_1080p", compare_separate_clears=True):
     """BASELINE configs[3]: 1M-triangle indexed mesh, D32 LESS + alpha blend, 1920x1080.  One frame = a render pass that
     clears colour and depth (LOAD_OP_CLEAR) + vkCmdDrawIndexed."""
     W, H = size
@@ -406,7 +406,7 @@ def mesh_extra(torch, abi, host, queue, stream, quads=(1000, 500), size=(1920, 1
         queue.cmd_draw_indexed(st, fb, vp, sc, vi, d_idx.data_ptr(), idx.nbytes, abi.INDEX_TYPE_UINT32, len(idx))
 
     reps = 20
-    ms_separate = time_region(torch, stream, frame_separate_clears, reps, 3) / reps
+    ms_separate = time_region(torch, stream, frame_separate_clears, reps, 3) / reps if compare_separate_clears else None
     color.fill_(0x5A); depth.fill_(0.25)  # the render pass must not depend on what the attachments held
     queue.set_draw_statistics(stats.data_ptr())
     frame(0)

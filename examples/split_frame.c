@@ -61,14 +61,18 @@ static int render(uint32_t gpus, uint32_t W, uint32_t H, const float* verts, uin
         CHECK(kzn_queue_upload(q, kzn_memory_device_address(imem[i]), idx, ibytes));
         KznFramebuffer fb;
         CHECK(kzn_split_frame_framebuffer(sf, i, &fb));
-        KznClearColorValue black = {{0, 0, 0, 0}};
-        KznClearDepthStencilValue far_plane = {1.0f, 0};
-        KznImageSubresourceRange color_range = {KZN_IMAGE_ASPECT_COLOR_BIT, 0, KZN_REMAINING_MIP_LEVELS, 0, KZN_REMAINING_ARRAY_LAYERS};
-        KznImageSubresourceRange depth_range = {KZN_IMAGE_ASPECT_DEPTH_BIT, 0, KZN_REMAINING_MIP_LEVELS, 0, KZN_REMAINING_ARRAY_LAYERS};
-        CHECK(kzn_cmd_clear_color_image(q, &fb.color, &black, 1, &color_range));
-        CHECK(kzn_cmd_clear_depth_stencil_image(q, &fb.depth, &far_plane, 1, &depth_range));
+        /* vkCmdBeginRenderPass with LOAD_OP_CLEAR on both attachments: the framebuffer names this rank's band, so only the
+         * band is cleared — and the draw takes the clear over (no clear kernels, no framebuffer read) */
+        KznRenderPassBegin rp;
+        memset(&rp, 0, sizeof rp);
+        rp.framebuffer = fb;
+        rp.render_area = sc;
+        rp.color_load_op = rp.depth_load_op = KZN_ATTACHMENT_LOAD_OP_CLEAR;
+        rp.clear_depth_stencil.depth = 1.0f; /* colour: 0, 0, 0, 0 */
+        CHECK(kzn_cmd_begin_render_pass(q, &rp));
         KznVertexInput vi = {kzn_memory_device_address(vmem[i]), vbytes, 28, 0, 3, 12};
         CHECK(kzn_cmd_draw_indexed(q, &st, &fb, &vp, &sc, &vi, kzn_memory_device_address(imem[i]), ibytes, KZN_INDEX_TYPE_UINT32, index_count, 1, 0, 0, 0));
+        CHECK(kzn_cmd_end_render_pass(q));
     }
     CHECK(kzn_split_frame_composite(sf)); /* the one exchange step: bands -> device 0 */
     CHECK(kzn_queue_download(kzn_split_frame_present_queue(sf), out, kzn_split_frame_present_address(sf), (uint64_t)W * H * 4));

@@ -764,8 +764,13 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
             atomicAdd(&p.stats[0], n);
             atomicAdd(&p.stats[1], n);
         }
-        if (blockIdx.x >= n_live) return;
-        blk = p.live_blocks[blockIdx.x];
+        // (a grid-stride loop over the list: the grid is capped, CTAs that only find the list's end cost a launch each —
+        // 13 000 of them on a band of the 4M-triangle frame were a third of this kernel's time)
+        for (uint32_t i = blockIdx.x; i < n_live; i += gridDim.x) {
+            if (i != blockIdx.x) __syncthreads();  // the previous block's staging area is free again
+            setup_block<BINNED>(p, p.live_blocks[i]);
+        }
+        return;
     }
     setup_block<BINNED>(p, blk);
 }
@@ -777,8 +782,10 @@ __global__ void __launch_bounds__(256) setup_kernel(const __grid_constant__ Draw
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ DrawParams p) {
     kzn_pdl_wait();
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-    if (!p.live_blocks || blockIdx.x < p.work_counter[8]) {  // (prefiltered draws have one instance: my block is one of setup's)
-        const uint32_t t = (p.live_blocks ? p.live_blocks[blockIdx.x] : blockIdx.x) * 256u + threadIdx.x;
+    // (prefiltered draws have one instance and a capped grid: the blocks of setup's list, grid-stride)
+    const uint32_t n_mine = p.live_blocks ? p.work_counter[8] : gridDim.x;
+    for (uint32_t i = blockIdx.x; i < n_mine; i += gridDim.x) {
+        const uint32_t t = (p.live_blocks ? p.live_blocks[i] : i) * 256u + threadIdx.x;
         bool valid = false;
         if (t < p.total_tris) valid = tile_range(p, unpack_box(__ldg(&p.boxes[t])), tx0, tx1, ty0, ty1);
         bin_emit<true>(p, valid, t << 3, 1u, tx0, tx1, ty0, ty1);  // list entries: record << 3 | fan index (0: the primitive's own record)
@@ -2918,6 +2925,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     }
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, (2 * tiles + (ntri + 31) / 32) * sizeof(uint32_t), q->stream));
     p.fused_setup = !p.binned && total <= kFusedMax;
+    uint32_t list_grid = 0;
     {
         static const long min_tris = [] { const char* e = getenv("KZN_BAND_PREFILTER_MIN"); return e ? atol(e) : 65536l; }();  // (negative: never)
         static const bool use_codes = [] { const char* e = getenv("KZN_BAND_CODES"); return !(e && e[0] == '0'); }();
@@ -2941,10 +2949,19 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
             if ((r = kzn_launched(q, "band_prefilter_kernel"))) return r;
             p.block_flags = s->block_flags;
             p.live_blocks = s->live_blocks;
+XX
+            // at least 8 per SM: too few make some CTAs loop while others have left, too many only find the list's end
+            static const double slack = [] { const char* e = getenv("KZN_BAND_LIST_SLACK"); const double v = e ? atof(e) : 2.5; return v > 0.0 ? v : 2.5; }();
+            const uint64_t blocks = (ntri + 255) / 256;
+            const double share = (double)(p.cy1 - p.cy0 + 1) / fabs((double)vp->height);
+            uint64_t want = (uint64_t)((double)blocks * share * slack) + 1, floor_ctas = (uint64_t)q->device->sm_count * 8;
+            if (want < floor_ctas) want = floor_ctas;
+            list_grid = (uint32_t)(blocks < want ? blocks : want);
         }
     }
     if (!p.fused_setup) {
-        if (p.binned) launch_draw_kernel(setup_kernel<true>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
+        // (after the band prefilter the grid is capped: the kernels loop over the list of blocks with work)
+        if (p.binned) launch_draw_kernel(setup_kernel<true>, dim3(p.live_blocks ? list_grid : (uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         else launch_draw_kernel(setup_kernel<false>, dim3((uint32_t)((ntri + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "setup_kernel"))) return r;
     }
@@ -2954,7 +2971,7 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
             launch_draw_kernel(bin_scan_kernel, dim3((uint32_t)(blocks < cap ? blocks : cap)), dim3(1024), 0, q->stream, p);
         }
         if ((r = kzn_launched(q, "bin_scan_kernel"))) return r;
-        launch_draw_kernel(bin_fill_kernel, dim3((uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
+        launch_draw_kernel(bin_fill_kernel, dim3(p.live_blocks ? list_grid : (uint32_t)((total + 255) / 256)), dim3(256), 0, q->stream, p);
         if ((r = kzn_launched(q, "bin_fill_kernel"))) return r;
         // few tiles with long lists: a CTA per tile; many tiles with short lists: a warp per tile (see the kernels).  The
         // length is estimated from the viewport (a band of a split frame sees 1 / N of the triangles in 1 / N of the tiles)

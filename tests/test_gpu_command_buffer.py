@@ -93,6 +93,36 @@ def test_recorded_draw_needs_reserved_scratch_and_matches_oracle(gpu):
     q.wait_idle()
     assert got_d.tobytes() == want_d.tobytes() and got_c.tobytes() == want_c.tobytes()
     cb.destroy()
+    # the same frame as a recorded render pass: vkCmdBeginRenderPass (LOAD_OP_CLEAR) .. draw .. vkCmdEndRenderPass on
+    # attachments that hold garbage; the draw takes the clear over (5 launches as for the draw alone), two draws in one pass
+    # (the second one loads what the first left), and a pass without a draw (the clear is recorded at vkCmdEndRenderPass)
+    garbage = np.full(color0.nbytes, 0xC3, dtype=np.uint8)
+    for m in mem[:2]:
+        q.upload(m.address, garbage.ctypes.data, garbage.nbytes)
+    with q.record() as cb:
+        q.cmd_begin_render_pass(fb, None, scene.clear_color, scene.clear_depth)
+        draw()
+        q.cmd_end_render_pass()
+    assert cb.launch_count == 5
+    for rep in range(2):
+        q.submit([cb])
+        q.download(got_c.ctypes.data, mem[0].address, got_c.nbytes)
+        q.download(got_d.ctypes.data, mem[1].address, got_d.nbytes)
+        q.wait_idle()
+        assert got_d.tobytes() == want_d.tobytes() and got_c.tobytes() == want_c.tobytes(), f"recorded render pass, replay {rep}"
+        for m in mem[:2]:
+            q.upload(m.address, garbage.ctypes.data, garbage.nbytes)
+    cb.destroy()
+    with q.record() as cb:
+        q.cmd_begin_render_pass(fb, None, scene.clear_color, scene.clear_depth)
+        q.cmd_end_render_pass()
+    assert cb.launch_count in (1, 2)  # (two fills of disjoint memory: one merged launch)
+    q.submit([cb])
+    q.download(got_c.ctypes.data, mem[0].address, got_c.nbytes)
+    q.download(got_d.ctypes.data, mem[1].address, got_d.nbytes)
+    q.wait_idle()
+    assert got_c.tobytes() == color0.tobytes() and got_d.tobytes() == depth0.tobytes()
+    cb.destroy()
     for m in mem:
         m.free()
     q.destroy(); dev.destroy()

@@ -26,4 +26,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
 # DRAM traffic of every kernel of the two mesh frames (roofline.traffic of extra.mesh_1M_1080p / split_frame_8k)
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 14 --csv --log-file $OUT/traffic_mesh.csv python tools/prof_mesh.py > $OUT/ncu_traffic_mesh.log 2>&1
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 14 --csv --log-file $OUT/traffic_8k.csv python tools/prof_8k.py > $OUT/ncu_traffic_8k.log 2>&1
+# the same with the caches as the stream leaves them (what roofline.traffic quotes): frames are 5 kernels now (the clears happen inside raster_kernel)
+timeout 900 ncu --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 15 --csv --log-file $OUT/traffic_mesh_in_stream.csv python tools/prof_mesh.py > $OUT/ncu_traffic_mesh2.log 2>&1
+timeout 900 ncu --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 40 -c 15 --csv --log-file $OUT/traffic_8k_in_stream.csv python tools/prof_8k.py > $OUT/ncu_traffic_8k2.log 2>&1
 ls -la $OUT
