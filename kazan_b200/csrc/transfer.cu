@@ -1327,6 +1327,15 @@ KznResult kzn_cmd_blit_image(KznQueue* queue, const KznImageDesc* src, const Kzn
                 float wf = blit_coord_host(k, d0->z, d1->z, s0->z, s1->z);
                 int32_t sz = (int32_t)__builtin_floorf(wf);
                 sz = sz < 0 ? 0 : (sz > (int32_t)src->depth - 1 ? (int32_t)src->depth - 1 : sz);
+                if (filter == KZN_FILTER_NEAREST && src->address != dst->address && d1->x > d0->x && d1->y > d0->y && d1->x - d0->x == s1->x - s0->x &&
+                    d1->y - d0->y == s1->y - s0->y) {
+                    // same size, not mirrored, point-sampled: texel (i, j) of the destination box reads floor(i + 0.5 - d0 + s0)
+                    // = i - d0 + s0 — a box copy (16-byte vectors where the boxes allow; joins a merged launch when recorded)
+                    Box sb = image_box(src, s0->x, s0->y, sz, b->srcSubresource.baseArrayLayer + l);
+                    Box db = image_box(dst, d0->x, d0->y, k, b->dstSubresource.baseArrayLayer + l);
+                    if ((r = launch_box(queue, &sb, db, p.w, p.h, 1, false, 0))) return r;
+                    continue;
+                }
                 p.src = lower(image_box(src, 0, 0, sz, b->srcSubresource.baseArrayLayer + l));
                 p.dst = lower(image_box(dst, 0, 0, k, b->dstSubresource.baseArrayLayer + l));
                 dim3 grid((p.w + 127) / 128, (p.h + kThreads / 32 - 1) / (kThreads / 32));

@@ -88,6 +88,16 @@ def blit_cases():
          [B((0, 0, 0), (50, 37, 1), (0, 0, 0), (70, 50, 1))], abi.FILTER_LINEAR),
         ("nearest_tiled_dst_layers", dict(width=20, height=20, array_layers=2), dict(width=45, height=31, tiling=T, array_layers=3),
          [B((0, 0, 0), (20, 20, 1), (5, 1, 0), (45, 31, 1), src_layer=0, dst_layer=1, layers=2)], abi.FILTER_NEAREST),
+        # same size, not mirrored, NEAREST: the library turns these into box copies (16-byte vectors / 4-byte texels, TILED sides,
+        # layers, 3D slices); the mirrored twin of the first one stays a blit
+        ("nearest_same_size_offsets_tiled_src", dict(width=80, height=60, tiling=T), dict(width=96, height=70),
+         [B((5, 3, 0), (69, 51, 1), (12, 9, 0), (76, 57, 1))], abi.FILTER_NEAREST),
+        ("nearest_same_size_mirrored", dict(width=80, height=60, tiling=T), dict(width=96, height=70),
+         [B((69, 3, 0), (5, 51, 1), (12, 9, 0), (76, 57, 1))], abi.FILTER_NEAREST),
+        ("nearest_same_size_aligned_layers", dict(width=64, height=40, array_layers=3), dict(width=128, height=48, tiling=T, array_layers=2),
+         [B((16, 8, 0), (48, 40, 1), (32, 16, 0), (64, 48, 1), src_layer=1, dst_layer=0, layers=2)], abi.FILTER_NEAREST),
+        ("nearest_same_size_3d_slices", dict(width=24, height=16, depth=4), dict(width=24, height=16, depth=8),
+         [B((0, 0, 0), (24, 16, 4), (0, 0, 0), (24, 16, 8))], abi.FILTER_NEAREST),
     ]
 
 
