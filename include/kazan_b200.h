@@ -395,13 +395,21 @@ typedef struct KznGraphicsPipelineState {
     /* VkPipelineInputAssemblyStateCreateInfo::topology: VK_PRIMITIVE_TOPOLOGY_TRIANGLE_LIST (3, and 0 is accepted as the
      * default), TRIANGLE_STRIP (4) or TRIANGLE_FAN (5), assembled as the specification's "Primitive Topologies" section
      * defines: strip triangle i = {v[i], v[i+(1+i%2)], v[i+(2-i%2)]}, fan triangle i = {v[i+1], v[i+2], v[0]}
-     * (primitive restart is not supported).  Points and lines return VK_ERROR_FEATURE_NOT_PRESENT. */
+     * (primitive restart is not supported); LINE_LIST (1) {v[2i], v[2i+1]}, LINE_STRIP (2) {v[i], v[i+1]} and POINT_LIST
+     * (VK value 0: pass KZN_TOPOLOGY_POINT_LIST, since 0 reads as the default here).  Points are one pixel (pointSizeRange
+     * [1, 1], api_impl.rs:1604), lines one pixel wide, non-strict (lineWidthRange [1, 1], strictLines FALSE, :1605-1608): the
+     * parallelogram of "Basic Line Segment Rasterization", attributes running along the major axis (rule R9 of
+     * oracle/raster.c).  They are never face-culled; a point outside the clip volume is discarded, a segment is cut to it.
+     * Adjacency and patch topologies return VK_ERROR_FEATURE_NOT_PRESENT. */
     uint32_t topology;
     uint32_t reserved;
 } KznGraphicsPipelineState;
+#define KZN_TOPOLOGY_LINE_LIST 1u
+#define KZN_TOPOLOGY_LINE_STRIP 2u
 #define KZN_TOPOLOGY_TRIANGLE_LIST 3u
 #define KZN_TOPOLOGY_TRIANGLE_STRIP 4u
 #define KZN_TOPOLOGY_TRIANGLE_FAN 5u
+#define KZN_TOPOLOGY_POINT_LIST 0x10u /* VK_PRIMITIVE_TOPOLOGY_POINT_LIST */
 
 typedef struct KznVertexInput { /* one binding, VkVertexInputBindingDescription + 2 attributes */
     uint64_t buffer_address;

@@ -161,6 +161,8 @@ class Framebuffer(C.Structure):
                 ("band_y0", u32), ("band_y1", u32)]
 
 
+TOPOLOGY_LINE_LIST, TOPOLOGY_LINE_STRIP, TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP, TOPOLOGY_TRIANGLE_FAN = 1, 2, 3, 4, 5
+TOPOLOGY_POINT_LIST = 0x10  # VK_PRIMITIVE_TOPOLOGY_POINT_LIST is 0, which KznGraphicsPipelineState reads as "default"
 LOAD_OP_LOAD, LOAD_OP_CLEAR = 0, 1
 
 

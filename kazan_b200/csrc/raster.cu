@@ -277,9 +277,13 @@ __device__ __forceinline__ bool depth_clip_cannot_reject(const DrawParams& p, fl
 // vertex k of triangle t of an instance: its index into the vertex buffer (negative or huge: out of range)
 __device__ __forceinline__ long long triangle_vertex(const DrawParams& p, uint32_t t, int k) {
     // Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0}
+    // points {t}; line list {2t, 2t+1}; line strip {t, t+1}
     unsigned long long rel;
     if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (unsigned long long)t + (k == 0 ? 0u : k == 1 ? 1u + (t & 1u) : 2u - (t & 1u));
     else if (p.st.topology == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0ull : (unsigned long long)t + 1u + k;
+    else if (p.st.topology == KZN_TOPOLOGY_POINT_LIST) rel = t;
+    else if (p.st.topology == KZN_TOPOLOGY_LINE_LIST) rel = 2ull * t + k;
+    else if (p.st.topology == KZN_TOPOLOGY_LINE_STRIP) rel = (unsigned long long)t + k;
     else rel = 3ull * t + k;
     unsigned long long i = (unsigned long long)p.first + rel;
     if (p.index_base) {
@@ -407,7 +411,15 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
     }
     return true;
 }
+__device__ __forceinline__ bool is_point_or_line(const DrawParams& p) {
+    return p.st.topology == KZN_TOPOLOGY_POINT_LIST || p.st.topology == KZN_TOPOLOGY_LINE_LIST || p.st.topology == KZN_TOPOLOGY_LINE_STRIP;
+}
 __device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow) {
+    if (is_point_or_line(p)) {  // R9: every point / line becomes two triangles, made where clipped polygons are made
+        box = make_int4(1, 0, 1, 0);
+        slow = true;
+        return false;
+    }
     return p.rows_first ? make_compact_t<true>(p, t, r, box, slow) : make_compact_t<false>(p, t, r, box, slow);
 }
 
@@ -428,7 +440,82 @@ __device__ __forceinline__ float clip_distance(const DrawParams& p, const float*
 
 // Triangle t of an instance, clipped: `poly` receives the polygon's vertices (x y z w r g b a each), the result is their
 // number (0, 3..8) or -1 when a clip coordinate is not finite (the triangle is discarded).
+// R9 (oracle/raster.c expand_point_or_line): a clip-space vertex (x y z w r g b a) in window form {X, Y, z_window, 1/w, r, g, b, a}
+// — snapped coordinates as floats (exact up to 2^23); false: behind w, outside the guard band or not finite
+__device__ __forceinline__ bool to_window(const DrawParams& p, const float* v, float* out) {
+    if (!(v[3] > 0.0f)) return false;
+    const float iw = 1.0f / v[3];
+    const float xf = fmaf(p.hw, v[0] * iw, p.ox);
+    const float yf = fmaf(p.hh, v[1] * iw, p.oy);
+    const float zf = fmaf(p.dz, v[2] * iw, p.zmin_vp);
+    if (!finite_f(xf) || !finite_f(yf) || !finite_f(zf) || !finite_f(iw) || fabsf(xf) > kGuardBand || fabsf(yf) > kGuardBand) return false;
+    out[0] = (float)__float2int_rn(xf * 16.0f);
+    out[1] = (float)__float2int_rn(yf * 16.0f);
+    out[2] = zf;
+    out[3] = iw;
+#pragma unroll
+    for (int k = 4; k < 8; ++k) out[k] = v[k];
+    return true;
+}
+// point / line t of an instance -> the four corners of its square / parallelogram, in window form, in poly[0..3]; the result is
+// 4, 0 (nothing to draw) or -1 (a clip coordinate is not finite)
+__device__ __forceinline__ int expand_point_or_line(const DrawParams& p, uint32_t t, float (*poly)[8]) {
+    const int n = p.st.topology == KZN_TOPOLOGY_POINT_LIST ? 1 : 2;
+    float e[2][8];
+    for (int i = 0; i < n; ++i) {
+        const long long vidx = triangle_vertex(p, t, i);
+        const float* pos = vertex_position(p, vidx);
+        const float x = __ldg(pos), y = __ldg(pos + 1), z = __ldg(pos + 2), w = p.pos_comps == 4 ? __ldg(pos + 3) : 1.0f;
+        if (!finite_f(x) || !finite_f(y) || !finite_f(z) || !finite_f(w)) return -1;
+        const float4 c = fetch_color(p, vidx);
+        e[i][0] = x; e[i][1] = y; e[i][2] = z; e[i][3] = w;
+        e[i][4] = c.x; e[i][5] = c.y; e[i][6] = c.z; e[i][7] = c.w;
+    }
+    float w0[8], w1[8];
+    if (n == 1) {
+        for (int plane = 0; plane < 5; ++plane)
+            if (!(clip_distance(p, e[0], plane) >= 0.0f)) return 0;
+        if (!to_window(p, e[0], w0)) return 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) poly[k][c] = w0[c];
+            poly[k][0] = w0[0] + ((k == 1 || k == 2) ? 8.0f : -8.0f);
+            poly[k][1] = w0[1] + (k >= 2 ? 8.0f : -8.0f);
+        }
+        return 4;
+    }
+    for (int plane = 0; plane < 5; ++plane) {  // the segment is cut plane by plane, from the inside end (R3's arithmetic)
+        const float da = clip_distance(p, e[0], plane), db = clip_distance(p, e[1], plane);
+        const bool in_a = da >= 0.0f, in_b = db >= 0.0f;
+        if (!in_a && !in_b) return 0;
+        if (in_a != in_b) {
+            const float* I = in_a ? e[0] : e[1];
+            const float* O = in_a ? e[1] : e[0];
+            const float di = in_a ? da : db, d_o = in_a ? db : da;
+            const float tt = __fdiv_rn(di, di - d_o);
+            float cut[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cut[k] = __fmaf_rn(tt, O[k] - I[k], I[k]);
+            if (plane == 0) cut[3] = kClipW;
+            float* dst = in_a ? e[1] : e[0];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = cut[k];
+        }
+    }
+    if (!to_window(p, e[0], w0) || !to_window(p, e[1], w1)) return 0;
+    const bool x_major = fabsf(w1[0] - w0[0]) >= fabsf(w1[1] - w0[1]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        poly[0][c] = w0[c]; poly[1][c] = w1[c]; poly[2][c] = w1[c]; poly[3][c] = w0[c];
+    }
+    const int ax = x_major ? 1 : 0;
+    poly[0][ax] -= 8.0f; poly[1][ax] -= 8.0f; poly[2][ax] += 8.0f; poly[3][ax] += 8.0f;
+    return 4;
+}
+
 __device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, float (*poly)[8]) {
+    if (is_point_or_line(p)) return expand_point_or_line(p, t, poly);
     float other[8][8];
     float(*src)[8] = other;
     float(*dst)[8] = poly;  // five planes: other -> poly -> other -> poly -> other -> poly
@@ -478,6 +565,24 @@ __device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, f
 // R4; oracle/raster.c setup_triangle); false: it produces no fragments.
 __device__ __forceinline__ bool make_compact_from(const DrawParams& p, const float* v0, const float* v1, const float* v2, TriRecC& r, int4& box) {
     box = make_int4(1, 0, 1, 0);
+    if (is_point_or_line(p)) {  // R9: corners in window form {X, Y, z, 1/w, colour}; no face culling
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float* v = k == 0 ? v0 : k == 1 ? v1 : v2;
+            r.X[k] = (int32_t)v[0];
+            r.Y[k] = (int32_t)v[1];
+            r.z[k] = v[2];
+            r.iw[k] = v[3];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) r.col[k][ch] = v[4 + ch] * v[3];
+        }
+        const long long area2 = (long long)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) - (long long)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);
+        if (area2 == 0) return false;
+        const int4 b = record_box(p, r);
+        if (b.x > b.y || b.z > b.w) return false;
+        box = b;
+        return true;
+    }
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -515,6 +620,7 @@ __device__ __forceinline__ int4 unpack_box(const uint2 b) {  // minx maxx miny m
 
 __device__ __forceinline__ void clip_statistics(const DrawParams& p, int m, unsigned long long n_inst) {
     if (!p.stats) return;
+    if (is_point_or_line(p) && m >= 0) return;  // (their two triangles are the primitive itself, not the clipper's work)
     if (m < 0) {
         atomicAdd(&p.stats[10], n_inst);
     } else {
@@ -2611,9 +2717,9 @@ KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebuffer* f
                 KZN_ERROR_FEATURE_NOT_PRESENT, "draw: blend factor not supported (dualSrcBlend is FALSE, api_impl.rs:883)");
     KZN_VALID(st->color_blend_op <= 4 && st->alpha_blend_op <= 4, "draw: bad blend op");
     KZN_VALID(st->logic_op <= 16, "draw: logic_op is 0 (disabled) or 1 + VkLogicOp");
-    KZN_VALID(st->topology <= 10, "draw: bad primitive topology");
-    KZN_REQUIRE(st->topology == 0 || (st->topology >= KZN_TOPOLOGY_TRIANGLE_LIST && st->topology <= KZN_TOPOLOGY_TRIANGLE_FAN),
-                KZN_ERROR_FEATURE_NOT_PRESENT, "draw: only triangle list / strip / fan topologies are rasterised");
+    KZN_VALID(st->topology <= 10 || st->topology == KZN_TOPOLOGY_POINT_LIST, "draw: bad primitive topology");
+    KZN_REQUIRE(st->topology <= KZN_TOPOLOGY_TRIANGLE_FAN || st->topology == KZN_TOPOLOGY_POINT_LIST, KZN_ERROR_FEATURE_NOT_PRESENT,
+                "draw: adjacency and patch topologies are not rasterised");
     bool has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     KZN_VALID(has_color || has_depth, "draw: framebuffer has no attachment");
     if (has_color) {
@@ -2780,7 +2886,11 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     memset(&p, 0, sizeof p);
     make_clip(fb, vp, sc, W, H, &p);
     const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
-    uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0), total = ntri * instance_count;
+    // primitives of an instance (called triangles below; points and lines become two triangles each where clipped polygons are made, R9)
+    uint64_t ntri = topo == KZN_TOPOLOGY_POINT_LIST ? count : topo == KZN_TOPOLOGY_LINE_LIST ? count / 2 :
+                    topo == KZN_TOPOLOGY_LINE_STRIP ? (count >= 2 ? count - 1 : 0) :
+                    topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0);
+    uint64_t total = ntri * instance_count;
     if (total == 0) return kzn_flush_render_pass_clear(q);
     if (p.cx1 < p.cx0 || p.cy1 < p.cy0) {  // empty clip rectangle (scissor, viewport, framebuffer and band do not meet)
         if ((r = kzn_flush_render_pass_clear(q))) return r;
@@ -2929,7 +3039,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
     {
         static const long min_tris = [] { const char* e = getenv("KZN_BAND_PREFILTER_MIN"); return e ? atol(e) : 65536l; }();  // (negative: never)
         static const bool use_codes = [] { const char* e = getenv("KZN_BAND_CODES"); return !(e && e[0] == '0'); }();
-        if (p.binned && p.rows_first && instance_count == 1 && min_tris >= 0 && (long)ntri >= min_tris) {
+        const bool triangles = topo >= KZN_TOPOLOGY_TRIANGLE_LIST && topo <= KZN_TOPOLOGY_TRIANGLE_FAN;
+        if (p.binned && p.rows_first && triangles && instance_count == 1 && min_tris >= 0 && (long)ntri >= min_tris) {
             // the code table pays when the vertex buffer is not much larger than what the draw can name (an indexed mesh)
             const bool codes = use_codes && index_base && p.pos_vertices <= 2ull * ntri && p.pos_vertices < 0xffffffffull && !q->recording;
             uint32_t n_codes = 0;

@@ -244,6 +244,123 @@ static int clip_triangle(const VsOut v[3], const KznViewport* vp, float poly[8][
     return n;
 }
 
+/* ---- points and lines (R9) -------------------------------------------------------------------------------------
+ * Vulkan 1.1 "Basic Point Rasterization" / "Basic Line Segment Rasterization" with the reference's limits: pointSizeRange
+ * and lineWidthRange [1, 1], strictLines FALSE (api_impl.rs:1604-1608).  Both are rasterised as two triangles over four
+ * corners in SNAPPED window coordinates (1/16 pixel), by the triangle rules R4-R8 (top-left rule: no pixel twice, none lost):
+ *   point  (X, Y):          the square X-8 .. X+8, Y-8 .. Y+8 — exactly one pixel centre;
+ *   line   (Xa,Ya)-(Xb,Yb): the non-strict parallelogram — x-major (|dX| >= |dY|): (Xa, Ya-8) (Xb, Yb-8) (Xb, Yb+8) (Xa, Ya+8),
+ *                           y-major: (Xa-8, Ya) (Xb-8, Yb) (Xb+8, Yb) (Xa+8, Ya); the corners of an end carry that end's depth,
+ *                           1/w and colour, so attributes run along the major axis, perspective-correct (R6); consecutive
+ *                           segments of a strip share no pixel; a segment of zero length draws nothing.
+ * Clipping: a point outside w >= 2^-20 or the guard band is discarded; a segment is cut to them first (same planes and
+ * intersection arithmetic as R3, from the inside end).  No face culling.  A corner is handed on as the 8 floats
+ * {X, Y, z_window, 1/w, r, g, b, a} ("window form": snapped coordinates up to 2^23 are exact in a float). */
+static int setup_window_triangle(const float c0[8], const float c1[8], const float c2[8], const ClipRect* clip, TriSetup* t) {
+    const float* c[3] = {c0, c1, c2};
+    int32_t X[3], Y[3];
+    for (int i = 0; i < 3; ++i) {
+        X[i] = (int32_t)c[i][0];
+        Y[i] = (int32_t)c[i][1];
+        t->z[i] = c[i][2];
+        t->iw[i] = c[i][3];
+        for (int ch = 0; ch < 4; ++ch) t->col[i][ch] = c[i][4 + ch] * c[i][3];
+    }
+    int64_t two_a = (int64_t)(X[1] - X[0]) * (Y[2] - Y[0]) - (int64_t)(X[2] - X[0]) * (Y[1] - Y[0]);
+    if (two_a == 0) return 0;
+    int64_t s = two_a < 0 ? -1 : 1;
+    for (int i = 0; i < 3; ++i) {
+        int ia = (i + 1) % 3, ib = (i + 2) % 3;
+        int64_t dx = X[ib] - X[ia], dy = Y[ib] - Y[ia];
+        t->a[i] = -dy * s;
+        t->b[i] = dx * s;
+        t->c[i] = s * (dy * X[ia] - dx * Y[ia]);
+        t->bias[i] = (t->a[i] > 0 || (t->a[i] == 0 && t->b[i] > 0)) ? 1 : 0;
+    }
+    t->inv2a = 1.0f / (float)(two_a * s);
+    int32_t minX = X[0], maxX = X[0], minY = Y[0], maxY = Y[0];
+    for (int i = 1; i < 3; ++i) {
+        if (X[i] < minX) minX = X[i];
+        if (X[i] > maxX) maxX = X[i];
+        if (Y[i] < minY) minY = Y[i];
+        if (Y[i] > maxY) maxY = Y[i];
+    }
+    t->minx = (minX - 8 + 15) >> 4;
+    t->maxx = (maxX - 8) >> 4;
+    t->miny = (minY - 8 + 15) >> 4;
+    t->maxy = (maxY - 8) >> 4;
+    if (t->minx < clip->x0) t->minx = clip->x0;
+    if (t->maxx > clip->x1) t->maxx = clip->x1;
+    if (t->miny < clip->y0) t->miny = clip->y0;
+    if (t->maxy > clip->y1) t->maxy = clip->y1;
+    return t->minx <= t->maxx && t->miny <= t->maxy;
+}
+
+/* clip-space vertex (x y z w r g b a) -> window form; 0: not representable (behind w, outside the guard band, not finite) */
+static int to_window(const float v[8], const KznViewport* vp, float out[8]) {
+    WindowScale s = window_scale(vp);
+    float dz = vp->maxDepth - vp->minDepth;
+    if (!(v[3] > 0.0f)) return 0;
+    float iw = 1.0f / v[3];
+    float xf = fmaf(s.hw, v[0] * iw, s.ox);
+    float yf = fmaf(s.hh, v[1] * iw, s.oy);
+    float zf = fmaf(dz, v[2] * iw, vp->minDepth);
+    if (!is_finite(xf) || !is_finite(yf) || !is_finite(zf) || !is_finite(iw) || fabsf(xf) > GUARD_BAND || fabsf(yf) > GUARD_BAND) return 0;
+    out[0] = (float)(int32_t)nearbyintf(xf * 16.0f);
+    out[1] = (float)(int32_t)nearbyintf(yf * 16.0f);
+    out[2] = zf;
+    out[3] = iw;
+    memcpy(out + 4, v + 4, 16);
+    return 1;
+}
+
+/* the four corners (window form) of a point (n = 1) or a line segment (n = 2); returns 4, 0 (nothing to draw) or -1 (a clip
+ * coordinate is not finite: discarded) */
+static int expand_point_or_line(const VsOut* v, int n, const KznViewport* vp, float quad[4][8]) {
+    float e[2][8];
+    for (int i = 0; i < n; ++i) {
+        if (!is_finite(v[i].x) || !is_finite(v[i].y) || !is_finite(v[i].z) || !is_finite(v[i].w)) return -1;
+        e[i][0] = v[i].x; e[i][1] = v[i].y; e[i][2] = v[i].z; e[i][3] = v[i].w;
+        memcpy(e[i] + 4, v[i].rgba, 16);
+    }
+    WindowScale s = window_scale(vp);
+    float w0[8], w1[8];
+    if (n == 1) {
+        for (int plane = 0; plane < 5; ++plane)
+            if (!(clip_distance(e[0], plane, &s) >= 0.0f)) return 0;
+        if (!to_window(e[0], vp, w0)) return 0;
+        const float dx[4] = {-8.0f, 8.0f, 8.0f, -8.0f}, dy[4] = {-8.0f, -8.0f, 8.0f, 8.0f};
+        for (int k = 0; k < 4; ++k) {
+            memcpy(quad[k], w0, 32);
+            quad[k][0] = w0[0] + dx[k];
+            quad[k][1] = w0[1] + dy[k];
+        }
+        return 4;
+    }
+    for (int plane = 0; plane < 5; ++plane) { /* the segment is cut plane by plane, from the inside end (R3's arithmetic) */
+        float da = clip_distance(e[0], plane, &s), db = clip_distance(e[1], plane, &s);
+        int in_a = da >= 0.0f, in_b = db >= 0.0f;
+        if (!in_a && !in_b) return 0;
+        if (in_a != in_b) {
+            const float* I = in_a ? e[0] : e[1];
+            const float* O = in_a ? e[1] : e[0];
+            float di = in_a ? da : db, dO = in_a ? db : da;
+            float t = di / (di - dO);
+            float cut[8];
+            for (int k = 0; k < 8; ++k) cut[k] = fmaf(t, O[k] - I[k], I[k]);
+            if (plane == 0) cut[3] = CLIP_W;
+            memcpy(in_a ? e[1] : e[0], cut, 32);
+        }
+    }
+    if (!to_window(e[0], vp, w0) || !to_window(e[1], vp, w1)) return 0;
+    float adx = fabsf(w1[0] - w0[0]), ady = fabsf(w1[1] - w0[1]);
+    int x_major = adx >= ady;
+    memcpy(quad[0], w0, 32); memcpy(quad[1], w1, 32); memcpy(quad[2], w1, 32); memcpy(quad[3], w0, 32);
+    if (x_major) { quad[0][1] -= 8.0f; quad[1][1] -= 8.0f; quad[2][1] += 8.0f; quad[3][1] += 8.0f; }
+    else { quad[0][0] -= 8.0f; quad[1][0] -= 8.0f; quad[2][0] += 8.0f; quad[3][0] += 8.0f; }
+    return 4;
+}
+
 /* ---- fragment programs ------------------------------------------------------------------------------ */
 
 void kzo_fs_procedural_orbit(uint32_t px, uint32_t py, float fb_width, float fb_height, float rgba[4]) {
@@ -380,9 +497,9 @@ static KznResult check_draw(const KznGraphicsPipelineState* st, const KznFramebu
         return KZN_ERROR_FEATURE_NOT_PRESENT;
     if (st->color_blend_op > 4 || st->alpha_blend_op > 4) return KZN_ERROR_VALIDATION_FAILED;
     if (st->logic_op > 16) return KZN_ERROR_VALIDATION_FAILED;
-    if (st->topology > 10) return KZN_ERROR_VALIDATION_FAILED;
-    if (st->topology != 0 && (st->topology < KZN_TOPOLOGY_TRIANGLE_LIST || st->topology > KZN_TOPOLOGY_TRIANGLE_FAN))
-        return KZN_ERROR_FEATURE_NOT_PRESENT; /* points, lines, adjacency, patches */
+    if (st->topology > 10 && st->topology != KZN_TOPOLOGY_POINT_LIST) return KZN_ERROR_VALIDATION_FAILED;
+    if (st->topology > KZN_TOPOLOGY_TRIANGLE_FAN && st->topology != KZN_TOPOLOGY_POINT_LIST)
+        return KZN_ERROR_FEATURE_NOT_PRESENT; /* adjacency, patches */
     int has_color = fb->color.format != 0, has_depth = fb->depth.format != 0;
     if (!has_color && !has_depth) return KZN_ERROR_VALIDATION_FAILED;
     if (has_color) {
@@ -507,7 +624,10 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
     ClipRect clip;
     make_clip(fb, vp, sc, W, H, &clip);
     const uint32_t topo = st->topology ? st->topology : KZN_TOPOLOGY_TRIANGLE_LIST;
-    uint64_t ntri = topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0);
+    const int prim_verts = topo == KZN_TOPOLOGY_POINT_LIST ? 1 : (topo == KZN_TOPOLOGY_LINE_LIST || topo == KZN_TOPOLOGY_LINE_STRIP) ? 2 : 3;
+    uint64_t ntri = topo == KZN_TOPOLOGY_POINT_LIST ? count : topo == KZN_TOPOLOGY_LINE_LIST ? count / 2 :
+                    topo == KZN_TOPOLOGY_LINE_STRIP ? (count >= 2 ? count - 1 : 0) :
+                    topo == KZN_TOPOLOGY_TRIANGLE_LIST ? count / 3 : (count >= 3 ? count - 2 : 0); /* primitives */
     uint64_t total = ntri * instance_count;
     if (total == 0) return KZN_SUCCESS;
     /* MAX_SUB record slots per primitive: slot 0 of an unclipped one, slots 0 .. n-1 of one clipped into n triangles */
@@ -520,9 +640,11 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
 #pragma omp parallel for num_threads(threads) schedule(static)
     for (int64_t t = 0; t < (int64_t)ntri; ++t) {
         VsOut v[3];
-        for (int k = 0; k < 3; ++k) {
-            /* Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0} */
-            uint64_t rel = 3 * (uint64_t)t + k;
+        for (int k = 0; k < prim_verts; ++k) {
+            /* Vulkan 1.1 "Primitive Topologies": list {3t, 3t+1, 3t+2}; strip {t, t+(1+t%2), t+(2-t%2)}; fan {t+1, t+2, 0};
+             * points {t}; line list {2t, 2t+1}; line strip {t, t+1} */
+            uint64_t rel = (uint64_t)prim_verts * (uint64_t)t + k;
+            if (topo == KZN_TOPOLOGY_LINE_STRIP) rel = (uint64_t)t + k;
             if (topo == KZN_TOPOLOGY_TRIANGLE_STRIP) rel = (uint64_t)t + (k == 0 ? 0 : k == 1 ? 1 + (uint64_t)t % 2 : 2 - (uint64_t)t % 2);
             if (topo == KZN_TOPOLOGY_TRIANGLE_FAN) rel = k == 2 ? 0 : (uint64_t)t + 1 + k;
             uint64_t i = first + rel;
@@ -535,6 +657,16 @@ static KznResult draw_common(const KznGraphicsPipelineState* st, const KznFrameb
             }
             if (vidx < 0) vidx = (int64_t)1 << 40; /* out of range -> robust fetch */
             fetch_vertex(vi, (uint64_t)vidx, &v[k]);
+        }
+        if (prim_verts < 3) { /* R9: two triangles over the four corners, in window form */
+            float quad[4][8];
+            int m = expand_point_or_line(v, prim_verts, vp, quad);
+            if (m < 0) fate[t] = 2;
+            if (m == 4) {
+                valid[t * MAX_SUB] = (uint8_t)setup_window_triangle(quad[0], quad[1], quad[2], &clip, &tris[t * MAX_SUB]);
+                valid[t * MAX_SUB + 1] = (uint8_t)setup_window_triangle(quad[0], quad[2], quad[3], &clip, &tris[t * MAX_SUB + 1]);
+            }
+            continue;
         }
         int cls = classify_triangle(v, vp, &clip);
         if (cls == 0) {

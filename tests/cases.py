@@ -354,6 +354,65 @@ def clip_scenes(rng) -> list[Scene]:
             many += [[x0, y0, 0.5, 1.0, *col], [x0 + 0.9, y0 + 0.1, 0.5, 1.0, *col], [x0 + 0.2, y0 + 0.8, 0.5, 1.0, *col]]
     scenes.append(Scene("clip_overflow_4400_tris_one_tile", 40, 24, np.array(many, dtype=np.float32), pos_comps=4, color_offset=16,
                         state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # ---- points and lines (R9): two triangles over four corners in snapped window coordinates ----
+    PTS, LL, LS = abi.TOPOLOGY_POINT_LIST, abi.TOPOLOGY_LINE_LIST, abi.TOPOLOGY_LINE_STRIP
+
+    def on_grid(pv, W, H, step):  # some coordinates on pixel centres / corners / sixteenths: ties of the top-left rule
+        return (np.round((pv * 0.5 + 0.5) * np.array([W, H]) * step) / step / np.array([W, H])) * 2 - 1
+
+    pts = []
+    for k in range(300):
+        pxy = rng.uniform(-1.05, 1.05, 2)
+        if k % 3 == 0:
+            pxy = on_grid(pxy, 96, 64, rng.choice([1, 2, 16]))
+        pts.append([pxy[0], pxy[1], rng.uniform(0, 1), *rng.uniform(0.1, 0.3, 4)])
+    pts = np.array(pts, dtype=np.float32)
+    scenes.append(Scene("points_300_additive", 96, 64, pts, state=pipeline_state(topology=PTS, blend=util.ADDITIVE_BLEND)))
+    scenes.append(Scene("points_40_depth_tiled_direct", 96, 64, pts[:40], state=pipeline_state(topology=PTS, depth=(abi.COMPARE_LESS, 1)),
+                        use_depth=True, color_tiling=T))
+    scenes.append(Scene("points_3_fused", 96, 64, pts[6:9], state=pipeline_state(topology=PTS)))
+    gone = np.array([[0.0, 0.0, 0.5, -1.0, 1, 1, 1, 1], [3.0e6, 0.0, 0.5, 1.0, 1, 1, 1, 1], [0.5, 0.5, 0.5, 0.0, 1, 1, 1, 1],
+                     [np.nan, 0.0, 0.5, 1.0, 1, 1, 1, 1], [0.25, -0.25, 0.5, 2.0, 1, 0.5, 0.25, 1]], dtype=np.float32)
+    scenes.append(Scene("points_behind_outside_nan", 64, 48, gone, pos_comps=4, color_offset=16, state=pipeline_state(topology=PTS)))
+    segs = []
+    for k in range(500):
+        a = rng.uniform(-1.1, 1.1, 2)
+        kind = k % 10
+        d = rng.uniform(-1, 1, 2) * rng.choice([0.01, 0.1, 0.6])
+        if kind == 0: d[1] = 0.0          # horizontal
+        if kind == 1: d[0] = 0.0          # vertical
+        if kind == 2: d[1] = d[0] * 96 / 64   # exactly diagonal in pixels: the major axis is a tie
+        if kind == 3: d[:] = 0.0          # zero length
+        b = a + d
+        if kind in (0, 1, 2, 4):
+            a, b = on_grid(a, 96, 64, 2), on_grid(b, 96, 64, 2)
+        ca, cb = rng.uniform(0.05, 0.25, 4), rng.uniform(0.05, 0.25, 4)
+        segs += [[a[0], a[1], rng.uniform(0, 1), *ca], [b[0], b[1], rng.uniform(0, 1), *cb]]
+    segs = np.array(segs, dtype=np.float32)
+    scenes.append(Scene("lines_500_additive", 96, 64, segs, state=pipeline_state(topology=LL, blend=util.ADDITIVE_BLEND)))
+    scenes.append(Scene("lines_60_depth_direct_band", 96, 64, segs[:120], state=pipeline_state(topology=LL, depth=(abi.COMPARE_LESS_OR_EQUAL, 1)),
+                        use_depth=True, band=(16, 48)))
+    scenes.append(Scene("lines_2_fused", 96, 64, segs[20:24], state=pipeline_state(topology=LL)))
+    # a spiral as an indexed (uint16) strip with perspective: w grows along it, colour and depth interpolate along the major axis
+    ang = np.linspace(0, 9 * np.pi, 400)
+    wv = np.linspace(1.0, 3.0, 400)
+    spiral = np.stack([np.cos(ang) * ang / 30 * wv, np.sin(ang) * ang / 30 * wv, np.linspace(0.1, 0.9, 400) * wv, wv,
+                       0.5 + 0.5 * np.cos(ang), 0.5 + 0.5 * np.sin(ang), np.linspace(0, 1, 400), np.full(400, 0.5)], axis=1).astype(np.float32)
+    scenes.append(Scene("line_strip_spiral_u16_depth_blend_instances2", 160, 120, spiral, np.arange(400, dtype=np.uint16), pos_comps=4, color_offset=16,
+                        index_type=abi.INDEX_TYPE_UINT16, instances=2, use_depth=True,
+                        state=pipeline_state(topology=LS, depth=(abi.COMPARE_LESS_OR_EQUAL, 1), blend=util.ALPHA_BLEND)))
+    # segments through the eye plane and far beyond the guard band (cut to w >= 2^-20 and +-2^18 px first), few and many
+    far = []
+    for k in range(150):
+        a = [rng.uniform(-0.9, 0.9), rng.uniform(-0.9, 0.9), 0.5, 1.0]
+        if k % 3 == 0: b = [rng.uniform(-2, 2), rng.uniform(-2, 2), 0.25, -rng.uniform(0.1, 2.0)]   # behind the eye
+        elif k % 3 == 1: b = [rng.uniform(-1, 1) * 5.0e6, rng.uniform(-1, 1) * 5.0e6, 0.75, 1.0]     # millions of pixels away
+        else: b = [rng.uniform(-0.9, 0.9), rng.uniform(-0.9, 0.9), 0.5, rng.uniform(0.5, 2.0)]
+        far += [[*a, *rng.uniform(0.05, 0.2, 4)], [*b, *rng.uniform(0.05, 0.2, 4)]]
+    far = np.array(far, dtype=np.float32)
+    scenes.append(Scene("lines_clipped_direct", 128, 96, far[:80], pos_comps=4, color_offset=16, state=pipeline_state(topology=LL, blend=util.ADDITIVE_BLEND)))
+    scenes.append(Scene("lines_clipped_binned_tiled", 128, 96, np.concatenate([far, far[::-1]]), pos_comps=4, color_offset=16, color_tiling=T,
+                        state=pipeline_state(topology=LL, blend=util.ADDITIVE_BLEND)))
     # bands of draws large enough for band_prefilter_kernel (>= 65536 triangles, the band under half of the viewport's rows):
     # blocks of 256 triangles that miss the band are skipped by setup and binning.  A plain mesh; a floor through the eye plane
     # (clipped primitives inside and outside the band); a frame so small that every tile's list overflows (the raster kernel

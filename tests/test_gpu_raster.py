@@ -61,8 +61,7 @@ def test_draw_in_a_render_pass_with_load_op_clear_matches_oracle(gpu, scene):
     assert (gs.fragments_covered, gs.fragments_depth_passed) == (os_.fragments_covered, os_.fragments_depth_passed)
     assert gd.tobytes() == od.tobytes(), "depth differs"
     assert gc.tobytes() == oc.tobytes(), "colour differs"
-    n_tri = scene.count // 3 if scene.state.topology in (0, 3) else max(0, scene.count - 2)
-    if n_tri * scene.instances > 256:  # binned: the draw took the clear over
+    if scene.primitives * scene.instances > 256:  # binned: the draw took the clear over
         assert launches == plain, f"the clear was not fused into the draw ({launches} launches against {plain})"
     else:
         assert launches == plain + (2 if scene.use_depth else 1)
@@ -239,7 +238,7 @@ def _random_scene(rng, k):
                 p = (np.round((p * 0.5 + 0.5) * np.array([W, H]) * 2) / 2 / np.array([W, H])) * 2 - 1
             verts.append([p[0], p[1], rng.uniform(-0.1, 1.1), *(col + rng.uniform(-0.1, 0.1, 4))])
     verts = np.array(verts, dtype=np.float32)
-    topology = int(rng.choice([0, 3, 4, 5])) if n_tri <= 40 else 3
+    topology = int(rng.choice([0, 3, 4, 5, 1, 2, abi.TOPOLOGY_POINT_LIST])) if n_tri <= 40 else int(rng.choice([3, 3, 1, 2, abi.TOPOLOGY_POINT_LIST]))
     depth = None if rng.random() < 0.4 else (int(rng.integers(0, 8)), int(rng.integers(0, 2)))
     blend = None
     if rng.random() < 0.6:
@@ -280,7 +279,7 @@ def test_random_scenes_agree_with_the_oracle(gpu, seed):
         sc = _random_scene(rng, k)
         oc, od, os_ = sc.run_oracle()
         gc, gd, gs = sc.run_gpu(gpu)
-        what = (k, sc.width, sc.height, len(sc.vertices) // 3, sc.state.topology, sc.state.logic_op, sc.state.blend_enable,
+        what = (k, sc.width, sc.height, sc.primitives, sc.state.topology, sc.state.logic_op, sc.state.blend_enable,
                 sc.state.depth_compare_op if sc.use_depth else None)
         assert (gs.triangles_in, gs.triangles_culled, gs.fragments_covered, gs.fragments_depth_passed) == \
                (os_.triangles_in, os_.triangles_culled, os_.fragments_covered, os_.fragments_depth_passed), what

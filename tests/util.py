@@ -99,7 +99,8 @@ def image_copy(extent, src_off=(0, 0, 0), dst_off=(0, 0, 0), src_layer=0, dst_la
 
 def pipeline_state(fs=abi.FS_VERTEX_COLOR, cull=abi.CULL_NONE, front=abi.FRONT_FACE_CCW, depth=None, blend=None,
                    write_mask=15, logic_op=None, topology=0) -> abi.GraphicsPipelineState:
-    """logic_op: a VkLogicOp 0..15 (logicOpEnable = TRUE) or None; topology: 0 / 3 list, 4 strip, 5 fan."""
+    """logic_op: a VkLogicOp 0..15 (logicOpEnable = TRUE) or None; topology: 0 / 3 list, 4 strip, 5 fan, 1 / 2 line list / strip,
+    abi.TOPOLOGY_POINT_LIST."""
     st = abi.GraphicsPipelineState()
     st.topology = topology
     st.logic_op = 0 if logic_op is None else 1 + logic_op
@@ -158,6 +159,13 @@ class Scene:
     @property
     def count(self):
         return (len(self.indices) if self.indices is not None else len(self.vertices)) - self.first
+
+    @property
+    def primitives(self):
+        """primitives of one instance (Vulkan 1.1 "Primitive Topologies")"""
+        n, topo = self.count, self.state.topology
+        return {abi.TOPOLOGY_POINT_LIST: n, abi.TOPOLOGY_LINE_LIST: n // 2, abi.TOPOLOGY_LINE_STRIP: max(0, n - 1),
+                0: n // 3, abi.TOPOLOGY_TRIANGLE_LIST: n // 3}.get(topo, max(0, n - 2))
 
     def _framebuffer(self, color_addr, depth_addr) -> abi.Framebuffer:
         fb = abi.Framebuffer()
