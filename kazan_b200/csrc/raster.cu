@@ -2200,30 +2200,13 @@ __device__ __forceinline__ uint8_t* tile_masks(const DrawParams& p, uint32_t til
 // themselves stay in global memory (the tile's segment of the bins and of a second buffer of the same size, ping-pong;
 // a few KiB that live in L2), so a warp needs 1 KiB of shared memory and no CTA barrier — 64 sorting warps per SM, where a
 // CTA per tile with the lists in shared memory spent its time in barriers (9 us per tile whatever its length).
-__global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __grid_constant__ DrawParams p) {
-    kzn_pdl_wait();
+// The list of one tile, n ids in the tile's segment of the bins, sorted by ONE warp in global memory (ping-pong with the
+// second buffer; `table`: 256 words of shared memory), then written back with its brick masks.  Any length: lists beyond
+// kSortCap, which the CTA form cannot hold in shared memory, come here too (a tile with tens of thousands of triangles takes
+// a warp a millisecond — against every brick of the tile walking every triangle of the draw, which is what used to happen).
+__device__ __forceinline__ void sort_tile_in_global(const DrawParams& p, uint32_t tile, uint32_t beg, uint32_t n, uint32_t* table, uint32_t lane,
+                                                    int tile_px0, int tile_py0) {
     constexpr uint32_t kFull = 0xffffffffu;
-    __shared__ uint32_t tables[kSortWarps][256];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // bin_fill_kernel was the last to need the allocator of extra records: zero for the next draw
-        p.work_counter[5] = p.work_counter[4];
-        p.work_counter[4] = 0u;
-        p.work_counter[6] = 0u;
-        p.work_counter[8] = 0u;  // band_prefilter_kernel's list of blocks and their triangle count
-        p.work_counter[9] = 0u;
-    }
-    const uint32_t tile = blockIdx.x * kSortWarps + warp;
-    if (tile >= p.tiles_x * p.tiles_y) return;
-    const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
-    const int tile_px0 = (int)(p.tile_x0 + tile_x) * kTileW, tile_py0 = (int)(p.tile_y0 + tile_y) * kTileH;
-    const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], n = end - beg;
-    if (n == 0) return;
-    if (p.stats && lane == 0) atomicAdd(&p.stats[6], 1ull);
-    if (n > (uint32_t)kSortCap || end > p.bin_capacity) {  // raster_kernel walks every triangle of the draw for this tile
-        if (p.stats && lane == 0) atomicAdd(&p.stats[7], 1ull);
-        return;
-    }
-    uint32_t* table = tables[warp];
     uint32_t* a = p.bin_entries + beg;
     uint32_t* b = p.bin_entries_alt + beg;
     // range of the ids
@@ -2315,6 +2298,32 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __gr
     }
 }
 
+__global__ void __launch_bounds__(kSortThreads) tile_sort_warp_kernel(const __grid_constant__ DrawParams p) {
+    kzn_pdl_wait();
+    constexpr uint32_t kFull = 0xffffffffu;
+    __shared__ uint32_t tables[kSortWarps][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // bin_fill_kernel was the last to need the allocator of extra records: zero for the next draw
+        p.work_counter[5] = p.work_counter[4];
+        p.work_counter[4] = 0u;
+        p.work_counter[6] = 0u;
+        p.work_counter[8] = 0u;  // band_prefilter_kernel's list of blocks and their triangle count
+        p.work_counter[9] = 0u;
+    }
+    const uint32_t tile = blockIdx.x * kSortWarps + warp;
+    if (tile >= p.tiles_x * p.tiles_y) return;
+    const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+    const int tile_px0 = (int)(p.tile_x0 + tile_x) * kTileW, tile_py0 = (int)(p.tile_y0 + tile_y) * kTileH;
+    const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], n = end - beg;
+    if (n == 0) return;
+    if (p.stats && lane == 0) atomicAdd(&p.stats[6], 1ull);
+    if (end > p.bin_capacity) {  // the bins overflowed: raster_kernel walks every triangle of the draw for this tile
+        if (p.stats && lane == 0) atomicAdd(&p.stats[7], 1ull);
+        return;
+    }
+    sort_tile_in_global(p, tile, beg, n, tables[warp], lane, tile_px0, tile_py0);
+}
+
 // The same with one CTA per tile and the lists in shared memory (per-warp slices, a [digit][warp] table orders batches and
 // warps, so every pass is stable): the better form when tiles are few and their lists long (a warp alone walks a list of a
 // thousand ids in 35 dependent steps per phase).
@@ -2335,8 +2344,12 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_cta_kernel(const __gri
     const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1], list_len = end - beg;
     if (list_len == 0) return;
     if (p.stats && tid == 0) atomicAdd(&p.stats[6], 1ull);
-    if (list_len > (uint32_t)kSortCap || end > p.bin_capacity) {  // raster_kernel walks every triangle of the draw for this tile
+    if (end > p.bin_capacity) {  // the bins overflowed: raster_kernel walks every triangle of the draw for this tile
         if (p.stats && tid == 0) atomicAdd(&p.stats[7], 1ull);
+        return;
+    }
+    if (list_len > (uint32_t)kSortCap) {  // too long for shared memory: one warp sorts it in global memory
+        if (tid < 32u) sort_tile_in_global(p, tile, beg, list_len, sh.table, tid, tile_px0, tile_py0);
         return;
     }
     for (uint32_t i = tid; i < list_len; i += kSortThreads) sh.list[i] = p.bin_entries[beg + i];
@@ -2393,7 +2406,7 @@ __device__ __forceinline__ void raster_body(const DrawParams& p) {
         // triangle source: the tile's sorted id list, or — a tile whose list did not fit — every triangle of the draw
         const uint32_t beg = p.tile_offsets[tile], end = p.tile_offsets[tile + 1];
         if (end == beg && !p.load_clear) continue;  // (with LOAD_OP_CLEAR an empty brick is still written: the clear values)
-        const bool direct = end - beg > (uint32_t)kSortCap || end > p.bin_capacity;
+        const bool direct = end > p.bin_capacity;  // the bins overflowed (more than 8 tiles per triangle on average): no list for this tile
         // (walking all triangles: with clipped primitives in the draw every primitive stands for eight list entries, its own
         // record and up to five extra ones, so that the extra triangles come at the primitive's place)
         const uint32_t walk_shift = direct && p.work_counter[5] ? 3u : 0u;

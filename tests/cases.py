@@ -426,4 +426,22 @@ def clip_scenes(rng) -> list[Scene]:
     va = v.copy()
     va[:, 3:] *= 0.05
     scenes.append(Scene("band_prefilter_overflow_tiles", 128, 80, va, i, band=(32, 48), state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    # the bins themselves overflow (more than 8 tiles per triangle on average on a queue that has drawn nothing larger): the
+    # tiles without a list walk every triangle of the draw — 300 triangles as large as the frame, some through the eye plane;
+    # and 66 048 wide slivers, half of them on a band (the walk must skip the blocks the band prefilter dropped)
+    big = []
+    for k in range(300):
+        cx, cy = rng.uniform(-0.3, 0.3, 2)
+        col = [0.004, 0.008, 0.012, 0.004]
+        wz = -0.5 if k % 37 == 5 else 1.0
+        big += [[cx - 1.6, cy - 1.4, 0.5, 1.0, *col], [cx + 1.7, cy - 1.2, 0.5, 1.0, *col], [(cx + 0.1) * wz, (cy + 1.8) * wz, 0.5 * wz, wz, *col]]
+    scenes.append(Scene("bins_overflow_300_large_clipped", 512, 256, np.array(big, dtype=np.float32), pos_comps=4, color_offset=16,
+                        state=pipeline_state(blend=util.ADDITIVE_BLEND)))
+    sl = np.zeros((66048 * 3, 7), dtype=np.float32)
+    yy = np.repeat(np.where(np.arange(66048) % 512 < 256, rng.uniform(-0.1, 0.1, 66048), rng.uniform(0.4, 0.95, 66048)), 3)
+    sl[:, 0] = np.tile([-0.98, 0.98, 0.0], 66048) + np.repeat(rng.uniform(-0.02, 0.02, 66048), 3)
+    sl[:, 1] = yy + np.tile([0.0, 0.0, 0.012], 66048)
+    sl[:, 2] = 0.5
+    sl[:, 3:] = [0.002, 0.004, 0.006, 0.002]
+    scenes.append(Scene("bins_overflow_band_prefilter_66048_slivers", 2048, 256, sl, band=(96, 160), state=pipeline_state(blend=util.ADDITIVE_BLEND)))
     return scenes
