@@ -18,8 +18,12 @@
 //                    with the targets nested in the order their labels appear, so that leaving block t jumps to label t.
 // Values are scalarised, like everything the PTX back end lowers: a SPIR-V vector is a list of scalar IR values, OpLoad /
 // OpStore of a composite are one access per scalar, OpAccessChain with constant indices is `ptr_add` with a constant.
-// Not translated (KZN_ERROR_FEATURE_NOT_PRESENT, by opcode): loops (OpLoopMerge), function calls and parameters, images,
-// matrices, dynamic indexing, OpPhi other than at a selection's merge block.
+// Loops: `OpLoopMerge %merge %continue` becomes the IR's `loop` (see loop_construct): header OpPhis are the loop's parameters,
+// the back edge `continue`, a jump to %merge a `break` out of the loop's body block, a jump to %continue a `break` out of a
+// block that the continue block's code follows; conditional branches without a selection merge (the `while` test, `do ..
+// while`, conditional break / continue) nest their targets in a block that nothing follows.
+// Not translated (KZN_ERROR_FEATURE_NOT_PRESENT, by opcode): function calls and parameters, images, matrices, dynamic
+// indexing, values defined inside a loop and used after it other than through OpPhi or variables.
 #include <algorithm>
 #include <functional>
 #include <map>
@@ -91,7 +95,8 @@ struct BasicBlock {
     std::vector<Inst> body;
     Inst terminator;
     uint32_t merge = 0;  // OpSelectionMerge target, 0 = none
-    bool loop = false;
+    bool loop = false;   // OpLoopMerge: this block is a loop header
+    uint32_t loop_merge = 0, loop_continue = 0;
 };
 
 struct Translator {
@@ -233,6 +238,7 @@ struct FunctionTranslator {
     std::map<uint32_t, Block*> open;        // labels that are the exit of an IR block that is open right now
     std::map<uint32_t, std::vector<std::pair<uint32_t, uint32_t>>> phis;  // merge label -> [(result id, type id)] (+ operands kept in the Inst)
     std::map<uint32_t, std::vector<Inst>> phi_insts;
+    std::map<uint32_t, Loop*> loop_open;    // headers of the loops that are open right now: a jump to one is a `continue`
     std::set<uint32_t> emitted;
 
     FunctionTranslator(Translator& t, Function* f) : T(t), m(t.m), fn(f) {}
@@ -471,20 +477,115 @@ struct FunctionTranslator {
     }
 
     // emits the code of SPIR-V block `label` (and what follows it linearly) into IR block `b`; `body` is the function's body block
-    void region(uint32_t label, Block* b, Block* body) {
+    Block* new_child_block(const std::string& name, Block* parent) {
+        Block* nb = m.new_block(name);
+        Instr* bi = m.new_instr(Op::BlockI);
+        bi->block = nb;
+        parent->body.push_back(bi);
+        return nb;
+    }
+    // the OpPhis of `label` as the results of IR block `nb` (what a `break nb[...]` binds); `bind`: they are the phis' values from now on
+    void phis_as_results(uint32_t label, Block* nb, bool bind) {
+        auto it = phi_insts.find(label);
+        if (it == phi_insts.end()) return;
+        for (const Inst& p : it->second) {
+            Value* r = m.new_value(T.name_of(p.w[1]), T.scalar_ir_type(T.type(p.w[0])));
+            nb->results.push_back(r);
+            if (bind) {
+                SValue sv;
+                sv.scalars = {r};
+                values[p.w[1]] = sv;
+            }
+        }
+    }
+    void continue_to(Block* b, Loop* lp, const std::vector<Value*>& vals, const Location& loc) {
+        Instr* c = m.new_instr(Op::Continue);
+        c->loop = lp;
+        c->args = vals;
+        push(b, c, loc);
+    }
+
+    // A structured loop (header `label` with OpLoopMerge %merge %continue), entered from SPIR-V block `from`:
+    //   loop L[the header's OpPhi operands for `from`] -> [the merge block's OpPhis] { -> [the header's OpPhis]; L {
+    //       block <continue> -> [the continue block's OpPhis] { <header and body; a jump to %continue breaks out of this block,
+    //                                                            a jump to %merge out of L> }
+    //       <continue block ... its jump back to the header is `continue L[the header's OpPhi operands for it]`>
+    //   } }
+    // (a loop whose continue target is its own header has no inner block).  A value defined inside the loop is in scope inside
+    // it only: what a shader carries out of a loop goes through OpPhis of the merge block or through variables, which is
+    // what glslang emits.
+    void loop_construct(uint32_t label, Block* b, Block* body, uint32_t from) {
+        BasicBlock& bb = blocks.at(label);
+        const uint32_t merge = bb.loop_merge, cont = bb.loop_continue;
+        if (!blocks.count(merge) || !blocks.count(cont)) throw Error("SPIR-V: OpLoopMerge names a label that is not in the function");
+        if (open.count(merge) || loop_open.count(label)) Translator::unsupported("a loop whose merge block is the exit of an enclosing construct");
+        Loop* lp = m.new_loop(T.name_of(label));
+        if (phi_insts.count(label)) {
+            if (!from) Translator::unsupported("OpPhi in a loop header that is the function's first block");
+            lp->arguments = phi_arguments(label, from);
+            for (const Inst& p : phi_insts[label]) {
+                Value* r = m.new_value(T.name_of(p.w[1]), T.scalar_ir_type(T.type(p.w[0])));
+                lp->params.push_back(r);
+                SValue sv;
+                sv.scalars = {r};
+                values[p.w[1]] = sv;
+            }
+        }
+        Block* lbody = m.new_block(T.name_of(label));
+        phis_as_results(merge, lbody, true);
+        lp->results = lbody->results;
+        lp->body = lbody;
+        Instr* li = m.new_instr(Op::LoopI);
+        li->loop = lp;
+        push(b, li, bb.terminator.loc);
+        const std::map<uint32_t, Block*> saved_open = open;
+        const std::map<uint32_t, Loop*> saved_loops = loop_open;
+        open[merge] = lbody;
+        loop_open[label] = lp;
+        Block* inner = lbody;
+        if (cont != label) {
+            inner = new_child_block(T.name_of(cont), lbody);
+            phis_as_results(cont, inner, true);
+            open[cont] = inner;
+        }
+        region(label, inner, body, from, true);
+        if (cont != label) {
+            open.erase(cont);
+            region(cont, lbody, body, 0, false);
+        }
+        open = saved_open;
+        loop_open = saved_loops;
+    }
+
+    // emits the code of SPIR-V block `label` (and what follows it linearly) into IR block `b`; `body` is the function's body block;
+    // `from`: the SPIR-V block control comes from (0: function entry); `header_inside`: `label` is a loop header whose loop is open already
+    void region(uint32_t label, Block* b, Block* body, uint32_t from = 0, bool header_inside = false) {
         for (;;) {
             auto it = blocks.find(label);
             if (it == blocks.end()) throw Error("SPIR-V: branch to a label that is not in the function");
-            if (!emitted.insert(label).second) Translator::unsupported("a basic block reached twice without a merge (unstructured control flow)");
             BasicBlock& bb = it->second;
-            if (bb.loop) Translator::unsupported("loops (OpLoopMerge)");
+            if (bb.loop && !header_inside) {
+                loop_construct(label, b, body, from);
+                from = 0;  // (the merge block's own OpPhis were bound as the loop's results)
+                label = bb.loop_merge;
+                continue;
+            }
+            header_inside = false;
+            if (!emitted.insert(label).second) Translator::unsupported("a basic block reached twice without a merge (unstructured control flow)");
             for (const Inst& in : bb.body) instruction(b, in);
             const Inst& t = bb.terminator;
-            auto jump = [&](uint32_t target, Block* from_block) -> bool {  // true: the jump was a break to an open construct
+            auto jump = [&](uint32_t target, Block* from_block) -> bool {  // true: the jump left through an open construct
                 auto o = open.find(target);
-                if (o == open.end()) return false;
-                break_to(from_block, o->second, phi_arguments(target, label), t.loc);
-                return true;
+                if (o != open.end()) {
+                    break_to(from_block, o->second, phi_arguments(target, label), t.loc);
+                    return true;
+                }
+                auto lo = loop_open.find(target);
+                if (lo != loop_open.end()) {  // the back edge
+                    continue_to(from_block, lo->second, phi_arguments(target, label), t.loc);
+                    return true;
+                }
+                return false;
             };
             if (t.op == OpReturn) {
                 break_to(b, body, {}, t.loc);
@@ -493,12 +594,18 @@ struct FunctionTranslator {
             if (t.op == OpKill || t.op == OpUnreachable || t.op == OpReturnValue) Translator::unsupported("terminator opcode " + std::to_string(t.op));
             if (t.op == OpBranch) {
                 if (jump(t.w[0], b)) return;
+                from = label;
                 label = t.w[0];  // a straight-line successor: keep going in the same IR block
                 continue;
             }
             if (t.op != OpSwitch && t.op != OpBranchConditional) throw Error("SPIR-V: a basic block ends without a terminator");
-            if (!bb.merge) Translator::unsupported("a conditional branch without OpSelectionMerge");
-            // the construct's targets: every label the branch can reach that is not an already open construct's exit
+            // A conditional branch without OpSelectionMerge is legal where every way out leaves through an enclosing construct:
+            // the branch of a loop header (`while`), of a continue block (`do .. while`), a conditional break / continue.  Its
+            // targets are nested in a block that nothing follows.
+            const bool no_merge = !bb.merge;
+            if (no_merge && loop_open.empty()) Translator::unsupported("a conditional branch without OpSelectionMerge outside a loop");
+            // the construct's targets: every label the branch can reach that is not an already open construct's exit; the
+            // header of an open loop is one too (a `branch` case can only `break`: it breaks to a block that holds the `continue`)
             std::vector<uint32_t> targets;
             auto add_target = [&](uint32_t l) {
                 if (l != bb.merge && !open.count(l) && std::find(targets.begin(), targets.end(), l) == targets.end()) targets.push_back(l);
@@ -515,29 +622,28 @@ struct FunctionTranslator {
             }
             std::sort(targets.begin(), targets.end(), [&](uint32_t x, uint32_t y) { return blocks.at(x).order < blocks.at(y).order; });
             // block merge { block t_last { ... block t_first { branch } <t_first> } ... <t_last> }
-            auto make_block = [&](uint32_t l, Block* parent) {
-                Block* nb = m.new_block(T.name_of(l));
-                Instr* bi = m.new_instr(Op::BlockI);
-                bi->block = nb;
-                parent->body.push_back(bi);
-                return nb;
-            };
-            Block* merge_block = make_block(bb.merge, b);
-            // the merge block's OpPhis are the results of its IR block
-            if (phi_insts.count(bb.merge))
-                for (const Inst& p : phi_insts[bb.merge]) {
-                    Value* r = m.new_value(T.name_of(p.w[1]), T.scalar_ir_type(T.type(p.w[0])));
-                    merge_block->results.push_back(r);
-                    SValue sv;
-                    sv.scalars = {r};
-                    values[p.w[1]] = sv;
-                }
+            Block* merge_block;
+            if (no_merge) {
+                merge_block = new_child_block(T.name_of(label) + "_branch", b);
+                merge_block->diverges = true;
+            } else {
+                merge_block = new_child_block(T.name_of(bb.merge), b);
+                phis_as_results(bb.merge, merge_block, true);  // the merge block's OpPhis are the results of its IR block
+            }
             const std::map<uint32_t, Block*> saved_open = open;
-            open[bb.merge] = merge_block;
+            if (!no_merge) open[bb.merge] = merge_block;
             std::vector<Block*> nest(targets.size());
+            std::vector<Loop*> back_edge(targets.size(), nullptr);
             Block* parent = merge_block;
             for (size_t k = targets.size(); k-- > 0;) {
-                nest[k] = make_block(targets[k], parent);
+                auto lo = loop_open.find(targets[k]);
+                if (lo != loop_open.end()) {  // the header of an open loop: the block's results are what `continue` passes on
+                    back_edge[k] = lo->second;
+                    nest[k] = new_child_block(T.name_of(targets[k]) + "_continue", parent);
+                    phis_as_results(targets[k], nest[k], false);
+                } else {
+                    nest[k] = new_child_block(T.name_of(targets[k]), parent);
+                }
                 parent = nest[k];
             }
             for (size_t k = 0; k < targets.size(); ++k) open[targets[k]] = nest[k];
@@ -578,9 +684,12 @@ struct FunctionTranslator {
             for (size_t k = 0; k < targets.size(); ++k) {
                 open.erase(targets[k]);
                 Block* where = k + 1 < targets.size() ? nest[k + 1] : merge_block;
-                region(targets[k], where, body);
+                if (back_edge[k]) continue_to(where, back_edge[k], nest[k]->results, t.loc);
+                else region(targets[k], where, body, label, false);
             }
             open = saved_open;
+            if (no_merge) return;  // nothing follows: every path left through an enclosing construct
+            from = 0;
             label = bb.merge;  // the merge block's code follows the construct, in the block the construct lives in
         }
     }
@@ -641,7 +750,10 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
                 need(2);
                 bb->merge = o[0];
             } else if (op == OpLoopMerge) {
+                need(2);
                 bb->loop = true;
+                bb->loop_merge = o[0];
+                bb->loop_continue = o[1];
             } else if (op == OpBranch || op == OpBranchConditional || op == OpSwitch || op == OpReturn || op == OpReturnValue || op == OpKill ||
                        op == OpUnreachable) {
                 bb->terminator = in;

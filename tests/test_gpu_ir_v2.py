@@ -135,6 +135,29 @@ def _saxpy(gpu, W, H, local, check_interpreter):
     gpu.release()
 
 
+@pytest.mark.parametrize("kind", ["variables", "phis"])
+def test_translated_spirv_loops_run_and_match_the_source_loops(gpu, kind):
+    """SPIR-V loop -> the IR's `loop` -> PTX -> sm_100a (tests/spirv_loop_shaders.py: loop state in Function variables with a
+    `continue` and a `break` inside selections; loop state in OpPhis): 4096 invocations whose trip counts differ inside every
+    warp (divergent loops), against what the source loops compute in fp32"""
+    from tests import spirv_loop_shaders as shaders
+    module, _ = backend.translate_spirv_to_ir(getattr(shaders, kind)(), "main", backend.EXECUTION_MODEL_VERTEX, 2)
+    a = shaders.inputs(4096, seed=9)
+    pipe = backend.ComputePipeline(gpu.device, module, (64, 1, 1))
+    assert pipe.inputs_size == shaders.SLOT.itemsize and pipe.outputs_size == shaders.OUT.itemsize
+    ibuf = gpu.buffer(a.nbytes, a)
+    obuf = gpu.buffer(shaders.OUT.itemsize * len(a), np.full(shaders.OUT.itemsize * len(a), 0xEE, dtype=np.uint8))
+    gpu.queue.cmd_dispatch(pipe, (len(a) // 64, 1, 1), ibuf.address, obuf.address)
+    gpu.queue.wait_idle()
+    got = obuf.download()[:shaders.OUT.itemsize * len(a)].view(shaders.OUT)
+    want = shaders.expected(kind, a)
+    assert np.array_equal(got["i"], want["i"])
+    assert np.array_equal(got["acc"].view(np.uint32), want["acc"].view(np.uint32))
+    pipe.destroy()
+    module.destroy()
+    gpu.release()
+
+
 def test_buffer_to_buffer_shader_through_a_descriptor_set_matches_interpreter(gpu):
     """f1: y = alpha * x + y over two STORAGE_BUFFER descriptors, alpha and the row length in push constants, the element
     index from global_invocation_id (16 x 12 invocations, LocalSize 8 x 4)"""
