@@ -198,8 +198,9 @@ def test_invalid_draw_state_is_rejected():
     wide = abi.VertexInput(sc.vertices.ctypes.data, sc.vertices.nbytes, 1 << 28, 0, 3, 12)
     assert lib.kzo_draw(C.byref(pipeline_state()), C.byref(fb), C.byref(sc.viewport), C.byref(sc.scissor), C.byref(wide), 3, 1, 0, 0,
                         None) == abi.ERROR_VALIDATION_FAILED  # index x stride must stay far from 2^64
-    lines = pipeline_state(topology=1)
-    assert args(lines, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
+    adjacency = pipeline_state(topology=6)  # LINE_LIST_WITH_ADJACENCY .. PATCH_LIST: not rasterised (points, lines and strips are: R9)
+    assert args(adjacency, sc.viewport) == abi.ERROR_FEATURE_NOT_PRESENT
+    assert args(pipeline_state(topology=11), sc.viewport) == abi.ERROR_VALIDATION_FAILED
     bad = pipeline_state()
     bad.logic_op = 17
     assert args(bad, sc.viewport) == abi.ERROR_VALIDATION_FAILED
