@@ -695,6 +695,144 @@ struct FunctionTranslator {
     }
 };
 
+// ---- values that leave the block they are defined in -------------------------------------------------------------------
+// SPIR-V lets an id be used wherever its definition dominates the use; the IR scopes a value to the block it is defined in
+// (text.rs scope stack).  After translation a use can therefore sit outside its definition's block — a value of a loop body
+// used in the continue block, a value of the header used after the loop.  Such a value is handed out through the results of
+// every block between the definition and the use: each `break` to that block passes the value where it is in scope (and
+// `undef` where it is not: by dominance such a break cannot lead to the use), and the uses outside are renamed to the result.
+struct ScopeFixer {
+    Translator& T;
+    Module& m;
+    std::map<const Block*, Block*> parent;      // enclosing block (for a loop's body block: the block that holds the loop)
+    std::map<const Block*, Loop*> loop_of_body; // body block -> its loop
+    explicit ScopeFixer(Translator& t) : T(t), m(t.m) {}
+
+    void index(Block* b) {
+        for (Instr* in : b->body) {
+            if (in->op == Op::BlockI) { parent[in->block] = b; index(in->block); }
+            if (in->op == Op::LoopI) { parent[in->loop->body] = b; loop_of_body[in->loop->body] = in->loop; index(in->loop->body); }
+        }
+    }
+    static bool has(const std::vector<Value*>& v, const Value* x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+    // first use of a value that is not in scope: the value (or null) and the block that holds the use
+    Value* offender = nullptr;
+    Block* offender_home = nullptr;
+    void check_use(Value* v, const std::set<const Value*>& visible, Block* where) {
+        if (offender || !v || v->has_const || visible.count(v)) return;
+        offender = v;
+        offender_home = where;  // (the block that holds the use)
+    }
+    void scan(Block* b, std::set<const Value*> visible) {
+        for (Instr* in : b->body) {
+            if (offender) return;
+            for (Value* a : in->args) check_use(a, visible, b);
+            for (BranchCase& c : in->cases)
+                for (Value* a : c.results) check_use(a, visible, b);
+            if (in->op == Op::BlockI) {
+                scan(in->block, visible);
+                for (Value* r : in->block->results) visible.insert(r);
+            } else if (in->op == Op::LoopI) {
+                for (Value* a : in->loop->arguments) check_use(a, visible, b);
+                std::set<const Value*> inner = visible;
+                for (Value* pv : in->loop->params) inner.insert(pv);
+                scan(in->loop->body, inner);
+                for (Value* r : in->loop->results) visible.insert(r);
+            } else {
+                for (Value* r : in->results) visible.insert(r);
+            }
+        }
+    }
+    // the block whose body holds the definition of v (an instruction result, or the results of a nested block / loop, which
+    // are defined in the block that holds the nested one); null: v is a loop parameter or a function-level value
+    Block* home_of(Block* b, const Value* v) {
+        for (Instr* in : b->body) {
+            if (has(in->results, v)) return b;
+            if (in->op == Op::BlockI) {
+                if (has(in->block->results, v)) return b;
+                if (Block* h = home_of(in->block, v)) return h;
+            }
+            if (in->op == Op::LoopI) {
+                if (has(in->loop->results, v)) return b;
+                if (has(in->loop->params, v)) return in->loop->body;
+                if (Block* h = home_of(in->loop->body, v)) return h;
+            }
+        }
+        return nullptr;
+    }
+    // every `break x` under b gets one more value: v where it is in scope, undef elsewhere
+    void pass_out(Block* b, Block* x, Value* v, Value* undef, bool in_scope) {
+        for (Instr* in : b->body) {
+            if (in->op == Op::Break && in->block == x) in->args.push_back(in_scope ? v : undef);
+            for (BranchCase& c : in->cases)
+                if (c.target == x) c.results.push_back(in_scope ? v : undef);
+            if (in->op == Op::BlockI) {
+                pass_out(in->block, x, v, undef, in_scope);
+                if (has(in->block->results, v)) in_scope = true;
+            } else if (in->op == Op::LoopI) {
+                pass_out(in->loop->body, x, v, undef, in_scope || has(in->loop->params, v));
+                if (has(in->loop->results, v)) in_scope = true;
+            } else if (has(in->results, v)) {
+                in_scope = true;
+            }
+        }
+    }
+    // uses of v anywhere except inside block x (and its nested blocks) become r
+    void rename_outside(Block* b, Block* x, Value* v, Value* r) {
+        if (b == x) return;
+        for (Instr* in : b->body) {
+            for (Value*& a : in->args)
+                if (a == v) a = r;
+            for (BranchCase& c : in->cases)
+                for (Value*& a : c.results)
+                    if (a == v) a = r;
+            if (in->op == Op::BlockI) rename_outside(in->block, x, v, r);
+            if (in->op == Op::LoopI) {
+                for (Value*& a : in->loop->arguments)
+                    if (a == v) a = r;
+                rename_outside(in->loop->body, x, v, r);
+            }
+        }
+    }
+    void run(Function* fn) {
+        index(fn->body);
+        for (int round = 0; round < 10000; ++round) {
+            offender = nullptr;
+            std::set<const Value*> visible;
+            for (Value* pv : fn->params) visible.insert(pv);
+            for (const Variable& var : fn->locals) visible.insert(var.pointer);
+            for (const Variable& var : m.built_in_inputs) visible.insert(var.pointer);
+            for (const Variable& var : m.built_in_outputs) visible.insert(var.pointer);
+            for (const Variable& var : m.globals) visible.insert(var.pointer);
+            visible.insert(m.user_inputs.pointer);
+            visible.insert(m.user_outputs.pointer);
+            scan(fn->body, visible);
+            if (!offender) return;
+            Value* v = offender;
+            // x: the block to hand v out of — the outermost block around the definition that does not also hold the use
+            Block* x = home_of(fn->body, v);
+            std::set<const Block*> around_use;
+            for (const Block* u = offender_home; u; u = parent.count(u) ? parent[u] : nullptr) around_use.insert(u);
+            if (!x || around_use.count(x)) throw Error("internal: SPIR-V -> IR left a value used before its definition ('" + v->name + "')");
+            while (parent.count(x) && !around_use.count(parent[x])) x = parent[x];
+            if (x->diverges) throw Error("internal: SPIR-V -> IR: a value would have to leave a block that nothing follows");
+            Value* r = m.new_value(v->name, v->type);  // (the printer tells equal names apart by a suffix)
+            Value* undef = T.constant(v->type, 0, ConstKind::Undef);
+            pass_out(x, x, v, undef, has_param(x, v));
+            x->results.push_back(r);
+            auto lb = loop_of_body.find(x);
+            if (lb != loop_of_body.end()) lb->second->results.push_back(r);
+            rename_outside(fn->body, x, v, r);
+        }
+        throw Error("internal: SPIR-V -> IR scope repair does not terminate");
+    }
+    bool has_param(Block* x, const Value* v) {
+        auto lb = loop_of_body.find(x);
+        return lb != loop_of_body.end() && has(lb->second->params, v);
+    }
+};
+
 }  // namespace
 
 std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, const std::string& entry_point, uint32_t execution_model,
@@ -999,6 +1137,7 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
     Block* body = m.new_block(T.name_of(fb->blocks.front().label));
     fn->body = body;
     F.region(fb->blocks.front().label, body, body);
+    ScopeFixer(T).run(fn);
     m.functions.push_back(fn);
     m.entry_point = fn;
     auto ls = local_sizes.find(entry->id);

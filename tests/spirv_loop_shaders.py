@@ -10,6 +10,7 @@
   `continue` and a `break` from inside selection constructs.
 `phis` — the optimised shape of  for (i = 0; i < n; ++i) acc = acc * 0.5 + x;  loop state in OpPhis of the header, the
   conditional branch in the header itself, OpPhis in the continue block and in the merge block.
+`do_while`, `nested` — see the functions.
 """
 import struct
 
@@ -93,6 +94,77 @@ def phis():
     return assemble(pro + body, 200)
 
 
+def header_values_after_loop():
+    """`phis` without OpPhis in the continue and merge blocks: the continue block uses a value of the body, the code after the
+    loop values of the header — legal SPIR-V (the definitions dominate the uses), outside the defining block in the IR: the
+    translator hands them out through block results"""
+    i = _Ids()
+    pro = _prologue(i)
+    body = [("Label", i("entry")), ("Load", i("int"), i("n"), i("nin")), ("Load", i("float"), i("x"), i("xin")), ("Branch", i("H")),
+            ("Label", i("H")),
+            ("Phi", i("int"), i("iv"), i("i0"), i("entry"), i("inc"), i("C")),
+            ("Phi", i("float"), i("acc"), i("f0"), i("entry"), i("a2"), i("C")),
+            ("LoopMerge", i("M"), i("C"), 0), ("SLessThan", i("bool"), i("c"), i("iv"), i("n")),
+            ("FAdd", i("float"), i("hsum"), i("acc"), i("f0")),
+            ("BranchConditional", i("c"), i("B"), i("M")),
+            ("Label", i("B")), ("FMul", i("float"), i("a1"), i("acc"), i("f05")), ("FAdd", i("float"), i("a2"), i("a1"), i("x")),
+            ("Branch", i("C")),
+            ("Label", i("C")), ("IAdd", i("int"), i("inc"), i("iv"), i("i1")), ("Branch", i("H")),
+            ("Label", i("M")), ("Store", i("acc_out"), i("hsum")), ("Store", i("i_out"), i("iv")),
+            ("Return",), ("FunctionEnd",)]
+    return assemble(pro + body, 200)
+
+
+def do_while():
+    """do { acc = acc * 0.5 + x; ++i; } while (i < n);  — the conditional back edge sits in the continue block (no selection
+    merge: `true` continues, `false` leaves), the header only branches into the body; loop state in OpPhis"""
+    i = _Ids()
+    pro = _prologue(i)
+    body = [("Label", i("entry")), ("Load", i("int"), i("n"), i("nin")), ("Load", i("float"), i("x"), i("xin")), ("Branch", i("H")),
+            ("Label", i("H")),
+            ("Phi", i("int"), i("iv"), i("i0"), i("entry"), i("inc"), i("C")),
+            ("Phi", i("float"), i("acc"), i("f0"), i("entry"), i("a2"), i("C")),
+            ("LoopMerge", i("M"), i("C"), 0), ("Branch", i("B")),
+            ("Label", i("B")), ("FMul", i("float"), i("a1"), i("acc"), i("f05")), ("FAdd", i("float"), i("a2"), i("a1"), i("x")),
+            ("Branch", i("C")),
+            ("Label", i("C")), ("IAdd", i("int"), i("inc"), i("iv"), i("i1")), ("SLessThan", i("bool"), i("c"), i("inc"), i("n")),
+            ("BranchConditional", i("c"), i("H"), i("M")),
+            ("Label", i("M")), ("Phi", i("float"), i("rf"), i("a2"), i("C")), ("Phi", i("int"), i("ri"), i("inc"), i("C")),
+            ("Store", i("acc_out"), i("rf")), ("Store", i("i_out"), i("ri")),
+            ("Return",), ("FunctionEnd",)]
+    return assemble(pro + body, 200)
+
+
+def nested():
+    """for (i = 0; i < n; ++i) for (j = 0; j < i; ++j) acc = acc * 0.5 + x + float(j);  — a loop inside a loop's body, both
+    with their state in Function variables; out.i = i"""
+    i = _Ids()
+    pro = _prologue(i)
+    body = [("Label", i("entry")),
+            ("Variable", i("p_fn_f"), i("acc"), FUNCTION), ("Variable", i("p_fn_i"), i("i"), FUNCTION), ("Variable", i("p_fn_i"), i("j"), FUNCTION),
+            ("Store", i("acc"), i("f0")), ("Store", i("i"), i("i0")),
+            ("Load", i("int"), i("n"), i("nin")), ("Load", i("float"), i("x"), i("xin")), ("Branch", i("H")),
+            ("Label", i("H")), ("LoopMerge", i("M"), i("C"), 0), ("Branch", i("T")),
+            ("Label", i("T")), ("Load", i("int"), i("iv"), i("i")), ("SLessThan", i("bool"), i("c"), i("iv"), i("n")),
+            ("BranchConditional", i("c"), i("B"), i("M")),
+            ("Label", i("B")), ("Store", i("j"), i("i0")), ("Branch", i("H2")),
+            ("Label", i("H2")), ("LoopMerge", i("M2"), i("C2"), 0), ("Branch", i("T2")),
+            ("Label", i("T2")), ("Load", i("int"), i("jv"), i("j")), ("Load", i("int"), i("iv4"), i("i")),
+            ("SLessThan", i("bool"), i("c2"), i("jv"), i("iv4")), ("BranchConditional", i("c2"), i("B2"), i("M2")),
+            ("Label", i("B2")), ("Load", i("float"), i("a0"), i("acc")), ("FMul", i("float"), i("a1"), i("a0"), i("f05")),
+            ("FAdd", i("float"), i("a2"), i("a1"), i("x")), ("Load", i("int"), i("jv2"), i("j")), ("ConvertSToF", i("float"), i("fj"), i("jv2")),
+            ("FAdd", i("float"), i("a3"), i("a2"), i("fj")), ("Store", i("acc"), i("a3")), ("Branch", i("C2")),
+            ("Label", i("C2")), ("Load", i("int"), i("jv3"), i("j")), ("IAdd", i("int"), i("jinc"), i("jv3"), i("i1")), ("Store", i("j"), i("jinc")),
+            ("Branch", i("H2")),
+            ("Label", i("M2")), ("Branch", i("C")),
+            ("Label", i("C")), ("Load", i("int"), i("iv3"), i("i")), ("IAdd", i("int"), i("inc"), i("iv3"), i("i1")), ("Store", i("i"), i("inc")),
+            ("Branch", i("H")),
+            ("Label", i("M")), ("Load", i("float"), i("af"), i("acc")), ("Store", i("acc_out"), i("af")),
+            ("Load", i("int"), i("if"), i("i")), ("Store", i("i_out"), i("if")),
+            ("Return",), ("FunctionEnd",)]
+    return assemble(pro + body, 200)
+
+
 SLOT = np.dtype([("x", "<f4"), ("pad0", "V12"), ("n", "<i4"), ("pad1", "V12")])       # one Location per 16 bytes
 OUT = np.dtype([("acc", "<f4"), ("pad0", "V12"), ("i", "<i4"), ("pad1", "V12")])
 
@@ -101,7 +173,7 @@ def inputs(count=64, seed=5):
     rng = np.random.default_rng(seed)
     a = np.zeros(count, dtype=SLOT)
     a["x"] = rng.uniform(-3, 12, count).astype(np.float32)
-    a["n"] = rng.integers(-2, 40, count)
+    a["n"] = rng.integers(-2, 24, count)
     a["n"][:4] = [0, 1, 2, 39]
     return a
 
@@ -118,9 +190,20 @@ def expected(kind, a):
                     if acc > f(100.0):
                         break
                 i += 1
-        else:
+        elif kind in ("phis", "header_values_after_loop"):
             while i < n:
                 acc = f(f(acc * f(0.5)) + x)
+                i += 1
+        elif kind == "do_while":
+            while True:
+                acc = f(f(acc * f(0.5)) + x)
+                i += 1
+                if not i < n:
+                    break
+        else:  # nested
+            while i < n:
+                for j in range(i):
+                    acc = f(f(f(acc * f(0.5)) + x) + f(j))
                 i += 1
         out["acc"][k], out["i"][k] = acc, i
     return out

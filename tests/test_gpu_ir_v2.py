@@ -135,7 +135,7 @@ def _saxpy(gpu, W, H, local, check_interpreter):
     gpu.release()
 
 
-@pytest.mark.parametrize("kind", ["variables", "phis"])
+@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop"])
 def test_translated_spirv_loops_run_and_match_the_source_loops(gpu, kind):
     """SPIR-V loop -> the IR's `loop` -> PTX -> sm_100a (tests/spirv_loop_shaders.py: loop state in Function variables with a
     `continue` and a `break` inside selections; loop state in OpPhis): 4096 invocations whose trip counts differ inside every

@@ -20,7 +20,7 @@ def _translate(kind):
     return module
 
 
-@pytest.mark.parametrize("kind", ["variables", "phis"])
+@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop"])
 def test_loop_shader_translates_round_trips_and_assembles(kind, tmp_path):
     from oracle import ir_oracle as iro
     module = _translate(kind)
@@ -30,6 +30,10 @@ def test_loop_shader_translates_round_trips_and_assembles(kind, tmp_path):
         assert "[c0: 0x0i32, c2: f32 0x0] -> [" in text.replace("\n", " ") or "loop" in text
         header = next(line for line in text.splitlines() if line.strip().startswith("loop "))
         assert header.count(":") >= 2 and "-> [" in header, header
+    elif kind == "do_while":  # the back edge under a condition: a block whose results `continue` passes on
+        assert "_continue -> [" in text and text.count("continue id_") == 1
+    elif kind == "nested":
+        assert text.count("loop id_") == 2 and text.count("continue id_") == 2
     else:
         assert "_branch -> !" in text, "the test block's conditional branch has no selection merge: a block nothing follows"
     assert backend.IrModule.parse(text, 2).to_text() == text
@@ -40,7 +44,7 @@ def test_loop_shader_translates_round_trips_and_assembles(kind, tmp_path):
         assert r.returncode == 0, r.stderr
 
 
-@pytest.mark.parametrize("kind", ["variables", "phis"])
+@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop"])
 def test_loop_shader_runs_in_the_interpreter(kind):
     from oracle import ir_oracle as iro
     from oracle import ir_simt as sim
