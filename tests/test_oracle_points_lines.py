@@ -115,3 +115,38 @@ def test_strips_and_quads_hit_every_pixel_once():
         cols = np.nonzero((img & 0xFF).sum(axis=0))[0]
         first, last = int(np.ceil((xs[0] * 16 - 8) / 16)), int(np.ceil((xs[-1] * 16 - 8) / 16)) - 1
         assert cols.tolist() == list(range(max(first, 0), min(last, W - 1) + 1)), "a column of the polyline has no pixel"
+
+
+def test_line_attributes_run_along_the_major_axis_perspective_correct():
+    """R9 / R6 against float64: at a covered pixel the colour is the perspective-correct blend of the two ends' colours at the
+    pixel centre's position along the major axis, the depth the screen-linear one (within 1 LSB of UNORM8 / 1e-6)."""
+    rng = np.random.default_rng(5)
+    for k in range(60):
+        ax, ay = rng.integers(2 * 2, (W - 2) * 2) / 2.0, rng.integers(2 * 2, (H - 2) * 2) / 2.0
+        bx, by = rng.integers(2 * 2, (W - 2) * 2) / 2.0, rng.integers(2 * 2, (H - 2) * 2) / 2.0
+        wa, wb = float(rng.uniform(0.5, 4.0)), float(rng.uniform(0.5, 4.0))
+        za, zb = float(rng.uniform(0.0, 1.0)), float(rng.uniform(0.0, 1.0))
+        ca, cb = rng.uniform(0, 1, 4), rng.uniform(0, 1, 4)
+        va = [c * wa for c in ndc(ax, ay)] + [za * wa, wa, *ca]
+        vb = [c * wb for c in ndc(bx, by)] + [zb * wb, wb, *cb]
+        st = pipeline_state(topology=abi.TOPOLOGY_LINE_LIST, depth=(abi.COMPARE_ALWAYS, 1))
+        sc = Scene("t", W, H, np.array([va, vb], dtype=np.float32), state=st, pos_comps=4, color_offset=16, use_depth=True, clear_depth=1.0)
+        color, depth, _ = sc.run_oracle()
+        img = color.reshape(H, W, 4)
+        dep = depth.view(np.float32).reshape(H, W)
+        Xa, Ya, Xb, Yb = snap(ax), snap(ay), snap(bx), snap(by)
+        x_major = abs(Xb - Xa) >= abs(Yb - Ya)
+        hits = np.argwhere(dep != 1.0)
+        if Xa == Xb and Ya == Yb:
+            assert len(hits) == 0
+            continue
+        for py, px in hits:
+            t = (16 * px + 8 - Xa) / (Xb - Xa) if x_major else (16 * py + 8 - Ya) / (Yb - Ya)
+            assert -1e-9 <= t <= 1 + 1e-9
+            fwa, fwb = np.float64(np.float32(wa)), np.float64(np.float32(wb))
+            den = (1 - t) / fwa + t / fwb
+            want_c = ((1 - t) * np.float32(ca).astype(np.float64) / fwa + t * np.float32(cb).astype(np.float64) / fwb) / den
+            got_c = img[py, px].astype(np.float64) / 255.0
+            assert np.all(np.abs(got_c - want_c) <= 1.0 / 255.0 + 1e-6), (k, px, py, got_c, want_c)
+            za32, zb32 = np.float64(np.float32(za * wa) / np.float32(wa)), np.float64(np.float32(zb * wb) / np.float32(wb))
+            assert abs(float(dep[py, px]) - ((1 - t) * za32 + t * zb32)) <= 2e-6, (k, px, py)
