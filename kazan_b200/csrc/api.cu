@@ -553,8 +553,9 @@ KznResult kzn_command_buffer_begin(KznQueue* queue, KznCommandBuffer** command_b
 KznResult kzn_command_buffer_end(KznCommandBuffer* cb) {
     KZN_VALID(cb && cb->recording, "vkEndCommandBuffer: the command buffer is not in the recording state");
     KznQueue* queue = cb->queue;
-    KznResult r = kzn_queue_enter(queue);
+    KznResult r = kzn_queue_enter(queue);  // (a render pass clear that no draw took over is recorded here at the latest)
     if (r) return r;
+    queue->in_render_pass = false;  // vkEndCommandBuffer inside a render pass is invalid usage (VUID 00060): the pass ends with its command buffer
     queue->recording = nullptr;
     cb->recording = false;
     cb->launches = queue->launches - cb->launches_at_begin;
