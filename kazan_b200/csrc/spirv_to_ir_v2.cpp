@@ -240,6 +240,7 @@ struct FunctionTranslator {
     std::map<uint32_t, std::vector<Inst>> phi_insts;
     std::map<uint32_t, Loop*> loop_open;    // headers of the loops that are open right now: a jump to one is a `continue`
     std::set<uint32_t> emitted;
+    std::set<uint32_t> loops_built;
 
     FunctionTranslator(Translator& t, Function* f) : T(t), m(t.m), fn(f) {}
 
@@ -518,6 +519,8 @@ struct FunctionTranslator {
         BasicBlock& bb = blocks.at(label);
         const uint32_t merge = bb.loop_merge, cont = bb.loop_continue;
         if (!blocks.count(merge) || !blocks.count(cont)) throw Error("SPIR-V: OpLoopMerge names a label that is not in the function");
+        if (merge == label || merge == cont) throw Error("SPIR-V: a loop's merge block is its header or its continue target");
+        if (!loops_built.insert(label).second) Translator::unsupported("a loop header reached twice (unstructured control flow)");
         if (open.count(merge) || loop_open.count(label)) Translator::unsupported("a loop whose merge block is the exit of an enclosing construct");
         Loop* lp = m.new_loop(T.name_of(label));
         if (phi_insts.count(label)) {

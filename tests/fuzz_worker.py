@@ -62,6 +62,9 @@ def main(seed, iterations):
     spv = [words_of(base64.b64decode(c["spv_base64"])) for c in
            json.loads((ROOT / "tests/golden/spirv_goldens.json").read_text())["cases"]]
     ir = json.loads((ROOT / "tests/golden/ir_goldens.json").read_text())
+    from tests import spirv_loop_shaders as loops  # hand-assembled shaders with loops: the version 2 translator's corpus
+    spv2 = spv + [getattr(loops, k)() for k in ("variables", "phis", "do_while", "nested", "header_values_after_loop")]
+    texts2 = [p.read_text() for p in sorted((ROOT / "tests/ir_programs_v2").glob("*.kazan-ir"))]
     texts = [p.read_text() for p in sorted((ROOT / "tests/ir_programs").glob("*.kazan-ir"))]
     texts += [v for v in json.dumps(ir).split('"') if "fn " in v or "block" in v][:20]
     pairs = [(v["kind"], v["text"]) for v in ir["text_round_trips"]]  # (grammar production, text) of the reference's vectors
@@ -80,6 +83,26 @@ def main(seed, iterations):
         if w:
             attempt(lambda: backend.disassemble_spirv(w))
             attempt(lambda: backend.translate_spirv_to_ir(w, "main", rng.choice([0, 4, 5]))[0].destroy())
+        w2 = mutate_words(rng, rng.choice(spv2))
+        if w2:  # version 2: loads, stores, selections, loops, the scope repair
+            def translate_v2():
+                m = backend.translate_spirv_to_ir(w2, "main", rng.choice([0, 4, 5]), 2)[0]
+                try:
+                    m.to_text()
+                    m.to_ptx()
+                finally:
+                    m.destroy()
+            attempt(translate_v2)
+        t2 = mutate_text(rng, rng.choice(texts2))
+
+        def parse_and_emit_v2():
+            m = backend.IrModule.parse(t2, 2)
+            try:
+                m.to_text()
+                m.to_ptx()
+            finally:
+                m.destroy()
+        attempt(parse_and_emit_v2)
         t = mutate_text(rng, rng.choice(texts))
 
         def parse_and_emit():

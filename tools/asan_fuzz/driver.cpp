@@ -16,6 +16,8 @@ int main(int argc, char** argv) {
         try {
             if (kind == 0) { std::vector<uint32_t> w(len / 4); if (len >= 4) memcpy(w.data(), &buf[i], len / 4 * 4); kir::disassemble_spirv(w.data(), w.size()); }
             else if (kind == 1) { std::vector<uint32_t> w(len / 4); if (len >= 4) memcpy(w.data(), &buf[i], len / 4 * 4); uint32_t ls[3]; kir::translate_spirv(w.data(), w.size(), "main", 5, ls); }
+            else if (kind == 4) { std::vector<uint32_t> w(len / 4); if (len >= 4) memcpy(w.data(), &buf[i], len / 4 * 4); uint32_t ls[3]; auto m = kir::translate_spirv_v2(w.data(), w.size(), "main", 0, ls); kir::module_to_text(*m); kir::emit_ptx(*m, nullptr); }
+            else if (kind == 5) { auto m = kir::parse_module(std::string((const char*)&buf[i], len), 2); kir::module_to_text(*m); kir::emit_ptx(*m, nullptr); }
             else if (kind == 2) { auto m = kir::parse_module(std::string((const char*)&buf[i], len)); kir::module_to_text(*m); kir::emit_ptx(*m, nullptr); }
             else { size_t z = 0; while (z < len && buf[i + z]) ++z; std::string k((const char*)&buf[i], z); if (z < len) kir::round_trip(k, std::string((const char*)&buf[i + z + 1], len - z - 1)); }
             ++ok;
