@@ -41,7 +41,7 @@ enum : uint32_t {
     OpExtension = 10, OpExtInstImport = 11, OpExtInst = 12, OpMemoryModel = 14, OpEntryPoint = 15, OpExecutionMode = 16, OpCapability = 17,
     OpTypeVoid = 19, OpTypeBool = 20, OpTypeInt = 21, OpTypeFloat = 22, OpTypeVector = 23, OpTypeArray = 28, OpTypeStruct = 30, OpTypePointer = 32,
     OpTypeFunction = 33, OpConstantTrue = 41, OpConstantFalse = 42, OpConstant = 43, OpConstantComposite = 44, OpFunction = 54,
-    OpFunctionParameter = 55, OpFunctionEnd = 56, OpVariable = 59, OpLoad = 61, OpStore = 62, OpAccessChain = 65, OpInBoundsAccessChain = 66,
+    OpFunctionParameter = 55, OpFunctionEnd = 56, OpFunctionCall = 57, OpVariable = 59, OpLoad = 61, OpStore = 62, OpAccessChain = 65, OpInBoundsAccessChain = 66,
     OpDecorate = 71, OpMemberDecorate = 72, OpCompositeConstruct = 80, OpCompositeExtract = 81, OpConvertFToU = 109, OpConvertFToS = 110,
     OpConvertSToF = 111, OpConvertUToF = 112, OpUConvert = 113, OpSConvert = 114, OpFConvert = 115, OpBitcast = 124, OpSNegate = 126, OpFNegate = 127,
     OpIAdd = 128, OpFAdd = 129, OpISub = 130, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136, OpLogicalOr = 166, OpLogicalAnd = 167,
@@ -99,9 +99,17 @@ struct BasicBlock {
     uint32_t loop_merge = 0, loop_continue = 0;
 };
 
+struct FunctionBody {  // one OpFunction .. OpFunctionEnd
+    uint32_t id = 0, control = 0, return_type = 0;
+    std::vector<uint32_t> params;  // OpFunctionParameter result ids
+    std::vector<BasicBlock> blocks;
+};
+
 struct Translator {
     Module& m;
     uint32_t bound;
+    std::map<uint32_t, const FunctionBody*> spv_functions;  // callable functions by id (OpFunctionCall inlines them)
+    std::vector<uint32_t> call_stack;                    // functions being inlined right now (recursion is refused)
     std::map<uint32_t, std::string> names, strings;
     std::map<uint32_t, SType> types;
     std::map<uint32_t, std::map<uint32_t, uint32_t>> decorations;                         // id -> decoration -> literal
@@ -137,6 +145,7 @@ struct Translator {
     // packed; every scalar naturally aligned)
     void leaves(uint32_t type_id, uint64_t at, std::vector<std::pair<uint64_t, const Type*>>* out) {
         const SType& t = type(type_id);
+        if (out->size() > 65536) unsupported("a value of more than 65536 scalars (nested arrays)");
         switch (t.kind) {
             case SType::Vector:
             case SType::Array: {
@@ -244,6 +253,23 @@ struct FunctionTranslator {
 
     FunctionTranslator(Translator& t, Function* f) : T(t), m(t.m), fn(f) {}
 
+    void load_blocks(const FunctionBody& fb) {
+        for (const BasicBlock& b : fb.blocks) {
+            BasicBlock copy = b;
+            std::vector<Inst> rest;  // OpPhis belong to the block they merge into
+            for (const Inst& in : copy.body) {
+                if (in.op == OpPhi) {
+                    if (in.w.size() < 2) throw Error("SPIR-V: OpPhi is missing operands");
+                    phi_insts[b.label].push_back(in);
+                }
+                else rest.push_back(in);
+            }
+            copy.body = rest;
+            blocks[b.label] = copy;
+            order.push_back(b.label);
+        }
+    }
+
     const SValue& value(uint32_t id) {
         auto it = values.find(id);
         if (it != values.end()) return it->second;
@@ -309,7 +335,56 @@ struct FunctionTranslator {
             }
             values[w[1]] = r;
         };
+        {   // operands every form of the instruction has (a truncated instruction must not be read past its end)
+            size_t least = 0;
+            switch (in.op) {
+                case OpStore: case OpCompositeConstruct: least = 2; break;
+                case OpVariable: case OpLoad: case OpAccessChain: case OpInBoundsAccessChain: case OpFunctionCall: case OpConvertFToU:
+                case OpConvertFToS: case OpConvertSToF: case OpConvertUToF: case OpUConvert: case OpSConvert: case OpFConvert: case OpBitcast:
+                case OpSNegate: case OpFNegate: case OpNot: case OpLogicalNot:
+                    least = 3;
+                    break;
+                case OpSelect: least = 5; break;
+                case OpExtInst: least = 5; break;  // result type, result, set, instruction, at least one operand
+                default: least = 4; break;         // result type, result, two operands (OpCompositeExtract: composite and one index)
+            }
+            if (w.size() < least) throw Error("SPIR-V: opcode " + std::to_string(in.op) + " is missing operands");
+        }
         switch (in.op) {
+            case OpFunctionCall: {
+                // The IR has no call instruction (instructions_impl.rs:395-433): the callee is inlined into a block of its own —
+                //   block <callee>_call -> [the return value's scalars] { <callee's body; OpReturn(Value) = break out of the block> }
+                // parameters stand for the arguments (pointers to the caller's variables included, which is how glslang
+                // passes everything), the callee's Function variables become more locals of this IR function.
+                if (w.size() < 3) throw Error("SPIR-V: OpFunctionCall is missing operands");
+                auto f = T.spv_functions.find(w[2]);
+                if (f == T.spv_functions.end()) throw Error("SPIR-V: OpFunctionCall of an id that is not a function");
+                const FunctionBody& callee = *f->second;
+                if (std::find(T.call_stack.begin(), T.call_stack.end(), callee.id) != T.call_stack.end())
+                    Translator::unsupported("recursion (a function that calls itself cannot be inlined)");
+                if (T.call_stack.size() >= 32) Translator::unsupported("calls nested more than 32 deep");
+                if (w.size() - 3 != callee.params.size()) throw Error("SPIR-V: OpFunctionCall argument count differs from the function's parameters");
+                if (callee.return_type != w[0]) throw Error("SPIR-V: OpFunctionCall result type differs from the function's return type");
+                FunctionTranslator g(T, fn);
+                g.load_blocks(callee);
+                for (size_t k = 0; k < callee.params.size(); ++k) g.values[callee.params[k]] = value(w[3 + k]);
+                Block* cb = new_child_block(T.name_of(callee.id) + "_call", b);
+                SValue ret;
+                if (T.type(w[0]).kind != SType::Void) {
+                    std::vector<std::pair<uint64_t, const Type*>> ls;
+                    T.leaves(w[0], 0, &ls);
+                    for (size_t k = 0; k < ls.size(); ++k) {
+                        Value* r = m.new_value(comp_name(w[1], k, ls.size()), ls[k].second);
+                        cb->results.push_back(r);
+                        ret.scalars.push_back(r);
+                    }
+                }
+                T.call_stack.push_back(callee.id);
+                g.region(callee.blocks.front().label, cb, cb);
+                T.call_stack.pop_back();
+                values[w[1]] = ret;
+                break;
+            }
             case OpVariable: {  // a Function variable: a local of the IR function
                 if (w[2] != ScFunction) Translator::unsupported("OpVariable of a storage class other than Function inside a function");
                 if (w.size() > 3) Translator::unsupported("variable initialisers");
@@ -443,6 +518,7 @@ struct FunctionTranslator {
             case OpExtInst: {
                 // GLSL.std.450: the instructions that have a version 2 counterpart
                 const uint32_t inst = w[3];
+                if (w.size() < (inst == 50 ? 7u : (inst == 37 || inst == 40) ? 6u : 5u)) throw Error("SPIR-V: OpExtInst is missing operands");
                 if (inst == 50) elementwise("fma", {w[4], w[5], w[6]});       // Fma
                 else if (inst == 4) elementwise("f_abs", {w[4]});             // FAbs
                 else if (inst == 37) elementwise("f_min", {w[4], w[5]});      // FMin
@@ -590,11 +666,21 @@ struct FunctionTranslator {
                 }
                 return false;
             };
-            if (t.op == OpReturn) {
-                break_to(b, body, {}, t.loc);
+            if (t.op == OpReturn || t.op == OpReturnValue) {  // (`body`: the function's body block, or the block an inlined call stands in)
+                std::vector<Value*> vals;
+                if (t.op == OpReturnValue) {
+                    if (t.w.empty()) throw Error("SPIR-V: OpReturnValue without a value");
+                    const SValue& rv = value(t.w[0]);
+                    if (rv.is_pointer) Translator::unsupported("returning a pointer");
+                    vals = rv.scalars;
+                }
+                if (vals.size() != body->results.size()) throw Error("SPIR-V: a return does not match the function's return type");
+                break_to(b, body, vals, t.loc);
                 return;
             }
-            if (t.op == OpKill || t.op == OpUnreachable || t.op == OpReturnValue) Translator::unsupported("terminator opcode " + std::to_string(t.op));
+            if (t.op == OpKill || t.op == OpUnreachable) Translator::unsupported("terminator opcode " + std::to_string(t.op));
+            if (t.w.size() < (t.op == OpBranch ? 1u : t.op == OpBranchConditional ? 3u : t.op == OpSwitch ? 2u : 0u))
+                throw Error("SPIR-V: a branch is missing operands");
             if (t.op == OpBranch) {
                 if (jump(t.w[0], b)) return;
                 from = label;
@@ -863,10 +949,6 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
         uint32_t id, type, storage;
     };
     std::vector<GlobalVar> globals;
-    struct FunctionBody {
-        uint32_t id = 0, control = 0;
-        std::vector<BasicBlock> blocks;
-    };
     std::vector<FunctionBody> bodies;
     FunctionBody* cur = nullptr;
     BasicBlock* bb = nullptr;
@@ -906,6 +988,10 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
             i += wc;
             continue;
         }
+        if (op >= OpTypeVoid && op <= OpTypeFunction) {  // (a type defined twice could be made to contain itself)
+            need(1);
+            if (T.types.count(o[0])) throw Error("SPIR-V: type id " + std::to_string(o[0]) + " is defined twice");
+        }
         switch (op) {
             case OpNop: case OpSourceContinued: case OpSource: case OpSourceExtension: case OpMemberName: case OpExtension:
             case OpExtInstImport: case OpMemoryModel: case OpCapability: case OpModuleProcessed:
@@ -932,24 +1018,50 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
             case OpMemberDecorate: need(3); T.member_decorations[o[0]][o[1]][o[2]] = n > 3 ? o[3] : 1; break;
             case OpTypeVoid: need(1); T.types[o[0]] = SType{SType::Void}; break;
             case OpTypeBool: need(1); T.types[o[0]] = SType{SType::Bool}; break;
-            case OpTypeInt: { need(3); SType t{SType::Int}; t.bits = o[1]; t.is_signed = o[2] != 0; T.types[o[0]] = t; break; }
-            case OpTypeFloat: { need(2); SType t{SType::Float}; t.bits = o[1]; T.types[o[0]] = t; break; }
-            case OpTypeVector: { need(3); SType t{SType::Vector}; t.element = o[1]; t.count = o[2]; T.types[o[0]] = t; break; }
+            case OpTypeInt: {
+                need(3);
+                if (o[1] != 8 && o[1] != 16 && o[1] != 32 && o[1] != 64) throw Error("SPIR-V: integer width " + std::to_string(o[1]));
+                SType t{SType::Int}; t.bits = o[1]; t.is_signed = o[2] != 0; T.types[o[0]] = t; break;
+            }
+            case OpTypeFloat: {
+                need(2);
+                if (o[1] != 16 && o[1] != 32 && o[1] != 64) throw Error("SPIR-V: float width " + std::to_string(o[1]));
+                SType t{SType::Float}; t.bits = o[1]; T.types[o[0]] = t; break;
+            }
+            case OpTypeVector: {
+                need(3);
+                if (!T.types.count(o[1]) || o[1] == o[0]) throw Error("SPIR-V: a type is used before it is defined");
+                if (o[2] < 2 || o[2] > 4) throw Error("SPIR-V: vectors have 2, 3 or 4 components (Vector16 is not a Shader capability)");
+                SType t{SType::Vector}; t.element = o[1]; t.count = o[2]; T.types[o[0]] = t; break;
+            }
             case OpTypeArray: {
                 need(3);
+                if (!T.types.count(o[1]) || o[1] == o[0]) throw Error("SPIR-V: a type is used before it is defined");
                 SType t{SType::Array};
                 t.element = o[1];
                 auto c = T.values.find(o[2]);
                 if (c == T.values.end() || c->second.scalars.size() != 1) throw Error("SPIR-V: array length is not a constant");
                 t.count = (uint32_t)c->second.scalars[0]->constant.bits;
+                // every element becomes scalars of its own here (no dynamic indexing): an array is as long as a shader's interface
+                // needs, not as long as a buffer
+                if (c->second.scalars[0]->constant.bits == 0 || c->second.scalars[0]->constant.bits > 1024) Translator::unsupported("arrays of more than 1024 elements");
                 T.types[o[0]] = t;
                 break;
             }
-            case OpTypeStruct: { need(1); SType t{SType::Struct}; t.members.assign(o + 1, o + n); T.types[o[0]] = t; break; }
-            case OpTypePointer: { need(3); SType t{SType::Pointer}; t.storage = o[1]; t.element = o[2]; T.types[o[0]] = t; break; }
+            case OpTypeStruct: {
+                need(1);
+                for (size_t k = 1; k < n; ++k)
+                    if (!T.types.count(o[k]) || o[k] == o[0]) throw Error("SPIR-V: a type is used before it is defined");
+                SType t{SType::Struct}; t.members.assign(o + 1, o + n); T.types[o[0]] = t; break;
+            }
+            case OpTypePointer: {
+                need(3);
+                if (!T.types.count(o[2]) || o[2] == o[0]) throw Error("SPIR-V: a type is used before it is defined (OpTypeForwardPointer is not supported)");
+                SType t{SType::Pointer}; t.storage = o[1]; t.element = o[2]; T.types[o[0]] = t; break;
+            }
             case OpTypeFunction: {
                 need(2);
-                if (n > 2) Translator::unsupported("function parameters (parse/functions.rs:236-268 is todo!() upstream)");
+                // (parameters: parse/functions.rs:236-268 is todo!() upstream; here functions other than the entry point are inlined)
                 SType t{SType::Function};
                 t.element = o[1];
                 T.types[o[0]] = t;
@@ -1000,9 +1112,15 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
                 cur = &bodies.back();
                 cur->id = o[1];
                 cur->control = o[2];
+                cur->return_type = o[0];
                 break;
             }
-            case OpFunctionParameter: Translator::unsupported("OpFunctionParameter (todo!() upstream)");
+            case OpFunctionParameter:
+                need(2);
+                if (!cur || !cur->blocks.empty()) throw Error("SPIR-V: OpFunctionParameter outside a function's head");
+                check_id(o[1]);
+                cur->params.push_back(o[1]);
+                break;
             case OpLabel:
                 need(1);
                 if (!cur) throw Error("SPIR-V: OpLabel outside a function");
@@ -1124,19 +1242,11 @@ std::unique_ptr<Module> translate_spirv_v2(const uint32_t* words, size_t count, 
     fn->side_effects = (fb->control & 4) ? "pure" : (fb->control & 8) ? "const" : "normal";
     Type ft{TypeKind::Fn};
     fn->type = m.intern(ft);
+    if (!fb->params.empty()) throw Error("SPIR-V: an entry point takes no parameters");
+    for (const FunctionBody& b : bodies) T.spv_functions[b.id] = &b;
+    T.call_stack.push_back(fb->id);
     FunctionTranslator F(T, fn);
-    for (const BasicBlock& b : fb->blocks) {
-        BasicBlock copy = b;
-        // OpPhis belong to the block they merge into
-        std::vector<Inst> rest;
-        for (const Inst& in : copy.body) {
-            if (in.op == OpPhi) F.phi_insts[b.label].push_back(in);
-            else rest.push_back(in);
-        }
-        copy.body = rest;
-        F.blocks[b.label] = copy;
-        F.order.push_back(b.label);
-    }
+    F.load_blocks(*fb);
     Block* body = m.new_block(T.name_of(fb->blocks.front().label));
     fn->body = body;
     F.region(fb->blocks.front().label, body, body);

@@ -63,7 +63,7 @@ def main(seed, iterations):
            json.loads((ROOT / "tests/golden/spirv_goldens.json").read_text())["cases"]]
     ir = json.loads((ROOT / "tests/golden/ir_goldens.json").read_text())
     from tests import spirv_loop_shaders as loops  # hand-assembled shaders with loops: the version 2 translator's corpus
-    spv2 = spv + [getattr(loops, k)() for k in ("variables", "phis", "do_while", "nested", "header_values_after_loop")]
+    spv2 = spv + [getattr(loops, k)() for k in ("variables", "phis", "do_while", "nested", "header_values_after_loop", "calls", "recursive")]
     texts2 = [p.read_text() for p in sorted((ROOT / "tests/ir_programs_v2").glob("*.kazan-ir"))]
     texts = [p.read_text() for p in sorted((ROOT / "tests/ir_programs").glob("*.kazan-ir"))]
     texts += [v for v in json.dumps(ir).split('"') if "fn " in v or "block" in v][:20]

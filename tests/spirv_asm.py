@@ -6,7 +6,7 @@ from __future__ import annotations
 OP = dict(Capability=17, ExtInstImport=11, MemoryModel=14, EntryPoint=15, Name=5, Decorate=71, TypeVoid=19, TypeBool=20, TypeInt=21,
           TypeFloat=22, TypePointer=32, TypeFunction=33, Constant=43, Variable=59, Function=54, FunctionEnd=56, Label=248, Load=61,
           Store=62, Branch=249, BranchConditional=250, LoopMerge=246, SelectionMerge=247, Return=253, Phi=245, IAdd=128, FAdd=129,
-          FMul=133, SLessThan=177, BitwiseAnd=199, IEqual=170, ConvertSToF=111, FOrdGreaterThan=186)
+          FMul=133, SLessThan=177, BitwiseAnd=199, IEqual=170, ConvertSToF=111, FOrdGreaterThan=186, FunctionParameter=55, FunctionCall=57, ReturnValue=254)
 INPUT, OUTPUT, FUNCTION = 1, 3, 7
 LOCATION = 30
 

@@ -165,6 +165,54 @@ def nested():
     return assemble(pro + body, 200)
 
 
+def calls():
+    """Functions, the way glslang emits them (arguments passed as pointers to Function variables) and the way an optimiser leaves
+    them (by value):
+        float halve_add(float a, float b) { return a * 0.5 + b; }               // by value
+        void  step(inout float acc, float x, inout int i) { acc = halve_add(acc, x); i = i + 1; }   // pointer parameters, a nested call
+        main: acc = 0; i = 0; while (i < n) step(acc, x, i); out = acc, i      // a call inside a loop: inlined once per call site
+    """
+    i = _Ids()
+    pro = _prologue(i)
+    pro = pro[:-1] + [("TypeFunction", i("fn_ff_f"), i("float"), i("float"), i("float")),
+                      ("TypeFunction", i("fn_step"), i("void"), i("p_fn_f"), i("float"), i("p_fn_i")), pro[-1]]
+    main = [("Label", i("entry")),
+            ("Variable", i("p_fn_f"), i("acc"), FUNCTION), ("Variable", i("p_fn_i"), i("i"), FUNCTION),
+            ("Store", i("acc"), i("f0")), ("Store", i("i"), i("i0")),
+            ("Load", i("int"), i("n"), i("nin")), ("Load", i("float"), i("x"), i("xin")), ("Branch", i("H")),
+            ("Label", i("H")), ("LoopMerge", i("M"), i("C"), 0), ("Branch", i("T")),
+            ("Label", i("T")), ("Load", i("int"), i("iv"), i("i")), ("SLessThan", i("bool"), i("c"), i("iv"), i("n")),
+            ("BranchConditional", i("c"), i("B"), i("M")),
+            ("Label", i("B")), ("FunctionCall", i("void"), i("call1"), i("step"), i("acc"), i("x"), i("i")), ("Branch", i("C")),
+            ("Label", i("C")), ("Branch", i("H")),
+            ("Label", i("M")), ("Load", i("float"), i("af"), i("acc")), ("Store", i("acc_out"), i("af")),
+            ("Load", i("int"), i("if"), i("i")), ("Store", i("i_out"), i("if")),
+            ("Return",), ("FunctionEnd",)]
+    halve_add = [("Function", i("float"), i("halve_add"), 0, i("fn_ff_f")),
+                 ("FunctionParameter", i("float"), i("pa")), ("FunctionParameter", i("float"), i("pb")),
+                 ("Label", i("ha_entry")), ("FMul", i("float"), i("h1"), i("pa"), i("f05")), ("FAdd", i("float"), i("h2"), i("h1"), i("pb")),
+                 ("ReturnValue", i("h2")), ("FunctionEnd",)]
+    step = [("Function", i("void"), i("step"), 0, i("fn_step")),
+            ("FunctionParameter", i("p_fn_f"), i("s_acc")), ("FunctionParameter", i("float"), i("s_x")), ("FunctionParameter", i("p_fn_i"), i("s_i")),
+            ("Label", i("s_entry")), ("Load", i("float"), i("s_a"), i("s_acc")),
+            ("FunctionCall", i("float"), i("s_r"), i("halve_add"), i("s_a"), i("s_x")), ("Store", i("s_acc"), i("s_r")),
+            ("Load", i("int"), i("s_iv"), i("s_i")), ("IAdd", i("int"), i("s_inc"), i("s_iv"), i("i1")), ("Store", i("s_i"), i("s_inc")),
+            ("Return",), ("FunctionEnd",)]
+    return assemble(pro + main + halve_add + step, 200)
+
+
+def recursive():
+    """a function that calls itself: refused (the IR has no call instruction and recursion cannot be inlined)"""
+    i = _Ids()
+    pro = _prologue(i)
+    pro = pro[:-1] + [("TypeFunction", i("fn_f_f"), i("float"), i("float")), pro[-1]]
+    main = [("Label", i("entry")), ("Load", i("float"), i("x"), i("xin")), ("FunctionCall", i("float"), i("r"), i("rec"), i("x")),
+            ("Store", i("acc_out"), i("r")), ("Return",), ("FunctionEnd",)]
+    rec = [("Function", i("float"), i("rec"), 0, i("fn_f_f")), ("FunctionParameter", i("float"), i("p")), ("Label", i("r_entry")),
+           ("FunctionCall", i("float"), i("r2"), i("rec"), i("p")), ("ReturnValue", i("r2")), ("FunctionEnd",)]
+    return assemble(pro + main + rec, 200)
+
+
 SLOT = np.dtype([("x", "<f4"), ("pad0", "V12"), ("n", "<i4"), ("pad1", "V12")])       # one Location per 16 bytes
 OUT = np.dtype([("acc", "<f4"), ("pad0", "V12"), ("i", "<i4"), ("pad1", "V12")])
 
@@ -190,7 +238,7 @@ def expected(kind, a):
                     if acc > f(100.0):
                         break
                 i += 1
-        elif kind in ("phis", "header_values_after_loop"):
+        elif kind in ("phis", "header_values_after_loop", "calls"):
             while i < n:
                 acc = f(f(acc * f(0.5)) + x)
                 i += 1

@@ -17,7 +17,7 @@ from tests.test_gpu_raster import GOLDEN, SCENES, sha
 
 pytestmark = pytest.mark.gpu
 # the loop shaders that have run on a B200 (tests/test_spirv_loops.py runs all five through the interpreter and ptxas on the CPU)
-LOOP_KINDS_ON_GPU = ["variables", "phis", "do_while", "nested", "header_values_after_loop"]
+LOOP_KINDS_ON_GPU = ["variables", "phis", "do_while", "nested", "header_values_after_loop", "calls"]
 
 
 def _dispatch(gpu, name, inputs, group_count, local_size=(1, 1, 1)):

@@ -20,12 +20,14 @@ def _translate(kind):
     return module
 
 
-@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop"])
+@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop", "calls"])
 def test_loop_shader_translates_round_trips_and_assembles(kind, tmp_path):
     from oracle import ir_oracle as iro
     module = _translate(kind)
     text = module.to_text()
     assert "loop id_" in text and "continue id_" in text
+    if kind == "calls":  # both functions inlined at their call sites: blocks named after the callee, no second function in the module
+        assert text.count("_call -> [") == 2 and text.count("fn id_") == 1
     if kind == "phis":  # header OpPhis are the loop's parameters, the merge block's OpPhis its results
         assert "[c0: 0x0i32, c2: f32 0x0] -> [" in text.replace("\n", " ") or "loop" in text
         header = next(line for line in text.splitlines() if line.strip().startswith("loop "))
@@ -44,7 +46,7 @@ def test_loop_shader_translates_round_trips_and_assembles(kind, tmp_path):
         assert r.returncode == 0, r.stderr
 
 
-@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop"])
+@pytest.mark.parametrize("kind", ["variables", "phis", "do_while", "nested", "header_values_after_loop", "calls"])
 def test_loop_shader_runs_in_the_interpreter(kind):
     from oracle import ir_oracle as iro
     from oracle import ir_simt as sim
@@ -63,3 +65,10 @@ def test_version_1_still_refuses_loops():
     from kazan_b200 import host
     with pytest.raises(host.KazanError):
         backend.translate_spirv_to_ir(shaders.variables(), "main", backend.EXECUTION_MODEL_VERTEX)
+
+
+def test_recursion_is_refused():
+    from kazan_b200 import host
+    with pytest.raises(host.KazanError) as e:
+        backend.translate_spirv_to_ir(shaders.recursive(), "main", backend.EXECUTION_MODEL_VERTEX, 2)
+    assert e.value.code == -8 and "recursion" in str(e.value)

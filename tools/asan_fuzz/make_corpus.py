@@ -12,7 +12,7 @@ import tests.ir_random as irr
 texts+=[irr.make_program(s)[0] for s in range(10)]
 pairs=[(v["kind"],v["text"]) for v in ir["text_round_trips"]]
 from tests import spirv_loop_shaders as loops
-spv2=spv+[getattr(loops,k)() for k in ("variables","phis","do_while","nested","header_values_after_loop")]
+spv2=spv+[getattr(loops,k)() for k in ("variables","phis","do_while","nested","header_values_after_loop","calls","recursive")]
 texts2=[p.read_text() for p in sorted((ROOT/"tests/ir_programs_v2").glob("*.kazan-ir"))]
 out=open(sys.argv[3],'wb')
 def rec(kind,payload):
