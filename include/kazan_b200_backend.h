@@ -70,7 +70,9 @@ KZN_API KznResult kzn_translate_spirv_to_ir(const uint32_t* words, size_t word_c
                                             uint32_t execution_model, KznIrModule** module, uint32_t local_size[3]);
 /* version KZN_IR_VERSION_2: shaders with a body — what the reference leaves todo!() (OpLoad / OpStore / OpAccessChain,
  * composites, conversions, arithmetic, compares, OpSelect, selection constructs with OpSwitch / OpBranchConditional, OpPhi at
- * their merge blocks) translated into the version 2 instructions of the IR (csrc/spirv_to_ir_v2.cpp), values scalarised.
+ * their merge blocks, structured loops (OpLoopMerge -> the IR's `loop`), function calls (inlined: the IR has no call;
+ * recursion returns VK_ERROR_FEATURE_NOT_PRESENT)) translated into the version 2 instructions of the IR
+ * (csrc/spirv_to_ir_v2.cpp), values scalarised.  Vectors have 2 .. 4 components, arrays at most 1024 elements.
  * Input / Output variables are laid out by Location (16 bytes each, io_layout.rs:5-13) in the two interface blocks, a
  * `BuiltIn Position` output is the `vertex_position` built-in variable.  The reference's own second test shader
  * (test_data/simple_test.spv, src/lib.rs:260-287: #[ignore], golden "not yet entered") translates. */
