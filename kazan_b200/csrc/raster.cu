@@ -414,8 +414,10 @@ __device__ __forceinline__ bool make_compact_t(const DrawParams& p, uint32_t t, 
 __device__ __forceinline__ bool is_point_or_line(const DrawParams& p) {
     return p.st.topology == KZN_TOPOLOGY_POINT_LIST || p.st.topology == KZN_TOPOLOGY_LINE_LIST || p.st.topology == KZN_TOPOLOGY_LINE_STRIP;
 }
-__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow) {
-    if (is_point_or_line(p)) {  // R9: every point / line becomes two triangles, made where clipped polygons are made
+// pl == false (a compile-time constant at the call): the caller only ever sees triangles — the fused setup of raster_direct_kernel —
+// and carries none of the point / line code (that kernel's speed depends on its size: DESIGN.md "raster_direct_kernel")
+__device__ __forceinline__ bool make_compact(const DrawParams& p, uint32_t t, TriRecC& r, int4& box, bool& slow, const bool pl = true) {
+    if (pl && is_point_or_line(p)) {  // R9: every point / line becomes two triangles, made where clipped polygons are made
         box = make_int4(1, 0, 1, 0);
         slow = true;
         return false;
@@ -514,8 +516,8 @@ __device__ __forceinline__ int expand_point_or_line(const DrawParams& p, uint32_
     return 4;
 }
 
-__device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, float (*poly)[8]) {
-    if (is_point_or_line(p)) return expand_point_or_line(p, t, poly);
+__device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, float (*poly)[8], const bool pl = true) {
+    if (pl && is_point_or_line(p)) return expand_point_or_line(p, t, poly);
     float other[8][8];
     float(*src)[8] = other;
     float(*dst)[8] = poly;  // five planes: other -> poly -> other -> poly -> other -> poly
@@ -563,9 +565,10 @@ __device__ __forceinline__ int clip_primitive(const DrawParams& p, uint32_t t, f
 
 // One triangle of a clipped polygon -> its compact record and scissored pixel box, by the rules of make_compact_t (R1, R2,
 // R4; oracle/raster.c setup_triangle); false: it produces no fragments.
-__device__ __forceinline__ bool make_compact_from(const DrawParams& p, const float* v0, const float* v1, const float* v2, TriRecC& r, int4& box) {
+__device__ __forceinline__ bool make_compact_from(const DrawParams& p, const float* v0, const float* v1, const float* v2, TriRecC& r, int4& box,
+                                                  const bool pl = true) {
     box = make_int4(1, 0, 1, 0);
-    if (is_point_or_line(p)) {  // R9: corners in window form {X, Y, z, 1/w, colour}; no face culling
+    if (pl && is_point_or_line(p)) {  // R9: corners in window form {X, Y, z, 1/w, colour}; no face culling
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float* v = k == 0 ? v0 : k == 1 ? v1 : v2;
@@ -618,9 +621,9 @@ __device__ __forceinline__ int4 unpack_box(const uint2 b) {  // minx maxx miny m
     return make_int4((int)(b.x & 0xffffu), (int)(b.x >> 16), (int)(b.y & 0xffffu), (int)(b.y >> 16));
 }
 
-__device__ __forceinline__ void clip_statistics(const DrawParams& p, int m, unsigned long long n_inst) {
+__device__ __forceinline__ void clip_statistics(const DrawParams& p, int m, unsigned long long n_inst, const bool pl = true) {
     if (!p.stats) return;
-    if (is_point_or_line(p) && m >= 0) return;  // (their two triangles are the primitive itself, not the clipper's work)
+    if (pl && is_point_or_line(p) && m >= 0) return;  // (their two triangles are the primitive itself, not the clipper's work)
     if (m < 0) {
         atomicAdd(&p.stats[10], n_inst);
     } else {
@@ -673,19 +676,19 @@ __device__ __forceinline__ void empty_record(TriRec& r) {
     r.minx = 1;
     r.miny = 1;
 }
-__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r, bool& slow) {
+__device__ __forceinline__ bool make_record(const DrawParams& p, uint32_t t, TriRec& r, bool& slow, const bool pl = true) {
     TriRecC c;
     int4 box;
-    const bool ok = make_compact(p, t, c, box, slow);
+    const bool ok = make_compact(p, t, c, box, slow, pl);
     if (ok) expand_record(p, c, box, r);
     else empty_record(r);
     return ok;
 }
 // triangle j of a clipped polygon -> expanded record (direct draws)
-__device__ __forceinline__ bool make_record_from(const DrawParams& p, const float (*poly)[8], int j, TriRec& r) {
+__device__ __forceinline__ bool make_record_from(const DrawParams& p, const float (*poly)[8], int j, TriRec& r, const bool pl = true) {
     TriRecC c;
     int4 box;
-    const bool ok = make_compact_from(p, poly[0], poly[j + 1], poly[j + 2], c, box);
+    const bool ok = make_compact_from(p, poly[0], poly[j + 1], poly[j + 2], c, box, pl);
     if (ok) expand_record(p, c, box, r);
     else empty_record(r);
     return ok;
@@ -1747,15 +1750,15 @@ __device__ __noinline__ uint32_t fused_clip_records(const DrawParams& p, uint32_
     TriRec r;
     bool ok = false, slow = false;
     const bool mine = lane < p.total_tris;
-    if (mine) ok = make_record(p, lane % p.tris_per_instance, r, slow);
+    if (mine) ok = make_record(p, lane % p.tris_per_instance, r, slow, false);  // (fused draws are triangles: draw_common)
     uint32_t n_recs = p.total_tris;
     __syncwarp();
     {  // records placed by a prefix sum over the polygon sizes
         float poly[8][8];
         int m = 0;
         if (slow) {
-            m = clip_primitive(p, lane % p.tris_per_instance, poly);
-            if (blockIdx.x == 0) clip_statistics(p, m, 1ull);
+            m = clip_primitive(p, lane % p.tris_per_instance, poly, false);
+            if (blockIdx.x == 0) clip_statistics(p, m, 1ull, false);
         }
         const uint32_t cnt = !mine ? 0u : (slow && m > 3) ? (uint32_t)m - 2u : 1u;
         uint32_t incl = cnt;
@@ -1768,7 +1771,7 @@ __device__ __noinline__ uint32_t fused_clip_records(const DrawParams& p, uint32_
         const uint32_t at = incl - cnt;
         for (uint32_t j = 0; j < cnt; ++j) {
             if (slow) {
-                if (m >= 3) ok = make_record_from(p, poly, (int)j, r) || ok;
+                if (m >= 3) ok = make_record_from(p, poly, (int)j, r, false) || ok;
                 else empty_record(r);
             }
             recs[at + j] = r;
@@ -1804,7 +1807,7 @@ __device__ __forceinline__ void raster_direct_body(const DrawParams& p) {
         bool ok = false, slow = false;
         if (lane < p.total_tris) {
             TriRec r;
-            ok = make_record(p, lane % p.tris_per_instance, r, slow);
+            ok = make_record(p, lane % p.tris_per_instance, r, slow, false);
             own_recs[lane] = r;
         }
         if (__builtin_expect(__any_sync(0xffffffffu, slow), 0)) {
@@ -3047,7 +3050,8 @@ KznResult draw_common(KznQueue* q, const KznGraphicsPipelineState* st, const Kzn
         }
     }
     if (p.binned) KZN_CUDA(cudaMemsetAsync(p.tile_counts, 0, (2 * tiles + (ntri + 31) / 32) * sizeof(uint32_t), q->stream));
-    p.fused_setup = !p.binned && total <= kFusedMax;
+    // (points and lines are never fused: raster_direct_kernel's own setup is compiled for triangles only)
+    p.fused_setup = !p.binned && total <= kFusedMax && topo >= KZN_TOPOLOGY_TRIANGLE_LIST && topo <= KZN_TOPOLOGY_TRIANGLE_FAN;
     uint32_t list_grid = 0;
     {
         static const long min_tris = [] { const char* e = getenv("KZN_BAND_PREFILTER_MIN"); return e ? atol(e) : 65536l; }();  // (negative: never)
